@@ -1,0 +1,88 @@
+// Library-wide plumbing of the C ABI: thread-local error slot, CUDA error mapping, TMA tensor-map
+// encoding via the runtime's driver entry point (no link-time libcuda dependency, so the shared
+// object also loads on a machine without a GPU driver — the symbol-export test relies on that).
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+#include "ctcb200.h"
+
+namespace ctcb200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
+    return ERR_CUDA;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+        return ERR_DRIVER;
+    }
+    if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0 || (row_stride_elems * 2) % 16 != 0) {
+        set_error("tensor map: base %p / row pitch %llu B must be 16-byte aligned", gptr,
+                  (unsigned long long)(row_stride_elems * 2));
+        return ERR_INVALID;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = (box_cols * 2 == 128)  ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (box_cols * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : (box_cols * 2 == 32) ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                   : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu pitch=%llu box=%ux%u", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows,
+                  box_cols);
+        return ERR_DRIVER;
+    }
+    return OK;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms) return sms;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    sms = v;
+    return sms;
+}
+
+}  // namespace ctcb200
+
+extern "C" CTCB200_API const char* ctcb200_last_error(void) { return ctcb200::g_err; }
+
+extern "C" CTCB200_API int ctcb200_version(void) { return 100; }

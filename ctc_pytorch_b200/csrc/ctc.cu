@@ -1,0 +1,325 @@
+// K7 — CTC loss forward (log-alpha) and backward (log-beta + gradient), warp per utterance.
+//
+// Replaces the library call the reference makes at timit/steps/train_ctc.py:144,47,63
+// (nn.CTCLoss(reduction='sum') forward + autograd backward). Semantics follow that call exactly:
+// blank index configurable (reference uses 0), targets are a zero-padded 2-D int64 matrix
+// (timit/utils/data_loader.py:125,140), frames t >= input_length get zero gradient, an infeasible
+// alignment gives +inf loss (zero_infinity=False), and the gradient is emitted in the convention
+// of torch's native kernel: d/dlog_probs = exp(lp) - exp(log-sum_{s:l'_s=c}(alpha+beta) + nll - lp).
+//
+// Mapping: one warp owns one utterance; the 2S+1 lattice states are blocked over the 32 lanes
+// (KS consecutive states per lane) so the s-1 / s-2 neighbours are lane-local except at block
+// edges, where one or two warp shuffles fetch them. Each (t, n) row of log-probs is brought in once
+// with coalesced cp.async into a per-warp double buffer, one step ahead of its use.
+#include "common.cuh"
+#include "ctcb200.h"
+
+namespace ctcb200 {
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 4;
+#define NEG_INF (-INFINITY)
+
+__device__ __forceinline__ float lse2(float a, float b) {
+    float m = fmaxf(a, b);
+    if (m == NEG_INF) return NEG_INF;
+    return m + __logf(__expf(a - m) + __expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+    float m = fmaxf(a, fmaxf(b, c));
+    if (m == NEG_INF) return NEG_INF;
+    return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_row(float* dst, const float* src, int C, int lane) {
+    for (int c = lane; c < C; c += 32) cp_async_4(dst + c, src + c);
+    cp_async_commit();
+}
+
+// Per-lane static description of the states this lane owns.
+template <int KS>
+struct LaneStates {
+    int label[KS];     // l'_s
+    bool valid[KS];    // s < L
+    bool skip_in[KS];  // transition s-2 -> s allowed
+    bool skip_out[KS]; // transition s -> s+2 allowed
+};
+
+template <int KS>
+__device__ __forceinline__ void load_states(LaneStates<KS>& st, const int64_t* tgt, int S, int blank, int lane) {
+    const int L = 2 * S + 1;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        int s = lane * KS + j;
+        bool v = s < L;
+        int lab = blank, lab_m2 = blank, lab_p2 = blank;
+        if (v && (s & 1)) lab = static_cast<int>(tgt[(s - 1) >> 1]);
+        if (v && (s & 1) && s >= 3) lab_m2 = static_cast<int>(tgt[(s - 3) >> 1]);
+        if (v && (s & 1) && s + 2 < L) lab_p2 = static_cast<int>(tgt[(s + 1) >> 1]);
+        st.label[j] = lab;
+        st.valid[j] = v;
+        st.skip_in[j] = v && (s & 1) && s >= 3 && lab != lab_m2;
+        st.skip_out[j] = v && (s & 1) && (s + 2 < L) && lab != lab_p2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: log-alpha sweep; writes alpha history [N][T][KS*32] (slot j*32+lane) and nll[N]
+// ---------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+ctc_alpha_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
+                 const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
+                 float* __restrict__ alpha_ws, float* __restrict__ nll, int T, int N, int C, int blank) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (n >= N) return;
+    float* rowbuf = smem + warp * 2 * C;  // two rows
+
+    const int S = static_cast<int>(tgt_len[n]);
+    const int L = 2 * S + 1;
+    int Tn = static_cast<int>(in_len[n]);
+    if (Tn > T) Tn = T;
+    if (Tn <= 0) {
+        if (lane == 0) nll[n] = (S == 0) ? 0.0f : INFINITY;
+        return;
+    }
+    LaneStates<KS> st;
+    load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
+
+    const size_t row_stride = static_cast<size_t>(N) * C;
+    const float* lp_n = lp + static_cast<size_t>(n) * C;
+    float* aws = alpha_ws + static_cast<size_t>(n) * T * (KS * 32);
+
+    prefetch_row(rowbuf, lp_n, C, lane);
+    float a[KS];
+    for (int t = 0; t < Tn; ++t) {
+        float* cur = rowbuf + (t & 1) * C;
+        cp_async_wait_all();
+        __syncwarp();
+        if (t + 1 < Tn) prefetch_row(rowbuf + ((t + 1) & 1) * C, lp_n + (t + 1) * row_stride, C, lane);
+        if (t == 0) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                int s = lane * KS + j;
+                a[j] = (st.valid[j] && s < 2) ? cur[st.label[j]] : NEG_INF;
+            }
+        } else {
+            // neighbours from the previous lane
+            float up1 = __shfl_up_sync(0xffffffffu, a[KS - 1], 1);
+            float up2 = (KS >= 2) ? __shfl_up_sync(0xffffffffu, a[KS >= 2 ? KS - 2 : 0], 1)
+                                  : __shfl_up_sync(0xffffffffu, a[0], 2);
+            if (lane == 0) { up1 = NEG_INF; up2 = NEG_INF; }
+            if (KS == 1 && lane == 1) up2 = NEG_INF;
+            float nw[KS];
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                float p1 = (j >= 1) ? a[j >= 1 ? j - 1 : 0] : up1;
+                float p2 = (j >= 2) ? a[j >= 2 ? j - 2 : 0] : ((j == 1) ? up1 : up2);
+                if (KS >= 2 && j == 0) p2 = up2;
+                if (!st.skip_in[j]) p2 = NEG_INF;
+                float v = lse3(a[j], p1, p2);
+                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+            }
+#pragma unroll
+            for (int j = 0; j < KS; ++j) a[j] = nw[j];
+        }
+#pragma unroll
+        for (int j = 0; j < KS; ++j) aws[static_cast<size_t>(t) * (KS * 32) + j * 32 + lane] = a[j];
+    }
+    // nll = -lse(alpha_{Tn-1}(L-1), alpha_{Tn-1}(L-2))
+    float loc = NEG_INF;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        int s = lane * KS + j;
+        if (s == L - 1 || s == L - 2) loc = lse2(loc, a[j]);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) loc = lse2(loc, __shfl_xor_sync(0xffffffffu, loc, o));
+    if (lane == 0) nll[n] = -loc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: log-beta sweep fused with the gradient row of every frame
+// ---------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
+                     const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
+                     const float* __restrict__ alpha_ws, const float* __restrict__ nll,
+                     const float* __restrict__ grad_nll, float grad_scale, float* __restrict__ grad, int T, int N,
+                     int C, int blank) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (n >= N) return;
+    float* rowbuf = smem + warp * 3 * C;  // two rows + occupancy accumulator
+    float* occ = rowbuf + 2 * C;
+
+    const int S = static_cast<int>(tgt_len[n]);
+    const int L = 2 * S + 1;
+    int Tn = static_cast<int>(in_len[n]);
+    if (Tn > T) Tn = T;
+    if (Tn < 0) Tn = 0;
+    const size_t row_stride = static_cast<size_t>(N) * C;
+    float* g_n = grad + static_cast<size_t>(n) * C;
+    // frames past the utterance end: zero gradient (torch semantics)
+    for (int t = Tn; t < T; ++t)
+        for (int c = lane; c < C; c += 32) g_n[t * row_stride + c] = 0.0f;
+    if (Tn == 0) return;
+
+    LaneStates<KS> st;
+    load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
+    const float* lp_n = lp + static_cast<size_t>(n) * C;
+    const float* aws = alpha_ws + static_cast<size_t>(n) * T * (KS * 32);
+    const float nll_n = nll[n];
+    const float gscale = grad_scale * (grad_nll ? grad_nll[n] : 1.0f);
+
+    for (int c = lane; c < C; c += 32) occ[c] = 0.0f;
+    prefetch_row(rowbuf + ((Tn - 1) & 1) * C, lp_n + (Tn - 1) * row_stride, C, lane);
+
+    float b[KS];
+    for (int t = Tn - 1; t >= 0; --t) {
+        float* cur = rowbuf + (t & 1) * C;
+        // alpha_t for this lane's states: issued early, consumed after the recursion
+        float al[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) al[j] = __ldg(aws + static_cast<size_t>(t) * (KS * 32) + j * 32 + lane);
+        cp_async_wait_all();
+        __syncwarp();
+        if (t > 0) prefetch_row(rowbuf + ((t - 1) & 1) * C, lp_n + (t - 1) * row_stride, C, lane);
+
+        if (t == Tn - 1) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                int s = lane * KS + j;
+                b[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
+            }
+        } else {
+            float dn1 = __shfl_down_sync(0xffffffffu, b[0], 1);
+            float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, b[KS >= 2 ? 1 : 0], 1)
+                                  : __shfl_down_sync(0xffffffffu, b[0], 2);
+            if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
+            if (KS == 1 && lane == 30) dn2 = NEG_INF;
+            float nw[KS];
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                float n1 = (j + 1 < KS) ? b[j + 1 < KS ? j + 1 : 0] : dn1;
+                float n2 = (j + 2 < KS) ? b[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
+                if (KS >= 2 && j == KS - 1) n2 = dn2;
+                if (!st.skip_out[j]) n2 = NEG_INF;
+                float v = lse3(b[j], n1, n2);
+                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+            }
+#pragma unroll
+            for (int j = 0; j < KS; ++j) b[j] = nw[j];
+        }
+        // state posteriors, accumulated per class in the linear domain
+        float blank_sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            if (st.valid[j]) {
+                float lpv = cur[st.label[j]];
+                float g = __expf(al[j] + b[j] + nll_n - lpv);
+                int s = lane * KS + j;
+                if (s & 1) atomicAdd(&occ[st.label[j]], g);
+                else blank_sum += g;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) blank_sum += __shfl_xor_sync(0xffffffffu, blank_sum, o);
+        if (lane == 0) atomicAdd(&occ[blank], blank_sum);
+        __syncwarp();
+        float* g_row = g_n + t * row_stride;
+        for (int c = lane; c < C; c += 32) {
+            float r = __expf(cur[c]) - occ[c];
+            g_row[c] = r * gscale;
+            occ[c] = 0.0f;
+        }
+        __syncwarp();
+    }
+}
+
+int ks_for(int max_target_len) {
+    int L = 2 * max_target_len + 1;
+    int k = (L + 31) / 32;
+    int ks = 1;
+    while (ks < k) ks <<= 1;
+    return ks;
+}
+
+}  // namespace
+
+}  // namespace ctcb200
+
+using namespace ctcb200;
+
+extern "C" CTCB200_API int64_t ctcb200_ctc_workspace_floats(int T, int N, int max_target_len) {
+    int ks = ks_for(max_target_len);
+    return static_cast<int64_t>(N) * T * ks * 32;
+}
+
+extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const int64_t* targets, int64_t target_stride,
+                                    const int64_t* input_lengths, const int64_t* target_lengths, int T, int N,
+                                    int C, int max_target_len, int blank, float* alpha_ws, float* nll,
+                                    ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(T > 0 && N > 0 && C > 0, "ctc_loss_fwd: empty shape T=%d N=%d C=%d", T, N, C);
+    CTCB_REQUIRE(blank >= 0 && blank < C, "ctc_loss_fwd: blank %d out of range [0,%d)", blank, C);
+    int ks = ks_for(max_target_len);
+    CTCB_REQUIRE(ks <= 16, "ctc_loss_fwd: target length %d exceeds the supported maximum 255", max_target_len);
+    dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+    size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * 2 * C * sizeof(float);
+    CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_fwd: class count %d too large for the row buffer", C);
+#define LAUNCH_A(KS)                                                                                          \
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_alpha_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
+                                                        target_lengths, alpha_ws, nll, T, N, C, blank)
+    switch (ks) {
+        case 1: LAUNCH_A(1); break;
+        case 2: LAUNCH_A(2); break;
+        case 4: LAUNCH_A(4); break;
+        case 8: LAUNCH_A(8); break;
+        default: LAUNCH_A(16); break;
+    }
+#undef LAUNCH_A
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_ctc_loss_bwd(const float* log_probs, const int64_t* targets, int64_t target_stride,
+                                    const int64_t* input_lengths, const int64_t* target_lengths, int T, int N,
+                                    int C, int max_target_len, int blank, const float* alpha_ws, const float* nll,
+                                    const float* grad_nll, float grad_scale, float* grad, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(T > 0 && N > 0 && C > 0, "ctc_loss_bwd: empty shape T=%d N=%d C=%d", T, N, C);
+    CTCB_REQUIRE(blank >= 0 && blank < C, "ctc_loss_bwd: blank %d out of range [0,%d)", blank, C);
+    int ks = ks_for(max_target_len);
+    CTCB_REQUIRE(ks <= 16, "ctc_loss_bwd: target length %d exceeds the supported maximum 255", max_target_len);
+    dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+    size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * 3 * C * sizeof(float);
+    CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_bwd: class count %d too large for the row buffer", C);
+#define LAUNCH_B(KS)                                                                                               \
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_beta_grad_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
+                                                            target_lengths, alpha_ws, nll, grad_nll, grad_scale,  \
+                                                            grad, T, N, C, blank)
+    switch (ks) {
+        case 1: LAUNCH_B(1); break;
+        case 2: LAUNCH_B(2); break;
+        case 4: LAUNCH_B(4); break;
+        case 8: LAUNCH_B(8); break;
+        default: LAUNCH_B(16); break;
+    }
+#undef LAUNCH_B
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}

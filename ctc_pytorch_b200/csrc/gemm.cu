@@ -1,0 +1,260 @@
+// K1 — dense "TN" GEMM on the 5th-generation tensor cores:  C[M,N] (+)= A[M,K] * B[N,K]^T
+// with A and B bf16, K contiguous (K-major), fp32 accumulation in TMEM, fp32 or bf16 output.
+//
+// This one kernel carries every dense contraction of the acoustic model that is not inside the
+// time recurrence (the reference reaches them through nn.LSTM / nn.Linear library calls,
+// timit/models/model_ctc.py:23-26,33,136-139,165-166):
+//   gate pre-activations   Gx[T*N, 8H]  = X[T*N, I]       * Wih_packed[8H, I]^T
+//   input gradient         dX[T*N, I]   = dG[T*N, 8H]     * WihT_packed[I, 8H]^T
+//   weight gradients       dWih[8H, I]  = dG^T[8H, T*N]   * X^T[I, T*N]^T        (K = T*N)
+//                          dWhh[4H, H]  = dG^T[4H, T*N]   * Hprev^T[H, T*N]^T    (K = T*N, shifted)
+//   output layer           logits, dXfc, dWfc likewise.
+//
+// Structure (one CTA per SM, persistent over 128 x BN output tiles):
+//   warp 0    TMA producer: cp.async.bulk.tensor 2-D boxes (128 x 64 of A, BN x 64 of B) into a
+//             STAGES-deep SWIZZLE_128B shared-memory ring, completion on mbarriers.
+//   warp 1    one elected thread issues tcgen05.mma (M=128, N=BN, K=16) from shared-memory
+//             descriptors into one of two TMEM accumulator buffers; tcgen05.commit releases ring
+//             slots back to the producer and hands finished accumulators to the epilogue.
+//   warp 2    TMEM allocation / deallocation (2*BN columns).
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, convert, store to global; the
+//             second accumulator buffer lets the next tile's MMAs run under the stores.
+#include "common.cuh"
+#include "ctcb200.h"
+
+namespace ctcb200 {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // ring + barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cout,
+               long long ldc, int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+    const int tiles = m_tiles * n_tiles;
+    const int kblocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, &full[stage], a_koff + kb * BK, m_blk * BM);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], b_koff + kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        int it = 0;
+        float* Cf = reinterpret_cast<float*>(Cout);
+        __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(Cout);
+        const bool vec_f32 = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
+        const bool vec_b16 = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BM + ew * 32 + lane;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c0, r);
+                tmem_ld_wait();
+                const int col0 = n_blk * BN + c0;
+                if (row < M && col0 < N) {
+                    const bool fullchunk = col0 + 32 <= N;
+                    if (!out_bf16) {
+                        float* dst = Cf + static_cast<long long>(row) * ldc + col0;
+                        if (fullchunk && vec_f32) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                                float4* p = reinterpret_cast<float4*>(dst) + q;
+                                if (accumulate) {
+                                    float4 o = *p;
+                                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                                }
+                                *p = v;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {
+                                if (col0 + q < N) {
+                                    float v = __uint_as_float(r[q]);
+                                    if (accumulate) v += dst[q];
+                                    dst[q] = v;
+                                }
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* dst = Cb + static_cast<long long>(row) * ldc + col0;
+                        if (fullchunk && vec_b16) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[8 * q + 2 * e]),
+                                                                             __uint_as_float(r[8 * q + 2 * e + 1]));
+                                    w[e] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                                reinterpret_cast<uint4*>(dst)[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (col0 + q < N) dst[q] = __float2bfloat16(__uint_as_float(r[q]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, long long ldc, int M, int N, int K,
+                int a_koff, int b_koff, int out_bf16, int accumulate, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CTCB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+    gemm_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16,
+                                                              accumulate);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+}  // namespace
+
+// Internal entry used by the other translation units as well as the C ABI below.
+int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
+                 int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, cudaStream_t stream) {
+    CTCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    int bn = force_bn;
+    if (bn == 0) {
+        // widest tile that still yields at least one full wave, else favour more tiles
+        const int sms = device_sm_count();
+        const long long t256 = static_cast<long long>((M + BM - 1) / BM) * ((N + 255) / 256);
+        const long long t128 = static_cast<long long>((M + BM - 1) / BM) * ((N + 127) / 128);
+        if (N > 128 && t256 >= sms) bn = 256;
+        else if (N > 64 && t128 >= sms / 2) bn = 128;
+        else if (N > 64) bn = 128;
+        else bn = 64;
+    }
+    CTCB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: tile width %d not in {64,128,256}", bn);
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_bf16_2d(&tmA, A, M, static_cast<uint64_t>(a_koff) + K, lda, BM, BK);
+    if (rc != OK) return rc;
+    rc = make_tmap_bf16_2d(&tmB, B, N, static_cast<uint64_t>(b_koff) + K, ldb, bn, BK);
+    if (rc != OK) return rc;
+    switch (bn) {
+        case 64: return launch_gemm<64>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, stream);
+        case 128: return launch_gemm<128>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, stream);
+        default: return launch_gemm<256>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, stream);
+    }
+}
+
+}  // namespace ctcb200
+
+extern "C" CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                                    int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
+                                    int tile_n, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    return ctcb200::gemm_tn_bf16(A, lda, B, ldb, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, tile_n,
+                                 stream);
+}

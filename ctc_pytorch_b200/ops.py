@@ -1,0 +1,54 @@
+"""Thin tensor-in / tensor-out wrappers over the C ABI (no arithmetic happens here)."""
+import torch
+
+from . import _lib
+
+
+def gemm_tn(a, b, out=None, out_dtype=torch.float32, accumulate=False, a_koff=0, b_koff=0, k=None, tile_n=0):
+    """C[M,N] (+)= A[M, a_koff:a_koff+K] @ B[N, b_koff:b_koff+K]^T on the tcgen05 tensor cores.
+
+    a, b: bf16, 2-D, K contiguous (row pitch may exceed the logical width but must be a multiple of 8).
+    """
+    _lib.require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "gemm_tn takes bf16 operands"
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, N = a.shape[0], b.shape[0]
+    if k is None:
+        k = a.shape[1] - a_koff
+    assert a_koff + k <= a.shape[1] and b_koff + k <= b.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.shape[0] == M and out.shape[1] == N and out.stride(1) == 1
+    assert out.dtype in (torch.float32, torch.bfloat16)
+    _lib.lib().call("ctcb200_gemm_tn_bf16", _lib.ptr(a), a.stride(0), _lib.ptr(b), b.stride(0), _lib.ptr(out),
+                    out.stride(0), M, N, k, a_koff, b_koff, 1 if out.dtype == torch.bfloat16 else 0,
+                    1 if accumulate else 0, tile_n, _lib.stream())
+    return out
+
+
+def argmax_nt(log_probs, want_max=False):
+    """Frame arg-max of [T,N,C] log-probs -> int32 [N,T] (first index on ties), optionally the max values."""
+    _lib.require_cuda(log_probs)
+    lp = log_probs.detach().float().contiguous()
+    T, N, C = lp.shape
+    idx = torch.empty((N, T), dtype=torch.int32, device=lp.device)
+    mx = torch.empty((N, T), dtype=torch.float32, device=lp.device) if want_max else None
+    _lib.lib().call("ctcb200_argmax", _lib.ptr(lp), T, N, C, _lib.ptr(idx), _lib.ptr(mx), _lib.stream())
+    return (idx, mx) if want_max else idx
+
+
+def greedy_decode(log_probs, lengths, blank=0):
+    """Arg-max + CTC collapse. Returns (idx [N,T] int32, labels [N,T] int32, label_lengths [N] int32)."""
+    _lib.require_cuda(log_probs)
+    lp = log_probs.detach().float().contiguous()
+    T, N, C = lp.shape
+    if torch.is_tensor(lengths):
+        lens = lengths.to(device=lp.device, dtype=torch.int64).contiguous()
+    else:
+        lens = torch.as_tensor(list(lengths), dtype=torch.int64, device=lp.device)
+    idx = torch.empty((N, T), dtype=torch.int32, device=lp.device)
+    labels = torch.zeros((N, T), dtype=torch.int32, device=lp.device)
+    out_len = torch.empty((N,), dtype=torch.int32, device=lp.device)
+    _lib.lib().call("ctcb200_greedy_decode", _lib.ptr(lp), _lib.ptr(lens), T, N, C, int(blank), _lib.ptr(idx),
+                    _lib.ptr(labels), _lib.ptr(out_len), _lib.stream())
+    return idx, labels, out_len
