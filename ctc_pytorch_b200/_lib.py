@@ -71,10 +71,16 @@ class _Lib(object):
         self.launches += 1
         if rc != 0:
             raise RuntimeError("%s failed (%d): %s" % (name, rc, self.last_error()))
+        if _DEBUG_SYNC:  # development aid: surface asynchronous kernel faults at the call that caused them
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:
+                raise RuntimeError("%s: kernel fault surfaced at synchronize: %s" % (name, str(e).split("\n")[0]))
         return rc
 
 
 _LIB = None
+_DEBUG_SYNC = os.environ.get("CTCB200_DEBUG_SYNC", "0") == "1"
 
 
 def lib():

@@ -101,7 +101,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Watchdog: a wait that lasts longer than ~2 s of SM clocks means a protocol bug (lost TMA, wrong
 // parity); trap so the launch fails with an error instead of hanging the device.
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;
-__device__ __noinline__ void spin_timeout_trap(int what) {
+static __device__ __noinline__ void spin_timeout_trap(int what) {
     printf("ctcb200: device wait timed out (kind %d) block %d thread %d\n", what, blockIdx.x, threadIdx.x);
     __trap();
 }
@@ -206,6 +206,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(taddr)
         : "memory");
 }

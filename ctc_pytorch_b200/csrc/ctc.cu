@@ -24,12 +24,12 @@ constexpr int WARPS_PER_BLOCK = 4;
 __device__ __forceinline__ float lse2(float a, float b) {
     float m = fmaxf(a, b);
     if (m == NEG_INF) return NEG_INF;
-    return m + __logf(__expf(a - m) + __expf(b - m));
+    return m + logf(expf(a - m) + expf(b - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
     float m = fmaxf(a, fmaxf(b, c));
     if (m == NEG_INF) return NEG_INF;
-    return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+    return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
 __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc) {
@@ -228,7 +228,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
         for (int j = 0; j < KS; ++j) {
             if (st.valid[j]) {
                 float lpv = cur[st.label[j]];
-                float g = __expf(al[j] + b[j] + nll_n - lpv);
+                float g = expf(al[j] + b[j] + nll_n - lpv);
                 int s = lane * KS + j;
                 if (s & 1) atomicAdd(&occ[st.label[j]], g);
                 else blank_sum += g;
@@ -240,7 +240,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
         __syncwarp();
         float* g_row = g_n + t * row_stride;
         for (int c = lane; c < C; c += 32) {
-            float r = __expf(cur[c]) - occ[c];
+            float r = expf(cur[c]) - occ[c];
             g_row[c] = r * gscale;
             occ[c] = 0.0f;
         }

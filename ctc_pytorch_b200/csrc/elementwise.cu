@@ -1,0 +1,425 @@
+// K5 / K6 and layout plumbing — the HBM-bound kernels around the tensor-core GEMMs and the recurrence.
+//
+//   pack_lstm_weights   fp32 nn.LSTM parameters -> bf16 operand layouts (row-permuted so that a CTA of the
+//                       recurrent kernel owns all four gates of 32 units; transposed copies for BPTT / dX)
+//   cast_transpose      fp32 [R,C] (optionally (t,n)-strided, optionally with a per-column affine = the
+//                       BatchNorm apply) -> bf16 [R,C] and/or bf16 [C,R]; feeds every GEMM operand
+//   bn_stats/finalize   training-mode BatchNorm1d statistics over T*N rows (model_ctc.py:29-32,136)
+//   bn_bwd_reduce/apply BatchNorm backward
+//   log_softmax fwd/bwd nn.LogSoftmax(dim=-1) (model_ctc.py:140,168)
+//   transpose_dg        dG bf16 [R,8H] (packed gate order) -> dG^T bf16 [8H,R] in torch's gate order
+//
+// All are grid-stride / tiled streaming kernels: coalesced 128-byte rows, 32x33 shared-memory tiles
+// for the transposes, grids sized in multiples of the SM count.
+#include "common.cuh"
+#include "ctcb200.h"
+
+namespace ctcb200 {
+namespace {
+
+__device__ __forceinline__ int packed_to_orig_row(int p, int H) {
+    // packed gate row p = j*128 + ul*4 + q  ->  torch row q*H + 32 j + ul
+    const int j = p >> 7, ul = (p & 127) >> 2, q = p & 3;
+    return q * H + j * 32 + ul;
+}
+
+__global__ void pack_lstm_weights_kernel(const float* __restrict__ wih_f, const float* __restrict__ whh_f,
+                                         const float* __restrict__ wih_r, const float* __restrict__ whh_r,
+                                         __nv_bfloat16* __restrict__ wih_p, __nv_bfloat16* __restrict__ wihT_p,
+                                         __nv_bfloat16* __restrict__ whh_p, __nv_bfloat16* __restrict__ whhT_p, int H,
+                                         int I, int Ipad) {
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int G4 = 4 * H, G8 = 8 * H;
+    // wih_p [8H, Ipad]
+    for (long long e = tid; e < static_cast<long long>(G8) * Ipad; e += stride) {
+        const int R = static_cast<int>(e / Ipad), i = static_cast<int>(e % Ipad);
+        const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
+        const float* w = dir ? wih_r : wih_f;
+        wih_p[e] = __float2bfloat16(i < I ? w[static_cast<size_t>(orow) * I + i] : 0.0f);
+    }
+    // wihT_p [I, 8H]
+    for (long long e = tid; e < static_cast<long long>(I) * G8; e += stride) {
+        const int i = static_cast<int>(e / G8), R = static_cast<int>(e % G8);
+        const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
+        const float* w = dir ? wih_r : wih_f;
+        wihT_p[e] = __float2bfloat16(w[static_cast<size_t>(orow) * I + i]);
+    }
+    // whh_p [8H, H]
+    for (long long e = tid; e < static_cast<long long>(G8) * H; e += stride) {
+        const int R = static_cast<int>(e / H), k = static_cast<int>(e % H);
+        const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
+        const float* w = dir ? whh_r : whh_f;
+        whh_p[e] = __float2bfloat16(w[static_cast<size_t>(orow) * H + k]);
+    }
+    // whhT_p [(dir,q,m), k] = whh_dir[q*H + k][m]
+    for (long long e = tid; e < static_cast<long long>(G8) * H; e += stride) {
+        const int R = static_cast<int>(e / H), k = static_cast<int>(e % H);
+        const int dir = R / G4, q = (R % G4) / H, m = R % H;
+        const float* w = dir ? whh_r : whh_f;
+        whhT_p[e] = __float2bfloat16(w[(static_cast<size_t>(q) * H + k) * H + m]);
+    }
+}
+
+// src element (r, c) lives at src[(r / n_inner) * s_outer + (r % n_inner) * s_inner + c].
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ src, long long s_outer, long long s_inner, int n_inner,
+                      const float* __restrict__ scale, const float* __restrict__ shift,
+                      __nv_bfloat16* __restrict__ dst, long long dst_pitch, __nv_bfloat16* __restrict__ dstT,
+                      long long dstT_pitch, int n_pad, int R, int C) {
+    __shared__ float tile[32][33];
+    const int tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+    const long long tiles = static_cast<long long>(tiles_c) * tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (long long tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
+        const int r0 = static_cast<int>(tile_id / tiles_c) * 32, c0 = static_cast<int>(tile_id % tiles_c) * 32;
+        const int c = c0 + tx;
+        float sc = 1.0f, sh = 0.0f;
+        if (scale && c < C) { sc = scale[c]; sh = shift[c]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k;
+            float v = 0.0f;
+            if (r < R && c < C) {
+                v = src[static_cast<long long>(r / n_inner) * s_outer + static_cast<long long>(r % n_inner) * s_inner + c];
+                v = v * sc + sh;
+                if (dst) dst[static_cast<long long>(r) * dst_pitch + c] = __float2bfloat16(v);
+            }
+            tile[ty + 8 * k][tx] = v;
+        }
+        if (dstT) {
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cc = c0 + ty + 8 * k, rr = r0 + tx;
+                // transposed column of row (t, n) is t * n_pad + n: the batch axis is padded so that a shift by
+                // one time step stays 16-byte aligned for TMA
+                if (cc < C && rr < R)
+                    dstT[static_cast<long long>(cc) * dstT_pitch + static_cast<long long>(rr / n_inner) * n_pad + rr % n_inner] =
+                        __float2bfloat16(tile[tx][ty + 8 * k]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// dG [R, 8H] bf16 with packed gate columns -> dG^T [8H, Rp] bf16 with rows in torch order (dir, q, unit).
+__global__ void __launch_bounds__(256)
+transpose_dg_kernel(const __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ dgT, long long dgT_pitch,
+                    int n_inner, int n_pad, int R, int H) {
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int G8 = 8 * H, G4 = 4 * H;
+    const int tiles_c = G8 / 32, tiles_r = (R + 31) / 32;
+    const long long tiles = static_cast<long long>(tiles_c) * tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (long long tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
+        const int r0 = static_cast<int>(tile_id / tiles_c) * 32, c0 = static_cast<int>(tile_id % tiles_c) * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k;
+            tile[ty + 8 * k][tx] = (r < R) ? dg[static_cast<long long>(r) * G8 + c0 + tx] : __float2bfloat16(0.0f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cc = c0 + ty + 8 * k, rr = r0 + tx;
+            const int dir = cc / G4, orow = dir * G4 + packed_to_orig_row(cc % G4, H);
+            if (rr < R)
+                dgT[static_cast<long long>(orow) * dgT_pitch + static_cast<long long>(rr / n_inner) * n_pad + rr % n_inner] =
+                    tile[tx][ty + 8 * k];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- BatchNorm ------------------------------------------------------------------------------------
+// partial column sums over a slab of rows; double atomics into ws[0..C) (sum) and ws[C..2C) (sum of squares)
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ x, double* __restrict__ ws, int R, int C, int rows_per_block) {
+    __shared__ float s1[8][32], s2[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int r_begin = blockIdx.y * rows_per_block;
+    const int r_end = min(R, r_begin + rows_per_block);
+    float a = 0.0f, b = 0.0f;
+    if (c < C)
+        for (int r = r_begin + ty; r < r_end; r += 8) {
+            const float v = x[static_cast<long long>(r) * C + c];
+            a += v;
+            b += v * v;
+        }
+    s1[ty][tx] = a;
+    s2[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double da = 0.0, db = 0.0;
+        for (int k = 0; k < 8; ++k) { da += s1[k][tx]; db += s2[k][tx]; }
+        atomicAdd(&ws[c], da);
+        atomicAdd(&ws[C + c], db);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift, int R,
+                                   int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = ws[c] / R;
+    double var = ws[C + c] / R - m * m;
+    if (var < 0.0) var = 0.0;
+    const float rs = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    mean[c] = static_cast<float>(m);
+    rstd[c] = rs;
+    const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    scale[c] = g * rs;
+    shift[c] = b - static_cast<float>(m) * g * rs;
+    if (running_mean) {
+        const double unbiased = R > 1 ? var * R / (R - 1) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(m);
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+// inference: scale/shift from running statistics
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float eps, float* __restrict__ scale, float* __restrict__ shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float rs = rsqrtf(running_var[c] + eps);
+    const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    scale[c] = g * rs;
+    shift[c] = b - running_mean[c] * g * rs;
+}
+
+// sums over rows of dy and dy * xhat (xhat = (x - mean) * rstd)
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, double* __restrict__ ws, int R, int C, int rows_per_block) {
+    __shared__ float s1[8][32], s2[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int r_begin = blockIdx.y * rows_per_block;
+    const int r_end = min(R, r_begin + rows_per_block);
+    float a = 0.0f, b = 0.0f;
+    if (c < C) {
+        const float m = mean[c], rs = rstd[c];
+        for (int r = r_begin + ty; r < r_end; r += 8) {
+            const long long o = static_cast<long long>(r) * C + c;
+            const float g = dy[o];
+            a += g;
+            b += g * (x[o] - m) * rs;
+        }
+    }
+    s1[ty][tx] = a;
+    s2[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double da = 0.0, db = 0.0;
+        for (int k = 0; k < 8; ++k) { da += s1[k][tx]; db += s2[k][tx]; }
+        atomicAdd(&ws[c], da);
+        atomicAdd(&ws[C + c], db);
+    }
+}
+
+// dx = gamma*rstd * (dy - sum_dy/R - xhat * sum_dy_xhat/R); also emits dgamma / dbeta (block 0)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ ws,
+                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
+    const long long total = static_cast<long long>(R) * C;
+    const float invR = 1.0f / R;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % C);
+        const float rs = rstd[c], g = gamma ? gamma[c] : 1.0f;
+        const float xh = (x[e] - mean[c]) * rs;
+        const float sdy = static_cast<float>(ws[c]), sdyx = static_cast<float>(ws[C + c]);
+        dx[e] = g * rs * (dy[e] - sdy * invR - xh * sdyx * invR);
+    }
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (dbeta) dbeta[c] = static_cast<float>(ws[c]);
+            if (dgamma) dgamma[c] = static_cast<float>(ws[C + c]);
+        }
+}
+
+// ---- log-softmax ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+log_softmax_fwd_kernel(const float* __restrict__ x, long long x_pitch, float* __restrict__ y, int R, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long wpb = blockDim.x >> 5;
+    for (long long r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+        const float* p = x + r * x_pitch;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, p[c]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.0f;
+        for (int c = lane; c < C; c += 32) s += expf(p[c] - m);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float lse = m + logf(s);
+        float* q = y + r * C;
+        for (int c = lane; c < C; c += 32) q[c] = p[c] - lse;
+    }
+}
+
+// dx = g - exp(y) * sum_c g
+__global__ void __launch_bounds__(256)
+log_softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ dx, int R, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long wpb = blockDim.x >> 5;
+    for (long long r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+        const float* gp = g + r * C;
+        const float* yp = y + r * C;
+        float s = 0.0f;
+        for (int c = lane; c < C; c += 32) s += gp[c];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        float* d = dx + r * C;
+        for (int c = lane; c < C; c += 32) d[c] = gp[c] - expf(yp[c]) * s;
+    }
+}
+
+// out[r, c] = a[r, c] * mask[r, c] * inv_keep (dropout apply; the mask comes from the host framework's RNG)
+__global__ void scale_mask_kernel(float* __restrict__ a, const uint8_t* __restrict__ mask, float inv_keep, long long n) {
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+         e += static_cast<long long>(gridDim.x) * blockDim.x)
+        a[e] = mask[e] ? a[e] * inv_keep : 0.0f;
+}
+
+int stream_grid(long long work_items, int per_block) {
+    long long b = (work_items + per_block - 1) / per_block;
+    const long long cap = static_cast<long long>(device_sm_count()) * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+}  // namespace
+}  // namespace ctcb200
+
+using namespace ctcb200;
+
+extern "C" CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const float* whh_f, const float* wih_r,
+                                                     const float* whh_r, void* wih_p, void* wihT_p, void* whh_p,
+                                                     void* whhT_p, int H, int I, int Ipad,
+                                                     ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(H % 32 == 0 && I > 0 && Ipad >= I && Ipad % 8 == 0, "pack_lstm_weights: bad sizes H=%d I=%d Ipad=%d", H, I, Ipad);
+    const long long work = static_cast<long long>(8) * H * (Ipad > H ? Ipad : H);
+    pack_lstm_weights_kernel<<<stream_grid(work, 1024), 256, 0, stream>>>(
+        wih_f, whh_f, wih_r, whh_r, static_cast<__nv_bfloat16*>(wih_p), static_cast<__nv_bfloat16*>(wihT_p),
+        static_cast<__nv_bfloat16*>(whh_p), static_cast<__nv_bfloat16*>(whhT_p), H, I, Ipad);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_outer, int64_t s_inner, int n_inner,
+                                                  const float* scale, const float* shift, void* dst, int64_t dst_pitch,
+                                                  void* dstT, int64_t dstT_pitch, int n_pad, int R, int C,
+                                                  ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(R > 0 && C > 0 && n_inner > 0, "cast_transpose: empty R=%d C=%d", R, C);
+    CTCB_REQUIRE(dst || dstT, "cast_transpose: no output requested");
+    CTCB_REQUIRE(n_pad >= n_inner, "cast_transpose: n_pad %d < n_inner %d", n_pad, n_inner);
+    const long long tiles = static_cast<long long>((R + 31) / 32) * ((C + 31) / 32);
+    cast_transpose_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(
+        src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch,
+        static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64_t dgT_pitch, int n_inner, int n_pad,
+                                                int R, int H, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(R > 0 && H % 32 == 0, "transpose_dg: bad sizes R=%d H=%d", R, H);
+    const long long tiles = static_cast<long long>((R + 31) / 32) * (8 * H / 32);
+    transpose_dg_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dg),
+                                                                 static_cast<__nv_bfloat16*>(dgT), dgT_pitch, n_inner,
+                                                                 n_pad, R, H);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+// ws: 2*C doubles of scratch. Training statistics over R rows; writes mean/rstd (saved for backward),
+// scale/shift (the affine cast_transpose applies) and updates the running statistics like nn.BatchNorm1d.
+extern "C" CTCB200_API int ctcb200_bn_train_stats(const float* x, int R, int C, const float* gamma, const float* beta,
+                                                  float* running_mean, float* running_var, float momentum, float eps,
+                                                  float* mean, float* rstd, float* scale, float* shift, void* ws,
+                                                  ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(R > 0 && C > 0, "bn_train_stats: empty R=%d C=%d", R, C);
+    CTCB_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(2) * C * sizeof(double), stream));
+    const int col_blocks = (C + 31) / 32;
+    int row_blocks = (device_sm_count() * 4 + col_blocks - 1) / col_blocks;
+    int rows_per_block = (R + row_blocks - 1) / row_blocks;
+    if (rows_per_block < 64) rows_per_block = 64;
+    row_blocks = (R + rows_per_block - 1) / rows_per_block;
+    bn_stats_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(x, static_cast<double*>(ws), R, C, rows_per_block);
+    CTCB_LAUNCH_CHECK();
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(static_cast<const double*>(ws), gamma, beta, running_mean,
+                                                          running_var, momentum, eps, mean, rstd, scale, shift, R, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                                                  const float* running_var, float eps, float* scale, float* shift,
+                                                  int C, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, scale, shift, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                          const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C,
+                                          void* ws, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(R > 0 && C > 0, "bn_bwd: empty R=%d C=%d", R, C);
+    CTCB_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(2) * C * sizeof(double), stream));
+    const int col_blocks = (C + 31) / 32;
+    int row_blocks = (device_sm_count() * 4 + col_blocks - 1) / col_blocks;
+    int rows_per_block = (R + row_blocks - 1) / row_blocks;
+    if (rows_per_block < 64) rows_per_block = 64;
+    row_blocks = (R + rows_per_block - 1) / rows_per_block;
+    bn_bwd_reduce_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(dy, x, mean, rstd, static_cast<double*>(ws), R, C,
+                                                                         rows_per_block);
+    CTCB_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<stream_grid(static_cast<long long>(R) * C, 1024), 256, 0, stream>>>(
+        dy, x, mean, rstd, gamma, static_cast<const double*>(ws), dx, dgamma, dbeta, R, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_log_softmax_fwd(const float* x, int64_t x_pitch, float* y, int R, int C,
+                                                   ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(R > 0 && C > 0, "log_softmax_fwd: empty R=%d C=%d", R, C);
+    log_softmax_fwd_kernel<<<stream_grid(R, 8), 256, 0, stream>>>(x, x_pitch, y, R, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_log_softmax_bwd(const float* g, const float* y, float* dx, int R, int C,
+                                                   ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(R > 0 && C > 0, "log_softmax_bwd: empty R=%d C=%d", R, C);
+    log_softmax_bwd_kernel<<<stream_grid(R, 8), 256, 0, stream>>>(g, y, dx, R, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_dropout_apply(float* a, const void* mask_u8, float inv_keep, int64_t n,
+                                                 ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(n > 0, "dropout_apply: empty");
+    scale_mask_kernel<<<stream_grid(n, 1024), 256, 0, stream>>>(a, static_cast<const uint8_t*>(mask_u8), inv_keep, n);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}

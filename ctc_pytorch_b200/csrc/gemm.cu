@@ -225,6 +225,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, long lo
 int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
                  int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, cudaStream_t stream) {
     CTCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    CTCB_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0 && a_koff >= 0 && b_koff >= 0,
+                 "gemm: K offsets (%d, %d) must be non-negative multiples of 8 (TMA box start is 16-byte aligned)", a_koff,
+                 b_koff);
     int bn = force_bn;
     if (bn == 0) {
         // widest tile that still yields at least one full wave, else favour more tiles

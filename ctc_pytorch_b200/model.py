@@ -1,0 +1,426 @@
+"""Drop-in for the reference's acoustic model, timit/models/model_ctc.py (BatchRNN :13-36,
+LayerCNN :38-68, CTC_Model :70-229).
+
+Same constructor arguments, attributes, `state_dict()` keys/shapes (`conv.{n}.conv.*`,
+`conv.{n}.batch_norm.*`, `rnns.{l}.batch_norm.*`, `rnns.{l}.rnn.weight_{ih,hh}_l0[_reverse]`, `fc.*`)
+and the same forward contract (x [N,T,F] f32 -> log-probs [T',N,C] f32, differentiable), but every FLOP
+runs in libctcb200's sm_100a kernels: the input projections, weight gradients and the output layer on the
+tcgen05 GEMM, the time recurrence in the persistent recurrent kernels, BatchNorm / LogSoftmax / layout
+changes in the streaming kernels. The torch modules below are parameter containers only (so checkpoints
+interchange with the reference); their forward() is never called.
+
+Behaviour kept on purpose: the LSTM and BatchNorm run over all padded frames,
+layer 0 never has BatchNorm, BatchNorm statistics are over T*N rows, the fc BatchNorm follows
+rnn_param['batch_norm'].
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import ops
+
+__all__ = ["BatchRNN", "LayerCNN", "CTC_Model"]
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class BatchRNN(nn.Module):
+    """Optional BatchNorm1d over the feature axis, a bidirectional bias-free LSTM, then dropout."""
+
+    def __init__(self, input_size, hidden_size, rnn_type=nn.LSTM, bidirectional=False, batch_norm=True, dropout=0.1):
+        super(BatchRNN, self).__init__()
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.bidirectional = bidirectional
+        self.batch_norm = nn.BatchNorm1d(input_size) if batch_norm else None
+        self.rnn = rnn_type(input_size=input_size, hidden_size=hidden_size, bidirectional=bidirectional, bias=False)
+        self.dropout = nn.Dropout(p=dropout)
+
+    def forward(self, x):
+        raise RuntimeError("BatchRNN is executed by CTC_Model's fused CUDA path; call the model, not the layer")
+
+
+class LayerCNN(nn.Module):
+    """Conv2d (+BatchNorm2d) + activation (+MaxPool2d) + dropout block of the optional CNN front."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride, padding, pooling_size=None,
+                 activation_function=nn.ReLU, batch_norm=True, dropout=0.1):
+        super(LayerCNN, self).__init__()
+        if len(kernel_size) == 2:
+            self.conv = nn.Conv2d(in_channel, out_channel, kernel_size=kernel_size, stride=stride, padding=padding)
+            self.batch_norm = nn.BatchNorm2d(out_channel) if batch_norm else None
+        else:
+            self.conv = nn.Conv1d(in_channel, out_channel, kernel_size=kernel_size, stride=stride, padding=padding)
+            self.batch_norm = nn.BatchNorm1d(out_channel) if batch_norm else None
+        self.activation = activation_function(inplace=True)
+        if pooling_size is not None and len(kernel_size) == 2:
+            self.pooling = nn.MaxPool2d(pooling_size)
+        elif len(kernel_size) == 1:
+            self.pooling = nn.MaxPool1d(pooling_size)
+        else:
+            self.pooling = None
+        self.dropout = nn.Dropout(p=dropout)
+
+    def forward(self, x):
+        raise RuntimeError("LayerCNN is executed by CTC_Model's CUDA path; call the model, not the layer")
+
+
+# ----------------------------------------------------------------------------------------------------
+# the fused RNN stack + output layer as one autograd node
+# ----------------------------------------------------------------------------------------------------
+class _Workspace(object):
+    """Per-call tensors kept between forward and backward."""
+    pass
+
+
+def _call(name, *args):
+    return _lib.lib().call(name, *args)
+
+
+def _cast_t(src, s_outer, s_inner, n_inner, R, C, scale=None, shift=None, want=True, want_t=False):
+    """fp32 (strided rows) -> bf16 [R, Cp] and/or bf16 [C, (R/n_inner)*n_pad] with the batch axis padded to 8."""
+    dev = src.device
+    Cp = _round_up(C, 8)
+    n_pad = _round_up(n_inner, 8) if n_inner > 1 else 1
+    Rp = _round_up((R // n_inner) * n_pad, 8)
+    dst = torch.empty((R, Cp), dtype=torch.bfloat16, device=dev) if want else None
+    dst_t = None
+    if want_t:
+        alloc = torch.empty if (n_pad == n_inner and Rp == R) else torch.zeros
+        dst_t = alloc((C, Rp), dtype=torch.bfloat16, device=dev)
+    _call("ctcb200_cast_transpose", _lib.ptr(src), s_outer, s_inner, n_inner, _lib.ptr(scale), _lib.ptr(shift),
+          _lib.ptr(dst), Cp, _lib.ptr(dst_t), Rp, n_pad, R, C, _lib.stream())
+    return dst, dst_t
+
+
+class _BNState(object):
+    __slots__ = ("mean", "rstd", "scale", "shift")
+
+
+def _bn_prepare(bn, x2d, R, C, training):
+    """Statistics (training) or running-stat affine (eval) for BatchNorm1d `bn` over rows of x2d [R, C]."""
+    dev = x2d.device
+    st = _BNState()
+    st.scale = torch.empty(C, dtype=torch.float32, device=dev)
+    st.shift = torch.empty(C, dtype=torch.float32, device=dev)
+    gamma = bn.weight if bn.affine else None
+    beta = bn.bias if bn.affine else None
+    use_batch = training or not bn.track_running_stats
+    if use_batch:
+        st.mean = torch.empty(C, dtype=torch.float32, device=dev)
+        st.rstd = torch.empty(C, dtype=torch.float32, device=dev)
+        ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        upd = training and bn.track_running_stats
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        if upd:
+            bn.num_batches_tracked.add_(1)
+            if bn.momentum is None:
+                mom = 1.0 / float(bn.num_batches_tracked.item())
+        _call("ctcb200_bn_train_stats", _lib.ptr(x2d), R, C, _lib.ptr(gamma), _lib.ptr(beta),
+              _lib.ptr(bn.running_mean if upd else None), _lib.ptr(bn.running_var if upd else None), mom,
+              float(bn.eps), _lib.ptr(st.mean), _lib.ptr(st.rstd), _lib.ptr(st.scale), _lib.ptr(st.shift),
+              _lib.ptr(ws), _lib.stream())
+    else:
+        st.mean = st.rstd = None
+        _call("ctcb200_bn_eval_affine", _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(bn.running_mean),
+              _lib.ptr(bn.running_var), float(bn.eps), _lib.ptr(st.scale), _lib.ptr(st.shift), C, _lib.stream())
+    return st
+
+
+class _RnnStackFn(torch.autograd.Function):
+    """x [T*N rows as (t,n), I0] view of the input -> log-probs [T, N, C]."""
+
+    @staticmethod
+    def forward(ctx, model, x_src, geom, *params):
+        # geom: (T, N, I0, s_outer, s_inner, need_grad) describing where row (t, n) of the layer-0 input lives in x_src
+        T, N, I0, s_outer, s_inner, need_grad = geom
+        dev = x_src.device
+        training = model.training
+        R = T * N
+        Np = _round_up(N, 8)
+        Rp = T * Np  # width of the time-major transposed operands (batch axis padded to 8)
+        H = model.rnn_param["rnn_hidden_size"]
+        C = model.num_class
+        layers = list(model.rnns.children())
+        ws = _Workspace()
+        ws.geom, ws.layers_n = geom, len(layers)
+        ws.L = []
+        stream = _lib.stream
+
+        scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
+        X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=need_grad)
+        h_prev = None
+        I = I0
+        for li, layer in enumerate(layers):
+            rec = _Workspace()
+            rec.I = I
+            rec.bn = None
+            if li > 0:
+                I = 2 * H
+                rec.I = I
+                if layer.batch_norm is not None:
+                    rec.bn = _bn_prepare(layer.batch_norm, h_prev, R, I, training)
+                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, rec.bn.scale, rec.bn.shift, True, need_grad)
+                else:
+                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, None, None, True, need_grad)
+            Ipad = _round_up(I, 8)
+            rnn = layer.rnn
+            wih_p = torch.empty((8 * H, Ipad), dtype=torch.bfloat16, device=dev)
+            wihT_p = torch.empty((I, 8 * H), dtype=torch.bfloat16, device=dev)
+            whh_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
+            whhT_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
+            _call("ctcb200_pack_lstm_weights", _lib.ptr(rnn.weight_ih_l0), _lib.ptr(rnn.weight_hh_l0),
+                  _lib.ptr(rnn.weight_ih_l0_reverse), _lib.ptr(rnn.weight_hh_l0_reverse), _lib.ptr(wih_p),
+                  _lib.ptr(wihT_p), _lib.ptr(whh_p), _lib.ptr(whhT_p), H, I, Ipad, stream())
+            gx = ops.gemm_tn(X, wih_p, k=I)  # [R, 8H] f32
+            hout = torch.empty((R, 2 * H), dtype=torch.float32, device=dev)
+            c_save = torch.empty((R, 2 * H), dtype=torch.float32, device=dev) if need_grad else None
+            gates = torch.empty((R, 2 * H, 4), dtype=torch.float16, device=dev) if need_grad else None
+            _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p), _lib.ptr(hout), _lib.ptr(c_save),
+                  _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, stream())
+            del gx
+            rec.HT = None
+            if need_grad:
+                _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True)
+            rec.mask = None
+            p_drop = float(layer.dropout.p)
+            if training and p_drop > 0.0:
+                rec.mask = (torch.rand(hout.shape, device=dev) >= p_drop).to(torch.uint8)
+                _call("ctcb200_dropout_apply", _lib.ptr(hout), _lib.ptr(rec.mask), 1.0 / (1.0 - p_drop), hout.numel(),
+                      stream())
+            rec.XT, rec.h_in = XT, h_prev
+            rec.c_save, rec.gates, rec.wihT_p, rec.whhT_p = c_save, gates, wihT_p, whhT_p
+            ws.L.append(rec)
+            h_prev = hout
+
+        # output layer: (BatchNorm1d) + Linear(no bias) + LogSoftmax
+        F2 = 2 * H
+        fc_bn, fc_lin = (model.fc[0], model.fc[1]) if isinstance(model.fc, nn.Sequential) else (None, model.fc)
+        ws.fc_bn = _bn_prepare(fc_bn, h_prev, R, F2, training) if fc_bn is not None else None
+        Xfc, XfcT = _cast_t(h_prev, N * F2, F2, N, R, F2, ws.fc_bn.scale if ws.fc_bn else None,
+                            ws.fc_bn.shift if ws.fc_bn else None, True, need_grad)
+        Wfc_b, WfcT_b = _cast_t(fc_lin.weight, F2, F2, 1, C, F2, want=True, want_t=need_grad)
+        logits = ops.gemm_tn(Xfc, Wfc_b, k=F2)  # [R, C]
+        out = torch.empty((T, N, C), dtype=torch.float32, device=dev)
+        _call("ctcb200_log_softmax_fwd", _lib.ptr(logits), logits.stride(0), _lib.ptr(out), R, C, stream())
+        ws.h_last, ws.XfcT, ws.WfcT_b, ws.out = h_prev, XfcT, WfcT_b, out
+        ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np = T, N, H, C, R, Rp, Np
+        ctx.ws = ws if need_grad else None
+        ctx.model = model
+        ctx.param_list = params
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        ws, model = ctx.ws, ctx.model
+        if ws is None:
+            raise RuntimeError("backward through a forward pass that ran without gradient bookkeeping")
+        T, N, H, C, R, Rp, Np = ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np
+        dev = g_out.device
+        stream = _lib.stream
+        F2 = 2 * H
+        layers = list(model.rnns.children())
+        grads = {}
+
+        g = g_out.detach().to(torch.float32).contiguous()
+        dlogits = torch.empty((R, C), dtype=torch.float32, device=dev)
+        _call("ctcb200_log_softmax_bwd", _lib.ptr(g), _lib.ptr(ws.out), _lib.ptr(dlogits), R, C, stream())
+        dLb, dLT = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=True)
+        fc_bn, fc_lin = (model.fc[0], model.fc[1]) if isinstance(model.fc, nn.Sequential) else (None, model.fc)
+        grads[fc_lin.weight] = ops.gemm_tn(dLT, ws.XfcT, k=Rp)              # [C, 2H]
+        dh = ops.gemm_tn(dLb, ws.WfcT_b, k=C)                              # [R, 2H]
+        dws = torch.empty(2 * F2, dtype=torch.float64, device=dev)
+        if fc_bn is not None:
+            dgam = torch.empty(F2, dtype=torch.float32, device=dev)
+            dbet = torch.empty(F2, dtype=torch.float32, device=dev)
+            _call("ctcb200_bn_bwd", _lib.ptr(dh), _lib.ptr(ws.h_last), _lib.ptr(ws.fc_bn.mean), _lib.ptr(ws.fc_bn.rstd),
+                  _lib.ptr(fc_bn.weight), _lib.ptr(dh), _lib.ptr(dgam), _lib.ptr(dbet), R, F2, _lib.ptr(dws), stream())
+            grads[fc_bn.weight], grads[fc_bn.bias] = dgam, dbet
+
+        scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
+        for li in range(len(layers) - 1, -1, -1):
+            layer, rec = layers[li], ws.L[li]
+            I = rec.I
+            if rec.mask is not None:
+                _call("ctcb200_dropout_apply", _lib.ptr(dh), _lib.ptr(rec.mask), 1.0 / (1.0 - float(layer.dropout.p)),
+                      dh.numel(), stream())
+            dg = torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev)
+            _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p), _lib.ptr(rec.c_save), _lib.ptr(rec.gates),
+                  _lib.ptr(dg), _lib.ptr(scratch), T, N, H, model.batch_tile, stream())
+            dgT = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
+            _call("ctcb200_transpose_dg", _lib.ptr(dg), _lib.ptr(dgT), Rp, N, Np, R, H, stream())
+            dwih = ops.gemm_tn(dgT, rec.XT, k=Rp)                          # [8H, I], torch row order
+            rnn = layer.rnn
+            grads[rnn.weight_ih_l0], grads[rnn.weight_ih_l0_reverse] = dwih[:4 * H], dwih[4 * H:]
+            if T > 1:
+                K = Rp - Np  # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan
+                grads[rnn.weight_hh_l0] = ops.gemm_tn(dgT[:4 * H], rec.HT[:H], a_koff=Np, b_koff=0, k=K)
+                grads[rnn.weight_hh_l0_reverse] = ops.gemm_tn(dgT[4 * H:], rec.HT[H:], a_koff=0, b_koff=Np, k=K)
+            else:
+                grads[rnn.weight_hh_l0] = torch.zeros_like(rnn.weight_hh_l0)
+                grads[rnn.weight_hh_l0_reverse] = torch.zeros_like(rnn.weight_hh_l0_reverse)
+            del dgT
+            if li > 0:
+                dh = ops.gemm_tn(dg, rec.wihT_p, k=8 * H)                  # [R, I]
+                bn = layer.batch_norm
+                if bn is not None:
+                    dgam = torch.empty(I, dtype=torch.float32, device=dev)
+                    dbet = torch.empty(I, dtype=torch.float32, device=dev)
+                    _call("ctcb200_bn_bwd", _lib.ptr(dh), _lib.ptr(rec.h_in), _lib.ptr(rec.bn.mean), _lib.ptr(rec.bn.rstd),
+                          _lib.ptr(bn.weight), _lib.ptr(dh), _lib.ptr(dgam), _lib.ptr(dbet), R, I, _lib.ptr(dws), stream())
+                    grads[bn.weight], grads[bn.bias] = dgam, dbet
+            del dg
+        ctx.ws = None
+        return (None, None, None) + tuple(grads.get(p) for p in ctx.param_list)
+
+
+class CTC_Model(nn.Module):
+    def __init__(self, add_cnn=False, cnn_param=None, rnn_param=None, num_class=39, drop_out=0.1):
+        """
+        add_cnn   [bool]:  put the Conv2d front before the RNN stack
+        cnn_param [dict]:  {"layer": [[(cin, cout), (kh, kw), (sh, sw), (ph, pw), pool], ...],
+                            "batch_norm": bool, "activate_function": nn.ReLU}
+        rnn_param [dict]:  {"rnn_input_size", "rnn_hidden_size", "rnn_layers", "rnn_type", "bidirectional",
+                            "batch_norm"}
+        num_class  [int]:  number of output classes including blank
+        drop_out [float]:  dropout probability used everywhere
+        """
+        super(CTC_Model, self).__init__()
+        self.add_cnn = add_cnn
+        self.cnn_param = cnn_param
+        if rnn_param is None or type(rnn_param) != dict:
+            raise ValueError("rnn_param need to be a dict to contain all params of rnn!")
+        self.rnn_param = rnn_param
+        self.num_class = num_class
+        self.num_directions = 2 if rnn_param["bidirectional"] else 1
+        self.drop_out = drop_out
+        self.batch_tile = 0  # 0 = let the library pick the recurrent kernels' batch tile (16 or 32)
+
+        rnn_input_size = rnn_param["rnn_input_size"]
+        if add_cnn:
+            blocks = []
+            out_channel = 1
+            for n, spec in enumerate(cnn_param["layer"]):
+                (in_channel, out_channel), kernel_size, stride, padding, pooling_size = spec
+                blocks.append(("%d" % n, LayerCNN(in_channel, out_channel, kernel_size, stride, padding, pooling_size,
+                                                  activation_function=cnn_param["activate_function"],
+                                                  batch_norm=cnn_param["batch_norm"], dropout=drop_out)))
+                try:
+                    rnn_input_size = int(math.floor((rnn_input_size + 2 * padding[1] - kernel_size[1]) / stride[1]) + 1)
+                except Exception:
+                    pass  # 1-d convolution keeps the feature size
+            self.conv = nn.Sequential(OrderedDict(blocks))
+            rnn_input_size *= out_channel
+
+        hidden = rnn_param["rnn_hidden_size"]
+        stack = [("0", BatchRNN(input_size=rnn_input_size, hidden_size=hidden, rnn_type=rnn_param["rnn_type"],
+                                bidirectional=rnn_param["bidirectional"], dropout=drop_out, batch_norm=False))]
+        for i in range(rnn_param["rnn_layers"] - 1):
+            stack.append(("%d" % (i + 1),
+                          BatchRNN(input_size=self.num_directions * hidden, hidden_size=hidden,
+                                   rnn_type=rnn_param["rnn_type"], bidirectional=rnn_param["bidirectional"],
+                                   dropout=drop_out, batch_norm=rnn_param["batch_norm"])))
+        self.rnns = nn.Sequential(OrderedDict(stack))
+
+        if rnn_param["batch_norm"]:
+            self.fc = nn.Sequential(nn.BatchNorm1d(self.num_directions * hidden),
+                                    nn.Linear(self.num_directions * hidden, num_class, bias=False))
+        else:
+            self.fc = nn.Linear(self.num_directions * hidden, num_class, bias=False)
+        self.log_softmax = nn.LogSoftmax(dim=-1)
+
+    # -- checks that keep the CUDA path honest -------------------------------------------------------
+    def _check_supported(self, x):
+        _lib.require_cuda(x)
+        if self.rnn_param["rnn_type"] is not nn.LSTM:
+            raise RuntimeError("the B200 path implements nn.LSTM layers only (got %r)" % (self.rnn_param["rnn_type"],))
+        if not self.rnn_param["bidirectional"]:
+            raise RuntimeError("the B200 path implements bidirectional LSTM layers only")
+        if next(self.parameters()).device != x.device:
+            raise RuntimeError("model parameters and input must live on the same CUDA device")
+
+    def _rnn_params(self):
+        plist = []
+        for layer in self.rnns.children():
+            if layer.batch_norm is not None:
+                plist += [layer.batch_norm.weight, layer.batch_norm.bias]
+            plist += [layer.rnn.weight_ih_l0, layer.rnn.weight_hh_l0, layer.rnn.weight_ih_l0_reverse,
+                      layer.rnn.weight_hh_l0_reverse]
+        if isinstance(self.fc, nn.Sequential):
+            plist += [self.fc[0].weight, self.fc[0].bias, self.fc[1].weight]
+        else:
+            plist += [self.fc.weight]
+        return plist
+
+    def forward(self, x, visualize=False):
+        # x: [batch, max_seq_length, feat_size]
+        self._check_supported(x)
+        visual = [x] if visualize else None
+        # activations for BPTT are kept only when a backward pass can follow
+        need_grad = self.training and torch.is_grad_enabled()
+        if self.add_cnn:
+            from . import cnn
+            feats = cnn.conv_front(self, x)  # [N, Cc, T', F'] f32
+            if visualize:
+                visual.append(feats)
+            Nb, Cc, Tp, Fp = feats.shape
+            seq = feats.transpose(1, 2).contiguous().view(Nb, Tp, Cc * Fp)  # [N, T', Cc*F']
+            if visualize:
+                visual.append(seq.transpose(0, 1))
+            src, geom = seq, (Tp, Nb, Cc * Fp, Cc * Fp, Tp * Cc * Fp, need_grad)
+        else:
+            if x.dtype != torch.float32:
+                x = x.float()
+            x = x.contiguous()
+            Nb, Tp, Fp = x.shape
+            src, geom = x, (Tp, Nb, Fp, Fp, Tp * Fp, need_grad)
+        out = _RnnStackFn.apply(self, src, geom, *self._rnn_params())
+        if visualize:
+            visual.append(out)
+            return out, visual
+        return out
+
+    # -- host-side helpers mirrored from the reference -------------------------------------------------
+    def compute_wer(self, index, input_sizes, targets, target_sizes):
+        """(edit-distance errors, reference tokens) over a batch of frame arg-max rows (model_ctc.py:187-202)."""
+        from .decoder import collapse_frames, edit_distance
+        batch_errs = 0
+        batch_tokens = 0
+        for i in range(len(index)):
+            label = [int(v) for v in targets[i][:int(target_sizes[i])]]
+            pred = collapse_frames(index[i][:int(input_sizes[i])], blank=0)
+            batch_errs += edit_distance(label, pred)
+            batch_tokens += len(label)
+        return batch_errs, batch_tokens
+
+    def add_weights_noise(self):
+        # the reference's version rebinds a local and therefore changes nothing (model_ctc.py:204-207)
+        return None
+
+    @staticmethod
+    def save_package(model, optimizer=None, decoder=None, epoch=None, loss_results=None, dev_loss_results=None,
+                     dev_cer_results=None):
+        package = {
+            "rnn_param": model.rnn_param,
+            "add_cnn": model.add_cnn,
+            "cnn_param": model.cnn_param,
+            "num_class": model.num_class,
+            "_drop_out": model.drop_out,
+            "state_dict": model.state_dict(),
+        }
+        if optimizer is not None:
+            package["optim_dict"] = optimizer.state_dict()
+        if decoder is not None:
+            package["decoder"] = decoder
+        if epoch is not None:
+            package["epoch"] = epoch
+        if loss_results is not None:
+            package["loss_results"] = loss_results
+            package["dev_loss_results"] = dev_loss_results
+            package["dev_cer_results"] = dev_cer_results
+        return package

@@ -67,12 +67,72 @@ CTCB200_API int ctcb200_greedy_decode(const float* log_probs, const int64_t* len
 
 /* ---- dense GEMM on tcgen05: C[M,N] (+)= A[M,K] * B[N,K]^T, A/B bf16 with K contiguous (pitches lda/ldb in
  * elements, multiples of 8), fp32 accumulate, C f32 (out_bf16=0) or bf16 (1) with pitch ldc.
- * a_koff/b_koff shift the K window of each operand (used for the h_{t-1} shift of dW_hh).
+ * a_koff/b_koff (multiples of 8) shift the K window of each operand (the h_{t-1} shift of dW_hh).
  * tile_n: 0 = auto, else 64/128/256. Carries the contractions behind nn.LSTM / nn.Linear at
  * timit/models/model_ctc.py:23-26,33,136-139. */
 CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                      int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
                                      int tile_n, ctcb200_stream_t stream);
+
+/* ---- bidirectional LSTM layer: replaces nn.LSTM(bias=False, bidirectional=True) fwd/bwd time loops,
+ * timit/models/model_ctc.py:23-26,33 and the BPTT behind timit/steps/train_ctc.py:63.
+ * Operand layouts (all produced by ctcb200_pack_lstm_weights from the torch-layout fp32 parameters
+ * weight_ih_l0[4H,I], weight_hh_l0[4H,H] and their *_reverse twins):
+ *   wih_p  bf16 [8H, Ipad]  rows (dir, j, unit_local, gate): B operand of Gx = X * wih_p^T
+ *   wihT_p bf16 [I, 8H]     B operand of dX = dG * wihT_p^T
+ *   whh_p  bf16 [8H, H]     same row order as wih_p; resident A operand of the forward recurrence
+ *   whhT_p bf16 [8H, H]     rows (dir, gate, unit), cols = gate-row unit: A operand of the backward recurrence
+ * lstm_fwd: gx f32 [T*N, 8H] (= X * wih_p^T), writes hout f32 [T*N, 2H] (fwd | reverse halves), and when
+ * c_save / gates_save are non-NULL the cell states f32 [T*N, 2H] and activated gates (4 x fp16 = 8 bytes per
+ * element, [T*N, 2H]) that lstm_bwd consumes. scratch: ctcb200_lstm_scratch_bytes(N, H) bytes.
+ * lstm_bwd: dhout f32 [T*N, 2H] -> dg bf16 [T*N, 8H] (gate gradients, wih_p column order).
+ * batch_tile: 0 = auto, or 16 / 32 batch columns per CTA group. H must be a multiple of 128, <= 640. */
+CTCB200_API int64_t ctcb200_lstm_scratch_bytes(int N, int H);
+CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const float* whh_f, const float* wih_r,
+                                          const float* whh_r, void* wih_p, void* wihT_p, void* whh_p, void* whhT_p,
+                                          int H, int I, int Ipad, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, float* hout, float* c_save,
+                                 void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
+                                 ctcb200_stream_t stream);
+CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
+                                 const void* gates_save, void* dg, void* scratch, int T, int N, int H,
+                                 int batch_tile, ctcb200_stream_t stream);
+
+/* ---- layout / normalisation kernels around the GEMMs (model_ctc.py:29-32 BatchNorm1d over T*N rows,
+ * model_ctc.py:136-140,165-168 fc BatchNorm + LogSoftmax, model_ctc.py:175 the (N,T,F)->(T,N,F) transpose).
+ * cast_transpose: src f32 element (r,c) at src[(r / n_inner)*s_outer + (r % n_inner)*s_inner + c], optional
+ * per-column affine v*scale[c]+shift[c]; writes bf16 dst [R, dst_pitch] and/or bf16 dstT [C, dstT_pitch], where
+ * the transposed column of row r is (r / n_inner)*n_pad + (r % n_inner): the batch axis is padded to n_pad
+ * (a multiple of 8) so that the one-time-step shift of the dW_hh contraction stays 16-byte aligned for TMA.
+ * Pad columns are not written; the caller zero-fills dstT when n_pad != n_inner. */
+CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_outer, int64_t s_inner, int n_inner,
+                                       const float* scale, const float* shift, void* dst, int64_t dst_pitch,
+                                       void* dstT, int64_t dstT_pitch, int n_pad, int R, int C,
+                                       ctcb200_stream_t stream);
+/* dg bf16 [R, 8H] (wih_p column order) -> dgT bf16 [8H, dgT_pitch] with rows in torch gate order (dir, gate, unit) */
+CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64_t dgT_pitch, int n_inner, int n_pad, int R,
+                                     int H, ctcb200_stream_t stream);
+/* ws: 2*C doubles. Batch statistics over R rows of x f32 [R, C]; mean/rstd saved for backward, scale/shift =
+ * the affine to apply (gamma*rstd, beta - mean*gamma*rstd); running stats updated with `momentum`
+ * (unbiased variance), pass NULL to skip. */
+CTCB200_API int ctcb200_bn_train_stats(const float* x, int R, int C, const float* gamma, const float* beta,
+                                       float* running_mean, float* running_var, float momentum, float eps,
+                                       float* mean, float* rstd, float* scale, float* shift, void* ws,
+                                       ctcb200_stream_t stream);
+CTCB200_API int ctcb200_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                                       const float* running_var, float eps, float* scale, float* shift, int C,
+                                       ctcb200_stream_t stream);
+/* dx may alias dy. dgamma / dbeta may be NULL. */
+CTCB200_API int ctcb200_bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                               const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C, void* ws,
+                               ctcb200_stream_t stream);
+CTCB200_API int ctcb200_log_softmax_fwd(const float* x, int64_t x_pitch, float* y, int R, int C,
+                                        ctcb200_stream_t stream);
+CTCB200_API int ctcb200_log_softmax_bwd(const float* g, const float* y, float* dx, int R, int C,
+                                        ctcb200_stream_t stream);
+/* a[e] = mask[e] ? a[e] * inv_keep : 0 (nn.Dropout, model_ctc.py:26,34); mask bytes come from the caller's RNG */
+CTCB200_API int ctcb200_dropout_apply(float* a, const void* mask_u8, float inv_keep, int64_t n,
+                                      ctcb200_stream_t stream);
 
 #ifdef __cplusplus
 }

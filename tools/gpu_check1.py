@@ -68,7 +68,7 @@ def check_ctc(T, N, C, S, seed=0, infeasible=False):
 
 def check_greedy(T, N, C):
     lp = torch.log_softmax(torch.randn(T, N, C) * 3, -1)
-    lp[5, 0, 3] = lp[5, 0, 7] = 1.0  # tie -> first index
+    lp[5, 0, 1] = lp[5, 0, 4] = 1.0  # tie -> first index
     il = torch.linspace(1.0, 0.5, N).mul(T).long()
     idx, labels, ol = ops.greedy_decode(lp.to(dev), il.to(dev), blank=0)
     ref = lp.argmax(-1).t()
@@ -84,9 +84,11 @@ def check_greedy(T, N, C):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    check_greedy(800, 32, 62); check_greedy(50, 3, 5)
-    check_ctc(800, 32, 62, 60); check_ctc(100, 5, 10, 12, seed=1, infeasible=True); check_ctc(64, 4, 40, 100, seed=2)
-    check_ctc(30, 2, 6, 1, seed=3)
+    import traceback
+    for fn, args in [(check_greedy, (800, 32, 62)), (check_greedy, (50, 3, 5)), (check_ctc, (800, 32, 62, 60)),
+                     (check_ctc, (100, 5, 10, 12, 1, True)), (check_ctc, (64, 4, 40, 100, 2)), (check_ctc, (30, 2, 6, 1, 3))]:
+        try: fn(*args)
+        except Exception: traceback.print_exc()
     allok = True
     for st in (True, False):
         allok &= check_gemm(128, 64, 64, 64, structured=st)
