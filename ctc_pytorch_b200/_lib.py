@@ -18,6 +18,7 @@ _CT = {
     "int": ctypes.c_int,
     "int64_t": ctypes.c_int64,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
     "ctcb200_stream_t": ctypes.c_void_p,
 }
 
@@ -48,6 +49,10 @@ def parse_header(path=HEADER_PATH):
     return protos
 
 
+# kernels of ours enqueued by one call of each entry point (memsets not counted)
+KERNELS_PER_CALL = {"ctcb200_greedy_decode": 2, "ctcb200_bn_train_stats": 2, "ctcb200_bn_bwd": 2}
+
+
 class _Lib(object):
     def __init__(self):
         if not os.path.exists(LIB_PATH):
@@ -56,7 +61,7 @@ class _Lib(object):
                 "or `python -m ctc_pytorch_b200._build`; there is no CPU / PyTorch fallback." % LIB_PATH)
         self.dll = ctypes.CDLL(LIB_PATH)
         self.protos = parse_header()
-        self.launches = 0  # number of C-ABI compute calls issued (each enqueues >= 1 kernel of ours)
+        self.launches = 0  # number of our kernels enqueued so far through the C ABI
         for name, (restype, argtypes, _) in self.protos.items():
             fn = getattr(self.dll, name)  # AttributeError here = header/library mismatch
             fn.restype = restype
@@ -68,7 +73,7 @@ class _Lib(object):
     def call(self, name, *args):
         """Invoke an int-returning entry point; raise RuntimeError with the library's message on failure."""
         rc = getattr(self.dll, name)(*args)
-        self.launches += 1
+        self.launches += KERNELS_PER_CALL.get(name, 1)
         if rc != 0:
             raise RuntimeError("%s failed (%d): %s" % (name, rc, self.last_error()))
         if _DEBUG_SYNC:  # development aid: surface asynchronous kernel faults at the call that caused them

@@ -1,0 +1,392 @@
+// K10 — CTC prefix beam search with bigram LM, one thread block per utterance.
+//
+// Replaces the pure-Python search of timit/utils/BeamSearch.py:73-153 (called from
+// BeamDecoder.decode, timit/utils/ctcDecoder.py:181-192) and follows its arithmetic exactly so that the
+// decoded label sequences are identical:
+//   * scores are float64 built from log() of the *float32* probabilities, added in the reference's order
+//     (log p + lm*alpha) + base; log_add(x,y) = max + log(1 + exp(min - max)) with the absorbing
+//     sentinel LOG_ZERO = -99999999.0;
+//   * a frame is skipped when (1 - p_blank) < 0.1 and a repeated label continues from the blank-ending
+//     score when p_{t-1}(blank) < 0.9, both compared in float32;
+//   * the next beam is the first `beam_width` entries of a *stable* descending sort of all candidates of
+//     the previous frame, ties resolved by dictionary insertion order = candidate position
+//     (beam rank major; the "stay" candidate first, then extensions by class index);
+//   * a prefix reached both by staying (y) and by extending its parent (y[:-1] + k) is one entry whose
+//     scores are log-added (each entry has at most these two contributions, and log_add is commutative
+//     bit-for-bit, so the merge order cannot change the result);
+//   * end of utterance: add alpha * bigram(last, </s>), divide the log score by the label count, arg-max.
+// Reference failure modes are reported through `status` so the Python shim can raise the same exception:
+// 1 = IndexError (empty prefix in the final beam), 2 = ValueError (log of a zero probability),
+// 3 = KeyError (unit pair missing from the LM).
+//
+// Device mapping: candidates (beam x class) are spread over the 1024 threads of the block, the candidate
+// keys live in shared memory and are ranked by an in-place bitonic sort, beam records (scores, last label,
+// length, 64-bit prefix hash) are double-buffered in shared memory, prefix equality for the merge is
+// found through a shared-memory hash table and then verified exactly on the stored label sequences.
+#include <cfloat>
+
+#include "common.cuh"
+#include "ctcb200.h"
+
+namespace ctcb200 {
+namespace {
+
+constexpr int BEAM_THREADS = 1024;
+constexpr double LOG_ZERO = -99999999.0;
+
+__device__ __forceinline__ double log_add(double x, double y) {
+    if (x <= LOG_ZERO) return y;
+    if (y <= LOG_ZERO) return x;
+    if (y - x > 0.0) { double t = x; x = y; y = t; }
+    return x + log(1.0 + exp(y - x));
+}
+
+__device__ __forceinline__ unsigned long long mix_hash(unsigned long long h, int k) {
+    unsigned long long z = h ^ (static_cast<unsigned long long>(k) + 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z ? z : 1ULL;
+}
+
+// a sorts before b: larger key first, equal keys by smaller position (stable order of the reference)
+__device__ __forceinline__ bool before(double ka, int pa, double kb, int pb) { return ka > kb || (ka == kb && pa < pb); }
+
+struct BeamRec {
+    double* total; double* nonblank; double* blank;
+    int* last; int* len;
+    unsigned long long* hash; unsigned long long* phash;
+};
+
+struct BeamParams {
+    const float* probs;       // [N, T, C] float32 probabilities
+    const int64_t* lengths;   // [N]
+    const double* lm;         // [(C+1), (C+1)]
+    double lm_alpha;
+    int T, N, C, W, blank, P2;  // P2 = power of two >= W*C (sort capacity)
+    double* pool_nb;          // [N, W*C]
+    double* pool_bl;          // [N, W*C]
+    int* pool_parent;         // [N, W*C]
+    int* pool_label;          // [N, W*C]
+    int* seq;                 // [N, 2, W, T]
+    int* out_labels;          // [N, T]
+    int* out_len;             // [N]
+    int* status;              // [N]
+};
+
+__device__ void bitonic_sort(double* key, int* pos, int n2) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double ka = key[i], kb = key[ixj];
+                    const int pa = pos[i], pb = pos[ixj];
+                    const bool up = (i & k) == 0;  // this run sorts "best first"
+                    const bool swap = up ? before(kb, pb, ka, pa) : before(ka, pa, kb, pb);
+                    if (swap) { key[i] = kb; key[ixj] = ka; pos[i] = pb; pos[ixj] = pa; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int C = p.C, W = p.W, T = p.T, blank = p.blank, P2 = p.P2;
+    const int PC = W * C;
+    // ---- shared memory carve-up ----
+    double* skey = reinterpret_cast<double*>(smem_raw);
+    double* rec_d = skey + P2;                       // 2 buffers x 3 arrays x W doubles
+    double* logp = rec_d + 6 * W;                    // C
+    unsigned long long* rec_h = reinterpret_cast<unsigned long long*>(logp + C);  // 2 x 2 x W
+    int HT = 1;
+    while (HT < 2 * W) HT <<= 1;
+    unsigned long long* ht_key = rec_h + 4 * W;      // HT
+    int* spos = reinterpret_cast<int*>(ht_key + HT); // P2
+    int* rec_i = spos + P2;                          // 2 x 2 x W
+    int* ht_val = rec_i + 4 * W;                     // HT
+    int* merged_with = ht_val + HT;                  // W
+    float* prow = reinterpret_cast<float*>(merged_with + W);  // C
+    __shared__ int s_flags[4];                       // [0] nbeams, [1] status, [2] processed frames, [3] skip
+
+    auto rec = [&](int b) {
+        BeamRec r;
+        r.total = rec_d + b * 3 * W; r.nonblank = r.total + W; r.blank = r.nonblank + W;
+        r.last = rec_i + b * 2 * W; r.len = r.last + W;
+        r.hash = rec_h + b * 2 * W; r.phash = r.hash + W;
+        return r;
+    };
+
+    const float* probs_n = p.probs + static_cast<size_t>(n) * T * C;
+    double* pool_nb = p.pool_nb + static_cast<size_t>(n) * PC;
+    double* pool_bl = p.pool_bl + static_cast<size_t>(n) * PC;
+    int* pool_parent = p.pool_parent + static_cast<size_t>(n) * PC;
+    int* pool_label = p.pool_label + static_cast<size_t>(n) * PC;
+    int* seq_base = p.seq + static_cast<size_t>(n) * 2 * W * T;
+    int len_n = static_cast<int>(p.lengths[n]);
+    if (len_n > T) len_n = T;
+
+    // root beam: the empty prefix with prBlank = prTotal = 0
+    int cur = 0;  // index of the beam-record buffer that holds the current beams
+    if (tid == 0) {
+        BeamRec r = rec(0);
+        r.total[0] = 0.0; r.nonblank[0] = LOG_ZERO; r.blank[0] = 0.0;
+        r.last[0] = -1; r.len[0] = 0; r.hash[0] = 0x243F6A8885A308D3ULL; r.phash[0] = 0ULL;
+        s_flags[0] = 1; s_flags[1] = 0; s_flags[2] = 0;
+    }
+    __syncthreads();
+    bool have_pool = false;  // candidates of an earlier frame are waiting to be ranked
+    int pool_n = 0;
+
+    // Rank the waiting candidates and turn the best W into the current beam records (+ their label sequences).
+    auto select_beams = [&]() {
+        for (int i = pool_n + tid; i < P2; i += blockDim.x) { skey[i] = -INFINITY; spos[i] = 0x7fffffff; }
+        __syncthreads();
+        bitonic_sort(skey, spos, P2);
+        int live = 0;
+        // number of live entries among the first W (dead ones carry -inf and sort last)
+        if (tid == 0) {
+            int c = 0;
+            const int lim = W < pool_n ? W : pool_n;
+            while (c < lim && skey[c] != -INFINITY) ++c;
+            s_flags[0] = c;
+        }
+        __syncthreads();
+        live = s_flags[0];
+        const BeamRec prev = rec(cur), nxt = rec(cur ^ 1);
+        const int frames_done = s_flags[2];
+        const int* seq_old = seq_base + static_cast<size_t>(frames_done & 1) * W * T;
+        int* seq_new = seq_base + static_cast<size_t>((frames_done + 1) & 1) * W * T;
+        for (int r = tid; r < live; r += blockDim.x) {
+            const int pos = spos[r];
+            const int parent = pool_parent[pos], label = pool_label[pos];
+            nxt.total[r] = skey[r];
+            nxt.nonblank[r] = pool_nb[pos];
+            nxt.blank[r] = pool_bl[pos];
+            nxt.len[r] = prev.len[parent] + (label >= 0 ? 1 : 0);
+            nxt.last[r] = label >= 0 ? label : prev.last[parent];
+            nxt.hash[r] = label >= 0 ? mix_hash(prev.hash[parent], label) : prev.hash[parent];
+            nxt.phash[r] = label >= 0 ? prev.hash[parent] : prev.phash[parent];
+        }
+        // label sequences: one warp per selected beam copies its parent's labels and appends
+        const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+        for (int r = warp; r < live; r += nwarps) {
+            const int pos = spos[r];
+            const int parent = pool_parent[pos], label = pool_label[pos];
+            const int plen = prev.len[parent];
+            for (int e = lane; e < plen; e += 32) seq_new[static_cast<size_t>(r) * T + e] = seq_old[static_cast<size_t>(parent) * T + e];
+            if (lane == 0 && label >= 0) seq_new[static_cast<size_t>(r) * T + plen] = label;
+        }
+        __syncthreads();
+        cur ^= 1;
+        if (tid == 0) s_flags[2] = frames_done + 1;
+        __syncthreads();
+    };
+
+    for (int t = 0; t < len_n; ++t) {
+        for (int c = tid; c < C; c += blockDim.x) prow[c] = probs_n[static_cast<size_t>(t) * C + c];
+        __syncthreads();
+        if ((1.0f - prow[blank]) < 0.1f) { __syncthreads(); continue; }  // near-certain blank: frame skipped
+        if (have_pool) select_beams();
+        const int nbeams = s_flags[0];
+        const BeamRec b = rec(cur);
+        const int* seq_cur = seq_base + static_cast<size_t>(s_flags[2] & 1) * W * T;
+        for (int c = tid; c < C; c += blockDim.x) {
+            const float pv = prow[c];
+            if (pv == 0.0f) s_flags[1] = 2;  // math.log(0.0) -> ValueError in the reference
+            logp[c] = log(static_cast<double>(pv));
+        }
+        for (int i = tid; i < HT; i += blockDim.x) { ht_key[i] = 0ULL; ht_val[i] = -1; }
+        for (int i = tid; i < nbeams; i += blockDim.x) merged_with[i] = -1;
+        __syncthreads();
+        for (int r = tid; r < nbeams; r += blockDim.x) {
+            const unsigned long long h = b.hash[r];
+            unsigned int slot = static_cast<unsigned int>(h) & (HT - 1);
+            while (true) {
+                const unsigned long long old = atomicCAS(&ht_key[slot], 0ULL, h);
+                if (old == 0ULL) { ht_val[slot] = r; break; }
+                slot = (slot + 1) & (HT - 1);  // distinct prefixes with equal hash simply occupy two slots
+            }
+        }
+        __syncthreads();
+        const int tprev = (t - 1 + T) % T;
+        const bool prev_blank_lt = probs_n[static_cast<size_t>(tprev) * C + blank] < 0.9f;
+        pool_n = nbeams * C;
+        // pass 1: extensions
+        for (int pos = tid; pos < pool_n; pos += blockDim.x) {
+            const int i = pos / C, slot = pos - i * C;
+            if (slot == 0) continue;
+            const int k = (slot - 1 < blank) ? slot - 1 : slot;
+            const int last_i = b.last[i], len_i = b.len[i];
+            const double lmv = p.lm[static_cast<size_t>(len_i ? last_i : C) * (C + 1) + k];
+            if (lmv != lmv) s_flags[1] = 3;  // unit pair unknown to the LM -> KeyError in the reference
+            const double lm_term = lmv * p.lm_alpha;
+            const double base = (len_i && last_i == k && prev_blank_lt) ? b.blank[i] : b.total[i];
+            const double score = logp[k] + lm_term + base;
+            skey[pos] = score;
+            spos[pos] = pos;
+            pool_nb[pos] = score;
+            pool_bl[pos] = LOG_ZERO;
+            pool_parent[pos] = i;
+            pool_label[pos] = k;
+            // does y_i + (k,) coincide with a beam prefix y_j (which contributes its own "stay" entry)?
+            const unsigned long long h = mix_hash(b.hash[i], k);
+            unsigned int hs = static_cast<unsigned int>(h) & (HT - 1);
+            while (ht_key[hs] != 0ULL) {
+                if (ht_key[hs] == h) {
+                    const int j = ht_val[hs];
+                    if (j >= 0 && b.len[j] == len_i + 1 && b.last[j] == k && b.phash[j] == b.hash[i]) {
+                        bool same = true;
+                        for (int e = 0; e < len_i; ++e)
+                            if (seq_cur[static_cast<size_t>(j) * T + e] != seq_cur[static_cast<size_t>(i) * T + e]) { same = false; break; }
+                        if (same) { merged_with[j] = pos; break; }
+                    }
+                }
+                hs = (hs + 1) & (HT - 1);
+            }
+        }
+        __syncthreads();
+        // pass 2: stays (and the merge with a coinciding extension)
+        for (int r = tid; r < nbeams; r += blockDim.x) {
+            double nb = LOG_ZERO;
+            if (b.len[r]) nb = b.nonblank[r] + logp[b.last[r]];
+            const double bl = b.total[r] + logp[blank];
+            double tot = log_add(bl, nb);
+            const int ps = r * C, pe = merged_with[r];
+            int home = ps;
+            if (pe >= 0) {
+                const double score = skey[pe];
+                nb = log_add(nb, score);
+                tot = log_add(tot, score);
+                home = pe < ps ? pe : ps;                 // the entry keeps its first insertion position
+                const int dead = pe < ps ? ps : pe;
+                skey[dead] = -INFINITY;
+                spos[dead] = dead;
+            }
+            skey[home] = tot;
+            spos[home] = home;
+            pool_nb[home] = nb;
+            pool_bl[home] = bl;
+            pool_parent[home] = r;
+            pool_label[home] = -1;
+        }
+        have_pool = true;
+        __syncthreads();
+        if (s_flags[1]) break;
+    }
+
+    int status = s_flags[1];
+    if (status == 0) {
+        if (have_pool) select_beams();
+        const int nbeams = s_flags[0];
+        const BeamRec b = rec(cur);
+        // final LM step over the best W prefixes, length normalisation, arg-max (first best wins)
+        for (int r = tid; r < nbeams; r += blockDim.x) {
+            if (b.len[r] == 0) { s_flags[1] = 1; skey[r] = -INFINITY; spos[r] = r; continue; }  // classes[y[-1]] on ()
+            const double lmv = p.lm[static_cast<size_t>(b.last[r]) * (C + 1) + C];
+            if (lmv != lmv) s_flags[1] = 3;
+            const double eos = b.total[r] + lmv * p.lm_alpha;
+            skey[r] = eos * (1.0 / static_cast<double>(b.len[r]));
+            spos[r] = r;
+        }
+        __syncthreads();
+        status = s_flags[1];
+        if (status == 0) {
+            if (tid == 0) {
+                int best = 0;
+                for (int r = 1; r < nbeams; ++r)
+                    if (skey[r] > skey[best]) best = r;
+                s_flags[3] = best;
+            }
+            __syncthreads();
+            const int best = s_flags[3];
+            const int* seq_cur = seq_base + static_cast<size_t>(s_flags[2] & 1) * W * T;
+            const int blen = b.len[best];
+            for (int e = tid; e < blen; e += blockDim.x) p.out_labels[static_cast<size_t>(n) * T + e] = seq_cur[static_cast<size_t>(best) * T + e];
+            if (tid == 0) p.out_len[n] = blen;
+        }
+    }
+    if (tid == 0) {
+        p.status[n] = status;
+        if (status) p.out_len[n] = 0;
+    }
+}
+
+// out[n, t, c] = expf(in[t, n, c]) — the torch.exp(probs.transpose(0,1)) of ctcDecoder.py:189-190
+__global__ void exp_transpose_kernel(const float* __restrict__ lp, float* __restrict__ out, int T, int N, int C) {
+    const long long total = static_cast<long long>(T) * N * C;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % C);
+        const long long tn = e / C;
+        const int nn = static_cast<int>(tn % N), t = static_cast<int>(tn / N);
+        out[(static_cast<long long>(nn) * T + t) * C + c] = expf(lp[e]);
+    }
+}
+
+size_t beam_smem_bytes(int W, int C, int P2) {
+    int HT = 1;
+    while (HT < 2 * W) HT <<= 1;
+    size_t b = 0;
+    b += sizeof(double) * (static_cast<size_t>(P2) + 6 * W + C);
+    b += sizeof(unsigned long long) * (4 * static_cast<size_t>(W) + HT);
+    b += sizeof(int) * (static_cast<size_t>(P2) + 4 * W + HT + W);
+    b += sizeof(float) * C;
+    return b + 16;
+}
+
+}  // namespace
+}  // namespace ctcb200
+
+using namespace ctcb200;
+
+extern "C" CTCB200_API int64_t ctcb200_beam_workspace_bytes(int T, int N, int C, int beam_width) {
+    const int64_t PC = static_cast<int64_t>(beam_width) * C;
+    return N * (PC * (8 + 8 + 4 + 4) + static_cast<int64_t>(2) * beam_width * T * 4) + 256;
+}
+
+extern "C" CTCB200_API int ctcb200_exp_transpose(const float* log_probs_tnc, float* probs_ntc, int T, int N, int C,
+                                                 ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(T > 0 && N > 0 && C > 0, "exp_transpose: empty shape");
+    long long total = static_cast<long long>(T) * N * C;
+    long long blocks = (total + 1023) / 1024;
+    long long cap = static_cast<long long>(device_sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    exp_transpose_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(log_probs_tnc, probs_ntc, T, N, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_beam_search(const float* probs_ntc, const int64_t* lengths, const double* lm_table,
+                                               double lm_alpha, int T, int N, int C, int beam_width, int blank,
+                                               void* workspace, int* out_labels, int* out_lengths, int* status,
+                                               ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(T > 0 && N > 0 && C > 1 && beam_width > 0, "beam_search: bad shape T=%d N=%d C=%d W=%d", T, N, C, beam_width);
+    CTCB_REQUIRE(blank >= 0 && blank < C, "beam_search: blank %d out of range", blank);
+    CTCB_REQUIRE(lm_table != nullptr, "beam_search: a bigram LM table is required (the reference cannot run without one)");
+    int P2 = 1;
+    while (P2 < beam_width * C) P2 <<= 1;
+    const size_t smem = beam_smem_bytes(beam_width, C, P2);
+    CTCB_REQUIRE(smem <= 227 * 1024, "beam_search: beam_width*classes = %d needs %zu B of shared memory (max 227 KB)",
+                 beam_width * C, smem);
+    CTCB_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    BeamParams p;
+    p.probs = probs_ntc; p.lengths = lengths; p.lm = lm_table; p.lm_alpha = lm_alpha;
+    p.T = T; p.N = N; p.C = C; p.W = beam_width; p.blank = blank; p.P2 = P2;
+    uint8_t* w = static_cast<uint8_t*>(workspace);
+    const size_t PC = static_cast<size_t>(beam_width) * C;
+    p.pool_nb = reinterpret_cast<double*>(w); w += sizeof(double) * N * PC;
+    p.pool_bl = reinterpret_cast<double*>(w); w += sizeof(double) * N * PC;
+    p.pool_parent = reinterpret_cast<int*>(w); w += sizeof(int) * N * PC;
+    p.pool_label = reinterpret_cast<int*>(w); w += sizeof(int) * N * PC;
+    p.seq = reinterpret_cast<int*>(w);
+    p.out_labels = out_labels; p.out_len = out_lengths; p.status = status;
+    beam_search_kernel<<<N, BEAM_THREADS, smem, stream>>>(p);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}

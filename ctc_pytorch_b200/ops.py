@@ -52,3 +52,45 @@ def greedy_decode(log_probs, lengths, blank=0):
     _lib.lib().call("ctcb200_greedy_decode", _lib.ptr(lp), _lib.ptr(lens), T, N, C, int(blank), _lib.ptr(idx),
                     _lib.ptr(labels), _lib.ptr(out_len), _lib.stream())
     return idx, labels, out_len
+
+
+_BEAM_ERRORS = {1: (IndexError, "tuple index out of range (the empty prefix reached the final LM step)"),
+                2: (ValueError, "math domain error (log of a zero probability)"),
+                3: (KeyError, "unit missing from the language model")}
+
+
+def beam_search(tensor, lengths, lm_table, beam_width, lm_alpha, blank=0, input_is_log=True):
+    """CTC prefix beam search with a dense bigram table. `tensor` is [T,N,C] log-probs (input_is_log) or
+    [N,T,C] float32 probabilities. Returns a list of label lists; raises the exception the reference's
+    ctcBeamSearch.decode would raise for the same utterance (IndexError / ValueError / KeyError)."""
+    _lib.require_cuda(tensor)
+    L = _lib.lib()
+    dev = tensor.device
+    if input_is_log:
+        lp = tensor.detach().float().contiguous()
+        T, N, C = lp.shape
+        probs = torch.empty((N, T, C), dtype=torch.float32, device=dev)
+        L.call("ctcb200_exp_transpose", _lib.ptr(lp), _lib.ptr(probs), T, N, C, _lib.stream())
+    else:
+        probs = tensor.detach().float().contiguous()
+        N, T, C = probs.shape
+    if torch.is_tensor(lengths):
+        lens = lengths.to(device=dev, dtype=torch.int64).contiguous()
+    else:
+        lens = torch.as_tensor(list(lengths), dtype=torch.int64, device=dev)
+    lm_table = lm_table.to(device=dev, dtype=torch.float64).contiguous()
+    assert lm_table.shape == (C + 1, C + 1)
+    ws = torch.empty(L.dll.ctcb200_beam_workspace_bytes(T, N, C, int(beam_width)), dtype=torch.uint8, device=dev)
+    out = torch.zeros((N, T), dtype=torch.int32, device=dev)
+    out_len = torch.zeros((N,), dtype=torch.int32, device=dev)
+    status = torch.zeros((N,), dtype=torch.int32, device=dev)
+    L.call("ctcb200_beam_search", _lib.ptr(probs), _lib.ptr(lens), _lib.ptr(lm_table), float(lm_alpha), T, N, C,
+           int(beam_width), int(blank), _lib.ptr(ws), _lib.ptr(out), _lib.ptr(out_len), _lib.ptr(status), _lib.stream())
+    st = status.cpu().tolist()
+    for n, code in enumerate(st):  # the reference decodes utterances in order and stops at the first failure
+        if code:
+            exc, msg = _BEAM_ERRORS[code]
+            raise exc(msg)
+    out = out.cpu().numpy()
+    out_len = out_len.cpu().numpy()
+    return [out[n, :out_len[n]].tolist() for n in range(N)]

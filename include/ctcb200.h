@@ -134,6 +134,21 @@ CTCB200_API int ctcb200_log_softmax_bwd(const float* g, const float* y, float* d
 CTCB200_API int ctcb200_dropout_apply(float* a, const void* mask_u8, float inv_keep, int64_t n,
                                       ctcb200_stream_t stream);
 
+/* ---- beam decode: replaces ctcBeamSearch.decode, timit/utils/BeamSearch.py:73-153 (called by
+ * BeamDecoder.decode, timit/utils/ctcDecoder.py:181-192) with LanguageModel.get_bi_prob
+ * (timit/utils/NgramLM.py:65-78) flattened into lm_table f64 [(C+1),(C+1)] (row = previous unit, row C =
+ * sentence start; column C = sentence end; NaN = pair unknown to the LM).
+ * probs_ntc f32 [N,T,C] are probabilities (ctcb200_exp_transpose produces them from [T,N,C] log-probs like
+ * ctcDecoder.py:189-190). Outputs: out_labels int32 [N,T] + out_lengths [N]; status [N]: 0 ok, 1 = the
+ * reference would raise IndexError (empty prefix reaches the final LM step), 2 = ValueError (log of a zero
+ * probability), 3 = KeyError (unit missing from the LM). workspace: ctcb200_beam_workspace_bytes(...) bytes. */
+CTCB200_API int64_t ctcb200_beam_workspace_bytes(int T, int N, int C, int beam_width);
+CTCB200_API int ctcb200_exp_transpose(const float* log_probs_tnc, float* probs_ntc, int T, int N, int C,
+                                      ctcb200_stream_t stream);
+CTCB200_API int ctcb200_beam_search(const float* probs_ntc, const int64_t* lengths, const double* lm_table,
+                                    double lm_alpha, int T, int N, int C, int beam_width, int blank, void* workspace,
+                                    int* out_labels, int* out_lengths, int* status, ctcb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

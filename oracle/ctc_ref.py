@@ -52,8 +52,8 @@ def ctc_alpha_beta(lp_n, target, T_n, blank=0):
         la[0, 1] = lp[0, ext[1]]
     for t in range(1, T_n):
         prev = la[t - 1]
-        p1 = np.concatenate(([NEG_INF], prev[:-1]))
-        p2 = np.concatenate(([NEG_INF, NEG_INF], prev[:-2]))
+        p1 = np.concatenate(([NEG_INF], prev))[:L]
+        p2 = np.concatenate(([NEG_INF, NEG_INF], prev))[:L]
         p2 = np.where(skip, p2, NEG_INF)
         la[t] = _logsumexp3(prev, p1, p2) + lp[t, ext]
     tail = la[T_n - 1, L - 1]
@@ -63,11 +63,11 @@ def ctc_alpha_beta(lp_n, target, T_n, blank=0):
     lb[T_n - 1, L - 1] = lp[T_n - 1, blank]
     if L > 1:
         lb[T_n - 1, L - 2] = lp[T_n - 1, ext[L - 2]]
-    skip_out = np.concatenate((skip[2:], [False, False]))  # transition s -> s+2 allowed
+    skip_out = np.concatenate((skip, [False, False]))[2:L + 2]  # transition s -> s+2 allowed
     for t in range(T_n - 2, -1, -1):
         nxt = lb[t + 1]
-        n1 = np.concatenate((nxt[1:], [NEG_INF]))
-        n2 = np.concatenate((nxt[2:], [NEG_INF, NEG_INF]))
+        n1 = np.concatenate((nxt, [NEG_INF]))[1:L + 1]
+        n2 = np.concatenate((nxt, [NEG_INF, NEG_INF]))[2:L + 2]
         n2 = np.where(skip_out, n2, NEG_INF)
         lb[t] = _logsumexp3(nxt, n1, n2) + lp[t, ext]
     return nll, la, lb

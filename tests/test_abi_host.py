@@ -1,0 +1,138 @@
+"""CPU suite: the C-ABI library loads and exports exactly what include/ctcb200.h declares, the host-side mirrors of
+the reference's classes behave like the reference, and the product path refuses to run without CUDA."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from ctc_pytorch_b200 import _build, _lib
+from ctc_pytorch_b200.decoder import Decoder, collapse_frames, edit_distance
+from ctc_pytorch_b200.lm import LanguageModel
+from ctc_pytorch_b200.model import CTC_Model
+from oracle import decode_ref, ref_shim
+
+HAVE_REF = ref_shim.available()
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    path = _build.build()
+    assert os.path.exists(path)
+    return path
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    protos = _lib.parse_header()
+    assert len(protos) >= 20
+    dll = ctypes.CDLL(built_lib)  # must load without a GPU driver (no libcuda link dependency)
+    for name in protos:
+        assert hasattr(dll, name), "include/ctcb200.h declares %s but libctcb200.so does not export it" % name
+    dll.ctcb200_version.restype = ctypes.c_int
+    assert dll.ctcb200_version() >= 100
+    dll.ctcb200_last_error.restype = ctypes.c_char_p
+    assert isinstance(dll.ctcb200_last_error(), bytes)
+
+
+def test_no_undeclared_exports(built_lib):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    declared = set(_lib.parse_header())
+    assert {e for e in exported if e.startswith("ctcb200_")} == declared
+
+
+def test_workspace_size_queries_need_no_gpu(built_lib):
+    L = _lib.lib()
+    assert L.dll.ctcb200_ctc_workspace_floats(800, 32, 60) == 32 * 800 * 4 * 32
+    assert L.dll.ctcb200_lstm_scratch_bytes(32, 512) > 0
+    assert L.dll.ctcb200_beam_workspace_bytes(800, 32, 62, 100) > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_path_fails_loudly_without_cuda():
+    from ctc_pytorch_b200.loss import CTCLoss
+    from ctc_pytorch_b200.decoder import GreedyDecoder
+    lp = torch.log_softmax(torch.randn(5, 2, 4), -1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        CTCLoss(reduction="sum")(lp, torch.ones(2, 2, dtype=torch.long), [5, 5], [2, 2])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GreedyDecoder({0: "_", 1: "a", 2: "b", 3: "c"}, space_idx=-1).decode(lp, [5, 5])
+    m = CTC_Model(rnn_param={"rnn_input_size": 8, "rnn_hidden_size": 128, "rnn_layers": 1, "rnn_type": nn.LSTM,
+                             "bidirectional": True, "batch_norm": False}, num_class=4, drop_out=0.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(2, 5, 8))
+
+
+def test_model_surface_and_state_dict_keys(golden_dir):
+    with pytest.raises(ValueError):
+        CTC_Model(rnn_param=None)
+    for name in ("rnn_bn", "rnn_nobn", "cnn_rnn"):
+        meta = json.load(open(os.path.join(golden_dir, "model_%s.json" % name)))
+        from oracle.make_golden import model_args
+        cfg = meta["cfg"]
+        torch.manual_seed(cfg["seed"])
+        m = CTC_Model(**model_args(cfg))
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(meta["checksum"].keys())
+        for k, v in sd.items():  # same creation order as the reference => identical initial weights under the seed
+            assert abs(float(v.double().abs().sum()) - meta["checksum"][k]) <= 1e-9 * max(1.0, meta["checksum"][k]), k
+        pkg = CTC_Model.save_package(m, epoch={"n_feats": 40})
+        assert set(pkg) == {"rnn_param", "add_cnn", "cnn_param", "num_class", "_drop_out", "state_dict", "epoch"}
+
+
+def test_compute_wer_matches_golden(golden_dir):
+    m = CTC_Model(rnn_param={"rnn_input_size": 8, "rnn_hidden_size": 128, "rnn_layers": 1, "rnn_type": nn.LSTM,
+                             "bidirectional": True, "batch_norm": False}, num_class=4, drop_out=0.0)
+    for name in ("rnn_bn", "rnn_nobn", "cnn_rnn"):
+        g = np.load(os.path.join(golden_dir, "model_%s.npz" % name))
+        errs, toks = m.compute_wer(g["argmax"].T, g["input_lengths"], g["targets"], g["target_lengths"])
+        assert (errs, toks) == (int(g["wer_errs"]), int(g["wer_toks"]))
+
+
+def test_decoder_host_helpers():
+    assert collapse_frames([3, 3, 0, 3, 1, 1, 0]) == [3, 3, 1]
+    assert edit_distance("abc", "") == 3 and edit_distance([1, 2, 3], [1, 3]) == 1
+    for a, b in (("kitten", "sitting"), ("", "x"), ("abcd", "abcd"), ([1, 2, 3, 4], [4, 3, 2, 1])):
+        assert edit_distance(a, b) == decode_ref.levenshtein(a, b)
+    d = Decoder({0: "_", 1: "a", 2: "b", 3: " "}, space_idx=-1, blank_index=0)
+    assert d._process_string(["a", "a", "_", "b"], remove_rep=True) == " a b"
+    assert d._process_string(["a", "a", "_", "b"], remove_rep=False) == " a a b"
+    assert d._convert_to_strings([[1, 2, 1, 0, 3]]) == [["a", "b", "a", "_", " "]]
+    d2 = Decoder({0: "_", 1: "a", 2: "b", 3: " "}, space_idx=3, blank_index=0)
+    assert d2._process_string(list("ab a"), remove_rep=False) == "ab a"
+    assert d.wer("a b c", "a c") == 1 and d.cer("abc", "abd") == 1
+    assert d._unflatten_targets([1, 2, 3, 4, 5], [2, 3]) == [[1, 2], [3, 4, 5]]
+
+
+def test_language_model_matches_oracle(golden_dir):
+    arpa = os.path.join(golden_dir, "lm_c8.arpa")
+    lm, olm = LanguageModel(arpa_file=arpa), decode_ref.BigramLM(arpa)
+    units = ["UNK", "a", "b", "c", "d", "e", "f"]
+    for w1 in units + [""]:
+        for w2 in units + [""]:
+            assert lm.get_bi_prob(w1, w2) == olm.bigram(w1, w2)
+    with pytest.raises(KeyError):
+        lm.get_bi_prob("nosuchunit", "a")
+    classes = ["blank"] + units
+    tab = lm.dense_table(classes)
+    np.testing.assert_array_equal(tab, olm.table(classes))
+    assert lm.score_bg("a b") == lm.get_bi_prob("<s>", "a") + lm.get_bi_prob("a", "b") + lm.get_bi_prob("b", "</s>")
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_host_mirrors_match_reference_live(golden_dir):
+    ref = ref_shim.load()
+    int2char = {0: "_", 1: "a", 2: "b", 3: "c"}
+    mine, theirs = Decoder(int2char, space_idx=-1, blank_index=0), ref.Decoder(int2char, space_idx=-1, blank_index=0)
+    for seq in (["a", "a", "_", "b", "b", "c"], ["_", "_"], ["c"]):
+        for rr in (True, False):
+            assert mine._process_string(seq, rr) == theirs._process_string(seq, rr)
+    assert mine.wer("a b c d", "b c e") == theirs.wer("a b c d", "b c e")
+    assert mine.cer(" a b", " b") == theirs.cer(" a b", " b")
+    arpa = os.path.join(golden_dir, "lm_c62.arpa")
+    a, b = LanguageModel(arpa_file=arpa), ref.LanguageModel(arpa_file=arpa)
+    assert a.unigram == b.unigram and a.bigram == b.bigram
