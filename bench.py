@@ -106,6 +106,13 @@ def rnn_param(cfg):
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
+def cpu_threads():
+    """Threads for the CPU arm. Measured on the GPU box's host (128 logical CPUs, profiles/cpu_thread_scaling_r1.txt):
+    the reference's nn.LSTM step peaks at 16 intra-op threads (3.3 utt/s) and gets slower beyond (1.6 at 32, 0.6 at
+    64), so 16 is "all the threads it can use"."""
+    return max(1, min(16, os.cpu_count() or 1))
+
+
 def cpu_reference_step_rate(cfg, n_utts, steps, warmup, threads):
     """The reference's CPU implementation of the path (nn.LSTM / BatchNorm1d / Linear / LogSoftmax / nn.CTCLoss /
     arg-max + collapse, composed as timit/models/model_ctc.py and train_ctc.py:44-65 compose them), restated in
@@ -144,7 +151,7 @@ def cpu_reference_step_rate(cfg, n_utts, steps, warmup, threads):
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     n_utts = 2
     warm = min(args.warmup, 1)
     rate, sec = cpu_reference_step_rate(cfg, n_utts, max(1, args.steps), warm, cores)
@@ -314,7 +321,7 @@ def run_ours(args, cfg, rank, world):
             extra[k]["frac"] = extra[k]["achieved"] / extra[k]["peak"]
 
     # ---- CPU baseline on the host cores (bounded sample) ----
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     cpu_rate, cpu_sec = cpu_reference_step_rate(cfg, 2, 2, 1, cores)
 
     total_utts = N * world * args.steps

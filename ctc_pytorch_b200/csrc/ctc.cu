@@ -19,6 +19,7 @@ namespace ctcb200 {
 namespace {
 
 constexpr int WARPS_PER_BLOCK = 4;
+constexpr int RENORM = 8;  // alpha / beta rows are renormalised every RENORM frames
 #define NEG_INF (-INFINITY)
 
 __device__ __forceinline__ float lse2(float a, float b) {
@@ -77,19 +78,25 @@ template <int KS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ctc_alpha_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
                  const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
-                 float* __restrict__ alpha_ws, float* __restrict__ nll, int T, int N, int C, int blank) {
+                 float* __restrict__ alpha_ws, double* __restrict__ offs_ws, float* __restrict__ nll, int T, int N,
+                 int C, int blank) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (n >= N) return;
     float* rowbuf = smem + warp * 2 * C;  // two rows
+    // offs[g] = total log-scale removed from alpha up to and including renormalisation group g; offs[G] = exact nll
+    double* offs = offs_ws + static_cast<size_t>(n) * (T / RENORM + 2);
 
     const int S = static_cast<int>(tgt_len[n]);
     const int L = 2 * S + 1;
     int Tn = static_cast<int>(in_len[n]);
     if (Tn > T) Tn = T;
     if (Tn <= 0) {
-        if (lane == 0) nll[n] = (S == 0) ? 0.0f : INFINITY;
+        if (lane == 0) {
+            nll[n] = (S == 0) ? 0.0f : INFINITY;
+            offs[T / RENORM + 1] = (S == 0) ? 0.0 : static_cast<double>(INFINITY);
+        }
         return;
     }
     LaneStates<KS> st;
@@ -101,6 +108,7 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
 
     prefetch_row(rowbuf, lp_n, C, lane);
     float a[KS];
+    double scale_acc = 0.0;  // log-scale removed so far (kept in double: the stored alphas stay O(100))
     for (int t = 0; t < Tn; ++t) {
         float* cur = rowbuf + (t & 1) * C;
         cp_async_wait_all();
@@ -132,6 +140,20 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
 #pragma unroll
             for (int j = 0; j < KS; ++j) a[j] = nw[j];
         }
+        if ((t % RENORM) == RENORM - 1 || t == Tn - 1) {
+            // renormalise: subtract the row maximum so float32 keeps ~1e-6 absolute resolution however long the utterance
+            float m = NEG_INF;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (m > NEG_INF) {
+#pragma unroll
+                for (int j = 0; j < KS; ++j) a[j] -= m;
+                scale_acc += static_cast<double>(m);
+            }
+            if (lane == 0) offs[t / RENORM] = scale_acc;
+        }
 #pragma unroll
         for (int j = 0; j < KS; ++j) aws[static_cast<size_t>(t) * (KS * 32) + j * 32 + lane] = a[j];
     }
@@ -144,7 +166,11 @@ ctc_alpha_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) loc = lse2(loc, __shfl_xor_sync(0xffffffffu, loc, o));
-    if (lane == 0) nll[n] = -loc;
+    if (lane == 0) {
+        const double nll_d = -(static_cast<double>(loc) + scale_acc);
+        nll[n] = static_cast<float>(nll_d);
+        offs[T / RENORM + 1] = nll_d;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -154,7 +180,7 @@ template <int KS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
                      const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
-                     const float* __restrict__ alpha_ws, const float* __restrict__ nll,
+                     const float* __restrict__ alpha_ws, const double* __restrict__ offs_ws,
                      const float* __restrict__ grad_nll, float grad_scale, float* __restrict__ grad, int T, int N,
                      int C, int blank) {
     extern __shared__ float smem[];
@@ -180,7 +206,9 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
     load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
     const float* lp_n = lp + static_cast<size_t>(n) * C;
     const float* aws = alpha_ws + static_cast<size_t>(n) * T * (KS * 32);
-    const float nll_n = nll[n];
+    const double* offs = offs_ws + static_cast<size_t>(n) * (T / RENORM + 2);
+    const double nll_d = offs[T / RENORM + 1];
+    double scale_acc = 0.0;  // log-scale removed from beta so far
     const float gscale = grad_scale * (grad_nll ? grad_nll[n] : 1.0f);
 
     for (int c = lane; c < C; c += 32) occ[c] = 0.0f;
@@ -222,13 +250,31 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
 #pragma unroll
             for (int j = 0; j < KS; ++j) b[j] = nw[j];
         }
+        if ((t % RENORM) == 0) {
+            float m = NEG_INF;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) m = fmaxf(m, b[j]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (m > NEG_INF) {
+#pragma unroll
+                for (int j = 0; j < KS; ++j) b[j] -= m;
+                scale_acc += static_cast<double>(m);
+            }
+        }
+        // alpha_t was stored with the scale of its own group if t closes the group (or the utterance), else of the
+        // previous group; combine all log-scales with the exact nll in double, then drop to float once
+        const bool closes = ((t % RENORM) == RENORM - 1) || (t == Tn - 1);
+        const int ga = closes ? (t / RENORM) : (t / RENORM - 1);
+        const double a_off = ga >= 0 ? offs[ga] : 0.0;
+        const float shift = static_cast<float>(a_off + scale_acc + nll_d);
         // state posteriors, accumulated per class in the linear domain
         float blank_sum = 0.0f;
 #pragma unroll
         for (int j = 0; j < KS; ++j) {
             if (st.valid[j]) {
                 float lpv = cur[st.label[j]];
-                float g = expf(al[j] + b[j] + nll_n - lpv);
+                float g = expf((al[j] + b[j] - lpv) + shift);
                 int s = lane * KS + j;
                 if (s & 1) atomicAdd(&occ[st.label[j]], g);
                 else blank_sum += g;
@@ -262,9 +308,12 @@ int ks_for(int max_target_len) {
 
 using namespace ctcb200;
 
+// alpha history [N][T][KS*32] floats, followed by [N][T/RENORM + 2] doubles of log-scale offsets (+ exact nll)
+static int64_t alpha_floats(int T, int N, int ks) { return ((static_cast<int64_t>(N) * T * ks * 32 + 1) / 2) * 2; }
+
 extern "C" CTCB200_API int64_t ctcb200_ctc_workspace_floats(int T, int N, int max_target_len) {
     int ks = ks_for(max_target_len);
-    return static_cast<int64_t>(N) * T * ks * 32;
+    return alpha_floats(T, N, ks) + static_cast<int64_t>(N) * (T / RENORM + 2) * 2;
 }
 
 extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const int64_t* targets, int64_t target_stride,
@@ -279,10 +328,11 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const in
     dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
     size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * 2 * C * sizeof(float);
     CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_fwd: class count %d too large for the row buffer", C);
+    double* offs = reinterpret_cast<double*>(alpha_ws + alpha_floats(T, N, ks));
 #define LAUNCH_A(KS)                                                                                          \
     CTCB_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     ctc_alpha_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
-                                                        target_lengths, alpha_ws, nll, T, N, C, blank)
+                                                        target_lengths, alpha_ws, offs, nll, T, N, C, blank)
     switch (ks) {
         case 1: LAUNCH_A(1); break;
         case 2: LAUNCH_A(2); break;
@@ -307,10 +357,12 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_bwd(const float* log_probs, const in
     dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
     size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * 3 * C * sizeof(float);
     CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_bwd: class count %d too large for the row buffer", C);
+    const double* offs = reinterpret_cast<const double*>(alpha_ws + alpha_floats(T, N, ks));
+    (void)nll;
 #define LAUNCH_B(KS)                                                                                               \
     CTCB_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     ctc_beta_grad_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
-                                                            target_lengths, alpha_ws, nll, grad_nll, grad_scale,  \
+                                                            target_lengths, alpha_ws, offs, grad_nll, grad_scale, \
                                                             grad, T, N, C, blank)
     switch (ks) {
         case 1: LAUNCH_B(1); break;

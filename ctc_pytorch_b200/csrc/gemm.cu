@@ -95,32 +95,36 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+        // the whole warp runs the (warp-uniform) pipeline bookkeeping so descriptors stay in uniform registers;
+        // one elected lane issues the tcgen05 instructions
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                  (kb | k) != 0 ? 1u : 0u);
-                    }
+                const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+                if (leader) {
+                    umma_bf16(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+                    umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                    umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                    umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
                     umma_commit(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (leader) umma_commit(&tfull[acc]);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;

@@ -23,6 +23,8 @@
 // that each CTA finishes 32 units: dh -> (do, dc, di, df, dg) -> next dG images.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ctcb200.h"
 
@@ -60,6 +62,67 @@ __device__ __forceinline__ int image_chunk_offset(int u, int n) {
     return kb * (NB * 64) + n * 64 + ((c ^ (n & 7)) << 3);
 }
 
+// ---- thread-block-cluster primitives (distributed shared memory exchange) ------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release at cluster scope) on an mbarrier that lives in CTA `cta_rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t cta_rank) {
+    const uint32_t raddr = mapa_shared(smem_u32(local_bar), cta_rank);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > SPIN_LIMIT_CYCLES) spin_timeout_trap(3);
+    }
+}
+
+// Load this CTA's [128 x H] bf16 weight slice into TMEM columns [col0, col0 + H/2): row r -> lane r, K elements
+// (2c, 2c+1) packed into 32-bit column c — the A-operand layout of tcgen05.mma with A in tensor memory.
+// Executed by warps 0-3 (warp w owns lanes 32w..32w+31).
+__device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* __restrict__ w_rows, int H, uint32_t tmem_base,
+                                                     uint32_t col0, int warp, int lane) {
+    const uint4* src = reinterpret_cast<const uint4*>(w_rows + static_cast<size_t>(warp * 32 + lane) * H);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + col0;
+    for (int kb = 0; kb < H / 16; ++kb) {
+        const uint4 a = __ldg(src + 2 * kb), b = __ldg(src + 2 * kb + 1);
+        const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        tmem_st_32x8(taddr + kb * 8, r);
+    }
+    tmem_st_wait();
+}
+
 struct FwdParams {
     const float* gx;          // [T*N, 8H] gate pre-activations from the input projection (packed column order)
     float* hout;              // [T*N, 2H] layer output (fwd | reverse)
@@ -68,25 +131,39 @@ struct FwdParams {
     __nv_bfloat16* himg;      // [2 dirs][groups][2][H*NB] operand images
     unsigned int* flags;      // [2 dirs][groups] step counters, 32 uints apart
     int T, N, H, groups, n0;  // n0 = first batch row of this launch's group 0
+    long long* trace;         // debug: per-step clock64 stamps of CTA (0,0,0), or null
+    const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (source of the TMEM-resident A operand)
+    int a_tmem;               // 1: A operand resident in TMEM, 0: in shared memory (TMA-loaded)
 };
 
-template <int NB>
+// CL = true: the H/32 CTAs of one (direction, batch group) form one thread-block cluster and exchange h_t through
+// distributed shared memory (every CTA pushes its 32 units straight into the next-step operand buffer of all
+// peers and arrives on their mbarrier) — no global-memory round trip on the recurrence's critical path.
+// CL = false: exchange through a global operand image + release/acquire counter (any H, needs a cooperative launch).
+template <int NB, int EX>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
+    // EX = 0: global image + global counter (cooperative launch, any H)
+    // EX = 1: cluster, data pushed through DSMEM            EX = 2: cluster, data through L2, hand-off on DSMEM mbarriers
+    constexpr bool CL = EX != 0, PUSH = EX == 1, HYB = EX == 2;
     constexpr int CPT = NB / 2;        // accumulator columns per thread
     constexpr int EPT = NB / 8;        // (unit, batch) elements per thread in the cell update
     constexpr int S_STRIDE = NB * 4 + 4;
+    constexpr int OUT_CHUNKS = NB * 4; // 16-byte chunks of h_t this CTA produces per step (32 units x NB)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, T = p.T, N = p.N;
-    uint8_t* sW = smem;
-    uint8_t* sH = sW + 128 * H * 2;
-    float* sS = reinterpret_cast<float*>(sH + H * NB * 2);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + 32 * S_STRIDE);
+    const int himg_bytes = H * NB * 2;
+    uint8_t* sW = smem;                                              // unused when the weights live in TMEM
+    uint8_t* sH = sW + (p.a_tmem ? 0 : 128 * H * 2);                 // PUSH: two buffers, else one
+    float* sS = reinterpret_cast<float*>(sH + (PUSH ? 2 : 1) * himg_bytes);
+    uint4* sOut = reinterpret_cast<uint4*>(sS + 32 * S_STRIDE);      // PUSH only: staging of this CTA's h chunks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (PUSH ? OUT_CHUNKS : 0));
     uint64_t* w_full = bars;
-    uint64_t* h_full = bars + 1;
-    uint64_t* acc_full = bars + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* h_full = bars + 1;   // [2]: CL -> peers' arrivals per parity; EX=0 -> [0] counts the local image copy
+    uint64_t* acc_full = bars + 3;
+    uint64_t* l_full = bars + 4;   // HYB: the image copy into shared memory is complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
@@ -96,17 +173,33 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     if (tid == 0) {
         tma_prefetch_desc(&tmW);
         mbar_init(w_full, 1);
-        mbar_init(h_full, LSTM_THREADS);
+        mbar_init(&h_full[0], CL ? ctas : LSTM_THREADS);
+        mbar_init(&h_full[1], CL ? ctas : LSTM_THREADS);
         mbar_init(acc_full, 1);
+        mbar_init(l_full, LSTM_THREADS);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, NB < 32 ? 32 : NB);
+    // TMEM: accumulator in columns [0, 32), the weight slice (A operand) in columns [32, 32 + H/2) when resident
+    uint32_t tmem_cols = 32;
+    if (p.a_tmem) { while (tmem_cols < 32u + H / 2) tmem_cols <<= 1; }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    if constexpr (PUSH) {
+        // h_{-1} = 0: the first operand buffer starts zeroed
+        for (int i = tid; i < himg_bytes / 16; i += LSTM_THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (CL) cluster_sync_all();  // peers' barriers are initialised before anyone arrives on them
 
-    if (tid == 0) {
+    if (p.a_tmem) {
+        if (warp < 4) load_weights_to_tmem(p.w + (static_cast<size_t>(dir) * 4 * H + j * 128) * H, H, tmem_base, 32, warp, lane);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    } else if (tid == 0) {
         mbar_expect_tx(w_full, 128 * H * 2);
         for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sW + kb * 16384, &tmW, w_full, kb * 64, dir * 4 * H + j * 128);
     }
@@ -117,8 +210,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     const float act_s = (q == 2) ? 2.0f : 1.0f;
     const size_t gx_col = static_cast<size_t>(dir) * 4 * H + j * 128 + row;
     const size_t G8 = static_cast<size_t>(8) * H, H2 = static_cast<size_t>(2) * H;
-    __nv_bfloat16* img = p.himg + (static_cast<size_t>(dir) * p.groups + grp) * 2 * H * NB;
-    unsigned int* flag = p.flags + (dir * p.groups + grp) * 32;
+    __nv_bfloat16* img = PUSH ? nullptr : p.himg + (static_cast<size_t>(dir) * p.groups + grp) * 2 * H * NB;
+    unsigned int* flag = CL ? nullptr : p.flags + (dir * p.groups + grp) * 32;
     const int chunks = H * NB / 8;
     constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
 
@@ -126,8 +219,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
 #pragma unroll
     for (int e = 0; e < EPT; ++e) c_state[e] = 0.0f;
 
+#define TRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == (k >= 8 ? 255 : 0)) p.trace[t * 16 + (k)] = clock64(); } while (0)
     for (int t = 0; t < T; ++t) {
         const int tt = dir ? (T - 1 - t) : t;
+        TRACE(0);
         // (1) this step's input-projection terms: independent of the recurrence, issued first
         float gx[CPT];
 #pragma unroll
@@ -135,40 +230,73 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             const int gn = p.n0 + grp * NB + ch * CPT + c;
             gx[c] = (gn < N) ? __ldg(p.gx + (static_cast<size_t>(tt) * N + gn) * G8 + gx_col) : 0.0f;
         }
-        // (2) all CTAs of this (direction, group) have published h_{t-1}
-        if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
-        __syncwarp();
-        // (3) operand image -> shared memory
-        {
+        if constexpr (!PUSH) {
+            // (2) all CTAs of this (direction, group) have published h_{t-1}
+            if constexpr (HYB) {
+                if (t > 0) mbar_wait_cluster(&h_full[t & 1], ((t - 1) >> 1) & 1);
+            } else {
+                if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
+                __syncwarp();
+            }
+            // (3) operand image -> shared memory
             const uint4* src = reinterpret_cast<const uint4*>(img + static_cast<size_t>(t & 1) * H * NB);
             uint4* dst = reinterpret_cast<uint4*>(sH);
             for (int i = tid; i < chunks; i += LSTM_THREADS) dst[i] = ld_cg_v4(src + i);
             fence_proxy_async_smem();
-            mbar_arrive(h_full);
+            mbar_arrive(HYB ? l_full : &h_full[0]);
         }
-        // (4) one thread issues the K = H MMA chain
-        if (tid == 0) {
-            if (t == 0) mbar_wait(w_full, 0);
-            mbar_wait(h_full, t & 1);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sH);
-            for (int kb = 0; kb < kblocks; ++kb) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem_base, umma_desc_sw128(a0 + kb * 16384 + kk * 32),
-                              umma_desc_sw128(b0 + kb * (NB * 128) + kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
+        // (4) warp 0 issues the K = H MMA chain: the whole warp runs the (warp-uniform) address arithmetic so the
+        // descriptors live in uniform registers; one elected lane issues each tcgen05.mma
+        if (warp == 0) {
+            if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
+            if constexpr (PUSH) {
+                if (t > 0) mbar_wait_cluster(&h_full[t & 1], ((t - 1) >> 1) & 1);  // all peers pushed h_{t-1}
+                fence_proxy_async_all();   // peers' generic-proxy DSMEM writes -> tensor-core (async proxy) reads
+            } else {
+                mbar_wait(HYB ? l_full : &h_full[0], t & 1);
             }
-            umma_commit(acc_full);
+            tc_fence_after();
+            TRACE(1);
+            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sH) + (PUSH ? (t & 1) * himg_bytes : 0);
+            const bool leader = elect_one();
+            if (p.a_tmem) {
+#pragma unroll 1
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const uint64_t bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    const uint32_t ta = tmem_base + 32 + kb * 32;
+                    if (leader) {
+                        umma_bf16_ts(tmem_base, ta, bd, idesc, kb != 0 ? 1u : 0u);
+                        umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 16, bd + 4, idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 24, bd + 6, idesc, 1u);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    if (leader) {
+                        umma_bf16(tmem_base, ad, bd, idesc, kb != 0 ? 1u : 0u);
+                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                    }
+                }
+            }
+            if (leader) umma_commit(acc_full);
+            TRACE(2);
         }
         __syncwarp();
         // (5) accumulator -> registers
         mbar_wait(acc_full, t & 1);
         tc_fence_after();
+        TRACE(3); TRACE(8);
         uint32_t acc[CPT];
         if constexpr (CPT == 16) tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, acc);
         else tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, acc);
         tmem_ld_wait();
         tc_fence_before();
+        TRACE(4); TRACE(9);
         // (6) gate non-linearity, then regroup the four gates of a unit through shared memory
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
@@ -176,11 +304,12 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             const float a = act_s * fast_sigmoid(act_s * pre) - (act_s - 1.0f);  // sigmoid, or tanh for gate g
             sS[u_loc * S_STRIDE + (ch * CPT + c) * 4 + q] = a;
         }
+        TRACE(10);
         __syncthreads();
-        // (7) cell update for (unit = lane, batch n = warp + 8e); publish h_t into the next image
+        TRACE(5); TRACE(11);
+        // (7) cell update for (unit = lane, batch n = warp + 8e); publish h_t as the next step's B operand
         float hv[EPT];
         float4 gv[EPT];
-        __nv_bfloat16* img_next = img + static_cast<size_t>((t + 1) & 1) * H * NB;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int n = warp + 8 * e;
@@ -191,12 +320,43 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             hv[e] = h;
             gv[e] = g4;
             const uint4 pk = pack8_bf16(h);
-            if ((lane & 7) == 0)
-                *reinterpret_cast<uint4*>(img_next + image_chunk_offset<NB>(j * 32 + lane, n)) = pk;
+            if ((lane & 7) == 0) {
+                if constexpr (PUSH) sOut[n * 4 + (lane >> 3)] = pk;
+                else *reinterpret_cast<uint4*>(img + static_cast<size_t>((t + 1) & 1) * H * NB +
+                                               image_chunk_offset<NB>(j * 32 + lane, n)) = pk;
+            }
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) red_release_add(flag, 1u);
+        TRACE(12);
+        if constexpr (HYB) {
+            __threadfence();   // h_t is in L2 before any peer is told about it
+            TRACE(6); TRACE(13);
+            __syncthreads();
+            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&h_full[(t + 1) & 1], static_cast<uint32_t>(tid));
+            TRACE(7);
+        } else if constexpr (PUSH) {
+            __syncthreads();
+            TRACE(6);
+            if (t + 1 < T) {
+                // push this CTA's OUT_CHUNKS chunks into buffer (t+1)&1 of every CTA of the cluster
+                const uint32_t next_base = smem_u32(sH) + ((t + 1) & 1) * himg_bytes;
+                for (int idx = tid; idx < OUT_CHUNKS * ctas; idx += LSTM_THREADS) {
+                    const int c = idx % OUT_CHUNKS;
+                    int d = idx / OUT_CHUNKS + j;  // start with the own rank: spreads the senders over the receivers
+                    if (d >= ctas) d -= ctas;
+                    const int n = c >> 2, oct = c & 3;
+                    const uint32_t local = next_base + image_chunk_offset<NB>(j * 32 + oct * 8, n) * 2;
+                    st_cluster_v4(mapa_shared(local, static_cast<uint32_t>(d)), sOut[c]);
+                }
+            }
+            TRACE(13);
+            __syncthreads();
+            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&h_full[(t + 1) & 1], static_cast<uint32_t>(tid));
+            TRACE(7);
+        } else {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) red_release_add(flag, 1u);
+        }
         // (8) off the critical path: layer output and the activations BPTT needs
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
@@ -214,25 +374,13 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, NB < 32 ? 32 : NB);
+    if constexpr (CL) cluster_sync_all();  // no CTA exits while a peer may still address its shared memory
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward (BPTT)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 struct BwdParams {
     const float* dhout;        // [T*N, 2H] gradient w.r.t. the layer output
     const float* c_save;       // [T*N, 2H]
@@ -241,49 +389,81 @@ struct BwdParams {
     __nv_bfloat16* dgimg;      // [2 dirs][groups][4 gates][2][H*NB] operand images
     unsigned int* flags;       // [2 dirs][groups]
     int T, N, H, groups, n0;
+    const __nv_bfloat16* w;    // packed transposed recurrent weights [8H, H]
+    int a_tmem;
 };
 
-template <int NB>
+// CTA (mb, q) keeps the [128 units x H] slice of gate q's transposed recurrent block. Per BPTT step:
+//   partial dh[128, NB] = slice * dG_q  ->  reduce-scatter of the 4 gate partials inside the (4,*) cluster row
+//   -> 32 finished units per CTA -> LSTM cell backward -> the four dG chunks go to the next step's operands.
+// CL = true: the whole (direction, group) = 4 x H/128 CTAs is one cluster; dG chunks are pushed through DSMEM into
+// the operand buffer of every CTA that holds the same gate, completion on remote mbarriers.
+// CL = false: cluster of the 4 gate CTAs only; dG images + release/acquire counter in global memory (any H).
+template <int NB, int EX>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
+    constexpr bool CL = EX != 0, PUSH = EX == 1, HYB = EX == 2;  // exchange modes as in the forward kernel
     constexpr int CPT = NB / 2;
     constexpr int EPT = NB / 8;
+    constexpr int OUT_CHUNKS = NB * 4;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, T = p.T, N = p.N;
-    uint8_t* sW = smem;
-    uint8_t* sB = sW + 128 * H * 2;
-    float* sR = reinterpret_cast<float*>(sB + H * NB * 2);  // [4 src][NB][32] partial dh blocks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 4 * NB * 32);
+    const int img_bytes = H * NB * 2;
+    uint8_t* sW = smem;                                               // unused when the weights live in TMEM
+    uint8_t* sB = sW + (p.a_tmem ? 0 : 128 * H * 2);                  // PUSH: two buffers, else one
+    float* sR = reinterpret_cast<float*>(sB + (PUSH ? 2 : 1) * img_bytes);  // [4 src][NB][32] partial dh blocks
+    uint4* sOut = reinterpret_cast<uint4*>(sR + 4 * NB * 32);         // PUSH only: [4 gates][OUT_CHUNKS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (PUSH ? 4 * OUT_CHUNKS : 0));
     uint64_t* w_full = bars;
-    uint64_t* b_full = bars + 1;
-    uint64_t* acc_full = bars + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* b_full = bars + 1;   // [2]
+    uint64_t* acc_full = bars + 3;
+    uint64_t* r_full = bars + 4;   // CL only: the 4 partial blocks of a step have landed
+    uint64_t* l_full = bars + 5;   // HYB: the image copy into shared memory is complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = blockIdx.x;  // gate handled by this CTA == rank in the 4-CTA cluster
-    const int mb = blockIdx.y;
+    const int q = blockIdx.x;   // gate handled by this CTA
+    const int mb = blockIdx.y;  // block of 128 hidden units
+    const int MB = gridDim.y;
     const int dir = blockIdx.z / p.groups, grp = blockIdx.z % p.groups;
-    const int ctas = 4 * gridDim.y;
+    const int ctas = 4 * MB;
     const int kblocks = H / 64;
+    // rank inside the cluster: CL -> x + 4*y (cluster spans the whole (4, MB) plane), else x
+    auto rank_of = [&](int qq, int mm) -> uint32_t { return static_cast<uint32_t>(CL ? qq + 4 * mm : qq); };
 
     if (tid == 0) {
         tma_prefetch_desc(&tmWT);
         mbar_init(w_full, 1);
-        mbar_init(b_full, LSTM_THREADS);
+        mbar_init(&b_full[0], CL ? ctas : LSTM_THREADS);
+        mbar_init(&b_full[1], CL ? ctas : LSTM_THREADS);
         mbar_init(acc_full, 1);
+        mbar_init(r_full, 4);
+        mbar_init(l_full, LSTM_THREADS);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, NB < 32 ? 32 : NB);
+    uint32_t tmem_cols = 32;
+    if (p.a_tmem) { while (tmem_cols < 32u + H / 2) tmem_cols <<= 1; }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    if constexpr (PUSH) {
+        for (int i = tid; i < img_bytes / 16; i += LSTM_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    cluster_sync_all();  // every CTA of the cluster has its barriers / receive buffer ready
+    cluster_sync_all();  // every CTA of the cluster has its barriers / receive buffers ready
 
-    if (tid == 0) {
+    // rows of the transposed gate block: (dir, q, unit); this CTA takes units [128 mb, +128)
+    if (p.a_tmem) {
+        if (warp < 4)
+            load_weights_to_tmem(p.w + (static_cast<size_t>(dir * 4 + q) * H + mb * 128) * H, H, tmem_base, 32, warp, lane);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    } else if (tid == 0) {
         mbar_expect_tx(w_full, 128 * H * 2);
-        // rows of the transposed gate block: (dir, q, unit); this CTA takes units [128 mb, +128)
         for (int kb = 0; kb < kblocks; ++kb)
             tma_load_2d(sW + kb * 16384, &tmWT, w_full, kb * 64, (dir * 4 + q) * H + mb * 128);
     }
@@ -292,12 +472,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     const int unit = mb * 128 + q * 32 + lane;  // the unit this thread finishes in the element phase
     const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
     const size_t dg_col = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4;
-    __nv_bfloat16* imgs = p.dgimg + (static_cast<size_t>(dir) * p.groups + grp) * 4 * 2 * H * NB;
-    unsigned int* flag = p.flags + (dir * p.groups + grp) * 32;
+    __nv_bfloat16* imgs = PUSH ? nullptr : p.dgimg + (static_cast<size_t>(dir) * p.groups + grp) * 4 * 2 * H * NB;
+    unsigned int* flag = CL ? nullptr : p.flags + (dir * p.groups + grp) * 32;
     const int chunks = H * NB / 8;
     constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
-    // remote receive slot: partial block from source gate q lands in CTA `lq` (owner of rows 32 lq..)
-    const uint32_t remote_base = mapa_shared(smem_u32(sR + (q * NB + ch * CPT) * 32 + lane), static_cast<uint32_t>(lq));
+    // remote receive slot: partial block from source gate q lands in the CTA that owns rows 32 lq.. of this unit block
+    const uint32_t remote_base = mapa_shared(smem_u32(sR + (q * NB + ch * CPT) * 32 + lane), rank_of(lq, mb));
 
     float dc_carry[EPT];
 #pragma unroll
@@ -322,30 +502,58 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
                               static_cast<size_t>(dir) * H + unit;
             c_p[e] = (ok && has_prev) ? __ldg(p.c_save + op) : 0.0f;
         }
-        // (2) gate gradients of the previous BPTT step are published
-        if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
-        __syncwarp();
-        // (3) dG image of gate q -> shared memory
-        {
+        if constexpr (!PUSH) {
+            // (2) gate gradients of the previous BPTT step are published
+            if constexpr (HYB) {
+                if (t > 0) mbar_wait_cluster(&b_full[t & 1], ((t - 1) >> 1) & 1);
+            } else {
+                if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
+                __syncwarp();
+            }
+            // (3) dG image of gate q -> shared memory
             const uint4* src = reinterpret_cast<const uint4*>(imgs + (static_cast<size_t>(q) * 2 + (t & 1)) * H * NB);
             uint4* dst = reinterpret_cast<uint4*>(sB);
             for (int i = tid; i < chunks; i += LSTM_THREADS) dst[i] = ld_cg_v4(src + i);
             fence_proxy_async_smem();
-            mbar_arrive(b_full);
+            mbar_arrive(HYB ? l_full : &b_full[0]);
         }
-        // (4) partial dh[128 units, NB] = W_q^T slice * dG_q
-        if (tid == 0) {
-            if (t == 0) mbar_wait(w_full, 0);
-            mbar_wait(b_full, t & 1);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sB);
-            for (int kb = 0; kb < kblocks; ++kb) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem_base, umma_desc_sw128(a0 + kb * 16384 + kk * 32),
-                              umma_desc_sw128(b0 + kb * (NB * 128) + kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
+        // (4) partial dh[128 units, NB] = W_q^T slice * dG_q (issued like the forward kernel's chain)
+        if (warp == 0) {
+            if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
+            if constexpr (PUSH) {
+                if (t > 0) mbar_wait_cluster(&b_full[t & 1], ((t - 1) >> 1) & 1);
+                fence_proxy_async_all();
+            } else {
+                mbar_wait(HYB ? l_full : &b_full[0], t & 1);
             }
-            umma_commit(acc_full);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sB) + (PUSH ? (t & 1) * img_bytes : 0);
+            const bool leader = elect_one();
+            if (p.a_tmem) {
+#pragma unroll 1
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const uint64_t bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    const uint32_t ta = tmem_base + 32 + kb * 32;
+                    if (leader) {
+                        umma_bf16_ts(tmem_base, ta, bd, idesc, kb != 0 ? 1u : 0u);
+                        umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 16, bd + 4, idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 24, bd + 6, idesc, 1u);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    if (leader) {
+                        umma_bf16(tmem_base, ad, bd, idesc, kb != 0 ? 1u : 0u);
+                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                    }
+                }
+            }
+            if (leader) umma_commit(acc_full);
         }
         __syncwarp();
         // (5) scatter the partial rows to their owner CTA through distributed shared memory
@@ -358,7 +566,13 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         tc_fence_before();
 #pragma unroll
         for (int c = 0; c < CPT; ++c) st_cluster_f32(remote_base + c * 32 * 4, __uint_as_float(acc[c]));
-        cluster_sync_all();
+        if constexpr (CL) {
+            __syncthreads();
+            if (tid < 4) mbar_arrive_remote(r_full, rank_of(tid, mb));
+            mbar_wait_cluster(r_full, t & 1);
+        } else {
+            cluster_sync_all();
+        }
         // (6) finish 32 units: recurrent dh, LSTM cell backward, publish the four gate gradients
         uint2 dgp[EPT];
 #pragma unroll
@@ -377,21 +591,51 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             const float d_f = dc * c_p[e] * gf * (1.0f - gf);
             const float d_g = dc * gi * (1.0f - gg * gg);
             dc_carry[e] = dc * gf;
-            const int off = image_chunk_offset<NB>(unit, n);
-            const size_t nxt = static_cast<size_t>((t + 1) & 1) * H * NB;
             const uint4 pi = pack8_bf16(d_i), pf = pack8_bf16(d_f), pg = pack8_bf16(d_g), po = pack8_bf16(d_o);
             if ((lane & 7) == 0) {
-                *reinterpret_cast<uint4*>(imgs + (0 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pi;
-                *reinterpret_cast<uint4*>(imgs + (1 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pf;
-                *reinterpret_cast<uint4*>(imgs + (2 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pg;
-                *reinterpret_cast<uint4*>(imgs + (3 * 2) * static_cast<size_t>(H) * NB + nxt + off) = po;
+                if constexpr (PUSH) {
+                    const int c = n * 4 + (lane >> 3);
+                    sOut[0 * OUT_CHUNKS + c] = pi;
+                    sOut[1 * OUT_CHUNKS + c] = pf;
+                    sOut[2 * OUT_CHUNKS + c] = pg;
+                    sOut[3 * OUT_CHUNKS + c] = po;
+                } else {
+                    const int off = image_chunk_offset<NB>(unit, n);
+                    const size_t nxt = static_cast<size_t>((t + 1) & 1) * H * NB;
+                    *reinterpret_cast<uint4*>(imgs + (0 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pi;
+                    *reinterpret_cast<uint4*>(imgs + (1 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pf;
+                    *reinterpret_cast<uint4*>(imgs + (2 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pg;
+                    *reinterpret_cast<uint4*>(imgs + (3 * 2) * static_cast<size_t>(H) * NB + nxt + off) = po;
+                }
             }
             __nv_bfloat162 b01 = __floats2bfloat162_rn(d_i, d_f), b23 = __floats2bfloat162_rn(d_g, d_o);
             dgp[e] = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) red_release_add(flag, 1u);
+        if constexpr (HYB) {
+            __threadfence();
+            __syncthreads();
+            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&b_full[(t + 1) & 1], static_cast<uint32_t>(tid));
+        } else if constexpr (PUSH) {
+            __syncthreads();
+            if (t + 1 < T) {
+                // gate g's chunks of this CTA's 32 units go to the operand buffer of every CTA (g, mb')
+                const uint32_t next_base = smem_u32(sB) + ((t + 1) & 1) * img_bytes;
+                const int per_gate = OUT_CHUNKS * MB;
+                for (int idx = tid; idx < 4 * per_gate; idx += LSTM_THREADS) {
+                    const int g = idx / per_gate, r = idx - g * per_gate;
+                    const int mdst = r / OUT_CHUNKS, c = r - mdst * OUT_CHUNKS;
+                    const int n = c >> 2, oct = c & 3;
+                    const uint32_t local = next_base + image_chunk_offset<NB>(mb * 128 + q * 32 + oct * 8, n) * 2;
+                    st_cluster_v4(mapa_shared(local, rank_of(g, mdst)), sOut[g * OUT_CHUNKS + c]);
+                }
+            }
+            __syncthreads();
+            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&b_full[(t + 1) & 1], static_cast<uint32_t>(tid));
+        } else {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) red_release_add(flag, 1u);
+        }
         // (7) off the critical path: dG rows for the dX / dW GEMMs
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
@@ -403,18 +647,39 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // no CTA exits while a peer may still address its shared memory
-    if (warp == 1) tmem_dealloc(tmem_base, NB < 32 ? 32 : NB);
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <int NB>
-size_t lstm_smem_bytes(int H, bool bwd) {
-    size_t b = static_cast<size_t>(128) * H * 2 + static_cast<size_t>(H) * NB * 2;
-    b += bwd ? static_cast<size_t>(4) * NB * 32 * 4 : static_cast<size_t>(32) * (NB * 4 + 4) * 4;
+bool weights_in_tmem() {
+    const char* e = getenv("CTCB200_LSTM_A");  // "smem" keeps the weight slice in shared memory (A/B comparison runs)
+    return !(e && e[0] == 's');
+}
+
+size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool a_tmem) {
+    const bool push = ex == 1;
+    size_t b = (a_tmem ? 0 : static_cast<size_t>(128) * H * 2) + static_cast<size_t>(push ? 2 : 1) * H * NB * 2;
+    if (bwd) b += static_cast<size_t>(4) * NB * 32 * 4 + (push ? static_cast<size_t>(4) * NB * 4 * 16 : 0);
+    else b += static_cast<size_t>(32) * (NB * 4 + 4) * 4 + (push ? static_cast<size_t>(NB) * 4 * 16 : 0);
     return b + 64 + 1024;
 }
 
-int pick_nb(int N, int H, int force_nb, bool bwd) {
+// How the CTAs of one (direction, batch group) hand h_t / dG_t to each other every step:
+//   1 (default for H <= 512)  one thread-block cluster; h_t / dG_t pushed through DSMEM, remote mbarrier hand-off
+//   2                         one cluster; data through L2, hand-off on remote (DSMEM) mbarriers
+//   0 (H > 512)               global image + global release/acquire counter, cooperative launch
+// CTCB200_LSTM_EXCHANGE = global | push | hybrid overrides the choice (A/B measurements).
+int exchange_mode(int H) {
+    const bool fits = H <= 512;  // H/32 CTAs (forward) and 4*H/128 CTAs (backward) fit one cluster of <= 16
+    const char* e = getenv("CTCB200_LSTM_EXCHANGE");
+    if (e && e[0] == 'g') return 0;
+    if (!fits) return 0;
+    if (e && e[0] == 'h') return 2;
+    return 1;  // measured on B200 (cfg2, NB=16): push 6.6k cycles/step, hybrid 6.8k, global 9.3k
+}
+
+int pick_nb(int N, int H, int force_nb, bool bwd, bool cl) {
     if (force_nb == 16 || force_nb == 32) return force_nb;
+    if (cl) return N <= 16 ? 16 : (((N + 15) / 16) * (bwd ? 4 * (H / 128) : H / 32) * 2 <= 128 ? 16 : 32);
     const int sms = device_sm_count();
     const int per_group = bwd ? 2 * 4 * (H / 128) : 2 * (H / 32);
     // prefer the narrow batch tile (shorter per-step chain) when every group fits at once
@@ -422,6 +687,36 @@ int pick_nb(int N, int H, int force_nb, bool bwd) {
     const int budget = bwd ? (sms / 4) * 4 - 16 : sms;  // clusters of 4 cannot use every SM
     if (g16 * per_group <= budget) return 16;
     return 32;
+}
+
+template <typename Kern, typename Params>
+int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool cooperative, const CUtensorMap& tm,
+                     const Params& p, cudaStream_t stream) {
+    CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (cluster.x * cluster.y * cluster.z > 8)
+        CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(LSTM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = cluster.x; attrs[0].val.clusterDim.y = cluster.y; attrs[0].val.clusterDim.z = cluster.z;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = cooperative ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, p);
+    if (e != cudaSuccess && cooperative) {
+        // some driver / tool combinations refuse cooperative + cluster together; co-residency is then guaranteed
+        // by the caller's CTA budget (one CTA per SM, grid <= schedulable clusters) on an otherwise idle device
+        (void)cudaGetLastError();
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tm, p);
+    }
+    CTCB_CUDA(e);
+    return OK;
 }
 
 }  // namespace
@@ -441,18 +736,70 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_fwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_fwd: hidden size %d must be a multiple of 128 in [128,640]", H);
-    const int NB = pick_nb(N, H, batch_tile, false);
+    const int ex = exchange_mode(H);
+    const bool cl = ex != 0;
+    const int NB = pick_nb(N, H, batch_tile, false, cl);
     const int groups_total = (N + NB - 1) / NB;
+    CUtensorMap tmW;
+    int rc = make_tmap_bf16_2d(&tmW, whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+    if (rc != OK) return rc;
+    const bool a_tmem = weights_in_tmem();
+    const size_t smem = lstm_smem_bytes(NB, H, false, ex, a_tmem);
+    CTCB_REQUIRE(smem <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
+    FwdParams p;
+    p.gx = gx; p.hout = hout; p.c_save = c_save; p.gates_save = static_cast<uint2*>(gates_save);
+    p.himg = nullptr; p.flags = nullptr; p.trace = nullptr;
+    p.w = static_cast<const __nv_bfloat16*>(whh_packed); p.a_tmem = a_tmem ? 1 : 0;
+    p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
+    if (getenv("CTCB200_LSTM_TRACE")) {  // development aid: per-phase cycle breakdown of the recurrence on stderr
+        static long long* dbuf = nullptr;
+        if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
+        if (T <= 4096) {
+            CTCB_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 16 * T, stream));
+            p.trace = dbuf;
+        }
+    }
+    struct TraceDump {
+        const FwdParams& p; cudaStream_t s;
+        ~TraceDump() {
+            if (!p.trace) return;
+            cudaStreamSynchronize(s);
+            const int T = p.T;
+            long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
+            cudaMemcpy(h, p.trace, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost);
+            double acc[16] = {0};
+            int cnt = 0;
+            for (int t = 8; t + 1 < T; ++t, ++cnt) {
+                for (int k = 1; k < 8; ++k) acc[k] += double(h[t * 16 + k] - h[t * 16 + k - 1]);
+                acc[0] += double(h[(t + 1) * 16] - h[t * 16]);
+                for (int k = 9; k < 14; ++k) acc[k] += double(h[t * 16 + k] - h[t * 16 + k - 1]);
+            }
+            fprintf(stderr, "lstm_fwd trace (cycles/step avg over %d steps): total %.0f | t0: start->hfull %.0f, mma issue %.0f, "
+                    "commit->acc %.0f, tmem ld %.0f, act+sync %.0f, cell+sync %.0f, push+sync+arrive %.0f | t255: ld %.0f act %.0f "
+                    "sync %.0f cell %.0f push %.0f\n", cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt,
+                    acc[5] / cnt, acc[6] / cnt, acc[7] / cnt, acc[9] / cnt, acc[10] / cnt, acc[11] / cnt, acc[12] / cnt, acc[13] / cnt);
+            free(h);
+        }
+    } trace_dump{p, stream};
+    if (cl) {
+        // independent clusters: no co-residency requirement between them, one launch covers every batch group
+        dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
+        if (ex == 2) {
+            const size_t img_bytes = static_cast<size_t>(2) * groups_total * 2 * H * NB * 2;
+            CTCB_CUDA(cudaMemsetAsync(scratch, 0, img_bytes, stream));
+            p.himg = static_cast<__nv_bfloat16*>(scratch);
+            if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 2>, grid, cluster, smem, false, tmW, p, stream);
+            return launch_clustered(lstm_fwd_kernel<32, 2>, grid, cluster, smem, false, tmW, p, stream);
+        }
+        if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 1>, grid, cluster, smem, false, tmW, p, stream);
+        return launch_clustered(lstm_fwd_kernel<32, 1>, grid, cluster, smem, false, tmW, p, stream);
+    }
     const int per_group = 2 * (H / 32);
     const int sms = device_sm_count();
     CTCB_REQUIRE(per_group <= sms, "lstm_fwd: one batch group needs %d CTAs but the device has %d SMs", per_group, sms);
     const int groups_per_launch = sms / per_group;
-    CUtensorMap tmW;
-    int rc = make_tmap_bf16_2d(&tmW, whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
-    if (rc != OK) return rc;
-    const size_t smem = NB == 16 ? lstm_smem_bytes<16>(H, false) : lstm_smem_bytes<32>(H, false);
-    CTCB_REQUIRE(smem <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
-    void* kern = NB == 16 ? reinterpret_cast<void*>(lstm_fwd_kernel<16>) : reinterpret_cast<void*>(lstm_fwd_kernel<32>);
+    void* kern = NB == 16 ? reinterpret_cast<void*>(lstm_fwd_kernel<16, 0>)
+                          : reinterpret_cast<void*>(lstm_fwd_kernel<32, 0>);
     CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     uint8_t* scr = static_cast<uint8_t*>(scratch);
     for (int g0 = 0; g0 < groups_total; g0 += groups_per_launch) {
@@ -460,11 +807,9 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         const size_t img_bytes = static_cast<size_t>(2) * groups * 2 * H * NB * 2;
         const size_t flag_bytes = static_cast<size_t>(2) * groups * 32 * 4;
         CTCB_CUDA(cudaMemsetAsync(scr, 0, img_bytes + flag_bytes, stream));
-        FwdParams p;
-        p.gx = gx; p.hout = hout; p.c_save = c_save; p.gates_save = static_cast<uint2*>(gates_save);
         p.himg = reinterpret_cast<__nv_bfloat16*>(scr);
         p.flags = reinterpret_cast<unsigned int*>(scr + img_bytes);
-        p.T = T; p.N = N; p.H = H; p.groups = groups; p.n0 = g0 * NB;
+        p.groups = groups; p.n0 = g0 * NB;
         void* args[] = {const_cast<CUtensorMap*>(&tmW), &p};
         dim3 grid(H / 32, 2, groups), block(LSTM_THREADS);
         CTCB_CUDA(cudaLaunchCooperativeKernel(kern, grid, block, args, smem, stream));
@@ -478,53 +823,54 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_bwd: hidden size %d must be a multiple of 128 in [128,640]", H);
-    const int NB = pick_nb(N, H, batch_tile, true);
+    const int ex = exchange_mode(H);
+    const bool cl = ex != 0;
+    const int NB = pick_nb(N, H, batch_tile, true, cl);
     const int groups_total = (N + NB - 1) / NB;
-    const int per_group = 2 * 4 * (H / 128);
+    const int MB = H / 128;
+    CUtensorMap tmWT;
+    int rc = make_tmap_bf16_2d(&tmWT, whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+    if (rc != OK) return rc;
+    const bool a_tmem = weights_in_tmem();
+    const size_t smem = lstm_smem_bytes(NB, H, true, ex, a_tmem);
+    CTCB_REQUIRE(smem <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
+    BwdParams p;
+    p.dhout = dhout; p.c_save = c_save; p.gates_save = static_cast<const uint2*>(gates_save);
+    p.dg = static_cast<__nv_bfloat16*>(dg);
+    p.dgimg = nullptr; p.flags = nullptr;
+    p.w = static_cast<const __nv_bfloat16*>(whhT_packed); p.a_tmem = a_tmem ? 1 : 0;
+    p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
+    if (cl) {
+        dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
+        if (ex == 2) {
+            const size_t img_bytes = static_cast<size_t>(2) * groups_total * 4 * 2 * H * NB * 2;
+            CTCB_CUDA(cudaMemsetAsync(scratch, 0, img_bytes, stream));
+            p.dgimg = static_cast<__nv_bfloat16*>(scratch);
+            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 2>, grid, cluster, smem, false, tmWT, p, stream);
+            return launch_clustered(lstm_bwd_kernel<32, 2>, grid, cluster, smem, false, tmWT, p, stream);
+        }
+        if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 1>, grid, cluster, smem, false, tmWT, p, stream);
+        return launch_clustered(lstm_bwd_kernel<32, 1>, grid, cluster, smem, false, tmWT, p, stream);
+    }
+    const int per_group = 2 * 4 * MB;
     const int sms = device_sm_count();
     const int budget = (sms / 4) * 4 - 16;  // clusters of 4 strand a few SMs
     CTCB_REQUIRE(per_group <= budget, "lstm_bwd: one batch group needs %d CTAs; device budget %d", per_group, budget);
     const int groups_per_launch = budget / per_group;
-    CUtensorMap tmWT;
-    int rc = make_tmap_bf16_2d(&tmWT, whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
-    if (rc != OK) return rc;
-    const size_t smem = NB == 16 ? lstm_smem_bytes<16>(H, true) : lstm_smem_bytes<32>(H, true);
-    CTCB_REQUIRE(smem <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
-    auto kern = NB == 16 ? lstm_bwd_kernel<16> : lstm_bwd_kernel<32>;
-    CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     uint8_t* scr = static_cast<uint8_t*>(scratch);
     for (int g0 = 0; g0 < groups_total; g0 += groups_per_launch) {
         const int groups = (groups_total - g0 < groups_per_launch) ? groups_total - g0 : groups_per_launch;
         const size_t img_bytes = static_cast<size_t>(2) * groups * 4 * 2 * H * NB * 2;
         const size_t flag_bytes = static_cast<size_t>(2) * groups * 32 * 4;
         CTCB_CUDA(cudaMemsetAsync(scr, 0, img_bytes + flag_bytes, stream));
-        BwdParams p;
-        p.dhout = dhout; p.c_save = c_save; p.gates_save = static_cast<const uint2*>(gates_save);
-        p.dg = static_cast<__nv_bfloat16*>(dg);
         p.dgimg = reinterpret_cast<__nv_bfloat16*>(scr);
         p.flags = reinterpret_cast<unsigned int*>(scr + img_bytes);
-        p.T = T; p.N = N; p.H = H; p.groups = groups; p.n0 = g0 * NB;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(4, H / 128, 2 * groups);
-        cfg.blockDim = dim3(LSTM_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attrs[2];
-        attrs[0].id = cudaLaunchAttributeClusterDimension;
-        attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-        attrs[1].id = cudaLaunchAttributeCooperative;
-        attrs[1].val.cooperative = 1;
-        cfg.attrs = attrs;
-        cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmWT, p);
-        if (e != cudaSuccess) {
-            // some drivers refuse cooperative + cluster together; co-residency is then guaranteed by the CTA
-            // budget above (one CTA per SM, grid <= schedulable clusters) on an otherwise idle device
-            (void)cudaGetLastError();
-            cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, kern, tmWT, p);
-        }
-        CTCB_CUDA(e);
+        p.groups = groups; p.n0 = g0 * NB;
+        dim3 grid(4, MB, 2 * groups), cluster(4, 1, 1);
+        const bool coop = getenv("CTCB200_BWD_NO_COOP") == nullptr;  // profilers may reject cooperative + cluster
+        if (NB == 16) rc = launch_clustered(lstm_bwd_kernel<16, 0>, grid, cluster, smem, coop, tmWT, p, stream);
+        else rc = launch_clustered(lstm_bwd_kernel<32, 0>, grid, cluster, smem, coop, tmWT, p, stream);
+        if (rc != OK) return rc;
     }
     return OK;
 }

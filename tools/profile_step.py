@@ -1,0 +1,30 @@
+"""One cfg2 training step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.nn as nn
+import bench
+from ctc_pytorch_b200.model import CTC_Model
+from ctc_pytorch_b200.loss import CTCLoss
+from ctc_pytorch_b200 import ops
+
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+cfg = dict(bench.CFG[name])
+if len(sys.argv) > 2: cfg["T"] = int(sys.argv[2])
+dev = "cuda"
+torch.manual_seed(0)
+m = CTC_Model(rnn_param=bench.rnn_param(cfg), num_class=cfg["C"], drop_out=0.0).to(dev)
+opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0.005)
+x, frac, tg, tl = (t.to(dev) for t in bench.make_batch(cfg, 1))
+lossf = CTCLoss(reduction="sum"); m.train()
+def step():
+    out = m(x); il = (frac * out.shape[0]).long()
+    loss = lossf(out, tg, il, tl) / x.shape[0]
+    ops.greedy_decode(out, il)
+    opt.zero_grad(); loss.backward(); opt.step()
+for _ in range(2): step()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("done")
