@@ -226,6 +226,7 @@ class _RnnStackFn(torch.autograd.Function):
         F2 = 2 * H
         layers = list(model.rnns.children())
         grads = {}
+        grad_x = None
 
         g = g_out.detach().to(torch.float32).contiguous()
         dlogits = torch.empty((R, C), dtype=torch.float32, device=dev)
@@ -265,6 +266,10 @@ class _RnnStackFn(torch.autograd.Function):
                 grads[rnn.weight_hh_l0] = torch.zeros_like(rnn.weight_hh_l0)
                 grads[rnn.weight_hh_l0_reverse] = torch.zeros_like(rnn.weight_hh_l0_reverse)
             del dgT
+            if li == 0 and ctx.needs_input_grad[1]:
+                dx0 = ops.gemm_tn(dg, rec.wihT_p, k=8 * H)                 # [R, I0] rows (t, n)
+                T0, N0, I0 = ws.geom[0], ws.geom[1], ws.geom[2]
+                grad_x = dx0.view(T0, N0, I0).transpose(0, 1)              # back to the [N, T, I0] layout of x_src
             if li > 0:
                 dh = ops.gemm_tn(dg, rec.wihT_p, k=8 * H)                  # [R, I]
                 bn = layer.batch_norm
@@ -276,7 +281,7 @@ class _RnnStackFn(torch.autograd.Function):
                     grads[bn.weight], grads[bn.bias] = dgam, dbet
             del dg
         ctx.ws = None
-        return (None, None, None) + tuple(grads.get(p) for p in ctx.param_list)
+        return (None, grad_x, None) + tuple(grads.get(p) for p in ctx.param_list)
 
 
 class CTC_Model(nn.Module):
@@ -365,14 +370,12 @@ class CTC_Model(nn.Module):
         need_grad = self.training and torch.is_grad_enabled()
         if self.add_cnn:
             from . import cnn
-            feats = cnn.conv_front(self, x)  # [N, Cc, T', F'] f32
+            seq = cnn.conv_front(self, x, need_grad)  # [N, T', Cc*F'] f32, feature index c*F' + f
+            Nb, Tp, Dp = seq.shape
             if visualize:
-                visual.append(feats)
-            Nb, Cc, Tp, Fp = feats.shape
-            seq = feats.transpose(1, 2).contiguous().view(Nb, Tp, Cc * Fp)  # [N, T', Cc*F']
-            if visualize:
+                visual.append(seq)
                 visual.append(seq.transpose(0, 1))
-            src, geom = seq, (Tp, Nb, Cc * Fp, Cc * Fp, Tp * Cc * Fp, need_grad)
+            src, geom = seq, (Tp, Nb, Dp, Dp, Tp * Dp, need_grad)
         else:
             if x.dtype != torch.float32:
                 x = x.float()

