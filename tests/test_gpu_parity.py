@@ -213,7 +213,8 @@ def test_gemm_vs_fp32(M, N, K):
     ref = a.float() @ b.float().t()       # plain fp32 reference on the same bf16-rounded operands
     for tile in (0, 64, 128, 256):
         c = ops.gemm_tn(a, b, tile_n=tile)
-        assert relnorm(c, ref) < 1e-5, (tile, relnorm(c, ref))
+        # tensor-core accumulation of K=25600 terms: 3e-5 against fp64 (torch fp32 FMA: 2e-6), profiles/gemm_accuracy_r1.txt
+        assert relnorm(c, ref) < (1e-5 if K <= 4096 else 1e-4), (tile, relnorm(c, ref))
     acc = ops.gemm_tn(a, b, out=ref.clone(), accumulate=True)
     assert relnorm(acc, 2 * ref) < (1e-5 if K <= 4096 else 1e-4), relnorm(acc, 2 * ref)
 
