@@ -195,6 +195,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Same for SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row atoms 512 bytes apart, tile base 512-byte aligned.
+// Used for the recurrent kernels' B operand so that the 32 hidden units one CTA produces form one contiguous block.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;            // SWIZZLE_64B
+    return d;
+}
+
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4)                              // D format f32

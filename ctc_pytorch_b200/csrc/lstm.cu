@@ -13,7 +13,7 @@
 // per step issues one tcgen05.mma chain (M=128, N=batch tile, K=H) into a TMEM accumulator.
 // The only per-step traffic is the all-gather of h_t (H x NB bf16) between the H/32 CTAs of a
 // (direction, batch-group): every CTA writes its 32 units into a global "operand image" that is
-// already laid out as the next step's K-major SWIZZLE_128B B operand, releases a counter, and all
+// already laid out as the next step's K-major SWIZZLE_64B B operand, releases a counter, and all
 // CTAs copy the image back into shared memory. Gate non-linearities, the cell update and the
 // hadamard products are fused in registers between tcgen05.ld and the image store.
 //
@@ -55,11 +55,13 @@ __device__ __forceinline__ uint4 pack8_bf16(float v) {
     return make_uint4(p1, p2, p3, p4);
 }
 
-// Element offset (bf16 units) of unit `u`, batch row `n` inside a [H x NB] K-major SWIZZLE_128B image.
+// Element offset (bf16 units) of the 16-byte chunk holding unit `u` (u % 8 == 0), batch row `n`, inside a [H x NB]
+// K-major SWIZZLE_64B operand image: K blocks of 32 units = [NB rows x 64 bytes], 16-byte chunk c of row n stored at
+// position c ^ ((n >> 1) & 3). The 32 units a CTA produces are therefore one contiguous NB*64-byte block.
 template <int NB>
 __device__ __forceinline__ int image_chunk_offset(int u, int n) {
-    const int kb = u >> 6, c = (u & 63) >> 3;
-    return kb * (NB * 64) + n * 64 + ((c ^ (n & 7)) << 3);
+    const int kb = u >> 5, c = (u & 31) >> 3;
+    return kb * (NB * 32) + n * 32 + ((c ^ ((n >> 1) & 3)) << 3);
 }
 
 // ---- thread-block-cluster primitives (distributed shared memory exchange) ------------------------------
@@ -89,6 +91,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t
     const uint32_t raddr = mapa_shared(smem_u32(local_bar), cta_rank);
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+// bulk (TMA-engine) copy of `bytes` from this CTA's shared memory into a peer CTA's shared memory; the peer's
+// mbarrier receives complete_tx(bytes) when the data has landed — no separate arrive, no release fence
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_cluster_addr),
+                 "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -144,8 +158,10 @@ template <int NB, int EX>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     // EX = 0: global image + global counter (cooperative launch, any H)
-    // EX = 1: cluster, data pushed through DSMEM            EX = 2: cluster, data through L2, hand-off on DSMEM mbarriers
-    constexpr bool CL = EX != 0, PUSH = EX == 1, HYB = EX == 2;
+    // EX = 1: cluster, data pushed through DSMEM stores     EX = 2: cluster, data through L2, hand-off on DSMEM mbarriers
+    // EX = 3: cluster, one bulk (TMA-engine) copy per peer with complete_tx on the peer's mbarrier
+    constexpr bool CL = EX != 0, PUSH = EX == 1 || EX == 3, BULK = EX == 3, HYB = EX == 2;
+    constexpr uint32_t BLK_BYTES = NB * 64;  // the 32 units x NB batch rows this CTA contributes to the operand image
     constexpr int CPT = NB / 2;        // accumulator columns per thread
     constexpr int EPT = NB / 8;        // (unit, batch) elements per thread in the cell update
     constexpr int S_STRIDE = NB * 4 + 4;
@@ -173,11 +189,15 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     if (tid == 0) {
         tma_prefetch_desc(&tmW);
         mbar_init(w_full, 1);
-        mbar_init(&h_full[0], CL ? ctas : LSTM_THREADS);
-        mbar_init(&h_full[1], CL ? ctas : LSTM_THREADS);
+        mbar_init(&h_full[0], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
+        mbar_init(&h_full[1], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
         mbar_init(acc_full, 1);
         mbar_init(l_full, LSTM_THREADS);
         fence_mbar_init();
+        if constexpr (BULK) {  // arm both parities: each expects one block from every CTA of the cluster
+            mbar_expect_tx(&h_full[0], ctas * BLK_BYTES);
+            mbar_expect_tx(&h_full[1], ctas * BLK_BYTES);
+        }
     }
     // TMEM: accumulator in columns [0, 32), the weight slice (A operand) in columns [32, 32 + H/2) when resident
     uint32_t tmem_cols = 32;
@@ -205,6 +225,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     }
 
     const int lq = warp & 3, ch = warp >> 2;
+    const bool warp_leader = elect_one();      // the lane of each warp that issues / tracks its bulk copies
     const int row = lq * 32 + lane;            // gate row inside this CTA's 128
     const int u_loc = row >> 2, q = row & 3;   // hidden unit (0..31) and gate (i,f,g,o)
     const float act_s = (q == 2) ? 2.0f : 1.0f;
@@ -249,7 +270,12 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
         // descriptors live in uniform registers; one elected lane issues each tcgen05.mma
         if (warp == 0) {
             if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
-            if constexpr (PUSH) {
+            if constexpr (BULK) {
+                if (t > 0) {
+                    mbar_wait(&h_full[t & 1], ((t - 1) >> 1) & 1);                // every peer's block has landed
+                    if (lane == 0) mbar_expect_tx(&h_full[t & 1], ctas * BLK_BYTES);  // re-arm for step t+2
+                }
+            } else if constexpr (PUSH) {
                 if (t > 0) mbar_wait_cluster(&h_full[t & 1], ((t - 1) >> 1) & 1);  // all peers pushed h_{t-1}
                 fence_proxy_async_all();   // peers' generic-proxy DSMEM writes -> tensor-core (async proxy) reads
             } else {
@@ -262,24 +288,25 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             if (p.a_tmem) {
 #pragma unroll 1
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const uint64_t bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
+                    const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
                     const uint32_t ta = tmem_base + 32 + kb * 32;
                     if (leader) {
                         umma_bf16_ts(tmem_base, ta, bd, idesc, kb != 0 ? 1u : 0u);
                         umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 16, bd + 4, idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 24, bd + 6, idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
             } else {
 #pragma unroll 1
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw64(b0 + kb * (NB * 128));
                     if (leader) {
                         umma_bf16(tmem_base, ad, bd, idesc, kb != 0 ? 1u : 0u);
                         umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
             }
@@ -305,6 +332,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             sS[u_loc * S_STRIDE + (ch * CPT + c) * 4 + q] = a;
         }
         TRACE(10);
+        if constexpr (BULK) { if (warp_leader) bulk_wait_read_all(); }  // last step's copies have finished reading sOut
         __syncthreads();
         TRACE(5); TRACE(11);
         // (7) cell update for (unit = lane, batch n = warp + 8e); publish h_t as the next step's B operand
@@ -321,7 +349,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             gv[e] = g4;
             const uint4 pk = pack8_bf16(h);
             if ((lane & 7) == 0) {
-                if constexpr (PUSH) sOut[n * 4 + (lane >> 3)] = pk;
+                // staging in destination order: chunk `oct` of row n sits at slot oct ^ ((n >> 1) & 3) of the row
+                if constexpr (PUSH) sOut[n * 4 + ((lane >> 3) ^ ((n >> 1) & 3))] = pk;
                 else *reinterpret_cast<uint4*>(img + static_cast<size_t>((t + 1) & 1) * H * NB +
                                                image_chunk_offset<NB>(j * 32 + lane, n)) = pk;
             }
@@ -333,19 +362,35 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             __syncthreads();
             if (t + 1 < T && tid < ctas) mbar_arrive_remote(&h_full[(t + 1) & 1], static_cast<uint32_t>(tid));
             TRACE(7);
+        } else if constexpr (BULK) {
+            fence_proxy_async_smem();   // staging writes (generic proxy) -> bulk-copy engine (async proxy)
+            __syncthreads();
+            TRACE(6);
+            if (t + 1 < T) {
+                // one bulk copy per peer (our contiguous block -> slot j of the peer's next operand buffer); warp w
+                // serves peers w and w + 8 so the copies are issued in parallel with warp-uniform operands
+                const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_BYTES;
+                const uint32_t bar = smem_u32(&h_full[(t + 1) & 1]);
+#pragma unroll
+                for (int d = warp; d < 16; d += 8) {
+                    if (d < ctas && warp_leader)
+                        bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), smem_u32(sOut), BLK_BYTES,
+                                          mapa_shared(bar, static_cast<uint32_t>(d)));
+                }
+                if (warp_leader) bulk_commit();
+            }
+            TRACE(13); TRACE(7);
         } else if constexpr (PUSH) {
             __syncthreads();
             TRACE(6);
             if (t + 1 < T) {
                 // push this CTA's OUT_CHUNKS chunks into buffer (t+1)&1 of every CTA of the cluster
-                const uint32_t next_base = smem_u32(sH) + ((t + 1) & 1) * himg_bytes;
+                const uint32_t next_base = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_BYTES;
                 for (int idx = tid; idx < OUT_CHUNKS * ctas; idx += LSTM_THREADS) {
                     const int c = idx % OUT_CHUNKS;
                     int d = idx / OUT_CHUNKS + j;  // start with the own rank: spreads the senders over the receivers
                     if (d >= ctas) d -= ctas;
-                    const int n = c >> 2, oct = c & 3;
-                    const uint32_t local = next_base + image_chunk_offset<NB>(j * 32 + oct * 8, n) * 2;
-                    st_cluster_v4(mapa_shared(local, static_cast<uint32_t>(d)), sOut[c]);
+                    st_cluster_v4(mapa_shared(next_base + c * 16, static_cast<uint32_t>(d)), sOut[c]);
                 }
             }
             TRACE(13);
@@ -402,7 +447,8 @@ struct BwdParams {
 template <int NB, int EX>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
-    constexpr bool CL = EX != 0, PUSH = EX == 1, HYB = EX == 2;  // exchange modes as in the forward kernel
+    constexpr bool CL = EX != 0, PUSH = EX == 1 || EX == 3, BULK = EX == 3, HYB = EX == 2;  // as in the forward kernel
+    constexpr uint32_t BLK_BYTES = NB * 64;
     constexpr int CPT = NB / 2;
     constexpr int EPT = NB / 8;
     constexpr int OUT_CHUNKS = NB * 4;
@@ -414,7 +460,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     uint8_t* sB = sW + (p.a_tmem ? 0 : 128 * H * 2);                  // PUSH: two buffers, else one
     float* sR = reinterpret_cast<float*>(sB + (PUSH ? 2 : 1) * img_bytes);  // [4 src][NB][32] partial dh blocks
     uint4* sOut = reinterpret_cast<uint4*>(sR + 4 * NB * 32);         // PUSH only: [4 gates][OUT_CHUNKS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (PUSH ? 4 * OUT_CHUNKS : 0));
+    float* sP = reinterpret_cast<float*>(sOut + (PUSH ? 4 * OUT_CHUNKS : 0));  // BULK only: [4 dst][NB][32] partial staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (BULK ? 4 * NB * 32 : 0));
     uint64_t* w_full = bars;
     uint64_t* b_full = bars + 1;   // [2]
     uint64_t* acc_full = bars + 3;
@@ -435,12 +482,17 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     if (tid == 0) {
         tma_prefetch_desc(&tmWT);
         mbar_init(w_full, 1);
-        mbar_init(&b_full[0], CL ? ctas : LSTM_THREADS);
-        mbar_init(&b_full[1], CL ? ctas : LSTM_THREADS);
+        mbar_init(&b_full[0], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
+        mbar_init(&b_full[1], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
         mbar_init(acc_full, 1);
-        mbar_init(r_full, 4);
+        mbar_init(r_full, BULK ? 1 : 4);
         mbar_init(l_full, LSTM_THREADS);
         fence_mbar_init();
+        if constexpr (BULK) {
+            mbar_expect_tx(&b_full[0], ctas * BLK_BYTES);
+            mbar_expect_tx(&b_full[1], ctas * BLK_BYTES);
+            mbar_expect_tx(r_full, 4 * NB * 32 * 4);  // four gate partials of [NB][32] floats per step
+        }
     }
     uint32_t tmem_cols = 32;
     if (p.a_tmem) { while (tmem_cols < 32u + H / 2) tmem_cols <<= 1; }
@@ -469,6 +521,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     }
 
     const int lq = warp & 3, ch = warp >> 2;
+    const bool warp_leader = elect_one();
     const int unit = mb * 128 + q * 32 + lane;  // the unit this thread finishes in the element phase
     const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
     const size_t dg_col = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4;
@@ -520,7 +573,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         // (4) partial dh[128 units, NB] = W_q^T slice * dG_q (issued like the forward kernel's chain)
         if (warp == 0) {
             if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
-            if constexpr (PUSH) {
+            if constexpr (BULK) {
+                if (t > 0) {
+                    mbar_wait(&b_full[t & 1], ((t - 1) >> 1) & 1);
+                    if (lane == 0) mbar_expect_tx(&b_full[t & 1], ctas * BLK_BYTES);
+                }
+            } else if constexpr (PUSH) {
                 if (t > 0) mbar_wait_cluster(&b_full[t & 1], ((t - 1) >> 1) & 1);
                 fence_proxy_async_all();
             } else {
@@ -532,24 +590,25 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             if (p.a_tmem) {
 #pragma unroll 1
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const uint64_t bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
+                    const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
                     const uint32_t ta = tmem_base + 32 + kb * 32;
                     if (leader) {
                         umma_bf16_ts(tmem_base, ta, bd, idesc, kb != 0 ? 1u : 0u);
                         umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 16, bd + 4, idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 24, bd + 6, idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(tmem_base, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
             } else {
 #pragma unroll 1
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw128(b0 + kb * (NB * 128));
+                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw64(b0 + kb * (NB * 128));
                     if (leader) {
                         umma_bf16(tmem_base, ad, bd, idesc, kb != 0 ? 1u : 0u);
                         umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
             }
@@ -564,14 +623,34 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         else tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, acc);
         tmem_ld_wait();
         tc_fence_before();
+        if constexpr (BULK) {
+            // every warp holds the [NB/2][32] sub-block of partial rows that belongs to CTA (lq, mb): stage it, then
+            // one bulk copy per warp into that CTA's receive slot for source gate q (complete_tx on its r_full)
+            if (warp_leader) bulk_wait_read_all();  // this warp's earlier copies have finished reading shared memory
+            __syncthreads();                         // ... for every warp: sP and sOut may be rewritten
+            float* stage = sP + (lq * NB + ch * CPT) * 32 + lane;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) st_cluster_f32(remote_base + c * 32 * 4, __uint_as_float(acc[c]));
-        if constexpr (CL) {
-            __syncthreads();
-            if (tid < 4) mbar_arrive_remote(r_full, rank_of(tid, mb));
-            mbar_wait_cluster(r_full, t & 1);
+            for (int c = 0; c < CPT; ++c) stage[c * 32] = __uint_as_float(acc[c]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (warp_leader) {
+                const uint32_t peer = rank_of(lq, mb);
+                bulk_copy_to_peer(mapa_shared(smem_u32(sR + (q * NB + ch * CPT) * 32), peer),
+                                  smem_u32(sP + (lq * NB + ch * CPT) * 32), CPT * 32 * 4, mapa_shared(smem_u32(r_full), peer));
+                bulk_commit();
+            }
+            mbar_wait(r_full, t & 1);
+            if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * 4);  // re-arm for the next step
         } else {
-            cluster_sync_all();
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) st_cluster_f32(remote_base + c * 32 * 4, __uint_as_float(acc[c]));
+            if constexpr (CL) {
+                __syncthreads();
+                if (tid < 4) mbar_arrive_remote(r_full, rank_of(tid, mb));
+                mbar_wait_cluster(r_full, t & 1);
+            } else {
+                cluster_sync_all();
+            }
         }
         // (6) finish 32 units: recurrent dh, LSTM cell backward, publish the four gate gradients
         uint2 dgp[EPT];
@@ -594,7 +673,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             const uint4 pi = pack8_bf16(d_i), pf = pack8_bf16(d_f), pg = pack8_bf16(d_g), po = pack8_bf16(d_o);
             if ((lane & 7) == 0) {
                 if constexpr (PUSH) {
-                    const int c = n * 4 + (lane >> 3);
+                    const int c = n * 4 + ((lane >> 3) ^ ((n >> 1) & 3));  // destination order inside the block
                     sOut[0 * OUT_CHUNKS + c] = pi;
                     sOut[1 * OUT_CHUNKS + c] = pf;
                     sOut[2 * OUT_CHUNKS + c] = pg;
@@ -615,18 +694,35 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             __threadfence();
             __syncthreads();
             if (t + 1 < T && tid < ctas) mbar_arrive_remote(&b_full[(t + 1) & 1], static_cast<uint32_t>(tid));
+        } else if constexpr (BULK) {
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (t + 1 < T) {
+                // copy i = (g, mdst): gate g's block of this CTA's 32 units -> slot (4 mb + q) of CTA (g, mdst)'s buffer;
+                // warp w issues copies w and w + 8
+                const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_BYTES;
+                const uint32_t bar = smem_u32(&b_full[(t + 1) & 1]);
+#pragma unroll
+                for (int i = warp; i < 16; i += 8) {
+                    const int g = i & 3, mdst = i >> 2;
+                    if (mdst < MB && warp_leader) {
+                        const uint32_t peer = rank_of(g, mdst);
+                        bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * OUT_CHUNKS), BLK_BYTES,
+                                          mapa_shared(bar, peer));
+                    }
+                }
+                if (warp_leader) bulk_commit();
+            }
         } else if constexpr (PUSH) {
             __syncthreads();
             if (t + 1 < T) {
                 // gate g's chunks of this CTA's 32 units go to the operand buffer of every CTA (g, mb')
-                const uint32_t next_base = smem_u32(sB) + ((t + 1) & 1) * img_bytes;
+                const uint32_t next_base = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_BYTES;
                 const int per_gate = OUT_CHUNKS * MB;
                 for (int idx = tid; idx < 4 * per_gate; idx += LSTM_THREADS) {
                     const int g = idx / per_gate, r = idx - g * per_gate;
                     const int mdst = r / OUT_CHUNKS, c = r - mdst * OUT_CHUNKS;
-                    const int n = c >> 2, oct = c & 3;
-                    const uint32_t local = next_base + image_chunk_offset<NB>(mb * 128 + q * 32 + oct * 8, n) * 2;
-                    st_cluster_v4(mapa_shared(local, rank_of(g, mdst)), sOut[g * OUT_CHUNKS + c]);
+                    st_cluster_v4(mapa_shared(next_base + c * 16, rank_of(g, mdst)), sOut[g * OUT_CHUNKS + c]);
                 }
             }
             __syncthreads();
@@ -656,25 +752,28 @@ bool weights_in_tmem() {
 }
 
 size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool a_tmem) {
-    const bool push = ex == 1;
+    const bool push = ex == 1 || ex == 3;
     size_t b = (a_tmem ? 0 : static_cast<size_t>(128) * H * 2) + static_cast<size_t>(push ? 2 : 1) * H * NB * 2;
-    if (bwd) b += static_cast<size_t>(4) * NB * 32 * 4 + (push ? static_cast<size_t>(4) * NB * 4 * 16 : 0);
+    if (bwd) b += static_cast<size_t>(4) * NB * 32 * 4 + (push ? static_cast<size_t>(4) * NB * 4 * 16 : 0) +
+                  (ex == 3 ? static_cast<size_t>(4) * NB * 32 * 4 : 0);
     else b += static_cast<size_t>(32) * (NB * 4 + 4) * 4 + (push ? static_cast<size_t>(NB) * 4 * 16 : 0);
     return b + 64 + 1024;
 }
 
 // How the CTAs of one (direction, batch group) hand h_t / dG_t to each other every step:
-//   1 (default for H <= 512)  one thread-block cluster; h_t / dG_t pushed through DSMEM, remote mbarrier hand-off
+//   1                         one thread-block cluster; h_t / dG_t pushed with DSMEM stores, remote mbarrier hand-off
 //   2                         one cluster; data through L2, hand-off on remote (DSMEM) mbarriers
 //   0 (H > 512)               global image + global release/acquire counter, cooperative launch
-// CTCB200_LSTM_EXCHANGE = global | push | hybrid overrides the choice (A/B measurements).
+//   3 (default for H <= 512)  one cluster; one bulk (TMA-engine) DSMEM copy per peer, complete_tx on the peer's mbarrier
+// CTCB200_LSTM_EXCHANGE = global | push | hybrid | bulk overrides the choice (A/B measurements).
 int exchange_mode(int H) {
     const bool fits = H <= 512;  // H/32 CTAs (forward) and 4*H/128 CTAs (backward) fit one cluster of <= 16
     const char* e = getenv("CTCB200_LSTM_EXCHANGE");
     if (e && e[0] == 'g') return 0;
     if (!fits) return 0;
     if (e && e[0] == 'h') return 2;
-    return 1;  // measured on B200 (cfg2, NB=16): push 6.6k cycles/step, hybrid 6.8k, global 9.3k
+    if (e && e[0] == 'p') return 1;
+    return 3;  // measured on B200 (cfg2, NB=16, cycles/step): bulk 4.5k, push 6.6k, hybrid 6.8k, global 9.3k
 }
 
 int pick_nb(int N, int H, int force_nb, bool bwd, bool cl) {
@@ -791,6 +890,10 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
             if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 2>, grid, cluster, smem, false, tmW, p, stream);
             return launch_clustered(lstm_fwd_kernel<32, 2>, grid, cluster, smem, false, tmW, p, stream);
         }
+        if (ex == 3) {
+            if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 3>, grid, cluster, smem, false, tmW, p, stream);
+            return launch_clustered(lstm_fwd_kernel<32, 3>, grid, cluster, smem, false, tmW, p, stream);
+        }
         if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 1>, grid, cluster, smem, false, tmW, p, stream);
         return launch_clustered(lstm_fwd_kernel<32, 1>, grid, cluster, smem, false, tmW, p, stream);
     }
@@ -848,6 +951,10 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
             p.dgimg = static_cast<__nv_bfloat16*>(scratch);
             if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 2>, grid, cluster, smem, false, tmWT, p, stream);
             return launch_clustered(lstm_bwd_kernel<32, 2>, grid, cluster, smem, false, tmWT, p, stream);
+        }
+        if (ex == 3) {
+            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 3>, grid, cluster, smem, false, tmWT, p, stream);
+            return launch_clustered(lstm_bwd_kernel<32, 3>, grid, cluster, smem, false, tmWT, p, stream);
         }
         if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 1>, grid, cluster, smem, false, tmWT, p, stream);
         return launch_clustered(lstm_bwd_kernel<32, 1>, grid, cluster, smem, false, tmWT, p, stream);
