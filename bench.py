@@ -203,7 +203,7 @@ def run_ours(args, cfg, rank, world):
     # L2 flush buffer (larger than the 126 MB L2) written between timed steps of the device-resident loop
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def step_dev(b, fetch=False):
+    def step_dev(b, fetch=False, comm=True):
         x, frac, tg, tl = b
         out = model(x)
         out_len, bsz, _ = out.size()
@@ -212,7 +212,8 @@ def run_ours(args, cfg, rank, world):
         _, labels, lens = ops.greedy_decode(out, il, blank=0)
         bucket.attach()
         loss.backward()
-        bucket.allreduce_mean()
+        if comm:
+            bucket.allreduce_mean()
         opt.step()
         if fetch:
             return loss.item(), labels.cpu(), lens.cpu()
@@ -278,7 +279,7 @@ def run_ours(args, cfg, rank, world):
     prof_steps = 3
     for k in range(prof_steps):
         flush.zero_()
-        step_dev(devb[k % n_batches])
+        step_dev(devb[k % n_batches], comm=False)  # rank 0 only: no collective in this diagnostic pass
     torch.cuda.synchronize()
     L.call = orig_call
     kern_ms = {nm: sum(s.elapsed_time(e) for s, e in v) / prof_steps for nm, v in per_call.items()}
@@ -357,6 +358,10 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CFG))
     args = ap.parse_args()
     cfg = CFG[args.config]
+    wd = int(os.environ.get("BENCH_WATCHDOG", "0"))
+    if wd > 0:  # debugging aid: dump every thread's stack if the run is still alive after `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, repeat=True, file=sys.stderr)
     from ctc_pytorch_b200.dist import init_from_env
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
