@@ -7,10 +7,15 @@
 // alignment gives +inf loss (zero_infinity=False), and the gradient is emitted in the convention
 // of torch's native kernel: d/dlog_probs = exp(lp) - exp(log-sum_{s:l'_s=c}(alpha+beta) + nll - lp).
 //
-// Mapping: one warp owns one utterance; the 2S+1 lattice states are blocked over the 32 lanes
-// (KS consecutive states per lane) so the s-1 / s-2 neighbours are lane-local except at block
-// edges, where one or two warp shuffles fetch them. Each (t, n) row of log-probs is brought in once
-// with coalesced cp.async into a per-warp double buffer, one step ahead of its use.
+// Mapping: the T-step dependency chains are the cost at N=32, so the alpha sweep (t = 0..T-1) and the beta sweep
+// (t = T-1..0) of an utterance run CONCURRENTLY in two warps of one launch; each stores its (renormalised) history.
+// Inside a warp the 2S+1 lattice states are blocked over the 32 lanes (KS consecutive states per lane) so the
+// s-1 / s-2 neighbours are lane-local except at block edges, where one or two warp shuffles fetch them; each
+// (t, n) row of log-probs is brought in with coalesced cp.async into a per-warp double buffer one step ahead.
+// The gradient is then a fully parallel kernel (one warp per (t, n) row): posteriors exp(alpha+beta+nll-lp) are
+// accumulated per class in shared memory, grad = exp(lp) - occupancy.
+// Numerics: every RENORM frames a sweep subtracts its row maximum and accumulates the removed log-scale in double;
+// the per-row scales are stored so the posterior exponent is formed as (a~ + b~ - lp) + float(A_t + B_t + nll).
 #include "common.cuh"
 #include "ctcb200.h"
 
@@ -72,210 +77,197 @@ __device__ __forceinline__ void load_states(LaneStates<KS>& st, const int64_t* t
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward: log-alpha sweep; writes alpha history [N][T][KS*32] (slot j*32+lane) and nll[N]
+// sweeps: warp 2k -> alpha of utterance k, warp 2k+1 -> beta of utterance k (same block)
+// workspace per utterance: hist_a / hist_b [T][KS*32] floats (slot j*32+lane), off_a / off_b [T] doubles (log-scale
+// removed from the stored row), nll_d (double)
 // ---------------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-ctc_alpha_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
-                 const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
-                 float* __restrict__ alpha_ws, double* __restrict__ offs_ws, float* __restrict__ nll, int T, int N,
-                 int C, int blank) {
+ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
+                 const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len, float* __restrict__ hist_a,
+                 float* __restrict__ hist_b, double* __restrict__ off_a, double* __restrict__ off_b,
+                 double* __restrict__ nll_d, float* __restrict__ nll, int T, int N, int C, int blank) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int n = blockIdx.x * (WARPS_PER_BLOCK / 2) + (warp >> 1);
+    const bool is_beta = warp & 1;
     if (n >= N) return;
     float* rowbuf = smem + warp * 2 * C;  // two rows
-    // offs[g] = total log-scale removed from alpha up to and including renormalisation group g; offs[G] = exact nll
-    double* offs = offs_ws + static_cast<size_t>(n) * (T / RENORM + 2);
 
     const int S = static_cast<int>(tgt_len[n]);
     const int L = 2 * S + 1;
     int Tn = static_cast<int>(in_len[n]);
     if (Tn > T) Tn = T;
     if (Tn <= 0) {
-        if (lane == 0) {
+        if (lane == 0 && !is_beta) {
             nll[n] = (S == 0) ? 0.0f : INFINITY;
-            offs[T / RENORM + 1] = (S == 0) ? 0.0 : static_cast<double>(INFINITY);
+            nll_d[n] = (S == 0) ? 0.0 : static_cast<double>(INFINITY);
         }
         return;
     }
     LaneStates<KS> st;
     load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
-
     const size_t row_stride = static_cast<size_t>(N) * C;
     const float* lp_n = lp + static_cast<size_t>(n) * C;
-    float* aws = alpha_ws + static_cast<size_t>(n) * T * (KS * 32);
-
-    prefetch_row(rowbuf, lp_n, C, lane);
+    float* hist = (is_beta ? hist_b : hist_a) + static_cast<size_t>(n) * T * (KS * 32);
+    double* offs = (is_beta ? off_b : off_a) + static_cast<size_t>(n) * T;
+    double scale_acc = 0.0;  // log-scale removed so far (double: the stored rows stay O(100) however long the utterance)
     float a[KS];
-    double scale_acc = 0.0;  // log-scale removed so far (kept in double: the stored alphas stay O(100))
-    for (int t = 0; t < Tn; ++t) {
-        float* cur = rowbuf + (t & 1) * C;
-        cp_async_wait_all();
-        __syncwarp();
-        if (t + 1 < Tn) prefetch_row(rowbuf + ((t + 1) & 1) * C, lp_n + (t + 1) * row_stride, C, lane);
-        if (t == 0) {
+
+    if (!is_beta) {
+        prefetch_row(rowbuf, lp_n, C, lane);
+        for (int t = 0; t < Tn; ++t) {
+            float* cur = rowbuf + (t & 1) * C;
+            cp_async_wait_all();
+            __syncwarp();
+            if (t + 1 < Tn) prefetch_row(rowbuf + ((t + 1) & 1) * C, lp_n + (t + 1) * row_stride, C, lane);
+            if (t == 0) {
 #pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                int s = lane * KS + j;
-                a[j] = (st.valid[j] && s < 2) ? cur[st.label[j]] : NEG_INF;
+                for (int j = 0; j < KS; ++j) {
+                    int s = lane * KS + j;
+                    a[j] = (st.valid[j] && s < 2) ? cur[st.label[j]] : NEG_INF;
+                }
+            } else {
+                float up1 = __shfl_up_sync(0xffffffffu, a[KS - 1], 1);
+                float up2 = (KS >= 2) ? __shfl_up_sync(0xffffffffu, a[KS >= 2 ? KS - 2 : 0], 1)
+                                      : __shfl_up_sync(0xffffffffu, a[0], 2);
+                if (lane == 0) { up1 = NEG_INF; up2 = NEG_INF; }
+                if (KS == 1 && lane == 1) up2 = NEG_INF;
+                float nw[KS];
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {
+                    float p1 = (j >= 1) ? a[j >= 1 ? j - 1 : 0] : up1;
+                    float p2 = (j >= 2) ? a[j >= 2 ? j - 2 : 0] : ((j == 1) ? up1 : up2);
+                    if (KS >= 2 && j == 0) p2 = up2;
+                    if (!st.skip_in[j]) p2 = NEG_INF;
+                    float v = lse3(a[j], p1, p2);
+                    nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+                }
+#pragma unroll
+                for (int j = 0; j < KS; ++j) a[j] = nw[j];
             }
-        } else {
-            // neighbours from the previous lane
-            float up1 = __shfl_up_sync(0xffffffffu, a[KS - 1], 1);
-            float up2 = (KS >= 2) ? __shfl_up_sync(0xffffffffu, a[KS >= 2 ? KS - 2 : 0], 1)
-                                  : __shfl_up_sync(0xffffffffu, a[0], 2);
-            if (lane == 0) { up1 = NEG_INF; up2 = NEG_INF; }
-            if (KS == 1 && lane == 1) up2 = NEG_INF;
-            float nw[KS];
+            if ((t % RENORM) == RENORM - 1 || t == Tn - 1) {
+                float m = NEG_INF;
 #pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                float p1 = (j >= 1) ? a[j >= 1 ? j - 1 : 0] : up1;
-                float p2 = (j >= 2) ? a[j >= 2 ? j - 2 : 0] : ((j == 1) ? up1 : up2);
-                if (KS >= 2 && j == 0) p2 = up2;
-                if (!st.skip_in[j]) p2 = NEG_INF;
-                float v = lse3(a[j], p1, p2);
-                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+                for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (m > NEG_INF) {
+#pragma unroll
+                    for (int j = 0; j < KS; ++j) a[j] -= m;
+                    scale_acc += static_cast<double>(m);
+                }
             }
+            if (lane == 0) offs[t] = scale_acc;
 #pragma unroll
-            for (int j = 0; j < KS; ++j) a[j] = nw[j];
+            for (int j = 0; j < KS; ++j) hist[static_cast<size_t>(t) * (KS * 32) + j * 32 + lane] = a[j];
         }
-        if ((t % RENORM) == RENORM - 1 || t == Tn - 1) {
-            // renormalise: subtract the row maximum so float32 keeps ~1e-6 absolute resolution however long the utterance
-            float m = NEG_INF;
+        // nll = -lse(alpha_{Tn-1}(L-1), alpha_{Tn-1}(L-2))
+        float loc = NEG_INF;
 #pragma unroll
-            for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (m > NEG_INF) {
-#pragma unroll
-                for (int j = 0; j < KS; ++j) a[j] -= m;
-                scale_acc += static_cast<double>(m);
-            }
-            if (lane == 0) offs[t / RENORM] = scale_acc;
+        for (int j = 0; j < KS; ++j) {
+            int s = lane * KS + j;
+            if (s == L - 1 || s == L - 2) loc = lse2(loc, a[j]);
         }
 #pragma unroll
-        for (int j = 0; j < KS; ++j) aws[static_cast<size_t>(t) * (KS * 32) + j * 32 + lane] = a[j];
-    }
-    // nll = -lse(alpha_{Tn-1}(L-1), alpha_{Tn-1}(L-2))
-    float loc = NEG_INF;
+        for (int o = 16; o >= 1; o >>= 1) loc = lse2(loc, __shfl_xor_sync(0xffffffffu, loc, o));
+        if (lane == 0) {
+            const double v = -(static_cast<double>(loc) + scale_acc);
+            nll[n] = static_cast<float>(v);
+            nll_d[n] = v;
+        }
+    } else {
+        prefetch_row(rowbuf + ((Tn - 1) & 1) * C, lp_n + (Tn - 1) * row_stride, C, lane);
+        for (int t = Tn - 1; t >= 0; --t) {
+            float* cur = rowbuf + (t & 1) * C;
+            cp_async_wait_all();
+            __syncwarp();
+            if (t > 0) prefetch_row(rowbuf + ((t - 1) & 1) * C, lp_n + (t - 1) * row_stride, C, lane);
+            if (t == Tn - 1) {
 #pragma unroll
-    for (int j = 0; j < KS; ++j) {
-        int s = lane * KS + j;
-        if (s == L - 1 || s == L - 2) loc = lse2(loc, a[j]);
-    }
+                for (int j = 0; j < KS; ++j) {
+                    int s = lane * KS + j;
+                    a[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
+                }
+            } else {
+                float dn1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+                float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
+                                      : __shfl_down_sync(0xffffffffu, a[0], 2);
+                if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
+                if (KS == 1 && lane == 30) dn2 = NEG_INF;
+                float nw[KS];
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) loc = lse2(loc, __shfl_xor_sync(0xffffffffu, loc, o));
-    if (lane == 0) {
-        const double nll_d = -(static_cast<double>(loc) + scale_acc);
-        nll[n] = static_cast<float>(nll_d);
-        offs[T / RENORM + 1] = nll_d;
+                for (int j = 0; j < KS; ++j) {
+                    float n1 = (j + 1 < KS) ? a[j + 1 < KS ? j + 1 : 0] : dn1;
+                    float n2 = (j + 2 < KS) ? a[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
+                    if (KS >= 2 && j == KS - 1) n2 = dn2;
+                    if (!st.skip_out[j]) n2 = NEG_INF;
+                    float v = lse3(a[j], n1, n2);
+                    nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+                }
+#pragma unroll
+                for (int j = 0; j < KS; ++j) a[j] = nw[j];
+            }
+            if ((t % RENORM) == 0) {
+                float m = NEG_INF;
+#pragma unroll
+                for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (m > NEG_INF) {
+#pragma unroll
+                    for (int j = 0; j < KS; ++j) a[j] -= m;
+                    scale_acc += static_cast<double>(m);
+                }
+            }
+            if (lane == 0) offs[t] = scale_acc;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) hist[static_cast<size_t>(t) * (KS * 32) + j * 32 + lane] = a[j];
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: log-beta sweep fused with the gradient row of every frame
+// gradient: one warp per (t, n) row, no dependency between rows
 // ---------------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
-                     const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
-                     const float* __restrict__ alpha_ws, const double* __restrict__ offs_ws,
-                     const float* __restrict__ grad_nll, float grad_scale, float* __restrict__ grad, int T, int N,
-                     int C, int blank) {
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
+                const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len, const float* __restrict__ hist_a,
+                const float* __restrict__ hist_b, const double* __restrict__ off_a, const double* __restrict__ off_b,
+                const double* __restrict__ nll_d, const float* __restrict__ grad_nll, float grad_scale,
+                float* __restrict__ grad, int T, int N, int C, int blank) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (n >= N) return;
-    float* rowbuf = smem + warp * 3 * C;  // two rows + occupancy accumulator
-    float* occ = rowbuf + 2 * C;
-
-    const int S = static_cast<int>(tgt_len[n]);
-    const int L = 2 * S + 1;
-    int Tn = static_cast<int>(in_len[n]);
-    if (Tn > T) Tn = T;
-    if (Tn < 0) Tn = 0;
-    const size_t row_stride = static_cast<size_t>(N) * C;
-    float* g_n = grad + static_cast<size_t>(n) * C;
-    // frames past the utterance end: zero gradient (torch semantics)
-    for (int t = Tn; t < T; ++t)
-        for (int c = lane; c < C; c += 32) g_n[t * row_stride + c] = 0.0f;
-    if (Tn == 0) return;
-
-    LaneStates<KS> st;
-    load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
-    const float* lp_n = lp + static_cast<size_t>(n) * C;
-    const float* aws = alpha_ws + static_cast<size_t>(n) * T * (KS * 32);
-    const double* offs = offs_ws + static_cast<size_t>(n) * (T / RENORM + 2);
-    const double nll_d = offs[T / RENORM + 1];
-    double scale_acc = 0.0;  // log-scale removed from beta so far
-    const float gscale = grad_scale * (grad_nll ? grad_nll[n] : 1.0f);
-
-    for (int c = lane; c < C; c += 32) occ[c] = 0.0f;
-    prefetch_row(rowbuf + ((Tn - 1) & 1) * C, lp_n + (Tn - 1) * row_stride, C, lane);
-
-    float b[KS];
-    for (int t = Tn - 1; t >= 0; --t) {
-        float* cur = rowbuf + (t & 1) * C;
-        // alpha_t for this lane's states: issued early, consumed after the recursion
-        float al[KS];
-#pragma unroll
-        for (int j = 0; j < KS; ++j) al[j] = __ldg(aws + static_cast<size_t>(t) * (KS * 32) + j * 32 + lane);
-        cp_async_wait_all();
+    const long long wpb = blockDim.x >> 5;
+    float* occ = smem + warp * C;
+    const long long rows = static_cast<long long>(T) * N;
+    for (long long row = blockIdx.x * wpb + warp; row < rows; row += gridDim.x * wpb) {
+        const int t = static_cast<int>(row / N), n = static_cast<int>(row % N);
+        float* g_row = grad + row * C;
+        int Tn = static_cast<int>(in_len[n]);
+        if (Tn > T) Tn = T;
+        if (t >= Tn) {  // frames past the utterance end: zero gradient (torch semantics)
+            for (int c = lane; c < C; c += 32) g_row[c] = 0.0f;
+            continue;
+        }
+        const int S = static_cast<int>(tgt_len[n]);
+        LaneStates<KS> st;
+        load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
+        const float* lp_row = lp + row * C;
+        for (int c = lane; c < C; c += 32) occ[c] = 0.0f;
         __syncwarp();
-        if (t > 0) prefetch_row(rowbuf + ((t - 1) & 1) * C, lp_n + (t - 1) * row_stride, C, lane);
-
-        if (t == Tn - 1) {
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                int s = lane * KS + j;
-                b[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
-            }
-        } else {
-            float dn1 = __shfl_down_sync(0xffffffffu, b[0], 1);
-            float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, b[KS >= 2 ? 1 : 0], 1)
-                                  : __shfl_down_sync(0xffffffffu, b[0], 2);
-            if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
-            if (KS == 1 && lane == 30) dn2 = NEG_INF;
-            float nw[KS];
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                float n1 = (j + 1 < KS) ? b[j + 1 < KS ? j + 1 : 0] : dn1;
-                float n2 = (j + 2 < KS) ? b[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
-                if (KS >= 2 && j == KS - 1) n2 = dn2;
-                if (!st.skip_out[j]) n2 = NEG_INF;
-                float v = lse3(b[j], n1, n2);
-                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
-            }
-#pragma unroll
-            for (int j = 0; j < KS; ++j) b[j] = nw[j];
-        }
-        if ((t % RENORM) == 0) {
-            float m = NEG_INF;
-#pragma unroll
-            for (int j = 0; j < KS; ++j) m = fmaxf(m, b[j]);
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (m > NEG_INF) {
-#pragma unroll
-                for (int j = 0; j < KS; ++j) b[j] -= m;
-                scale_acc += static_cast<double>(m);
-            }
-        }
-        // alpha_t was stored with the scale of its own group if t closes the group (or the utterance), else of the
-        // previous group; combine all log-scales with the exact nll in double, then drop to float once
-        const bool closes = ((t % RENORM) == RENORM - 1) || (t == Tn - 1);
-        const int ga = closes ? (t / RENORM) : (t / RENORM - 1);
-        const double a_off = ga >= 0 ? offs[ga] : 0.0;
-        const float shift = static_cast<float>(a_off + scale_acc + nll_d);
-        // state posteriors, accumulated per class in the linear domain
+        const size_t h = (static_cast<size_t>(n) * T + t) * (KS * 32);
+        const float shift = static_cast<float>(off_a[static_cast<size_t>(n) * T + t] + off_b[static_cast<size_t>(n) * T + t] +
+                                               nll_d[n]);
         float blank_sum = 0.0f;
 #pragma unroll
         for (int j = 0; j < KS; ++j) {
             if (st.valid[j]) {
-                float lpv = cur[st.label[j]];
-                float g = expf((al[j] + b[j] - lpv) + shift);
-                int s = lane * KS + j;
+                const float al = hist_a[h + j * 32 + lane], be = hist_b[h + j * 32 + lane];
+                const float lpv = __ldg(lp_row + st.label[j]);
+                const float g = expf((al + be - lpv) + shift);
+                const int s = lane * KS + j;
                 if (s & 1) atomicAdd(&occ[st.label[j]], g);
                 else blank_sum += g;
             }
@@ -284,12 +276,8 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
         for (int o = 16; o >= 1; o >>= 1) blank_sum += __shfl_xor_sync(0xffffffffu, blank_sum, o);
         if (lane == 0) atomicAdd(&occ[blank], blank_sum);
         __syncwarp();
-        float* g_row = g_n + t * row_stride;
-        for (int c = lane; c < C; c += 32) {
-            float r = expf(cur[c]) - occ[c];
-            g_row[c] = r * gscale;
-            occ[c] = 0.0f;
-        }
+        const float gscale = grad_scale * (grad_nll ? grad_nll[n] : 1.0f);
+        for (int c = lane; c < C; c += 32) g_row[c] = (expf(__ldg(lp_row + c)) - occ[c]) * gscale;
         __syncwarp();
     }
 }
@@ -302,18 +290,30 @@ int ks_for(int max_target_len) {
     return ks;
 }
 
+// workspace layout (floats): hist_a | hist_b | then doubles: off_a [N*T] | off_b [N*T] | nll_d [N]
+struct CtcWs {
+    float* hist_a; float* hist_b; double* off_a; double* off_b; double* nll_d;
+};
+int64_t hist_floats(int T, int N, int ks) { return ((static_cast<int64_t>(N) * T * ks * 32 + 1) / 2) * 2; }
+CtcWs carve(float* ws, int T, int N, int ks) {
+    CtcWs w;
+    w.hist_a = ws;
+    w.hist_b = ws + hist_floats(T, N, ks);
+    w.off_a = reinterpret_cast<double*>(ws + 2 * hist_floats(T, N, ks));
+    w.off_b = w.off_a + static_cast<int64_t>(N) * T;
+    w.nll_d = w.off_b + static_cast<int64_t>(N) * T;
+    return w;
+}
+
 }  // namespace
 
 }  // namespace ctcb200
 
 using namespace ctcb200;
 
-// alpha history [N][T][KS*32] floats, followed by [N][T/RENORM + 2] doubles of log-scale offsets (+ exact nll)
-static int64_t alpha_floats(int T, int N, int ks) { return ((static_cast<int64_t>(N) * T * ks * 32 + 1) / 2) * 2; }
-
 extern "C" CTCB200_API int64_t ctcb200_ctc_workspace_floats(int T, int N, int max_target_len) {
     int ks = ks_for(max_target_len);
-    return alpha_floats(T, N, ks) + static_cast<int64_t>(N) * (T / RENORM + 2) * 2;
+    return 2 * hist_floats(T, N, ks) + 2 * (2 * static_cast<int64_t>(N) * T + N) + 2;
 }
 
 extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const int64_t* targets, int64_t target_stride,
@@ -323,16 +323,19 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0 && C > 0, "ctc_loss_fwd: empty shape T=%d N=%d C=%d", T, N, C);
     CTCB_REQUIRE(blank >= 0 && blank < C, "ctc_loss_fwd: blank %d out of range [0,%d)", blank, C);
+    CTCB_REQUIRE((reinterpret_cast<uintptr_t>(alpha_ws) & 7) == 0, "ctc_loss_fwd: workspace must be 8-byte aligned");
     int ks = ks_for(max_target_len);
     CTCB_REQUIRE(ks <= 16, "ctc_loss_fwd: target length %d exceeds the supported maximum 255", max_target_len);
-    dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+    const int utt_per_block = WARPS_PER_BLOCK / 2;
+    dim3 grid((N + utt_per_block - 1) / utt_per_block), block(WARPS_PER_BLOCK * 32);
     size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * 2 * C * sizeof(float);
     CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_fwd: class count %d too large for the row buffer", C);
-    double* offs = reinterpret_cast<double*>(alpha_ws + alpha_floats(T, N, ks));
+    CtcWs w = carve(alpha_ws, T, N, ks);
 #define LAUNCH_A(KS)                                                                                          \
-    CTCB_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ctc_alpha_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
-                                                        target_lengths, alpha_ws, offs, nll, T, N, C, blank)
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_sweep_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
+                                                        target_lengths, w.hist_a, w.hist_b, w.off_a, w.off_b, \
+                                                        w.nll_d, nll, T, N, C, blank)
     switch (ks) {
         case 1: LAUNCH_A(1); break;
         case 2: LAUNCH_A(2); break;
@@ -354,16 +357,19 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_bwd(const float* log_probs, const in
     CTCB_REQUIRE(blank >= 0 && blank < C, "ctc_loss_bwd: blank %d out of range [0,%d)", blank, C);
     int ks = ks_for(max_target_len);
     CTCB_REQUIRE(ks <= 16, "ctc_loss_bwd: target length %d exceeds the supported maximum 255", max_target_len);
-    dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
-    size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * 3 * C * sizeof(float);
-    CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_bwd: class count %d too large for the row buffer", C);
-    const double* offs = reinterpret_cast<const double*>(alpha_ws + alpha_floats(T, N, ks));
     (void)nll;
+    const long long rows = static_cast<long long>(T) * N;
+    long long blocks = (rows + 7) / 8;
+    const long long cap = static_cast<long long>(device_sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    size_t smem = static_cast<size_t>(8) * C * sizeof(float);
+    CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_bwd: class count %d too large for the occupancy buffer", C);
+    CtcWs w = carve(const_cast<float*>(alpha_ws), T, N, ks);
 #define LAUNCH_B(KS)                                                                                               \
-    CTCB_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ctc_beta_grad_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
-                                                            target_lengths, alpha_ws, offs, grad_nll, grad_scale, \
-                                                            grad, T, N, C, blank)
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_grad_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    ctc_grad_kernel<KS><<<static_cast<int>(blocks), 256, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
+                                                       target_lengths, w.hist_a, w.hist_b, w.off_a, w.off_b, w.nll_d, \
+                                                       grad_nll, grad_scale, grad, T, N, C, blank)
     switch (ks) {
         case 1: LAUNCH_B(1); break;
         case 2: LAUNCH_B(2); break;

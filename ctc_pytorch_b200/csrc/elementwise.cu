@@ -103,30 +103,106 @@ cast_transpose_kernel(const float* __restrict__ src, long long s_outer, long lon
     }
 }
 
+// Vectorised variant for even C and even strides: 64 x 64 tiles, float2 loads (256-byte rows), bf16x2 stores
+// (128-byte rows) for both the straight and the transposed output.
+__global__ void __launch_bounds__(256)
+cast_transpose_v2_kernel(const float* __restrict__ src, long long s_outer, long long s_inner, int n_inner,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         __nv_bfloat16* __restrict__ dst, long long dst_pitch, __nv_bfloat16* __restrict__ dstT,
+                         long long dstT_pitch, int n_pad, int R, int C) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int tiles_c = (C + 63) / 64, tiles_r = (R + 63) / 64;
+    const long long tiles = static_cast<long long>(tiles_c) * tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const bool fast_rows = (n_inner == n_pad) && (R % 2 == 0);
+    for (long long tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
+        const int r0 = static_cast<int>(tile_id / tiles_c) * 64, c0 = static_cast<int>(tile_id % tiles_c) * 64;
+        const int c = c0 + 2 * tx;
+        float sc0 = 1.0f, sc1 = 1.0f, sh0 = 0.0f, sh1 = 0.0f;
+        if (scale && c < C) { sc0 = scale[c]; sc1 = scale[c + 1]; sh0 = shift[c]; sh1 = shift[c + 1]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = r0 + ty + 8 * k;
+            __nv_bfloat162 b = __floats2bfloat162_rn(0.0f, 0.0f);
+            if (r < R && c < C) {
+                const float2 v = *reinterpret_cast<const float2*>(
+                    src + static_cast<long long>(r / n_inner) * s_outer + static_cast<long long>(r % n_inner) * s_inner + c);
+                b = __floats2bfloat162_rn(v.x * sc0 + sh0, v.y * sc1 + sh1);
+                if (dst) *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<long long>(r) * dst_pitch + c) = b;
+            }
+            tile[ty + 8 * k][2 * tx] = b.x;
+            tile[ty + 8 * k][2 * tx + 1] = b.y;
+        }
+        if (dstT) {
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int cc = c0 + ty + 8 * k, rr = r0 + 2 * tx;
+                if (cc < C) {
+                    __nv_bfloat16* orow = dstT + static_cast<long long>(cc) * dstT_pitch;
+                    if (fast_rows) {
+                        if (rr < R) {
+                            __nv_bfloat162 v;
+                            v.x = tile[2 * tx][ty + 8 * k];
+                            v.y = tile[2 * tx + 1][ty + 8 * k];
+                            *reinterpret_cast<__nv_bfloat162*>(orow + rr) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = rr + h;
+                            if (r < R) orow[static_cast<long long>(r / n_inner) * n_pad + r % n_inner] = tile[2 * tx + h][ty + 8 * k];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // dG [R, 8H] bf16 with packed gate columns -> dG^T [8H, Rp] bf16 with rows in torch order (dir, q, unit).
+// 64 x 64 tiles, 4-byte (bf16x2) global accesses on both sides: 128-byte rows in, 128-byte rows out.
 __global__ void __launch_bounds__(256)
 transpose_dg_kernel(const __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ dgT, long long dgT_pitch,
                     int n_inner, int n_pad, int R, int H) {
-    __shared__ __nv_bfloat16 tile[32][34];
+    __shared__ __nv_bfloat16 tile[64][66];
     const int G8 = 8 * H, G4 = 4 * H;
-    const int tiles_c = G8 / 32, tiles_r = (R + 31) / 32;
+    const int tiles_c = G8 / 64, tiles_r = (R + 63) / 64;
     const long long tiles = static_cast<long long>(tiles_c) * tiles_r;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const bool fast_rows = (n_inner == n_pad) && (R % 2 == 0);  // output columns are the input rows, pairs stay adjacent
     for (long long tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
-        const int r0 = static_cast<int>(tile_id / tiles_c) * 32, c0 = static_cast<int>(tile_id % tiles_c) * 32;
+        const int r0 = static_cast<int>(tile_id / tiles_c) * 64, c0 = static_cast<int>(tile_id % tiles_c) * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
             const int r = r0 + ty + 8 * k;
-            tile[ty + 8 * k][tx] = (r < R) ? dg[static_cast<long long>(r) * G8 + c0 + tx] : __float2bfloat16(0.0f);
+            __nv_bfloat162 v = __floats2bfloat162_rn(0.0f, 0.0f);
+            if (r < R) v = *reinterpret_cast<const __nv_bfloat162*>(dg + static_cast<long long>(r) * G8 + c0 + 2 * tx);
+            tile[ty + 8 * k][2 * tx] = v.x;
+            tile[ty + 8 * k][2 * tx + 1] = v.y;
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int cc = c0 + ty + 8 * k, rr = r0 + tx;
+        for (int k = 0; k < 8; ++k) {
+            const int cc = c0 + ty + 8 * k;
             const int dir = cc / G4, orow = dir * G4 + packed_to_orig_row(cc % G4, H);
-            if (rr < R)
-                dgT[static_cast<long long>(orow) * dgT_pitch + static_cast<long long>(rr / n_inner) * n_pad + rr % n_inner] =
-                    tile[tx][ty + 8 * k];
+            const int rr = r0 + 2 * tx;
+            __nv_bfloat16* orow_p = dgT + static_cast<long long>(orow) * dgT_pitch;
+            if (fast_rows) {
+                if (rr < R) {
+                    __nv_bfloat162 v;
+                    v.x = tile[2 * tx][ty + 8 * k];
+                    v.y = tile[2 * tx + 1][ty + 8 * k];
+                    *reinterpret_cast<__nv_bfloat162*>(orow_p + rr) = v;
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = rr + h;
+                    if (r < R) orow_p[static_cast<long long>(r / n_inner) * n_pad + r % n_inner] = tile[2 * tx + h][ty + 8 * k];
+                }
+            }
         }
         __syncthreads();
     }
@@ -326,10 +402,19 @@ extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_ou
     CTCB_REQUIRE(R > 0 && C > 0 && n_inner > 0, "cast_transpose: empty R=%d C=%d", R, C);
     CTCB_REQUIRE(dst || dstT, "cast_transpose: no output requested");
     CTCB_REQUIRE(n_pad >= n_inner, "cast_transpose: n_pad %d < n_inner %d", n_pad, n_inner);
-    const long long tiles = static_cast<long long>((R + 31) / 32) * ((C + 31) / 32);
-    cast_transpose_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(
-        src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch,
-        static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C);
+    const bool vec = (C % 2 == 0) && (s_outer % 2 == 0) && (s_inner % 2 == 0) && (dst_pitch % 2 == 0) &&
+                     (dstT_pitch % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+    if (vec) {
+        const long long tiles = static_cast<long long>((R + 63) / 64) * ((C + 63) / 64);
+        cast_transpose_v2_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(
+            src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch,
+            static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C);
+    } else {
+        const long long tiles = static_cast<long long>((R + 31) / 32) * ((C + 31) / 32);
+        cast_transpose_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(
+            src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch,
+            static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C);
+    }
     CTCB_LAUNCH_CHECK();
     return OK;
 }
@@ -337,8 +422,8 @@ extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_ou
 extern "C" CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64_t dgT_pitch, int n_inner, int n_pad,
                                                 int R, int H, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    CTCB_REQUIRE(R > 0 && H % 32 == 0, "transpose_dg: bad sizes R=%d H=%d", R, H);
-    const long long tiles = static_cast<long long>((R + 31) / 32) * (8 * H / 32);
+    CTCB_REQUIRE(R > 0 && H % 32 == 0 && (dgT_pitch % 2) == 0, "transpose_dg: bad sizes R=%d H=%d", R, H);
+    const long long tiles = static_cast<long long>((R + 63) / 64) * (8 * H / 64);
     transpose_dg_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dg),
                                                                  static_cast<__nv_bfloat16*>(dgT), dgT_pitch, n_inner,
                                                                  n_pad, R, H);

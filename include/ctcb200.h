@@ -42,7 +42,8 @@ CTCB200_API int ctcb200_version(void);
 /* ---- CTC loss: replaces nn.CTCLoss(reduction='sum') fwd/bwd, timit/steps/train_ctc.py:144,47,63 ------
  * log_probs [T,N,C] f32; targets [N,*] int64 zero-padded rows of pitch target_stride
  * (timit/utils/data_loader.py:125,140); input_lengths / target_lengths [N] int64.
- * alpha_ws: caller-provided workspace of ctcb200_ctc_workspace_floats(T,N,max_target_len) floats, kept
+ * alpha_ws: caller-provided, 8-byte aligned workspace of ctcb200_ctc_workspace_floats(T,N,max_target_len) floats (alpha and
+ * beta histories + their log-scale offsets; fwd runs both sweeps concurrently, bwd is the parallel gradient kernel), kept
  * between fwd and bwd. nll [N] f32 = per-utterance negative log likelihood (+inf if infeasible).
  * bwd writes grad [T,N,C] f32 = grad_scale * grad_nll[n] * (exp(lp) - exp(lcab + nll - lp)), zero for
  * t >= input_length (torch's native convention); grad_nll may be NULL (= all ones). */
