@@ -19,6 +19,8 @@
 //   warp 2    TMEM allocation / deallocation (2*BN columns).
 //   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, convert, store to global; the
 //             second accumulator buffer lets the next tile's MMAs run under the stores.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ctcb200.h"
 
@@ -35,18 +37,21 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // ring + barriers + alignment slack
+    static constexpr int STAGING_BYTES = 4 * 2 * 4096;  // per epilogue warp: two 32x32 fp32 boxes for the TMA store
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;  // + barriers + alignment
 };
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cout,
-               long long ldc, int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, void* __restrict__ Cout, long long ldc, int M, int N, int K,
+               int a_koff, int b_koff, int out_bf16, int accumulate, int tma_store, int split_k) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-byte aligned (stage sizes are multiples of 1024)
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -54,12 +59,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-    const int tiles = m_tiles * n_tiles;
-    const int kblocks = (K + BK - 1) / BK;
+    const int out_tiles = m_tiles * n_tiles;
+    const int tiles = out_tiles * split_k;  // work items: (output tile, K split); splits add into C through the TMA unit
+    const int kblocks_total = (K + BK - 1) / BK;
+    const int kb_per_split = (kblocks_total + split_k - 1) / split_k;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (tma_store) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -83,8 +91,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                const int ot = tile % out_tiles, sp = tile / out_tiles;
+                const int m_blk = ot % m_tiles, n_blk = ot / m_tiles;
+                const int kb0 = sp * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -108,13 +118,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < kblocks; ++kb) {
+            const int sp = tile / out_tiles;
+            const int kb0 = sp * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(a_addr + Cfg::A_BYTES);
                 if (leader) {
-                    umma_bf16(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+                    umma_bf16(d_tmem, ad, bd, idesc, kb != kb0 ? 1u : 0u);
                     umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
                     umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
                     umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
@@ -134,13 +146,47 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool vec_f32 = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
         const bool vec_b16 = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            const int ot = tile % out_tiles;
+            const int m_blk = ot % m_tiles, n_blk = ot / m_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int row = m_blk * BM + ew * 32 + lane;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+            if (tma_store) {
+                // registers -> 128B-swizzled shared box -> TMA store: full 128-byte lines leave the SM, bounds are
+                // clipped by the hardware; two boxes per warp so the next tcgen05.ld overlaps the previous store
+                uint8_t* wbuf = staging + ew * 8192;
+                const int sp = tile / out_tiles;
+                const bool has_work = sp * kb_per_split < kblocks_total;  // an empty K split contributes nothing
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int col0 = n_blk * BN + c0;
+                    if (col0 >= N || !has_work) break;
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + c0, r);
+                    tmem_ld_wait();
+                    uint8_t* box = wbuf + ((c0 >> 5) & 1) * 4096;
+                    if (lane == 0) bulk_group_wait_read<1>();  // the store issued two chunks ago has left this box
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<uint4*>(box + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                            make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (split_k > 1) tma_reduce_add_2d(&tmC, box, col0, m_blk * BM + ew * 32);
+                        else tma_store_2d(&tmC, box, col0, m_blk * BM + ew * 32);
+                        bulk_group_commit();
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                continue;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
@@ -199,6 +245,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        if (tma_store && lane == 0) bulk_group_wait_all();  // all stores of this warp are complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -206,8 +253,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, long long ldc, int M, int N, int K,
-                int a_koff, int b_koff, int out_bf16, int accumulate, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int tma_store, int split_k,
+                void* C, long long ldc, int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
+                int max_ctas, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -215,10 +263,13 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, long lo
                                        Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    gemm_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16,
-                                                              accumulate);
+    int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * split_k;
+    // max_ctas: 0 = persistent over all SMs; > 0 = cap (leave SMs to a concurrent kernel); < 0 = one tile per CTA
+    // (short-lived CTAs, so a kernel launched later on another stream gets SMs quickly)
+    int limit = max_ctas > 0 ? max_ctas : device_sm_count();
+    int grid = (max_ctas < 0 || tiles < limit) ? tiles : limit;
+    gemm_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, C, ldc, M, N, K, a_koff, b_koff, out_bf16,
+                                                              accumulate, tma_store, split_k);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
@@ -227,21 +278,26 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, long lo
 
 // Internal entry used by the other translation units as well as the C ABI below.
 int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
-                 int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, cudaStream_t stream) {
+                 int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, int max_ctas,
+                 cudaStream_t stream) {
     CTCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     CTCB_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0 && a_koff >= 0 && b_koff >= 0,
                  "gemm: K offsets (%d, %d) must be non-negative multiples of 8 (TMA box start is 16-byte aligned)", a_koff,
                  b_koff);
     int bn = force_bn;
+    const int sms = device_sm_count();
+    const int m_tiles = (M + BM - 1) / BM;
     if (bn == 0) {
-        // widest tile that still yields at least one full wave, else favour more tiles
-        const int sms = device_sm_count();
-        const long long t256 = static_cast<long long>((M + BM - 1) / BM) * ((N + 255) / 256);
-        const long long t128 = static_cast<long long>((M + BM - 1) / BM) * ((N + 127) / 128);
-        if (N > 128 && t256 >= sms) bn = 256;
-        else if (N > 64 && t128 >= sms / 2) bn = 128;
-        else if (N > 64) bn = 128;
-        else bn = 64;
+        // waves x measured relative cost of one tile (B200: 256-wide tiles run the tensor pipe ~65 % busy, 128-wide
+        // ones are shared-memory bound at ~0.62 of that per tile, 64-wide ~0.45): pick the cheapest estimate
+        const struct { int bn; double cost; } cand[3] = {{256, 1.0}, {128, 0.62}, {64, 0.45}};
+        double best = 1e30;
+        for (const auto& c : cand) {
+            if (c.bn > 64 && N <= c.bn / 2) continue;  // more than half of the tile would be padding
+            const long long t = static_cast<long long>(m_tiles) * ((N + c.bn - 1) / c.bn);
+            const double est = static_cast<double>((t + sms - 1) / sms) * c.cost;
+            if (est < best - 1e-9) { best = est; bn = c.bn; }
+        }
     }
     CTCB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: tile width %d not in {64,128,256}", bn);
     CUtensorMap tmA, tmB;
@@ -249,10 +305,28 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
     if (rc != OK) return rc;
     rc = make_tmap_bf16_2d(&tmB, B, N, static_cast<uint64_t>(b_koff) + K, ldb, bn, BK);
     if (rc != OK) return rc;
+    // fp32 results leave through TMA stores when the row pitch allows a tensor map (16-byte multiples)
+    CUtensorMap tmC = tmA;
+    int tma_store = 0;
+    static const bool allow_tma_store = getenv("CTCB200_GEMM_EPILOGUE") == nullptr || getenv("CTCB200_GEMM_EPILOGUE")[0] != 'd';
+    if (allow_tma_store && !out_bf16 && !accumulate && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+        rc = make_tmap_f32_2d(&tmC, C, M, N, ldc, 32, 32);
+        if (rc != OK) return rc;
+        tma_store = 1;
+    }
+    // split K when the output has too few tiles to fill the machine and K is long (weight gradients: K = T*N);
+    // partial tiles are added into a zeroed C by the TMA unit
+    int split_k = 1;
+    if (tma_store && max_ctas == 0 && ldc == N) {
+        const long long t = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+        const int kblocks = (K + BK - 1) / BK;
+        while (split_k < 8 && t * (split_k * 2) <= sms && kblocks / (split_k * 2) >= 16) split_k *= 2;
+        if (split_k > 1) CTCB_CUDA(cudaMemsetAsync(C, 0, static_cast<size_t>(M) * ldc * sizeof(float), stream));
+    }
     switch (bn) {
-        case 64: return launch_gemm<64>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, stream);
-        case 128: return launch_gemm<128>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, stream);
-        default: return launch_gemm<256>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, stream);
+        case 64: return launch_gemm<64>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream);
+        case 128: return launch_gemm<128>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream);
+        default: return launch_gemm<256>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream);
     }
 }
 
@@ -260,8 +334,8 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
 
 extern "C" CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                     int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
-                                    int tile_n, ctcb200_stream_t stream_) {
+                                    int tile_n, int max_ctas, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     return ctcb200::gemm_tn_bf16(A, lda, B, ldb, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, tile_n,
-                                 stream);
+                                 max_ctas, stream);
 }

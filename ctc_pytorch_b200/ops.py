@@ -4,7 +4,8 @@ import torch
 from . import _lib
 
 
-def gemm_tn(a, b, out=None, out_dtype=torch.float32, accumulate=False, a_koff=0, b_koff=0, k=None, tile_n=0):
+def gemm_tn(a, b, out=None, out_dtype=torch.float32, accumulate=False, a_koff=0, b_koff=0, k=None, tile_n=0,
+            max_ctas=0):
     """C[M,N] (+)= A[M, a_koff:a_koff+K] @ B[N, b_koff:b_koff+K]^T on the tcgen05 tensor cores.
 
     a, b: bf16, 2-D, K contiguous (row pitch may exceed the logical width but must be a multiple of 8).
@@ -22,7 +23,7 @@ def gemm_tn(a, b, out=None, out_dtype=torch.float32, accumulate=False, a_koff=0,
     assert out.dtype in (torch.float32, torch.bfloat16)
     _lib.lib().call("ctcb200_gemm_tn_bf16", _lib.ptr(a), a.stride(0), _lib.ptr(b), b.stride(0), _lib.ptr(out),
                     out.stride(0), M, N, k, a_koff, b_koff, 1 if out.dtype == torch.bfloat16 else 0,
-                    1 if accumulate else 0, tile_n, _lib.stream())
+                    1 if accumulate else 0, tile_n, max_ctas, _lib.stream())
     return out
 
 

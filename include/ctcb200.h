@@ -69,11 +69,12 @@ CTCB200_API int ctcb200_greedy_decode(const float* log_probs, const int64_t* len
 /* ---- dense GEMM on tcgen05: C[M,N] (+)= A[M,K] * B[N,K]^T, A/B bf16 with K contiguous (pitches lda/ldb in
  * elements, multiples of 8), fp32 accumulate, C f32 (out_bf16=0) or bf16 (1) with pitch ldc.
  * a_koff/b_koff (multiples of 8) shift the K window of each operand (the h_{t-1} shift of dW_hh).
- * tile_n: 0 = auto, else 64/128/256. Carries the contractions behind nn.LSTM / nn.Linear at
- * timit/models/model_ctc.py:23-26,33,136-139. */
+ * tile_n: 0 = auto, else 64/128/256. max_ctas: 0 = persistent over all SMs, > 0 = cap on the CTA count, < 0 = one
+ * tile per CTA (for weight-gradient GEMMs that run on a side stream beside the recurrent kernels). Carries the
+ * contractions behind nn.LSTM / nn.Linear at timit/models/model_ctc.py:23-26,33,136-139. */
 CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                      int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
-                                     int tile_n, ctcb200_stream_t stream);
+                                     int tile_n, int max_ctas, ctcb200_stream_t stream);
 
 /* ---- bidirectional LSTM layer: replaces nn.LSTM(bias=False, bidirectional=True) fwd/bwd time loops,
  * timit/models/model_ctc.py:23-26,33 and the BPTT behind timit/steps/train_ctc.py:63.
