@@ -137,6 +137,32 @@ __device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* __rest
     tmem_st_wait();
 }
 
+// Accumulator columns of up to four issuing warps -> registers, all loads in flight before the single wait, summed.
+template <int CPT>
+__device__ __forceinline__ void tmem_ld_cpt(uint32_t taddr, uint32_t (&r)[CPT]) {
+    if constexpr (CPT == 16) tmem_ld_32x16(taddr, r);
+    else tmem_ld_32x8(taddr, r);
+}
+template <int CPT>
+__device__ __forceinline__ void load_partial_sums(uint32_t taddr, int acc_stride, int parts, uint32_t (&acc)[CPT]) {
+    uint32_t a1[CPT], a2[CPT], a3[CPT];
+    tmem_ld_cpt<CPT>(taddr, acc);
+    if (parts > 1) tmem_ld_cpt<CPT>(taddr + acc_stride, a1);
+    if (parts > 2) {
+        tmem_ld_cpt<CPT>(taddr + 2 * acc_stride, a2);
+        tmem_ld_cpt<CPT>(taddr + 3 * acc_stride, a3);
+    }
+    tmem_ld_wait();
+    if (parts > 1) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            float v = __uint_as_float(acc[c]) + __uint_as_float(a1[c]);
+            if (parts > 2) v += __uint_as_float(a2[c]) + __uint_as_float(a3[c]);
+            acc[c] = __float_as_uint(v);
+        }
+    }
+}
+
 struct FwdParams {
     const float* gx;          // [T*N, 8H] gate pre-activations from the input projection (packed column order)
     float* hout;              // [T*N, 2H] layer output (fwd | reverse)
@@ -148,6 +174,7 @@ struct FwdParams {
     long long* trace;         // debug: per-step clock64 stamps of CTA (0,0,0), or null
     const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (source of the TMEM-resident A operand)
     int a_tmem;               // 1: A operand resident in TMEM, 0: in shared memory (TMA-loaded)
+    int mma_split;            // number of warps (1, 2 or 4) that issue slices of the K chain into their own accumulator
 };
 
 // CL = true: the H/32 CTAs of one (direction, batch group) form one thread-block cluster and exchange h_t through
@@ -191,7 +218,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
         mbar_init(w_full, 1);
         mbar_init(&h_full[0], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
         mbar_init(&h_full[1], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
-        mbar_init(acc_full, 1);
+        mbar_init(acc_full, p.mma_split);
         mbar_init(l_full, LSTM_THREADS);
         fence_mbar_init();
         if constexpr (BULK) {  // arm both parities: each expects one block from every CTA of the cluster
@@ -199,9 +226,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             mbar_expect_tx(&h_full[1], ctas * BLK_BYTES);
         }
     }
-    // TMEM: accumulator in columns [0, 32), the weight slice (A operand) in columns [32, 32 + H/2) when resident
-    uint32_t tmem_cols = 32;
-    if (p.a_tmem) { while (tmem_cols < 32u + H / 2) tmem_cols <<= 1; }
+    // TMEM: up to four accumulators in columns [0, 64), the weight slice (A operand) in columns [64, 64 + H/2)
+    uint32_t tmem_cols = 64;
+    if (p.a_tmem) { while (tmem_cols < 64u + H / 2) tmem_cols <<= 1; }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     if constexpr (PUSH) {
         // h_{-1} = 0: the first operand buffer starts zeroed
@@ -215,7 +242,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     if constexpr (CL) cluster_sync_all();  // peers' barriers are initialised before anyone arrives on them
 
     if (p.a_tmem) {
-        if (warp < 4) load_weights_to_tmem(p.w + (static_cast<size_t>(dir) * 4 * H + j * 128) * H, H, tmem_base, 32, warp, lane);
+        if (warp < 4) load_weights_to_tmem(p.w + (static_cast<size_t>(dir) * 4 * H + j * 128) * H, H, tmem_base, 64, warp, lane);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -268,12 +295,12 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
         }
         // (4) warp 0 issues the K = H MMA chain: the whole warp runs the (warp-uniform) address arithmetic so the
         // descriptors live in uniform registers; one elected lane issues each tcgen05.mma
-        if (warp == 0) {
+        if (warp < p.mma_split) {
             if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
             if constexpr (BULK) {
                 if (t > 0) {
                     mbar_wait(&h_full[t & 1], ((t - 1) >> 1) & 1);                // every peer's block has landed
-                    if (lane == 0) mbar_expect_tx(&h_full[t & 1], ctas * BLK_BYTES);  // re-arm for step t+2
+                    if (lane == 0 && warp == 0) mbar_expect_tx(&h_full[t & 1], ctas * BLK_BYTES);  // re-arm for step t+2
                 }
             } else if constexpr (PUSH) {
                 if (t > 0) mbar_wait_cluster(&h_full[t & 1], ((t - 1) >> 1) & 1);  // all peers pushed h_{t-1}
@@ -286,16 +313,20 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sH) + (PUSH ? (t & 1) * himg_bytes : 0);
             const bool leader = elect_one();
             if (p.a_tmem) {
+                // the issue rate of one warp (~40 cycles per tcgen05.mma) bounds the chain, so up to four warps issue
+                // interleaved K blocks into their own accumulator; the epilogue adds the partial sums
+                const int kstep = p.mma_split, kfirst = warp;
+                const uint32_t dacc = tmem_base + warp * NB;
 #pragma unroll 1
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = kfirst; kb < kblocks; kb += kstep) {
                     // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
                     const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
-                    const uint32_t ta = tmem_base + 32 + kb * 32;
+                    const uint32_t ta = tmem_base + 64 + kb * 32;
                     if (leader) {
-                        umma_bf16_ts(tmem_base, ta, bd, idesc, kb != 0 ? 1u : 0u);
-                        umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
+                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
             } else {
@@ -319,9 +350,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
         tc_fence_after();
         TRACE(3); TRACE(8);
         uint32_t acc[CPT];
-        if constexpr (CPT == 16) tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, acc);
-        else tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, acc);
-        tmem_ld_wait();
+        load_partial_sums<CPT>(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, NB, p.mma_split, acc);
         tc_fence_before();
         TRACE(4); TRACE(9);
         // (6) gate non-linearity, then regroup the four gates of a unit through shared memory
@@ -347,12 +376,16 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             const float h = g4.w * fast_tanh(cn);
             hv[e] = h;
             gv[e] = g4;
-            const uint4 pk = pack8_bf16(h);
-            if ((lane & 7) == 0) {
-                // staging in destination order: chunk `oct` of row n sits at slot oct ^ ((n >> 1) & 3) of the row
-                if constexpr (PUSH) sOut[n * 4 + ((lane >> 3) ^ ((n >> 1) & 3))] = pk;
-                else *reinterpret_cast<uint4*>(img + static_cast<size_t>((t + 1) & 1) * H * NB +
-                                               image_chunk_offset<NB>(j * 32 + lane, n)) = pk;
+            if constexpr (PUSH) {
+                // staging in destination order: chunk `oct` of row n sits at slot oct ^ ((n >> 1) & 3) of the 64-byte
+                // row; every lane drops its own bf16 (no shuffle chain on the critical path)
+                reinterpret_cast<__nv_bfloat16*>(sOut)[n * 32 + (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7)] =
+                    __float2bfloat16(h);
+            } else {
+                const uint4 pk = pack8_bf16(h);
+                if ((lane & 7) == 0)
+                    *reinterpret_cast<uint4*>(img + static_cast<size_t>((t + 1) & 1) * H * NB +
+                                              image_chunk_offset<NB>(j * 32 + lane, n)) = pk;
             }
         }
         TRACE(12);
@@ -436,6 +469,7 @@ struct BwdParams {
     int T, N, H, groups, n0;
     const __nv_bfloat16* w;    // packed transposed recurrent weights [8H, H]
     int a_tmem;
+    int mma_split;
 };
 
 // CTA (mb, q) keeps the [128 units x H] slice of gate q's transposed recurrent block. Per BPTT step:
@@ -484,7 +518,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         mbar_init(w_full, 1);
         mbar_init(&b_full[0], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
         mbar_init(&b_full[1], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
-        mbar_init(acc_full, 1);
+        mbar_init(acc_full, p.mma_split);
         mbar_init(r_full, BULK ? 1 : 4);
         mbar_init(l_full, LSTM_THREADS);
         fence_mbar_init();
@@ -494,8 +528,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             mbar_expect_tx(r_full, 4 * NB * 32 * 4);  // four gate partials of [NB][32] floats per step
         }
     }
-    uint32_t tmem_cols = 32;
-    if (p.a_tmem) { while (tmem_cols < 32u + H / 2) tmem_cols <<= 1; }
+    uint32_t tmem_cols = 64;
+    if (p.a_tmem) { while (tmem_cols < 64u + H / 2) tmem_cols <<= 1; }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     if constexpr (PUSH) {
         for (int i = tid; i < img_bytes / 16; i += LSTM_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -510,7 +544,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     // rows of the transposed gate block: (dir, q, unit); this CTA takes units [128 mb, +128)
     if (p.a_tmem) {
         if (warp < 4)
-            load_weights_to_tmem(p.w + (static_cast<size_t>(dir * 4 + q) * H + mb * 128) * H, H, tmem_base, 32, warp, lane);
+            load_weights_to_tmem(p.w + (static_cast<size_t>(dir * 4 + q) * H + mb * 128) * H, H, tmem_base, 64, warp, lane);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -571,12 +605,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             mbar_arrive(HYB ? l_full : &b_full[0]);
         }
         // (4) partial dh[128 units, NB] = W_q^T slice * dG_q (issued like the forward kernel's chain)
-        if (warp == 0) {
+        if (warp < p.mma_split) {
             if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
             if constexpr (BULK) {
                 if (t > 0) {
                     mbar_wait(&b_full[t & 1], ((t - 1) >> 1) & 1);
-                    if (lane == 0) mbar_expect_tx(&b_full[t & 1], ctas * BLK_BYTES);
+                    if (lane == 0 && warp == 0) mbar_expect_tx(&b_full[t & 1], ctas * BLK_BYTES);
                 }
             } else if constexpr (PUSH) {
                 if (t > 0) mbar_wait_cluster(&b_full[t & 1], ((t - 1) >> 1) & 1);
@@ -588,16 +622,18 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sB) + (PUSH ? (t & 1) * img_bytes : 0);
             const bool leader = elect_one();
             if (p.a_tmem) {
+                const int kstep = p.mma_split, kfirst = warp;
+                const uint32_t dacc = tmem_base + warp * NB;
 #pragma unroll 1
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = kfirst; kb < kblocks; kb += kstep) {
                     // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
                     const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
-                    const uint32_t ta = tmem_base + 32 + kb * 32;
+                    const uint32_t ta = tmem_base + 64 + kb * 32;
                     if (leader) {
-                        umma_bf16_ts(tmem_base, ta, bd, idesc, kb != 0 ? 1u : 0u);
-                        umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
-                        umma_bf16_ts(tmem_base, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
+                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
             } else {
@@ -619,9 +655,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         mbar_wait(acc_full, t & 1);
         tc_fence_after();
         uint32_t acc[CPT];
-        if constexpr (CPT == 16) tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, acc);
-        else tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, acc);
-        tmem_ld_wait();
+        load_partial_sums<CPT>(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, NB, p.mma_split, acc);
         tc_fence_before();
         if constexpr (BULK) {
             // every warp holds the [NB/2][32] sub-block of partial rows that belongs to CTA (lq, mb): stage it, then
@@ -670,15 +704,17 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             const float d_f = dc * c_p[e] * gf * (1.0f - gf);
             const float d_g = dc * gi * (1.0f - gg * gg);
             dc_carry[e] = dc * gf;
-            const uint4 pi = pack8_bf16(d_i), pf = pack8_bf16(d_f), pg = pack8_bf16(d_g), po = pack8_bf16(d_o);
-            if ((lane & 7) == 0) {
-                if constexpr (PUSH) {
-                    const int c = n * 4 + ((lane >> 3) ^ ((n >> 1) & 3));  // destination order inside the block
-                    sOut[0 * OUT_CHUNKS + c] = pi;
-                    sOut[1 * OUT_CHUNKS + c] = pf;
-                    sOut[2 * OUT_CHUNKS + c] = pg;
-                    sOut[3 * OUT_CHUNKS + c] = po;
-                } else {
+            if constexpr (PUSH) {
+                // destination order inside each gate's block; one bf16 store per gate and lane
+                __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut) + n * 32 +
+                                    (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7);
+                so[0 * OUT_CHUNKS * 8] = __float2bfloat16(d_i);
+                so[1 * OUT_CHUNKS * 8] = __float2bfloat16(d_f);
+                so[2 * OUT_CHUNKS * 8] = __float2bfloat16(d_g);
+                so[3 * OUT_CHUNKS * 8] = __float2bfloat16(d_o);
+            } else {
+                const uint4 pi = pack8_bf16(d_i), pf = pack8_bf16(d_f), pg = pack8_bf16(d_g), po = pack8_bf16(d_o);
+                if ((lane & 7) == 0) {
                     const int off = image_chunk_offset<NB>(unit, n);
                     const size_t nxt = static_cast<size_t>((t + 1) & 1) * H * NB;
                     *reinterpret_cast<uint4*>(imgs + (0 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pi;
@@ -749,6 +785,17 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
 bool weights_in_tmem() {
     const char* e = getenv("CTCB200_LSTM_A");  // "smem" keeps the weight slice in shared memory (A/B comparison runs)
     return !(e && e[0] == 's');
+}
+
+// warps that issue slices of the per-step MMA chain (each into its own TMEM accumulator, 64 columns in total)
+int mma_issuers(int NB, int H, bool a_tmem) {
+    if (!a_tmem) return 1;
+    int n = 64 / NB;  // accumulators that fit in front of the weight columns
+    const char* e = getenv("CTCB200_LSTM_MMA_ISSUERS");
+    if (e) n = atoi(e);
+    if (n > 4) n = 4;
+    while (n > 1 && (n > H / 64 || n * NB > 64)) n >>= 1;
+    return n < 1 ? 1 : n;
 }
 
 size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool a_tmem) {
@@ -849,6 +896,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     p.gx = gx; p.hout = hout; p.c_save = c_save; p.gates_save = static_cast<uint2*>(gates_save);
     p.himg = nullptr; p.flags = nullptr; p.trace = nullptr;
     p.w = static_cast<const __nv_bfloat16*>(whh_packed); p.a_tmem = a_tmem ? 1 : 0;
+    p.mma_split = mma_issuers(NB, H, a_tmem);
     p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
     if (getenv("CTCB200_LSTM_TRACE")) {  // development aid: per-phase cycle breakdown of the recurrence on stderr
         static long long* dbuf = nullptr;
@@ -942,6 +990,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     p.dg = static_cast<__nv_bfloat16*>(dg);
     p.dgimg = nullptr; p.flags = nullptr;
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed); p.a_tmem = a_tmem ? 1 : 0;
+    p.mma_split = mma_issuers(NB, H, a_tmem);
     p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
     if (cl) {
         dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
