@@ -125,11 +125,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // Load this CTA's [128 x H] bf16 weight slice into TMEM columns [col0, col0 + H/2): row r -> lane r, K elements
 // (2c, 2c+1) packed into 32-bit column c — the A-operand layout of tcgen05.mma with A in tensor memory.
 // Executed by warps 0-3 (warp w owns lanes 32w..32w+31).
-__device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* __restrict__ w_rows, int H, uint32_t tmem_base,
-                                                     uint32_t col0, int warp, int lane) {
-    const uint4* src = reinterpret_cast<const uint4*>(w_rows + static_cast<size_t>(warp * 32 + lane) * H);
+__device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* __restrict__ w_rows, int K, uint32_t tmem_base,
+                                                     uint32_t col0, int warp, int lane, int row_pitch = 0) {
+    if (row_pitch == 0) row_pitch = K;  // K = number of K elements to load per row
+    const uint4* src = reinterpret_cast<const uint4*>(w_rows + static_cast<size_t>(warp * 32 + lane) * row_pitch);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + col0;
-    for (int kb = 0; kb < H / 16; ++kb) {
+    for (int kb = 0; kb < K / 16; ++kb) {
         const uint4 a = __ldg(src + 2 * kb), b = __ldg(src + 2 * kb + 1);
         const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         tmem_st_32x8(taddr + kb * 8, r);
@@ -782,9 +783,429 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+
+// ================================================================================================
+// Two-tile variants for H > 512 (cfg4: H = 640). H/32 CTAs would not fit one cluster (max 16), so every CTA owns
+// 64 hidden units = two 128-row gate tiles: tile 0's weights are resident in TMEM, tile 1's in shared memory
+// (TMA-loaded, SWIZZLE_128B); four warps issue the two MMA chains (two per tile, split accumulators). The H/64
+// CTAs of a (direction, batch group) form one cluster and exchange h_t with bulk DSMEM copies exactly as above.
+// ================================================================================================
+template <int NB>
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
+    constexpr uint32_t BLK_BYTES = NB * 64;
+    constexpr int CPT = NB / 2, EPT = NB / 8, S_STRIDE = NB * 4 + 4, OUT_CHUNKS = NB * 4;
+    static_assert(4 * NB <= 64, "four split accumulators must fit the 64 accumulator columns");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = p.H, T = p.T, N = p.N;
+    const int himg_bytes = H * NB * 2;
+    uint8_t* sW1 = smem;                                              // tile 1 weights [128 x H] bf16
+    uint8_t* sH = sW1 + 128 * H * 2;                                  // two operand buffers
+    float* sS = reinterpret_cast<float*>(sH + 2 * himg_bytes);        // [2 tiles][32 units][S_STRIDE]
+    uint4* sOut = reinterpret_cast<uint4*>(sS + 2 * 32 * S_STRIDE);   // [2 tiles][OUT_CHUNKS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * OUT_CHUNKS);
+    uint64_t* w_full = bars;
+    uint64_t* h_full = bars + 1;  // [2]
+    uint64_t* acc_full = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
+    const int ctas = gridDim.x;
+    const int kblocks = H / 64;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmW);
+        mbar_init(w_full, 1);
+        mbar_init(&h_full[0], 1);
+        mbar_init(&h_full[1], 1);
+        mbar_init(acc_full, 4);
+        fence_mbar_init();
+        mbar_expect_tx(&h_full[0], ctas * 2 * BLK_BYTES);
+        mbar_expect_tx(&h_full[1], ctas * 2 * BLK_BYTES);
+    }
+    uint32_t tmem_cols = 64;
+    while (tmem_cols < 64u + H / 2) tmem_cols <<= 1;
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = tid; i < himg_bytes / 16; i += LSTM_THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();
+
+    const size_t row0 = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(2 * j) * 128;  // packed rows of tile 0
+    if (warp < 4) load_weights_to_tmem(p.w + row0 * H, H, tmem_base, 64, warp, lane);
+    if (tid == 0) {
+        mbar_expect_tx(w_full, 128 * H * 2);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sW1 + kb * 16384, &tmW, w_full, kb * 64, static_cast<int>(row0) + 128);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int lq = warp & 3, ch = warp >> 2;
+    const bool warp_leader = elect_one();
+    const int row = lq * 32 + lane;
+    const int u_loc = row >> 2, q = row & 3;
+    const float act_s = (q == 2) ? 2.0f : 1.0f;
+    const size_t gx_col = row0 + row;
+    const size_t G8 = static_cast<size_t>(8) * H, H2 = static_cast<size_t>(2) * H;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
+
+    float c_state[2][EPT];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) c_state[u][e] = 0.0f;
+
+    for (int t = 0; t < T; ++t) {
+        const int tt = dir ? (T - 1 - t) : t;
+        float gx[2][CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int gn = p.n0 + grp * NB + ch * CPT + c;
+            const float* g = p.gx + (static_cast<size_t>(tt) * N + (gn < N ? gn : 0)) * G8 + gx_col;
+            gx[0][c] = (gn < N) ? __ldg(g) : 0.0f;
+            gx[1][c] = (gn < N) ? __ldg(g + 128) : 0.0f;
+        }
+        if (warp < 4) {
+            const int u = warp >> 1, slot = warp & 1;
+            if (t == 0 && u == 1) mbar_wait(w_full, 0);
+            if (t > 0) {
+                mbar_wait(&h_full[t & 1], ((t - 1) >> 1) & 1);
+                if (lane == 0 && warp == 0) mbar_expect_tx(&h_full[t & 1], ctas * 2 * BLK_BYTES);
+            }
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sW1), b0 = smem_u32(sH) + (t & 1) * himg_bytes;
+            const uint32_t dacc = tmem_base + warp * NB;
+            const bool leader = elect_one();
+#pragma unroll 1
+            for (int kb = slot; kb < kblocks; kb += 2) {
+                const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
+                if (u == 0) {
+                    const uint32_t ta = tmem_base + 64 + kb * 32;
+                    if (leader) {
+                        umma_bf16_ts(dacc, ta, bd, idesc, kb != slot ? 1u : 0u);
+                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                    }
+                } else {
+                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384);
+                    if (leader) {
+                        umma_bf16(dacc, ad, bd, idesc, kb != slot ? 1u : 0u);
+                        umma_bf16(dacc, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(dacc, ad + 4, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16(dacc, ad + 6, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                    }
+                }
+            }
+            if (leader) umma_commit(acc_full);
+        }
+        __syncwarp();
+        mbar_wait(acc_full, t & 1);
+        tc_fence_after();
+        uint32_t acc[2][CPT];
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT;
+        load_partial_sums<CPT>(trow, NB, 2, acc[0]);
+        load_partial_sums<CPT>(trow + 2 * NB, NB, 2, acc[1]);
+        tc_fence_before();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const float pre = __uint_as_float(acc[u][c]) + gx[u][c];
+                sS[(u * 32 + u_loc) * S_STRIDE + (ch * CPT + c) * 4 + q] = act_s * fast_sigmoid(act_s * pre) - (act_s - 1.0f);
+            }
+        if (warp_leader) bulk_wait_read_all();
+        __syncthreads();
+        float hv[2][EPT];
+        float4 gv[2][EPT];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int n = warp + 8 * e;
+                const float4 g4 = *reinterpret_cast<const float4*>(&sS[(u * 32 + lane) * S_STRIDE + n * 4]);
+                const float cn = g4.y * c_state[u][e] + g4.x * g4.z;
+                c_state[u][e] = cn;
+                const float h = g4.w * fast_tanh(cn);
+                hv[u][e] = h;
+                gv[u][e] = g4;
+                reinterpret_cast<__nv_bfloat16*>(sOut)[u * OUT_CHUNKS * 8 + n * 32 + (((lane >> 3) ^ ((n >> 1) & 3)) << 3) +
+                                                       (lane & 7)] = __float2bfloat16(h);
+            }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (t + 1 < T) {
+            const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + (2 * j) * BLK_BYTES;
+            const uint32_t bar = smem_u32(&h_full[(t + 1) & 1]);
+#pragma unroll
+            for (int d = warp; d < 16; d += 8) {
+                if (d < ctas && warp_leader)
+                    bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), smem_u32(sOut), 2 * BLK_BYTES,
+                                      mapa_shared(bar, static_cast<uint32_t>(d)));
+            }
+            if (warp_leader) bulk_commit();
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int gn = p.n0 + grp * NB + warp + 8 * e;
+                if (gn < N) {
+                    const size_t o = (static_cast<size_t>(tt) * N + gn) * H2 + static_cast<size_t>(dir) * H + j * 64 + u * 32 + lane;
+                    p.hout[o] = hv[u][e];
+                    if (p.c_save) p.c_save[o] = c_state[u][e];
+                    if (p.gates_save) {
+                        __half2 lo = __floats2half2_rn(gv[u][e].x, gv[u][e].y), hi = __floats2half2_rn(gv[u][e].z, gv[u][e].w);
+                        p.gates_save[o] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    }
+                }
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// BPTT counterpart: CTA (qp, mb) owns the gate pair (2 qp, 2 qp + 1) for the 128 units of block mb and finishes 64 of
+// them per step; cluster = (2, H/128). Gate a's transposed slice sits in TMEM, gate b's first 256 K columns too, the
+// rest of gate b in shared memory; four warps issue the 2 * H/64 K blocks round-robin into split accumulators.
+template <int NB>
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
+    constexpr uint32_t BLK_BYTES = NB * 64;
+    constexpr int CPT = NB / 2, EPT = NB / 8, OUT_CHUNKS = NB * 4;
+    static_assert(4 * NB <= 64, "four split accumulators must fit the 64 accumulator columns");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = p.H, T = p.T, N = p.N;
+    const int img_bytes = H * NB * 2;
+    const int kblocks = H / 64;
+    constexpr int KB_TMEM_B = 4;                                      // K blocks of gate b that live in TMEM (256 columns of K)
+    uint8_t* sW2 = smem;                                              // gate b, K columns [256, H): [128 x (H-256)] bf16
+    uint8_t* sB = sW2 + 128 * (H - 64 * KB_TMEM_B) * 2;               // [2 local gates][2 buffers][H x NB] operand images
+    float* sR = reinterpret_cast<float*>(sB + 4 * img_bytes);         // [2 src][2 halves][NB][32] partial dh blocks
+    uint4* sOut = reinterpret_cast<uint4*>(sR + 4 * NB * 32);         // [4 gates][2 halves][OUT_CHUNKS]
+    float* sP = reinterpret_cast<float*>(sOut + 8 * OUT_CHUNKS);      // [4 lane quarters][NB][32] partial staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * NB * 32);
+    uint64_t* w_full = bars;
+    uint64_t* b_full = bars + 1;  // [2]
+    uint64_t* acc_full = bars + 3;
+    uint64_t* r_full = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qp = blockIdx.x, mb = blockIdx.y, MB = gridDim.y;
+    const int dir = blockIdx.z / p.groups, grp = blockIdx.z % p.groups;
+    const int ctas = 2 * MB;
+    auto rank_of = [&](int qq, int mm) -> uint32_t { return static_cast<uint32_t>(qq + 2 * mm); };
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmWT);
+        mbar_init(w_full, 1);
+        mbar_init(&b_full[0], 1);
+        mbar_init(&b_full[1], 1);
+        mbar_init(acc_full, 4);
+        mbar_init(r_full, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&b_full[0], 2 * img_bytes);
+        mbar_expect_tx(&b_full[1], 2 * img_bytes);
+        mbar_expect_tx(r_full, 4 * NB * 32 * 4);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    for (int g = 0; g < 2; ++g)  // buffer 0 of both gate images starts zeroed (dG of "step -1")
+        for (int i = tid; i < img_bytes / 16; i += LSTM_THREADS)
+            reinterpret_cast<uint4*>(sB + (g * 2) * img_bytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();
+
+    // transposed weight rows: (dir, gate, unit); gates 2qp (a) and 2qp+1 (b), units [128 mb, +128)
+    const size_t row_a = (static_cast<size_t>(dir * 4 + 2 * qp) * H + mb * 128), row_b = row_a + H;
+    const uint32_t col_a = 64, col_b = 64 + H / 2;
+    if (warp < 4) {
+        load_weights_to_tmem(p.w + row_a * H, H, tmem_base, col_a, warp, lane);
+        load_weights_to_tmem(p.w + row_b * H, 64 * KB_TMEM_B, tmem_base, col_b, warp, lane, H);
+    }
+    if (tid == 0) {
+        mbar_expect_tx(w_full, 128 * (H - 64 * KB_TMEM_B) * 2);
+        for (int kb = KB_TMEM_B; kb < kblocks; ++kb)
+            tma_load_2d(sW2 + (kb - KB_TMEM_B) * 16384, &tmWT, w_full, kb * 64, static_cast<int>(row_b));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int lq = warp & 3, ch = warp >> 2;
+    const bool warp_leader = elect_one();
+    const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
+    const int unit0 = mb * 128 + qp * 64 + lane;  // + 32 * half
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
+
+    float dc_carry[2][EPT];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) dc_carry[hf][e] = 0.0f;
+
+    for (int t = 0; t < T; ++t) {
+        const int tt = dir ? t : (T - 1 - t);
+        const int tprev = dir ? tt + 1 : tt - 1;
+        const bool has_prev = dir ? (tt + 1 < T) : (tt >= 1);
+        float dh_in[2][EPT], c_t[2][EPT], c_p[2][EPT];
+        uint2 gts[2][EPT];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int gn = p.n0 + grp * NB + warp + 8 * e;
+                const bool ok = gn < N;
+                const int unit = unit0 + 32 * hf;
+                const size_t o = (static_cast<size_t>(tt) * N + (ok ? gn : 0)) * H2 + static_cast<size_t>(dir) * H + unit;
+                dh_in[hf][e] = ok ? __ldg(p.dhout + o) : 0.0f;
+                c_t[hf][e] = ok ? __ldg(p.c_save + o) : 0.0f;
+                gts[hf][e] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
+                const size_t op = (static_cast<size_t>(has_prev ? tprev : tt) * N + (ok ? gn : 0)) * H2 +
+                                  static_cast<size_t>(dir) * H + unit;
+                c_p[hf][e] = (ok && has_prev) ? __ldg(p.c_save + op) : 0.0f;
+            }
+        // partial dh[128 units, NB] = W_a^T dG_a + W_b^T dG_b, 2 * kblocks K blocks round-robin over four issuing warps
+        if (warp < 4) {
+            if (t == 0) mbar_wait(w_full, 0);
+            if (t > 0) {
+                mbar_wait(&b_full[t & 1], ((t - 1) >> 1) & 1);
+                if (lane == 0 && warp == 0) mbar_expect_tx(&b_full[t & 1], 2 * img_bytes);
+            }
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sW2);
+            const uint32_t dacc = tmem_base + warp * NB;
+            const bool leader = elect_one();
+#pragma unroll 1
+            for (int it = warp; it < 2 * kblocks; it += 4) {
+                const int g = it >= kblocks ? 1 : 0, kb = it - g * kblocks;
+                const uint64_t bd = umma_desc_sw64(smem_u32(sB) + (g * 2 + (t & 1)) * img_bytes + kb * (NB * 128));
+                const uint32_t first = it == warp ? 0u : 1u;
+                if (g == 0 || kb < KB_TMEM_B) {
+                    const uint32_t ta = tmem_base + (g == 0 ? col_a : col_b) + kb * 32;
+                    if (leader) {
+                        umma_bf16_ts(dacc, ta, bd, idesc, first);
+                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                    }
+                } else {
+                    const uint64_t ad = umma_desc_sw128(a0 + (kb - KB_TMEM_B) * 16384);
+                    if (leader) {
+                        umma_bf16(dacc, ad, bd, idesc, first);
+                        umma_bf16(dacc, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(dacc, ad + 4, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16(dacc, ad + 6, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                    }
+                }
+            }
+            if (leader) umma_commit(acc_full);
+        }
+        __syncwarp();
+        mbar_wait(acc_full, t & 1);
+        tc_fence_after();
+        uint32_t acc[CPT];
+        load_partial_sums<CPT>(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, NB, 4, acc);
+        tc_fence_before();
+        // rows 32 lq.. of the unit block belong to CTA (lq >> 1, mb), half lq & 1: one bulk copy per warp
+        if (warp_leader) bulk_wait_read_all();
+        __syncthreads();
+        {
+            float* stage = sP + (lq * NB + ch * CPT) * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) stage[c * 32] = __uint_as_float(acc[c]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (warp_leader) {
+                const uint32_t peer = rank_of(lq >> 1, mb);
+                bulk_copy_to_peer(mapa_shared(smem_u32(sR + ((qp * 2 + (lq & 1)) * NB + ch * CPT) * 32), peer),
+                                  smem_u32(sP + (lq * NB + ch * CPT) * 32), CPT * 32 * 4, mapa_shared(smem_u32(r_full), peer));
+                bulk_commit();
+            }
+            mbar_wait(r_full, t & 1);
+            if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * 4);
+        }
+        uint2 dgp[2][EPT];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int n = warp + 8 * e;
+                float dh = dh_in[hf][e] + sR[((0 * 2 + hf) * NB + n) * 32 + lane] + sR[((1 * 2 + hf) * NB + n) * 32 + lane];
+                const __half2 lo = *reinterpret_cast<const __half2*>(&gts[hf][e].x);
+                const __half2 hi = *reinterpret_cast<const __half2*>(&gts[hf][e].y);
+                const float gi = __low2float(lo), gf = __high2float(lo), gg = __low2float(hi), go = __high2float(hi);
+                const float tc = fast_tanh(c_t[hf][e]);
+                const float d_o = dh * tc * go * (1.0f - go);
+                const float dc = dc_carry[hf][e] + dh * go * (1.0f - tc * tc);
+                const float d_i = dc * gg * gi * (1.0f - gi);
+                const float d_f = dc * c_p[hf][e] * gf * (1.0f - gf);
+                const float d_g = dc * gi * (1.0f - gg * gg);
+                dc_carry[hf][e] = dc * gf;
+                __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut) + hf * OUT_CHUNKS * 8 + n * 32 +
+                                    (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7);
+                so[0 * 2 * OUT_CHUNKS * 8] = __float2bfloat16(d_i);
+                so[1 * 2 * OUT_CHUNKS * 8] = __float2bfloat16(d_f);
+                so[2 * 2 * OUT_CHUNKS * 8] = __float2bfloat16(d_g);
+                so[3 * 2 * OUT_CHUNKS * 8] = __float2bfloat16(d_o);
+                __nv_bfloat162 b01 = __floats2bfloat162_rn(d_i, d_f), b23 = __floats2bfloat162_rn(d_g, d_o);
+                dgp[hf][e] = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
+            }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (t + 1 < T) {
+            // gate g's two adjacent 32-unit blocks -> K blocks (4 mb + 2 qp, +1) of local gate (g & 1) in CTA (g >> 1, mb')
+            const uint32_t koff = (4 * mb + 2 * qp) * BLK_BYTES;
+            for (int i = warp; i < 4 * MB; i += 8) {
+                const int g = i / MB, mdst = i - g * MB;
+                const uint32_t peer = rank_of(g >> 1, mdst);
+                const uint32_t dst = smem_u32(sB) + ((g & 1) * 2 + ((t + 1) & 1)) * img_bytes + koff;
+                if (warp_leader)
+                    bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * 2 * OUT_CHUNKS), 2 * BLK_BYTES,
+                                      mapa_shared(smem_u32(&b_full[(t + 1) & 1]), peer));
+            }
+            if (warp_leader) bulk_commit();
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int gn = p.n0 + grp * NB + warp + 8 * e;
+                const int unit = unit0 + 32 * hf;
+                if (gn < N)
+                    *reinterpret_cast<uint2*>(p.dg + (static_cast<size_t>(tt) * N + gn) * G8 + static_cast<size_t>(dir) * 4 * H +
+                                              static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4) = dgp[hf][e];
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 bool weights_in_tmem() {
     const char* e = getenv("CTCB200_LSTM_A");  // "smem" keeps the weight slice in shared memory (A/B comparison runs)
     return !(e && e[0] == 's');
+}
+
+// H in (512, 640]: the two-tile cluster kernels (64 units per CTA); CTCB200_LSTM_EXCHANGE=global keeps the old path
+bool two_tile_path(int H) {
+    const char* e = getenv("CTCB200_LSTM_EXCHANGE");
+    if (e && e[0] == 'g') return false;
+    return H > 512 && H <= 640 && H % 128 == 0 && weights_in_tmem();
 }
 
 // warps that issue slices of the per-step MMA chain (each into its own TMEM accumulator, 64 columns in total)
@@ -882,6 +1303,24 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_fwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_fwd: hidden size %d must be a multiple of 128 in [128,640]", H);
+    if (two_tile_path(H)) {
+        // H > 512: 64 units per CTA (tile 0 in TMEM, tile 1 in shared memory), H/64 CTAs per cluster, NB = 16
+        constexpr int NB2 = 16;
+        const int groups2 = (N + NB2 - 1) / NB2;
+        CUtensorMap tmW2;
+        int rc2 = make_tmap_bf16_2d(&tmW2, whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+        if (rc2 != OK) return rc2;
+        const size_t smem2 = static_cast<size_t>(128) * H * 2 + static_cast<size_t>(2) * H * NB2 * 2 +
+                             static_cast<size_t>(2) * 32 * (NB2 * 4 + 4) * 4 + static_cast<size_t>(2) * NB2 * 4 * 16 + 64 + 1024;
+        CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
+        FwdParams p2;
+        p2.gx = gx; p2.hout = hout; p2.c_save = c_save; p2.gates_save = static_cast<uint2*>(gates_save);
+        p2.himg = nullptr; p2.flags = nullptr; p2.trace = nullptr;
+        p2.w = static_cast<const __nv_bfloat16*>(whh_packed); p2.a_tmem = 1; p2.mma_split = 4;
+        p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
+        return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p2,
+                                stream);
+    }
     const int ex = exchange_mode(H);
     const bool cl = ex != 0;
     const int NB = pick_nb(N, H, batch_tile, false, cl);
@@ -974,6 +1413,24 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_bwd: hidden size %d must be a multiple of 128 in [128,640]", H);
+    if (two_tile_path(H)) {
+        constexpr int NB2 = 16;
+        const int groups2 = (N + NB2 - 1) / NB2;
+        CUtensorMap tmWT2;
+        int rc2 = make_tmap_bf16_2d(&tmWT2, whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+        if (rc2 != OK) return rc2;
+        const size_t smem2 = static_cast<size_t>(128) * (H - 256) * 2 + static_cast<size_t>(4) * H * NB2 * 2 +
+                             static_cast<size_t>(4) * NB2 * 32 * 4 * 2 + static_cast<size_t>(8) * NB2 * 4 * 16 + 64 + 1024;
+        CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
+        BwdParams p2;
+        p2.dhout = dhout; p2.c_save = c_save; p2.gates_save = static_cast<const uint2*>(gates_save);
+        p2.dg = static_cast<__nv_bfloat16*>(dg);
+        p2.dgimg = nullptr; p2.flags = nullptr;
+        p2.w = static_cast<const __nv_bfloat16*>(whhT_packed); p2.a_tmem = 1; p2.mma_split = 4;
+        p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
+        return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false, tmWT2,
+                                p2, stream);
+    }
     const int ex = exchange_mode(H);
     const bool cl = ex != 0;
     const int NB = pick_nb(N, H, batch_tile, true, cl);
