@@ -1256,6 +1256,64 @@ int pick_nb(int N, int H, int force_nb, bool bwd, bool cl) {
     return 32;
 }
 
+// Can at least one cluster of this shape be resident? (fails on parts / partitions whose GPCs are too small)
+template <typename Kern>
+bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem);
+
+template <typename Kern>
+bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem) {
+    // the answer depends only on (kernel, cluster shape, shared memory): remember the last few probes
+    struct Entry { const void* k; unsigned cx, cy; size_t smem; bool ok; };
+    static Entry cache[16];
+    static int n_cache = 0;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].k == reinterpret_cast<const void*>(kern) && cache[i].cx == cluster.x && cache[i].cy == cluster.y &&
+            cache[i].smem == smem)
+            return cache[i].ok;
+    const bool ok = cluster_probe(kern, grid, cluster, smem);
+    if (n_cache < 16) cache[n_cache++] = Entry{reinterpret_cast<const void*>(kern), cluster.x, cluster.y, smem, ok};
+    return ok;
+}
+
+template <typename Kern>
+bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    if (cluster.x * cluster.y * cluster.z > 8 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(LSTM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = cluster.x; attr.val.clusterDim.y = cluster.y; attr.val.clusterDim.z = cluster.z;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return n >= 1;
+}
+
+using FwdKern = void (*)(CUtensorMap, FwdParams);
+using BwdKern = void (*)(CUtensorMap, BwdParams);
+FwdKern fwd_kernel(int NB, int ex) {
+    if (NB == 16) return ex == 1 ? lstm_fwd_kernel<16, 1> : ex == 2 ? lstm_fwd_kernel<16, 2> : ex == 3 ? lstm_fwd_kernel<16, 3> : lstm_fwd_kernel<16, 0>;
+    return ex == 1 ? lstm_fwd_kernel<32, 1> : ex == 2 ? lstm_fwd_kernel<32, 2> : ex == 3 ? lstm_fwd_kernel<32, 3> : lstm_fwd_kernel<32, 0>;
+}
+BwdKern bwd_kernel(int NB, int ex) {
+    if (NB == 16) return ex == 1 ? lstm_bwd_kernel<16, 1> : ex == 2 ? lstm_bwd_kernel<16, 2> : ex == 3 ? lstm_bwd_kernel<16, 3> : lstm_bwd_kernel<16, 0>;
+    return ex == 1 ? lstm_bwd_kernel<32, 1> : ex == 2 ? lstm_bwd_kernel<32, 2> : ex == 3 ? lstm_bwd_kernel<32, 3> : lstm_bwd_kernel<32, 0>;
+}
+
 template <typename Kern, typename Params>
 int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool cooperative, const CUtensorMap& tm,
                      const Params& p, cudaStream_t stream) {
@@ -1318,10 +1376,17 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         p2.himg = nullptr; p2.flags = nullptr; p2.trace = nullptr;
         p2.w = static_cast<const __nv_bfloat16*>(whh_packed); p2.a_tmem = 1; p2.mma_split = 4;
         p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
-        return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p2,
-                                stream);
+        if (cluster_ok(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2))
+            return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p2,
+                                    stream);
     }
-    const int ex = exchange_mode(H);
+    int ex = exchange_mode(H);
+    {   // fall back to the global-memory exchange when a cluster of this size cannot be scheduled on this device
+        const int nb_try = pick_nb(N, H, batch_tile, false, ex != 0);
+        if (ex != 0 && !cluster_ok(fwd_kernel(nb_try, ex), dim3(H / 32, 2, (N + nb_try - 1) / nb_try), dim3(H / 32, 1, 1),
+                                   lstm_smem_bytes(nb_try, H, false, ex, weights_in_tmem())))
+            ex = 0;
+    }
     const bool cl = ex != 0;
     const int NB = pick_nb(N, H, batch_tile, false, cl);
     const int groups_total = (N + NB - 1) / NB;
@@ -1428,10 +1493,17 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         p2.dgimg = nullptr; p2.flags = nullptr;
         p2.w = static_cast<const __nv_bfloat16*>(whhT_packed); p2.a_tmem = 1; p2.mma_split = 4;
         p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
-        return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false, tmWT2,
-                                p2, stream);
+        if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
+            return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false,
+                                    tmWT2, p2, stream);
     }
-    const int ex = exchange_mode(H);
+    int ex = exchange_mode(H);
+    {
+        const int nb_try = pick_nb(N, H, batch_tile, true, ex != 0);
+        if (ex != 0 && !cluster_ok(bwd_kernel(nb_try, ex), dim3(4, H / 128, 2 * ((N + nb_try - 1) / nb_try)),
+                                   dim3(4, H / 128, 1), lstm_smem_bytes(nb_try, H, true, ex, weights_in_tmem())))
+            ex = 0;
+    }
     const bool cl = ex != 0;
     const int NB = pick_nb(N, H, batch_tile, true, cl);
     const int groups_total = (N + NB - 1) / NB;
