@@ -277,11 +277,14 @@ def run_ours(args, cfg, rank, world):
         return r
     L.call = timed_call
     prof_steps = 3
+    overlap_was = model.overlap_wgrad
+    model.overlap_wgrad = False  # kernels timed one at a time on one stream (the timed steps above overlap the wgrad GEMMs)
     for k in range(prof_steps):
         flush.zero_()
         step_dev(devb[k % n_batches], comm=False)  # rank 0 only: no collective in this diagnostic pass
     torch.cuda.synchronize()
     L.call = orig_call
+    model.overlap_wgrad = overlap_was
     kern_ms = {nm: sum(s.elapsed_time(e) for s, e in v) / prof_steps for nm, v in per_call.items()}
     kern_cnt = {nm: len(v) // prof_steps for nm, v in per_call.items()}
     step_ms_prof = sum(kern_ms.values())

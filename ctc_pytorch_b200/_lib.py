@@ -19,6 +19,7 @@ _CT = {
     "int64_t": ctypes.c_int64,
     "float": ctypes.c_float,
     "double": ctypes.c_double,
+    "uint32_t": ctypes.c_uint32,
     "ctcb200_stream_t": ctypes.c_void_p,
 }
 
@@ -50,7 +51,7 @@ def parse_header(path=HEADER_PATH):
 
 
 # kernels of ours enqueued by one call of each entry point (memsets not counted)
-KERNELS_PER_CALL = {"ctcb200_greedy_decode": 2, "ctcb200_bn_train_stats": 2, "ctcb200_bn_bwd": 2}
+KERNELS_PER_CALL = {"ctcb200_stream_wait_geq": 0, "ctcb200_greedy_decode": 2, "ctcb200_bn_train_stats": 2, "ctcb200_bn_bwd": 2}
 
 
 class _Lib(object):

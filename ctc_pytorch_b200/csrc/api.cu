@@ -111,3 +111,31 @@ int device_sm_count() {
 extern "C" CTCB200_API const char* ctcb200_last_error(void) { return ctcb200::g_err; }
 
 extern "C" CTCB200_API int ctcb200_version(void) { return 100; }
+
+// Stream-ordered wait on a device word (driver stream memory operation): work enqueued on `stream` after this call
+// does not start before *counter >= value (wrap-around compare). No SM is occupied while waiting.
+extern "C" CTCB200_API int ctcb200_stream_wait_geq(ctcb200_stream_t stream_, const void* counter, uint32_t value) {
+    typedef CUresult (*WaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WaitFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            (void)cudaGetLastError();
+            ctcb200::set_error("cuStreamWaitValue32 driver entry point unavailable");
+            return ctcb200::ERR_DRIVER;
+        }
+        fn = reinterpret_cast<WaitFn>(p);
+    }
+    if (!counter || (reinterpret_cast<uintptr_t>(counter) & 3) != 0) {
+        ctcb200::set_error("stream_wait_geq: counter %p must be a 4-byte aligned device address", counter);
+        return ctcb200::ERR_INVALID;
+    }
+    CUresult r = fn(static_cast<CUstream>(stream_), reinterpret_cast<CUdeviceptr>(counter), value, 0u /* GEQ */);
+    if (r != CUDA_SUCCESS) {
+        ctcb200::set_error("cuStreamWaitValue32 failed (%d)", static_cast<int>(r));
+        return ctcb200::ERR_DRIVER;
+    }
+    return ctcb200::OK;
+}

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int RENORM = 8;  // alpha / beta rows are renormalised every RENORM frames
+constexpr int PF = 8;      // log-prob rows kept in flight per sweep (cp.async ring): hides the L2/HBM latency of a row
 #define NEG_INF (-INFINITY)
 
 __device__ __forceinline__ float lse2(float a, float b) {
@@ -32,20 +33,41 @@ __device__ __forceinline__ float lse2(float a, float b) {
     if (m == NEG_INF) return NEG_INF;
     return m + logf(expf(a - m) + expf(b - m));
 }
+// Branch-free log-sum-exp of three terms on the dependent chain of the sweeps: ex2.approx / lg2.approx (one MUFU op
+// each). The arguments of ex2 are <= 0 and only terms within ~20 of the maximum matter, where the scaled-argument
+// rounding is < 1e-6 relative; the sum lies in [1, 3], where lg2.approx has ~2^-22 absolute error — both below the
+// fp32 spacing of the renormalised alpha / beta values themselves. All-(-inf) inputs give -inf without a branch:
+// ex2(-inf) = 0, lg2(0) = -inf.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float lse3(float a, float b, float c) {
-    float m = fmaxf(a, fmaxf(b, c));
-    if (m == NEG_INF) return NEG_INF;
-    return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    const float m = fmaxf(a, fmaxf(b, c));
+    const float ms = (m == NEG_INF) ? 0.0f : m;
+    // differences first: the maximum term is exactly ex2(0) = 1 and terms near it keep full relative precision
+    const float sum = ex2_approx((a - ms) * LOG2E) + ex2_approx((b - ms) * LOG2E) + ex2_approx((c - ms) * LOG2E);
+    return fmaf(lg2_approx(sum), LN2, ms);
 }
 
 __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
-__device__ __forceinline__ void prefetch_row(float* dst, const float* src, int C, int lane) {
-    for (int c = lane; c < C; c += 32) cp_async_4(dst + c, src + c);
+// one commit group per call, empty when `pred` is false, so the group count stays in step with the frame count
+__device__ __forceinline__ void prefetch_row(float* dst, const float* src, int C, int lane, bool pred) {
+    if (pred)
+        for (int c = lane; c < C; c += 32) cp_async_4(dst + c, src + c);
     cp_async_commit();
 }
 
@@ -92,7 +114,7 @@ ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
     const int n = blockIdx.x * (WARPS_PER_BLOCK / 2) + (warp >> 1);
     const bool is_beta = warp & 1;
     if (n >= N) return;
-    float* rowbuf = smem + warp * 2 * C;  // two rows
+    float* rowbuf = smem + warp * PF * C;  // ring of PF rows
 
     const int S = static_cast<int>(tgt_len[n]);
     const int L = 2 * S + 1;
@@ -107,7 +129,7 @@ ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
     }
     LaneStates<KS> st;
     load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
-    const size_t row_stride = static_cast<size_t>(N) * C;
+    const long long row_stride = static_cast<long long>(N) * C;
     const float* lp_n = lp + static_cast<size_t>(n) * C;
     float* hist = (is_beta ? hist_b : hist_a) + static_cast<size_t>(n) * T * (KS * 32);
     double* offs = (is_beta ? off_b : off_a) + static_cast<size_t>(n) * T;
@@ -115,12 +137,15 @@ ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
     float a[KS];
 
     if (!is_beta) {
-        prefetch_row(rowbuf, lp_n, C, lane);
+        // rows 0 .. PF-2 in flight before the first frame; frame t tops the ring up with row t + PF - 1, whose slot held
+        // row t - 1 (all lanes are done with it after the __syncwarp)
+#pragma unroll
+        for (int i = 0; i < PF - 1; ++i) prefetch_row(rowbuf + i * C, lp_n + i * row_stride, C, lane, i < Tn);
         for (int t = 0; t < Tn; ++t) {
-            float* cur = rowbuf + (t & 1) * C;
-            cp_async_wait_all();
+            float* cur = rowbuf + (t % PF) * C;
+            cp_async_wait_pending<PF - 2>();
             __syncwarp();
-            if (t + 1 < Tn) prefetch_row(rowbuf + ((t + 1) & 1) * C, lp_n + (t + 1) * row_stride, C, lane);
+            prefetch_row(rowbuf + ((t + PF - 1) % PF) * C, lp_n + (t + PF - 1) * row_stride, C, lane, t + PF - 1 < Tn);
             if (t == 0) {
 #pragma unroll
                 for (int j = 0; j < KS; ++j) {
@@ -177,12 +202,19 @@ ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
             nll_d[n] = v;
         }
     } else {
-        prefetch_row(rowbuf + ((Tn - 1) & 1) * C, lp_n + (Tn - 1) * row_stride, C, lane);
+#pragma unroll
+        for (int i = 0; i < PF - 1; ++i) {
+            const int r = Tn - 1 - i;
+            prefetch_row(rowbuf + ((r % PF + PF) % PF) * C, lp_n + static_cast<long long>(r) * row_stride, C, lane, r >= 0);
+        }
         for (int t = Tn - 1; t >= 0; --t) {
-            float* cur = rowbuf + (t & 1) * C;
-            cp_async_wait_all();
+            float* cur = rowbuf + (t % PF) * C;
+            cp_async_wait_pending<PF - 2>();
             __syncwarp();
-            if (t > 0) prefetch_row(rowbuf + ((t - 1) & 1) * C, lp_n + (t - 1) * row_stride, C, lane);
+            {
+                const int r = t - (PF - 1);
+                prefetch_row(rowbuf + ((r % PF + PF) % PF) * C, lp_n + static_cast<long long>(r) * row_stride, C, lane, r >= 0);
+            }
             if (t == Tn - 1) {
 #pragma unroll
                 for (int j = 0; j < KS; ++j) {
@@ -328,7 +360,7 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const in
     CTCB_REQUIRE(ks <= 16, "ctc_loss_fwd: target length %d exceeds the supported maximum 255", max_target_len);
     const int utt_per_block = WARPS_PER_BLOCK / 2;
     dim3 grid((N + utt_per_block - 1) / utt_per_block), block(WARPS_PER_BLOCK * 32);
-    size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * 2 * C * sizeof(float);
+    size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * PF * C * sizeof(float);
     CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_fwd: class count %d too large for the row buffer", C);
     CtcWs w = carve(alpha_ws, T, N, ks);
 #define LAUNCH_A(KS)                                                                                          \

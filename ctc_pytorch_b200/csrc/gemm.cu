@@ -285,7 +285,8 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
                  "gemm: K offsets (%d, %d) must be non-negative multiples of 8 (TMA box start is 16-byte aligned)", a_koff,
                  b_koff);
     int bn = force_bn;
-    const int sms = device_sm_count();
+    // SMs this launch may use: a positive max_ctas leaves the rest of the device to a concurrent kernel
+    const int sms = (max_ctas > 0 && max_ctas < device_sm_count()) ? max_ctas : device_sm_count();
     const int m_tiles = (M + BM - 1) / BM;
     if (bn == 0) {
         // waves x measured relative cost of one tile (B200: 256-wide tiles run the tensor pipe ~65 % busy, 128-wide
@@ -317,7 +318,7 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
     // split K when the output has too few tiles to fill the machine and K is long (weight gradients: K = T*N);
     // partial tiles are added into a zeroed C by the TMA unit
     int split_k = 1;
-    if (tma_store && max_ctas == 0 && ldc == N) {
+    if (tma_store && max_ctas >= 0 && ldc == N) {
         const long long t = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
         const int kblocks = (K + BK - 1) / BK;
         while (split_k < 8 && t * (split_k * 2) <= sms && kblocks / (split_k * 2) >= 16) split_k *= 2;

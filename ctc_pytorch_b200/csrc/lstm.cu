@@ -43,6 +43,12 @@ __device__ __forceinline__ void wait_counter(const unsigned int* flag, unsigned 
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// single-MUFU hyperbolic tangent (max relative error ~2^-11): experiment switch CTCB200_LSTM_ACT=approx
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // Pack the bf16 of 8 consecutive lanes (this lane = lowest) into a uint4; valid on lanes % 8 == 0.
 __device__ __forceinline__ uint4 pack8_bf16(float v) {
@@ -176,6 +182,7 @@ struct FwdParams {
     const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (source of the TMEM-resident A operand)
     int a_tmem;               // 1: A operand resident in TMEM, 0: in shared memory (TMA-loaded)
     int mma_split;            // number of warps (1, 2 or 4) that issue slices of the K chain into their own accumulator
+    int act_approx;           // 1: gate non-linearities through tanh.approx (one MUFU op each)
 };
 
 // CL = true: the H/32 CTAs of one (direction, batch group) form one thread-block cluster and exchange h_t through
@@ -257,6 +264,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     const int row = lq * 32 + lane;            // gate row inside this CTA's 128
     const int u_loc = row >> 2, q = row & 3;   // hidden unit (0..31) and gate (i,f,g,o)
     const float act_s = (q == 2) ? 2.0f : 1.0f;
+    const float act_h = (q == 2) ? 1.0f : 0.5f;
     const size_t gx_col = static_cast<size_t>(dir) * 4 * H + j * 128 + row;
     const size_t G8 = static_cast<size_t>(8) * H, H2 = static_cast<size_t>(2) * H;
     __nv_bfloat16* img = PUSH ? nullptr : p.himg + (static_cast<size_t>(dir) * p.groups + grp) * 2 * H * NB;
@@ -358,7 +366,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const float pre = __uint_as_float(acc[c]) + gx[c];
-            const float a = act_s * fast_sigmoid(act_s * pre) - (act_s - 1.0f);  // sigmoid, or tanh for gate g
+            float a;
+            if (p.act_approx) a = act_h * tanh_approx(act_h * pre) + (1.0f - act_h);   // sigmoid(x) = (tanh(x/2) + 1) / 2
+            else a = act_s * fast_sigmoid(act_s * pre) - (act_s - 1.0f);              // sigmoid, or tanh for gate g
             sS[u_loc * S_STRIDE + (ch * CPT + c) * 4 + q] = a;
         }
         TRACE(10);
@@ -374,7 +384,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             const float4 g4 = *reinterpret_cast<const float4*>(&sS[lane * S_STRIDE + n * 4]);
             const float cn = g4.y * c_state[e] + g4.x * g4.z;
             c_state[e] = cn;
-            const float h = g4.w * fast_tanh(cn);
+            const float h = g4.w * (p.act_approx ? tanh_approx(cn) : fast_tanh(cn));
             hv[e] = h;
             gv[e] = g4;
             if constexpr (PUSH) {
@@ -471,7 +481,22 @@ struct BwdParams {
     const __nv_bfloat16* w;    // packed transposed recurrent weights [8H, H]
     int a_tmem;
     int mma_split;
+    unsigned int* resident;    // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
 };
+
+// Tell the host-side scheduler that the whole grid of this launch is resident: from then on the SMs this kernel does
+// not use can be handed to off-critical-path work (the weight-gradient GEMMs of the layer above) without delaying the
+// cluster launch. The last CTA to arrive publishes; the arrival word is reset for the next launch.
+__device__ __forceinline__ void announce_resident(unsigned int* resident) {
+    if (resident != nullptr && threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(resident + 1, 1u) == total - 1) {
+            atomicExch(resident + 1, 0u);
+            __threadfence();
+            atomicAdd(resident, 1u);
+        }
+    }
+}
 
 // CTA (mb, q) keeps the [128 units x H] slice of gate q's transposed recurrent block. Per BPTT step:
 //   partial dh[128, NB] = slice * dG_q  ->  reduce-scatter of the 4 gate partials inside the (4,*) cluster row
@@ -505,6 +530,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    announce_resident(p.resident);
     const int q = blockIdx.x;   // gate handled by this CTA
     const int mb = blockIdx.y;  // block of 128 hidden units
     const int MB = gridDim.y;
@@ -1001,6 +1027,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    announce_resident(p.resident);
     const int qp = blockIdx.x, mb = blockIdx.y, MB = gridDim.y;
     const int dir = blockIdx.z / p.groups, grp = blockIdx.z % p.groups;
     const int ctas = 2 * MB;
@@ -1355,6 +1382,17 @@ extern "C" CTCB200_API int64_t ctcb200_lstm_scratch_bytes(int N, int H) {
     return 2 * groups * 8 * static_cast<int64_t>(H) * 32 * 2 + 2 * groups * 32 * 4 + 1024;
 }
 
+extern "C" CTCB200_API int ctcb200_lstm_bwd_ctas(int N, int H, int batch_tile) {
+    // SMs the (first) BPTT launch occupies: one CTA per SM, 4 gates x H/128 unit blocks x 2 directions x batch groups
+    if (H % 128 != 0 || H < 128 || H > 640 || N <= 0) return 0;
+    const int nb = two_tile_path(H) ? 16 : pick_nb(N, H, batch_tile, true, exchange_mode(H) != 0);
+    const int groups = (N + nb - 1) / nb;
+    const int per_group = two_tile_path(H) ? 2 * 2 * (H / 128) : 2 * 4 * (H / 128);
+    const int sms = device_sm_count();
+    const int total = per_group * groups;
+    return total < sms ? total : sms;
+}
+
 extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, float* hout, float* c_save,
                                             void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
                                             ctcb200_stream_t stream_) {
@@ -1373,7 +1411,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
         FwdParams p2;
         p2.gx = gx; p2.hout = hout; p2.c_save = c_save; p2.gates_save = static_cast<uint2*>(gates_save);
-        p2.himg = nullptr; p2.flags = nullptr; p2.trace = nullptr;
+        p2.himg = nullptr; p2.flags = nullptr; p2.trace = nullptr; p2.act_approx = 0;
         p2.w = static_cast<const __nv_bfloat16*>(whh_packed); p2.a_tmem = 1; p2.mma_split = 4;
         p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
         if (cluster_ok(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2))
@@ -1399,6 +1437,10 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     FwdParams p;
     p.gx = gx; p.hout = hout; p.c_save = c_save; p.gates_save = static_cast<uint2*>(gates_save);
     p.himg = nullptr; p.flags = nullptr; p.trace = nullptr;
+    {
+        const char* act = getenv("CTCB200_LSTM_ACT");
+        p.act_approx = (act != nullptr && act[0] == 'a') ? 1 : 0;
+    }
     p.w = static_cast<const __nv_bfloat16*>(whh_packed); p.a_tmem = a_tmem ? 1 : 0;
     p.mma_split = mma_issuers(NB, H, a_tmem);
     p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
@@ -1474,9 +1516,10 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
 
 extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
                                             const void* gates_save, void* dg, void* scratch, int T, int N, int H,
-                                            int batch_tile, ctcb200_stream_t stream_) {
+                                            int batch_tile, void* resident_counter, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
+    CTCB_REQUIRE((reinterpret_cast<uintptr_t>(resident_counter) & 3) == 0, "lstm_bwd: resident_counter must be 4-byte aligned");
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_bwd: hidden size %d must be a multiple of 128 in [128,640]", H);
     if (two_tile_path(H)) {
         constexpr int NB2 = 16;
@@ -1490,7 +1533,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         BwdParams p2;
         p2.dhout = dhout; p2.c_save = c_save; p2.gates_save = static_cast<const uint2*>(gates_save);
         p2.dg = static_cast<__nv_bfloat16*>(dg);
-        p2.dgimg = nullptr; p2.flags = nullptr;
+        p2.dgimg = nullptr; p2.flags = nullptr; p2.resident = static_cast<unsigned int*>(resident_counter);
         p2.w = static_cast<const __nv_bfloat16*>(whhT_packed); p2.a_tmem = 1; p2.mma_split = 4;
         p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
@@ -1517,7 +1560,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     BwdParams p;
     p.dhout = dhout; p.c_save = c_save; p.gates_save = static_cast<const uint2*>(gates_save);
     p.dg = static_cast<__nv_bfloat16*>(dg);
-    p.dgimg = nullptr; p.flags = nullptr;
+    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter);
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed); p.a_tmem = a_tmem ? 1 : 0;
     p.mma_split = mma_issuers(NB, H, a_tmem);
     p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
@@ -1551,6 +1594,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         p.dgimg = reinterpret_cast<__nv_bfloat16*>(scr);
         p.flags = reinterpret_cast<unsigned int*>(scr + img_bytes);
         p.groups = groups; p.n0 = g0 * NB;
+        if (g0 > 0) p.resident = nullptr;
         dim3 grid(4, MB, 2 * groups), cluster(4, 1, 1);
         const bool coop = getenv("CTCB200_BWD_NO_COOP") == nullptr;  // profilers may reject cooperative + cluster
         if (NB == 16) rc = launch_clustered(lstm_bwd_kernel<16, 0>, grid, cluster, smem, coop, tmWT, p, stream);

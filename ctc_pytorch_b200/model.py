@@ -14,6 +14,7 @@ layer 0 never has BatchNorm, BatchNorm statistics are over T*N rows, the fc Batc
 rnn_param['batch_norm'].
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -109,6 +110,25 @@ def _side_stream(dev):
     return _SIDE_STREAMS[key]
 
 
+_RESIDENT = {}
+
+
+def _resident_state(dev):
+    """[uint32[2] device counter, host-side expected value] for the BPTT 'grid is resident' notifications."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _RESIDENT:
+        _RESIDENT[key] = [torch.zeros(2, dtype=torch.int32, device=dev), 0]
+    return _RESIDENT[key]
+
+
+def _overlap_enabled(model):
+    """Weight-gradient work on a side stream under the BPTT kernels (CTC_Model.overlap_wgrad, env override)."""
+    env = os.environ.get("CTCB200_OVERLAP_WGRAD")
+    if env is not None:
+        return env == "1"
+    return bool(getattr(model, "overlap_wgrad", True))
+
+
 class _BNState(object):
     __slots__ = ("mean", "rstd", "scale", "shift")
 
@@ -164,7 +184,13 @@ class _RnnStackFn(torch.autograd.Function):
         stream = _lib.stream
 
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
-        X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=need_grad)
+        # With the overlapped weight-gradient pipeline the transposed operands (X^T, H^T) are only produced in the
+        # backward pass, on the side stream, so the forward pass does not pay for them.
+        defer_t = need_grad and _overlap_enabled(model)
+        want_t = need_grad and not defer_t
+        ws.defer_t = defer_t
+        X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=want_t)
+        ws.x_src = x_src if defer_t else None
         h_prev = None
         I = I0
         for li, layer in enumerate(layers):
@@ -176,9 +202,9 @@ class _RnnStackFn(torch.autograd.Function):
                 rec.I = I
                 if layer.batch_norm is not None:
                     rec.bn = _bn_prepare(layer.batch_norm, h_prev, R, I, training)
-                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, rec.bn.scale, rec.bn.shift, True, need_grad)
+                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, rec.bn.scale, rec.bn.shift, True, want_t)
                 else:
-                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, None, None, True, need_grad)
+                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, None, None, True, want_t)
             Ipad = _round_up(I, 8)
             rnn = layer.rnn
             wih_p = torch.empty((8 * H, Ipad), dtype=torch.bfloat16, device=dev)
@@ -196,10 +222,12 @@ class _RnnStackFn(torch.autograd.Function):
                   _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, stream())
             del gx
             rec.HT = None
-            if need_grad:
-                _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True)
-            rec.mask = None
             p_drop = float(layer.dropout.p)
+            # H^T pairs dG_t with the *pre-dropout* h_{t-1}: it can only be deferred when hout is not modified in place
+            if need_grad and not (defer_t and not (training and p_drop > 0.0)):
+                _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True)
+            rec.h_out = hout if need_grad else None
+            rec.mask = None
             if training and p_drop > 0.0:
                 rec.mask = (torch.rand(hout.shape, device=dev) >= p_drop).to(torch.uint8)
                 _call("ctcb200_dropout_apply", _lib.ptr(hout), _lib.ptr(rec.mask), 1.0 / (1.0 - p_drop), hout.numel(),
@@ -239,9 +267,13 @@ class _RnnStackFn(torch.autograd.Function):
         grads = {}
         grad_x = None
         main = torch.cuda.current_stream(dev)
-        overlap = bool(getattr(model, "overlap_wgrad", False))  # measured on B200: side-stream wgrad GEMMs delay the cluster launches (26.8 vs 21.7 ms/step)
+        overlap = bool(ws.defer_t)
         side = _side_stream(dev) if overlap else None
         keep = []
+        if overlap:
+            res = _resident_state(dev)
+            side_ctas = max(8, torch.cuda.get_device_properties(dev).multi_processor_count
+                            - int(_lib.lib().dll.ctcb200_lstm_bwd_ctas(N, H, model.batch_tile)))
 
         g = g_out.detach().to(torch.float32).contiguous()
         dlogits = torch.empty((R, C), dtype=torch.float32, device=dev)
@@ -258,6 +290,39 @@ class _RnnStackFn(torch.autograd.Function):
                   _lib.ptr(fc_bn.weight), _lib.ptr(dh), _lib.ptr(dgam), _lib.ptr(dbet), R, F2, _lib.ptr(dws), stream())
             grads[fc_bn.weight], grads[fc_bn.bias] = dgam, dbet
 
+        def _wgrad(item, mc):
+            """dW_ih, dW_hh (both directions) of one layer from its gate gradients; runs on the current stream."""
+            layer_, rec_, dg_, li_ = item
+            rnn = layer_.rnn
+            I_ = rec_.I
+            XT, HT = rec_.XT, rec_.HT
+            if XT is None:   # deferred transposed operands (see forward)
+                if li_ == 0:
+                    _, XT = _cast_t(ws.x_src, ws.geom[3], ws.geom[4], N, R, I_, want=False, want_t=True)
+                elif rec_.bn is not None:
+                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, rec_.bn.scale, rec_.bn.shift, False, True)
+                else:
+                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, None, None, False, True)
+            if HT is None:
+                _, HT = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True)
+            dgT = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
+            _call("ctcb200_transpose_dg", _lib.ptr(dg_), _lib.ptr(dgT), Rp, N, Np, R, H, stream())
+            dwih = ops.gemm_tn(dgT, XT, k=Rp, max_ctas=mc)                 # [8H, I], torch row order
+            grads[rnn.weight_ih_l0], grads[rnn.weight_ih_l0_reverse] = dwih[:4 * H], dwih[4 * H:]
+            if T > 1:
+                K = Rp - Np  # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan
+                grads[rnn.weight_hh_l0] = ops.gemm_tn(dgT[:4 * H], HT[:H], a_koff=Np, b_koff=0, k=K, max_ctas=mc)
+                grads[rnn.weight_hh_l0_reverse] = ops.gemm_tn(dgT[4 * H:], HT[H:], a_koff=0, b_koff=Np, k=K,
+                                                              max_ctas=mc)
+            else:
+                grads[rnn.weight_hh_l0] = torch.zeros_like(rnn.weight_hh_l0)
+                grads[rnn.weight_hh_l0_reverse] = torch.zeros_like(rnn.weight_hh_l0_reverse)
+            if torch.cuda.current_stream(dev) != main:  # consumed on the main stream after the join
+                for g_ in (dwih, grads[rnn.weight_hh_l0], grads[rnn.weight_hh_l0_reverse]):
+                    g_.record_stream(main)
+            keep.append((dg_, dgT, XT, HT))  # alive until the streams are joined
+
+        pending = None
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
         for li in range(len(layers) - 1, -1, -1):
             layer, rec = layers[li], ws.L[li]
@@ -267,32 +332,21 @@ class _RnnStackFn(torch.autograd.Function):
                       dh.numel(), stream())
             dg = torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev)
             _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p), _lib.ptr(rec.c_save), _lib.ptr(rec.gates),
-                  _lib.ptr(dg), _lib.ptr(scratch), T, N, H, model.batch_tile, stream())
-            # Weight gradients of this layer are not needed by the rest of the backward pass: they run on a side
-            # stream (short-lived one-tile CTAs on the SMs the latency-bound BPTT kernel of the next layer leaves idle)
-            rnn = layer.rnn
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(side if overlap else main):
-                if overlap:
-                    side.wait_event(ev)
-                mc = -1 if overlap else 0
-                dgT = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
-                _call("ctcb200_transpose_dg", _lib.ptr(dg), _lib.ptr(dgT), Rp, N, Np, R, H, stream())
-                dwih = ops.gemm_tn(dgT, rec.XT, k=Rp, max_ctas=mc)         # [8H, I], torch row order
-                grads[rnn.weight_ih_l0], grads[rnn.weight_ih_l0_reverse] = dwih[:4 * H], dwih[4 * H:]
-                if T > 1:
-                    K = Rp - Np  # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan
-                    grads[rnn.weight_hh_l0] = ops.gemm_tn(dgT[:4 * H], rec.HT[:H], a_koff=Np, b_koff=0, k=K, max_ctas=mc)
-                    grads[rnn.weight_hh_l0_reverse] = ops.gemm_tn(dgT[4 * H:], rec.HT[H:], a_koff=0, b_koff=Np, k=K,
-                                                                  max_ctas=mc)
-                else:
-                    grads[rnn.weight_hh_l0] = torch.zeros_like(rnn.weight_hh_l0)
-                    grads[rnn.weight_hh_l0_reverse] = torch.zeros_like(rnn.weight_hh_l0_reverse)
-                if overlap:  # the gradients are consumed on the main stream after the join
-                    for g_ in (dwih, grads[rnn.weight_hh_l0], grads[rnn.weight_hh_l0_reverse]):
-                        g_.record_stream(main)
-                keep.append((dg, dgT, rec.XT, rec.HT))  # alive until the streams are joined
+                  _lib.ptr(dg), _lib.ptr(scratch), T, N, H, model.batch_tile, _lib.ptr(res[0]) if overlap else None,
+                  stream())
+            # Weight gradients are not needed by the rest of the backward pass. Overlapped mode: those of the layer
+            # above (its dG is complete) go to the side stream, gated on *this* layer's BPTT grid being resident, and
+            # are confined to the SMs that latency-bound kernel leaves idle. The gate is only ever enqueued after the
+            # launch it waits for.
+            if overlap:
+                res[1] = (res[1] + 1) & 0xFFFFFFFF
+                if pending is not None:
+                    with torch.cuda.stream(side):
+                        _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
+                        _wgrad(pending, side_ctas)
+                pending = (layer, rec, dg, li)
+            else:
+                _wgrad((layer, rec, dg, li), 0)
             if li == 0 and ctx.needs_input_grad[1]:
                 dx0 = ops.gemm_tn(dg, rec.wihT_p, k=8 * H)                 # [R, I0] rows (t, n)
                 T0, N0, I0 = ws.geom[0], ws.geom[1], ws.geom[2]
@@ -307,6 +361,8 @@ class _RnnStackFn(torch.autograd.Function):
                           _lib.ptr(bn.weight), _lib.ptr(dh), _lib.ptr(dgam), _lib.ptr(dbet), R, I, _lib.ptr(dws), stream())
                     grads[bn.weight], grads[bn.bias] = dgam, dbet
         if overlap:
+            if pending is not None:
+                _wgrad(pending, 0)  # the first layer's weight gradients: nothing left to hide them under
             main.wait_stream(side)  # every gradient is complete before autograd hands them out
         del keep
         ctx.ws = None
@@ -334,6 +390,7 @@ class CTC_Model(nn.Module):
         self.num_directions = 2 if rnn_param["bidirectional"] else 1
         self.drop_out = drop_out
         self.batch_tile = 0  # 0 = let the library pick the recurrent kernels' batch tile (16 or 32)
+        self.overlap_wgrad = True  # weight-gradient GEMMs on a side stream, on the SMs the BPTT kernels leave idle
 
         rnn_input_size = rnn_param["rnn_input_size"]
         if add_cnn:

@@ -98,7 +98,14 @@ CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, float*
                                  ctcb200_stream_t stream);
 CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
                                  const void* gates_save, void* dg, void* scratch, int T, int N, int H,
-                                 int batch_tile, ctcb200_stream_t stream);
+                                 int batch_tile, void* resident_counter, ctcb200_stream_t stream);
+/* Scheduling aid for overlapping off-critical-path work (weight-gradient GEMMs) with the latency-bound BPTT kernel:
+ * resident_counter (NULL = off) points at two zero-initialised uint32 words owned by the caller; word 0 is incremented
+ * once per lstm_bwd launch as soon as every CTA of that launch is running. ctcb200_stream_wait_geq makes `stream`
+ * wait (a driver stream memory operation, no SM is occupied) until *counter >= value, and ctcb200_lstm_bwd_ctas says
+ * how many SMs the BPTT launch occupies, i.e. how many a concurrent kernel may take (gemm max_ctas). */
+CTCB200_API int ctcb200_lstm_bwd_ctas(int N, int H, int batch_tile);
+CTCB200_API int ctcb200_stream_wait_geq(ctcb200_stream_t stream, const void* counter, uint32_t value);
 
 /* ---- layout / normalisation kernels around the GEMMs (model_ctc.py:29-32 BatchNorm1d over T*N rows,
  * model_ctc.py:136-140,165-168 fc BatchNorm + LogSoftmax, model_ctc.py:175 the (N,T,F)->(T,N,F) transpose).

@@ -348,3 +348,31 @@ def test_dropout_training_mode_runs():
     out = m(torch.randn(3, 12, 40, device=DEV))
     out.sum().backward()
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("H,L,N,drop", [(128, 3, 20, 0.0), (256, 2, 9, 0.2), (640, 2, 40, 0.0)])
+def test_overlapped_wgrad_matches_serial(H, L, N, drop):
+    """The side-stream weight-gradient pipeline (gated on the BPTT grid being resident) changes scheduling only."""
+    from ctc_pytorch_b200.model import CTC_Model
+    from ctc_pytorch_b200.loss import CTCLoss
+    T, F, C = 40, 40, 20
+    rnn_param = {"rnn_input_size": F, "rnn_hidden_size": H, "rnn_layers": L, "rnn_type": nn.LSTM, "bidirectional": True,
+                 "batch_norm": True}
+    torch.manual_seed(H + L)
+    m = CTC_Model(rnn_param=rnn_param, num_class=C, drop_out=drop).to(DEV)
+    x, frac, tg, tl = model_ref.synthetic_batch(T, N, F, C, 6, 11)
+    il = (frac * T).long()
+    m.train()
+    grads = {}
+    for mode in (False, True, True):
+        m.overlap_wgrad = mode
+        m.zero_grad(set_to_none=True)
+        torch.manual_seed(123)  # same dropout masks in both modes
+        out = m(x.to(DEV))
+        loss = CTCLoss(reduction="sum")(out, tg.to(DEV), il.to(DEV), tl.to(DEV)) / N
+        loss.backward()
+        torch.cuda.synchronize()
+        grads[mode] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for k in grads[False]:
+        assert torch.isfinite(grads[True][k]).all(), k
+        assert relnorm(grads[True][k], grads[False][k]) < 1e-4, (k, relnorm(grads[True][k], grads[False][k]))
