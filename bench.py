@@ -168,7 +168,7 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": rate, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # -------------------------------------------------------------------------------------------------------- our arm
@@ -349,10 +349,33 @@ def run_ours(args, cfg, rank, world):
                          "sample": "2 utterances x 2 steps of the same shape, torch CPU kernels (%d threads); "
                                    "oracle/model_ref.py restates the reference's composition" % cores},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr while the run is in progress (NCCL and friends print banners on stdout from C); the one
+    JSON line goes to the real stdout through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
