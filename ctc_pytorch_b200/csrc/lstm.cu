@@ -148,7 +148,8 @@ __device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* __rest
 template <int CPT>
 __device__ __forceinline__ void tmem_ld_cpt(uint32_t taddr, uint32_t (&r)[CPT]) {
     if constexpr (CPT == 16) tmem_ld_32x16(taddr, r);
-    else tmem_ld_32x8(taddr, r);
+    else if constexpr (CPT == 8) tmem_ld_32x8(taddr, r);
+    else tmem_ld_32x4(taddr, r);
 }
 template <int CPT>
 __device__ __forceinline__ void load_partial_sums(uint32_t taddr, int acc_stride, int parts, uint32_t (&acc)[CPT]) {
@@ -464,6 +465,230 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     tc_fence_before();
     __syncthreads();
     if constexpr (CL) cluster_sync_all();  // no CTA exits while a peer may still address its shared memory
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, software-pipelined: the 16 batch columns of a group are two independent recurrences (columns 0-7 = half A,
+// 8-15 = half B). Warps 0-7 run the element phase (TMEM -> gates -> cell -> h_t -> bulk copies to the peers) of A and B
+// alternately; warps 8-11 only issue tensor-core work. While half A's h_t is in flight to the cluster and its next
+// W_hh h product is being issued, the element warps are busy with half B, and vice versa — the DSMEM hand-off and the
+// MMA chain disappear from the per-step critical path of the CTA. Each half has its own mbarriers, accumulators and
+// staging block; both halves share the operand image (half A = rows 0-7 of every 16-row block, half B = rows 8-15:
+// the 1 KB block a CTA contributes per step is the two halves back to back). An MMA (N = 16) of one half also
+// multiplies the other half's rows, possibly mid-update: those accumulator columns are never read.
+// ------------------------------------------------------------------------------------------------
+constexpr int PIPE_THREADS = 512;   // 8 element warps + 4 tensor-core warps + 4 copy warps
+
+__device__ __forceinline__ void bar_sync_elem() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// 4-byte cp.async; `ok` false -> zero fill (src-size 0), so every call belongs to exactly one commit group
+__device__ __forceinline__ void cp_async_f32_zfill(float* smem_dst, const float* gsrc, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ void bulk_wait_read_2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
+    constexpr int NB = 16, HB = 8;              // batch columns per group / per half
+    constexpr uint32_t BLK_BYTES = NB * 64;     // block of one CTA inside the operand image (both halves)
+    constexpr uint32_t HALF_BYTES = HB * 64;
+    constexpr uint32_t ACC_COLS = 128;          // 2 halves x 4 issuing warps x 16 accumulator columns
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = p.H, T = p.T, N = p.N;
+    const int himg_bytes = H * NB * 2;
+    uint8_t* sH = smem;                                                     // two parities
+    uint8_t* sOut = sH + 2 * himg_bytes;                                    // [2 halves][2 parities][HALF_BYTES] staging
+    float* sGx = reinterpret_cast<float*>(sOut + 4 * HALF_BYTES);           // [4 stages][8 batch rows][128 gate rows] (TMA boxes)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sGx + 4 * HB * 128);
+    uint64_t* h_full = bars;          // [half][parity]: every peer's half block of h_{t-1} has landed
+    uint64_t* acc_full = bars + 4;    // [half]: the four partial accumulators of a half-step are complete
+    uint64_t* so_ready = bars + 6;    // [half]: all element warps have staged their part of h_t
+    uint64_t* gx_full = bars + 8;     // [4 stages]: the input-projection box of a half-step has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
+    const int ctas = gridDim.x;
+    const int kblocks = H / 64;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&h_full[i], 1);
+        mbar_init(&acc_full[0], 4);
+        mbar_init(&acc_full[1], 4);
+        mbar_init(&so_ready[0], 8);
+        mbar_init(&so_ready[1], 8);
+        for (int i = 0; i < 4; ++i) mbar_init(&gx_full[i], 1);
+        tma_prefetch_desc(&tmGx);
+        fence_mbar_init();
+        for (int i = 0; i < 4; ++i) mbar_expect_tx(&h_full[i], ctas * HALF_BYTES);
+    }
+    uint32_t tmem_cols = 256;
+    while (tmem_cols < ACC_COLS + H / 2) tmem_cols <<= 1;
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = tid; i < 2 * himg_bytes / 16; i += PIPE_THREADS)
+        reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();
+    if (warp < 4) load_weights_to_tmem(p.w + (static_cast<size_t>(dir) * 4 * H + j * 128) * H, H, tmem_base, ACC_COLS, warp, lane);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
+#define PTRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[t * 16 + (k)] = clock64(); } while (0)
+
+    if (warp >= 12) {
+        // ---------------- copy warps: warp 12 + w ships this CTA's staged half block to peers 4w .. 4w+3 (issuing a bulk
+        // copy costs ~60 cycles of its scheduler, so the sixteen copies are spread over the four schedulers);
+        // the element warps never wait for the copy engine. A staging block (half, parity of t) is reused two steps later,
+        // by which time the element phase has consumed h_{t+1} of every peer, which they could only produce after this
+        // block had landed everywhere — no wait_group needed.
+        // Warp 12 also keeps a 4-deep ring of input-projection boxes (gx rows of the 8 batch columns of a half-step x this
+        // CTA's 128 gate rows, one TMA tensor load each) four half-steps ahead of the element phase.
+        auto fetch_gx = [&](int k) {   // k = 2 t + half
+            const int t_ = k >> 1, half_ = k & 1;
+            const int tt_ = dir ? (T - 1 - t_) : t_;
+            mbar_expect_tx(&gx_full[k & 3], HB * 128 * 4);
+            tma_load_2d(sGx + (k & 3) * HB * 128, &tmGx, &gx_full[k & 3], dir * 4 * H + j * 128, tt_ * N + grp * NB + half_ * HB);
+        };
+        if (warp == 12 && lane == 0)
+            for (int k = 0; k < 4 && k < 2 * T; ++k) fetch_gx(k);
+        for (int t = 0; t + 1 < T; ++t) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&so_ready[half], t & 1);
+                if (warp == 12 && half == 0) PTRACE(10);
+                if (warp == 12 && lane == 0 && 2 * t + half + 4 < 2 * T) fetch_gx(2 * t + half + 4);  // its stage was read in this half-step
+                const int d = (warp - 12) * 4 + lane;
+                if (lane < 4 && d < ctas) {
+                    const uint32_t src = smem_u32(sOut + (half * 2 + (t & 1)) * HALF_BYTES);
+                    const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_BYTES + half * HALF_BYTES;
+                    const uint32_t bar = smem_u32(&h_full[half * 2 + ((t + 1) & 1)]);
+                    bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), src, HALF_BYTES,
+                                      mapa_shared(bar, static_cast<uint32_t>(d)));
+                }
+                __syncwarp();
+                if (warp == 12 && half == 0) PTRACE(11);
+            }
+        }
+    } else if (warp >= 8) {
+        // ---------------- tensor-core warps: K blocks m, m+4, ... of every half-step into accumulator (half, m) ----------
+        const int m = warp - 8;
+        const bool leader = elect_one();
+        for (int t = 0; t < T; ++t) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint64_t* hf = &h_full[half * 2 + (t & 1)];
+                if (t > 0) {
+                    mbar_wait(hf, ((t - 1) >> 1) & 1);                       // every peer's half block has landed
+                    if (m == 0 && lane == 0) mbar_expect_tx(hf, ctas * HALF_BYTES);   // re-arm for step t + 2
+                }
+                tc_fence_after();
+                if (m == 0) PTRACE(12 + 2 * half);
+                const uint32_t b0 = smem_u32(sH) + (t & 1) * himg_bytes;
+                const uint32_t dacc = tmem_base + half * 64 + m * NB;
+#pragma unroll 1
+                for (int kb = m; kb < kblocks; kb += 4) {
+                    const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
+                    const uint32_t ta = tmem_base + ACC_COLS + kb * 32;
+                    if (leader) {
+                        umma_bf16_ts(dacc, ta, bd, idesc, kb != m ? 1u : 0u);
+                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                    }
+                }
+                if (leader) umma_commit(&acc_full[half]);
+                __syncwarp();
+                if (m == 0) PTRACE(13 + 2 * half);
+            }
+        }
+    } else {
+        // ---------------- element warps ---------------------------------------------------------------------------------
+        // Thread (lq, ch, lane): TMEM lane = gate row lq*32 + lane = (unit lq*8 + lane/4, gate lane%4), accumulator columns
+        // ch*4 .. ch*4+3 of the half. After the non-linearity a 4x4 transpose inside each lane quad (two shuffle rounds)
+        // gives every lane the four gates of ONE batch column, so the cell update needs no shared-memory regrouping.
+        const int lq = warp & 3, ch = warp >> 2;
+        const int row = lq * 32 + lane;
+        const int q = lane & 3, u = lq * 8 + (lane >> 2);       // gate of the accumulator row; hidden unit inside this CTA
+        const bool b0 = (q & 1) != 0, b1 = (q & 2) != 0;
+        const int n = ch * 4 + q;                               // batch column (inside the half) this lane finishes
+        const float act_s = (q == 2) ? 2.0f : 1.0f;
+        const float act_h = (q == 2) ? 1.0f : 0.5f;
+        const size_t gx_col = static_cast<size_t>(dir) * 4 * H + j * 128 + row;
+        const size_t G8 = static_cast<size_t>(8) * H, H2 = static_cast<size_t>(2) * H;
+        const int parts = (kblocks < 4) ? kblocks : 4;   // accumulators that received MMAs (H = 128: two K blocks)
+        const int so_off = n * 32 + ((lq ^ ((n >> 1) & 3)) << 3) + (lane >> 2);   // bf16 slot of (row n, unit u) in a half block
+        float c_state[2] = {0.0f, 0.0f};
+        for (int t = 0; t < T; ++t) {
+            const int tt = dir ? (T - 1 - t) : t;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (warp == 0) PTRACE(6 * half + 0);
+                mbar_wait(&acc_full[half], t & 1);
+                tc_fence_after();
+                if (warp == 0) PTRACE(6 * half + 1);
+                uint32_t acc[4];
+                // accumulator column = image row: half B's batch columns are columns 8-15 of its accumulators
+                load_partial_sums<4>(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + half * 64 + half * HB + ch * 4, NB, parts,
+                                     acc);
+                tc_fence_before();
+                if (warp == 0) PTRACE(6 * half + 2);
+                mbar_wait(&gx_full[((t & 1) << 1) | half], (t >> 1) & 1);   // box of half-step k = 2t + half: stage k & 3, phase k >> 2
+                const float* gxs = sGx + ((((t & 1) << 1) | half) * HB + ch * 4) * 128 + row;
+                float a[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float pre = __uint_as_float(acc[c]) + gxs[c * 128];
+                    if (p.act_approx) a[c] = act_h * tanh_approx(act_h * pre) + (1.0f - act_h);
+                    else a[c] = act_s * fast_sigmoid(act_s * pre) - (act_s - 1.0f);   // sigmoid, or tanh for gate g
+                }
+                // quad transpose: round 1 swaps the odd/even column of each column pair with lane q^1, round 2 swaps
+                // column pairs with lane q^2; afterwards r0..r3 = gates q, q^1, q^2, q^3 of column n
+                const float k0 = b0 ? a[1] : a[0], s0 = b0 ? a[0] : a[1];
+                const float k1 = b0 ? a[3] : a[2], s1 = b0 ? a[2] : a[3];
+                const float x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                const float r0 = b1 ? k1 : k0, r1 = b1 ? x1 : x0;
+                const float y0 = b1 ? k0 : k1, y1 = b1 ? x0 : x1;
+                const float r2 = __shfl_xor_sync(0xffffffffu, y0, 2), r3 = __shfl_xor_sync(0xffffffffu, y1, 2);
+                const float e0 = b0 ? r1 : r0, e1 = b0 ? r0 : r1, e2 = b0 ? r3 : r2, e3 = b0 ? r2 : r3;
+                const float gi = b1 ? e2 : e0, gf = b1 ? e3 : e1, gg = b1 ? e0 : e2, go = b1 ? e1 : e3;
+                if (warp == 0) PTRACE(6 * half + 3);
+                const float cn = gf * c_state[half] + gi * gg;
+                c_state[half] = cn;
+                const float h = go * (p.act_approx ? tanh_approx(cn) : fast_tanh(cn));
+                // staging blocks are double-buffered per half (parity of t); see the copy warp for why reuse is safe
+                uint8_t* so = sOut + (half * 2 + (t & 1)) * HALF_BYTES;
+                reinterpret_cast<__nv_bfloat16*>(so)[so_off] = __float2bfloat16(h);
+                fence_proxy_async_smem();   // staging writes (generic proxy) -> bulk-copy engine (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&so_ready[half]);
+                if (warp == 0) PTRACE(6 * half + 4);
+                // off the critical path: layer output and what BPTT needs
+                const int gn = grp * NB + half * HB + n;
+                if (gn < N) {
+                    const size_t o = (static_cast<size_t>(tt) * N + gn) * H2 + static_cast<size_t>(dir) * H + j * 32 + u;
+                    p.hout[o] = h;
+                    if (p.c_save) p.c_save[o] = cn;
+                    if (p.gates_save) {
+                        __half2 lo = __floats2half2_rn(gi, gf), hi = __floats2half2_rn(gg, go);
+                        p.gates_save[o] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    }
+                }
+                if (warp == 0 && half == 0) PTRACE(5);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -1235,6 +1460,12 @@ bool two_tile_path(int H) {
     return H > 512 && H <= 640 && H % 128 == 0 && weights_in_tmem();
 }
 
+// CTCB200_LSTM_PIPE=0 selects the un-pipelined forward kernel (one element phase per step over all 16 columns)
+bool pipelined_fwd() {
+    const char* e = getenv("CTCB200_LSTM_PIPE");
+    return e == nullptr || e[0] != '0';
+}
+
 // warps that issue slices of the per-step MMA chain (each into its own TMEM accumulator, 64 columns in total)
 int mma_issuers(int NB, int H, bool a_tmem) {
     if (!a_tmem) return 1;
@@ -1285,10 +1516,10 @@ int pick_nb(int N, int H, int force_nb, bool bwd, bool cl) {
 
 // Can at least one cluster of this shape be resident? (fails on parts / partitions whose GPCs are too small)
 template <typename Kern>
-bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem);
+bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads);
 
 template <typename Kern>
-bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem) {
+bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads = LSTM_THREADS) {
     // the answer depends only on (kernel, cluster shape, shared memory): remember the last few probes
     struct Entry { const void* k; unsigned cx, cy; size_t smem; bool ok; };
     static Entry cache[16];
@@ -1297,13 +1528,13 @@ bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem) {
         if (cache[i].k == reinterpret_cast<const void*>(kern) && cache[i].cx == cluster.x && cache[i].cy == cluster.y &&
             cache[i].smem == smem)
             return cache[i].ok;
-    const bool ok = cluster_probe(kern, grid, cluster, smem);
+    const bool ok = cluster_probe(kern, grid, cluster, smem, threads);
     if (n_cache < 16) cache[n_cache++] = Entry{reinterpret_cast<const void*>(kern), cluster.x, cluster.y, smem, ok};
     return ok;
 }
 
 template <typename Kern>
-bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem) {
+bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
         (void)cudaGetLastError();
         return false;
@@ -1315,7 +1546,7 @@ bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(LSTM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
@@ -1343,13 +1574,13 @@ BwdKern bwd_kernel(int NB, int ex) {
 
 template <typename Kern, typename Params>
 int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool cooperative, const CUtensorMap& tm,
-                     const Params& p, cudaStream_t stream) {
+                     const Params& p, cudaStream_t stream, int threads = LSTM_THREADS) {
     CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     if (cluster.x * cluster.y * cluster.z > 8)
         CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(LSTM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attrs[2];
@@ -1453,13 +1684,33 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         }
     }
     struct TraceDump {
-        const FwdParams& p; cudaStream_t s;
+        const FwdParams& p; cudaStream_t s; bool pipe;
         ~TraceDump() {
             if (!p.trace) return;
             cudaStreamSynchronize(s);
             const int T = p.T;
             long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
             cudaMemcpy(h, p.trace, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost);
+            if (pipe) {
+                // stamps relative to the start of half A's element phase: A0..A5 = start, acc ready, loaded, gates regrouped,
+                // h staged + arrive, stores issued; B0..B4 likewise; [11] = copy warp issued half A; M: hA landed, A issued,
+                // hB landed, B issued
+                double rel[16] = {0}, tot = 0;
+                int cnt = 0;
+                for (int t = 8; t + 1 < T; ++t, ++cnt) {
+                    for (int k = 0; k < 16; ++k) rel[k] += double(h[t * 16 + k] - h[t * 16]);
+                    tot += double(h[(t + 1) * 16] - h[t * 16]);
+                }
+                fprintf(stderr, "lstm_fwd_pipe trace (cycles, avg over %d steps): step %.0f | A:", cnt, tot / cnt);
+                for (int k = 0; k < 6; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
+                fprintf(stderr, " | B:");
+                for (int k = 6; k < 12; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
+                fprintf(stderr, " | M(hA landed, A issued, hB landed, B issued):");
+                for (int k = 12; k < 16; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
+                fprintf(stderr, "\n");
+                free(h);
+                return;
+            }
             double acc[16] = {0};
             int cnt = 0;
             for (int t = 8; t + 1 < T; ++t, ++cnt) {
@@ -1473,7 +1724,17 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
                     acc[5] / cnt, acc[6] / cnt, acc[7] / cnt, acc[9] / cnt, acc[10] / cnt, acc[11] / cnt, acc[12] / cnt, acc[13] / cnt);
             free(h);
         }
-    } trace_dump{p, stream};
+    } trace_dump{p, stream, false};
+    if (cl && ex == 3 && a_tmem && NB == 16 && pipelined_fwd()) {
+        trace_dump.pipe = true;
+        // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core warps
+        dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
+        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 4 * 512 + 4 * 8 * 128 * 4 + 128 + 1024;
+        CUtensorMap tmGx;   // gate pre-activations as a 2-D f32 tensor [T*N rows, 8H columns], boxes of 8 rows x 128 columns
+        rc = make_tmap_f32_2d(&tmGx, gx, static_cast<uint64_t>(T) * N, static_cast<uint64_t>(8) * H, static_cast<uint64_t>(8) * H, 8, 128);
+        if (rc == OK && cluster_ok(lstm_fwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS))
+            return launch_clustered(lstm_fwd_pipe_kernel, grid, cluster, smem_p, false, tmGx, p, stream, PIPE_THREADS);
+    }
     if (cl) {
         // independent clusters: no co-residency requirement between them, one launch covers every batch group
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
