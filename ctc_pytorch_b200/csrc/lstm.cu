@@ -707,6 +707,7 @@ struct BwdParams {
     int a_tmem;
     int mma_split;
     unsigned int* resident;    // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
+    long long* trace;          // debug (pipelined kernel): per-step clock64 stamps of CTA (0,0,0), or null
 };
 
 // Tell the host-side scheduler that the whole grid of this launch is resident: from then on the SMs this kernel does
@@ -777,7 +778,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         if constexpr (BULK) {
             mbar_expect_tx(&b_full[0], ctas * BLK_BYTES);
             mbar_expect_tx(&b_full[1], ctas * BLK_BYTES);
-            mbar_expect_tx(r_full, 4 * NB * 32 * 4);  // four gate partials of [NB][32] floats per step
+            mbar_expect_tx(r_full, 4 * NB * 32 * 2);  // four gate partials of [NB][32] fp16 values per step
         }
     }
     uint32_t tmem_cols = 64;
@@ -914,19 +915,22 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             // one bulk copy per warp into that CTA's receive slot for source gate q (complete_tx on its r_full)
             if (warp_leader) bulk_wait_read_all();  // this warp's earlier copies have finished reading shared memory
             __syncthreads();                         // ... for every warp: sP and sOut may be rewritten
-            float* stage = sP + (lq * NB + ch * CPT) * 32 + lane;
+            // partials cross the cluster as fp16 (the DSMEM fabric, ~17 B/clk per SM both ways, bounds this kernel; the four
+            // partials are summed in fp32 on arrival, so the rounding stays far below that of the bf16 operands)
+            __half* stage = reinterpret_cast<__half*>(sP) + (lq * NB + ch * CPT) * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) stage[c * 32] = __uint_as_float(acc[c]);
+            for (int c = 0; c < CPT; ++c) stage[c * 32] = __float2half_rn(__uint_as_float(acc[c]));
             fence_proxy_async_smem();
             __syncwarp();
             if (warp_leader) {
                 const uint32_t peer = rank_of(lq, mb);
-                bulk_copy_to_peer(mapa_shared(smem_u32(sR + (q * NB + ch * CPT) * 32), peer),
-                                  smem_u32(sP + (lq * NB + ch * CPT) * 32), CPT * 32 * 4, mapa_shared(smem_u32(r_full), peer));
+                bulk_copy_to_peer(mapa_shared(smem_u32(reinterpret_cast<__half*>(sR) + (q * NB + ch * CPT) * 32), peer),
+                                  smem_u32(reinterpret_cast<__half*>(sP) + (lq * NB + ch * CPT) * 32), CPT * 32 * 2,
+                                  mapa_shared(smem_u32(r_full), peer));
                 bulk_commit();
             }
             mbar_wait(r_full, t & 1);
-            if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * 4);  // re-arm for the next step
+            if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * 2);  // re-arm for the next step
         } else {
 #pragma unroll
             for (int c = 0; c < CPT; ++c) st_cluster_f32(remote_base + c * 32 * 4, __uint_as_float(acc[c]));
@@ -945,7 +949,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             const int n = warp + 8 * e;
             float dh = dh_in[e];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) dh += sR[(s * NB + n) * 32 + lane];
+            for (int s = 0; s < 4; ++s) {
+                if constexpr (BULK) dh += __half2float(reinterpret_cast<const __half*>(sR)[(s * NB + n) * 32 + lane]);
+                else dh += sR[(s * NB + n) * 32 + lane];
+            }
             const __half2 lo = *reinterpret_cast<const __half2*>(&gts[e].x);
             const __half2 hi = *reinterpret_cast<const __half2*>(&gts[e].y);
             const float gi = __low2float(lo), gf = __high2float(lo), gg = __low2float(hi), go = __high2float(hi);
@@ -1034,6 +1041,250 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// BPTT, software-pipelined like lstm_fwd_pipe_kernel: the 16 batch columns of a group are two independent chains
+// (half A = columns 0-7, half B = 8-15). Per half-step a CTA (gate q, unit block mb) goes through
+//   M  : partial dh[128 units, 8] = W_q^T slice x dG_q image                       (tensor-core warps 8-11)
+//   E.1: accumulators -> staging, one 1 KB block per owner CTA (lq, mb)              (element warps 0-7)
+//   C  : four bulk copies (reduce-scatter of the gate partials)                     (copy warps 12-15)
+//   E.2: dh = dh_in + four landed partials, LSTM cell backward, four gate-gradient blocks of its 32 units -> staging
+//   C  : sixteen bulk copies: gate g's block -> operand image of every CTA (g, *)   (all-gather)
+// The element warps run A.1, B.1, A.2, B.2; while one half waits for a hand-off the other half is processed, so the
+// two DSMEM exchanges and the MMA chain of a half overlap the element work of the other half.
+// Buffer reuse needs no extra waits: a staging / receive block is rewritten only after a hand-off that transitively
+// required every earlier copy out of (or into) it to have landed (see the per-buffer notes below).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+lstm_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmUnused, BwdParams p) {
+    constexpr int NB = 16, HB = 8;
+    constexpr uint32_t BLK_BYTES = NB * 64, HALF_BYTES = HB * 64;
+    constexpr uint32_t PART_BYTES = HB * 32 * 4;     // one partial block: [8 columns][32 units] f32
+    constexpr uint32_t ACC_COLS = 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = p.H, T = p.T, N = p.N;
+    const int img_bytes = H * NB * 2;
+    uint8_t* sB = smem;                                                        // [2 parities] dG_q operand image
+    float* sR = reinterpret_cast<float*>(sB + 2 * img_bytes);                  // [half][4 source gates][8][32] landed partials
+    float* sP = sR + 2 * 4 * HB * 32;                                          // [half][4 owner CTAs][8][32] partials to send
+    uint8_t* sOut = reinterpret_cast<uint8_t*>(sP + 2 * 4 * HB * 32);          // [half][parity][4 gates][HALF_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * 2 * 4 * HALF_BYTES);
+    uint64_t* b_full = bars;          // [half][parity]: gate q's dG image half has landed
+    uint64_t* acc_full = bars + 4;    // [half]
+    uint64_t* p_ready = bars + 6;     // [half]: partials staged by all element warps
+    uint64_t* r_full = bars + 8;      // [half]: the four gate partials of this CTA's 32 units have landed
+    uint64_t* g_ready = bars + 10;    // [half]: gate-gradient blocks staged
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    (void)tmUnused;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    announce_resident(p.resident);
+    const int q = blockIdx.x, mb = blockIdx.y, MB = gridDim.y;
+    const int dir = blockIdx.z / p.groups, grp = blockIdx.z % p.groups;
+    const int ctas = 4 * MB;
+    const int kblocks = H / 64;
+    auto rank_of = [&](int qq, int mm) -> uint32_t { return static_cast<uint32_t>(qq + 4 * mm); };
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&b_full[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 4);
+            mbar_init(&p_ready[i], 8);
+            mbar_init(&r_full[i], 1);
+            mbar_init(&g_ready[i], 8);
+        }
+        fence_mbar_init();
+        for (int i = 0; i < 4; ++i) mbar_expect_tx(&b_full[i], ctas * HALF_BYTES);
+        for (int i = 0; i < 2; ++i) mbar_expect_tx(&r_full[i], 4 * PART_BYTES);
+    }
+    uint32_t tmem_cols = 256;
+    while (tmem_cols < ACC_COLS + H / 2) tmem_cols <<= 1;
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = tid; i < 2 * img_bytes / 16; i += PIPE_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();
+    if (warp < 4)
+        load_weights_to_tmem(p.w + (static_cast<size_t>(dir * 4 + q) * H + mb * 128) * H, H, tmem_base, ACC_COLS, warp, lane);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
+#define BTRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[t * 16 + (k)] = clock64(); } while (0)
+
+    if (warp >= 12) {
+        // ---------------- copy warps --------------------------------------------------------------------------------
+        const int w = warp - 12;
+        for (int t = 0; t < T; ++t) {
+            // reduce-scatter: warp w ships the partial block of owner CTA (w, mb) into slot q of its receive buffer.
+            // sP[half] is rewritten one step later, after this CTA's next dG image has landed, which needed every
+            // row-mate's element phase of this step, i.e. these copies had landed.
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&p_ready[half], t & 1);
+                if (w == 0 && half == 0) BTRACE(8);
+                if (lane == 0) {
+                    const uint32_t peer = rank_of(w, mb);
+                    bulk_copy_to_peer(mapa_shared(smem_u32(sR + ((half * 4 + q) * HB) * 32), peer),
+                                      smem_u32(sP + ((half * 4 + w) * HB) * 32), PART_BYTES, mapa_shared(smem_u32(&r_full[half]), peer));
+                }
+                __syncwarp();
+                if (w == 0 && half == 0) BTRACE(9);
+            }
+            // all-gather: copy i = (g, mdst): gate g's block of this CTA's 32 units -> K block (4 mb + q) of CTA (g, mdst).
+            // sOut is double-buffered on the parity of t: a block is rewritten two steps later, when every CTA has finished
+            // the step in between, which it could only start after this block had landed there.
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&g_ready[half], t & 1);
+                if (w == 0 && half == 0) BTRACE(10);
+                const int i = w * 4 + lane;
+                const int g = i & 3, mdst = i >> 2;
+                if (t + 1 < T && lane < 4 && mdst < MB) {
+                    const uint32_t peer = rank_of(g, mdst);
+                    const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_BYTES + half * HALF_BYTES;
+                    bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + (((half * 2 + (t & 1)) * 4) + g) * HALF_BYTES), HALF_BYTES,
+                                      mapa_shared(smem_u32(&b_full[half * 2 + ((t + 1) & 1)]), peer));
+                }
+                __syncwarp();
+                if (w == 0 && half == 0) BTRACE(11);
+            }
+        }
+    } else if (warp >= 8) {
+        // ---------------- tensor-core warps -------------------------------------------------------------------------
+        const int m = warp - 8;
+        const bool leader = elect_one();
+        for (int t = 0; t < T; ++t) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint64_t* bf = &b_full[half * 2 + (t & 1)];
+                if (t > 0) {
+                    mbar_wait(bf, ((t - 1) >> 1) & 1);
+                    if (m == 0 && lane == 0) mbar_expect_tx(bf, ctas * HALF_BYTES);   // re-arm for step t + 2
+                }
+                tc_fence_after();
+                if (m == 0) BTRACE(12 + 2 * half);
+                const uint32_t b0 = smem_u32(sB) + (t & 1) * img_bytes;
+                const uint32_t dacc = tmem_base + half * 64 + m * NB;
+#pragma unroll 1
+                for (int kb = m; kb < kblocks; kb += 4) {
+                    const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
+                    const uint32_t ta = tmem_base + ACC_COLS + kb * 32;
+                    if (leader) {
+                        umma_bf16_ts(dacc, ta, bd, idesc, kb != m ? 1u : 0u);
+                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                    }
+                }
+                if (leader) umma_commit(&acc_full[half]);
+                __syncwarp();
+                if (m == 0) BTRACE(13 + 2 * half);
+            }
+        }
+    } else {
+        // ---------------- element warps -----------------------------------------------------------------------------
+        const int lq = warp & 3, ch = warp >> 2;
+        const int unit = mb * 128 + q * 32 + lane;   // the unit this thread finishes in E.2 (batch column = warp)
+        const int n = warp;
+        const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
+        const size_t dg_col = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4;
+        const int parts = (kblocks < 4) ? kblocks : 4;
+        const int so_off = n * 32 + (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7);   // bf16 slot of (row n, unit lane)
+        float dc_carry[2] = {0.0f, 0.0f};
+        float dh_in[2], c_t[2], c_p[2];
+        uint2 gts[2];
+        // saved activations / incoming gradient of a whole step (both halves) are fetched together, one step ahead, so
+        // that no younger global load sits between a load and its use
+        auto fetch = [&](int t_) {
+            const int tt_ = dir ? t_ : (T - 1 - t_);
+            const int tprev = dir ? tt_ + 1 : tt_ - 1;
+            const bool has_prev = dir ? (tt_ + 1 < T) : (tt_ >= 1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int gn = grp * NB + half * HB + n;
+                const bool ok = gn < N && t_ < T;
+                const size_t o = (static_cast<size_t>(ok ? tt_ : 0) * N + (ok ? gn : 0)) * H2 + static_cast<size_t>(dir) * H + unit;
+                dh_in[half] = ok ? __ldg(p.dhout + o) : 0.0f;
+                c_t[half] = ok ? __ldg(p.c_save + o) : 0.0f;
+                gts[half] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
+                const size_t op = (static_cast<size_t>((ok && has_prev) ? tprev : 0) * N + (ok ? gn : 0)) * H2 +
+                                  static_cast<size_t>(dir) * H + unit;
+                c_p[half] = (ok && has_prev) ? __ldg(p.c_save + op) : 0.0f;
+            }
+        };
+        fetch(0);
+        for (int t = 0; t < T; ++t) {
+            const int tt = dir ? t : (T - 1 - t);
+            // E.1 (A then B): partial rows -> staging block of their owner CTA
+            if (warp == 0) BTRACE(0);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&acc_full[half], t & 1);
+                tc_fence_after();
+                if (warp == 0 && half == 0) BTRACE(1);
+                uint32_t acc[4];
+                load_partial_sums<4>(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + half * 64 + half * HB + ch * 4, NB, parts,
+                                     acc);
+                tc_fence_before();
+                float* stage = sP + ((half * 4 + lq) * HB + ch * 4) * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) stage[c * 32] = __uint_as_float(acc[c]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_ready[half]);
+                if (warp == 0) BTRACE(2 + half);
+            }
+            // E.2 (A then B): finish 32 units x 8 columns
+            uint2 dgp[2];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&r_full[half], t & 1);
+                if (warp == 0 && lane == 0) mbar_expect_tx(&r_full[half], 4 * PART_BYTES);   // re-arm for the next step
+                if (warp == 0) BTRACE(4 + 2 * half);
+                float dh = dh_in[half];
+#pragma unroll
+                for (int src = 0; src < 4; ++src) dh += sR[((half * 4 + src) * HB + n) * 32 + lane];
+                const __half2 lo = *reinterpret_cast<const __half2*>(&gts[half].x);
+                const __half2 hi = *reinterpret_cast<const __half2*>(&gts[half].y);
+                const float gi = __low2float(lo), gf = __high2float(lo), gg = __low2float(hi), go = __high2float(hi);
+                const float tc = fast_tanh(c_t[half]);
+                const float d_o = dh * tc * go * (1.0f - go);
+                const float dc = dc_carry[half] + dh * go * (1.0f - tc * tc);
+                const float d_i = dc * gg * gi * (1.0f - gi);
+                const float d_f = dc * c_p[half] * gf * (1.0f - gf);
+                const float d_g = dc * gi * (1.0f - gg * gg);
+                dc_carry[half] = dc * gf;
+                __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut + ((half * 2 + (t & 1)) * 4) * HALF_BYTES) + so_off;
+                so[0 * (HALF_BYTES / 2)] = __float2bfloat16(d_i);
+                so[1 * (HALF_BYTES / 2)] = __float2bfloat16(d_f);
+                so[2 * (HALF_BYTES / 2)] = __float2bfloat16(d_g);
+                so[3 * (HALF_BYTES / 2)] = __float2bfloat16(d_o);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&g_ready[half]);
+                if (warp == 0) BTRACE(5 + 2 * half);
+                __nv_bfloat162 b01 = __floats2bfloat162_rn(d_i, d_f), b23 = __floats2bfloat162_rn(d_g, d_o);
+                dgp[half] = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
+            }
+            // off the critical path: dG rows for the dX / dW GEMMs, then next step's saved activations
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int gn = grp * NB + half * HB + n;
+                if (gn < N) *reinterpret_cast<uint2*>(p.dg + (static_cast<size_t>(tt) * N + gn) * G8 + dg_col) = dgp[half];
+            }
+            fetch(t + 1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
 
 // ================================================================================================
 // Two-tile variants for H > 512 (cfg4: H = 640). H/32 CTAs would not fit one cluster (max 16), so every CTA owns
@@ -1466,6 +1717,13 @@ bool pipelined_fwd() {
     return e == nullptr || e[0] != '0';
 }
 
+// The pipelined BPTT kernel is correct (tools/gpu_check9.py) but not faster: with two exchanges per step the kernel sits at
+// ~80 % of the DSMEM fabric's bandwidth either way (profiles/lstm_trace_r1.txt). Opt in with CTCB200_LSTM_PIPE_BWD=1.
+bool pipelined_bwd() {
+    const char* e = getenv("CTCB200_LSTM_PIPE_BWD");
+    return e != nullptr && e[0] == '1';
+}
+
 // warps that issue slices of the per-step MMA chain (each into its own TMEM accumulator, 64 columns in total)
 int mma_issuers(int NB, int H, bool a_tmem) {
     if (!a_tmem) return 1;
@@ -1794,7 +2052,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         BwdParams p2;
         p2.dhout = dhout; p2.c_save = c_save; p2.gates_save = static_cast<const uint2*>(gates_save);
         p2.dg = static_cast<__nv_bfloat16*>(dg);
-        p2.dgimg = nullptr; p2.flags = nullptr; p2.resident = static_cast<unsigned int*>(resident_counter);
+        p2.dgimg = nullptr; p2.flags = nullptr; p2.resident = static_cast<unsigned int*>(resident_counter); p2.trace = nullptr;
         p2.w = static_cast<const __nv_bfloat16*>(whhT_packed); p2.a_tmem = 1; p2.mma_split = 4;
         p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
@@ -1821,10 +2079,43 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     BwdParams p;
     p.dhout = dhout; p.c_save = c_save; p.gates_save = static_cast<const uint2*>(gates_save);
     p.dg = static_cast<__nv_bfloat16*>(dg);
-    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter);
+    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter); p.trace = nullptr;
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed); p.a_tmem = a_tmem ? 1 : 0;
     p.mma_split = mma_issuers(NB, H, a_tmem);
     p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
+    if (cl && ex == 3 && a_tmem && NB == 16 && pipelined_bwd()) {
+        // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core and copy warps
+        dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
+        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 3 * 8192 + 128 + 1024;
+        if (cluster_ok(lstm_bwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS)) {
+            if (getenv("CTCB200_LSTM_TRACE") && T <= 4096) {   // development aid: per-phase cycle stamps on stderr
+                static long long* dbuf = nullptr;
+                if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
+                CTCB_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 16 * T, stream));
+                p.trace = dbuf;
+            }
+            rc = launch_clustered(lstm_bwd_pipe_kernel, grid, cluster, smem_p, false, tmWT, p, stream, PIPE_THREADS);
+            if (p.trace && rc == OK) {
+                cudaStreamSynchronize(stream);
+                long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
+                cudaMemcpy(h, p.trace, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost);
+                double rel[16] = {0}, tot = 0;
+                int cnt = 0;
+                for (int t = 8; t + 2 < T; ++t, ++cnt) {
+                    for (int k = 0; k < 16; ++k) rel[k] += double(h[t * 16 + k] - h[t * 16]);
+                    tot += double(h[(t + 1) * 16] - h[t * 16]);
+                }
+                fprintf(stderr, "lstm_bwd_pipe trace (cycles after the step start, avg over %d steps): step %.0f | E: A acc ready %.0f, A.1 staged "
+                        "%.0f, B.1 staged %.0f, A partials landed %.0f, A.2 staged %.0f, B partials landed %.0f, B.2 staged %.0f | C(A): "
+                        "p_ready %.0f, rs issued %.0f, g_ready %.0f, ag issued %.0f | M: A image landed %.0f, A issued %.0f, B landed %.0f, "
+                        "B issued %.0f\n", cnt, tot / cnt, rel[1] / cnt, rel[2] / cnt, rel[3] / cnt, rel[4] / cnt, rel[5] / cnt, rel[6] / cnt,
+                        rel[7] / cnt, rel[8] / cnt, rel[9] / cnt, rel[10] / cnt, rel[11] / cnt, rel[12] / cnt, rel[13] / cnt, rel[14] / cnt,
+                        rel[15] / cnt);
+                free(h);
+            }
+            return rc;
+        }
+    }
     if (cl) {
         dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
         if (ex == 2) {

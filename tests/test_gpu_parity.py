@@ -376,3 +376,44 @@ def test_overlapped_wgrad_matches_serial(H, L, N, drop):
     for k in grads[False]:
         assert torch.isfinite(grads[True][k]).all(), k
         assert relnorm(grads[True][k], grads[False][k]) < 1e-4, (k, relnorm(grads[True][k], grads[False][k]))
+
+
+@pytest.mark.parametrize("T,N,H", [(12, 4, 256), (9, 21, 512), (7, 16, 128)])
+def test_lstm_kernel_variants_agree(T, N, H):
+    """Selectable recurrent-kernel variants compute the same thing: pipelined vs plain forward (bit-identical) and the opt-in
+    pipelined BPTT kernel vs the default one (fp32 vs fp16 hand-off of the gate partials: 1e-2 of the largest element)."""
+    from ctc_pytorch_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(T + N + H)
+    R = T * N
+    whh = (0.05 * torch.randn(8 * H, H, device=DEV)).to(torch.bfloat16)
+    gx = torch.randn(R, 8 * H, device=DEV)
+    scratch = torch.empty(L.dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=DEV)
+    outs = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["CTCB200_LSTM_PIPE"] = mode
+            hout = torch.zeros(R, 2 * H, device=DEV)
+            c_save = torch.zeros(R, 2 * H, device=DEV)
+            gates = torch.zeros(R, 2 * H, 4, dtype=torch.float16, device=DEV)
+            L.call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh), _lib.ptr(hout), _lib.ptr(c_save), _lib.ptr(gates),
+                   _lib.ptr(scratch), T, N, H, 0, _lib.stream())
+            torch.cuda.synchronize()
+            outs[mode] = (hout, c_save, gates)
+        for a, b in zip(outs["0"], outs["1"]):
+            assert torch.equal(a, b)
+        hout, c_save, gates = outs["1"]
+        dh = torch.randn(R, 2 * H, device=DEV)
+        dgs = {}
+        for mode in ("0", "1"):
+            os.environ["CTCB200_LSTM_PIPE_BWD"] = mode
+            dg = torch.zeros(R, 8 * H, dtype=torch.bfloat16, device=DEV)
+            L.call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(whh), _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(dg),
+                   _lib.ptr(scratch), T, N, H, 0, None, _lib.stream())
+            torch.cuda.synchronize()
+            dgs[mode] = dg.float()
+        assert torch.isfinite(dgs["1"]).all()
+        assert (dgs["0"] - dgs["1"]).abs().max().item() < 1e-2 * dgs["0"].abs().max().item()
+    finally:
+        os.environ.pop("CTCB200_LSTM_PIPE", None)
+        os.environ.pop("CTCB200_LSTM_PIPE_BWD", None)
