@@ -296,10 +296,20 @@ def run_ours(args, cfg, rank, world):
     bwd_ms = kern_ms.get("ctcb200_lstm_bwd", 0.0) / max(1, kern_cnt.get("ctcb200_lstm_bwd", 1))
     dom_name, dom_ms = ("lstm_bwd_kernel", bwd_ms) if bwd_ms >= fwd_ms else ("lstm_fwd_kernel", fwd_ms)
     ach = rec_flops_launch / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    # What actually bounds the recurrent kernels is the SM-to-SM (DSMEM) fabric: per time step every CTA receives and sends
+    # the whole operand image of its cluster (fwd: H*16*2 B of h_t; BPTT: the same of dG plus the fp16 gate partials).
+    dsmem_out = H * 16 * 2 + (4 * 16 * 32 * 2 if dom_name == "lstm_bwd_kernel" else 0)
+    sm_hz = 1965e6
+    dsmem_bpc = 2.0 * dsmem_out / (dom_ms * 1e-3 / T * sm_hz) if dom_ms > 0 else 0.0
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
                 "avg_launch_ms": dom_ms, "us_per_timestep": dom_ms * 1e3 / T,
-                "note": "latency-bound recurrence: T dependent steps per launch; see DESIGN.md"}
+                "limiter": {"resource": "DSMEM fabric (cluster all-gather / reduce-scatter every time step)",
+                            "bytes_per_timestep_per_sm_in_plus_out": 2 * dsmem_out, "achieved_B_per_clk_per_sm": dsmem_bpc,
+                            "peak_B_per_clk_per_sm": 17.0, "frac": dsmem_bpc / 17.0,
+                            "peak_source": "B300_MICROARCH.md: 17 B/clk bidirectional per SM (measured on sm_103a), SM clock 1965 MHz"},
+                "note": "recurrence: T dependent steps per launch, each moving the cluster's operand image between all CTAs; "
+                        "tensor-pipe fraction reported for the contract, the DSMEM fraction is the binding one (DESIGN.md 3.2)"}
     # secondary rooflines: all dense GEMM launches together, and the CTC alpha/beta sweep
     rows = T * N
     gemm_flops = 0.0
