@@ -322,6 +322,75 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
         }
 }
 
+// float4 variant of the reduction (C % 4 == 0): 128 columns per block, 8 rows in flight per block, 4 rows unrolled
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, double* __restrict__ ws, int R, int C, int rows_per_block) {
+    __shared__ float4 s1[8][32], s2[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 4;
+    const int r_begin = blockIdx.y * rows_per_block;
+    const int r_end = min(R, r_begin + rows_per_block);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c < C) {
+        const float4 m = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+        int r = r_begin + ty;
+        for (; r + 24 < r_end; r += 32) {
+            float4 g[4], v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long o = static_cast<long long>(r + 8 * k) * C + c;
+                g[k] = __ldcs(reinterpret_cast<const float4*>(dy + o));
+                v[k] = __ldcs(reinterpret_cast<const float4*>(x + o));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a.x += g[k].x; a.y += g[k].y; a.z += g[k].z; a.w += g[k].w;
+                b.x += g[k].x * (v[k].x - m.x) * rs.x; b.y += g[k].y * (v[k].y - m.y) * rs.y;
+                b.z += g[k].z * (v[k].z - m.z) * rs.z; b.w += g[k].w * (v[k].w - m.w) * rs.w;
+            }
+        }
+        for (; r < r_end; r += 8) {
+            const long long o = static_cast<long long>(r) * C + c;
+            const float4 g = *reinterpret_cast<const float4*>(dy + o), v = *reinterpret_cast<const float4*>(x + o);
+            a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+            b.x += g.x * (v.x - m.x) * rs.x; b.y += g.y * (v.y - m.y) * rs.y;
+            b.z += g.z * (v.z - m.z) * rs.z; b.w += g.w * (v.w - m.w) * rs.w;
+        }
+    }
+    s1[ty][tx] = a;
+    s2[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; ++k) {
+            da[0] += s1[k][tx].x; da[1] += s1[k][tx].y; da[2] += s1[k][tx].z; da[3] += s1[k][tx].w;
+            db[0] += s2[k][tx].x; db[1] += s2[k][tx].y; db[2] += s2[k][tx].z; db[3] += s2[k][tx].w;
+        }
+        for (int k = 0; k < 4; ++k) {
+            atomicAdd(&ws[c + k], da[k]);
+            atomicAdd(&ws[C + c + k], db[k]);
+        }
+    }
+}
+
+// Per-column coefficients of the input gradient, dx = A*dy + B*x + D, for consumers that apply BatchNorm's backward on the
+// fly (the BPTT kernel of the layer below): A = g rstd, B = -g rstd^2 S2/R, D = g rstd (mean rstd S2 - S1)/R with
+// S1 = sum dy, S2 = sum dy*xhat. Also emits dgamma = S2, dbeta = S1.
+__global__ void bn_bwd_coef_kernel(const double* __restrict__ ws, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, int R, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double s1 = ws[c], s2 = ws[C + c];
+    const double g = gamma ? static_cast<double>(gamma[c]) : 1.0, rs = rstd[c], m = mean[c];
+    coef[c] = static_cast<float>(g * rs);
+    coef[C + c] = static_cast<float>(-g * rs * rs * s2 / R);
+    coef[2 * C + c] = static_cast<float>(g * rs * (m * rs * s2 - s1) / R);
+    if (dbeta) dbeta[c] = static_cast<float>(s1);
+    if (dgamma) dgamma[c] = static_cast<float>(s2);
+}
+
 // ---- log-softmax ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 log_softmax_fwd_kernel(const float* __restrict__ x, long long x_pitch, float* __restrict__ y, int R, int C) {
@@ -478,6 +547,33 @@ extern "C" CTCB200_API int ctcb200_bn_bwd(const float* dy, const float* x, const
     CTCB_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<stream_grid(static_cast<long long>(R) * C, 1024), 256, 0, stream>>>(
         dy, x, mean, rstd, gamma, static_cast<const double*>(ws), dx, dgamma, dbeta, R, C);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_bn_bwd_coef(const float* dy, const float* x, const float* mean, const float* rstd,
+                                               const float* gamma, float* coef, float* dgamma, float* dbeta, int R, int C,
+                                               void* ws, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(R > 0 && C > 0, "bn_bwd_coef: empty R=%d C=%d", R, C);
+    CTCB_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(2) * C * sizeof(double), stream));
+    const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+                                       reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(rstd)) & 15) == 0;
+    const int cols_per_block = vec ? 128 : 32;
+    const int col_blocks = (C + cols_per_block - 1) / cols_per_block;
+    int row_blocks = (device_sm_count() * 4 + col_blocks - 1) / col_blocks;
+    int rows_per_block = (R + row_blocks - 1) / row_blocks;
+    if (rows_per_block < 64) rows_per_block = 64;
+    row_blocks = (R + rows_per_block - 1) / rows_per_block;
+    if (vec)
+        bn_bwd_reduce4_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(dy, x, mean, rstd, static_cast<double*>(ws), R, C,
+                                                                              rows_per_block);
+    else
+        bn_bwd_reduce_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(dy, x, mean, rstd, static_cast<double*>(ws), R, C,
+                                                                             rows_per_block);
+    CTCB_LAUNCH_CHECK();
+    bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, stream>>>(static_cast<const double*>(ws), mean, rstd, gamma, coef, dgamma, dbeta,
+                                                          R, C);
     CTCB_LAUNCH_CHECK();
     return OK;
 }

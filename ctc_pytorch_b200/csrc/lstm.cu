@@ -708,7 +708,21 @@ struct BwdParams {
     int mma_split;
     unsigned int* resident;    // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
     long long* trace;          // debug (pipelined kernel): per-step clock64 stamps of CTA (0,0,0), or null
+    const float* bn_x;         // optional: layer output [T*N, 2H]; the BatchNorm backward of the layer above is applied to
+    const float* bn_coef;      // dhout on the fly: dh = coef[0][c]*dhout + coef[1][c]*bn_x + coef[2][c], coef f32 [3][2H]
 };
+
+// BatchNorm-backward coefficients of column c (identity when the fusion is off)
+struct BnCoef { float a, b, d; };
+__device__ __forceinline__ BnCoef load_bn_coef(const BwdParams& p, int c) {
+    BnCoef k{1.0f, 0.0f, 0.0f};
+    if (p.bn_x != nullptr) {
+        k.a = __ldg(p.bn_coef + c);
+        k.b = __ldg(p.bn_coef + 2 * p.H + c);
+        k.d = __ldg(p.bn_coef + 4 * p.H + c);
+    }
+    return k;
+}
 
 // Tell the host-side scheduler that the whole grid of this launch is resident: from then on the SMs this kernel does
 // not use can be handed to off-critical-path work (the weight-gradient GEMMs of the layer above) without delaying the
@@ -810,6 +824,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     const int lq = warp & 3, ch = warp >> 2;
     const bool warp_leader = elect_one();
     const int unit = mb * 128 + q * 32 + lane;  // the unit this thread finishes in the element phase
+    const BnCoef bnk = load_bn_coef(p, dir * H + unit);
     const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
     const size_t dg_col = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4;
     __nv_bfloat16* imgs = PUSH ? nullptr : p.dgimg + (static_cast<size_t>(dir) * p.groups + grp) * 4 * 2 * H * NB;
@@ -828,7 +843,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         const int tprev = dir ? tt + 1 : tt - 1;       // time index that held c_{prev} in the forward scan
         const bool has_prev = dir ? (tt + 1 < T) : (tt >= 1);
         // (1) saved activations and the incoming gradient for this thread's elements
-        float dh_in[EPT], c_t[EPT], c_p[EPT];
+        float dh_in[EPT], bx_in[EPT], c_t[EPT], c_p[EPT];
         uint2 gts[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
@@ -836,6 +851,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             const bool ok = gn < N;
             const size_t o = (static_cast<size_t>(tt) * N + (ok ? gn : 0)) * H2 + static_cast<size_t>(dir) * H + unit;
             dh_in[e] = ok ? __ldg(p.dhout + o) : 0.0f;
+            bx_in[e] = (p.bn_x != nullptr && ok) ? __ldg(p.bn_x + o) : 0.0f;   // combined with dh_in where it is consumed
             c_t[e] = ok ? __ldg(p.c_save + o) : 0.0f;
             gts[e] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
             const size_t op = (static_cast<size_t>(has_prev ? tprev : tt) * N + (ok ? gn : 0)) * H2 +
@@ -947,7 +963,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int n = warp + 8 * e;
-            float dh = dh_in[e];
+            float dh = bnk.a * dh_in[e] + bnk.b * bx_in[e] + ((p.n0 + grp * NB + n < N) ? bnk.d : 0.0f);   // BatchNorm backward on the fly
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 if constexpr (BULK) dh += __half2float(reinterpret_cast<const __half*>(sR)[(s * NB + n) * 32 + lane]);
@@ -1190,13 +1206,14 @@ lstm_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmUnused, BwdParams p) 
         // ---------------- element warps -----------------------------------------------------------------------------
         const int lq = warp & 3, ch = warp >> 2;
         const int unit = mb * 128 + q * 32 + lane;   // the unit this thread finishes in E.2 (batch column = warp)
+        const BnCoef bnk = load_bn_coef(p, dir * H + unit);
         const int n = warp;
         const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
         const size_t dg_col = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4;
         const int parts = (kblocks < 4) ? kblocks : 4;
         const int so_off = n * 32 + (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7);   // bf16 slot of (row n, unit lane)
         float dc_carry[2] = {0.0f, 0.0f};
-        float dh_in[2], c_t[2], c_p[2];
+        float dh_in[2], bx_in[2], c_t[2], c_p[2];
         uint2 gts[2];
         // saved activations / incoming gradient of a whole step (both halves) are fetched together, one step ahead, so
         // that no younger global load sits between a load and its use
@@ -1210,6 +1227,7 @@ lstm_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmUnused, BwdParams p) 
                 const bool ok = gn < N && t_ < T;
                 const size_t o = (static_cast<size_t>(ok ? tt_ : 0) * N + (ok ? gn : 0)) * H2 + static_cast<size_t>(dir) * H + unit;
                 dh_in[half] = ok ? __ldg(p.dhout + o) : 0.0f;
+                bx_in[half] = (p.bn_x != nullptr && ok) ? __ldg(p.bn_x + o) : 0.0f;
                 c_t[half] = ok ? __ldg(p.c_save + o) : 0.0f;
                 gts[half] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
                 const size_t op = (static_cast<size_t>((ok && has_prev) ? tprev : 0) * N + (ok ? gn : 0)) * H2 +
@@ -1246,7 +1264,7 @@ lstm_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmUnused, BwdParams p) 
                 mbar_wait(&r_full[half], t & 1);
                 if (warp == 0 && lane == 0) mbar_expect_tx(&r_full[half], 4 * PART_BYTES);   // re-arm for the next step
                 if (warp == 0) BTRACE(4 + 2 * half);
-                float dh = dh_in[half];
+                float dh = bnk.a * dh_in[half] + bnk.b * bx_in[half] + ((grp * NB + half * HB + n < N) ? bnk.d : 0.0f);
 #pragma unroll
                 for (int src = 0; src < 4; ++src) dh += sR[((half * 4 + src) * HB + n) * 32 + lane];
                 const __half2 lo = *reinterpret_cast<const __half2*>(&gts[half].x);
@@ -1552,6 +1570,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     const bool warp_leader = elect_one();
     const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
     const int unit0 = mb * 128 + qp * 64 + lane;  // + 32 * half
+    const BnCoef bnk2[2] = {load_bn_coef(p, dir * H + unit0), load_bn_coef(p, dir * H + unit0 + 32)};
     constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
 
     float dc_carry[2][EPT];
@@ -1564,7 +1583,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         const int tt = dir ? t : (T - 1 - t);
         const int tprev = dir ? tt + 1 : tt - 1;
         const bool has_prev = dir ? (tt + 1 < T) : (tt >= 1);
-        float dh_in[2][EPT], c_t[2][EPT], c_p[2][EPT];
+        float dh_in[2][EPT], bx_in[2][EPT], c_t[2][EPT], c_p[2][EPT];
         uint2 gts[2][EPT];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf)
@@ -1575,6 +1594,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
                 const int unit = unit0 + 32 * hf;
                 const size_t o = (static_cast<size_t>(tt) * N + (ok ? gn : 0)) * H2 + static_cast<size_t>(dir) * H + unit;
                 dh_in[hf][e] = ok ? __ldg(p.dhout + o) : 0.0f;
+                bx_in[hf][e] = (p.bn_x != nullptr && ok) ? __ldg(p.bn_x + o) : 0.0f;
                 c_t[hf][e] = ok ? __ldg(p.c_save + o) : 0.0f;
                 gts[hf][e] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
                 const size_t op = (static_cast<size_t>(has_prev ? tprev : tt) * N + (ok ? gn : 0)) * H2 +
@@ -1647,7 +1667,8 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
                 const int n = warp + 8 * e;
-                float dh = dh_in[hf][e] + sR[((0 * 2 + hf) * NB + n) * 32 + lane] + sR[((1 * 2 + hf) * NB + n) * 32 + lane];
+                float dh = bnk2[hf].a * dh_in[hf][e] + bnk2[hf].b * bx_in[hf][e] + ((p.n0 + grp * NB + n < N) ? bnk2[hf].d : 0.0f) +
+                           sR[((0 * 2 + hf) * NB + n) * 32 + lane] + sR[((1 * 2 + hf) * NB + n) * 32 + lane];
                 const __half2 lo = *reinterpret_cast<const __half2*>(&gts[hf][e].x);
                 const __half2 hi = *reinterpret_cast<const __half2*>(&gts[hf][e].y);
                 const float gi = __low2float(lo), gf = __high2float(lo), gg = __low2float(hi), go = __high2float(hi);
@@ -2035,10 +2056,12 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
 
 extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
                                             const void* gates_save, void* dg, void* scratch, int T, int N, int H,
-                                            int batch_tile, void* resident_counter, ctcb200_stream_t stream_) {
+                                            int batch_tile, const float* bn_x, const float* bn_coef, void* resident_counter,
+                                            ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE((reinterpret_cast<uintptr_t>(resident_counter) & 3) == 0, "lstm_bwd: resident_counter must be 4-byte aligned");
+    CTCB_REQUIRE((bn_x == nullptr) == (bn_coef == nullptr), "lstm_bwd: bn_x and bn_coef must be given together");
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_bwd: hidden size %d must be a multiple of 128 in [128,640]", H);
     if (two_tile_path(H)) {
         constexpr int NB2 = 16;
@@ -2052,7 +2075,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         BwdParams p2;
         p2.dhout = dhout; p2.c_save = c_save; p2.gates_save = static_cast<const uint2*>(gates_save);
         p2.dg = static_cast<__nv_bfloat16*>(dg);
-        p2.dgimg = nullptr; p2.flags = nullptr; p2.resident = static_cast<unsigned int*>(resident_counter); p2.trace = nullptr;
+        p2.dgimg = nullptr; p2.flags = nullptr; p2.resident = static_cast<unsigned int*>(resident_counter); p2.trace = nullptr; p2.bn_x = bn_x; p2.bn_coef = bn_coef;
         p2.w = static_cast<const __nv_bfloat16*>(whhT_packed); p2.a_tmem = 1; p2.mma_split = 4;
         p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
@@ -2079,7 +2102,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     BwdParams p;
     p.dhout = dhout; p.c_save = c_save; p.gates_save = static_cast<const uint2*>(gates_save);
     p.dg = static_cast<__nv_bfloat16*>(dg);
-    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter); p.trace = nullptr;
+    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter); p.trace = nullptr; p.bn_x = bn_x; p.bn_coef = bn_coef;
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed); p.a_tmem = a_tmem ? 1 : 0;
     p.mma_split = mma_issuers(NB, H, a_tmem);
     p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;

@@ -283,12 +283,27 @@ class _RnnStackFn(torch.autograd.Function):
         grads[fc_lin.weight] = ops.gemm_tn(dLT, ws.XfcT, k=Rp)              # [C, 2H]
         dh = ops.gemm_tn(dLb, ws.WfcT_b, k=C)                              # [R, 2H]
         dws = torch.empty(2 * F2, dtype=torch.float64, device=dev)
+        fuse_env = os.environ.get("CTCB200_BN_FUSE", "1") != "0"
+
+        def _bn_backward(bn_mod, st, dy, x_in, C_, below):
+            """BatchNorm1d backward of `bn_mod` for gradient dy [R, C_] w.r.t. its output; x_in is its input (the output of the
+            layer below). Returns (bn_x, bn_coef) when the input gradient is left to the BPTT kernel of that layer (no dropout
+            mask in between), else applies it in place and returns None."""
+            dgam = torch.empty(C_, dtype=torch.float32, device=dev)
+            dbet = torch.empty(C_, dtype=torch.float32, device=dev)
+            grads[bn_mod.weight], grads[bn_mod.bias] = dgam, dbet
+            if fuse_env and ws.L[below].mask is None:
+                coef = torch.empty(3 * C_, dtype=torch.float32, device=dev)
+                _call("ctcb200_bn_bwd_coef", _lib.ptr(dy), _lib.ptr(x_in), _lib.ptr(st.mean), _lib.ptr(st.rstd),
+                      _lib.ptr(bn_mod.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), stream())
+                return (x_in, coef)
+            _call("ctcb200_bn_bwd", _lib.ptr(dy), _lib.ptr(x_in), _lib.ptr(st.mean), _lib.ptr(st.rstd),
+                  _lib.ptr(bn_mod.weight), _lib.ptr(dy), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), stream())
+            return None
+
+        bn_fuse = None
         if fc_bn is not None:
-            dgam = torch.empty(F2, dtype=torch.float32, device=dev)
-            dbet = torch.empty(F2, dtype=torch.float32, device=dev)
-            _call("ctcb200_bn_bwd", _lib.ptr(dh), _lib.ptr(ws.h_last), _lib.ptr(ws.fc_bn.mean), _lib.ptr(ws.fc_bn.rstd),
-                  _lib.ptr(fc_bn.weight), _lib.ptr(dh), _lib.ptr(dgam), _lib.ptr(dbet), R, F2, _lib.ptr(dws), stream())
-            grads[fc_bn.weight], grads[fc_bn.bias] = dgam, dbet
+            bn_fuse = _bn_backward(fc_bn, ws.fc_bn, dh, ws.h_last, F2, len(layers) - 1)
 
         def _wgrad(item, mc):
             """dW_ih, dW_hh (both directions) of one layer from its gate gradients; runs on the current stream."""
@@ -332,8 +347,12 @@ class _RnnStackFn(torch.autograd.Function):
                       dh.numel(), stream())
             dg = torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev)
             _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p), _lib.ptr(rec.c_save), _lib.ptr(rec.gates),
-                  _lib.ptr(dg), _lib.ptr(scratch), T, N, H, model.batch_tile, _lib.ptr(res[0]) if overlap else None,
-                  stream())
+                  _lib.ptr(dg), _lib.ptr(scratch), T, N, H, model.batch_tile,
+                  _lib.ptr(bn_fuse[0]) if bn_fuse else None, _lib.ptr(bn_fuse[1]) if bn_fuse else None,
+                  _lib.ptr(res[0]) if overlap else None, stream())
+            if bn_fuse:
+                keep.append(bn_fuse)
+                bn_fuse = None
             # Weight gradients are not needed by the rest of the backward pass. Overlapped mode: those of the layer
             # above (its dG is complete) go to the side stream, gated on *this* layer's BPTT grid being resident, and
             # are confined to the SMs that latency-bound kernel leaves idle. The gate is only ever enqueued after the
@@ -355,11 +374,7 @@ class _RnnStackFn(torch.autograd.Function):
                 dh = ops.gemm_tn(dg, rec.wihT_p, k=8 * H)                  # [R, I]
                 bn = layer.batch_norm
                 if bn is not None:
-                    dgam = torch.empty(I, dtype=torch.float32, device=dev)
-                    dbet = torch.empty(I, dtype=torch.float32, device=dev)
-                    _call("ctcb200_bn_bwd", _lib.ptr(dh), _lib.ptr(rec.h_in), _lib.ptr(rec.bn.mean), _lib.ptr(rec.bn.rstd),
-                          _lib.ptr(bn.weight), _lib.ptr(dh), _lib.ptr(dgam), _lib.ptr(dbet), R, I, _lib.ptr(dws), stream())
-                    grads[bn.weight], grads[bn.bias] = dgam, dbet
+                    bn_fuse = _bn_backward(bn, rec.bn, dh, rec.h_in, I, li - 1)
         if overlap:
             if pending is not None:
                 _wgrad(pending, 0)  # the first layer's weight gradients: nothing left to hide them under

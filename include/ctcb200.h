@@ -87,7 +87,10 @@ CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, 
  * lstm_fwd: gx f32 [T*N, 8H] (= X * wih_p^T), writes hout f32 [T*N, 2H] (fwd | reverse halves), and when
  * c_save / gates_save are non-NULL the cell states f32 [T*N, 2H] and activated gates (4 x fp16 = 8 bytes per
  * element, [T*N, 2H]) that lstm_bwd consumes. scratch: ctcb200_lstm_scratch_bytes(N, H) bytes.
- * lstm_bwd: dhout f32 [T*N, 2H] -> dg bf16 [T*N, 8H] (gate gradients, wih_p column order).
+ * lstm_bwd: dhout f32 [T*N, 2H] -> dg bf16 [T*N, 8H] (gate gradients, wih_p column order). When bn_x / bn_coef are
+ * non-NULL the layer output feeds a training-mode BatchNorm1d (model_ctc.py:29-32) whose backward is applied on the fly:
+ * dhout is then the gradient w.r.t. the normalised tensor, bn_x f32 [T*N, 2H] the layer output itself and
+ * bn_coef f32 [3][2H] comes from ctcb200_bn_bwd_coef.
  * batch_tile: 0 = auto, or 16 / 32 batch columns per CTA group. H must be a multiple of 128, <= 640. */
 CTCB200_API int64_t ctcb200_lstm_scratch_bytes(int N, int H);
 CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const float* whh_f, const float* wih_r,
@@ -98,7 +101,8 @@ CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, float*
                                  ctcb200_stream_t stream);
 CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
                                  const void* gates_save, void* dg, void* scratch, int T, int N, int H,
-                                 int batch_tile, void* resident_counter, ctcb200_stream_t stream);
+                                 int batch_tile, const float* bn_x, const float* bn_coef, void* resident_counter,
+                                 ctcb200_stream_t stream);
 /* Scheduling aid for overlapping off-critical-path work (weight-gradient GEMMs) with the latency-bound BPTT kernel:
  * resident_counter (NULL = off) points at two zero-initialised uint32 words owned by the caller; word 0 is incremented
  * once per lstm_bwd launch as soon as every CTA of that launch is running. ctcb200_stream_wait_geq makes `stream`
@@ -135,6 +139,11 @@ CTCB200_API int ctcb200_bn_eval_affine(const float* gamma, const float* beta, co
 CTCB200_API int ctcb200_bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C, void* ws,
                                ctcb200_stream_t stream);
+/* Same reduction, but instead of writing dx it emits coef f32 [3][C] with dx = coef[0][c]*dy + coef[1][c]*x + coef[2][c];
+ * ctcb200_lstm_bwd applies it while it reads its incoming gradient (bn_x / bn_coef), which saves one pass over [R, C]. */
+CTCB200_API int ctcb200_bn_bwd_coef(const float* dy, const float* x, const float* mean, const float* rstd,
+                                    const float* gamma, float* coef, float* dgamma, float* dbeta, int R, int C, void* ws,
+                                    ctcb200_stream_t stream);
 CTCB200_API int ctcb200_log_softmax_fwd(const float* x, int64_t x_pitch, float* y, int R, int C,
                                         ctcb200_stream_t stream);
 CTCB200_API int ctcb200_log_softmax_bwd(const float* g, const float* y, float* dx, int R, int C,
