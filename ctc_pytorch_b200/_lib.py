@@ -20,6 +20,7 @@ _CT = {
     "float": ctypes.c_float,
     "double": ctypes.c_double,
     "uint32_t": ctypes.c_uint32,
+    "int32_t": ctypes.c_int32,
     "ctcb200_stream_t": ctypes.c_void_p,
 }
 

@@ -235,6 +235,49 @@ bn_stats_kernel(const float* __restrict__ x, double* __restrict__ ws, int R, int
     }
 }
 
+// float4 variant (C % 4 == 0): 128 columns per block, 8 rows in flight per block, 4 rows unrolled per thread
+__global__ void __launch_bounds__(256)
+bn_stats4_kernel(const float* __restrict__ x, double* __restrict__ ws, int R, int C, int rows_per_block) {
+    __shared__ float4 s1[8][32], s2[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 4;
+    const int r_begin = blockIdx.y * rows_per_block;
+    const int r_end = min(R, r_begin + rows_per_block);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c < C) {
+        int r = r_begin + ty;
+        for (; r + 24 < r_end; r += 32) {
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(x + static_cast<long long>(r + 8 * k) * C + c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+                b.x += v[k].x * v[k].x; b.y += v[k].y * v[k].y; b.z += v[k].z * v[k].z; b.w += v[k].w * v[k].w;
+            }
+        }
+        for (; r < r_end; r += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * C + c);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            b.x += v.x * v.x; b.y += v.y * v.y; b.z += v.z * v.z; b.w += v.w * v.w;
+        }
+    }
+    s1[ty][tx] = a;
+    s2[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; ++k) {
+            da[0] += s1[k][tx].x; da[1] += s1[k][tx].y; da[2] += s1[k][tx].z; da[3] += s1[k][tx].w;
+            db[0] += s2[k][tx].x; db[1] += s2[k][tx].y; db[2] += s2[k][tx].z; db[3] += s2[k][tx].w;
+        }
+        for (int k = 0; k < 4; ++k) {
+            atomicAdd(&ws[c + k], da[k]);
+            atomicAdd(&ws[C + c + k], db[k]);
+        }
+    }
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
@@ -463,6 +506,32 @@ extern "C" CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const f
     return OK;
 }
 
+namespace ctcb200 {
+namespace {
+// dst only (no transposed copy): pure streaming cast, float4 in / 4 x bf16 out, optional per-column affine (BatchNorm apply)
+__global__ void __launch_bounds__(256)
+cast_rows4_kernel(const float* __restrict__ src, long long s_outer, long long s_inner, int n_inner,
+                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dst,
+                  long long dst_pitch, int R, int C) {
+    const int c4 = C >> 2;
+    const long long total = static_cast<long long>(R) * c4;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(e / c4), c = static_cast<int>(e - static_cast<long long>(r) * c4) * 4;
+        float4 v = __ldcs(reinterpret_cast<const float4*>(src + static_cast<long long>(r / n_inner) * s_outer +
+                                                           static_cast<long long>(r % n_inner) * s_inner + c));
+        if (scale) {
+            const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+            v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        *reinterpret_cast<uint2*>(dst + static_cast<long long>(r) * dst_pitch + c) = o;
+    }
+}
+}  // namespace
+}  // namespace ctcb200
+
 extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_outer, int64_t s_inner, int n_inner,
                                                   const float* scale, const float* shift, void* dst, int64_t dst_pitch,
                                                   void* dstT, int64_t dstT_pitch, int n_pad, int R, int C,
@@ -473,7 +542,13 @@ extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_ou
     CTCB_REQUIRE(n_pad >= n_inner, "cast_transpose: n_pad %d < n_inner %d", n_pad, n_inner);
     const bool vec = (C % 2 == 0) && (s_outer % 2 == 0) && (s_inner % 2 == 0) && (dst_pitch % 2 == 0) &&
                      (dstT_pitch % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
-    if (vec) {
+    const bool rows4 = dst && !dstT && (C % 4 == 0) && (s_outer % 4 == 0) && (s_inner % 4 == 0) && (dst_pitch % 4 == 0) &&
+                       dst_pitch == C && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) &&
+                       (!scale || ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0);
+    if (rows4) {
+        ctcb200::cast_rows4_kernel<<<stream_grid(static_cast<long long>(R) * (C / 4), 2048), 256, 0, stream>>>(
+            src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch, R, C);
+    } else if (vec) {
         const long long tiles = static_cast<long long>((R + 63) / 64) * ((C + 63) / 64);
         cast_transpose_v2_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(
             src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch,
@@ -509,12 +584,15 @@ extern "C" CTCB200_API int ctcb200_bn_train_stats(const float* x, int R, int C, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(R > 0 && C > 0, "bn_train_stats: empty R=%d C=%d", R, C);
     CTCB_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(2) * C * sizeof(double), stream));
-    const int col_blocks = (C + 31) / 32;
+    const bool vec = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const int cols_per_block = vec ? 128 : 32;
+    const int col_blocks = (C + cols_per_block - 1) / cols_per_block;
     int row_blocks = (device_sm_count() * 4 + col_blocks - 1) / col_blocks;
     int rows_per_block = (R + row_blocks - 1) / row_blocks;
     if (rows_per_block < 64) rows_per_block = 64;
     row_blocks = (R + rows_per_block - 1) / rows_per_block;
-    bn_stats_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(x, static_cast<double*>(ws), R, C, rows_per_block);
+    if (vec) bn_stats4_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(x, static_cast<double*>(ws), R, C, rows_per_block);
+    else bn_stats_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(x, static_cast<double*>(ws), R, C, rows_per_block);
     CTCB_LAUNCH_CHECK();
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(static_cast<const double*>(ws), gamma, beta, running_mean,
                                                           running_var, momentum, eps, mean, rstd, scale, shift, R, C);

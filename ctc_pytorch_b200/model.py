@@ -502,6 +502,15 @@ class CTC_Model(nn.Module):
             batch_tokens += len(label)
         return batch_errs, batch_tokens
 
+    def compute_wer_device(self, log_probs, input_sizes, targets, target_sizes):
+        """Same two numbers as compute_wer(torch.max(out, -1)[1].transpose(0, 1), ...) (train_ctc.py:51-52), computed on the
+        device from the log-probabilities: arg-max + collapse + batched Levenshtein, one small D2H read at the end."""
+        _, labels, lens = ops.greedy_decode(log_probs, input_sizes, blank=0)
+        tsz = torch.as_tensor(target_sizes).to(device=log_probs.device, dtype=torch.int64)
+        dist = ops.edit_distance(labels, lens, torch.as_tensor(targets).to(log_probs.device), tsz)
+        both = torch.stack([dist.sum().to(torch.int64), tsz.sum()]).cpu()
+        return int(both[0]), int(both[1])
+
     def add_weights_noise(self):
         # the reference's version rebinds a local and therefore changes nothing (model_ctc.py:204-207)
         return None

@@ -55,6 +55,27 @@ def greedy_decode(log_probs, lengths, blank=0):
     return idx, labels, out_len
 
 
+def edit_distance(hyp, hyp_len, ref, ref_len):
+    """Levenshtein distance per row between int32 hypotheses hyp [N, *] (lengths hyp_len) and int64 references ref [N, *]
+    (lengths ref_len), all on the device; returns int32 [N]. Feeds on greedy_decode's (labels, label_lengths)."""
+    _lib.require_cuda(hyp, ref)
+    dev = hyp.device
+    hyp = hyp.to(torch.int32).contiguous()
+    hyp_len = hyp_len.to(device=dev, dtype=torch.int32).contiguous()
+    ref = ref.to(device=dev, dtype=torch.int64)
+    if ref.dim() == 1:
+        ref = ref.view(1, -1)
+    ref = ref.contiguous()
+    ref_len = ref_len.to(device=dev, dtype=torch.int64).contiguous()
+    N = hyp.shape[0]
+    if ref.shape[0] != N or hyp_len.numel() != N or ref_len.numel() != N:
+        raise ValueError("edit_distance: batch sizes differ")
+    dist = torch.empty(N, dtype=torch.int32, device=dev)
+    _lib.lib().call("ctcb200_edit_distance", _lib.ptr(hyp), hyp.stride(0), _lib.ptr(hyp_len), _lib.ptr(ref), ref.stride(0),
+                    _lib.ptr(ref_len), N, int(ref.shape[1]), _lib.ptr(dist), _lib.stream())
+    return dist
+
+
 _BEAM_ERRORS = {1: (IndexError, "tuple index out of range (the empty prefix reached the final LM step)"),
                 2: (ValueError, "math domain error (log of a zero probability)"),
                 3: (KeyError, "unit missing from the language model")}

@@ -65,6 +65,13 @@ CTCB200_API int ctcb200_argmax(const float* log_probs, int T, int N, int C, int*
                                ctcb200_stream_t stream);
 CTCB200_API int ctcb200_greedy_decode(const float* log_probs, const int64_t* lengths, int T, int N, int C, int blank,
                                       int* idx_nt, int* labels_nt, int* label_lengths, ctcb200_stream_t stream);
+/* Batched Levenshtein distance (unit costs) between hypothesis rows a [N, a_stride] int32 of lengths a_len [N] int32 (the
+ * labels_nt / label_lengths of ctcb200_greedy_decode) and reference rows b [N, b_stride] int64 of lengths b_len [N] int64
+ * (the padded targets of data_loader.py:125,140): the editdistance.eval call of CTC_Model.compute_wer
+ * (model_ctc.py:200) and Decoder._edit_distance (ctcDecoder.py:131-149). dist [N] int32. max_b_len <= 1024. */
+CTCB200_API int ctcb200_edit_distance(const int32_t* a, int64_t a_stride, const int32_t* a_len, const int64_t* b,
+                                      int64_t b_stride, const int64_t* b_len, int N, int max_b_len, int32_t* dist,
+                                      ctcb200_stream_t stream);
 
 /* ---- dense GEMM on tcgen05: C[M,N] (+)= A[M,K] * B[N,K]^T, A/B bf16 with K contiguous (pitches lda/ldb in
  * elements, multiples of 8), fp32 accumulate, C f32 (out_bf16=0) or bf16 (1) with pitch ldc.

@@ -417,3 +417,47 @@ def test_lstm_kernel_variants_agree(T, N, H):
     finally:
         os.environ.pop("CTCB200_LSTM_PIPE", None)
         os.environ.pop("CTCB200_LSTM_PIPE_BWD", None)
+
+
+def test_edit_distance_vs_oracle():
+    """Batched device Levenshtein = the reference's DP (ctcDecoder.py:131-149) on random and edge-case pairs."""
+    from ctc_pytorch_b200 import ops
+    rng = np.random.RandomState(5)
+    hyps, refs = [], []
+    for la, lb in [(0, 0), (0, 5), (7, 0), (1, 1), (30, 30), (33, 31), (64, 65), (100, 128), (129, 40), (800, 255), (300, 300),
+                   (5, 700), (1000, 1000)]:
+        a = rng.randint(1, 6, size=la)
+        b = a.copy()[:lb] if (la + lb) % 3 == 0 else rng.randint(1, 6, size=lb)
+        if len(b) < lb:
+            b = np.concatenate([b, rng.randint(1, 6, size=lb - len(b))])
+        hyps.append(a); refs.append(b)
+    for _ in range(20):
+        hyps.append(rng.randint(1, 40, size=rng.randint(0, 120))); refs.append(rng.randint(1, 40, size=rng.randint(0, 90)))
+    N = len(hyps)
+    A = np.zeros((N, max(len(h) for h in hyps) + 3), dtype=np.int32)
+    B = np.zeros((N, max(len(r) for r in refs)), dtype=np.int64)
+    for i, (h, r) in enumerate(zip(hyps, refs)):
+        A[i, :len(h)] = h; B[i, :len(r)] = r
+    al = torch.tensor([len(h) for h in hyps], dtype=torch.int32)
+    bl = torch.tensor([len(r) for r in refs], dtype=torch.int64)
+    got = ops.edit_distance(torch.from_numpy(A).to(DEV), al.to(DEV), torch.from_numpy(B).to(DEV), bl.to(DEV)).cpu().tolist()
+    want = [decode_ref.levenshtein([int(v) for v in h], [int(v) for v in r]) for h, r in zip(hyps, refs)]
+    assert got == want
+
+
+def test_compute_wer_device_matches_reference_semantics():
+    """compute_wer_device == the reference's compute_wer on the arg-max rows (model_ctc.py:187-202) at the cfg2 shape."""
+    from ctc_pytorch_b200.model import CTC_Model
+    torch.manual_seed(2)
+    T, N, C = 800, 32, 62
+    lp = torch.log_softmax(2.0 * torch.randn(T, N, C), -1)
+    lp[:, :, 0] += 1.0
+    x, frac, tg, tl = model_ref.synthetic_batch(T, N, 40, C, 60, 4)
+    il = (frac * T).long()
+    rnn_param = {"rnn_input_size": 40, "rnn_hidden_size": 128, "rnn_layers": 1, "rnn_type": nn.LSTM, "bidirectional": True,
+                 "batch_norm": False}
+    m = CTC_Model(rnn_param=rnn_param, num_class=C, drop_out=0.0)
+    errs, toks = m.compute_wer_device(lp.to(DEV), il, tg, tl)
+    idx = lp.argmax(-1).transpose(0, 1).numpy()
+    want = decode_ref.batch_errors(idx, il.numpy(), tg.numpy(), tl.numpy())
+    assert (errs, toks) == tuple(int(v) for v in want)
