@@ -461,3 +461,61 @@ def test_compute_wer_device_matches_reference_semantics():
     idx = lp.argmax(-1).transpose(0, 1).numpy()
     want = decode_ref.batch_errors(idx, il.numpy(), tg.numpy(), tl.numpy())
     assert (errs, toks) == tuple(int(v) for v in want)
+
+
+def _toy_loader(n_batches, T=60, N=4, F=40, C=12, S=6, seed=0):
+    data = []
+    for b in range(n_batches):
+        x, frac, tg, tl = model_ref.synthetic_batch(T, N, F, C, S, seed + b)
+        data.append((x, frac, tg, tl, ["utt%d_%d" % (b, n) for n in range(N)]))
+    return data
+
+
+def test_run_epoch_matches_reference_bookkeeping():
+    """train.run_epoch (device-side loss / WER accumulation) returns what the reference's loop computes step by step
+    (train_ctc.py:37-69): mean of CTCLoss(sum)/batch over the steps and 1 - errors/tokens of the arg-max path."""
+    from ctc_pytorch_b200.model import CTC_Model
+    from ctc_pytorch_b200.loss import CTCLoss
+    from ctc_pytorch_b200 import train
+    torch.manual_seed(0)
+    rnn_param = {"rnn_input_size": 40, "rnn_hidden_size": 128, "rnn_layers": 2, "rnn_type": nn.LSTM, "bidirectional": True,
+                 "batch_norm": True}
+    m = CTC_Model(rnn_param=rnn_param, num_class=12, drop_out=0.0).to(DEV)
+    loader = _toy_loader(3)
+    logs = []
+    acc, avg = train.run_epoch(1, m, loader, CTCLoss(reduction="sum"), DEV, optimizer=None, is_training=False, log=logs.append)
+    m.eval()
+    tot, errs, toks = 0.0, 0, 0
+    with torch.no_grad():
+        for x, frac, tg, tl, _ in loader:
+            out = m(x.to(DEV))
+            il = (frac.to(DEV) * out.shape[0]).long()
+            tot += float(CTCLoss(reduction="sum")(out, tg.to(DEV), il, tl.to(DEV))) / x.shape[0]
+            e, t = m.compute_wer(out.argmax(-1).transpose(0, 1).cpu().numpy(), il.cpu().numpy(), tg.numpy(), tl.numpy())
+            errs += e; toks += t
+    assert abs(avg - tot / 3) < 1e-4 * abs(tot / 3)
+    assert abs(acc - (1 - errs / toks)) < 1e-9
+    assert logs and "Valid done" in logs[-1]
+
+
+def test_fit_learns_and_resumes(tmp_path):
+    from ctc_pytorch_b200.model import CTC_Model
+    from ctc_pytorch_b200.loss import CTCLoss
+    from ctc_pytorch_b200 import train
+    torch.manual_seed(1)
+    rnn_param = {"rnn_input_size": 40, "rnn_hidden_size": 128, "rnn_layers": 1, "rnn_type": nn.LSTM, "bidirectional": True,
+                 "batch_norm": True}
+    m = CTC_Model(rnn_param=rnn_param, num_class=12, drop_out=0.0).to(DEV)
+    opt = torch.optim.Adam(m.parameters(), lr=3e-3)
+    tr, dv = _toy_loader(4), _toy_loader(1, seed=0)
+    path = str(tmp_path / "ckpt" / "ctc_best_model.pkl")
+    pkg, sched = train.fit(m, tr, dv, CTCLoss(reduction="sum"), opt, DEV, init_lr=3e-3, decay=0.5, end_adjust_acc=0.05,
+                           num_epoches=4, params={"feature_type": "fbank", "n_feats": 40}, checkpoint_path=path, log=lambda s: None)
+    assert len(pkg["loss_results"]) == 4 and pkg["loss_results"][-1] < pkg["loss_results"][0]
+    assert pkg["epoch"]["epoch"] == 4 and os.path.exists(path)
+    # resume from the file with a fresh model / optimizer: epoch counter and histories continue
+    m2, pkg2, opt2 = train.load_package(path, device=DEV, with_optimizer=lambda mm: torch.optim.Adam(mm.parameters(), lr=3e-3))
+    pkg3, _ = train.fit(m2, tr, dv, CTCLoss(reduction="sum"), opt2, DEV, init_lr=3e-3, decay=0.5, end_adjust_acc=0.05,
+                        num_epoches=6, resume=pkg2, log=lambda s: None)
+    assert pkg3["epoch"]["epoch"] == 6 and len(pkg3["loss_results"]) == 6
+    assert pkg3["loss_results"][:4] == pkg["loss_results"]
