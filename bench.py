@@ -187,7 +187,8 @@ def run_ours(args, cfg, rank, world):
 
     torch.manual_seed(0)
     model = CTC_Model(rnn_param=rnn_param(cfg), num_class=C, drop_out=0.0).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.005)
+    # the reference's optimizer (train_ctc.py:145: Adam + L2 weight decay), torch's single-launch (fused) implementation
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.005, fused=True)
     loss_fn = CTCLoss(reduction="sum")
     bucket = GradBucket(model.parameters())
     model.train()

@@ -13,7 +13,7 @@ if len(sys.argv) > 2: cfg["T"] = int(sys.argv[2])
 dev = "cuda"
 torch.manual_seed(0)
 m = CTC_Model(rnn_param=bench.rnn_param(cfg), num_class=cfg["C"], drop_out=0.0).to(dev)
-opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0.005)
+opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0.005, fused=True)
 x, frac, tg, tl = (t.to(dev) for t in bench.make_batch(cfg, 1))
 lossf = CTCLoss(reduction="sum"); m.train()
 def step():
