@@ -52,6 +52,30 @@ for _ in range(10):
 ts.sort()
 ms = ts[len(ts) // 2]
 
+# per-entry-point device time (one stream, overlap off), as bench.py does for cfg2
+from ctc_pytorch_b200 import _lib
+L = _lib.lib()
+per_call, orig_call = {}, L.call
+
+
+def timed_call(name, *a):
+    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_.record(); r = orig_call(name, *a); e_.record()
+    per_call.setdefault(name, []).append((s_, e_))
+    return r
+
+
+L.call = timed_call
+m.overlap_wgrad = False
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+L.call = orig_call
+m.overlap_wgrad = True
+kern = {k: sum(a.elapsed_time(b) for a, b in v) / 2 for k, v in per_call.items()}
+kern_ms = {k: round(v, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])}
+kern_n = {k: len(v) // 2 for k, v in per_call.items()}
+
 # CPU: the oracle's restatement of the reference composition, 2 utterances, 16 threads
 threads = bench.cpu_threads()
 torch.set_num_threads(threads)
@@ -69,7 +93,7 @@ for it in range(2):
     ropt.zero_grad(); l.backward(); ropt.step()
 cpu_s = time.perf_counter() - t0
 res = {"config": "cfg3: 2xConv2d front + 4xBiLSTM-512, T=800 -> T'=%d, N=32, C=62" % shape[0], "gpu_ms_per_step": ms,
-       "gpu_utt_s": cfg["N"] / (ms * 1e-3), "loss": float(loss.detach()),
+       "gpu_utt_s": cfg["N"] / (ms * 1e-3), "loss": float(loss.detach()), "kernel_ms_per_step": kern_ms, "calls_per_step": kern_n,
        "cpu": {"kind": "port", "cores": threads, "utt_s": 2 / cpu_s, "sample": "2 utterances x 1 timed step"}}
 print(json.dumps(res))
 if len(sys.argv) > 1:
