@@ -122,10 +122,18 @@ def _resident_state(dev):
 
 
 def _overlap_enabled(model):
-    """Weight-gradient work on a side stream under the BPTT kernels (CTC_Model.overlap_wgrad, env override)."""
+    """Weight-gradient work on a side stream under the BPTT kernels (CTC_Model.overlap_wgrad, env override).
+
+    The side stream is gated by a stream memory operation (cuStreamWaitValue32), whose ordering is invisible to the CUDA
+    scheduler. In a single-process, single-communicator job that is safe here (the gate is enqueued only after the launch
+    that satisfies it); with a NCCL communicator in the process (extra internal streams sharing hardware queues) a
+    2-GPU run was observed to stall, so data-parallel jobs keep the weight-gradient GEMMs on the main stream unless
+    CTCB200_OVERLAP_WGRAD=1 forces the overlap."""
     env = os.environ.get("CTCB200_OVERLAP_WGRAD")
     if env is not None:
         return env == "1"
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        return False
     return bool(getattr(model, "overlap_wgrad", True))
 
 
