@@ -1853,7 +1853,7 @@ BwdKern bwd_kernel(int NB, int ex) {
 
 template <typename Kern, typename Params>
 int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool cooperative, const CUtensorMap& tm,
-                     const Params& p, cudaStream_t stream, int threads = LSTM_THREADS) {
+                     const Params& p, cudaStream_t stream, int threads = LSTM_THREADS, cudaEvent_t start_event = nullptr) {
     CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     if (cluster.x * cluster.y * cluster.z > 8)
         CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1862,19 +1862,32 @@ int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool coope
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attrs[2];
+    cudaLaunchAttribute attrs[3];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = cluster.x; attrs[0].val.clusterDim.y = cluster.y; attrs[0].val.clusterDim.z = cluster.z;
-    attrs[1].id = cudaLaunchAttributeCooperative;
-    attrs[1].val.cooperative = 1;
+    int n_attrs = 1;
+    if (start_event != nullptr) {
+        // programmatic event: fires once every block of this grid has started, i.e. the grid is resident — other streams can
+        // cudaStreamWaitEvent on it to hand the remaining SMs to independent work (a dependency the CUDA scheduler sees)
+        attrs[n_attrs].id = cudaLaunchAttributeProgrammaticEvent;
+        attrs[n_attrs].val.programmaticEvent.event = start_event;
+        attrs[n_attrs].val.programmaticEvent.flags = 0;
+        attrs[n_attrs].val.programmaticEvent.triggerAtBlockStart = 1;
+        ++n_attrs;
+    }
+    if (cooperative) {
+        attrs[n_attrs].id = cudaLaunchAttributeCooperative;
+        attrs[n_attrs].val.cooperative = 1;
+        ++n_attrs;
+    }
     cfg.attrs = attrs;
-    cfg.numAttrs = cooperative ? 2 : 1;
+    cfg.numAttrs = n_attrs;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, p);
     if (e != cudaSuccess && cooperative) {
         // some driver / tool combinations refuse cooperative + cluster together; co-residency is then guaranteed
         // by the caller's CTA budget (one CTA per SM, grid <= schedulable clusters) on an otherwise idle device
         (void)cudaGetLastError();
-        cfg.numAttrs = 1;
+        cfg.numAttrs = n_attrs - 1;
         e = cudaLaunchKernelEx(&cfg, kern, tm, p);
     }
     CTCB_CUDA(e);
@@ -2057,8 +2070,9 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
 extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
                                             const void* gates_save, void* dg, void* scratch, int T, int N, int H,
                                             int batch_tile, const float* bn_x, const float* bn_coef, void* resident_counter,
-                                            ctcb200_stream_t stream_) {
+                                            void* resident_event, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaEvent_t start_ev = static_cast<cudaEvent_t>(resident_event);
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE((reinterpret_cast<uintptr_t>(resident_counter) & 3) == 0, "lstm_bwd: resident_counter must be 4-byte aligned");
     CTCB_REQUIRE((bn_x == nullptr) == (bn_coef == nullptr), "lstm_bwd: bn_x and bn_coef must be given together");
@@ -2080,7 +2094,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
             return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false,
-                                    tmWT2, p2, stream);
+                                    tmWT2, p2, stream, LSTM_THREADS, start_ev);
     }
     int ex = exchange_mode(H);
     {
@@ -2117,7 +2131,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
                 CTCB_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 16 * T, stream));
                 p.trace = dbuf;
             }
-            rc = launch_clustered(lstm_bwd_pipe_kernel, grid, cluster, smem_p, false, tmWT, p, stream, PIPE_THREADS);
+            rc = launch_clustered(lstm_bwd_pipe_kernel, grid, cluster, smem_p, false, tmWT, p, stream, PIPE_THREADS, start_ev);
             if (p.trace && rc == OK) {
                 cudaStreamSynchronize(stream);
                 long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
@@ -2145,15 +2159,15 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
             const size_t img_bytes = static_cast<size_t>(2) * groups_total * 4 * 2 * H * NB * 2;
             CTCB_CUDA(cudaMemsetAsync(scratch, 0, img_bytes, stream));
             p.dgimg = static_cast<__nv_bfloat16*>(scratch);
-            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 2>, grid, cluster, smem, false, tmWT, p, stream);
-            return launch_clustered(lstm_bwd_kernel<32, 2>, grid, cluster, smem, false, tmWT, p, stream);
+            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 2>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
+            return launch_clustered(lstm_bwd_kernel<32, 2>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
         }
         if (ex == 3) {
-            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 3>, grid, cluster, smem, false, tmWT, p, stream);
-            return launch_clustered(lstm_bwd_kernel<32, 3>, grid, cluster, smem, false, tmWT, p, stream);
+            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 3>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
+            return launch_clustered(lstm_bwd_kernel<32, 3>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
         }
-        if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 1>, grid, cluster, smem, false, tmWT, p, stream);
-        return launch_clustered(lstm_bwd_kernel<32, 1>, grid, cluster, smem, false, tmWT, p, stream);
+        if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 1>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
+        return launch_clustered(lstm_bwd_kernel<32, 1>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
     }
     const int per_group = 2 * 4 * MB;
     const int sms = device_sm_count();
@@ -2172,8 +2186,8 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         if (g0 > 0) p.resident = nullptr;
         dim3 grid(4, MB, 2 * groups), cluster(4, 1, 1);
         const bool coop = getenv("CTCB200_BWD_NO_COOP") == nullptr;  // profilers may reject cooperative + cluster
-        if (NB == 16) rc = launch_clustered(lstm_bwd_kernel<16, 0>, grid, cluster, smem, coop, tmWT, p, stream);
-        else rc = launch_clustered(lstm_bwd_kernel<32, 0>, grid, cluster, smem, coop, tmWT, p, stream);
+        if (NB == 16) rc = launch_clustered(lstm_bwd_kernel<16, 0>, grid, cluster, smem, coop, tmWT, p, stream, LSTM_THREADS, g0 == 0 ? start_ev : nullptr);
+        else rc = launch_clustered(lstm_bwd_kernel<32, 0>, grid, cluster, smem, coop, tmWT, p, stream, LSTM_THREADS, g0 == 0 ? start_ev : nullptr);
         if (rc != OK) return rc;
     }
     return OK;

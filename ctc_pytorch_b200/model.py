@@ -13,6 +13,7 @@ Behaviour kept on purpose: the LSTM and BatchNorm run ove
 layer 0 never has BatchNorm, BatchNorm statistics are over T*N rows, the fc BatchNorm follows
 rnn_param['batch_norm'].
 """
+import ctypes
 import math
 import os
 from collections import OrderedDict
@@ -121,19 +122,46 @@ def _resident_state(dev):
     return _RESIDENT[key]
 
 
+_RESIDENT_EVENTS = {}
+
+
+def _resident_event(dev):
+    """Per-device cudaEvent (timing disabled) the BPTT launch fires, as a programmatic event, once all of its blocks have
+    started. Returns (torch event, raw handle)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _RESIDENT_EVENTS:
+        ev = torch.cuda.Event(enable_timing=False)
+        ev.record(torch.cuda.current_stream(dev))   # materialises the underlying cudaEvent_t
+        _RESIDENT_EVENTS[key] = ev
+    ev = _RESIDENT_EVENTS[key]
+    return ev, ctypes.c_void_p(ev.cuda_event)
+
+
+def _distributed():
+    return torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+
+
+def _overlap_gate():
+    """How the side stream learns that the BPTT grid is resident.
+    'memop': counter bumped by the kernel + cuStreamWaitValue32 — precise (cfg2 fwd+loss+bwd 13.5 ms vs 14.95 without
+             overlap) but invisible to the CUDA scheduler; one 2-GPU run with a NCCL communicator in the process stalled on it.
+    'event': programmatic launch event (fires when every block has started) + cudaStreamWaitEvent — an ordinary stream
+             dependency; observed later than the memop (14.4 ms), safe next to other libraries' streams.
+    Default: memop in single-process jobs, event when the process belongs to a world_size > 1 group; CTCB200_OVERLAP_GATE
+    overrides."""
+    g = os.environ.get("CTCB200_OVERLAP_GATE")
+    if g in ("event", "memop"):
+        return g
+    return "event" if _distributed() else "memop"
+
+
 def _overlap_enabled(model):
     """Weight-gradient work on a side stream under the BPTT kernels (CTC_Model.overlap_wgrad, env override).
 
-    The side stream is gated by a stream memory operation (cuStreamWaitValue32), whose ordering is invisible to the CUDA
-    scheduler. In a single-process, single-communicator job that is safe here (the gate is enqueued only after the launch
-    that satisfies it); with a NCCL communicator in the process (extra internal streams sharing hardware queues) a
-    2-GPU run was observed to stall, so data-parallel jobs keep the weight-gradient GEMMs on the main stream unless
-    CTCB200_OVERLAP_WGRAD=1 forces the overlap."""
+    See _overlap_gate() for the two gating mechanisms. CTCB200_OVERLAP_WGRAD=0/1 overrides."""
     env = os.environ.get("CTCB200_OVERLAP_WGRAD")
     if env is not None:
         return env == "1"
-    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-        return False
     return bool(getattr(model, "overlap_wgrad", True))
 
 
@@ -278,8 +306,10 @@ class _RnnStackFn(torch.autograd.Function):
         overlap = bool(ws.defer_t)
         side = _side_stream(dev) if overlap else None
         keep = []
+        gate = _overlap_gate()
         if overlap:
             res = _resident_state(dev)
+            gate_ev, gate_ev_ptr = _resident_event(dev)
             side_ctas = max(8, torch.cuda.get_device_properties(dev).multi_processor_count
                             - int(_lib.lib().dll.ctcb200_lstm_bwd_ctas(N, H, model.batch_tile)))
 
@@ -357,7 +387,8 @@ class _RnnStackFn(torch.autograd.Function):
             _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p), _lib.ptr(rec.c_save), _lib.ptr(rec.gates),
                   _lib.ptr(dg), _lib.ptr(scratch), T, N, H, model.batch_tile,
                   _lib.ptr(bn_fuse[0]) if bn_fuse else None, _lib.ptr(bn_fuse[1]) if bn_fuse else None,
-                  _lib.ptr(res[0]) if overlap else None, stream())
+                  _lib.ptr(res[0]) if (overlap and gate == "memop") else None,
+                  gate_ev_ptr if (overlap and gate == "event") else None, stream())
             if bn_fuse:
                 keep.append(bn_fuse)
                 bn_fuse = None
@@ -366,10 +397,14 @@ class _RnnStackFn(torch.autograd.Function):
             # are confined to the SMs that latency-bound kernel leaves idle. The gate is only ever enqueued after the
             # launch it waits for.
             if overlap:
-                res[1] = (res[1] + 1) & 0xFFFFFFFF
+                if gate == "memop":
+                    res[1] = (res[1] + 1) & 0xFFFFFFFF
                 if pending is not None:
                     with torch.cuda.stream(side):
-                        _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
+                        if gate == "event":
+                            side.wait_event(gate_ev)   # fires when every block of the BPTT grid just launched has started
+                        else:
+                            _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
                         _wgrad(pending, side_ctas)
                 pending = (layer, rec, dg, li)
             else:

@@ -109,8 +109,11 @@ CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, float*
 CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
                                  const void* gates_save, void* dg, void* scratch, int T, int N, int H,
                                  int batch_tile, const float* bn_x, const float* bn_coef, void* resident_counter,
-                                 ctcb200_stream_t stream);
+                                 void* resident_event, ctcb200_stream_t stream);
 /* Scheduling aid for overlapping off-critical-path work (weight-gradient GEMMs) with the latency-bound BPTT kernel:
+ * resident_event (NULL = off) is a cudaEvent_t (created with timing disabled) attached to the launch as a programmatic event
+ * that fires once every block of the BPTT grid has started: cudaStreamWaitEvent on it from another stream is a dependency
+ * the CUDA scheduler can see (preferred). The older variant:
  * resident_counter (NULL = off) points at two zero-initialised uint32 words owned by the caller; word 0 is incremented
  * once per lstm_bwd launch as soon as every CTA of that launch is running. ctcb200_stream_wait_geq makes `stream`
  * wait (a driver stream memory operation, no SM is occupied) until *counter >= value, and ctcb200_lstm_bwd_ctas says

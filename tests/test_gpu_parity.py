@@ -409,7 +409,7 @@ def test_lstm_kernel_variants_agree(T, N, H):
             os.environ["CTCB200_LSTM_PIPE_BWD"] = mode
             dg = torch.zeros(R, 8 * H, dtype=torch.bfloat16, device=DEV)
             L.call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(whh), _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(dg),
-                   _lib.ptr(scratch), T, N, H, 0, None, None, None, _lib.stream())
+                   _lib.ptr(scratch), T, N, H, 0, None, None, None, None, _lib.stream())
             torch.cuda.synchronize()
             dgs[mode] = dg.float()
         assert torch.isfinite(dgs["1"]).all()

@@ -13,6 +13,7 @@ from ctc_pytorch_b200 import ops
 
 env = sys.argv[1]
 name = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+vals = sys.argv[3].split(",") if len(sys.argv) > 3 else ["0", "1"]
 dev = "cuda"
 cfg = dict(bench.CFG[name])
 torch.manual_seed(0)
@@ -34,7 +35,7 @@ def step():
 
 
 g = {}
-for mode in ("0", "1", "0", "1"):
+for mode in (vals[0], vals[1], vals[0], vals[1]):
     os.environ[env] = mode
     for _ in range(3):
         step()
@@ -50,5 +51,5 @@ for mode in ("0", "1", "0", "1"):
     g[mode] = torch.cat([p.grad.flatten().double() for p in m.parameters()])
     print("%s %s=%s: fwd+loss+bwd median %.3f ms (min %.3f), loss %.6f" % (name, env, mode, ts[len(ts) // 2], ts[0], float(loss.detach())),
           flush=True)
-print("%s: gradient rel L2 (%s=1 vs 0) %.3e, finite %s" % (name, env, float((g["0"] - g["1"]).norm() / g["0"].norm()),
-                                                          bool(torch.isfinite(g["1"]).all())))
+print("%s: gradient rel L2 (%s=1 vs 0) %.3e, finite %s" % (name, env, float((g[vals[0]] - g[vals[1]]).norm() / g[vals[0]].norm()),
+                                                          bool(torch.isfinite(g[vals[1]]).all())))

@@ -46,7 +46,7 @@ out = []
 for fused in (False, True):
     dg = torch.zeros(R, 8 * H, dtype=torch.bfloat16, device=dev)
     L.call("ctcb200_lstm_bwd", _lib.ptr(dy if fused else dx_un), _lib.ptr(whhT), _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(dg),
-           _lib.ptr(scratch), T, N, H, 0, _lib.ptr(x) if fused else None, _lib.ptr(coef) if fused else None, None, _lib.stream())
+           _lib.ptr(scratch), T, N, H, 0, _lib.ptr(x) if fused else None, _lib.ptr(coef) if fused else None, None, None, _lib.stream())
     torch.cuda.synchronize()
     out.append(dg.float())
 print("BPTT dG: fused vs pre-applied rel L2 %.2e, max abs %.2e (max |dG| %.2e)" % (rel(out[1], out[0]), float((out[1] - out[0]).abs().max()),

@@ -25,7 +25,7 @@ for mode in ("0", "1"):
     for rep in range(reps):
         dg = torch.full((R, 8 * H), float("nan"), dtype=torch.bfloat16, device=dev)
         L.call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(whhT), _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(dg), _lib.ptr(scratch),
-               T, N, H, 0, None, None, _lib.ptr(res), _lib.stream())
+               T, N, H, 0, None, None, _lib.ptr(res), None, _lib.stream())
         torch.cuda.synchronize()
         if rep and not torch.equal(dg.float().nan_to_num(7.0), prev.float().nan_to_num(7.0)):
             print("mode %s: run %d differs from run 0 (non-deterministic)" % (mode, rep))

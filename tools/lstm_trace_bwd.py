@@ -23,16 +23,16 @@ for mode in ("1", "0"):
     os.environ.pop("CTCB200_LSTM_TRACE", None)
     for _ in range(2):
         L.call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(whhT), _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(dg), _lib.ptr(scratch),
-               T, N, H, 0, None, None, None, _lib.stream())
+               T, N, H, 0, None, None, None, None, _lib.stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     L.call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(whhT), _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(dg), _lib.ptr(scratch),
-           T, N, H, 0, None, None, None, _lib.stream())
+           T, N, H, 0, None, None, None, None, _lib.stream())
     e1.record()
     torch.cuda.synchronize()
     print("pipe_bwd=%s: %.3f ms per launch (%.3f us/step)" % (mode, e0.elapsed_time(e1), e0.elapsed_time(e1) * 1e3 / T), flush=True)
     if mode == "1":
         os.environ["CTCB200_LSTM_TRACE"] = "1"
         L.call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(whhT), _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(dg), _lib.ptr(scratch),
-               T, N, H, 0, None, None, None, _lib.stream())
+               T, N, H, 0, None, None, None, None, _lib.stream())
         torch.cuda.synchronize()
