@@ -136,3 +136,42 @@ def test_host_mirrors_match_reference_live(golden_dir):
     arpa = os.path.join(golden_dir, "lm_c62.arpa")
     a, b = LanguageModel(arpa_file=arpa), ref.LanguageModel(arpa_file=arpa)
     assert a.unigram == b.unigram and a.bigram == b.bigram
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under ctc_pytorch_b200/ may import it."""
+    import re
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ctc_pytorch_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+            assert "/root/reference" not in src, fn
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md is the maintainer-facing map of the C ABI: every declared entry point appears in it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ctcb200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = set(re.findall(r"\b(ctcb200_\w+)\s*\(", hdr)) - {"ctcb200_version"}
+    assert names and not [n for n in sorted(names) if n not in doc]
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "cfg1", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
