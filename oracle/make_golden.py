@@ -149,6 +149,47 @@ def gen_beam(ref):
     print("all-blank utterance raises:", blank_err)
 
 
+PACKED_CASE = dict(T=24, N=5, F=40, H=128, L=3, C=12, S=4, seed=11)
+
+
+def gen_packed():
+    """Variable-length (packed) semantics of the 863 path: the UNMODIFIED my_863_corpus/steps/model.py
+    CTC_RNN on a pack_padded_sequence input, warp-ctc style loss restated with torch (oracle/packed_ref.warp_ctc_loss)."""
+    sys.path.insert(0, "/root/reference/my_863_corpus/steps")
+    import model as m863   # noqa: E402  (the reference's module, imported in place)
+    from oracle import packed_ref
+    cfg = PACKED_CASE
+    torch.manual_seed(cfg["seed"])
+    net = m863.CTC_RNN(rnn_input_size=cfg["F"], rnn_hidden_size=cfg["H"], rnn_layers=cfg["L"], rnn_type=nn.LSTM,
+                       bidirectional=True, batch_norm=True, num_class=cfg["C"], drop_out=0.0)
+    checksum = {k: float(v.double().abs().sum()) for k, v in net.state_dict().items()}
+    x, lens, targets, tsz = packed_ref.synthetic_packed_batch(cfg["T"], cfg["N"], cfg["F"], cfg["C"], cfg["S"], cfg["seed"])
+    net.train()
+    act = net(nn.utils.rnn.pack_padded_sequence(x, lens))
+    loss = packed_ref.warp_ctc_loss(act, targets, lens, tsz)
+    loss.backward()
+    grads = {}
+    for k, p_ in net.named_parameters():
+        vals, step = sample(p_.grad)
+        grads[k] = dict(norm=float(p_.grad.norm()), step=int(step), vals=vals)
+    buffers = {k: v.detach().clone().numpy() for k, v in net.named_buffers() if "running" in k}
+    net.eval()
+    with torch.no_grad():
+        logp = net(nn.utils.rnn.pack_padded_sequence(x, lens))
+    payload = dict(x=x.numpy(), lengths=np.asarray(lens, dtype=np.int64), targets=targets.numpy(),
+                   target_sizes=np.asarray(tsz, dtype=np.int64), act_train=act.detach().numpy(), logp_eval=logp.numpy(),
+                   loss=float(loss))
+    for k, g in grads.items():
+        payload["gradvals/" + k] = g["vals"]
+    for k, b in buffers.items():
+        payload["buffer/" + k] = b
+    np.savez_compressed(os.path.join(OUT, "packed_rnn.npz"), **payload)
+    with open(os.path.join(OUT, "packed_rnn.json"), "w") as fh:
+        json.dump(dict(cfg=cfg, checksum=checksum, grad_norm={k: g["norm"] for k, g in grads.items()},
+                       grad_step={k: g["step"] for k, g in grads.items()}), fh, indent=1)
+    print("packed_rnn: loss %.6f, lengths %s" % (float(loss), lens))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
@@ -156,6 +197,7 @@ def main():
     gen_ctc()
     gen_models(ref)
     gen_beam(ref)
+    gen_packed()
 
 
 if __name__ == "__main__":

@@ -187,3 +187,69 @@ def test_model_oracle_matches_reference_live():
             a, b = rm(x), om(x)
             # same library kernels, different reduction order inside BatchNorm -> float32 round-off only
             assert torch.allclose(a, b, atol=2e-6, rtol=0), (name, mode, (a - b).abs().max())
+
+
+# ------------------------------------------------------------------- packed / variable-length semantics (N1)
+def _packed_golden(golden_dir):
+    from oracle import packed_ref
+    meta = json.load(open(os.path.join(golden_dir, "packed_rnn.json")))
+    g = np.load(os.path.join(golden_dir, "packed_rnn.npz"))
+    cfg = meta["cfg"]
+    torch.manual_seed(cfg["seed"])
+    m = packed_ref.RefPackedModel(cfg["F"], cfg["H"], cfg["L"], True, cfg["C"])
+    for k, v in m.state_dict().items():   # same construction order as the reference => same weights from the seed
+        if k in meta["checksum"]:
+            assert abs(float(v.double().abs().sum()) - meta["checksum"][k]) <= 1e-6 * max(1.0, meta["checksum"][k]), k
+    return packed_ref, meta, g, m
+
+
+def test_packed_oracle_matches_golden(golden_dir):
+    """The mask formulation of oracle/packed_ref.py reproduces what the unmodified 863 CTC_RNN computed on a
+    pack_padded_sequence batch (tests/golden/packed_rnn.*): activations, warp-ctc style loss, gradients, eval log-probs."""
+    packed_ref, meta, g, m = _packed_golden(golden_dir)
+    x, lens = torch.from_numpy(g["x"]), g["lengths"].tolist()
+    m.train()
+    act = m(x, lens)
+    np.testing.assert_allclose(act.detach().numpy(), g["act_train"], atol=5e-6)
+    # padded frames are exactly zero after pad_packed_sequence
+    for n, l in enumerate(lens):
+        assert np.all(g["act_train"][l:, n] == 0.0) and torch.all(act[l:, n] == 0.0)
+    loss = packed_ref.warp_ctc_loss(act, torch.from_numpy(g["targets"]), lens, g["target_sizes"].tolist())
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    for k, p in m.named_parameters():
+        step = meta["grad_step"][k]
+        vals = p.grad.reshape(-1)[::step][:256].numpy()
+        np.testing.assert_allclose(vals, g["gradvals/" + k], atol=2e-5 * max(1.0, meta["grad_norm"][k]))
+        assert abs(float(p.grad.norm()) - meta["grad_norm"][k]) < 1e-4 * max(1.0, meta["grad_norm"][k])
+    for k, v in m.named_buffers():
+        if "running" in k:
+            np.testing.assert_allclose(v.numpy(), g["buffer/" + k], atol=1e-6)
+    m.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(m(x, lens).numpy(), g["logp_eval"], atol=5e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/my_863_corpus/steps"), reason="reference tree only exists in the build container")
+def test_packed_oracle_matches_reference_live():
+    import sys
+    from oracle import packed_ref
+    sys.path.insert(0, "/root/reference/my_863_corpus/steps")
+    import model as m863
+    for seed, (T, N, H, L, bn) in enumerate([(18, 3, 128, 2, True), (25, 4, 128, 3, True), (12, 2, 128, 2, False)]):
+        torch.manual_seed(100 + seed)
+        ref = m863.CTC_RNN(rnn_input_size=40, rnn_hidden_size=H, rnn_layers=L, rnn_type=nn.LSTM, bidirectional=True,
+                           batch_norm=bn, num_class=9, drop_out=0.0)
+        mine = packed_ref.RefPackedModel(40, H, L, bn, 9)
+        mine.load_state_dict(ref.state_dict())
+        x, lens, tg, tsz = packed_ref.synthetic_packed_batch(T, N, 40, 9, 3, seed)
+        ref.train(); mine.train()
+        a = ref(nn.utils.rnn.pack_padded_sequence(x, lens))
+        b = mine(x, lens)
+        assert (a - b).abs().max().item() < 5e-6
+        la = packed_ref.warp_ctc_loss(a, tg, lens, tsz); la.backward()
+        lb = packed_ref.warp_ctc_loss(b, tg, lens, tsz); lb.backward()
+        assert abs(la.item() - lb.item()) < 1e-5 * abs(la.item())
+        pa, pb = dict(ref.named_parameters()), dict(mine.named_parameters())
+        for k in pa:
+            assert (pa[k].grad - pb[k].grad).abs().max().item() < 2e-5 * max(1.0, pa[k].grad.abs().max().item()), k
