@@ -8,19 +8,22 @@
 //
 // Decomposition. The input projection x_t W_ih^T for all t is one big tensor-core GEMM (gemm.cu)
 // done beforehand; what remains per step is the thin product W_hh h_{t-1} ([4H x H] x [H x N]).
-// W_hh never leaves the chip: each CTA owns 32 hidden units = 128 gate rows of one direction,
-// keeps that [128 x H] bf16 slice resident in shared memory (loaded once by TMA, SWIZZLE_128B) and
-// per step issues one tcgen05.mma chain (M=128, N=batch tile, K=H) into a TMEM accumulator.
-// The only per-step traffic is the all-gather of h_t (H x NB bf16) between the H/32 CTAs of a
-// (direction, batch-group): every CTA writes its 32 units into a global "operand image" that is
-// already laid out as the next step's K-major SWIZZLE_64B B operand, releases a counter, and all
-// CTAs copy the image back into shared memory. Gate non-linearities, the cell update and the
-// hadamard products are fused in registers between tcgen05.ld and the image store.
+// W_hh never leaves the chip: each CTA owns 32 hidden units = 128 gate rows of one direction and keeps that
+// [128 x H] bf16 slice resident in TENSOR MEMORY (tcgen05.mma with the A operand in TMEM); per step it issues the
+// K = H MMA chain from four warps into four TMEM accumulators. The H/32 CTAs of a (direction, batch group) form
+// one thread-block cluster; the only per-step traffic is the all-gather of h_t (H x NB bf16), one bulk DSMEM copy
+// per peer with complete_tx on the peer's mbarrier, landing directly in the next step's K-major SWIZZLE_64B
+// B-operand image. Gate non-linearities, the cell update and the hadamard products are fused in registers.
 //
-// The backward kernel mirrors this with W_hh^T: CTA (mb, q) of a 4-CTA cluster holds the
-// [128 units x H] slice of gate q's transposed block, multiplies it with gate q's dG image, and the
-// four partial dh blocks of a cluster are reduce-scattered through distributed shared memory so
-// that each CTA finishes 32 units: dh -> (do, dc, di, df, dg) -> next dG images.
+// Kernels in this file (DESIGN.md §3.2 has the measurements):
+//   lstm_fwd_pipe_kernel   default forward for H <= 512: two 8-column halves software-pipelined over element,
+//                          tensor-core and copy warps; gx arrives as TMA boxes
+//   lstm_fwd_kernel<NB,EX> un-pipelined forward; EX selects the exchange (3 = bulk DSMEM copies, 1 = DSMEM stores,
+//                          2 = L2 + remote mbarriers, 0 = global image + counter, cooperative launch: the fallback)
+//   lstm_bwd_kernel<NB,EX> BPTT: CTA (q, mb) of a (4, H/128) cluster holds gate q's transposed slice for 128 units; the
+//                          four gate partials are reduce-scattered (fp16 on the wire), the dG blocks all-gathered
+//   lstm_bwd_pipe_kernel   pipelined BPTT (opt-in, not faster: the DSMEM fabric is the bound either way)
+//   lstm_fwd2/bwd2_kernel  two gate tiles per CTA for H in (512, 640]
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -480,15 +483,6 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
 // ------------------------------------------------------------------------------------------------
 constexpr int PIPE_THREADS = 512;   // 8 element warps + 4 tensor-core warps + 4 copy warps
 
-__device__ __forceinline__ void bar_sync_elem() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-// 4-byte cp.async; `ok` false -> zero fill (src-size 0), so every call belongs to exactly one commit group
-__device__ __forceinline__ void cp_async_f32_zfill(float* smem_dst, const float* gsrc, bool ok) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(ok ? 4 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
-__device__ __forceinline__ void bulk_wait_read_2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
 lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
