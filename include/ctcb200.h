@@ -73,6 +73,18 @@ CTCB200_API int ctcb200_edit_distance(const int32_t* a, int64_t a_stride, const 
                                       int64_t b_stride, const int64_t* b_len, int N, int max_b_len, int32_t* dist,
                                       ctcb200_stream_t stream);
 
+/* ---- batch assembly on the device: SpeechDataset.__getitem__'s make_context -> skip_feat -> pad to a
+ * multiple of n_downsample (timit/utils/data_loader.py:103-110, timit/utils/tools.py:66-86) and create_input's zero padding
+ * (data_loader.py:119-140). feat f32 [sum(L_n), F] = the raw utterance features back to back, offsets int64 [N+1] their row
+ * offsets. Writes x f32 [N, T_max, F*(left+right+1)] and input_sizes f32 [N] = L''_n / T_max (T_max = max L''_n, computed by
+ * the caller from the lengths). pad_labels: labels int64 [sum(S_n)] + offsets -> targets int64 [N, S_max] zero padded and
+ * target_sizes int64 [N]. Pure copies: bit-exact. */
+CTCB200_API int ctcb200_assemble_features(const float* feat, const int64_t* offsets, int N, int F, int left, int right,
+                                          int skip, int n_downsample, int T_max, float* x, float* input_sizes,
+                                          ctcb200_stream_t stream);
+CTCB200_API int ctcb200_pad_labels(const int64_t* labels, const int64_t* offsets, int N, int S_max, int64_t* targets,
+                                   int64_t* target_sizes, ctcb200_stream_t stream);
+
 /* ---- dense GEMM on tcgen05: C[M,N] (+)= A[M,K] * B[N,K]^T, A/B bf16 with K contiguous (pitches lda/ldb in
  * elements, multiples of 8), fp32 accumulate, C f32 (out_bf16=0) or bf16 (1) with pitch ldc.
  * a_koff/b_koff (multiples of 8) shift the K window of each operand (the h_{t-1} shift of dW_hh).

@@ -190,6 +190,42 @@ def gen_packed():
     print("packed_rnn: loss %.6f, lengths %s" % (float(loss), lens))
 
 
+BATCH_CASES = [(0, 0, 1, 1), (2, 2, 1, 1), (3, 1, 3, 1), (1, 2, 2, 4), (0, 0, 0, 3), (5, 5, 4, 2)]
+
+
+def gen_batch():
+    """Host-side batch assembly of the UNMODIFIED reference (utils/tools.py make_context / skip_feat, the n_downsample padding of
+    SpeechDataset.__getitem__, utils/data_loader.py create_input; kaldiio stubbed, it is only used to read ark files)."""
+    import types
+    sys.path.insert(0, "/root/reference/timit")
+    sys.path.insert(0, "/root/reference/timit/utils")
+    sys.modules.setdefault("kaldiio", types.ModuleType("kaldiio"))
+    import tools         # noqa: E402
+    import data_loader   # noqa: E402
+    rng = np.random.RandomState(21)
+    feats = [rng.randn(L, 8).astype(np.float32) for L in (13, 1, 9, 20, 16)]
+    labs = [rng.randint(1, 9, size=k).astype(np.int64) for k in (4, 1, 3, 6, 2)]
+    payload = {"n": np.asarray(len(feats))}
+    for i, (f, l) in enumerate(zip(feats, labs)):
+        payload["feat/%d" % i] = f
+        payload["label/%d" % i] = l
+    for ci, (left, right, skip, down) in enumerate(BATCH_CASES):
+        items = []
+        for f, lab in zip(feats, labs):
+            ft = tools.skip_feat(tools.make_context(f, left, right), skip)
+            if ft.shape[0] % down != 0:
+                ft = np.vstack([ft, np.zeros((down - ft.shape[0] % down, ft.shape[1]))])
+            items.append((torch.from_numpy(ft), torch.LongTensor(lab), "utt"))
+        x, isz, tg, tsz, _ = data_loader.create_input(items)
+        payload["case%d/x" % ci] = x.numpy()
+        payload["case%d/input_sizes" % ci] = isz.numpy()
+        payload["case%d/targets" % ci] = tg.numpy()
+        payload["case%d/target_sizes" % ci] = tsz.numpy()
+    payload["cases"] = np.asarray(BATCH_CASES, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "batch_small.npz"), **payload)
+    print("batch_small: %d cases" % len(BATCH_CASES))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
@@ -198,6 +234,7 @@ def main():
     gen_models(ref)
     gen_beam(ref)
     gen_packed()
+    gen_batch()
 
 
 if __name__ == "__main__":

@@ -519,3 +519,26 @@ def test_fit_learns_and_resumes(tmp_path):
                         num_epoches=6, resume=pkg2, log=lambda s: None)
     assert pkg3["epoch"]["epoch"] == 6 and len(pkg3["loss_results"]) == 6
     assert pkg3["loss_results"][:4] == pkg["loss_results"]
+
+
+def test_assemble_batch_bit_exact(golden_dir):
+    """Device-side batch assembly == the reference's host pipeline (golden from the unmodified reference) and == the oracle on
+    a larger ragged batch; pure copies, so everything is compared with array_equal."""
+    from ctc_pytorch_b200.data import assemble_batch
+    from oracle import batch_ref
+    g = np.load(os.path.join(golden_dir, "batch_small.npz"))
+    n = int(g["n"])
+    feats = [torch.from_numpy(g["feat/%d" % i]) for i in range(n)]
+    labs = [g["label/%d" % i].tolist() for i in range(n)]
+    for ci, (left, right, skip, down) in enumerate(g["cases"].tolist()):
+        x, isz, tg, tsz = assemble_batch(feats, labs, left, right, skip, down, device=DEV)
+        assert np.array_equal(x.cpu().numpy(), g["case%d/x" % ci]), ci
+        assert np.array_equal(isz.cpu().numpy(), g["case%d/input_sizes" % ci]), ci
+        assert np.array_equal(tg.cpu().numpy(), g["case%d/targets" % ci]) and np.array_equal(tsz.cpu().numpy(), g["case%d/target_sizes" % ci])
+    rng = np.random.RandomState(9)
+    feats = [rng.randn(rng.randint(200, 801), 40).astype(np.float32) for _ in range(32)]
+    labs = [rng.randint(1, 62, size=rng.randint(1, 61)).tolist() for _ in range(32)]
+    want = batch_ref.batch(feats, labs, 1, 1, 2, 4)
+    got = assemble_batch([torch.from_numpy(f) for f in feats], labs, 1, 1, 2, 4, device=DEV)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)

@@ -253,3 +253,38 @@ def test_packed_oracle_matches_reference_live():
         pa, pb = dict(ref.named_parameters()), dict(mine.named_parameters())
         for k in pa:
             assert (pa[k].grad - pb[k].grad).abs().max().item() < 2e-5 * max(1.0, pa[k].grad.abs().max().item()), k
+
+
+# ------------------------------------------------------------------- host batch assembly (N2)
+def _batch_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "batch_small.npz"))
+    n = int(g["n"])
+    feats = [g["feat/%d" % i] for i in range(n)]
+    labs = [g["label/%d" % i] for i in range(n)]
+    return g, feats, labs
+
+
+def test_batch_oracle_matches_golden(golden_dir):
+    from oracle import batch_ref
+    g, feats, labs = _batch_golden(golden_dir)
+    for ci, (left, right, skip, down) in enumerate(g["cases"].tolist()):
+        x, isz, tg, tsz = batch_ref.batch(feats, labs, left, right, skip, down)
+        assert np.array_equal(x, g["case%d/x" % ci]) and np.array_equal(isz, g["case%d/input_sizes" % ci])
+        assert np.array_equal(tg, g["case%d/targets" % ci]) and np.array_equal(tsz, g["case%d/target_sizes" % ci])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/timit/utils"), reason="reference tree only exists in the build container")
+def test_batch_oracle_matches_reference_live():
+    import sys
+    import types
+    from oracle import batch_ref
+    sys.path.insert(0, "/root/reference/timit")
+    sys.path.insert(0, "/root/reference/timit/utils")
+    sys.modules.setdefault("kaldiio", types.ModuleType("kaldiio"))
+    import tools
+    rng = np.random.RandomState(3)
+    for left, right, skip in [(0, 0, 1), (4, 0, 1), (0, 3, 2), (2, 2, 5), (7, 7, 3)]:
+        f = rng.randn(rng.randint(1, 30), 5).astype(np.float32)
+        a = tools.skip_feat(tools.make_context(f, left, right), skip)
+        b = batch_ref.skipped(batch_ref.spliced(f, left, right), skip)
+        assert a.shape == b.shape and np.array_equal(a, b)
