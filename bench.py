@@ -302,8 +302,12 @@ def run_ours(args, cfg, rank, world):
     dsmem_out = H * 16 * 2 + (4 * 16 * 32 * 2 if dom_name == "lstm_bwd_kernel" else 0)
     sm_hz = 1965e6
     dsmem_bpc = 2.0 * dsmem_out / (dom_ms * 1e-3 / T * sm_hz) if dom_ms > 0 else 0.0
+    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/prof_lstm_r1.txt:
+    # dram__bytes_read.sum + dram__bytes_write.sum), known for the cfg2 shape only
+    ncu_traffic = {("cfg2", "lstm_bwd_kernel"): 528.6e6 + 186.5e6, ("cfg2", "lstm_fwd_kernel"): 423.7e6 + 378.5e6}
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                "frac": ach / pk["tf_sust"], "traffic": ncu_traffic.get((args.config, dom_name)),
+                "traffic_unit": "bytes per launch (ncu, profiles/prof_lstm_r1.txt)", "peak_source": pk["src"] + " (sustained bf16)",
                 "avg_launch_ms": dom_ms, "us_per_timestep": dom_ms * 1e3 / T,
                 "limiter": {"resource": "DSMEM fabric (cluster all-gather / reduce-scatter every time step)",
                             "bytes_per_timestep_per_sm_in_plus_out": 2 * dsmem_out, "achieved_B_per_clk_per_sm": dsmem_bpc,
