@@ -105,3 +105,106 @@ def synthetic_packed_batch(T, N, F_, num_class, S, seed):
     tsz = [int(v) for v in torch.randint(max(1, S // 2), S + 1, (N,), generator=g)]
     targets = torch.cat([torch.randint(1, num_class + 1, (t,), generator=g) for t in tsz]).int()
     return x, lengths, targets, tsz
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Design check for the CUDA path of N1: "alignment instead of masks". The recurrent kernels always scan all T
+# rows of a padded batch; packed semantics follow if the forward direction sees the LEFT-aligned batch and the reverse
+# direction a RIGHT-aligned copy. aligned_bilstm() emulates exactly what those kernels would compute (full-length scans,
+# arbitrary garbage in the padding rows) so that tests can compare it with the per-utterance formulation above.
+# ---------------------------------------------------------------------------------------------------------------------
+def _scan(w_ih, w_hh, x, reverse):
+    """Plain LSTM scan over all rows of x [T, N, I] (zero initial state, no bias), t = 0..T-1 or T-1..0; returns h [T, N, H]."""
+    T, N, _ = x.shape
+    H = w_hh.shape[1]
+    h = x.new_zeros(N, H)
+    c = x.new_zeros(N, H)
+    out = []
+    order = range(T - 1, -1, -1) if reverse else range(T)
+    for t in order:
+        g = x[t] @ w_ih.t() + h @ w_hh.t()
+        i, f, gg, o = g.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out.append(h)
+    if reverse:
+        out.reverse()
+    return torch.stack(out, 0)
+
+
+def right_aligned(x, lengths, fill=None):
+    """x [T, N, .] left-aligned -> frame k of utterance n at row T - len_n + k; padding rows = `fill` rows (or zeros)."""
+    T = x.shape[0]
+    out = torch.zeros_like(x) if fill is None else fill.clone()
+    for n, L in enumerate(lengths):
+        out[T - L:, n] = x[:L, n]
+    return out
+
+
+def left_aligned(x_r, lengths):
+    """Inverse of right_aligned; padding rows are zero."""
+    T = x_r.shape[0]
+    out = torch.zeros_like(x_r)
+    for n, L in enumerate(lengths):
+        out[:L, n] = x_r[T - L:, n]
+    return out
+
+
+def aligned_bilstm(rnn, x, lengths, garbage=None):
+    """Bidirectional layer output [T, N, 2H] with packed semantics, computed the way the CUDA path would: two full-length
+    scans (forward over the left-aligned batch, reverse over the right-aligned one), realignment and zeroing of the padding.
+    `garbage` [T, N, I]: what the padding rows contain (anything finite) — the result must not depend on it."""
+    T, N, _ = x.shape
+    lengths = [int(v) for v in lengths]
+    mask = (torch.arange(T).unsqueeze(1) < torch.as_tensor(lengths).unsqueeze(0)).unsqueeze(-1)
+    x_l = x if garbage is None else torch.where(mask, x, garbage)
+    h_f = _scan(rnn.weight_ih_l0, rnn.weight_hh_l0, x_l, reverse=False)
+    x_r = right_aligned(x, lengths, fill=garbage)
+    h_r = left_aligned(_scan(rnn.weight_ih_l0_reverse, rnn.weight_hh_l0_reverse, x_r, reverse=True), lengths)
+    return torch.cat([h_f * mask, h_r], dim=-1)
+
+
+def _count_bn(bn, x, n_valid, valid_mask):
+    """BatchNorm1d over rows whose padding is ZERO: the column sums over all T*N rows equal the sums over the valid rows, only
+    the divisor is the valid-frame count (biased variance for normalisation, unbiased for running_var, as torch does).
+    Output rows at padded positions are re-zeroed (BN(0) = shift is not zero)."""
+    T, N, C = x.shape
+    flat = x.reshape(T * N, C)
+    if bn.training:
+        s1, s2 = flat.sum(0), (flat * flat).sum(0)
+        mean = s1 / n_valid
+        var = s2 / n_valid - mean * mean
+        if bn.track_running_stats:
+            with torch.no_grad():
+                m = bn.momentum
+                bn.running_mean.mul_(1 - m).add_(m * mean.detach())
+                bn.running_var.mul_(1 - m).add_(m * var.detach() * n_valid / max(n_valid - 1, 1))
+                bn.num_batches_tracked.add_(1)
+    else:
+        mean, var = bn.running_mean, bn.running_var
+    y = (flat - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
+    return y.reshape(T, N, C) * valid_mask
+
+
+def aligned_model_forward(model, x, lengths, garbage_scale=0.0):
+    """RefPackedModel.forward restated the way the CUDA path of N1 is planned: dense [T, N, .] tensors with zero
+    padding, BatchNorm by column sums + valid count, the recurrent layers by aligned_bilstm, the output layer on all rows with
+    the padding re-zeroed. Must equal model(x, lengths) — tests/test_oracle.py."""
+    T, N, _ = x.shape
+    lengths = [int(v) for v in lengths]
+    n_valid = sum(lengths)
+    mask = (torch.arange(T).unsqueeze(1) < torch.as_tensor(lengths).unsqueeze(0)).unsqueeze(-1).to(x.dtype)
+    for layer in model.rnns.children():
+        if layer.batch_norm is not None:
+            x = _count_bn(layer.batch_norm.module, x, n_valid, mask)
+        garbage = garbage_scale * torch.randn_like(x) if garbage_scale else None
+        x = aligned_bilstm(layer.rnn, x, lengths, garbage=garbage)
+    fc = model.fc.module
+    if isinstance(fc, nn.Sequential):
+        x = _count_bn(fc[0], x, n_valid, mask)
+        logits = (x.reshape(T * N, -1) @ fc[1].weight.t()).reshape(T, N, -1) * mask
+    else:
+        logits = (x.reshape(T * N, -1) @ fc.weight.t()).reshape(T, N, -1) * mask
+    if not model.training:
+        return F.log_softmax(logits, dim=-1)
+    return logits

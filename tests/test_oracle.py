@@ -288,3 +288,59 @@ def test_batch_oracle_matches_reference_live():
         a = tools.skip_feat(tools.make_context(f, left, right), skip)
         b = batch_ref.skipped(batch_ref.spliced(f, left, right), skip)
         assert a.shape == b.shape and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_alignment_design_reproduces_packed_semantics(seed):
+    """full-length scans over a left-aligned (forward) and a right-aligned (reverse) batch, with arbitrary
+    finite garbage in the padding rows, give exactly the packed bidirectional LSTM — outputs and every gradient."""
+    from oracle import packed_ref
+    torch.manual_seed(seed)
+    T, N, I, H = 17, 4, 6, 5
+    lengths = [17, 12, 12, 3]
+    rnn = nn.LSTM(I, H, bidirectional=True, bias=False).double()
+    x = torch.randn(T, N, I, dtype=torch.float64)
+    for n, L in enumerate(lengths):
+        x[L:, n] = 0.0
+    x.requires_grad_(True)
+    # reference formulation: each utterance alone through torch's LSTM on its valid slice
+    want = torch.zeros(T, N, 2 * H, dtype=torch.float64)
+    for n, L in enumerate(lengths):
+        y, _ = rnn(x[:L, n:n + 1])
+        want[:L, n] = y[:, 0]
+    w = torch.randn(T, N, 2 * H, dtype=torch.float64)
+    gw = torch.autograd.grad((want * w).sum(), [x] + list(rnn.parameters()))
+    got = packed_ref.aligned_bilstm(rnn, x, lengths, garbage=3.0 * torch.randn(T, N, I, dtype=torch.float64))
+    gg = torch.autograd.grad((got * w).sum(), [x] + list(rnn.parameters()))
+    assert (got - want).abs().max().item() < 1e-12
+    for a, b in zip(gg, gw):
+        assert (a - b).abs().max().item() < 1e-11
+    # and the padding rows of the input receive no gradient at all
+    for n, L in enumerate(lengths):
+        assert gg[0][L:, n].abs().max().item() == 0.0 if L < T else True
+
+
+def test_alignment_design_full_model_matches_packed_oracle(golden_dir):
+    """The whole planned N1 composition (column-sum BatchNorm with the valid-frame count, aligned recurrent scans with garbage
+    in the padding, output layer on all rows with re-zeroed padding) equals the packed oracle — and therefore the unmodified 863
+    model, to which that oracle is pinned — in activations, loss, gradients, running statistics and eval log-probs."""
+    import copy
+    packed_ref, meta, g, m = _packed_golden(golden_dir)
+    m = m.double()
+    m2 = copy.deepcopy(m)
+    x, lens = torch.from_numpy(g["x"]).double(), g["lengths"].tolist()
+    tg, tsz = torch.from_numpy(g["targets"]), g["target_sizes"].tolist()
+    m.train(); m2.train()
+    a = m(x, lens)
+    b = packed_ref.aligned_model_forward(m2, x, lens, garbage_scale=2.0)
+    assert (a - b).abs().max().item() < 1e-10
+    la = packed_ref.warp_ctc_loss(a, tg, lens, tsz); la.backward()
+    lb = packed_ref.warp_ctc_loss(b, tg, lens, tsz); lb.backward()
+    assert abs(la.item() - lb.item()) < 1e-10 * abs(la.item())
+    for (k, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
+        assert (p.grad - q.grad).abs().max().item() < 1e-9 * max(1.0, p.grad.abs().max().item()), k
+    for (k, u), (_, v) in zip(m.named_buffers(), m2.named_buffers()):
+        assert torch.allclose(u.double(), v.double(), atol=1e-12), k
+    m.eval(); m2.eval()
+    with torch.no_grad():
+        assert (m(x, lens) - packed_ref.aligned_model_forward(m2, x, lens)).abs().max().item() < 1e-10
