@@ -2,15 +2,19 @@
 """Benchmark of the CTC acoustic hot path (BASELINE.json: utterances/sec at T=800, N=32, feat=40, C=62).
 
     python bench.py --gpus 1 --steps K --warmup W            # our arm (sm_100a kernels through the C ABI)
-    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path on the host cores
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference's own CPU path on the host cores
 
-One "step" = one pass of the training hot path of timit/steps/train_ctc.py:44-65 over one synthetic batch of the
-named shape (cfg2: 4 x BiLSTM-512 + BatchNorm, T=800, N=32 per GPU): forward, CTC loss / batch, frame arg-max +
-collapse, backward, (N>1: one all-reduce of the flat gradient bucket), Adam step.
+One "step" = one pass of the training hot loop of timit/steps/train_ctc.py:44-65 over one synthetic batch of the named
+shape (default cfg2: 4 x BiLSTM-512 + BatchNorm, T=800, N=32 per GPU): forward, CTC loss / batch, frame arg-max + collapse +
+edit distance (compute_wer), backward, (N>1: gradient all-reduce, bucketed per layer and overlapped with the backward pass),
+Adam step.
   value  utterances/s with the batch already resident in HBM;
-  e2e    the same step driven through the public classes with HOST buffers: pinned H2D of features / labels /
-         lengths and D2H of the loss and the collapsed arg-max labels inside the timed region.
-Weak scaling: every rank processes its own N=32 shard. Prints ONE JSON line on rank 0.
+  e2e    the same step driven through the public classes with HOST buffers: pinned H2D of features / labels / lengths and
+         D2H of the loss and the (errors, tokens) pair inside the timed region.
+Default: weak scaling of cfg2 (every rank its own N=32 shard). Every run also measures SURVEY.md §8(e)'s partitioning
+(cfg4, N=64 sharded N/G per rank: strong scaling) as the secondary `strong_cfg4` object; `--scaling strong` makes that the
+headline instead. `--precision x3` selects the split-bf16 (3-product) operand mode whose gradients meet the fp32 1e-3 bar.
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -26,12 +30,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
-CFG = {
-    "cfg1": dict(T=800, N=4, F=40, C=62, H=256, L=2, S=60),
-    "cfg2": dict(T=800, N=32, F=40, C=62, H=512, L=4, S=60),
-    "cfg4": dict(T=1200, N=64, F=40, C=48, H=640, L=5, S=100),
-}
-# algorithmic FLOPs of the recurrent product per launch: 2 dirs * T * 2*4H*H*N
+from ctc_pytorch_b200 import synth  # noqa: E402
+
+CFG = synth.CONFIGS
 
 
 def peaks():
@@ -41,6 +42,18 @@ def peaks():
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def ncu_traffic(config, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summary."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    d = json.load(open(path))
+    ent = d.get(config, {}).get(kernel)
+    if not ent:
+        return None, None
+    return ent["dram_bytes"], ent.get("source")
 
 
 class ClockSampler(object):
@@ -95,76 +108,85 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_batch(cfg, seed):
-    from oracle.model_ref import synthetic_batch  # input generator only (seeded synthetic fbank batch)
-    return synthetic_batch(cfg["T"], cfg["N"], cfg["F"], cfg["C"], cfg["S"], seed)
+def make_batch(cfg, seed, lo=0, hi=None):
+    """Seeded synthetic batch of the config's global shape; [lo, hi) selects a rank's shard of the padded batch."""
+    x, frac, tg, tl = synth.synthetic_batch(cfg["T"], cfg["N"], cfg["F"], cfg["C"], cfg["S"], seed)
+    hi = cfg["N"] if hi is None else hi
+    return tuple(t[lo:hi].contiguous() for t in (x, frac, tg, tl))
 
 
-def rnn_param(cfg):
-    return {"rnn_input_size": cfg["F"], "rnn_hidden_size": cfg["H"], "rnn_layers": cfg["L"], "rnn_type": nn.LSTM,
-            "bidirectional": True, "batch_norm": True}
+def workload_name(name, cfg, per_gpu):
+    return "%s: T=%d N=%d/GPU feat=%d C=%d %s%dxBiLSTM-%d+BN" % (
+        name, cfg["T"], per_gpu, cfg["F"], cfg["C"], "2xConv2d+" if cfg.get("cnn") else "", cfg["L"], cfg["H"])
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
 def cpu_threads():
     """Threads for the CPU arm. Measured on the GPU box's host (128 logical CPUs, profiles/cpu_thread_scaling_r1.txt):
     the reference's nn.LSTM step peaks at 16 intra-op threads (3.3 utt/s) and gets slower beyond (1.6 at 32, 0.6 at
-    64), so 16 is "all the threads it can use"."""
+    64), so 16 is "all the threads it can use"; CTCB200_CPU_THREADS overrides."""
+    env = os.environ.get("CTCB200_CPU_THREADS")
+    if env:
+        return max(1, int(env))
     return max(1, min(16, os.cpu_count() or 1))
 
 
-def cpu_reference_step_rate(cfg, n_utts, steps, warmup, threads):
-    """The reference's CPU implementation of the path (nn.LSTM / BatchNorm1d / Linear / LogSoftmax / nn.CTCLoss /
-    arg-max + collapse, composed as timit/models/model_ctc.py and train_ctc.py:44-65 compose them), restated in
-    oracle/model_ref.py because /root/reference does not travel to the GPU box. Bounded sample: n_utts utterances."""
-    from oracle.model_ref import RefAcousticModel
-    from oracle import decode_ref
+def reference_step_rate(cfg, steps, warmup, threads, budget_s):
+    """The reference's own CPU path, unmodified: models/model_ctc.py CTC_Model + nn.CTCLoss(reduction='sum') + torch.optim.Adam
+    driven by steps/train_ctc.py's run_epoch (forward, loss / batch, .item(), arg-max, compute_wer, zero_grad, backward,
+    optimizer step), imported through oracle/ref_shim.py from /root/reference or its byte-for-byte staged copy oracle/_ref/
+    (oracle/build_ref.py). One run_epoch call over a one-batch iterator = one step of the loop. Returns
+    (utt/s, s/step, steps actually timed, source)."""
+    from oracle import ref_shim
+    ref = ref_shim.load()
+    run_epoch = ref_shim.load_train_loop()
     torch.set_num_threads(threads)
-    sub = dict(cfg, N=n_utts)
     torch.manual_seed(0)
-    model = RefAcousticModel(cfg["F"], cfg["H"], cfg["L"], cfg["C"], batch_norm=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.005)
-    loss_fn = nn.CTCLoss(reduction="sum")
-    x, frac, tg, tl = make_batch(sub, 1)
-    model.train()
-
-    def step():
-        out = model(x)
-        il = (frac * out.shape[0]).long()
-        loss = loss_fn(out, tg, il, tl) / n_utts
-        _ = loss.item()
-        idx = out.detach().argmax(-1).t().numpy()
-        for n in range(n_utts):
-            decode_ref.collapse(idx[n, :int(il[n])])
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-    for _ in range(warmup):
-        step()
+    model = ref.CTC_Model(**synth.model_kwargs(cfg))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.005)   # train_ctc.py:145 with conf/ctc_config.yaml
+    loss_fn = nn.CTCLoss(reduction="sum")                                     # train_ctc.py:144
+    batches = []
+    for b in range(2):
+        x, frac, tg, tl = make_batch(cfg, 1 + b)
+        batches.append((x, frac, tg, tl, ["utt%d" % i for i in range(x.shape[0])]))
+    cpu = torch.device("cpu")
+    t_begin = time.perf_counter()
+    for w in range(warmup):
+        run_epoch(0, model, [batches[w % 2]], loss_fn, cpu, optimizer=opt, print_every=10 ** 9, is_training=True)
+        if time.perf_counter() - t_begin > 0.4 * budget_s:
+            break
+    done = 0
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
+    for k in range(steps):
+        run_epoch(1, model, [batches[k % 2]], loss_fn, cpu, optimizer=opt, print_every=10 ** 9, is_training=True)
+        done += 1
+        if time.perf_counter() - t_begin > budget_s and done >= 3:
+            break
     dt = time.perf_counter() - t0
-    return n_utts * steps / dt, dt / steps
+    src = "oracle/_ref (staged copy of the unmodified reference)" if ref_shim.is_staged_copy() else "/root/reference"
+    return cfg["N"] * done / dt, dt / done, done, src
 
 
-def run_reference(args, cfg, rank, world):
+def run_reference(args, name, cfg, rank, world):
     if rank != 0:
         return
+    from oracle import ref_shim
+    if not ref_shim.available():
+        emit({"impl": "reference", "unavailable": "reference modules not staged: run __graft_entry__.build() where "
+                                                  "/root/reference is mounted (oracle/build_ref.py)"})
+        return
     cores = cpu_threads()
-    n_utts = 2
-    warm = min(args.warmup, 1)
-    rate, sec = cpu_reference_step_rate(cfg, n_utts, max(1, args.steps), warm, cores)
+    budget = float(os.environ.get("CTCB200_REF_BUDGET_S", "420"))
+    rate, sec, done, src = reference_step_rate(cfg, max(1, args.steps), args.warmup, cores, budget)
+    sample = "full %s batches (N=%d utterances per step), %d timed steps, %d threads; unmodified run_epoch + CTC_Model from %s" % (
+        name, cfg["N"], done, cores, src)
     line = {
         "impl": "reference", "metric": "utterances/sec (training step)", "value": rate, "unit": "utt/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3,
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: T=%d feat=%d C=%d %dxBiLSTM-%d+BN, CTC, greedy, Adam" % (
-            args.config, cfg["T"], cfg["F"], cfg["C"], cfg["L"], cfg["H"]), "per_step_sample_utts": n_utts},
-        "cpu_baseline": {"value": rate, "unit": "utt/s", "cores": cores, "kind": "port",
-                         "sample": "%d utterances of the %s shape per step (torch CPU kernels, %d threads); the reference "
-                                   "tree is not on the GPU box so its composition is restated in oracle/model_ref.py" % (
-                                       n_utts, args.config, cores)},
+        "config": {"workload": workload_name(name, cfg, cfg["N"]) + "; fwd + CTC loss + arg-max/collapse/edit distance + bwd + Adam",
+                   "global_batch": cfg["N"], "host_threads": cores, "steps_requested": args.steps},
+        "cpu_baseline": {"value": rate, "unit": "utt/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": rate, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -172,96 +194,145 @@ def run_reference(args, cfg, rank, world):
 
 
 # -------------------------------------------------------------------------------------------------------- our arm
-def run_ours(args, cfg, rank, world):
-    from ctc_pytorch_b200 import _lib, ops
-    from ctc_pytorch_b200.model import CTC_Model
-    from ctc_pytorch_b200.loss import CTCLoss
-    from ctc_pytorch_b200.dist import GradBucket
+class Job(object):
+    """Model + optimizer + batches of one (config, shard) on this rank's GPU, and the step function."""
+
+    def __init__(self, name, cfg, rank, world, dev, precision, strong, n_batches=4):
+        from ctc_pytorch_b200.model import CTC_Model
+        from ctc_pytorch_b200.loss import CTCLoss
+        from ctc_pytorch_b200.dist import GradSync, shard_range
+        self.name, self.cfg, self.dev, self.world = name, cfg, dev, world
+        if strong:
+            self.lo, self.hi = shard_range(cfg["N"], rank, world)
+        else:
+            self.lo, self.hi = 0, cfg["N"]
+        self.n_local = self.hi - self.lo
+        self.n_global = cfg["N"] if strong else cfg["N"] * world
+        torch.manual_seed(0)
+        self.model = CTC_Model(**synth.model_kwargs(cfg)).to(dev)
+        self.model.precision = precision
+        # the reference's optimizer (train_ctc.py:145: Adam + L2 weight decay), torch's single-launch (fused) implementation
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3, weight_decay=0.005, fused=True)
+        self.loss_fn = CTCLoss(reduction="sum")
+        # strong scaling: every rank's loss is divided by ITS shard size (train_ctc.py:48), so the full-batch gradient is the
+        # shard-size-weighted mean of the rank gradients
+        weight = (self.n_local * world / float(self.n_global)) if strong else 1.0
+        self.sync = GradSync(weight=weight) if world > 1 else None
+        self.model.grad_sync = self.sync
+        self.model.train()
+        self.host = []
+        for b in range(n_batches):
+            seed = (100 * rank + b) if not strong else (1000 + b)
+            hb = make_batch(cfg, seed, self.lo, self.hi)
+            self.host.append(tuple(t.pin_memory() for t in hb))
+        self.devb = [tuple(t.to(dev) for t in hb) for hb in self.host]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
+        self.wer_acc = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def step(self, b, fetch=False, comm=True):
+        from ctc_pytorch_b200 import ops
+        x, frac, tg, tl = b
+        model = self.model
+        model.grad_sync = self.sync if comm else None
+        out = model(x)
+        out_len, bsz, _ = out.size()
+        il = (frac * out_len).long()
+        loss = self.loss_fn(out, tg, il, tl) / bsz
+        # train_ctc.py:51-52: arg-max + compute_wer (collapse + edit distance), here on the device
+        _, labels, lens = ops.greedy_decode(out, il, blank=0)
+        dist_ = ops.edit_distance(labels, lens, tg, tl)
+        self.wer_acc[0] += dist_.sum()
+        self.wer_acc[1] += tl.sum()
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()        # with grad_sync set, the per-layer all-reduces are launched and joined inside the backward pass
+        self.opt.step()
+        if fetch:
+            return loss.item(), self.wer_acc.cpu()
+        return loss
+
+
+def timed_loop(job, steps, flush, world, e2e):
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(steps):
+        if e2e:
+            hb = job.host[k % len(job.host)]
+            b = tuple(t.to(job.dev, non_blocking=True) for t in hb)
+            job.step(b, fetch=True)
+        else:
+            flush.zero_()  # L2 flush between steps (counted inside the timed region: ~0.03 ms)
+            job.step(job.devb[k % len(job.devb)])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=job.dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def run_ours(args, name, cfg, rank, world):
+    from ctc_pytorch_b200 import _lib
     import torch.distributed as dist
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     L = _lib.lib()
-    T, N, F, C, H, Lyr = cfg["T"], cfg["N"], cfg["F"], cfg["C"], cfg["H"], cfg["L"]
-
-    torch.manual_seed(0)
-    model = CTC_Model(rnn_param=rnn_param(cfg), num_class=C, drop_out=0.0).to(dev)
-    # the reference's optimizer (train_ctc.py:145: Adam + L2 weight decay), torch's single-launch (fused) implementation
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.005, fused=True)
-    loss_fn = CTCLoss(reduction="sum")
-    bucket = GradBucket(model.parameters())
-    model.train()
-
-    # several distinct host batches (pinned); the device-resident loop cycles over copies in HBM
-    n_batches = 4
-    host = []
-    for b in range(n_batches):
-        x, frac, tg, tl = make_batch(cfg, 100 * rank + b)
-        host.append(tuple(t.pin_memory() for t in (x, frac, tg, tl)))
-    devb = [tuple(t.to(dev) for t in hb) for hb in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
-    # L2 flush buffer (larger than the 126 MB L2) written between timed steps of the device-resident loop
-    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def step_dev(b, fetch=False, comm=True):
-        x, frac, tg, tl = b
-        out = model(x)
-        out_len, bsz, _ = out.size()
-        il = (frac * out_len).long()
-        loss = loss_fn(out, tg, il, tl) / bsz
-        _, labels, lens = ops.greedy_decode(out, il, blank=0)
-        bucket.attach()
-        loss.backward()
-        if comm:
-            bucket.allreduce_mean()
-        opt.step()
-        if fetch:
-            return loss.item(), labels.cpu(), lens.cpu()
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for w in range(max(args.warmup, 3)):
-        step_dev(devb[w % n_batches])
-    barrier()
+    strong = args.scaling == "strong"
+    job = Job(name, cfg, rank, world, dev, args.precision, strong)
+    T, F, C, H, Lyr = cfg["T"], cfg["F"], cfg["C"], cfg["H"], cfg["L"]
+    N = job.n_local
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # larger than the 126 MB L2
+    warm = max(args.warmup, 3)
+    for w in range(warm):
+        job.step(job.devb[w % len(job.devb)])
 
     # ---- timed region 1: inputs resident in HBM ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = L.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        flush.zero_()  # L2 flush between steps (counted inside the timed region: ~0.03 ms)
-        step_dev(devb[k % n_batches])
-    e1.record()
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
+    ms_dev = timed_loop(job, args.steps, flush, world, e2e=False)
     launches = L.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
-
     # ---- timed region 2: end to end from host buffers ----
-    barrier()
-    d2h_bytes = 4 + N * T * 4 + N * 4
-    e0.record()
-    for k in range(args.steps):
-        hb = host[k % n_batches]
-        b = tuple(t.to(dev, non_blocking=True) for t in hb)
-        step_dev(b, fetch=True)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = timed_loop(job, args.steps, flush, world, e2e=True)
+    d2h_bytes = 4 + 16
 
-    t_dev = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = t_dev.tolist()
+    # ---- secondary measurements (all ranks take part in the collectives) ----
+    other_precision = None
+    if args.both_precisions:
+        alt = "x3" if args.precision == "bf16" else "bf16"
+        job.model.precision = alt
+        for w in range(3):
+            job.step(job.devb[w % len(job.devb)])
+        k_alt = max(3, min(args.steps, 6))
+        ms_alt = timed_loop(job, k_alt, flush, world, e2e=False)
+        job.model.precision = args.precision
+        other_precision = {"precision": alt, "ms_per_step": ms_alt / k_alt, "value": job.n_global * k_alt / (ms_alt * 1e-3),
+                           "unit": "utt/s", "steps": k_alt}
+    strong_line = None
+    if args.strong_cfg4 and not strong and not (name == "cfg4"):
+        c4 = CFG["cfg4"]
+        job4 = Job("cfg4", c4, rank, world, dev, args.precision, True, n_batches=2)
+        for w in range(3):
+            job4.step(job4.devb[w % 2])
+        k4 = max(3, min(args.steps, 5))
+        ms4 = timed_loop(job4, k4, flush, world, e2e=False)
+        strong_line = {"config": workload_name("cfg4", c4, job4.n_local), "scaling": "strong", "global_batch": c4["N"],
+                       "per_gpu_batch": job4.n_local, "n_gpus": world, "steps": k4, "ms_per_step": ms4 / k4,
+                       "value": c4["N"] * k4 / (ms4 * 1e-3), "unit": "utt/s",
+                       "limiter": "the recurrence is latency-bound: T*L dependent time steps per pass cost the same for 8 as for "
+                                  "64 utterances per GPU, so sharding the batch only shrinks the GEMM / streaming part of the step"}
+        del job4
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return
@@ -269,69 +340,70 @@ def run_ours(args, cfg, rank, world):
     per_call = {}
     orig_call = L.call
 
-    def timed_call(name, *a):
+    def timed_call(nm, *a):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        r = orig_call(name, *a)
+        r = orig_call(nm, *a)
         e.record()
-        per_call.setdefault(name, []).append((s, e))
+        per_call.setdefault(nm, []).append((s, e))
         return r
     L.call = timed_call
     prof_steps = 3
-    overlap_was = model.overlap_wgrad
-    model.overlap_wgrad = False  # kernels timed one at a time on one stream (the timed steps above overlap the wgrad GEMMs)
+    overlap_was = job.model.overlap_wgrad
+    job.model.overlap_wgrad = False  # kernels timed one at a time on one stream (the timed steps above overlap the wgrad GEMMs)
     for k in range(prof_steps):
         flush.zero_()
-        step_dev(devb[k % n_batches], comm=False)  # rank 0 only: no collective in this diagnostic pass
+        job.step(job.devb[k % len(job.devb)], comm=False)  # rank 0 only: no collective in this diagnostic pass
     torch.cuda.synchronize()
     L.call = orig_call
-    model.overlap_wgrad = overlap_was
+    job.model.overlap_wgrad = overlap_was
     kern_ms = {nm: sum(s.elapsed_time(e) for s, e in v) / prof_steps for nm, v in per_call.items()}
     kern_cnt = {nm: len(v) // prof_steps for nm, v in per_call.items()}
     step_ms_prof = sum(kern_ms.values())
 
     pk = peaks()
+    Tr = T // 2 if cfg.get("cnn") else T     # frames the recurrence runs over (the CNN front halves the time axis)
     # dominant kernels: the persistent recurrent kernels (tensor-core work, latency bound by the per-step hand-off)
-    rec_flops_launch = 2.0 * T * 2 * 4 * H * H * N           # one layer, both directions
+    prods = 3.0 if args.precision == "x3" else 1.0
+    rec_flops_launch = 2.0 * Tr * 2 * 4 * H * H * N           # algorithmic: one layer, both directions (x3 mode issues 3x this)
     fwd_ms = kern_ms.get("ctcb200_lstm_fwd", 0.0) / max(1, kern_cnt.get("ctcb200_lstm_fwd", 1))
     bwd_ms = kern_ms.get("ctcb200_lstm_bwd", 0.0) / max(1, kern_cnt.get("ctcb200_lstm_bwd", 1))
     dom_name, dom_ms = ("lstm_bwd_kernel", bwd_ms) if bwd_ms >= fwd_ms else ("lstm_fwd_kernel", fwd_ms)
     ach = rec_flops_launch / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    # What actually bounds the recurrent kernels is the SM-to-SM (DSMEM) fabric: per time step every CTA receives and sends
-    # the whole operand image of its cluster (fwd: H*16*2 B of h_t; BPTT: the same of dG plus the fp16 gate partials).
-    dsmem_out = H * 16 * 2 + (4 * 16 * 32 * 2 if dom_name == "lstm_bwd_kernel" else 0)
-    sm_hz = 1965e6
-    dsmem_bpc = 2.0 * dsmem_out / (dom_ms * 1e-3 / T * sm_hz) if dom_ms > 0 else 0.0
-    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/prof_lstm_r1.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum), known for the cfg2 shape only
-    ncu_traffic = {("cfg2", "lstm_bwd_kernel"): 528.6e6 + 186.5e6, ("cfg2", "lstm_fwd_kernel"): 423.7e6 + 378.5e6}
+    traffic, traffic_src = ncu_traffic(name, dom_name)
+    dsmem = None
+    p_dsmem = os.path.join(ROOT, "profiles", "dsmem_microbench.json")
+    if os.path.exists(p_dsmem):
+        dsmem = json.load(open(p_dsmem))
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sust"], "traffic": ncu_traffic.get((args.config, dom_name)),
-                "traffic_unit": "bytes per launch (ncu, profiles/prof_lstm_r1.txt)", "peak_source": pk["src"] + " (sustained bf16)",
-                "avg_launch_ms": dom_ms, "us_per_timestep": dom_ms * 1e3 / T,
-                "limiter": {"resource": "DSMEM fabric (cluster all-gather / reduce-scatter every time step)",
-                            "bytes_per_timestep_per_sm_in_plus_out": 2 * dsmem_out, "achieved_B_per_clk_per_sm": dsmem_bpc,
-                            "peak_B_per_clk_per_sm": 17.0, "frac": dsmem_bpc / 17.0,
-                            "peak_source": "B300_MICROARCH.md: 17 B/clk bidirectional per SM (measured on sm_103a), SM clock 1965 MHz"},
-                "note": "recurrence: T dependent steps per launch, each moving the cluster's operand image between all CTAs; "
-                        "tensor-pipe fraction reported for the contract, the DSMEM fraction is the binding one (DESIGN.md 3.2)"}
+                "frac": ach / pk["tf_sust"], "traffic": traffic,
+                "traffic_unit": "bytes per launch (%s)" % (traffic_src or "no ncu capture for this config"),
+                "peak_source": pk["src"] + " (sustained bf16)", "avg_launch_ms": dom_ms, "us_per_timestep": dom_ms * 1e3 / Tr,
+                "tensor_products_per_algorithmic_flop": prods,
+                "note": "recurrence: T dependent steps per launch; each step is a cluster-wide hand-off of h_t / dG_t "
+                        "(DSMEM bulk copies + mbarriers) around a [4H x H] x [H x 16] product, so the kernel is latency-bound, "
+                        "not tensor-bound (DESIGN.md 3.2); the dense GEMMs' fraction is under rooflines_other"}
+    if dsmem:
+        roofline["dsmem_microbench"] = dsmem
     # secondary rooflines: all dense GEMM launches together, and the CTC alpha/beta sweep
-    rows = T * N
+    rows = Tr * N
     gemm_flops = 0.0
+    I0 = (32 * 10) if cfg.get("cnn") else F
     for l in range(Lyr):
-        I = F if l == 0 else 2 * H
-        gemm_flops += 2.0 * rows * 8 * H * I * (3 if l > 0 else 2)   # Gx, dWih (+ dX for l>0)
+        I = I0 if l == 0 else 2 * H
+        gemm_flops += 2.0 * rows * 8 * H * I * (3 if (l > 0 or cfg.get("cnn")) else 2)   # Gx, dWih (+ dX)
         gemm_flops += 2.0 * rows * 8 * H * H                          # dWhh (both directions)
     gemm_flops += 3 * 2.0 * rows * 2 * H * C
     gemm_ms = kern_ms.get("ctcb200_gemm_tn_bf16", 0.0)
-    ctc_bytes = 2.0 * T * N * C * 4
+    ctc_bytes = 2.0 * Tr * N * C * 4
     ctc_ms = kern_ms.get("ctcb200_ctc_loss_fwd", 0.0) + kern_ms.get("ctcb200_ctc_loss_bwd", 0.0)
     extra = {
         "gemm_all": {"bound": "tensor", "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
-                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "ms_per_step": gemm_ms},
+                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "ms_per_step": gemm_ms,
+                     "note": "algorithmic flops of the RNN-stack contractions; x3 mode issues 3 tensor products per flop"},
         "ctc_alpha_beta": {"bound": "hbm", "achieved": ctc_bytes / (ctc_ms * 1e-3) / 1e9 if ctc_ms else None,
                            "peak": pk["hbm"], "unit": "GB/s", "ms_per_step": ctc_ms,
-                           "note": "N=32 is latency-bound (T dependent steps per warp)"},
+                           "note": "N=32 is latency-bound (T dependent steps per warp); saturating-batch sweep: profiles/ctc_sweep_r2.json"},
         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
         "kernel_share_of_step": {k: round(v / step_ms_prof, 4) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
     }
@@ -339,31 +411,46 @@ def run_ours(args, cfg, rank, world):
         if extra[k]["achieved"]:
             extra[k]["frac"] = extra[k]["achieved"] / extra[k]["peak"]
 
-    # ---- CPU baseline on the host cores (bounded sample) ----
+    # ---- CPU baseline on the host cores: the unmodified reference on a bounded sample (2 full-size steps after 1 warm-up) ----
     cores = cpu_threads()
-    cpu_rate, cpu_sec = cpu_reference_step_rate(cfg, 2, 2, 1, cores)
+    cpu_base = None
+    if not args.no_cpu_baseline:
+        from oracle import ref_shim
+        if ref_shim.available():
+            rate, sec, done, src = reference_step_rate(cfg, 2, 1, cores, 90.0)
+            cpu_base = {"value": rate, "unit": "utt/s", "cores": cores, "kind": "reference",
+                        "sample": "%d timed steps of full %s batches (N=%d) after 1 warm-up step; unmodified run_epoch + CTC_Model "
+                                  "from %s" % (done, name, cfg["N"], src)}
+        else:
+            cpu_base = {"value": None, "unit": "utt/s", "cores": cores, "kind": "reference",
+                        "sample": "unavailable: reference modules not staged (oracle/build_ref.py)"}
 
-    total_utts = N * world * args.steps
+    total_utts = job.n_global * args.steps
     line = {
         "metric": "utterances/sec (training step)", "value": total_utts / (ms_dev * 1e-3), "unit": "utt/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "%s: T=%d N=%d/GPU feat=%d C=%d %dxBiLSTM-%d+BN; fwd + CTC loss + arg-max/collapse + bwd"
-                               "%s + Adam" % (args.config, T, N, F, C, Lyr, H, " + grad all-reduce" if world > 1 else ""),
-                   "global_batch": N * world, "parallelism": "dp%d" % world,
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "data": "synthetic",
+        "config": {"workload": workload_name(name, cfg, N) + "; fwd + CTC loss + arg-max/collapse/edit distance + bwd"
+                               "%s + Adam" % (" + per-layer gradient all-reduce" if world > 1 else ""),
+                   "global_batch": job.n_global, "parallelism": "dp%d" % world,
                    "timing": "CUDA events, max over ranks, 192 MiB L2 flush write between timed steps",
-                   "numerics": "bf16 tensor-core operands, fp32 accumulate/state/loss"},
-        "e2e": {"value": total_utts / (ms_e2e * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": h2d_bytes,
+                   "numerics": ("bf16 tensor-core operands, fp32 accumulate/state/loss" if args.precision == "bf16" else
+                                "split-bf16 operands (hi+lo, 3 tensor-core products per contraction), fp32 accumulate/state/loss")},
+        "e2e": {"value": total_utts / (ms_e2e * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": job.h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
-                "note": "pinned H2D of x/frac/targets/lengths + D2H of loss and collapsed arg-max labels each step"},
+                "note": "pinned H2D of x/frac/targets/lengths + D2H of the loss and the (errors, tokens) pair each step"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
         "rooflines_other": extra,
-        "cpu_baseline": {"value": cpu_rate, "unit": "utt/s", "cores": cores, "kind": "port",
-                         "sample": "2 utterances x 2 steps of the same shape, torch CPU kernels (%d threads); "
-                                   "oracle/model_ref.py restates the reference's composition" % cores},
     }
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    if other_precision is not None:
+        line["other_precision"] = other_precision
+    if strong_line is not None:
+        line["strong_cfg4"] = strong_line
     emit(line)
 
 
@@ -371,8 +458,8 @@ _REAL_STDOUT = None
 
 
 def quiet_stdout():
-    """Route fd 1 to stderr while the run is in progress (NCCL and friends print banners on stdout from C); the one
-    JSON line goes to the real stdout through emit()."""
+    """Route fd 1 to stderr while the run is in progress (NCCL, the reference's run_epoch and friends print on stdout);
+    the one JSON line goes to the real stdout through emit()."""
     global _REAL_STDOUT
     if _REAL_STDOUT is None:
         sys.stdout.flush()
@@ -396,9 +483,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CFG))
+    ap.add_argument("--config", default=None, choices=sorted(CFG))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "x3"])
+    ap.add_argument("--both-precisions", dest="both_precisions", type=int, default=1,
+                    help="also time a few steps in the other operand mode (other_precision object)")
+    ap.add_argument("--strong-cfg4", dest="strong_cfg4", type=int, default=1,
+                    help="also measure cfg4 sharded N/G per rank (strong_cfg4 object)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    cfg = CFG[args.config]
+    name = args.config or ("cfg4" if args.scaling == "strong" else "cfg2")
+    cfg = CFG[name]
     wd = int(os.environ.get("BENCH_WATCHDOG", "0"))
     if wd > 0:  # debugging aid: dump every thread's stack if the run is still alive after `wd` seconds
         import faulthandler
@@ -406,10 +501,10 @@ def main():
     from ctc_pytorch_b200.dist import init_from_env
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
-        run_reference(args, cfg, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        run_reference(args, name, cfg, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
     rank, world = init_from_env()
-    run_ours(args, cfg, rank, world)
+    run_ours(args, name, cfg, rank, world)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -5,6 +5,7 @@ the ABI. There is deliberately no fallback: if the shared object is missing or a
 caller gets a RuntimeError — the product path never silently degrades to PyTorch or CPU code.
 """
 import ctypes
+import functools
 import os
 import re
 
@@ -106,7 +107,24 @@ def ptr(t):
 
 
 def stream():
+    """Current stream of the CURRENT device: every public entry point runs under `on_tensor_device`, which makes the
+    tensors' device current first, so the launch, its stream and the library's per-device state always agree."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_tensor_device(fn):
+    """Decorator: run `fn` with the device of its first CUDA tensor argument as the current CUDA device (a model on cuda:1
+    while cuda:0 is current would otherwise launch on the wrong device / stream)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        for a in list(args) + list(kw.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kw)
+        return fn(*args, **kw)
+    return wrapper
 
 
 def require_cuda(*tensors):

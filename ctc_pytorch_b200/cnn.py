@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from . import _lib
 from . import ops
-from .model import _bn_prepare, _call, _round_up
+from .model import _bn_prepare, _call, _dropout_mask, _inv_keep, _round_up
 
 
 def _geometry(conv, Hi, Wi):
@@ -89,8 +89,8 @@ class _ConvFrontFn(torch.autograd.Function):
             mask = None
             p_drop = float(block.dropout.p)
             if training and p_drop > 0.0:
-                mask = (torch.rand(out.shape, device=dev) >= p_drop).to(torch.uint8)
-                _call("ctcb200_dropout_apply", _lib.ptr(out), _lib.ptr(mask), 1.0 / (1.0 - p_drop), out.numel(), stream())
+                mask = _dropout_mask(model, out.shape, p_drop, dev)
+                _call("ctcb200_dropout_apply", _lib.ptr(out), _lib.ptr(mask), _inv_keep(p_drop), out.numel(), stream())
             if need_grad:
                 saved.append(dict(geom=geom, Cout=Cout, K=K, Kp=Kp, Coutp=Coutp, M=M, Mp=Mp, colsT=colsT, w_pT=w_pT,
                                   y=y, st=st, out=out, strides=strides, mask=mask, p_drop=p_drop))
@@ -117,7 +117,7 @@ class _ConvFrontFn(torch.autograd.Function):
             N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw = rec["geom"]
             Cout, K, M, Mp = rec["Cout"], rec["K"], rec["M"], rec["Mp"]
             if rec["mask"] is not None:
-                _call("ctcb200_dropout_apply", _lib.ptr(da), _lib.ptr(rec["mask"]), 1.0 / (1.0 - rec["p_drop"]), da.numel(),
+                _call("ctcb200_dropout_apply", _lib.ptr(da), _lib.ptr(rec["mask"]), _inv_keep(rec["p_drop"]), da.numel(),
                       stream())
             dz = torch.empty((M, Cout), dtype=torch.float32, device=dev)
             s = rec["strides"]
@@ -128,8 +128,15 @@ class _ConvFrontFn(torch.autograd.Function):
                 dgam = torch.empty(Cout, dtype=torch.float32, device=dev)
                 dbet = torch.empty(Cout, dtype=torch.float32, device=dev)
                 ws = torch.empty(2 * Cout, dtype=torch.float64, device=dev)
-                _call("ctcb200_bn_bwd", _lib.ptr(dz), _lib.ptr(rec["y"]), _lib.ptr(rec["st"].mean), _lib.ptr(rec["st"].rstd),
-                      _lib.ptr(bn.weight), _lib.ptr(dz), _lib.ptr(dgam), _lib.ptr(dbet), M, Cout, _lib.ptr(ws), stream())
+                st = rec["st"]
+                if st.batch:
+                    _call("ctcb200_bn_bwd", _lib.ptr(dz), _lib.ptr(rec["y"]), _lib.ptr(st.mean), _lib.ptr(st.rstd),
+                          _lib.ptr(bn.weight), _lib.ptr(dz), _lib.ptr(dgam), _lib.ptr(dbet), M, Cout, _lib.ptr(ws), stream())
+                else:   # frozen statistics (eval-mode fine-tuning): dx = gamma * rstd * dy
+                    coef = torch.empty(3 * Cout, dtype=torch.float32, device=dev)
+                    _call("ctcb200_bn_bwd_coef", _lib.ptr(dz), _lib.ptr(rec["y"]), _lib.ptr(st.mean), _lib.ptr(st.rstd),
+                          _lib.ptr(bn.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), M, Cout, _lib.ptr(ws), stream())
+                    dz.mul_(coef[:Cout])
                 grads[bn.weight], grads[bn.bias] = dgam, dbet
             conv = block.conv
             if conv.bias is not None:
@@ -141,7 +148,7 @@ class _ConvFrontFn(torch.autograd.Function):
                 torch.zeros((M, rec["Coutp"]), dtype=torch.bfloat16, device=dev)
             dyT = (torch.empty if Mp == M else torch.zeros)((Cout, Mp), dtype=torch.bfloat16, device=dev)
             _call("ctcb200_cast_transpose", _lib.ptr(dz), Cout, Cout, 1, None, None, _lib.ptr(dyb), rec["Coutp"],
-                  _lib.ptr(dyT), Mp, 1, M, Cout, stream())
+                  _lib.ptr(dyT), Mp, 1, M, Cout, 0, stream())
             dw = ops.gemm_tn(dyT, rec["colsT"], k=Mp)  # [Cout, K]
             grads[conv.weight] = dw.view(Cout, kh, kw, Cin).permute(0, 3, 1, 2).contiguous()
             if bi > 0:

@@ -95,15 +95,23 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t
     return OK;
 }
 
-int device_sm_count() {
-    static int sms = 0;
-    if (sms) return sms;
+int current_device() {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+
+int device_sm_count() {
+    static int sms[MAX_DEVICES] = {0};   // per device ordinal (a process may drive several GPUs)
+    const int dev = current_device();
+    if (sms[dev]) return sms[dev];
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    sms = v;
-    return sms;
+    sms[dev] = v;
+    return v;
 }
 
 }  // namespace ctcb200

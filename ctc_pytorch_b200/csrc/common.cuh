@@ -50,6 +50,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 int make_tmap_f32_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                      uint32_t box_rows, uint32_t box_cols);
 
+// Per-device host-side state (function attributes, probe caches, SM counts) is indexed by the CUDA device ordinal.
+constexpr int MAX_DEVICES = 64;
+int current_device();
 int device_sm_count();
 
 }  // namespace ctcb200

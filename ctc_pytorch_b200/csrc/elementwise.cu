@@ -17,6 +17,18 @@
 namespace ctcb200 {
 namespace {
 
+// part 0: the bf16 rounding of v; part 1: the bf16 rounding of what part 0 lost (split-operand "x3" mode)
+__device__ __forceinline__ __nv_bfloat16 bf16_part(float v, int part) {
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    return part ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
+}
+__device__ __forceinline__ __nv_bfloat162 bf16x2_part(float a, float b, int part) {
+    __nv_bfloat162 r;
+    r.x = bf16_part(a, part);
+    r.y = bf16_part(b, part);
+    return r;
+}
+
 __device__ __forceinline__ int packed_to_orig_row(int p, int H) {
     // packed gate row p = j*128 + ul*4 + q  ->  torch row q*H + 32 j + ul
     const int j = p >> 7, ul = (p & 127) >> 2, q = p & 3;
@@ -27,7 +39,7 @@ __global__ void pack_lstm_weights_kernel(const float* __restrict__ wih_f, const 
                                          const float* __restrict__ wih_r, const float* __restrict__ whh_r,
                                          __nv_bfloat16* __restrict__ wih_p, __nv_bfloat16* __restrict__ wihT_p,
                                          __nv_bfloat16* __restrict__ whh_p, __nv_bfloat16* __restrict__ whhT_p, int H,
-                                         int I, int Ipad) {
+                                         int I, int Ipad, int part) {
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const int G4 = 4 * H, G8 = 8 * H;
@@ -36,28 +48,28 @@ __global__ void pack_lstm_weights_kernel(const float* __restrict__ wih_f, const 
         const int R = static_cast<int>(e / Ipad), i = static_cast<int>(e % Ipad);
         const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
         const float* w = dir ? wih_r : wih_f;
-        wih_p[e] = __float2bfloat16(i < I ? w[static_cast<size_t>(orow) * I + i] : 0.0f);
+        wih_p[e] = bf16_part(i < I ? w[static_cast<size_t>(orow) * I + i] : 0.0f, part);
     }
     // wihT_p [I, 8H]
     for (long long e = tid; e < static_cast<long long>(I) * G8; e += stride) {
         const int i = static_cast<int>(e / G8), R = static_cast<int>(e % G8);
         const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
         const float* w = dir ? wih_r : wih_f;
-        wihT_p[e] = __float2bfloat16(w[static_cast<size_t>(orow) * I + i]);
+        wihT_p[e] = bf16_part(w[static_cast<size_t>(orow) * I + i], part);
     }
     // whh_p [8H, H]
     for (long long e = tid; e < static_cast<long long>(G8) * H; e += stride) {
         const int R = static_cast<int>(e / H), k = static_cast<int>(e % H);
         const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
         const float* w = dir ? whh_r : whh_f;
-        whh_p[e] = __float2bfloat16(w[static_cast<size_t>(orow) * H + k]);
+        whh_p[e] = bf16_part(w[static_cast<size_t>(orow) * H + k], part);
     }
     // whhT_p [(dir,q,m), k] = whh_dir[q*H + k][m]
     for (long long e = tid; e < static_cast<long long>(G8) * H; e += stride) {
         const int R = static_cast<int>(e / H), k = static_cast<int>(e % H);
         const int dir = R / G4, q = (R % G4) / H, m = R % H;
         const float* w = dir ? whh_r : whh_f;
-        whhT_p[e] = __float2bfloat16(w[(static_cast<size_t>(q) * H + k) * H + m]);
+        whhT_p[e] = bf16_part(w[(static_cast<size_t>(q) * H + k) * H + m], part);
     }
 }
 
@@ -66,7 +78,7 @@ __global__ void __launch_bounds__(256)
 cast_transpose_kernel(const float* __restrict__ src, long long s_outer, long long s_inner, int n_inner,
                       const float* __restrict__ scale, const float* __restrict__ shift,
                       __nv_bfloat16* __restrict__ dst, long long dst_pitch, __nv_bfloat16* __restrict__ dstT,
-                      long long dstT_pitch, int n_pad, int R, int C) {
+                      long long dstT_pitch, int n_pad, int R, int C, int part) {
     __shared__ float tile[32][33];
     const int tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
     const long long tiles = static_cast<long long>(tiles_c) * tiles_r;
@@ -83,7 +95,7 @@ cast_transpose_kernel(const float* __restrict__ src, long long s_outer, long lon
             if (r < R && c < C) {
                 v = src[static_cast<long long>(r / n_inner) * s_outer + static_cast<long long>(r % n_inner) * s_inner + c];
                 v = v * sc + sh;
-                if (dst) dst[static_cast<long long>(r) * dst_pitch + c] = __float2bfloat16(v);
+                if (dst) dst[static_cast<long long>(r) * dst_pitch + c] = bf16_part(v, part);
             }
             tile[ty + 8 * k][tx] = v;
         }
@@ -96,7 +108,7 @@ cast_transpose_kernel(const float* __restrict__ src, long long s_outer, long lon
                 // one time step stays 16-byte aligned for TMA
                 if (cc < C && rr < R)
                     dstT[static_cast<long long>(cc) * dstT_pitch + static_cast<long long>(rr / n_inner) * n_pad + rr % n_inner] =
-                        __float2bfloat16(tile[tx][ty + 8 * k]);
+                        bf16_part(tile[tx][ty + 8 * k], part);
             }
             __syncthreads();
         }
@@ -109,7 +121,7 @@ __global__ void __launch_bounds__(256)
 cast_transpose_v2_kernel(const float* __restrict__ src, long long s_outer, long long s_inner, int n_inner,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          __nv_bfloat16* __restrict__ dst, long long dst_pitch, __nv_bfloat16* __restrict__ dstT,
-                         long long dstT_pitch, int n_pad, int R, int C) {
+                         long long dstT_pitch, int n_pad, int R, int C, int part) {
     __shared__ __nv_bfloat16 tile[64][66];
     const int tiles_c = (C + 63) / 64, tiles_r = (R + 63) / 64;
     const long long tiles = static_cast<long long>(tiles_c) * tiles_r;
@@ -127,7 +139,7 @@ cast_transpose_v2_kernel(const float* __restrict__ src, long long s_outer, long 
             if (r < R && c < C) {
                 const float2 v = *reinterpret_cast<const float2*>(
                     src + static_cast<long long>(r / n_inner) * s_outer + static_cast<long long>(r % n_inner) * s_inner + c);
-                b = __floats2bfloat162_rn(v.x * sc0 + sh0, v.y * sc1 + sh1);
+                b = bf16x2_part(v.x * sc0 + sh0, v.y * sc1 + sh1, part);
                 if (dst) *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<long long>(r) * dst_pitch + c) = b;
             }
             tile[ty + 8 * k][2 * tx] = b.x;
@@ -494,14 +506,14 @@ using namespace ctcb200;
 
 extern "C" CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const float* whh_f, const float* wih_r,
                                                      const float* whh_r, void* wih_p, void* wihT_p, void* whh_p,
-                                                     void* whhT_p, int H, int I, int Ipad,
+                                                     void* whhT_p, int H, int I, int Ipad, int part,
                                                      ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(H % 32 == 0 && I > 0 && Ipad >= I && Ipad % 8 == 0, "pack_lstm_weights: bad sizes H=%d I=%d Ipad=%d", H, I, Ipad);
     const long long work = static_cast<long long>(8) * H * (Ipad > H ? Ipad : H);
     pack_lstm_weights_kernel<<<stream_grid(work, 1024), 256, 0, stream>>>(
         wih_f, whh_f, wih_r, whh_r, static_cast<__nv_bfloat16*>(wih_p), static_cast<__nv_bfloat16*>(wihT_p),
-        static_cast<__nv_bfloat16*>(whh_p), static_cast<__nv_bfloat16*>(whhT_p), H, I, Ipad);
+        static_cast<__nv_bfloat16*>(whh_p), static_cast<__nv_bfloat16*>(whhT_p), H, I, Ipad, part);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
@@ -512,7 +524,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 cast_rows4_kernel(const float* __restrict__ src, long long s_outer, long long s_inner, int n_inner,
                   const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dst,
-                  long long dst_pitch, int R, int C) {
+                  long long dst_pitch, int R, int C, int part) {
     const int c4 = C >> 2;
     const long long total = static_cast<long long>(R) * c4;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
@@ -524,7 +536,7 @@ cast_rows4_kernel(const float* __restrict__ src, long long s_outer, long long s_
             const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
             v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
         }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        __nv_bfloat162 lo = bf16x2_part(v.x, v.y, part), hi = bf16x2_part(v.z, v.w, part);
         uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
         *reinterpret_cast<uint2*>(dst + static_cast<long long>(r) * dst_pitch + c) = o;
     }
@@ -534,7 +546,7 @@ cast_rows4_kernel(const float* __restrict__ src, long long s_outer, long long s_
 
 extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_outer, int64_t s_inner, int n_inner,
                                                   const float* scale, const float* shift, void* dst, int64_t dst_pitch,
-                                                  void* dstT, int64_t dstT_pitch, int n_pad, int R, int C,
+                                                  void* dstT, int64_t dstT_pitch, int n_pad, int R, int C, int part,
                                                   ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(R > 0 && C > 0 && n_inner > 0, "cast_transpose: empty R=%d C=%d", R, C);
@@ -547,17 +559,17 @@ extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_ou
                        (!scale || ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0);
     if (rows4) {
         ctcb200::cast_rows4_kernel<<<stream_grid(static_cast<long long>(R) * (C / 4), 2048), 256, 0, stream>>>(
-            src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch, R, C);
+            src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch, R, C, part);
     } else if (vec) {
         const long long tiles = static_cast<long long>((R + 63) / 64) * ((C + 63) / 64);
         cast_transpose_v2_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(
             src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch,
-            static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C);
+            static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C, part);
     } else {
         const long long tiles = static_cast<long long>((R + 31) / 32) * ((C + 31) / 32);
         cast_transpose_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(
             src, s_outer, s_inner, n_inner, scale, shift, static_cast<__nv_bfloat16*>(dst), dst_pitch,
-            static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C);
+            static_cast<__nv_bfloat16*>(dstT), dstT_pitch, n_pad, R, C, part);
     }
     CTCB_LAUNCH_CHECK();
     return OK;

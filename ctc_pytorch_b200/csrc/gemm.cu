@@ -177,7 +177,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (split_k > 1) tma_reduce_add_2d(&tmC, box, col0, m_blk * BM + ew * 32);
+                        if (split_k > 1 || accumulate) tma_reduce_add_2d(&tmC, box, col0, m_blk * BM + ew * 32);
                         else tma_store_2d(&tmC, box, col0, m_blk * BM + ew * 32);
                         bulk_group_commit();
                     }
@@ -257,11 +257,12 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
                 void* C, long long ldc, int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
                 int max_ctas, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[MAX_DEVICES] = {false};   // function attributes are per device (context)
+    const int dev = current_device();
+    if (!attr_set[dev]) {
         CTCB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * split_k;
     // max_ctas: 0 = persistent over all SMs; > 0 = cap (leave SMs to a concurrent kernel); < 0 = one tile per CTA
@@ -310,7 +311,8 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
     CUtensorMap tmC = tmA;
     int tma_store = 0;
     static const bool allow_tma_store = getenv("CTCB200_GEMM_EPILOGUE") == nullptr || getenv("CTCB200_GEMM_EPILOGUE")[0] != 'd';
-    if (allow_tma_store && !out_bf16 && !accumulate && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+    // accumulate = 1 rides the same path: the tile is ADDED to C by the TMA unit (cp.reduce.async.bulk ... .add)
+    if (allow_tma_store && !out_bf16 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
         rc = make_tmap_f32_2d(&tmC, C, M, N, ldc, 32, 32);
         if (rc != OK) return rc;
         tma_store = 1;
@@ -322,7 +324,7 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
         const long long t = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
         const int kblocks = (K + BK - 1) / BK;
         while (split_k < 8 && t * (split_k * 2) <= sms && kblocks / (split_k * 2) >= 16) split_k *= 2;
-        if (split_k > 1) CTCB_CUDA(cudaMemsetAsync(C, 0, static_cast<size_t>(M) * ldc * sizeof(float), stream));
+        if (split_k > 1 && !accumulate) CTCB_CUDA(cudaMemsetAsync(C, 0, static_cast<size_t>(M) * ldc * sizeof(float), stream));
     }
     switch (bn) {
         case 64: return launch_gemm<64>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream);

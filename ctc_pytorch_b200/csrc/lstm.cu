@@ -18,11 +18,12 @@
 // Kernels in this file (DESIGN.md §3.2 has the measurements):
 //   lstm_fwd_pipe_kernel   default forward for H <= 512: two 8-column halves software-pipelined over element,
 //                          tensor-core and copy warps; gx arrives as TMA boxes
-//   lstm_fwd_kernel<NB,EX> un-pipelined forward; EX selects the exchange (3 = bulk DSMEM copies, 1 = DSMEM stores,
-//                          2 = L2 + remote mbarriers, 0 = global image + counter, cooperative launch: the fallback)
-//   lstm_bwd_kernel<NB,EX> BPTT: CTA (q, mb) of a (4, H/128) cluster holds gate q's transposed slice for 128 units; the
+//   lstm_fwd_kernel<NB,EX,X3> un-pipelined forward; EX selects the exchange (3 = bulk DSMEM copies inside one cluster,
+//                          0 = global image + counter, cooperative launch: the fallback when no cluster fits)
+//   lstm_bwd_kernel<NB,EX,X3> BPTT: CTA (q, mb) of a (4, H/128) cluster holds gate q's transposed slice for 128 units; the
 //                          four gate partials are reduce-scattered (fp16 on the wire), the dG blocks all-gathered
-//   lstm_bwd_pipe_kernel   pipelined BPTT (opt-in, not faster: the DSMEM fabric is the bound either way)
+//   X3 = split-operand mode (precision "x3"): every product is W_hi h_hi + W_hi h_lo + W_lo h_hi on bf16 hi/lo halves,
+//                          fp32 hand-offs and fp32 saved gates: the path whose gradients meet the reference's fp32 numbers to 1e-3
 //   lstm_fwd2/bwd2_kernel  two gate tiles per CTA for H in (512, 640]
 #include <cuda_fp16.h>
 
@@ -67,10 +68,11 @@ __device__ __forceinline__ uint4 pack8_bf16(float v) {
 // Element offset (bf16 units) of the 16-byte chunk holding unit `u` (u % 8 == 0), batch row `n`, inside a [H x NB]
 // K-major SWIZZLE_64B operand image: K blocks of 32 units = [NB rows x 64 bytes], 16-byte chunk c of row n stored at
 // position c ^ ((n >> 1) & 3). The 32 units a CTA produces are therefore one contiguous NB*64-byte block.
-template <int NB>
+// With PARTS = 2 (split-operand mode) every 32-unit block is [hi part | lo part]; this is the offset of the hi part.
+template <int NB, int PARTS = 1>
 __device__ __forceinline__ int image_chunk_offset(int u, int n) {
     const int kb = u >> 5, c = (u & 31) >> 3;
-    return kb * (NB * 32) + n * 32 + ((c ^ ((n >> 1) & 3)) << 3);
+    return kb * (NB * 32 * PARTS) + n * 32 + ((c ^ ((n >> 1) & 3)) << 3);
 }
 
 // ---- thread-block-cluster primitives (distributed shared memory exchange) ------------------------------
@@ -173,52 +175,59 @@ __device__ __forceinline__ void load_partial_sums(uint32_t taddr, int acc_stride
         }
     }
 }
-
 struct FwdParams {
     const float* gx;          // [T*N, 8H] gate pre-activations from the input projection (packed column order)
     float* hout;              // [T*N, 2H] layer output (fwd | reverse)
     float* c_save;            // [T*N, 2H] cell states, or null (inference)
     uint2* gates_save;        // [T*N, 2H] activated gates as 4 x fp16 (i,f,g,o), or null
-    __nv_bfloat16* himg;      // [2 dirs][groups][2][H*NB] operand images
-    unsigned int* flags;      // [2 dirs][groups] step counters, 32 uints apart
+    float4* gates_save32;     // split-operand mode: the same as 4 x fp32 (BPTT then sees the gates at full precision)
+    __nv_bfloat16* himg;      // EX = 0: [2 dirs][groups][2 parities][H*NB*PARTS] operand images in global memory
+    unsigned int* flags;      // EX = 0: [2 dirs][groups] step counters, 32 uints apart
     int T, N, H, groups, n0;  // n0 = first batch row of this launch's group 0
     long long* trace;         // debug: per-step clock64 stamps of CTA (0,0,0), or null
-    const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (source of the TMEM-resident A operand)
-    int a_tmem;               // 1: A operand resident in TMEM, 0: in shared memory (TMA-loaded)
+    const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (hi part): source of the TMEM-resident A operand
     int mma_split;            // number of warps (1, 2 or 4) that issue slices of the K chain into their own accumulator
     int act_approx;           // 1: gate non-linearities through tanh.approx (one MUFU op each)
 };
 
-// CL = true: the H/32 CTAs of one (direction, batch group) form one thread-block cluster and exchange h_t through
-// distributed shared memory (every CTA pushes its 32 units straight into the next-step operand buffer of all
-// peers and arrives on their mbarrier) — no global-memory round trip on the recurrence's critical path.
-// CL = false: exchange through a global operand image + release/acquire counter (any H, needs a cooperative launch).
-template <int NB, int EX>
+// Split a float into bf16 hi + bf16 lo (hi + lo carries 16 mantissa bits of the value).
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16(v);
+    lo = __float2bfloat16(v - __bfloat162float(hi));
+}
+
+// Un-pipelined forward recurrence (one element phase per step over all NB columns of the group).
+//   EX = 3: the H/32 CTAs of one (direction, batch group) form one thread-block cluster and all-gather h_t with one bulk
+//           (TMA-engine) DSMEM copy per peer, complete_tx on the peer's mbarrier.
+//   EX = 0: exchange through a global operand image + release/acquire counter (any H, needs a cooperative launch).
+//   X3    : split-operand ("bf16x3") mode for fp32-grade results: W = W_hi + W_lo, h = h_hi + h_lo (all bf16) and the product
+//           is accumulated as W_hi h_hi + W_hi h_lo + W_lo h_hi in the fp32 TMEM accumulator (the dropped W_lo h_lo term is
+//           2^-18 relative). W_hi stays resident in TMEM, W_lo in shared memory (TMA-loaded once, SWIZZLE_128B); every
+//           32-unit block of the operand image carries [hi | lo], so the exchange is still one copy per peer.
+template <int NB, int EX, bool X3>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
-    // EX = 0: global image + global counter (cooperative launch, any H)
-    // EX = 1: cluster, data pushed through DSMEM stores     EX = 2: cluster, data through L2, hand-off on DSMEM mbarriers
-    // EX = 3: cluster, one bulk (TMA-engine) copy per peer with complete_tx on the peer's mbarrier
-    constexpr bool CL = EX != 0, PUSH = EX == 1 || EX == 3, BULK = EX == 3, HYB = EX == 2;
-    constexpr uint32_t BLK_BYTES = NB * 64;  // the 32 units x NB batch rows this CTA contributes to the operand image
+lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
+    constexpr bool CL = EX != 0, BULK = EX == 3;
+    constexpr int PARTS = X3 ? 2 : 1;
+    constexpr uint32_t BLK_BYTES = NB * 64;             // 32 units x NB batch rows of one operand part
+    constexpr uint32_t BLK_STRIDE = PARTS * BLK_BYTES;  // what one CTA contributes to the operand image per step
     constexpr int CPT = NB / 2;        // accumulator columns per thread
     constexpr int EPT = NB / 8;        // (unit, batch) elements per thread in the cell update
     constexpr int S_STRIDE = NB * 4 + 4;
-    constexpr int OUT_CHUNKS = NB * 4; // 16-byte chunks of h_t this CTA produces per step (32 units x NB)
+    constexpr int OUT_CHUNKS = NB * 4; // 16-byte chunks of one part of h_t this CTA produces per step (32 units x NB)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, T = p.T, N = p.N;
-    const int himg_bytes = H * NB * 2;
-    uint8_t* sW = smem;                                              // unused when the weights live in TMEM
-    uint8_t* sH = sW + (p.a_tmem ? 0 : 128 * H * 2);                 // PUSH: two buffers, else one
-    float* sS = reinterpret_cast<float*>(sH + (PUSH ? 2 : 1) * himg_bytes);
-    uint4* sOut = reinterpret_cast<uint4*>(sS + 32 * S_STRIDE);      // PUSH only: staging of this CTA's h chunks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (PUSH ? OUT_CHUNKS : 0));
+    const int himg_bytes = H * NB * 2 * PARTS;
+    uint8_t* sW = smem;                                              // X3: the W_lo slice [128 x H] bf16
+    uint8_t* sH = sW + (X3 ? 128 * H * 2 : 0);                       // BULK: two parities, else one buffer
+    float* sS = reinterpret_cast<float*>(sH + (BULK ? 2 : 1) * himg_bytes);
+    uint4* sOut = reinterpret_cast<uint4*>(sS + 32 * S_STRIDE);      // BULK only: staging of this CTA's block [hi | lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (BULK ? PARTS * OUT_CHUNKS : 0));
     uint64_t* w_full = bars;
-    uint64_t* h_full = bars + 1;   // [2]: CL -> peers' arrivals per parity; EX=0 -> [0] counts the local image copy
+    uint64_t* h_full = bars + 1;   // [2]: BULK -> the peers' blocks of a parity have landed; EX=0 -> [0] counts the local image copy
     uint64_t* acc_full = bars + 3;
-    uint64_t* l_full = bars + 4;   // HYB: the image copy into shared memory is complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
@@ -226,23 +235,22 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     const int kblocks = H / 64;
 
     if (tid == 0) {
-        tma_prefetch_desc(&tmW);
+        if constexpr (X3) tma_prefetch_desc(&tmWlo);
         mbar_init(w_full, 1);
-        mbar_init(&h_full[0], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
-        mbar_init(&h_full[1], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
+        mbar_init(&h_full[0], BULK ? 1 : LSTM_THREADS);
+        mbar_init(&h_full[1], BULK ? 1 : LSTM_THREADS);
         mbar_init(acc_full, p.mma_split);
-        mbar_init(l_full, LSTM_THREADS);
         fence_mbar_init();
         if constexpr (BULK) {  // arm both parities: each expects one block from every CTA of the cluster
-            mbar_expect_tx(&h_full[0], ctas * BLK_BYTES);
-            mbar_expect_tx(&h_full[1], ctas * BLK_BYTES);
+            mbar_expect_tx(&h_full[0], ctas * BLK_STRIDE);
+            mbar_expect_tx(&h_full[1], ctas * BLK_STRIDE);
         }
     }
-    // TMEM: up to four accumulators in columns [0, 64), the weight slice (A operand) in columns [64, 64 + H/2)
+    // TMEM: up to four accumulators in columns [0, 64), the W_hi slice (A operand) in columns [64, 64 + H/2)
     uint32_t tmem_cols = 64;
-    if (p.a_tmem) { while (tmem_cols < 64u + H / 2) tmem_cols <<= 1; }
+    while (tmem_cols < 64u + H / 2) tmem_cols <<= 1;
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-    if constexpr (PUSH) {
+    if constexpr (BULK) {
         // h_{-1} = 0: the first operand buffer starts zeroed
         for (int i = tid; i < himg_bytes / 16; i += LSTM_THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async_smem();
@@ -253,15 +261,16 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     const uint32_t tmem_base = *tmem_slot;
     if constexpr (CL) cluster_sync_all();  // peers' barriers are initialised before anyone arrives on them
 
-    if (p.a_tmem) {
-        if (warp < 4) load_weights_to_tmem(p.w + (static_cast<size_t>(dir) * 4 * H + j * 128) * H, H, tmem_base, 64, warp, lane);
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-    } else if (tid == 0) {
-        mbar_expect_tx(w_full, 128 * H * 2);
-        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sW + kb * 16384, &tmW, w_full, kb * 64, dir * 4 * H + j * 128);
+    if (warp < 4) load_weights_to_tmem(p.w + (static_cast<size_t>(dir) * 4 * H + j * 128) * H, H, tmem_base, 64, warp, lane);
+    if constexpr (X3) {
+        if (tid == 0) {
+            mbar_expect_tx(w_full, 128 * H * 2);
+            for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sW + kb * 16384, &tmWlo, w_full, kb * 64, dir * 4 * H + j * 128);
+        }
     }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     const int lq = warp & 3, ch = warp >> 2;
     const bool warp_leader = elect_one();      // the lane of each warp that issues / tracks its bulk copies
@@ -271,9 +280,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     const float act_h = (q == 2) ? 1.0f : 0.5f;
     const size_t gx_col = static_cast<size_t>(dir) * 4 * H + j * 128 + row;
     const size_t G8 = static_cast<size_t>(8) * H, H2 = static_cast<size_t>(2) * H;
-    __nv_bfloat16* img = PUSH ? nullptr : p.himg + (static_cast<size_t>(dir) * p.groups + grp) * 2 * H * NB;
+    __nv_bfloat16* img = BULK ? nullptr : p.himg + (static_cast<size_t>(dir) * p.groups + grp) * 2 * H * NB * PARTS;
     unsigned int* flag = CL ? nullptr : p.flags + (dir * p.groups + grp) * 32;
-    const int chunks = H * NB / 8;
+    const int chunks = H * NB / 8 * PARTS;
     constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
 
     float c_state[EPT];
@@ -291,66 +300,62 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             const int gn = p.n0 + grp * NB + ch * CPT + c;
             gx[c] = (gn < N) ? __ldg(p.gx + (static_cast<size_t>(tt) * N + gn) * G8 + gx_col) : 0.0f;
         }
-        if constexpr (!PUSH) {
+        if constexpr (!BULK) {
             // (2) all CTAs of this (direction, group) have published h_{t-1}
-            if constexpr (HYB) {
-                if (t > 0) mbar_wait_cluster(&h_full[t & 1], ((t - 1) >> 1) & 1);
-            } else {
-                if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
-                __syncwarp();
-            }
+            if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
+            __syncwarp();
             // (3) operand image -> shared memory
-            const uint4* src = reinterpret_cast<const uint4*>(img + static_cast<size_t>(t & 1) * H * NB);
+            const uint4* src = reinterpret_cast<const uint4*>(img + static_cast<size_t>(t & 1) * H * NB * PARTS);
             uint4* dst = reinterpret_cast<uint4*>(sH);
             for (int i = tid; i < chunks; i += LSTM_THREADS) dst[i] = ld_cg_v4(src + i);
             fence_proxy_async_smem();
-            mbar_arrive(HYB ? l_full : &h_full[0]);
+            mbar_arrive(&h_full[0]);
         }
-        // (4) warp 0 issues the K = H MMA chain: the whole warp runs the (warp-uniform) address arithmetic so the
-        // descriptors live in uniform registers; one elected lane issues each tcgen05.mma
+        // (4) up to four warps issue interleaved K blocks of the chain into their own accumulator (the issue rate of one
+        // warp, ~40 cycles per tcgen05.mma, would bound the chain); the whole warp runs the warp-uniform address
+        // arithmetic so the descriptors live in uniform registers, one elected lane issues each tcgen05.mma
         if (warp < p.mma_split) {
-            if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
+            if constexpr (X3) { if (t == 0) mbar_wait(w_full, 0); }
             if constexpr (BULK) {
                 if (t > 0) {
                     mbar_wait(&h_full[t & 1], ((t - 1) >> 1) & 1);                // every peer's block has landed
-                    if (lane == 0 && warp == 0) mbar_expect_tx(&h_full[t & 1], ctas * BLK_BYTES);  // re-arm for step t+2
+                    if (lane == 0 && warp == 0) mbar_expect_tx(&h_full[t & 1], ctas * BLK_STRIDE);  // re-arm for step t+2
                 }
-            } else if constexpr (PUSH) {
-                if (t > 0) mbar_wait_cluster(&h_full[t & 1], ((t - 1) >> 1) & 1);  // all peers pushed h_{t-1}
-                fence_proxy_async_all();   // peers' generic-proxy DSMEM writes -> tensor-core (async proxy) reads
             } else {
-                mbar_wait(HYB ? l_full : &h_full[0], t & 1);
+                mbar_wait(&h_full[0], t & 1);
             }
             tc_fence_after();
             TRACE(1);
-            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sH) + (PUSH ? (t & 1) * himg_bytes : 0);
+            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sH) + (BULK ? (t & 1) * himg_bytes : 0);
             const bool leader = elect_one();
-            if (p.a_tmem) {
-                // the issue rate of one warp (~40 cycles per tcgen05.mma) bounds the chain, so up to four warps issue
-                // interleaved K blocks into their own accumulator; the epilogue adds the partial sums
-                const int kstep = p.mma_split, kfirst = warp;
-                const uint32_t dacc = tmem_base + warp * NB;
+            const int kstep = p.mma_split, kfirst = warp;
+            const uint32_t dacc = tmem_base + warp * NB;
+            constexpr uint32_t B2 = BLK_STRIDE / 16;   // descriptor step to the second 32-unit block of a 64-wide K block
+            constexpr uint32_t LO = BLK_BYTES / 16;    // descriptor step from a block's hi part to its lo part
 #pragma unroll 1
-                for (int kb = kfirst; kb < kblocks; kb += kstep) {
-                    // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
-                    const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
-                    const uint32_t ta = tmem_base + 64 + kb * 32;
-                    if (leader) {
-                        umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
-                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
-                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
-                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
-                    }
+            for (int kb = kfirst; kb < kblocks; kb += kstep) {
+                // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
+                const uint64_t bd = umma_desc_sw64(b0 + kb * (2 * BLK_STRIDE));
+                const uint32_t ta = tmem_base + 64 + kb * 32;
+                if (leader) {
+                    umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
+                    umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                    umma_bf16_ts(dacc, ta + 16, bd + B2, idesc, 1u);
+                    umma_bf16_ts(dacc, ta + 24, bd + B2 + 2, idesc, 1u);
                 }
-            } else {
-#pragma unroll 1
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw64(b0 + kb * (NB * 128));
+                if constexpr (X3) {
+                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384);
                     if (leader) {
-                        umma_bf16(tmem_base, ad, bd, idesc, kb != 0 ? 1u : 0u);
-                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 4, bd + (NB * 64 / 16), idesc, 1u);
-                        umma_bf16(tmem_base, ad + 6, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                        // W_hi x h_lo
+                        umma_bf16_ts(dacc, ta, bd + LO, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 8, bd + LO + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + B2 + LO, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + B2 + LO + 2, idesc, 1u);
+                        // W_lo x h_hi
+                        umma_bf16(dacc, ad, bd, idesc, 1u);
+                        umma_bf16(dacc, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(dacc, ad + 4, bd + B2, idesc, 1u);
+                        umma_bf16(dacc, ad + 6, bd + B2 + 2, idesc, 1u);
                     }
                 }
             }
@@ -391,60 +396,43 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
             const float h = g4.w * (p.act_approx ? tanh_approx(cn) : fast_tanh(cn));
             hv[e] = h;
             gv[e] = g4;
-            if constexpr (PUSH) {
+            __nv_bfloat16 h_hi, h_lo;
+            split_bf16(h, h_hi, h_lo);
+            if constexpr (BULK) {
                 // staging in destination order: chunk `oct` of row n sits at slot oct ^ ((n >> 1) & 3) of the 64-byte
                 // row; every lane drops its own bf16 (no shuffle chain on the critical path)
-                reinterpret_cast<__nv_bfloat16*>(sOut)[n * 32 + (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7)] =
-                    __float2bfloat16(h);
+                const int so = n * 32 + (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7);
+                reinterpret_cast<__nv_bfloat16*>(sOut)[so] = h_hi;
+                if constexpr (X3) reinterpret_cast<__nv_bfloat16*>(sOut)[OUT_CHUNKS * 8 + so] = h_lo;
             } else {
-                const uint4 pk = pack8_bf16(h);
-                if ((lane & 7) == 0)
-                    *reinterpret_cast<uint4*>(img + static_cast<size_t>((t + 1) & 1) * H * NB +
-                                              image_chunk_offset<NB>(j * 32 + lane, n)) = pk;
+                __nv_bfloat16* nxt = img + static_cast<size_t>((t + 1) & 1) * H * NB * PARTS + image_chunk_offset<NB, PARTS>(j * 32 + lane, n);
+                const uint4 pk = pack8_bf16(__bfloat162float(h_hi));
+                if ((lane & 7) == 0) *reinterpret_cast<uint4*>(nxt) = pk;
+                if constexpr (X3) {
+                    const uint4 pl = pack8_bf16(__bfloat162float(h_lo));
+                    if ((lane & 7) == 0) *reinterpret_cast<uint4*>(nxt + NB * 32) = pl;
+                }
             }
         }
         TRACE(12);
-        if constexpr (HYB) {
-            __threadfence();   // h_t is in L2 before any peer is told about it
-            TRACE(6); TRACE(13);
-            __syncthreads();
-            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&h_full[(t + 1) & 1], static_cast<uint32_t>(tid));
-            TRACE(7);
-        } else if constexpr (BULK) {
+        if constexpr (BULK) {
             fence_proxy_async_smem();   // staging writes (generic proxy) -> bulk-copy engine (async proxy)
             __syncthreads();
             TRACE(6);
             if (t + 1 < T) {
                 // one bulk copy per peer (our contiguous block -> slot j of the peer's next operand buffer); warp w
                 // serves peers w and w + 8 so the copies are issued in parallel with warp-uniform operands
-                const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_BYTES;
+                const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_STRIDE;
                 const uint32_t bar = smem_u32(&h_full[(t + 1) & 1]);
 #pragma unroll
                 for (int d = warp; d < 16; d += 8) {
                     if (d < ctas && warp_leader)
-                        bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), smem_u32(sOut), BLK_BYTES,
+                        bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), smem_u32(sOut), BLK_STRIDE,
                                           mapa_shared(bar, static_cast<uint32_t>(d)));
                 }
                 if (warp_leader) bulk_commit();
             }
             TRACE(13); TRACE(7);
-        } else if constexpr (PUSH) {
-            __syncthreads();
-            TRACE(6);
-            if (t + 1 < T) {
-                // push this CTA's OUT_CHUNKS chunks into buffer (t+1)&1 of every CTA of the cluster
-                const uint32_t next_base = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_BYTES;
-                for (int idx = tid; idx < OUT_CHUNKS * ctas; idx += LSTM_THREADS) {
-                    const int c = idx % OUT_CHUNKS;
-                    int d = idx / OUT_CHUNKS + j;  // start with the own rank: spreads the senders over the receivers
-                    if (d >= ctas) d -= ctas;
-                    st_cluster_v4(mapa_shared(next_base + c * 16, static_cast<uint32_t>(d)), sOut[c]);
-                }
-            }
-            TRACE(13);
-            __syncthreads();
-            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&h_full[(t + 1) & 1], static_cast<uint32_t>(tid));
-            TRACE(7);
         } else {
             __threadfence();
             __syncthreads();
@@ -458,7 +446,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
                 const size_t o = (static_cast<size_t>(tt) * N + gn) * H2 + static_cast<size_t>(dir) * H + j * 32 + lane;
                 p.hout[o] = hv[e];
                 if (p.c_save) p.c_save[o] = c_state[e];
-                if (p.gates_save) {
+                if (p.gates_save32) {
+                    p.gates_save32[o] = gv[e];
+                } else if (p.gates_save) {
                     __half2 lo = __floats2half2_rn(gv[e].x, gv[e].y), hi = __floats2half2_rn(gv[e].z, gv[e].w);
                     p.gates_save[o] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
                 }
@@ -693,15 +683,15 @@ struct BwdParams {
     const float* dhout;        // [T*N, 2H] gradient w.r.t. the layer output
     const float* c_save;       // [T*N, 2H]
     const uint2* gates_save;   // [T*N, 2H] 4 x fp16
-    __nv_bfloat16* dg;         // [T*N, 8H] gate gradients, packed column order (A operand of the dX GEMM)
-    __nv_bfloat16* dgimg;      // [2 dirs][groups][4 gates][2][H*NB] operand images
-    unsigned int* flags;       // [2 dirs][groups]
+    const float4* gates_save32;  // split-operand mode: 4 x fp32 instead
+    __nv_bfloat16* dg;         // [T*N, 8H] gate gradients, packed column order (A operand of the dX GEMM); hi part in X3 mode
+    __nv_bfloat16* dg_lo;      // X3: the lo part of the same
+    __nv_bfloat16* dgimg;      // EX = 0: [2 dirs][groups][4 gates][2][H*NB*PARTS] operand images
+    unsigned int* flags;       // EX = 0: [2 dirs][groups]
     int T, N, H, groups, n0;
-    const __nv_bfloat16* w;    // packed transposed recurrent weights [8H, H]
-    int a_tmem;
+    const __nv_bfloat16* w;    // packed transposed recurrent weights [8H, H] (hi part)
     int mma_split;
     unsigned int* resident;    // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
-    long long* trace;          // debug (pipelined kernel): per-step clock64 stamps of CTA (0,0,0), or null
     const float* bn_x;         // optional: layer output [T*N, 2H]; the BatchNorm backward of the layer above is applied to
     const float* bn_coef;      // dhout on the fly: dh = coef[0][c]*dhout + coef[1][c]*bn_x + coef[2][c], coef f32 [3][2H]
 };
@@ -735,33 +725,36 @@ __device__ __forceinline__ void announce_resident(unsigned int* resident) {
 // CTA (mb, q) keeps the [128 units x H] slice of gate q's transposed recurrent block. Per BPTT step:
 //   partial dh[128, NB] = slice * dG_q  ->  reduce-scatter of the 4 gate partials inside the (4,*) cluster row
 //   -> 32 finished units per CTA -> LSTM cell backward -> the four dG chunks go to the next step's operands.
-// CL = true: the whole (direction, group) = 4 x H/128 CTAs is one cluster; dG chunks are pushed through DSMEM into
-// the operand buffer of every CTA that holds the same gate, completion on remote mbarriers.
-// CL = false: cluster of the 4 gate CTAs only; dG images + release/acquire counter in global memory (any H).
-template <int NB, int EX>
+// EX = 3: the whole (direction, group) = 4 x H/128 CTAs is one cluster; partial rows and dG blocks travel as bulk DSMEM
+//         copies with complete_tx on the receiver's mbarrier (partials as fp16, or fp32 in X3 mode).
+// EX = 0: cluster of the 4 gate CTAs only; dG images + release/acquire counter in global memory (any H).
+// X3    : split-operand mode as in the forward kernel: W^T = hi (TMEM) + lo (shared memory), dG = hi + lo blocks.
+template <int NB, int EX, bool X3>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
-    constexpr bool CL = EX != 0, PUSH = EX == 1 || EX == 3, BULK = EX == 3, HYB = EX == 2;  // as in the forward kernel
+lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
+    constexpr bool CL = EX != 0, BULK = EX == 3;
+    constexpr int PARTS = X3 ? 2 : 1;
     constexpr uint32_t BLK_BYTES = NB * 64;
+    constexpr uint32_t BLK_STRIDE = PARTS * BLK_BYTES;
     constexpr int CPT = NB / 2;
     constexpr int EPT = NB / 8;
     constexpr int OUT_CHUNKS = NB * 4;
+    constexpr uint32_t PART_BYTES = X3 ? 4 : 2;   // width of one partial-dh element on the wire (BULK)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, T = p.T, N = p.N;
-    const int img_bytes = H * NB * 2;
-    uint8_t* sW = smem;                                               // unused when the weights live in TMEM
-    uint8_t* sB = sW + (p.a_tmem ? 0 : 128 * H * 2);                  // PUSH: two buffers, else one
-    float* sR = reinterpret_cast<float*>(sB + (PUSH ? 2 : 1) * img_bytes);  // [4 src][NB][32] partial dh blocks
-    uint4* sOut = reinterpret_cast<uint4*>(sR + 4 * NB * 32);         // PUSH only: [4 gates][OUT_CHUNKS]
-    float* sP = reinterpret_cast<float*>(sOut + (PUSH ? 4 * OUT_CHUNKS : 0));  // BULK only: [4 dst][NB][32] partial staging
+    const int img_bytes = H * NB * 2 * PARTS;
+    uint8_t* sW = smem;                                               // X3: the W^T_lo slice [128 x H] bf16
+    uint8_t* sB = sW + (X3 ? 128 * H * 2 : 0);                        // BULK: two parities, else one buffer
+    float* sR = reinterpret_cast<float*>(sB + (BULK ? 2 : 1) * img_bytes);  // [4 src][NB][32] partial dh blocks
+    uint4* sOut = reinterpret_cast<uint4*>(sR + 4 * NB * 32);         // BULK only: [4 gates][PARTS][OUT_CHUNKS]
+    float* sP = reinterpret_cast<float*>(sOut + (BULK ? 4 * PARTS * OUT_CHUNKS : 0));  // BULK only: [4 dst][NB][32] partial staging
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (BULK ? 4 * NB * 32 : 0));
     uint64_t* w_full = bars;
     uint64_t* b_full = bars + 1;   // [2]
     uint64_t* acc_full = bars + 3;
-    uint64_t* r_full = bars + 4;   // CL only: the 4 partial blocks of a step have landed
-    uint64_t* l_full = bars + 5;   // HYB: the image copy into shared memory is complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* r_full = bars + 4;   // BULK: the 4 partial blocks of a step have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     announce_resident(p.resident);
@@ -775,24 +768,23 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     auto rank_of = [&](int qq, int mm) -> uint32_t { return static_cast<uint32_t>(CL ? qq + 4 * mm : qq); };
 
     if (tid == 0) {
-        tma_prefetch_desc(&tmWT);
+        if constexpr (X3) tma_prefetch_desc(&tmWTlo);
         mbar_init(w_full, 1);
-        mbar_init(&b_full[0], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
-        mbar_init(&b_full[1], BULK ? 1 : (CL ? ctas : LSTM_THREADS));
+        mbar_init(&b_full[0], BULK ? 1 : LSTM_THREADS);
+        mbar_init(&b_full[1], BULK ? 1 : LSTM_THREADS);
         mbar_init(acc_full, p.mma_split);
-        mbar_init(r_full, BULK ? 1 : 4);
-        mbar_init(l_full, LSTM_THREADS);
+        mbar_init(r_full, 1);
         fence_mbar_init();
         if constexpr (BULK) {
-            mbar_expect_tx(&b_full[0], ctas * BLK_BYTES);
-            mbar_expect_tx(&b_full[1], ctas * BLK_BYTES);
-            mbar_expect_tx(r_full, 4 * NB * 32 * 2);  // four gate partials of [NB][32] fp16 values per step
+            mbar_expect_tx(&b_full[0], ctas * BLK_STRIDE);
+            mbar_expect_tx(&b_full[1], ctas * BLK_STRIDE);
+            mbar_expect_tx(r_full, 4 * NB * 32 * PART_BYTES);  // four gate partials of [NB][32] values per step
         }
     }
     uint32_t tmem_cols = 64;
-    if (p.a_tmem) { while (tmem_cols < 64u + H / 2) tmem_cols <<= 1; }
+    while (tmem_cols < 64u + H / 2) tmem_cols <<= 1;
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-    if constexpr (PUSH) {
+    if constexpr (BULK) {
         for (int i = tid; i < img_bytes / 16; i += LSTM_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async_smem();
     }
@@ -803,17 +795,18 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     cluster_sync_all();  // every CTA of the cluster has its barriers / receive buffers ready
 
     // rows of the transposed gate block: (dir, q, unit); this CTA takes units [128 mb, +128)
-    if (p.a_tmem) {
-        if (warp < 4)
-            load_weights_to_tmem(p.w + (static_cast<size_t>(dir * 4 + q) * H + mb * 128) * H, H, tmem_base, 64, warp, lane);
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-    } else if (tid == 0) {
-        mbar_expect_tx(w_full, 128 * H * 2);
-        for (int kb = 0; kb < kblocks; ++kb)
-            tma_load_2d(sW + kb * 16384, &tmWT, w_full, kb * 64, (dir * 4 + q) * H + mb * 128);
+    if (warp < 4)
+        load_weights_to_tmem(p.w + (static_cast<size_t>(dir * 4 + q) * H + mb * 128) * H, H, tmem_base, 64, warp, lane);
+    if constexpr (X3) {
+        if (tid == 0) {
+            mbar_expect_tx(w_full, 128 * H * 2);
+            for (int kb = 0; kb < kblocks; ++kb)
+                tma_load_2d(sW + kb * 16384, &tmWTlo, w_full, kb * 64, (dir * 4 + q) * H + mb * 128);
+        }
     }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     const int lq = warp & 3, ch = warp >> 2;
     const bool warp_leader = elect_one();
@@ -821,9 +814,9 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     const BnCoef bnk = load_bn_coef(p, dir * H + unit);
     const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
     const size_t dg_col = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4;
-    __nv_bfloat16* imgs = PUSH ? nullptr : p.dgimg + (static_cast<size_t>(dir) * p.groups + grp) * 4 * 2 * H * NB;
+    __nv_bfloat16* imgs = BULK ? nullptr : p.dgimg + (static_cast<size_t>(dir) * p.groups + grp) * 4 * 2 * H * NB * PARTS;
     unsigned int* flag = CL ? nullptr : p.flags + (dir * p.groups + grp) * 32;
-    const int chunks = H * NB / 8;
+    const int chunks = H * NB / 8 * PARTS;
     constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
     // remote receive slot: partial block from source gate q lands in the CTA that owns rows 32 lq.. of this unit block
     const uint32_t remote_base = mapa_shared(smem_u32(sR + (q * NB + ch * CPT) * 32 + lane), rank_of(lq, mb));
@@ -838,7 +831,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         const bool has_prev = dir ? (tt + 1 < T) : (tt >= 1);
         // (1) saved activations and the incoming gradient for this thread's elements
         float dh_in[EPT], bx_in[EPT], c_t[EPT], c_p[EPT];
-        uint2 gts[EPT];
+        float4 gts[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int gn = p.n0 + grp * NB + warp + 8 * e;
@@ -847,67 +840,67 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             dh_in[e] = ok ? __ldg(p.dhout + o) : 0.0f;
             bx_in[e] = (p.bn_x != nullptr && ok) ? __ldg(p.bn_x + o) : 0.0f;   // combined with dh_in where it is consumed
             c_t[e] = ok ? __ldg(p.c_save + o) : 0.0f;
-            gts[e] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
+            if constexpr (X3) {
+                gts[e] = ok ? __ldg(p.gates_save32 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const uint2 g2 = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
+                const __half2 lo = *reinterpret_cast<const __half2*>(&g2.x), hi = *reinterpret_cast<const __half2*>(&g2.y);
+                gts[e] = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+            }
             const size_t op = (static_cast<size_t>(has_prev ? tprev : tt) * N + (ok ? gn : 0)) * H2 +
                               static_cast<size_t>(dir) * H + unit;
             c_p[e] = (ok && has_prev) ? __ldg(p.c_save + op) : 0.0f;
         }
-        if constexpr (!PUSH) {
+        if constexpr (!BULK) {
             // (2) gate gradients of the previous BPTT step are published
-            if constexpr (HYB) {
-                if (t > 0) mbar_wait_cluster(&b_full[t & 1], ((t - 1) >> 1) & 1);
-            } else {
-                if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
-                __syncwarp();
-            }
+            if (lane == 0) wait_counter(flag, static_cast<unsigned int>(ctas) * t);
+            __syncwarp();
             // (3) dG image of gate q -> shared memory
-            const uint4* src = reinterpret_cast<const uint4*>(imgs + (static_cast<size_t>(q) * 2 + (t & 1)) * H * NB);
+            const uint4* src = reinterpret_cast<const uint4*>(imgs + (static_cast<size_t>(q) * 2 + (t & 1)) * H * NB * PARTS);
             uint4* dst = reinterpret_cast<uint4*>(sB);
             for (int i = tid; i < chunks; i += LSTM_THREADS) dst[i] = ld_cg_v4(src + i);
             fence_proxy_async_smem();
-            mbar_arrive(HYB ? l_full : &b_full[0]);
+            mbar_arrive(&b_full[0]);
         }
         // (4) partial dh[128 units, NB] = W_q^T slice * dG_q (issued like the forward kernel's chain)
         if (warp < p.mma_split) {
-            if (t == 0 && !p.a_tmem) mbar_wait(w_full, 0);
+            if constexpr (X3) { if (t == 0) mbar_wait(w_full, 0); }
             if constexpr (BULK) {
                 if (t > 0) {
                     mbar_wait(&b_full[t & 1], ((t - 1) >> 1) & 1);
-                    if (lane == 0 && warp == 0) mbar_expect_tx(&b_full[t & 1], ctas * BLK_BYTES);
+                    if (lane == 0 && warp == 0) mbar_expect_tx(&b_full[t & 1], ctas * BLK_STRIDE);
                 }
-            } else if constexpr (PUSH) {
-                if (t > 0) mbar_wait_cluster(&b_full[t & 1], ((t - 1) >> 1) & 1);
-                fence_proxy_async_all();
             } else {
-                mbar_wait(HYB ? l_full : &b_full[0], t & 1);
+                mbar_wait(&b_full[0], t & 1);
             }
             tc_fence_after();
-            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sB) + (PUSH ? (t & 1) * img_bytes : 0);
+            const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sB) + (BULK ? (t & 1) * img_bytes : 0);
             const bool leader = elect_one();
-            if (p.a_tmem) {
-                const int kstep = p.mma_split, kfirst = warp;
-                const uint32_t dacc = tmem_base + warp * NB;
+            const int kstep = p.mma_split, kfirst = warp;
+            const uint32_t dacc = tmem_base + warp * NB;
+            constexpr uint32_t B2 = BLK_STRIDE / 16, LO = BLK_BYTES / 16;
 #pragma unroll 1
-                for (int kb = kfirst; kb < kblocks; kb += kstep) {
-                    // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
-                    const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
-                    const uint32_t ta = tmem_base + 64 + kb * 32;
-                    if (leader) {
-                        umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
-                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
-                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
-                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
-                    }
+            for (int kb = kfirst; kb < kblocks; kb += kstep) {
+                // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
+                const uint64_t bd = umma_desc_sw64(b0 + kb * (2 * BLK_STRIDE));
+                const uint32_t ta = tmem_base + 64 + kb * 32;
+                if (leader) {
+                    umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
+                    umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
+                    umma_bf16_ts(dacc, ta + 16, bd + B2, idesc, 1u);
+                    umma_bf16_ts(dacc, ta + 24, bd + B2 + 2, idesc, 1u);
                 }
-            } else {
-#pragma unroll 1
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384), bd = umma_desc_sw64(b0 + kb * (NB * 128));
+                if constexpr (X3) {
+                    const uint64_t ad = umma_desc_sw128(a0 + kb * 16384);
                     if (leader) {
-                        umma_bf16(tmem_base, ad, bd, idesc, kb != 0 ? 1u : 0u);
-                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 4, bd + (NB * 64 / 16), idesc, 1u);
-                        umma_bf16(tmem_base, ad + 6, bd + (NB * 64 / 16) + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta, bd + LO, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 8, bd + LO + 2, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 16, bd + B2 + LO, idesc, 1u);
+                        umma_bf16_ts(dacc, ta + 24, bd + B2 + LO + 2, idesc, 1u);
+                        umma_bf16(dacc, ad, bd, idesc, 1u);
+                        umma_bf16(dacc, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(dacc, ad + 4, bd + B2, idesc, 1u);
+                        umma_bf16(dacc, ad + 6, bd + B2 + 2, idesc, 1u);
                     }
                 }
             }
@@ -925,47 +918,44 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             // one bulk copy per warp into that CTA's receive slot for source gate q (complete_tx on its r_full)
             if (warp_leader) bulk_wait_read_all();  // this warp's earlier copies have finished reading shared memory
             __syncthreads();                         // ... for every warp: sP and sOut may be rewritten
-            // partials cross the cluster as fp16 (the DSMEM fabric, ~17 B/clk per SM both ways, bounds this kernel; the four
-            // partials are summed in fp32 on arrival, so the rounding stays far below that of the bf16 operands)
-            __half* stage = reinterpret_cast<__half*>(sP) + (lq * NB + ch * CPT) * 32 + lane;
+            // bf16 mode: partials cross the cluster as fp16 (less DSMEM traffic; the four partials are summed in fp32 on
+            // arrival, so the rounding stays far below that of the bf16 operands); X3 mode: fp32 on the wire
+            const int pe = (lq * NB + ch * CPT) * 32, re = (q * NB + ch * CPT) * 32;   // element offsets in sP / the peer's sR
+            if constexpr (X3) {
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) stage[c * 32] = __float2half_rn(__uint_as_float(acc[c]));
+                for (int c = 0; c < CPT; ++c) sP[pe + c * 32 + lane] = __uint_as_float(acc[c]);
+            } else {
+                __half* stage = reinterpret_cast<__half*>(sP) + pe + lane;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) stage[c * 32] = __float2half_rn(__uint_as_float(acc[c]));
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (warp_leader) {
                 const uint32_t peer = rank_of(lq, mb);
-                bulk_copy_to_peer(mapa_shared(smem_u32(reinterpret_cast<__half*>(sR) + (q * NB + ch * CPT) * 32), peer),
-                                  smem_u32(reinterpret_cast<__half*>(sP) + (lq * NB + ch * CPT) * 32), CPT * 32 * 2,
-                                  mapa_shared(smem_u32(r_full), peer));
+                bulk_copy_to_peer(mapa_shared(smem_u32(sR) + re * PART_BYTES, peer), smem_u32(sP) + pe * PART_BYTES,
+                                  CPT * 32 * PART_BYTES, mapa_shared(smem_u32(r_full), peer));
                 bulk_commit();
             }
             mbar_wait(r_full, t & 1);
-            if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * 2);  // re-arm for the next step
+            if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * PART_BYTES);  // re-arm for the next step
         } else {
 #pragma unroll
             for (int c = 0; c < CPT; ++c) st_cluster_f32(remote_base + c * 32 * 4, __uint_as_float(acc[c]));
-            if constexpr (CL) {
-                __syncthreads();
-                if (tid < 4) mbar_arrive_remote(r_full, rank_of(tid, mb));
-                mbar_wait_cluster(r_full, t & 1);
-            } else {
-                cluster_sync_all();
-            }
+            cluster_sync_all();
         }
         // (6) finish 32 units: recurrent dh, LSTM cell backward, publish the four gate gradients
-        uint2 dgp[EPT];
+        uint2 dgp[EPT], dgl[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int n = warp + 8 * e;
             float dh = bnk.a * dh_in[e] + bnk.b * bx_in[e] + ((p.n0 + grp * NB + n < N) ? bnk.d : 0.0f);   // BatchNorm backward on the fly
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                if constexpr (BULK) dh += __half2float(reinterpret_cast<const __half*>(sR)[(s * NB + n) * 32 + lane]);
+                if constexpr (BULK && !X3) dh += __half2float(reinterpret_cast<const __half*>(sR)[(s * NB + n) * 32 + lane]);
                 else dh += sR[(s * NB + n) * 32 + lane];
             }
-            const __half2 lo = *reinterpret_cast<const __half2*>(&gts[e].x);
-            const __half2 hi = *reinterpret_cast<const __half2*>(&gts[e].y);
-            const float gi = __low2float(lo), gf = __high2float(lo), gg = __low2float(hi), go = __high2float(hi);
+            const float gi = gts[e].x, gf = gts[e].y, gg = gts[e].z, go = gts[e].w;
             const float tc = fast_tanh(c_t[e]);
             const float d_o = dh * tc * go * (1.0f - go);
             const float dc = dc_carry[e] + dh * go * (1.0f - tc * tc);
@@ -973,65 +963,62 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
             const float d_f = dc * c_p[e] * gf * (1.0f - gf);
             const float d_g = dc * gi * (1.0f - gg * gg);
             dc_carry[e] = dc * gf;
-            if constexpr (PUSH) {
-                // destination order inside each gate's block; one bf16 store per gate and lane
+            __nv_bfloat16 hi4[4], lo4[4];
+            split_bf16(d_i, hi4[0], lo4[0]);
+            split_bf16(d_f, hi4[1], lo4[1]);
+            split_bf16(d_g, hi4[2], lo4[2]);
+            split_bf16(d_o, hi4[3], lo4[3]);
+            if constexpr (BULK) {
+                // destination order inside each gate's block; one bf16 store per gate (and part) and lane
                 __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut) + n * 32 +
                                     (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7);
-                so[0 * OUT_CHUNKS * 8] = __float2bfloat16(d_i);
-                so[1 * OUT_CHUNKS * 8] = __float2bfloat16(d_f);
-                so[2 * OUT_CHUNKS * 8] = __float2bfloat16(d_g);
-                so[3 * OUT_CHUNKS * 8] = __float2bfloat16(d_o);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    so[g * PARTS * OUT_CHUNKS * 8] = hi4[g];
+                    if constexpr (X3) so[(g * PARTS + 1) * OUT_CHUNKS * 8] = lo4[g];
+                }
             } else {
-                const uint4 pi = pack8_bf16(d_i), pf = pack8_bf16(d_f), pg = pack8_bf16(d_g), po = pack8_bf16(d_o);
-                if ((lane & 7) == 0) {
-                    const int off = image_chunk_offset<NB>(unit, n);
-                    const size_t nxt = static_cast<size_t>((t + 1) & 1) * H * NB;
-                    *reinterpret_cast<uint4*>(imgs + (0 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pi;
-                    *reinterpret_cast<uint4*>(imgs + (1 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pf;
-                    *reinterpret_cast<uint4*>(imgs + (2 * 2) * static_cast<size_t>(H) * NB + nxt + off) = pg;
-                    *reinterpret_cast<uint4*>(imgs + (3 * 2) * static_cast<size_t>(H) * NB + nxt + off) = po;
+                const int off = image_chunk_offset<NB, PARTS>(unit, n);
+                const size_t nxt = static_cast<size_t>((t + 1) & 1) * H * NB * PARTS;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 ph = pack8_bf16(__bfloat162float(hi4[g]));
+                    __nv_bfloat16* dst = imgs + (static_cast<size_t>(g) * 2) * H * NB * PARTS + nxt + off;
+                    if ((lane & 7) == 0) *reinterpret_cast<uint4*>(dst) = ph;
+                    if constexpr (X3) {
+                        const uint4 pl = pack8_bf16(__bfloat162float(lo4[g]));
+                        if ((lane & 7) == 0) *reinterpret_cast<uint4*>(dst + NB * 32) = pl;
+                    }
                 }
             }
-            __nv_bfloat162 b01 = __floats2bfloat162_rn(d_i, d_f), b23 = __floats2bfloat162_rn(d_g, d_o);
+            __nv_bfloat162 b01, b23;
+            b01.x = hi4[0]; b01.y = hi4[1]; b23.x = hi4[2]; b23.y = hi4[3];
             dgp[e] = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
+            if constexpr (X3) {
+                __nv_bfloat162 l01, l23;
+                l01.x = lo4[0]; l01.y = lo4[1]; l23.x = lo4[2]; l23.y = lo4[3];
+                dgl[e] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+            }
         }
-        if constexpr (HYB) {
-            __threadfence();
-            __syncthreads();
-            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&b_full[(t + 1) & 1], static_cast<uint32_t>(tid));
-        } else if constexpr (BULK) {
+        if constexpr (BULK) {
             fence_proxy_async_smem();
             __syncthreads();
             if (t + 1 < T) {
-                // copy i = (g, mdst): gate g's block of this CTA's 32 units -> slot (4 mb + q) of CTA (g, mdst)'s buffer;
-                // warp w issues copies w and w + 8
-                const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_BYTES;
+                // copy i = (g, mdst): gate g's block [hi | lo] of this CTA's 32 units -> slot (4 mb + q) of CTA (g, mdst)'s
+                // buffer; warp w issues copies w and w + 8
+                const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_STRIDE;
                 const uint32_t bar = smem_u32(&b_full[(t + 1) & 1]);
 #pragma unroll
                 for (int i = warp; i < 16; i += 8) {
                     const int g = i & 3, mdst = i >> 2;
                     if (mdst < MB && warp_leader) {
                         const uint32_t peer = rank_of(g, mdst);
-                        bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * OUT_CHUNKS), BLK_BYTES,
+                        bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * PARTS * OUT_CHUNKS), BLK_STRIDE,
                                           mapa_shared(bar, peer));
                     }
                 }
                 if (warp_leader) bulk_commit();
             }
-        } else if constexpr (PUSH) {
-            __syncthreads();
-            if (t + 1 < T) {
-                // gate g's chunks of this CTA's 32 units go to the operand buffer of every CTA (g, mb')
-                const uint32_t next_base = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_BYTES;
-                const int per_gate = OUT_CHUNKS * MB;
-                for (int idx = tid; idx < 4 * per_gate; idx += LSTM_THREADS) {
-                    const int g = idx / per_gate, r = idx - g * per_gate;
-                    const int mdst = r / OUT_CHUNKS, c = r - mdst * OUT_CHUNKS;
-                    st_cluster_v4(mapa_shared(next_base + c * 16, rank_of(g, mdst)), sOut[g * OUT_CHUNKS + c]);
-                }
-            }
-            __syncthreads();
-            if (t + 1 < T && tid < ctas) mbar_arrive_remote(&b_full[(t + 1) & 1], static_cast<uint32_t>(tid));
         } else {
             __threadfence();
             __syncthreads();
@@ -1041,260 +1028,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int gn = p.n0 + grp * NB + warp + 8 * e;
-            if (gn < N)
+            if (gn < N) {
                 *reinterpret_cast<uint2*>(p.dg + (static_cast<size_t>(tt) * N + gn) * G8 + dg_col) = dgp[e];
+                if constexpr (X3) *reinterpret_cast<uint2*>(p.dg_lo + (static_cast<size_t>(tt) * N + gn) * G8 + dg_col) = dgl[e];
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // no CTA exits while a peer may still address its shared memory
-    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// BPTT, software-pipelined like lstm_fwd_pipe_kernel: the 16 batch columns of a group are two independent chains
-// (half A = columns 0-7, half B = 8-15). Per half-step a CTA (gate q, unit block mb) goes through
-//   M  : partial dh[128 units, 8] = W_q^T slice x dG_q image                       (tensor-core warps 8-11)
-//   E.1: accumulators -> staging, one 1 KB block per owner CTA (lq, mb)              (element warps 0-7)
-//   C  : four bulk copies (reduce-scatter of the gate partials)                     (copy warps 12-15)
-//   E.2: dh = dh_in + four landed partials, LSTM cell backward, four gate-gradient blocks of its 32 units -> staging
-//   C  : sixteen bulk copies: gate g's block -> operand image of every CTA (g, *)   (all-gather)
-// The element warps run A.1, B.1, A.2, B.2; while one half waits for a hand-off the other half is processed, so the
-// two DSMEM exchanges and the MMA chain of a half overlap the element work of the other half.
-// Buffer reuse needs no extra waits: a staging / receive block is rewritten only after a hand-off that transitively
-// required every earlier copy out of (or into) it to have landed (see the per-buffer notes below).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PIPE_THREADS, 1)
-lstm_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmUnused, BwdParams p) {
-    constexpr int NB = 16, HB = 8;
-    constexpr uint32_t BLK_BYTES = NB * 64, HALF_BYTES = HB * 64;
-    constexpr uint32_t PART_BYTES = HB * 32 * 4;     // one partial block: [8 columns][32 units] f32
-    constexpr uint32_t ACC_COLS = 128;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int H = p.H, T = p.T, N = p.N;
-    const int img_bytes = H * NB * 2;
-    uint8_t* sB = smem;                                                        // [2 parities] dG_q operand image
-    float* sR = reinterpret_cast<float*>(sB + 2 * img_bytes);                  // [half][4 source gates][8][32] landed partials
-    float* sP = sR + 2 * 4 * HB * 32;                                          // [half][4 owner CTAs][8][32] partials to send
-    uint8_t* sOut = reinterpret_cast<uint8_t*>(sP + 2 * 4 * HB * 32);          // [half][parity][4 gates][HALF_BYTES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * 2 * 4 * HALF_BYTES);
-    uint64_t* b_full = bars;          // [half][parity]: gate q's dG image half has landed
-    uint64_t* acc_full = bars + 4;    // [half]
-    uint64_t* p_ready = bars + 6;     // [half]: partials staged by all element warps
-    uint64_t* r_full = bars + 8;      // [half]: the four gate partials of this CTA's 32 units have landed
-    uint64_t* g_ready = bars + 10;    // [half]: gate-gradient blocks staged
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    (void)tmUnused;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    announce_resident(p.resident);
-    const int q = blockIdx.x, mb = blockIdx.y, MB = gridDim.y;
-    const int dir = blockIdx.z / p.groups, grp = blockIdx.z % p.groups;
-    const int ctas = 4 * MB;
-    const int kblocks = H / 64;
-    auto rank_of = [&](int qq, int mm) -> uint32_t { return static_cast<uint32_t>(qq + 4 * mm); };
-
-    if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&b_full[i], 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc_full[i], 4);
-            mbar_init(&p_ready[i], 8);
-            mbar_init(&r_full[i], 1);
-            mbar_init(&g_ready[i], 8);
-        }
-        fence_mbar_init();
-        for (int i = 0; i < 4; ++i) mbar_expect_tx(&b_full[i], ctas * HALF_BYTES);
-        for (int i = 0; i < 2; ++i) mbar_expect_tx(&r_full[i], 4 * PART_BYTES);
-    }
-    uint32_t tmem_cols = 256;
-    while (tmem_cols < ACC_COLS + H / 2) tmem_cols <<= 1;
-    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-    for (int i = tid; i < 2 * img_bytes / 16; i += PIPE_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    cluster_sync_all();
-    if (warp < 4)
-        load_weights_to_tmem(p.w + (static_cast<size_t>(dir * 4 + q) * H + mb * 128) * H, H, tmem_base, ACC_COLS, warp, lane);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
-#define BTRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[t * 16 + (k)] = clock64(); } while (0)
-
-    if (warp >= 12) {
-        // ---------------- copy warps --------------------------------------------------------------------------------
-        const int w = warp - 12;
-        for (int t = 0; t < T; ++t) {
-            // reduce-scatter: warp w ships the partial block of owner CTA (w, mb) into slot q of its receive buffer.
-            // sP[half] is rewritten one step later, after this CTA's next dG image has landed, which needed every
-            // row-mate's element phase of this step, i.e. these copies had landed.
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                mbar_wait(&p_ready[half], t & 1);
-                if (w == 0 && half == 0) BTRACE(8);
-                if (lane == 0) {
-                    const uint32_t peer = rank_of(w, mb);
-                    bulk_copy_to_peer(mapa_shared(smem_u32(sR + ((half * 4 + q) * HB) * 32), peer),
-                                      smem_u32(sP + ((half * 4 + w) * HB) * 32), PART_BYTES, mapa_shared(smem_u32(&r_full[half]), peer));
-                }
-                __syncwarp();
-                if (w == 0 && half == 0) BTRACE(9);
-            }
-            // all-gather: copy i = (g, mdst): gate g's block of this CTA's 32 units -> K block (4 mb + q) of CTA (g, mdst).
-            // sOut is double-buffered on the parity of t: a block is rewritten two steps later, when every CTA has finished
-            // the step in between, which it could only start after this block had landed there.
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                mbar_wait(&g_ready[half], t & 1);
-                if (w == 0 && half == 0) BTRACE(10);
-                const int i = w * 4 + lane;
-                const int g = i & 3, mdst = i >> 2;
-                if (t + 1 < T && lane < 4 && mdst < MB) {
-                    const uint32_t peer = rank_of(g, mdst);
-                    const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_BYTES + half * HALF_BYTES;
-                    bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + (((half * 2 + (t & 1)) * 4) + g) * HALF_BYTES), HALF_BYTES,
-                                      mapa_shared(smem_u32(&b_full[half * 2 + ((t + 1) & 1)]), peer));
-                }
-                __syncwarp();
-                if (w == 0 && half == 0) BTRACE(11);
-            }
-        }
-    } else if (warp >= 8) {
-        // ---------------- tensor-core warps -------------------------------------------------------------------------
-        const int m = warp - 8;
-        const bool leader = elect_one();
-        for (int t = 0; t < T; ++t) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint64_t* bf = &b_full[half * 2 + (t & 1)];
-                if (t > 0) {
-                    mbar_wait(bf, ((t - 1) >> 1) & 1);
-                    if (m == 0 && lane == 0) mbar_expect_tx(bf, ctas * HALF_BYTES);   // re-arm for step t + 2
-                }
-                tc_fence_after();
-                if (m == 0) BTRACE(12 + 2 * half);
-                const uint32_t b0 = smem_u32(sB) + (t & 1) * img_bytes;
-                const uint32_t dacc = tmem_base + half * 64 + m * NB;
-#pragma unroll 1
-                for (int kb = m; kb < kblocks; kb += 4) {
-                    const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
-                    const uint32_t ta = tmem_base + ACC_COLS + kb * 32;
-                    if (leader) {
-                        umma_bf16_ts(dacc, ta, bd, idesc, kb != m ? 1u : 0u);
-                        umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
-                        umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
-                        umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
-                    }
-                }
-                if (leader) umma_commit(&acc_full[half]);
-                __syncwarp();
-                if (m == 0) BTRACE(13 + 2 * half);
-            }
-        }
-    } else {
-        // ---------------- element warps -----------------------------------------------------------------------------
-        const int lq = warp & 3, ch = warp >> 2;
-        const int unit = mb * 128 + q * 32 + lane;   // the unit this thread finishes in E.2 (batch column = warp)
-        const BnCoef bnk = load_bn_coef(p, dir * H + unit);
-        const int n = warp;
-        const size_t H2 = static_cast<size_t>(2) * H, G8 = static_cast<size_t>(8) * H;
-        const size_t dg_col = static_cast<size_t>(dir) * 4 * H + static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4;
-        const int parts = (kblocks < 4) ? kblocks : 4;
-        const int so_off = n * 32 + (((lane >> 3) ^ ((n >> 1) & 3)) << 3) + (lane & 7);   // bf16 slot of (row n, unit lane)
-        float dc_carry[2] = {0.0f, 0.0f};
-        float dh_in[2], bx_in[2], c_t[2], c_p[2];
-        uint2 gts[2];
-        // saved activations / incoming gradient of a whole step (both halves) are fetched together, one step ahead, so
-        // that no younger global load sits between a load and its use
-        auto fetch = [&](int t_) {
-            const int tt_ = dir ? t_ : (T - 1 - t_);
-            const int tprev = dir ? tt_ + 1 : tt_ - 1;
-            const bool has_prev = dir ? (tt_ + 1 < T) : (tt_ >= 1);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int gn = grp * NB + half * HB + n;
-                const bool ok = gn < N && t_ < T;
-                const size_t o = (static_cast<size_t>(ok ? tt_ : 0) * N + (ok ? gn : 0)) * H2 + static_cast<size_t>(dir) * H + unit;
-                dh_in[half] = ok ? __ldg(p.dhout + o) : 0.0f;
-                bx_in[half] = (p.bn_x != nullptr && ok) ? __ldg(p.bn_x + o) : 0.0f;
-                c_t[half] = ok ? __ldg(p.c_save + o) : 0.0f;
-                gts[half] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
-                const size_t op = (static_cast<size_t>((ok && has_prev) ? tprev : 0) * N + (ok ? gn : 0)) * H2 +
-                                  static_cast<size_t>(dir) * H + unit;
-                c_p[half] = (ok && has_prev) ? __ldg(p.c_save + op) : 0.0f;
-            }
-        };
-        fetch(0);
-        for (int t = 0; t < T; ++t) {
-            const int tt = dir ? t : (T - 1 - t);
-            // E.1 (A then B): partial rows -> staging block of their owner CTA
-            if (warp == 0) BTRACE(0);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                mbar_wait(&acc_full[half], t & 1);
-                tc_fence_after();
-                if (warp == 0 && half == 0) BTRACE(1);
-                uint32_t acc[4];
-                load_partial_sums<4>(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + half * 64 + half * HB + ch * 4, NB, parts,
-                                     acc);
-                tc_fence_before();
-                float* stage = sP + ((half * 4 + lq) * HB + ch * 4) * 32 + lane;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) stage[c * 32] = __uint_as_float(acc[c]);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_ready[half]);
-                if (warp == 0) BTRACE(2 + half);
-            }
-            // E.2 (A then B): finish 32 units x 8 columns
-            uint2 dgp[2];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                mbar_wait(&r_full[half], t & 1);
-                if (warp == 0 && lane == 0) mbar_expect_tx(&r_full[half], 4 * PART_BYTES);   // re-arm for the next step
-                if (warp == 0) BTRACE(4 + 2 * half);
-                float dh = bnk.a * dh_in[half] + bnk.b * bx_in[half] + ((grp * NB + half * HB + n < N) ? bnk.d : 0.0f);
-#pragma unroll
-                for (int src = 0; src < 4; ++src) dh += sR[((half * 4 + src) * HB + n) * 32 + lane];
-                const __half2 lo = *reinterpret_cast<const __half2*>(&gts[half].x);
-                const __half2 hi = *reinterpret_cast<const __half2*>(&gts[half].y);
-                const float gi = __low2float(lo), gf = __high2float(lo), gg = __low2float(hi), go = __high2float(hi);
-                const float tc = fast_tanh(c_t[half]);
-                const float d_o = dh * tc * go * (1.0f - go);
-                const float dc = dc_carry[half] + dh * go * (1.0f - tc * tc);
-                const float d_i = dc * gg * gi * (1.0f - gi);
-                const float d_f = dc * c_p[half] * gf * (1.0f - gf);
-                const float d_g = dc * gi * (1.0f - gg * gg);
-                dc_carry[half] = dc * gf;
-                __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut + ((half * 2 + (t & 1)) * 4) * HALF_BYTES) + so_off;
-                so[0 * (HALF_BYTES / 2)] = __float2bfloat16(d_i);
-                so[1 * (HALF_BYTES / 2)] = __float2bfloat16(d_f);
-                so[2 * (HALF_BYTES / 2)] = __float2bfloat16(d_g);
-                so[3 * (HALF_BYTES / 2)] = __float2bfloat16(d_o);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&g_ready[half]);
-                if (warp == 0) BTRACE(5 + 2 * half);
-                __nv_bfloat162 b01 = __floats2bfloat162_rn(d_i, d_f), b23 = __floats2bfloat162_rn(d_g, d_o);
-                dgp[half] = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
-            }
-            // off the critical path: dG rows for the dX / dW GEMMs, then next step's saved activations
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int gn = grp * NB + half * HB + n;
-                if (gn < N) *reinterpret_cast<uint2*>(p.dg + (static_cast<size_t>(tt) * N + gn) * G8 + dg_col) = dgp[half];
-            }
-            fetch(t + 1);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -1714,16 +1456,11 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-bool weights_in_tmem() {
-    const char* e = getenv("CTCB200_LSTM_A");  // "smem" keeps the weight slice in shared memory (A/B comparison runs)
-    return !(e && e[0] == 's');
-}
-
-// H in (512, 640]: the two-tile cluster kernels (64 units per CTA); CTCB200_LSTM_EXCHANGE=global keeps the old path
+// H in (512, 640]: the two-tile cluster kernels (64 units per CTA); CTCB200_LSTM_EXCHANGE=global keeps the global-exchange path
 bool two_tile_path(int H) {
     const char* e = getenv("CTCB200_LSTM_EXCHANGE");
     if (e && e[0] == 'g') return false;
-    return H > 512 && H <= 640 && H % 128 == 0 && weights_in_tmem();
+    return H > 512 && H <= 640 && H % 128 == 0;
 }
 
 // CTCB200_LSTM_PIPE=0 selects the un-pipelined forward kernel (one element phase per step over all 16 columns)
@@ -1732,16 +1469,8 @@ bool pipelined_fwd() {
     return e == nullptr || e[0] != '0';
 }
 
-// The pipelined BPTT kernel is correct (tools/gpu_check9.py) but not faster: with two exchanges per step the kernel sits at
-// ~80 % of the DSMEM fabric's bandwidth either way (profiles/lstm_trace_r1.txt). Opt in with CTCB200_LSTM_PIPE_BWD=1.
-bool pipelined_bwd() {
-    const char* e = getenv("CTCB200_LSTM_PIPE_BWD");
-    return e != nullptr && e[0] == '1';
-}
-
 // warps that issue slices of the per-step MMA chain (each into its own TMEM accumulator, 64 columns in total)
-int mma_issuers(int NB, int H, bool a_tmem) {
-    if (!a_tmem) return 1;
+int mma_issuers(int NB, int H) {
     int n = 64 / NB;  // accumulators that fit in front of the weight columns
     const char* e = getenv("CTCB200_LSTM_MMA_ISSUERS");
     if (e) n = atoi(e);
@@ -1750,29 +1479,25 @@ int mma_issuers(int NB, int H, bool a_tmem) {
     return n < 1 ? 1 : n;
 }
 
-size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool a_tmem) {
-    const bool push = ex == 1 || ex == 3;
-    size_t b = (a_tmem ? 0 : static_cast<size_t>(128) * H * 2) + static_cast<size_t>(push ? 2 : 1) * H * NB * 2;
-    if (bwd) b += static_cast<size_t>(4) * NB * 32 * 4 + (push ? static_cast<size_t>(4) * NB * 4 * 16 : 0) +
-                  (ex == 3 ? static_cast<size_t>(4) * NB * 32 * 4 : 0);
-    else b += static_cast<size_t>(32) * (NB * 4 + 4) * 4 + (push ? static_cast<size_t>(NB) * 4 * 16 : 0);
+size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool x3) {
+    const bool bulk = ex == 3;
+    const size_t parts = x3 ? 2 : 1;
+    size_t b = (x3 ? static_cast<size_t>(128) * H * 2 : 0) + static_cast<size_t>(bulk ? 2 : 1) * H * NB * 2 * parts;
+    if (bwd) b += static_cast<size_t>(4) * NB * 32 * 4 + (bulk ? static_cast<size_t>(4) * parts * NB * 4 * 16 + static_cast<size_t>(4) * NB * 32 * 4 : 0);
+    else b += static_cast<size_t>(32) * (NB * 4 + 4) * 4 + (bulk ? parts * NB * 4 * 16 : 0);
     return b + 64 + 1024;
 }
 
 // How the CTAs of one (direction, batch group) hand h_t / dG_t to each other every step:
-//   1                         one thread-block cluster; h_t / dG_t pushed with DSMEM stores, remote mbarrier hand-off
-//   2                         one cluster; data through L2, hand-off on remote (DSMEM) mbarriers
-//   0 (H > 512)               global image + global release/acquire counter, cooperative launch
 //   3 (default for H <= 512)  one cluster; one bulk (TMA-engine) DSMEM copy per peer, complete_tx on the peer's mbarrier
-// CTCB200_LSTM_EXCHANGE = global | push | hybrid | bulk overrides the choice (A/B measurements).
+//   0 (H > 512, or no cluster of the needed size can be scheduled)  global image + global release/acquire counter,
+//                             cooperative launch
+// CTCB200_LSTM_EXCHANGE=global forces 0 (A/B measurements). Measured on B200 (cfg2, NB=16, cycles/step): bulk 3.2k
+// (2.5k pipelined), global 9.3k; the DSMEM-store and L2+mbarrier variants of round 1 (6.6k / 6.8k) were removed.
 int exchange_mode(int H) {
-    const bool fits = H <= 512;  // H/32 CTAs (forward) and 4*H/128 CTAs (backward) fit one cluster of <= 16
     const char* e = getenv("CTCB200_LSTM_EXCHANGE");
     if (e && e[0] == 'g') return 0;
-    if (!fits) return 0;
-    if (e && e[0] == 'h') return 2;
-    if (e && e[0] == 'p') return 1;
-    return 3;  // measured on B200 (cfg2, NB=16, cycles/step): bulk 4.5k, push 6.6k, hybrid 6.8k, global 9.3k
+    return H <= 512 ? 3 : 0;  // H/32 CTAs (forward) and 4*H/128 CTAs (backward) fit one cluster of <= 16
 }
 
 int pick_nb(int N, int H, int force_nb, bool bwd, bool cl) {
@@ -1788,24 +1513,6 @@ int pick_nb(int N, int H, int force_nb, bool bwd, bool cl) {
 }
 
 // Can at least one cluster of this shape be resident? (fails on parts / partitions whose GPCs are too small)
-template <typename Kern>
-bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads);
-
-template <typename Kern>
-bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads = LSTM_THREADS) {
-    // the answer depends only on (kernel, cluster shape, shared memory): remember the last few probes
-    struct Entry { const void* k; unsigned cx, cy; size_t smem; bool ok; };
-    static Entry cache[16];
-    static int n_cache = 0;
-    for (int i = 0; i < n_cache; ++i)
-        if (cache[i].k == reinterpret_cast<const void*>(kern) && cache[i].cx == cluster.x && cache[i].cy == cluster.y &&
-            cache[i].smem == smem)
-            return cache[i].ok;
-    const bool ok = cluster_probe(kern, grid, cluster, smem, threads);
-    if (n_cache < 16) cache[n_cache++] = Entry{reinterpret_cast<const void*>(kern), cluster.x, cluster.y, smem, ok};
-    return ok;
-}
-
 template <typename Kern>
 bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
@@ -1834,15 +1541,33 @@ bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads)
     return n >= 1;
 }
 
+template <typename Kern>
+bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads = LSTM_THREADS) {
+    // the answer depends only on (device, kernel, cluster shape, shared memory): remember the last few probes
+    struct Entry { int dev; const void* k; unsigned cx, cy; size_t smem; bool ok; };
+    static Entry cache[32];
+    static int n_cache = 0;
+    const int dev = current_device();
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].dev == dev && cache[i].k == reinterpret_cast<const void*>(kern) && cache[i].cx == cluster.x &&
+            cache[i].cy == cluster.y && cache[i].smem == smem)
+            return cache[i].ok;
+    const bool ok = cluster_probe(kern, grid, cluster, smem, threads);
+    if (n_cache < 32) cache[n_cache++] = Entry{dev, reinterpret_cast<const void*>(kern), cluster.x, cluster.y, smem, ok};
+    return ok;
+}
+
 using FwdKern = void (*)(CUtensorMap, FwdParams);
 using BwdKern = void (*)(CUtensorMap, BwdParams);
-FwdKern fwd_kernel(int NB, int ex) {
-    if (NB == 16) return ex == 1 ? lstm_fwd_kernel<16, 1> : ex == 2 ? lstm_fwd_kernel<16, 2> : ex == 3 ? lstm_fwd_kernel<16, 3> : lstm_fwd_kernel<16, 0>;
-    return ex == 1 ? lstm_fwd_kernel<32, 1> : ex == 2 ? lstm_fwd_kernel<32, 2> : ex == 3 ? lstm_fwd_kernel<32, 3> : lstm_fwd_kernel<32, 0>;
+FwdKern fwd_kernel(int NB, int ex, bool x3) {
+    if (x3) return ex == 3 ? lstm_fwd_kernel<16, 3, true> : lstm_fwd_kernel<16, 0, true>;
+    if (NB == 16) return ex == 3 ? lstm_fwd_kernel<16, 3, false> : lstm_fwd_kernel<16, 0, false>;
+    return ex == 3 ? lstm_fwd_kernel<32, 3, false> : lstm_fwd_kernel<32, 0, false>;
 }
-BwdKern bwd_kernel(int NB, int ex) {
-    if (NB == 16) return ex == 1 ? lstm_bwd_kernel<16, 1> : ex == 2 ? lstm_bwd_kernel<16, 2> : ex == 3 ? lstm_bwd_kernel<16, 3> : lstm_bwd_kernel<16, 0>;
-    return ex == 1 ? lstm_bwd_kernel<32, 1> : ex == 2 ? lstm_bwd_kernel<32, 2> : ex == 3 ? lstm_bwd_kernel<32, 3> : lstm_bwd_kernel<32, 0>;
+BwdKern bwd_kernel(int NB, int ex, bool x3) {
+    if (x3) return ex == 3 ? lstm_bwd_kernel<16, 3, true> : lstm_bwd_kernel<16, 0, true>;
+    if (NB == 16) return ex == 3 ? lstm_bwd_kernel<16, 3, false> : lstm_bwd_kernel<16, 0, false>;
+    return ex == 3 ? lstm_bwd_kernel<32, 3, false> : lstm_bwd_kernel<32, 0, false>;
 }
 
 template <typename Kern, typename Params>
@@ -1857,9 +1582,12 @@ int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool coope
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attrs[3];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = cluster.x; attrs[0].val.clusterDim.y = cluster.y; attrs[0].val.clusterDim.z = cluster.z;
-    int n_attrs = 1;
+    int n_attrs = 0;
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        attrs[n_attrs].id = cudaLaunchAttributeClusterDimension;
+        attrs[n_attrs].val.clusterDim.x = cluster.x; attrs[n_attrs].val.clusterDim.y = cluster.y; attrs[n_attrs].val.clusterDim.z = cluster.z;
+        ++n_attrs;
+    }
     if (start_event != nullptr) {
         // programmatic event: fires once every block of this grid has started, i.e. the grid is resident — other streams can
         // cudaStreamWaitEvent on it to hand the remaining SMs to independent work (a dependency the CUDA scheduler sees)
@@ -1888,13 +1616,57 @@ int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool coope
     return OK;
 }
 
+// development aid (CTCB200_LSTM_TRACE=1): per-phase cycle breakdown of the forward recurrence on stderr
+struct FwdTraceDump {
+    const FwdParams& p; cudaStream_t s; bool pipe;
+    ~FwdTraceDump() {
+        if (!p.trace) return;
+        cudaStreamSynchronize(s);
+        const int T = p.T;
+        long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
+        cudaMemcpy(h, p.trace, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost);
+        if (pipe) {
+            // stamps relative to the start of half A's element phase: A0..A5 = start, acc ready, loaded, gates regrouped,
+            // h staged + arrive, stores issued; B0..B4 likewise; [11] = copy warp issued half A; M: hA landed, A issued,
+            // hB landed, B issued
+            double rel[16] = {0}, tot = 0;
+            int cnt = 0;
+            for (int t = 8; t + 1 < T; ++t, ++cnt) {
+                for (int k = 0; k < 16; ++k) rel[k] += double(h[t * 16 + k] - h[t * 16]);
+                tot += double(h[(t + 1) * 16] - h[t * 16]);
+            }
+            fprintf(stderr, "lstm_fwd_pipe trace (cycles, avg over %d steps): step %.0f | A:", cnt, tot / cnt);
+            for (int k = 0; k < 6; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
+            fprintf(stderr, " | B:");
+            for (int k = 6; k < 12; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
+            fprintf(stderr, " | M(hA landed, A issued, hB landed, B issued):");
+            for (int k = 12; k < 16; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
+            fprintf(stderr, "\n");
+            free(h);
+            return;
+        }
+        double acc[16] = {0};
+        int cnt = 0;
+        for (int t = 8; t + 1 < T; ++t, ++cnt) {
+            for (int k = 1; k < 8; ++k) acc[k] += double(h[t * 16 + k] - h[t * 16 + k - 1]);
+            acc[0] += double(h[(t + 1) * 16] - h[t * 16]);
+            for (int k = 9; k < 14; ++k) acc[k] += double(h[t * 16 + k] - h[t * 16 + k - 1]);
+        }
+        fprintf(stderr, "lstm_fwd trace (cycles/step avg over %d steps): total %.0f | t0: start->hfull %.0f, mma issue %.0f, "
+                "commit->acc %.0f, tmem ld %.0f, act+sync %.0f, cell+sync %.0f, push+sync+arrive %.0f | t255: ld %.0f act %.0f "
+                "sync %.0f cell %.0f push %.0f\n", cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt,
+                acc[5] / cnt, acc[6] / cnt, acc[7] / cnt, acc[9] / cnt, acc[10] / cnt, acc[11] / cnt, acc[12] / cnt, acc[13] / cnt);
+        free(h);
+    }
+};
+
 }  // namespace
 }  // namespace ctcb200
 
 using namespace ctcb200;
 
 extern "C" CTCB200_API int64_t ctcb200_lstm_scratch_bytes(int N, int H) {
-    // two directions x groups(16-wide worst case) x (4 gates x 2 parities) images + flags
+    // two directions x groups(16-wide worst case) x (4 gates x 2 parities) images (32-wide, or 16-wide hi+lo) + flags
     const int64_t groups = (N + 15) / 16;
     return 2 * groups * 8 * static_cast<int64_t>(H) * 32 * 2 + 2 * groups * 32 * 4 + 1024;
 }
@@ -1910,13 +1682,21 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd_ctas(int N, int H, int batch_tile) {
     return total < sms ? total : sms;
 }
 
-extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, float* hout, float* c_save,
-                                            void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
-                                            ctcb200_stream_t stream_) {
+extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
+                                            float* c_save, void* gates_save, void* scratch, int T, int N, int H,
+                                            int batch_tile, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool x3 = whh_lo_packed != nullptr;
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_fwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_fwd: hidden size %d must be a multiple of 128 in [128,640]", H);
-    if (two_tile_path(H)) {
+    FwdParams p;
+    p.gx = gx; p.hout = hout; p.c_save = c_save;
+    p.gates_save = x3 ? nullptr : static_cast<uint2*>(gates_save);
+    p.gates_save32 = x3 ? static_cast<float4*>(gates_save) : nullptr;
+    p.himg = nullptr; p.flags = nullptr; p.trace = nullptr; p.act_approx = 0;
+    p.w = static_cast<const __nv_bfloat16*>(whh_packed);
+    p.T = T; p.N = N; p.H = H; p.n0 = 0;
+    if (!x3 && two_tile_path(H)) {
         // H > 512: 64 units per CTA (tile 0 in TMEM, tile 1 in shared memory), H/64 CTAs per cluster, NB = 16
         constexpr int NB2 = 16;
         const int groups2 = (N + NB2 - 1) / NB2;
@@ -1926,42 +1706,33 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         const size_t smem2 = static_cast<size_t>(128) * H * 2 + static_cast<size_t>(2) * H * NB2 * 2 +
                              static_cast<size_t>(2) * 32 * (NB2 * 4 + 4) * 4 + static_cast<size_t>(2) * NB2 * 4 * 16 + 64 + 1024;
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
-        FwdParams p2;
-        p2.gx = gx; p2.hout = hout; p2.c_save = c_save; p2.gates_save = static_cast<uint2*>(gates_save);
-        p2.himg = nullptr; p2.flags = nullptr; p2.trace = nullptr; p2.act_approx = 0;
-        p2.w = static_cast<const __nv_bfloat16*>(whh_packed); p2.a_tmem = 1; p2.mma_split = 4;
-        p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
+        p.mma_split = 4; p.groups = groups2;
         if (cluster_ok(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2))
-            return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p2,
+            return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p,
                                     stream);
     }
     int ex = exchange_mode(H);
     {   // fall back to the global-memory exchange when a cluster of this size cannot be scheduled on this device
-        const int nb_try = pick_nb(N, H, batch_tile, false, ex != 0);
-        if (ex != 0 && !cluster_ok(fwd_kernel(nb_try, ex), dim3(H / 32, 2, (N + nb_try - 1) / nb_try), dim3(H / 32, 1, 1),
-                                   lstm_smem_bytes(nb_try, H, false, ex, weights_in_tmem())))
+        const int nb_try = x3 ? 16 : pick_nb(N, H, batch_tile, false, ex != 0);
+        if (ex != 0 && !cluster_ok(fwd_kernel(nb_try, ex, x3), dim3(H / 32, 2, (N + nb_try - 1) / nb_try), dim3(H / 32, 1, 1),
+                                   lstm_smem_bytes(nb_try, H, false, ex, x3)))
             ex = 0;
     }
     const bool cl = ex != 0;
-    const int NB = pick_nb(N, H, batch_tile, false, cl);
+    const int NB = x3 ? 16 : pick_nb(N, H, batch_tile, false, cl);
     const int groups_total = (N + NB - 1) / NB;
-    CUtensorMap tmW;
-    int rc = make_tmap_bf16_2d(&tmW, whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+    CUtensorMap tmW;   // only read by the split-operand kernels (W_lo slice -> shared memory)
+    int rc = make_tmap_bf16_2d(&tmW, x3 ? whh_lo_packed : whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
     if (rc != OK) return rc;
-    const bool a_tmem = weights_in_tmem();
-    const size_t smem = lstm_smem_bytes(NB, H, false, ex, a_tmem);
+    const size_t smem = lstm_smem_bytes(NB, H, false, ex, x3);
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
-    FwdParams p;
-    p.gx = gx; p.hout = hout; p.c_save = c_save; p.gates_save = static_cast<uint2*>(gates_save);
-    p.himg = nullptr; p.flags = nullptr; p.trace = nullptr;
     {
         const char* act = getenv("CTCB200_LSTM_ACT");
-        p.act_approx = (act != nullptr && act[0] == 'a') ? 1 : 0;
+        p.act_approx = (!x3 && act != nullptr && act[0] == 'a') ? 1 : 0;
     }
-    p.w = static_cast<const __nv_bfloat16*>(whh_packed); p.a_tmem = a_tmem ? 1 : 0;
-    p.mma_split = mma_issuers(NB, H, a_tmem);
-    p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
-    if (getenv("CTCB200_LSTM_TRACE")) {  // development aid: per-phase cycle breakdown of the recurrence on stderr
+    p.mma_split = mma_issuers(NB, H);
+    p.groups = groups_total;
+    if (getenv("CTCB200_LSTM_TRACE")) {
         static long long* dbuf = nullptr;
         if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
         if (T <= 4096) {
@@ -1969,49 +1740,8 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
             p.trace = dbuf;
         }
     }
-    struct TraceDump {
-        const FwdParams& p; cudaStream_t s; bool pipe;
-        ~TraceDump() {
-            if (!p.trace) return;
-            cudaStreamSynchronize(s);
-            const int T = p.T;
-            long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
-            cudaMemcpy(h, p.trace, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost);
-            if (pipe) {
-                // stamps relative to the start of half A's element phase: A0..A5 = start, acc ready, loaded, gates regrouped,
-                // h staged + arrive, stores issued; B0..B4 likewise; [11] = copy warp issued half A; M: hA landed, A issued,
-                // hB landed, B issued
-                double rel[16] = {0}, tot = 0;
-                int cnt = 0;
-                for (int t = 8; t + 1 < T; ++t, ++cnt) {
-                    for (int k = 0; k < 16; ++k) rel[k] += double(h[t * 16 + k] - h[t * 16]);
-                    tot += double(h[(t + 1) * 16] - h[t * 16]);
-                }
-                fprintf(stderr, "lstm_fwd_pipe trace (cycles, avg over %d steps): step %.0f | A:", cnt, tot / cnt);
-                for (int k = 0; k < 6; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
-                fprintf(stderr, " | B:");
-                for (int k = 6; k < 12; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
-                fprintf(stderr, " | M(hA landed, A issued, hB landed, B issued):");
-                for (int k = 12; k < 16; ++k) fprintf(stderr, " %.0f", rel[k] / cnt);
-                fprintf(stderr, "\n");
-                free(h);
-                return;
-            }
-            double acc[16] = {0};
-            int cnt = 0;
-            for (int t = 8; t + 1 < T; ++t, ++cnt) {
-                for (int k = 1; k < 8; ++k) acc[k] += double(h[t * 16 + k] - h[t * 16 + k - 1]);
-                acc[0] += double(h[(t + 1) * 16] - h[t * 16]);
-                for (int k = 9; k < 14; ++k) acc[k] += double(h[t * 16 + k] - h[t * 16 + k - 1]);
-            }
-            fprintf(stderr, "lstm_fwd trace (cycles/step avg over %d steps): total %.0f | t0: start->hfull %.0f, mma issue %.0f, "
-                    "commit->acc %.0f, tmem ld %.0f, act+sync %.0f, cell+sync %.0f, push+sync+arrive %.0f | t255: ld %.0f act %.0f "
-                    "sync %.0f cell %.0f push %.0f\n", cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt,
-                    acc[5] / cnt, acc[6] / cnt, acc[7] / cnt, acc[9] / cnt, acc[10] / cnt, acc[11] / cnt, acc[12] / cnt, acc[13] / cnt);
-            free(h);
-        }
-    } trace_dump{p, stream, false};
-    if (cl && ex == 3 && a_tmem && NB == 16 && pipelined_fwd()) {
+    FwdTraceDump trace_dump{p, stream, false};
+    if (cl && !x3 && NB == 16 && pipelined_fwd()) {
         trace_dump.pipe = true;
         // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core warps
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
@@ -2024,54 +1754,50 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     if (cl) {
         // independent clusters: no co-residency requirement between them, one launch covers every batch group
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
-        if (ex == 2) {
-            const size_t img_bytes = static_cast<size_t>(2) * groups_total * 2 * H * NB * 2;
-            CTCB_CUDA(cudaMemsetAsync(scratch, 0, img_bytes, stream));
-            p.himg = static_cast<__nv_bfloat16*>(scratch);
-            if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 2>, grid, cluster, smem, false, tmW, p, stream);
-            return launch_clustered(lstm_fwd_kernel<32, 2>, grid, cluster, smem, false, tmW, p, stream);
-        }
-        if (ex == 3) {
-            if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 3>, grid, cluster, smem, false, tmW, p, stream);
-            return launch_clustered(lstm_fwd_kernel<32, 3>, grid, cluster, smem, false, tmW, p, stream);
-        }
-        if (NB == 16) return launch_clustered(lstm_fwd_kernel<16, 1>, grid, cluster, smem, false, tmW, p, stream);
-        return launch_clustered(lstm_fwd_kernel<32, 1>, grid, cluster, smem, false, tmW, p, stream);
+        return launch_clustered(fwd_kernel(NB, ex, x3), grid, cluster, smem, false, tmW, p, stream);
     }
     const int per_group = 2 * (H / 32);
     const int sms = device_sm_count();
     CTCB_REQUIRE(per_group <= sms, "lstm_fwd: one batch group needs %d CTAs but the device has %d SMs", per_group, sms);
     const int groups_per_launch = sms / per_group;
-    void* kern = NB == 16 ? reinterpret_cast<void*>(lstm_fwd_kernel<16, 0>)
-                          : reinterpret_cast<void*>(lstm_fwd_kernel<32, 0>);
-    CTCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const size_t parts = x3 ? 2 : 1;
     uint8_t* scr = static_cast<uint8_t*>(scratch);
     for (int g0 = 0; g0 < groups_total; g0 += groups_per_launch) {
         const int groups = (groups_total - g0 < groups_per_launch) ? groups_total - g0 : groups_per_launch;
-        const size_t img_bytes = static_cast<size_t>(2) * groups * 2 * H * NB * 2;
+        const size_t img_bytes = static_cast<size_t>(2) * groups * 2 * H * NB * 2 * parts;
         const size_t flag_bytes = static_cast<size_t>(2) * groups * 32 * 4;
         CTCB_CUDA(cudaMemsetAsync(scr, 0, img_bytes + flag_bytes, stream));
         p.himg = reinterpret_cast<__nv_bfloat16*>(scr);
         p.flags = reinterpret_cast<unsigned int*>(scr + img_bytes);
         p.groups = groups; p.n0 = g0 * NB;
-        void* args[] = {const_cast<CUtensorMap*>(&tmW), &p};
-        dim3 grid(H / 32, 2, groups), block(LSTM_THREADS);
-        CTCB_CUDA(cudaLaunchCooperativeKernel(kern, grid, block, args, smem, stream));
+        rc = launch_clustered(fwd_kernel(NB, 0, x3), dim3(H / 32, 2, groups), dim3(1, 1, 1), smem, true, tmW, p, stream);
+        if (rc != OK) return rc;
     }
     return OK;
 }
 
-extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
-                                            const void* gates_save, void* dg, void* scratch, int T, int N, int H,
-                                            int batch_tile, const float* bn_x, const float* bn_coef, void* resident_counter,
-                                            void* resident_event, ctcb200_stream_t stream_) {
+extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
+                                            const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* scratch,
+                                            int T, int N, int H, int batch_tile, const float* bn_x, const float* bn_coef,
+                                            void* resident_counter, void* resident_event, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     cudaEvent_t start_ev = static_cast<cudaEvent_t>(resident_event);
+    const bool x3 = whhT_lo_packed != nullptr;
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE((reinterpret_cast<uintptr_t>(resident_counter) & 3) == 0, "lstm_bwd: resident_counter must be 4-byte aligned");
     CTCB_REQUIRE((bn_x == nullptr) == (bn_coef == nullptr), "lstm_bwd: bn_x and bn_coef must be given together");
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_bwd: hidden size %d must be a multiple of 128 in [128,640]", H);
-    if (two_tile_path(H)) {
+    CTCB_REQUIRE(!x3 || dg_lo != nullptr, "lstm_bwd: the split-operand mode needs dg_lo");
+    BwdParams p;
+    p.dhout = dhout; p.c_save = c_save;
+    p.gates_save = x3 ? nullptr : static_cast<const uint2*>(gates_save);
+    p.gates_save32 = x3 ? static_cast<const float4*>(gates_save) : nullptr;
+    p.dg = static_cast<__nv_bfloat16*>(dg); p.dg_lo = static_cast<__nv_bfloat16*>(dg_lo);
+    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter);
+    p.bn_x = bn_x; p.bn_coef = bn_coef;
+    p.w = static_cast<const __nv_bfloat16*>(whhT_packed);
+    p.T = T; p.N = N; p.H = H; p.n0 = 0;
+    if (!x3 && two_tile_path(H)) {
         constexpr int NB2 = 16;
         const int groups2 = (N + NB2 - 1) / NB2;
         CUtensorMap tmWT2;
@@ -2080,98 +1806,43 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         const size_t smem2 = static_cast<size_t>(128) * (H - 256) * 2 + static_cast<size_t>(4) * H * NB2 * 2 +
                              static_cast<size_t>(4) * NB2 * 32 * 4 * 2 + static_cast<size_t>(8) * NB2 * 4 * 16 + 64 + 1024;
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
-        BwdParams p2;
-        p2.dhout = dhout; p2.c_save = c_save; p2.gates_save = static_cast<const uint2*>(gates_save);
-        p2.dg = static_cast<__nv_bfloat16*>(dg);
-        p2.dgimg = nullptr; p2.flags = nullptr; p2.resident = static_cast<unsigned int*>(resident_counter); p2.trace = nullptr; p2.bn_x = bn_x; p2.bn_coef = bn_coef;
-        p2.w = static_cast<const __nv_bfloat16*>(whhT_packed); p2.a_tmem = 1; p2.mma_split = 4;
-        p2.T = T; p2.N = N; p2.H = H; p2.groups = groups2; p2.n0 = 0;
+        p.mma_split = 4; p.groups = groups2;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
             return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false,
-                                    tmWT2, p2, stream, LSTM_THREADS, start_ev);
+                                    tmWT2, p, stream, LSTM_THREADS, start_ev);
     }
     int ex = exchange_mode(H);
     {
-        const int nb_try = pick_nb(N, H, batch_tile, true, ex != 0);
-        if (ex != 0 && !cluster_ok(bwd_kernel(nb_try, ex), dim3(4, H / 128, 2 * ((N + nb_try - 1) / nb_try)),
-                                   dim3(4, H / 128, 1), lstm_smem_bytes(nb_try, H, true, ex, weights_in_tmem())))
+        const int nb_try = x3 ? 16 : pick_nb(N, H, batch_tile, true, ex != 0);
+        if (ex != 0 && !cluster_ok(bwd_kernel(nb_try, ex, x3), dim3(4, H / 128, 2 * ((N + nb_try - 1) / nb_try)),
+                                   dim3(4, H / 128, 1), lstm_smem_bytes(nb_try, H, true, ex, x3)))
             ex = 0;
     }
     const bool cl = ex != 0;
-    const int NB = pick_nb(N, H, batch_tile, true, cl);
+    const int NB = x3 ? 16 : pick_nb(N, H, batch_tile, true, cl);
     const int groups_total = (N + NB - 1) / NB;
     const int MB = H / 128;
-    CUtensorMap tmWT;
-    int rc = make_tmap_bf16_2d(&tmWT, whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+    CUtensorMap tmWT;   // only read by the split-operand kernels (W^T_lo slice -> shared memory)
+    int rc = make_tmap_bf16_2d(&tmWT, x3 ? whhT_lo_packed : whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
     if (rc != OK) return rc;
-    const bool a_tmem = weights_in_tmem();
-    const size_t smem = lstm_smem_bytes(NB, H, true, ex, a_tmem);
+    const size_t smem = lstm_smem_bytes(NB, H, true, ex, x3);
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
-    BwdParams p;
-    p.dhout = dhout; p.c_save = c_save; p.gates_save = static_cast<const uint2*>(gates_save);
-    p.dg = static_cast<__nv_bfloat16*>(dg);
-    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter); p.trace = nullptr; p.bn_x = bn_x; p.bn_coef = bn_coef;
-    p.w = static_cast<const __nv_bfloat16*>(whhT_packed); p.a_tmem = a_tmem ? 1 : 0;
-    p.mma_split = mma_issuers(NB, H, a_tmem);
-    p.T = T; p.N = N; p.H = H; p.groups = groups_total; p.n0 = 0;
-    if (cl && ex == 3 && a_tmem && NB == 16 && pipelined_bwd()) {
-        // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core and copy warps
-        dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
-        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 3 * 8192 + 128 + 1024;
-        if (cluster_ok(lstm_bwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS)) {
-            if (getenv("CTCB200_LSTM_TRACE") && T <= 4096) {   // development aid: per-phase cycle stamps on stderr
-                static long long* dbuf = nullptr;
-                if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
-                CTCB_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 16 * T, stream));
-                p.trace = dbuf;
-            }
-            rc = launch_clustered(lstm_bwd_pipe_kernel, grid, cluster, smem_p, false, tmWT, p, stream, PIPE_THREADS, start_ev);
-            if (p.trace && rc == OK) {
-                cudaStreamSynchronize(stream);
-                long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
-                cudaMemcpy(h, p.trace, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost);
-                double rel[16] = {0}, tot = 0;
-                int cnt = 0;
-                for (int t = 8; t + 2 < T; ++t, ++cnt) {
-                    for (int k = 0; k < 16; ++k) rel[k] += double(h[t * 16 + k] - h[t * 16]);
-                    tot += double(h[(t + 1) * 16] - h[t * 16]);
-                }
-                fprintf(stderr, "lstm_bwd_pipe trace (cycles after the step start, avg over %d steps): step %.0f | E: A acc ready %.0f, A.1 staged "
-                        "%.0f, B.1 staged %.0f, A partials landed %.0f, A.2 staged %.0f, B partials landed %.0f, B.2 staged %.0f | C(A): "
-                        "p_ready %.0f, rs issued %.0f, g_ready %.0f, ag issued %.0f | M: A image landed %.0f, A issued %.0f, B landed %.0f, "
-                        "B issued %.0f\n", cnt, tot / cnt, rel[1] / cnt, rel[2] / cnt, rel[3] / cnt, rel[4] / cnt, rel[5] / cnt, rel[6] / cnt,
-                        rel[7] / cnt, rel[8] / cnt, rel[9] / cnt, rel[10] / cnt, rel[11] / cnt, rel[12] / cnt, rel[13] / cnt, rel[14] / cnt,
-                        rel[15] / cnt);
-                free(h);
-            }
-            return rc;
-        }
-    }
+    p.mma_split = mma_issuers(NB, H);
+    p.groups = groups_total;
     if (cl) {
         dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
-        if (ex == 2) {
-            const size_t img_bytes = static_cast<size_t>(2) * groups_total * 4 * 2 * H * NB * 2;
-            CTCB_CUDA(cudaMemsetAsync(scratch, 0, img_bytes, stream));
-            p.dgimg = static_cast<__nv_bfloat16*>(scratch);
-            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 2>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
-            return launch_clustered(lstm_bwd_kernel<32, 2>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
-        }
-        if (ex == 3) {
-            if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 3>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
-            return launch_clustered(lstm_bwd_kernel<32, 3>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
-        }
-        if (NB == 16) return launch_clustered(lstm_bwd_kernel<16, 1>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
-        return launch_clustered(lstm_bwd_kernel<32, 1>, grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
+        return launch_clustered(bwd_kernel(NB, ex, x3), grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
     }
     const int per_group = 2 * 4 * MB;
     const int sms = device_sm_count();
     const int budget = (sms / 4) * 4 - 16;  // clusters of 4 strand a few SMs
     CTCB_REQUIRE(per_group <= budget, "lstm_bwd: one batch group needs %d CTAs; device budget %d", per_group, budget);
     const int groups_per_launch = budget / per_group;
+    const size_t parts = x3 ? 2 : 1;
     uint8_t* scr = static_cast<uint8_t*>(scratch);
     for (int g0 = 0; g0 < groups_total; g0 += groups_per_launch) {
         const int groups = (groups_total - g0 < groups_per_launch) ? groups_total - g0 : groups_per_launch;
-        const size_t img_bytes = static_cast<size_t>(2) * groups * 4 * 2 * H * NB * 2;
+        const size_t img_bytes = static_cast<size_t>(2) * groups * 4 * 2 * H * NB * 2 * parts;
         const size_t flag_bytes = static_cast<size_t>(2) * groups * 32 * 4;
         CTCB_CUDA(cudaMemsetAsync(scr, 0, img_bytes + flag_bytes, stream));
         p.dgimg = reinterpret_cast<__nv_bfloat16*>(scr);
@@ -2180,8 +1851,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         if (g0 > 0) p.resident = nullptr;
         dim3 grid(4, MB, 2 * groups), cluster(4, 1, 1);
         const bool coop = getenv("CTCB200_BWD_NO_COOP") == nullptr;  // profilers may reject cooperative + cluster
-        if (NB == 16) rc = launch_clustered(lstm_bwd_kernel<16, 0>, grid, cluster, smem, coop, tmWT, p, stream, LSTM_THREADS, g0 == 0 ? start_ev : nullptr);
-        else rc = launch_clustered(lstm_bwd_kernel<32, 0>, grid, cluster, smem, coop, tmWT, p, stream, LSTM_THREADS, g0 == 0 ? start_ev : nullptr);
+        rc = launch_clustered(bwd_kernel(NB, 0, x3), grid, cluster, smem, coop, tmWT, p, stream, LSTM_THREADS, g0 == 0 ? start_ev : nullptr);
         if (rc != OK) return rc;
     }
     return OK;

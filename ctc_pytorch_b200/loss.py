@@ -70,6 +70,7 @@ class _CTCLossFn(torch.autograd.Function):
         return grad, None, None, None, None, None, None
 
 
+@_lib.on_tensor_device
 def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean", zero_infinity=False):
     """Functional form; argument meaning identical to torch.nn.functional.ctc_loss."""
     _lib.require_cuda(log_probs)

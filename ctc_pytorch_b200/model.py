@@ -84,20 +84,50 @@ def _call(name, *args):
     return _lib.lib().call(name, *args)
 
 
-def _cast_t(src, s_outer, s_inner, n_inner, R, C, scale=None, shift=None, want=True, want_t=False):
-    """fp32 (strided rows) -> bf16 [R, Cp] and/or bf16 [C, (R/n_inner)*n_pad] with the batch axis padded to 8."""
+class _Opnd(object):
+    """A GEMM operand: bf16 `hi`, plus the bf16 remainder `lo` in the split-operand ("x3") precision mode (else None)."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    def rows(self, a, b):
+        return _Opnd(self.hi[a:b], None if self.lo is None else self.lo[a:b])
+
+
+def _gemm(a, b, out=None, **kw):
+    """C = A * B^T on the tcgen05 GEMM; in x3 mode the three products A_lo B_hi + A_hi B_lo + A_hi B_hi accumulate in fp32
+    (the accumulating launches add their tiles into C through the TMA unit)."""
+    if a.lo is None:
+        return ops.gemm_tn(a.hi, b.hi, out=out, **kw)
+    out = ops.gemm_tn(a.lo, b.hi, out=out, **kw)
+    ops.gemm_tn(a.hi, b.lo, out=out, accumulate=True, **kw)
+    ops.gemm_tn(a.hi, b.hi, out=out, accumulate=True, **kw)
+    return out
+
+
+def _cast_t(src, s_outer, s_inner, n_inner, R, C, scale=None, shift=None, want=True, want_t=False, x3=False):
+    """fp32 (strided rows) -> bf16 [R, Cp] and/or bf16 [C, (R/n_inner)*n_pad] with the batch axis padded to 8; returns
+    (_Opnd or None, _Opnd or None). x3: every output also gets its remainder part."""
     dev = src.device
     Cp = _round_up(C, 8)
     n_pad = _round_up(n_inner, 8) if n_inner > 1 else 1
     Rp = _round_up((R // n_inner) * n_pad, 8)
-    dst = torch.empty((R, Cp), dtype=torch.bfloat16, device=dev) if want else None
-    dst_t = None
-    if want_t:
-        alloc = torch.empty if (n_pad == n_inner and Rp == R) else torch.zeros
-        dst_t = alloc((C, Rp), dtype=torch.bfloat16, device=dev)
-    _call("ctcb200_cast_transpose", _lib.ptr(src), s_outer, s_inner, n_inner, _lib.ptr(scale), _lib.ptr(shift),
-          _lib.ptr(dst), Cp, _lib.ptr(dst_t), Rp, n_pad, R, C, _lib.stream())
-    return dst, dst_t
+    outs = []
+    for part in ((0, 1) if x3 else (0,)):
+        dst = None
+        if want:
+            dst = (torch.empty if Cp == C else torch.zeros)((R, Cp), dtype=torch.bfloat16, device=dev)
+        dst_t = None
+        if want_t:
+            alloc = torch.empty if (n_pad == n_inner and Rp == R) else torch.zeros
+            dst_t = alloc((C, Rp), dtype=torch.bfloat16, device=dev)
+        _call("ctcb200_cast_transpose", _lib.ptr(src), s_outer, s_inner, n_inner, _lib.ptr(scale), _lib.ptr(shift),
+              _lib.ptr(dst), Cp, _lib.ptr(dst_t), Rp, n_pad, R, C, part, _lib.stream())
+        outs.append((dst, dst_t))
+    X = _Opnd(outs[0][0], outs[1][0] if x3 else None) if want else None
+    XT = _Opnd(outs[0][1], outs[1][1] if x3 else None) if want_t else None
+    return X, XT
 
 
 _SIDE_STREAMS = {}
@@ -165,8 +195,21 @@ def _overlap_enabled(model):
     return bool(getattr(model, "overlap_wgrad", True))
 
 
+def _dropout_mask(model, shape, p, dev):
+    """uint8 keep-mask for nn.Dropout(p). `model.mask_source(shape, p, device)` (tests: masks shared with the oracle)
+    replaces the framework RNG when set."""
+    src = getattr(model, "mask_source", None)
+    if src is not None:
+        return src(shape, p, dev).to(device=dev, dtype=torch.uint8).contiguous()
+    return (torch.rand(shape, device=dev) >= p).to(torch.uint8)
+
+
+def _inv_keep(p):
+    return 0.0 if p >= 1.0 else 1.0 / (1.0 - p)
+
+
 class _BNState(object):
-    __slots__ = ("mean", "rstd", "scale", "shift")
+    __slots__ = ("mean", "rstd", "scale", "shift", "batch")
 
 
 def _bn_prepare(bn, x2d, R, C, training):
@@ -178,6 +221,7 @@ def _bn_prepare(bn, x2d, R, C, training):
     gamma = bn.weight if bn.affine else None
     beta = bn.bias if bn.affine else None
     use_batch = training or not bn.track_running_stats
+    st.batch = use_batch
     if use_batch:
         st.mean = torch.empty(C, dtype=torch.float32, device=dev)
         st.rstd = torch.empty(C, dtype=torch.float32, device=dev)
@@ -193,10 +237,36 @@ def _bn_prepare(bn, x2d, R, C, training):
               float(bn.eps), _lib.ptr(st.mean), _lib.ptr(st.rstd), _lib.ptr(st.scale), _lib.ptr(st.shift),
               _lib.ptr(ws), _lib.stream())
     else:
-        st.mean = st.rstd = None
+        # frozen statistics (eval mode): the same per-column affine; mean / rstd kept for a possible backward pass
+        st.mean = bn.running_mean.detach().float().contiguous()
+        st.rstd = torch.rsqrt(bn.running_var.detach().float() + float(bn.eps)).contiguous()
         _call("ctcb200_bn_eval_affine", _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(bn.running_mean),
               _lib.ptr(bn.running_var), float(bn.eps), _lib.ptr(st.scale), _lib.ptr(st.shift), C, _lib.stream())
     return st
+
+
+def _packed_weights(model, li, rnn, H, I, Ipad, x3, dev):
+    """bf16 operand layouts of one layer's four weight matrices (hi, and lo in x3 mode). Re-packed only when a parameter
+    changed since the last call (inference / evaluation loops reuse them; an optimizer step bumps the version counters)."""
+    key = (x3, rnn.weight_ih_l0._version, rnn.weight_hh_l0._version, rnn.weight_ih_l0_reverse._version,
+           rnn.weight_hh_l0_reverse._version, rnn.weight_ih_l0.data_ptr(), str(dev))
+    cache = model.__dict__.setdefault("_pack_cache", {})
+    ent = cache.get(li)
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    parts = []
+    for part in ((0, 1) if x3 else (0,)):
+        wih_p = torch.empty((8 * H, Ipad), dtype=torch.bfloat16, device=dev)
+        wihT_p = torch.empty((I, 8 * H), dtype=torch.bfloat16, device=dev)
+        whh_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
+        whhT_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
+        _call("ctcb200_pack_lstm_weights", _lib.ptr(rnn.weight_ih_l0), _lib.ptr(rnn.weight_hh_l0),
+              _lib.ptr(rnn.weight_ih_l0_reverse), _lib.ptr(rnn.weight_hh_l0_reverse), _lib.ptr(wih_p),
+              _lib.ptr(wihT_p), _lib.ptr(whh_p), _lib.ptr(whhT_p), H, I, Ipad, part, _lib.stream())
+        parts.append((wih_p, wihT_p, whh_p, whhT_p))
+    packed = tuple(_Opnd(parts[0][i], parts[1][i] if x3 else None) for i in range(4))
+    cache[li] = (key, packed)
+    return packed
 
 
 class _RnnStackFn(torch.autograd.Function):
@@ -208,6 +278,7 @@ class _RnnStackFn(torch.autograd.Function):
         T, N, I0, s_outer, s_inner, need_grad = geom
         dev = x_src.device
         training = model.training
+        x3 = model.precision == "x3"
         R = T * N
         Np = _round_up(N, 8)
         Rp = T * Np  # width of the time-major transposed operands (batch axis padded to 8)
@@ -215,7 +286,7 @@ class _RnnStackFn(torch.autograd.Function):
         C = model.num_class
         layers = list(model.rnns.children())
         ws = _Workspace()
-        ws.geom, ws.layers_n = geom, len(layers)
+        ws.geom, ws.layers_n, ws.x3 = geom, len(layers), x3
         ws.L = []
         stream = _lib.stream
 
@@ -225,7 +296,7 @@ class _RnnStackFn(torch.autograd.Function):
         defer_t = need_grad and _overlap_enabled(model)
         want_t = need_grad and not defer_t
         ws.defer_t = defer_t
-        X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=want_t)
+        X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=want_t, x3=x3)
         ws.x_src = x_src if defer_t else None
         h_prev = None
         I = I0
@@ -238,36 +309,28 @@ class _RnnStackFn(torch.autograd.Function):
                 rec.I = I
                 if layer.batch_norm is not None:
                     rec.bn = _bn_prepare(layer.batch_norm, h_prev, R, I, training)
-                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, rec.bn.scale, rec.bn.shift, True, want_t)
+                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, rec.bn.scale, rec.bn.shift, True, want_t, x3)
                 else:
-                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, None, None, True, want_t)
+                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, None, None, True, want_t, x3)
             Ipad = _round_up(I, 8)
-            rnn = layer.rnn
-            wih_p = torch.empty((8 * H, Ipad), dtype=torch.bfloat16, device=dev)
-            wihT_p = torch.empty((I, 8 * H), dtype=torch.bfloat16, device=dev)
-            whh_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
-            whhT_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
-            _call("ctcb200_pack_lstm_weights", _lib.ptr(rnn.weight_ih_l0), _lib.ptr(rnn.weight_hh_l0),
-                  _lib.ptr(rnn.weight_ih_l0_reverse), _lib.ptr(rnn.weight_hh_l0_reverse), _lib.ptr(wih_p),
-                  _lib.ptr(wihT_p), _lib.ptr(whh_p), _lib.ptr(whhT_p), H, I, Ipad, stream())
-            gx = ops.gemm_tn(X, wih_p, k=I)  # [R, 8H] f32
+            wih_p, wihT_p, whh_p, whhT_p = _packed_weights(model, li, layer.rnn, H, I, Ipad, x3, dev)
+            gx = _gemm(X, wih_p, k=I)  # [R, 8H] f32
             hout = torch.empty((R, 2 * H), dtype=torch.float32, device=dev)
             c_save = torch.empty((R, 2 * H), dtype=torch.float32, device=dev) if need_grad else None
-            gates = torch.empty((R, 2 * H, 4), dtype=torch.float16, device=dev) if need_grad else None
-            _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p), _lib.ptr(hout), _lib.ptr(c_save),
+            gates = torch.empty((R, 2 * H, 4), dtype=torch.float32 if x3 else torch.float16, device=dev) if need_grad else None
+            _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout), _lib.ptr(c_save),
                   _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, stream())
             del gx
             rec.HT = None
             p_drop = float(layer.dropout.p)
             # H^T pairs dG_t with the *pre-dropout* h_{t-1}: it can only be deferred when hout is not modified in place
             if need_grad and not (defer_t and not (training and p_drop > 0.0)):
-                _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True)
+                _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True, x3=x3)
             rec.h_out = hout if need_grad else None
             rec.mask = None
             if training and p_drop > 0.0:
-                rec.mask = (torch.rand(hout.shape, device=dev) >= p_drop).to(torch.uint8)
-                _call("ctcb200_dropout_apply", _lib.ptr(hout), _lib.ptr(rec.mask), 1.0 / (1.0 - p_drop), hout.numel(),
-                      stream())
+                rec.mask = _dropout_mask(model, hout.shape, p_drop, dev)
+                _call("ctcb200_dropout_apply", _lib.ptr(hout), _lib.ptr(rec.mask), _inv_keep(p_drop), hout.numel(), stream())
             rec.XT, rec.h_in = XT, h_prev
             rec.c_save, rec.gates, rec.wihT_p, rec.whhT_p = c_save, gates, wihT_p, whhT_p
             ws.L.append(rec)
@@ -278,9 +341,9 @@ class _RnnStackFn(torch.autograd.Function):
         fc_bn, fc_lin = (model.fc[0], model.fc[1]) if isinstance(model.fc, nn.Sequential) else (None, model.fc)
         ws.fc_bn = _bn_prepare(fc_bn, h_prev, R, F2, training) if fc_bn is not None else None
         Xfc, XfcT = _cast_t(h_prev, N * F2, F2, N, R, F2, ws.fc_bn.scale if ws.fc_bn else None,
-                            ws.fc_bn.shift if ws.fc_bn else None, True, need_grad)
-        Wfc_b, WfcT_b = _cast_t(fc_lin.weight, F2, F2, 1, C, F2, want=True, want_t=need_grad)
-        logits = ops.gemm_tn(Xfc, Wfc_b, k=F2)  # [R, C]
+                            ws.fc_bn.shift if ws.fc_bn else None, True, need_grad, x3)
+        Wfc_b, WfcT_b = _cast_t(fc_lin.weight, F2, F2, 1, C, F2, want=True, want_t=need_grad, x3=x3)
+        logits = _gemm(Xfc, Wfc_b, k=F2)  # [R, C]
         out = torch.empty((T, N, C), dtype=torch.float32, device=dev)
         _call("ctcb200_log_softmax_fwd", _lib.ptr(logits), logits.stride(0), _lib.ptr(out), R, C, stream())
         ws.h_last, ws.XfcT, ws.WfcT_b, ws.out = h_prev, XfcT, WfcT_b, out
@@ -296,6 +359,7 @@ class _RnnStackFn(torch.autograd.Function):
         if ws is None:
             raise RuntimeError("backward through a forward pass that ran without gradient bookkeeping")
         T, N, H, C, R, Rp, Np = ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np
+        x3 = ws.x3
         dev = g_out.device
         stream = _lib.stream
         F2 = 2 * H
@@ -307,33 +371,46 @@ class _RnnStackFn(torch.autograd.Function):
         side = _side_stream(dev) if overlap else None
         keep = []
         gate = _overlap_gate()
+        sync = getattr(model, "grad_sync", None)   # data parallel: per-layer gradient all-reduce launched from in here
         if overlap:
             res = _resident_state(dev)
             gate_ev, gate_ev_ptr = _resident_event(dev)
             side_ctas = max(8, torch.cuda.get_device_properties(dev).multi_processor_count
                             - int(_lib.lib().dll.ctcb200_lstm_bwd_ctas(N, H, model.batch_tile)))
 
+        def _flat(sizes):
+            """One flat fp32 buffer per layer (views per parameter): its all-reduce is a single collective."""
+            buf = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for n_ in sizes:
+                views.append(buf[off:off + n_])
+                off += n_
+            return buf, views
+
         g = g_out.detach().to(torch.float32).contiguous()
         dlogits = torch.empty((R, C), dtype=torch.float32, device=dev)
         _call("ctcb200_log_softmax_bwd", _lib.ptr(g), _lib.ptr(ws.out), _lib.ptr(dlogits), R, C, stream())
-        dLb, dLT = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=True)
+        dLb, dLT = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=True, x3=x3)
         fc_bn, fc_lin = (model.fc[0], model.fc[1]) if isinstance(model.fc, nn.Sequential) else (None, model.fc)
-        grads[fc_lin.weight] = ops.gemm_tn(dLT, ws.XfcT, k=Rp)              # [C, 2H]
-        dh = ops.gemm_tn(dLb, ws.WfcT_b, k=C)                              # [R, 2H]
+        fc_buf, fc_views = _flat([C * F2] + ([F2, F2] if fc_bn is not None else []))
+        grads[fc_lin.weight] = _gemm(dLT, ws.XfcT, out=fc_views[0].view(C, F2), k=Rp)   # [C, 2H]
+        dh = _gemm(dLb, ws.WfcT_b, k=C)                                                # [R, 2H]
         dws = torch.empty(2 * F2, dtype=torch.float64, device=dev)
         fuse_env = os.environ.get("CTCB200_BN_FUSE", "1") != "0"
 
-        def _bn_backward(bn_mod, st, dy, x_in, C_, below):
+        def _bn_backward(bn_mod, st, dy, x_in, C_, below, dgam, dbet):
             """BatchNorm1d backward of `bn_mod` for gradient dy [R, C_] w.r.t. its output; x_in is its input (the output of the
             layer below). Returns (bn_x, bn_coef) when the input gradient is left to the BPTT kernel of that layer (no dropout
             mask in between), else applies it in place and returns None."""
-            dgam = torch.empty(C_, dtype=torch.float32, device=dev)
-            dbet = torch.empty(C_, dtype=torch.float32, device=dev)
             grads[bn_mod.weight], grads[bn_mod.bias] = dgam, dbet
-            if fuse_env and ws.L[below].mask is None:
+            if (fuse_env and ws.L[below].mask is None) or not st.batch:
                 coef = torch.empty(3 * C_, dtype=torch.float32, device=dev)
                 _call("ctcb200_bn_bwd_coef", _lib.ptr(dy), _lib.ptr(x_in), _lib.ptr(st.mean), _lib.ptr(st.rstd),
                       _lib.ptr(bn_mod.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), stream())
+                if not st.batch:
+                    coef[C_:].zero_()   # frozen statistics: dx = gamma * rstd * dy, no batch-coupling terms
+                    if ws.L[below].mask is not None:   # (cannot happen: masks only exist in training mode)
+                        raise RuntimeError("dropout mask together with frozen BatchNorm statistics")
                 return (x_in, coef)
             _call("ctcb200_bn_bwd", _lib.ptr(dy), _lib.ptr(x_in), _lib.ptr(st.mean), _lib.ptr(st.rstd),
                   _lib.ptr(bn_mod.weight), _lib.ptr(dy), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), stream())
@@ -341,38 +418,49 @@ class _RnnStackFn(torch.autograd.Function):
 
         bn_fuse = None
         if fc_bn is not None:
-            bn_fuse = _bn_backward(fc_bn, ws.fc_bn, dh, ws.h_last, F2, len(layers) - 1)
+            bn_fuse = _bn_backward(fc_bn, ws.fc_bn, dh, ws.h_last, F2, len(layers) - 1, fc_views[1], fc_views[2])
+        if sync is not None:
+            sync.reduce(fc_buf)   # the output layer's gradients travel while the whole RNN stack is still back-propagating
 
         def _wgrad(item, mc):
             """dW_ih, dW_hh (both directions) of one layer from its gate gradients; runs on the current stream."""
-            layer_, rec_, dg_, li_ = item
+            layer_, rec_, dg_, li_, buf_, views_ = item
             rnn = layer_.rnn
             I_ = rec_.I
             XT, HT = rec_.XT, rec_.HT
             if XT is None:   # deferred transposed operands (see forward)
                 if li_ == 0:
-                    _, XT = _cast_t(ws.x_src, ws.geom[3], ws.geom[4], N, R, I_, want=False, want_t=True)
+                    _, XT = _cast_t(ws.x_src, ws.geom[3], ws.geom[4], N, R, I_, want=False, want_t=True, x3=x3)
                 elif rec_.bn is not None:
-                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, rec_.bn.scale, rec_.bn.shift, False, True)
+                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, rec_.bn.scale, rec_.bn.shift, False, True, x3)
                 else:
-                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, None, None, False, True)
+                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, None, None, False, True, x3)
             if HT is None:
-                _, HT = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True)
-            dgT = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
-            _call("ctcb200_transpose_dg", _lib.ptr(dg_), _lib.ptr(dgT), Rp, N, Np, R, H, stream())
-            dwih = ops.gemm_tn(dgT, XT, k=Rp, max_ctas=mc)                 # [8H, I], torch row order
+                _, HT = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True, x3=x3)
+            dgTs = []
+            for d_ in (dg_.hi, dg_.lo):
+                if d_ is None:
+                    dgTs.append(None)
+                    continue
+                t_ = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
+                _call("ctcb200_transpose_dg", _lib.ptr(d_), _lib.ptr(t_), Rp, N, Np, R, H, stream())
+                dgTs.append(t_)
+            dgT = _Opnd(dgTs[0], dgTs[1])
+            dwih = _gemm(dgT, XT, out=views_[0].view(8 * H, I_), k=Rp, max_ctas=mc)     # [8H, I], torch row order
             grads[rnn.weight_ih_l0], grads[rnn.weight_ih_l0_reverse] = dwih[:4 * H], dwih[4 * H:]
+            whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
             if T > 1:
                 K = Rp - Np  # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan
-                grads[rnn.weight_hh_l0] = ops.gemm_tn(dgT[:4 * H], HT[:H], a_koff=Np, b_koff=0, k=K, max_ctas=mc)
-                grads[rnn.weight_hh_l0_reverse] = ops.gemm_tn(dgT[4 * H:], HT[H:], a_koff=0, b_koff=Np, k=K,
-                                                              max_ctas=mc)
+                _gemm(dgT.rows(0, 4 * H), HT.rows(0, H), out=whf, a_koff=Np, b_koff=0, k=K, max_ctas=mc)
+                _gemm(dgT.rows(4 * H, 8 * H), HT.rows(H, 2 * H), out=whr, a_koff=0, b_koff=Np, k=K, max_ctas=mc)
             else:
-                grads[rnn.weight_hh_l0] = torch.zeros_like(rnn.weight_hh_l0)
-                grads[rnn.weight_hh_l0_reverse] = torch.zeros_like(rnn.weight_hh_l0_reverse)
-            if torch.cuda.current_stream(dev) != main:  # consumed on the main stream after the join
-                for g_ in (dwih, grads[rnn.weight_hh_l0], grads[rnn.weight_hh_l0_reverse]):
-                    g_.record_stream(main)
+                whf.zero_()
+                whr.zero_()
+            grads[rnn.weight_hh_l0], grads[rnn.weight_hh_l0_reverse] = whf, whr
+            if sync is not None:
+                sync.reduce(buf_)    # one collective per layer, behind the BPTT kernels of the layers below
+            if torch.cuda.current_stream(dev) != main:  # allocated on the main stream, written here on the side stream
+                buf_.record_stream(torch.cuda.current_stream(dev))
             keep.append((dg_, dgT, XT, HT))  # alive until the streams are joined
 
         pending = None
@@ -380,12 +468,15 @@ class _RnnStackFn(torch.autograd.Function):
         for li in range(len(layers) - 1, -1, -1):
             layer, rec = layers[li], ws.L[li]
             I = rec.I
+            has_bn = li > 0 and layer.batch_norm is not None
+            buf, views = _flat([8 * H * I, 4 * H * H, 4 * H * H] + ([I, I] if has_bn else []))
             if rec.mask is not None:
-                _call("ctcb200_dropout_apply", _lib.ptr(dh), _lib.ptr(rec.mask), 1.0 / (1.0 - float(layer.dropout.p)),
+                _call("ctcb200_dropout_apply", _lib.ptr(dh), _lib.ptr(rec.mask), _inv_keep(float(layer.dropout.p)),
                       dh.numel(), stream())
-            dg = torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev)
-            _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p), _lib.ptr(rec.c_save), _lib.ptr(rec.gates),
-                  _lib.ptr(dg), _lib.ptr(scratch), T, N, H, model.batch_tile,
+            dg = _Opnd(torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev),
+                       torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev) if x3 else None)
+            _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p.hi), _lib.ptr(rec.whhT_p.lo), _lib.ptr(rec.c_save),
+                  _lib.ptr(rec.gates), _lib.ptr(dg.hi), _lib.ptr(dg.lo), _lib.ptr(scratch), T, N, H, model.batch_tile,
                   _lib.ptr(bn_fuse[0]) if bn_fuse else None, _lib.ptr(bn_fuse[1]) if bn_fuse else None,
                   _lib.ptr(res[0]) if (overlap and gate == "memop") else None,
                   gate_ev_ptr if (overlap and gate == "event") else None, stream())
@@ -401,27 +492,33 @@ class _RnnStackFn(torch.autograd.Function):
                     res[1] = (res[1] + 1) & 0xFFFFFFFF
                 if pending is not None:
                     with torch.cuda.stream(side):
+                        if pending[6] is not None:
+                            side.wait_event(pending[6])   # this layer's BatchNorm gradients (main stream) share its bucket
                         if gate == "event":
                             side.wait_event(gate_ev)   # fires when every block of the BPTT grid just launched has started
                         else:
                             _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
-                        _wgrad(pending, side_ctas)
-                pending = (layer, rec, dg, li)
-            else:
-                _wgrad((layer, rec, dg, li), 0)
+                        _wgrad(pending[:6], side_ctas)
+                pending = [layer, rec, dg, li, buf, views, None]
             if li == 0 and ctx.needs_input_grad[1]:
-                dx0 = ops.gemm_tn(dg, rec.wihT_p, k=8 * H)                 # [R, I0] rows (t, n)
+                dx0 = _gemm(dg, rec.wihT_p, k=8 * H)                       # [R, I0] rows (t, n)
                 T0, N0, I0 = ws.geom[0], ws.geom[1], ws.geom[2]
                 grad_x = dx0.view(T0, N0, I0).transpose(0, 1)              # back to the [N, T, I0] layout of x_src
             if li > 0:
-                dh = ops.gemm_tn(dg, rec.wihT_p, k=8 * H)                  # [R, I]
-                bn = layer.batch_norm
-                if bn is not None:
-                    bn_fuse = _bn_backward(bn, rec.bn, dh, rec.h_in, I, li - 1)
+                dh = _gemm(dg, rec.wihT_p, k=8 * H)                        # [R, I]
+                if has_bn:
+                    bn_fuse = _bn_backward(layer.batch_norm, rec.bn, dh, rec.h_in, I, li - 1, views[3], views[4])
+                    if overlap and sync is not None:
+                        pending[6] = torch.cuda.Event()
+                        pending[6].record(main)
+            if not overlap:
+                _wgrad((layer, rec, dg, li, buf, views), 0)
         if overlap:
             if pending is not None:
-                _wgrad(pending, 0)  # the first layer's weight gradients: nothing left to hide them under
+                _wgrad(pending[:6], 0)  # the first layer's weight gradients: nothing left to hide them under
             main.wait_stream(side)  # every gradient is complete before autograd hands them out
+        if sync is not None:
+            sync.wait()             # the collectives are joined on the main stream
         del keep
         ctx.ws = None
         return (None, grad_x, None) + tuple(grads.get(p) for p in ctx.param_list)
@@ -449,6 +546,11 @@ class CTC_Model(nn.Module):
         self.drop_out = drop_out
         self.batch_tile = 0  # 0 = let the library pick the recurrent kernels' batch tile (16 or 32)
         self.overlap_wgrad = True  # weight-gradient GEMMs on a side stream, on the SMs the BPTT kernels leave idle
+        # operand mode of every contraction: "bf16" (fast; gradients within ~1 % of fp32) or "x3" (split bf16 hi+lo, three
+        # tensor-core products per contraction: gradients within 1e-3 of the reference's fp32 arithmetic)
+        self.precision = os.environ.get("CTCB200_PRECISION", "bf16")
+        self.grad_sync = None     # data parallel: a dist.GradSync whose per-layer all-reduces run inside backward()
+        self.mask_source = None   # tests: callable(shape, p, device) -> keep-mask, replaces torch.rand for the dropout masks
 
         rnn_input_size = rnn_param["rnn_input_size"]
         if add_cnn:
@@ -492,6 +594,8 @@ class CTC_Model(nn.Module):
             raise RuntimeError("the B200 path implements bidirectional LSTM layers only")
         if next(self.parameters()).device != x.device:
             raise RuntimeError("model parameters and input must live on the same CUDA device")
+        if self.precision not in ("bf16", "x3"):
+            raise RuntimeError("CTC_Model.precision must be 'bf16' or 'x3' (got %r)" % (self.precision,))
 
     def _rnn_params(self):
         plist = []
@@ -509,9 +613,14 @@ class CTC_Model(nn.Module):
     def forward(self, x, visualize=False):
         # x: [batch, max_seq_length, feat_size]
         self._check_supported(x)
+        with torch.cuda.device(x.device):   # launches, streams and the library's per-device state follow the tensors
+            return self._forward(x, visualize)
+
+    def _forward(self, x, visualize):
         visual = [x] if visualize else None
-        # activations for BPTT are kept only when a backward pass can follow
-        need_grad = self.training and torch.is_grad_enabled()
+        # activations for BPTT are kept whenever a backward pass can follow (train or eval mode alike: eval only freezes
+        # the BatchNorm statistics and disables dropout)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if self.add_cnn:
             from . import cnn
             seq = cnn.conv_front(self, x, need_grad)  # [N, T', Cc*F'] f32, feature index c*F' + f

@@ -4,6 +4,7 @@ import torch
 from . import _lib
 
 
+@_lib.on_tensor_device
 def gemm_tn(a, b, out=None, out_dtype=torch.float32, accumulate=False, a_koff=0, b_koff=0, k=None, tile_n=0,
             max_ctas=0):
     """C[M,N] (+)= A[M, a_koff:a_koff+K] @ B[N, b_koff:b_koff+K]^T on the tcgen05 tensor cores.
@@ -27,6 +28,7 @@ def gemm_tn(a, b, out=None, out_dtype=torch.float32, accumulate=False, a_koff=0,
     return out
 
 
+@_lib.on_tensor_device
 def argmax_nt(log_probs, want_max=False):
     """Frame arg-max of [T,N,C] log-probs -> int32 [N,T] (first index on ties), optionally the max values."""
     _lib.require_cuda(log_probs)
@@ -38,6 +40,7 @@ def argmax_nt(log_probs, want_max=False):
     return (idx, mx) if want_max else idx
 
 
+@_lib.on_tensor_device
 def greedy_decode(log_probs, lengths, blank=0):
     """Arg-max + CTC collapse. Returns (idx [N,T] int32, labels [N,T] int32, label_lengths [N] int32)."""
     _lib.require_cuda(log_probs)
@@ -55,6 +58,7 @@ def greedy_decode(log_probs, lengths, blank=0):
     return idx, labels, out_len
 
 
+@_lib.on_tensor_device
 def edit_distance(hyp, hyp_len, ref, ref_len):
     """Levenshtein distance per row between int32 hypotheses hyp [N, *] (lengths hyp_len) and int64 references ref [N, *]
     (lengths ref_len), all on the device; returns int32 [N]. Feeds on greedy_decode's (labels, label_lengths)."""
@@ -81,6 +85,7 @@ _BEAM_ERRORS = {1: (IndexError, "tuple index out of range (the empty prefix reac
                 3: (KeyError, "unit missing from the language model")}
 
 
+@_lib.on_tensor_device
 def beam_search(tensor, lengths, lm_table, beam_width, lm_alpha, blank=0, input_is_log=True):
     """CTC prefix beam search with a dense bigram table. `tensor` is [T,N,C] log-probs (input_is_log) or
     [N,T,C] float32 probabilities. Returns a list of label lists; raises the exception the reference's

@@ -112,16 +112,22 @@ CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, 
  * bn_coef f32 [3][2H] comes from ctcb200_bn_bwd_coef.
  * batch_tile: 0 = auto, or 16 / 32 batch columns per CTA group. H must be a multiple of 128, <= 640. */
 CTCB200_API int64_t ctcb200_lstm_scratch_bytes(int N, int H);
+/* Split-operand ("x3") precision mode — fp32-grade results from bf16 tensor-core products, for parity with the reference's
+ * fp32 nn.LSTM arithmetic (model_ctc.py:23-26) to 1e-3 on every gradient: each fp32 operand v is carried as two bf16 tensors,
+ * hi = bf16(v) and lo = bf16(v - hi) (`part` = 0 / 1 in the producers below), and a contraction A*B is accumulated in fp32 as
+ * A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (three ctcb200_gemm_tn_bf16 launches with accumulate=1, or three tcgen05.mma chains
+ * inside the recurrent kernels). Passing the *_lo operands to lstm_fwd / lstm_bwd selects the mode there: gates_save is then
+ * 4 x fp32 = 16 bytes per element and lstm_bwd also writes dg_lo. */
 CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const float* whh_f, const float* wih_r,
                                           const float* whh_r, void* wih_p, void* wihT_p, void* whh_p, void* whhT_p,
-                                          int H, int I, int Ipad, ctcb200_stream_t stream);
-CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, float* hout, float* c_save,
-                                 void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
+                                          int H, int I, int Ipad, int part, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
+                                 float* c_save, void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
                                  ctcb200_stream_t stream);
-CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const float* c_save,
-                                 const void* gates_save, void* dg, void* scratch, int T, int N, int H,
-                                 int batch_tile, const float* bn_x, const float* bn_coef, void* resident_counter,
-                                 void* resident_event, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
+                                 const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* scratch, int T,
+                                 int N, int H, int batch_tile, const float* bn_x, const float* bn_coef,
+                                 void* resident_counter, void* resident_event, ctcb200_stream_t stream);
 /* Scheduling aid for overlapping off-critical-path work (weight-gradient GEMMs) with the latency-bound BPTT kernel:
  * resident_event (NULL = off) is a cudaEvent_t (created with timing disabled) attached to the launch as a programmatic event
  * that fires once every block of the BPTT grid has started: cudaStreamWaitEvent on it from another stream is a dependency
@@ -139,10 +145,11 @@ CTCB200_API int ctcb200_stream_wait_geq(ctcb200_stream_t stream, const void* cou
  * per-column affine v*scale[c]+shift[c]; writes bf16 dst [R, dst_pitch] and/or bf16 dstT [C, dstT_pitch], where
  * the transposed column of row r is (r / n_inner)*n_pad + (r % n_inner): the batch axis is padded to n_pad
  * (a multiple of 8) so that the one-time-step shift of the dW_hh contraction stays 16-byte aligned for TMA.
- * Pad columns are not written; the caller zero-fills dstT when n_pad != n_inner. */
+ * Pad columns are not written; the caller zero-fills dstT when n_pad != n_inner. part = 0: bf16(v); part = 1: the
+ * split-operand remainder bf16(v - bf16(v)). */
 CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_outer, int64_t s_inner, int n_inner,
                                        const float* scale, const float* shift, void* dst, int64_t dst_pitch,
-                                       void* dstT, int64_t dstT_pitch, int n_pad, int R, int C,
+                                       void* dstT, int64_t dstT_pitch, int n_pad, int R, int C, int part,
                                        ctcb200_stream_t stream);
 /* dg bf16 [R, 8H] (wih_p column order) -> dgT bf16 [8H, dgT_pitch] with rows in torch gate order (dir, gate, unit) */
 CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64_t dgT_pitch, int n_inner, int n_pad, int R,

@@ -31,12 +31,15 @@ class _RnnBlock(nn.Module):
         self.batch_norm = nn.BatchNorm1d(input_size) if batch_norm else None
         self.rnn = nn.LSTM(input_size=input_size, hidden_size=hidden, bidirectional=True, bias=False)
         self.p = dropout
+        self.fixed_mask = None   # tests: keep-mask [T*N, 2H] shared with the CUDA path instead of this process's RNG
 
     def forward(self, seq):  # seq [T, N, I]
         if self.batch_norm is not None:
             T, N, I = seq.shape
             seq = self.batch_norm(seq.reshape(T * N, I)).reshape(T, N, I)
         out, _ = self.rnn(seq)
+        if self.fixed_mask is not None and self.training and self.p > 0:
+            return out * self.fixed_mask.view_as(out).to(out.dtype) / (1.0 - self.p)
         return F.dropout(out, self.p, self.training)
 
 
@@ -95,17 +98,4 @@ class RefAcousticModel(nn.Module):
         return F.log_softmax(logits, dim=-1)
 
 
-def synthetic_batch(T, N, feat, num_class, max_target, seed):
-    """Seeded synthetic batch of SURVEY.md §8(d): x ~ N(0,1) zeroed past each utterance's end, lengths
-    linspace(1.0 -> 0.6)*T, targets uniform in [1, C-1] with S_n ~ U{S/2..S}, zero padded."""
-    g = torch.Generator().manual_seed(seed)
-    x = torch.randn(N, T, feat, generator=g)
-    lens = torch.linspace(1.0, 0.6, N).mul(T).round().long().clamp(min=1)
-    for n in range(N):
-        x[n, lens[n]:] = 0.0
-    frac = (lens.float() / T)
-    tl = torch.randint(max(1, max_target // 2), max_target + 1, (N,), generator=g)
-    targets = torch.zeros(N, max_target, dtype=torch.long)
-    for n in range(N):
-        targets[n, :tl[n]] = torch.randint(1, num_class, (int(tl[n]),), generator=g)
-    return x, frac, targets, tl
+from ctc_pytorch_b200.synth import synthetic_batch  # noqa: E402,F401  (one generator for bench, tests and golden scripts)

@@ -10,11 +10,18 @@ import os
 import sys
 import types
 
-REF_ROOT = "/root/reference/timit"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the mounted reference in the build container; on the GPU box the byte-for-byte staged copy (oracle/build_ref.py)
+_CANDIDATES = ["/root/reference/timit", os.path.join(_HERE, "_ref", "timit")]
+REF_ROOT = next((c for c in _CANDIDATES if os.path.isfile(os.path.join(c, "models", "model_ctc.py"))), _CANDIDATES[0])
 
 
 def available():
-    return os.path.isdir(REF_ROOT)
+    return os.path.isfile(os.path.join(REF_ROOT, "models", "model_ctc.py"))
+
+
+def is_staged_copy():
+    return REF_ROOT == _CANDIDATES[1]
 
 
 def _install_editdistance_stub():
@@ -23,14 +30,23 @@ def _install_editdistance_stub():
     mod = types.ModuleType("editdistance")
 
     def _eval(a, b):
+        # Levenshtein distance, row by row over the shorter sequence; the in-row dependency d[j] = min(c[j], d[j-1] + 1) is
+        # a running minimum of c[j] - j (numpy), so a 600 x 60 problem costs 60 vector steps instead of 36 000 Python ones
+        import numpy as np
         a, b = list(a), list(b)
-        prev = list(range(len(b) + 1))
-        for i in range(1, len(a) + 1):
-            cur = [i] + [0] * len(b)
-            for j in range(1, len(b) + 1):
-                cur[j] = min(cur[j - 1] + 1, prev[j] + 1, prev[j - 1] + (0 if a[i - 1] == b[j - 1] else 1))
-            prev = cur
-        return prev[len(b)]
+        if len(a) < len(b):
+            a, b = b, a
+        if not b:
+            return len(a)
+        av = np.asarray([hash(x) for x in a], dtype=np.int64)
+        idx = np.arange(len(a) + 1, dtype=np.int64)
+        prev = idx.copy()
+        for i, y in enumerate(b, 1):
+            c = np.empty_like(prev)
+            c[0] = i
+            np.minimum(prev[1:] + 1, prev[:-1] + (av != hash(y)), out=c[1:])
+            prev = np.minimum.accumulate(c - idx) + idx
+        return int(prev[-1])
 
     mod.eval = _eval
     sys.modules["editdistance"] = mod
@@ -56,6 +72,16 @@ def load():
     ns.ctcBeamSearch = bs.ctcBeamSearch
     ns.LanguageModel = lm.LanguageModel
     return ns
+
+
+def load_train_loop():
+    """The reference's own training loop body, `run_epoch` of steps/train_ctc.py:24-69, imported unmodified. Its module-level
+    imports pull in utils/data_loader.py, which needs `kaldiio` (only used to read Kaldi ark files): stubbed."""
+    load()
+    sys.modules.setdefault("kaldiio", types.ModuleType("kaldiio"))
+    import importlib
+    mod = importlib.import_module("steps.train_ctc")
+    return mod.run_epoch
 
 
 def write_synthetic_arpa(path, units, seed=0, bigram_frac=0.3):
