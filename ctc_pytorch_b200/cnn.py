@@ -1,7 +1,8 @@
 """CUDA execution of the reference's optional CNN front (`self.conv`, timit/models/model_ctc.py:92-116,148):
 a stack of LayerCNN blocks = Conv2d(bias) -> BatchNorm2d -> activation -> [MaxPool2d] -> Dropout.
 
-Each convolution is an im2col (csrc/conv.cu) followed by the tcgen05 GEMM; BatchNorm2d statistics are the
+Each convolution is a direct fp32 kernel (csrc/conv.cu: forward, weight gradient, data gradient from shared-memory
+tiles — exact fp32 like the reference's nn.Conv2d in both precision modes); BatchNorm2d statistics are the
 row-statistics kernels over the M = N*Ho*Wo rows; ReLU is fused with the BatchNorm apply. Supported on the
 CUDA path: 2-D convolutions, ReLU activation, no pooling (the shipped config, conf/ctc_config.yaml:32-40);
 anything else raises instead of silently falling back.
@@ -54,26 +55,10 @@ class _ConvFrontFn(torch.autograd.Function):
                 raise RuntimeError("conv block %d expects %d input channels, got %d" % (bi, conv.in_channels, Cin))
             kh, kw, sh, sw, ph, pw, Ho, Wo = _geometry(conv, Hi, Wi)
             Cout = conv.out_channels
-            K = kh * kw * Cin
-            Kp, Coutp = _round_up(K, 8), _round_up(Cout, 8)
             M = N * Ho * Wo
-            Mp = _round_up(M, 8)
-            cols = torch.empty((M, Kp), dtype=torch.bfloat16, device=dev) if Kp == K else \
-                torch.zeros((M, Kp), dtype=torch.bfloat16, device=dev)
-            geom = (N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw)
-            _call("ctcb200_conv_im2col", _lib.ptr(act), _lib.ptr(cols), Kp, 0, *geom, stream())
-            colsT = None
-            if need_grad:
-                colsT = (torch.empty if Mp == M else torch.zeros)((K, Mp), dtype=torch.bfloat16, device=dev)
-                _call("ctcb200_conv_im2col", _lib.ptr(act), _lib.ptr(colsT), Mp, 1, *geom, stream())
-            w_p = torch.empty((Cout, Kp), dtype=torch.bfloat16, device=dev)
-            w_pT = torch.zeros((K, Coutp), dtype=torch.bfloat16, device=dev) if need_grad else None
-            _call("ctcb200_conv_pack_weight", _lib.ptr(conv.weight), _lib.ptr(w_p), _lib.ptr(w_pT), Cout, Cin, kh, kw, Kp,
-                  Coutp, stream())
-            y = ops.gemm_tn(cols, w_p, k=K)  # [M, Cout] f32
-            del cols
-            if conv.bias is not None:
-                _call("ctcb200_add_bias_rows", _lib.ptr(y), _lib.ptr(conv.bias), M, Cout, stream())
+            geom = (N, Hi, Wi, Cin, Cout, Ho, Wo, kh, kw, sh, sw, ph, pw)
+            y = torch.empty((M, Cout), dtype=torch.float32, device=dev)
+            _call("ctcb200_conv2d_fwd", _lib.ptr(act), _lib.ptr(conv.weight), _lib.ptr(conv.bias), _lib.ptr(y), *geom, stream())
             bn = block.batch_norm
             st = _bn_prepare(bn, y, M, Cout, training) if bn is not None else None
             last = bi == len(blocks) - 1
@@ -92,8 +77,8 @@ class _ConvFrontFn(torch.autograd.Function):
                 mask = _dropout_mask(model, out.shape, p_drop, dev)
                 _call("ctcb200_dropout_apply", _lib.ptr(out), _lib.ptr(mask), _inv_keep(p_drop), out.numel(), stream())
             if need_grad:
-                saved.append(dict(geom=geom, Cout=Cout, K=K, Kp=Kp, Coutp=Coutp, M=M, Mp=Mp, colsT=colsT, w_pT=w_pT,
-                                  y=y, st=st, out=out, strides=strides, mask=mask, p_drop=p_drop))
+                saved.append(dict(geom=geom, Cout=Cout, M=M, x=act, y=y, st=st, out=out, strides=strides, mask=mask,
+                                  p_drop=p_drop))
             act, Hi, Wi, Cin = out, Ho, Wo, Cout
         ctx.saved = saved if need_grad else None
         ctx.model = model
@@ -114,8 +99,8 @@ class _ConvFrontFn(torch.autograd.Function):
         da = g_out.detach().to(torch.float32).contiguous()  # same strided layout as the block's output
         for bi in range(len(blocks) - 1, -1, -1):
             block, rec = blocks[bi], saved[bi]
-            N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw = rec["geom"]
-            Cout, K, M, Mp = rec["Cout"], rec["K"], rec["M"], rec["Mp"]
+            N, Hi, Wi, Cin, Cout, Ho, Wo, kh, kw, sh, sw, ph, pw = rec["geom"]
+            M = rec["M"]
             if rec["mask"] is not None:
                 _call("ctcb200_dropout_apply", _lib.ptr(da), _lib.ptr(rec["mask"]), _inv_keep(rec["p_drop"]), da.numel(),
                       stream())
@@ -131,11 +116,11 @@ class _ConvFrontFn(torch.autograd.Function):
                 st = rec["st"]
                 if st.batch:
                     _call("ctcb200_bn_bwd", _lib.ptr(dz), _lib.ptr(rec["y"]), _lib.ptr(st.mean), _lib.ptr(st.rstd),
-                          _lib.ptr(bn.weight), _lib.ptr(dz), _lib.ptr(dgam), _lib.ptr(dbet), M, Cout, _lib.ptr(ws), stream())
+                          _lib.ptr(bn.weight), _lib.ptr(dz), _lib.ptr(dgam), _lib.ptr(dbet), M, Cout, _lib.ptr(ws), 0, stream())
                 else:   # frozen statistics (eval-mode fine-tuning): dx = gamma * rstd * dy
                     coef = torch.empty(3 * Cout, dtype=torch.float32, device=dev)
                     _call("ctcb200_bn_bwd_coef", _lib.ptr(dz), _lib.ptr(rec["y"]), _lib.ptr(st.mean), _lib.ptr(st.rstd),
-                          _lib.ptr(bn.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), M, Cout, _lib.ptr(ws), stream())
+                          _lib.ptr(bn.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), M, Cout, _lib.ptr(ws), 0, stream())
                     dz.mul_(coef[:Cout])
                 grads[bn.weight], grads[bn.bias] = dgam, dbet
             conv = block.conv
@@ -143,19 +128,14 @@ class _ConvFrontFn(torch.autograd.Function):
                 db = torch.empty(Cout, dtype=torch.float32, device=dev)
                 _call("ctcb200_col_sum", _lib.ptr(dz), _lib.ptr(db), M, Cout, stream())
                 grads[conv.bias] = db
-            # dW[Cout, (r,s,c)] = dY^T [Cout, M] * cols^T [K, M]^T
-            dyb = torch.empty((M, rec["Coutp"]), dtype=torch.bfloat16, device=dev) if rec["Coutp"] == Cout else \
-                torch.zeros((M, rec["Coutp"]), dtype=torch.bfloat16, device=dev)
-            dyT = (torch.empty if Mp == M else torch.zeros)((Cout, Mp), dtype=torch.bfloat16, device=dev)
-            _call("ctcb200_cast_transpose", _lib.ptr(dz), Cout, Cout, 1, None, None, _lib.ptr(dyb), rec["Coutp"],
-                  _lib.ptr(dyT), Mp, 1, M, Cout, 0, stream())
-            dw = ops.gemm_tn(dyT, rec["colsT"], k=Mp)  # [Cout, K]
-            grads[conv.weight] = dw.view(Cout, kh, kw, Cin).permute(0, 3, 1, 2).contiguous()
+            # dW[o, c, r, s] = sum_m dz[m, o] * patch(m)[r, s, c]; per-CTA partial sums reduced in a fixed order
+            dw = torch.empty_like(conv.weight)
+            wws = torch.empty(_lib.lib().dll.ctcb200_conv2d_wgrad_ws_bytes(Cin, Cout, kh, kw), dtype=torch.uint8, device=dev)
+            _call("ctcb200_conv2d_wgrad", _lib.ptr(rec["x"]), _lib.ptr(dz), _lib.ptr(dw), _lib.ptr(wws), *rec["geom"], stream())
+            grads[conv.weight] = dw
             if bi > 0:
-                dcols = ops.gemm_tn(dyb, rec["w_pT"], k=Cout)  # [M, K] f32
                 da = torch.empty((N, Hi, Wi, Cin), dtype=torch.float32, device=dev)
-                _call("ctcb200_conv_col2im", _lib.ptr(dcols), K, _lib.ptr(da), N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw,
-                      stream())
+                _call("ctcb200_conv2d_dgrad", _lib.ptr(dz), _lib.ptr(conv.weight), _lib.ptr(da), *rec["geom"], stream())
         ctx.saved = None
         return (None, None, None) + tuple(grads.get(p) for p in ctx.param_list)
 

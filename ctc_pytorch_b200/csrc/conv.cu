@@ -1,13 +1,12 @@
 // K9 — the optional 2-D convolution front of the acoustic model (LayerCNN, timit/models/model_ctc.py:38-68,
 // applied at model_ctc.py:148): Conv2d(bias) -> BatchNorm2d -> ReLU [-> Dropout].
 //
-// The convolution is lowered to the tensor-core GEMM of gemm.cu: an im2col kernel writes the bf16 patch matrix
-// cols[M = N*Ho*Wo, K = kh*kw*Cin] (and, for training, its transpose, the B operand of the weight-gradient
-// GEMM); BatchNorm2d statistics are per-channel over the M rows, i.e. exactly the row-statistics kernels of
-// elementwise.cu; ReLU is fused with the BatchNorm apply. Activations are kept channel-last ([N,H,W,C] fp32)
-// between blocks so that GEMM outputs need no transposition; the last block writes [N,H,C,W] so that the RNN
+// The convolutions (3x3, 1 or 32 input channels, 32 output channels in the shipped config) are direct fp32 kernels working
+// from shared-memory tiles (forward, weight gradient, data gradient; round 1 lowered them to im2col + the 128-wide tensor-core
+// GEMM tiles, mostly padding: 3.7 ms per cfg3 step). Outputs are rows y[M = N*Ho*Wo, Cout]; BatchNorm2d statistics are
+// per-channel over the M rows, i.e. exactly the row-statistics kernels of elementwise.cu; ReLU is fused with the BatchNorm
+// apply. Activations are kept channel-last ([N,H,W,C] fp32) between blocks; the last block writes [N,H,C,W] so that the RNN
 // stack sees the reference's feature order c*F' + f (model_ctc.py:153-158).
-// These kernels are HBM streaming kernels (the conv FLOPs are ~0.5 % of the model): coalesced rows, grid-stride.
 #include "common.cuh"
 #include "ctcb200.h"
 
@@ -18,67 +17,213 @@ struct ConvGeom {
     int N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw;
 };
 
-// cols[m, k] with m = (n, ho, wo), k = (r, s, c): x[n, ho*sh - ph + r, wo*sw - pw + s, c] (0 outside).
-// transposed = 0 writes cols [M, Kp] (k fastest), transposed = 1 writes colsT [K, Mp] (m fastest).
-__global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long pitch, ConvGeom g, int transposed) {
-    const long long M = static_cast<long long>(g.N) * g.Ho * g.Wo;
-    const int K = g.kh * g.kw * g.Cin;
-    const long long total = M * K;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        long long m;
-        int k;
-        if (transposed) { k = static_cast<int>(e / M); m = e % M; }
-        else { m = e / K; k = static_cast<int>(e % K); }
-        const int wo = static_cast<int>(m % g.Wo);
-        const int ho = static_cast<int>((m / g.Wo) % g.Ho);
-        const int n = static_cast<int>(m / (static_cast<long long>(g.Wo) * g.Ho));
-        const int c = k % g.Cin, s = (k / g.Cin) % g.kw, r = k / (g.Cin * g.kw);
-        const int hi = ho * g.sh - g.ph + r, wi = wo * g.sw - g.pw + s;
+// ---- direct fp32 convolution (forward, weight gradient, data gradient) ------------------------------------------------
+// The conv front is 0.5 % of the model's FLOPs and its tensors are tall and thin (Cout = 32, K = 9 or 288), so it runs on the
+// fp32 CUDA cores from shared-memory tiles instead of being padded into 128-wide tensor-core tiles: one CTA stages the input
+// rows a band of TH output rows needs (zero-padded halo, channel-last, coalesced row copies) plus the whole weight tensor
+// (<= 36 KB), and computes from shared memory. Exact fp32 arithmetic like the reference's nn.Conv2d (model_ctc.py:46-50).
+constexpr int CONV_THREADS = 256;
+
+struct Band {
+    int TH;        // output rows per band
+    int IH;        // input rows staged per band: (TH - 1) * sh + kh
+    int IW;        // padded input row width in pixels: Wi + 2 * pw
+    int bands;     // bands per image
+};
+__host__ __device__ inline Band make_band(const ConvGeom& g, int TH) {
+    Band b;
+    b.TH = TH;
+    b.IH = (TH - 1) * g.sh + g.kh;
+    b.IW = g.Wi + 2 * g.pw;
+    b.bands = (g.Ho + TH - 1) / TH;
+    return b;
+}
+
+// input rows [hi0, hi0 + IH) of image n -> xs[IH][IW][Cin], zero outside the image
+__device__ __forceinline__ void stage_input_band(const float* __restrict__ x, float* __restrict__ xs, const ConvGeom& g,
+                                                 const Band& b, int n, int hi0) {
+    const int row_elems = b.IW * g.Cin, in_row = g.Wi * g.Cin, pad = g.pw * g.Cin;
+    for (int e = threadIdx.x; e < b.IH * row_elems; e += CONV_THREADS) {
+        const int rr = e / row_elems, ce = e - rr * row_elems;
+        const int hi = hi0 + rr, src = ce - pad;
         float v = 0.0f;
-        if (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi)
-            v = x[((static_cast<long long>(n) * g.Hi + hi) * g.Wi + wi) * g.Cin + c];
-        if (transposed) out[static_cast<long long>(k) * pitch + m] = __float2bfloat16(v);
-        else out[m * pitch + k] = __float2bfloat16(v);
+        if (hi >= 0 && hi < g.Hi && src >= 0 && src < in_row)
+            v = __ldg(x + (static_cast<long long>(n) * g.Hi + hi) * in_row + src);
+        xs[e] = v;
     }
 }
 
-// scatter-add of dcols [M, K] (fp32) back onto dx [N, Hi, Wi, Cin]
-__global__ void __launch_bounds__(256)
-col2im_kernel(const float* __restrict__ dcols, long long pitch, float* __restrict__ dx, ConvGeom g) {
-    const long long M = static_cast<long long>(g.N) * g.Ho * g.Wo;
+// y[m, o] = bias[o] + sum_{r,s,c} x[n, ho*sh-ph+r, wo*sw-pw+s, c] * w[o, c, r, s];  m = (n, ho, wo)
+template <int CG>
+__global__ void __launch_bounds__(CONV_THREADS)
+conv2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, ConvGeom g, int Cout, Band b) {
+    extern __shared__ float smem_f[];
     const int K = g.kh * g.kw * g.Cin;
-    const long long total = M * K;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long m = e / K;
-        const int k = static_cast<int>(e % K);
-        const int wo = static_cast<int>(m % g.Wo);
-        const int ho = static_cast<int>((m / g.Wo) % g.Ho);
-        const int n = static_cast<int>(m / (static_cast<long long>(g.Wo) * g.Ho));
+    float* ws = smem_f;                 // [K][Cout], k = (r, s, c)
+    float* xs = ws + K * Cout;          // [IH][IW][Cin]
+    for (int e = threadIdx.x; e < K * Cout; e += CONV_THREADS) {
+        const int k = e / Cout, o = e - k * Cout;
         const int c = k % g.Cin, s = (k / g.Cin) % g.kw, r = k / (g.Cin * g.kw);
-        const int hi = ho * g.sh - g.ph + r, wi = wo * g.sw - g.pw + s;
-        if (hi >= 0 && hi < g.Hi && wi >= 0 && wi < g.Wi)
-            atomicAdd(&dx[((static_cast<long long>(n) * g.Hi + hi) * g.Wi + wi) * g.Cin + c], dcols[m * pitch + k]);
+        ws[e] = __ldg(w + ((static_cast<long long>(o) * g.Cin + c) * g.kh + r) * g.kw + s);
     }
-}
-
-// torch weight [Cout, Cin, kh, kw] fp32 -> w_p bf16 [Cout, Kp] with k = (r, s, c) and w_pT bf16 [K, Coutp]
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_p,
-                                        __nv_bfloat16* __restrict__ w_pT, int Cout, int Cin, int kh, int kw, int Kp,
-                                        int Coutp) {
-    const int K = kh * kw * Cin;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Cout * Kp; e += gridDim.x * blockDim.x) {
-        const int o = e / Kp, k = e % Kp;
-        float v = 0.0f;
-        if (k < K) {
-            const int c = k % Cin, s = (k / Cin) % kw, r = k / (Cin * kw);
-            v = w[((static_cast<long long>(o) * Cin + c) * kh + r) * kw + s];
+    const int groups = Cout / CG;
+    for (int tile = blockIdx.x; tile < g.N * b.bands; tile += gridDim.x) {
+        const int n = tile / b.bands, ho0 = (tile % b.bands) * b.TH;
+        __syncthreads();
+        stage_input_band(x, xs, g, b, n, ho0 * g.sh - g.ph);
+        __syncthreads();
+        const int rows = min(b.TH, g.Ho - ho0);
+        for (int it = threadIdx.x; it < rows * g.Wo * groups; it += CONV_THREADS) {
+            const int og = it % groups, p = it / groups;
+            const int wo = p % g.Wo, hl = p / g.Wo;
+            float acc[CG];
+#pragma unroll
+            for (int q = 0; q < CG; ++q) acc[q] = bias ? __ldg(bias + og * CG + q) : 0.0f;
+            for (int r = 0; r < g.kh; ++r) {
+                const float* xrow = xs + ((hl * g.sh + r) * b.IW + wo * g.sw) * g.Cin;   // pixel (wo*sw - pw + s) sits at padded index wo*sw + s
+                const float* wrow = ws + (r * g.kw * g.Cin) * Cout + og * CG;
+                for (int sc = 0; sc < g.kw * g.Cin; ++sc) {
+                    const float xv = xrow[sc];
+#pragma unroll
+                    for (int q = 0; q < CG; ++q) acc[q] = fmaf(xv, wrow[sc * Cout + q], acc[q]);
+                }
+            }
+            float* dst = y + ((static_cast<long long>(n) * g.Ho + ho0 + hl) * g.Wo + wo) * Cout + og * CG;
+#pragma unroll
+            for (int q = 0; q < CG; ++q) dst[q] = acc[q];
         }
-        w_p[e] = __float2bfloat16(v);
-        if (k < K && w_pT) w_pT[static_cast<long long>(k) * Coutp + o] = __float2bfloat16(v);
     }
+}
+
+// partial[block][o][c][r][s] = sum over the block's bands of dy[m, o] * x[n, ho*sh-ph+r, wo*sw-pw+s, c]
+__global__ void __launch_bounds__(CONV_THREADS)
+conv2d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial, ConvGeom g,
+                    int Cout, Band b) {
+    extern __shared__ float smem_f[];
+    const int K = g.kh * g.kw * g.Cin;
+    float* xs = smem_f;                                  // [IH][IW][Cin]
+    float* dys = xs + b.IH * b.IW * g.Cin;               // [TH * Wo][Cout]
+    constexpr int MAX_OWN = 40;                          // outputs (o, k) owned by one thread: K * Cout / 256 <= 40
+    float acc[MAX_OWN];
+#pragma unroll
+    for (int i = 0; i < MAX_OWN; ++i) acc[i] = 0.0f;
+    const int total = K * Cout;
+    for (int tile = blockIdx.x; tile < g.N * b.bands; tile += gridDim.x) {
+        const int n = tile / b.bands, ho0 = (tile % b.bands) * b.TH;
+        const int rows = min(b.TH, g.Ho - ho0);
+        __syncthreads();
+        stage_input_band(x, xs, g, b, n, ho0 * g.sh - g.ph);
+        const float* dsrc = dy + (static_cast<long long>(n) * g.Ho + ho0) * g.Wo * Cout;
+        for (int e = threadIdx.x; e < rows * g.Wo * Cout; e += CONV_THREADS) dys[e] = __ldg(dsrc + e);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < MAX_OWN; ++i) {
+            const int idx = threadIdx.x + i * CONV_THREADS;   // (k, o) with o fastest: a warp shares k, lanes differ in o
+            if (idx < total) {
+                const int k = idx / Cout, o = idx - k * Cout;
+                const int c = k % g.Cin, s = (k / g.Cin) % g.kw, r = k / (g.Cin * g.kw);
+                float a = acc[i];
+                for (int hl = 0; hl < rows; ++hl) {
+                    const float* xrow = xs + ((hl * g.sh + r) * b.IW + s) * g.Cin + c;
+                    const float* drow = dys + hl * g.Wo * Cout + o;
+                    for (int wo = 0; wo < g.Wo; ++wo) a = fmaf(drow[wo * Cout], xrow[wo * g.sw * g.Cin], a);
+                }
+                acc[i] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_OWN; ++i) {
+        const int idx = threadIdx.x + i * CONV_THREADS;
+        if (idx < total) {
+            const int k = idx / Cout, o = idx - k * Cout;
+            const int c = k % g.Cin, s = (k / g.Cin) % g.kw, r = k / (g.Cin * g.kw);
+            partial[static_cast<long long>(blockIdx.x) * total + ((static_cast<long long>(o) * g.Cin + c) * g.kh + r) * g.kw + s] = acc[i];
+        }
+    }
+}
+
+// dw[e] = sum over blocks of partial[block][e] (fixed order: deterministic)
+__global__ void conv2d_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int blocks, int total) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    float a = 0.0f;
+    for (int bk = 0; bk < blocks; ++bk) a += partial[static_cast<long long>(bk) * total + e];
+    dw[e] = a;
+}
+
+// dx[n, hi, wi, c] = sum over (r, s) with ho = (hi + ph - r) / sh, wo = (wi + pw - s) / sw integral and in range, and o:
+//                    dy[(n, ho, wo), o] * w[o, c, r, s]
+template <int CG>
+__global__ void __launch_bounds__(CONV_THREADS)
+conv2d_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, ConvGeom g, int Cout,
+                    int TH_in) {
+    extern __shared__ float smem_f[];
+    const int taps = g.kh * g.kw;
+    float* ws = smem_f;                           // [tap][o][c]
+    float* dys = ws + taps * Cout * g.Cin;        // [rows of ho][Wo][Cout]
+    for (int e = threadIdx.x; e < taps * Cout * g.Cin; e += CONV_THREADS) {
+        const int c = e % g.Cin, o = (e / g.Cin) % Cout, tap = e / (g.Cin * Cout);
+        const int r = tap / g.kw, s = tap % g.kw;
+        ws[e] = __ldg(w + ((static_cast<long long>(o) * g.Cin + c) * g.kh + r) * g.kw + s);
+    }
+    const int bands = (g.Hi + TH_in - 1) / TH_in;
+    const int groups = g.Cin / CG;
+    for (int tile = blockIdx.x; tile < g.N * bands; tile += gridDim.x) {
+        const int n = tile / bands, hi0 = (tile % bands) * TH_in;
+        const int rows_in = min(TH_in, g.Hi - hi0);
+        // output rows that can touch input rows [hi0, hi0 + rows_in): ho*sh - ph + r = hi
+        int ho_lo = (hi0 + g.ph - (g.kh - 1) + g.sh - 1) / g.sh;
+        if (hi0 + g.ph - (g.kh - 1) < 0) ho_lo = 0;
+        int ho_hi = (hi0 + rows_in - 1 + g.ph) / g.sh;
+        if (ho_hi > g.Ho - 1) ho_hi = g.Ho - 1;
+        const int nrows = ho_hi - ho_lo + 1;
+        __syncthreads();
+        if (nrows > 0) {
+            const float* dsrc = dy + (static_cast<long long>(n) * g.Ho + ho_lo) * g.Wo * Cout;
+            for (int e = threadIdx.x; e < nrows * g.Wo * Cout; e += CONV_THREADS) dys[e] = __ldg(dsrc + e);
+        }
+        __syncthreads();
+        for (int it = threadIdx.x; it < rows_in * g.Wi * groups; it += CONV_THREADS) {
+            const int cg = it % groups, p = it / groups;
+            const int wi = p % g.Wi, hl = p / g.Wi;
+            const int hi = hi0 + hl;
+            float acc[CG];
+#pragma unroll
+            for (int q = 0; q < CG; ++q) acc[q] = 0.0f;
+            for (int r = 0; r < g.kh; ++r) {
+                const int hn = hi + g.ph - r;
+                if (hn < 0 || hn % g.sh != 0) continue;
+                const int ho = hn / g.sh;
+                if (ho < ho_lo || ho > ho_hi) continue;
+                for (int s = 0; s < g.kw; ++s) {
+                    const int wn = wi + g.pw - s;
+                    if (wn < 0 || wn % g.sw != 0) continue;
+                    const int wo = wn / g.sw;
+                    if (wo >= g.Wo) continue;
+                    const float* drow = dys + ((ho - ho_lo) * g.Wo + wo) * Cout;
+                    const float* wtap = ws + (r * g.kw + s) * Cout * g.Cin + cg * CG;
+                    for (int o = 0; o < Cout; ++o) {
+                        const float dv = drow[o];
+#pragma unroll
+                        for (int q = 0; q < CG; ++q) acc[q] = fmaf(dv, wtap[o * g.Cin + q], acc[q]);
+                    }
+                }
+            }
+            float* dst = dx + ((static_cast<long long>(n) * g.Hi + hi) * g.Wi + wi) * g.Cin + cg * CG;
+#pragma unroll
+            for (int q = 0; q < CG; ++q) dst[q] = acc[q];
+        }
+    }
+}
+
+constexpr int CONV_TH = 8;        // output rows per band (forward / weight gradient)
+constexpr int CONV_TH_IN = 16;    // input rows per band (data gradient)
+
+int conv_grid(long long tiles, int per_sm) {
+    long long cap = static_cast<long long>(device_sm_count()) * per_sm;
+    return static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 
 // y[m, c] += bias[c]
@@ -154,36 +299,67 @@ int grid_for(long long work) {
 
 using namespace ctcb200;
 
-extern "C" CTCB200_API int ctcb200_conv_im2col(const float* x_nhwc, void* cols, int64_t pitch, int transposed, int N,
-                                               int Hi, int Wi, int Cin, int Ho, int Wo, int kh, int kw, int sh, int sw,
-                                               int ph, int pw, ctcb200_stream_t stream_) {
+extern "C" CTCB200_API int ctcb200_conv2d_fwd(const float* x_nhwc, const float* w, const float* bias, float* y, int N, int Hi,
+                                              int Wi, int Cin, int Cout, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph,
+                                              int pw, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    CTCB_REQUIRE(N > 0 && Ho > 0 && Wo > 0 && Cin > 0, "conv_im2col: empty geometry");
+    CTCB_REQUIRE(N > 0 && Ho > 0 && Wo > 0 && Cin > 0 && Cout > 0, "conv2d_fwd: empty geometry");
     ConvGeom g{N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw};
-    const long long total = static_cast<long long>(N) * Ho * Wo * kh * kw * Cin;
-    im2col_kernel<<<grid_for(total), 256, 0, stream>>>(x_nhwc, static_cast<__nv_bfloat16*>(cols), pitch, g, transposed);
+    const Band b = make_band(g, CONV_TH);
+    const size_t smem = (static_cast<size_t>(kh) * kw * Cin * Cout + static_cast<size_t>(b.IH) * b.IW * Cin) * sizeof(float);
+    CTCB_REQUIRE(smem <= 200 * 1024, "conv2d_fwd: tile needs %zu bytes of shared memory (Cin=%d Cout=%d Wi=%d)", smem, Cin, Cout, Wi);
+    const int grid = conv_grid(static_cast<long long>(N) * b.bands, 4);
+    if (Cout % 8 == 0) {
+        CTCB_CUDA(cudaFuncSetAttribute(conv2d_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        conv2d_fwd_kernel<8><<<grid, CONV_THREADS, smem, stream>>>(x_nhwc, w, bias, y, g, Cout, b);
+    } else {
+        CTCB_CUDA(cudaFuncSetAttribute(conv2d_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        conv2d_fwd_kernel<1><<<grid, CONV_THREADS, smem, stream>>>(x_nhwc, w, bias, y, g, Cout, b);
+    }
     CTCB_LAUNCH_CHECK();
     return OK;
 }
 
-extern "C" CTCB200_API int ctcb200_conv_col2im(const float* dcols, int64_t pitch, float* dx_nhwc, int N, int Hi, int Wi,
-                                               int Cin, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
-                                               ctcb200_stream_t stream_) {
+extern "C" CTCB200_API int64_t ctcb200_conv2d_wgrad_ws_bytes(int Cin, int Cout, int kh, int kw) {
+    return static_cast<int64_t>(device_sm_count()) * 2 * kh * kw * Cin * Cout * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" CTCB200_API int ctcb200_conv2d_wgrad(const float* x_nhwc, const float* dy, float* dw, void* ws, int N, int Hi, int Wi,
+                                                int Cin, int Cout, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                                                ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ConvGeom g{N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw};
-    CTCB_CUDA(cudaMemsetAsync(dx_nhwc, 0, sizeof(float) * static_cast<size_t>(N) * Hi * Wi * Cin, stream));
-    const long long total = static_cast<long long>(N) * Ho * Wo * kh * kw * Cin;
-    col2im_kernel<<<grid_for(total), 256, 0, stream>>>(dcols, pitch, dx_nhwc, g);
+    const Band b = make_band(g, CONV_TH);
+    const int total = kh * kw * Cin * Cout;
+    CTCB_REQUIRE(total <= 40 * CONV_THREADS, "conv2d_wgrad: %d weights exceed the per-thread accumulator budget", total);
+    const size_t smem = (static_cast<size_t>(b.IH) * b.IW * Cin + static_cast<size_t>(CONV_TH) * Wo * Cout) * sizeof(float);
+    CTCB_REQUIRE(smem <= 200 * 1024, "conv2d_wgrad: tile needs %zu bytes of shared memory", smem);
+    const int grid = conv_grid(static_cast<long long>(N) * b.bands, 2);
+    CTCB_CUDA(cudaFuncSetAttribute(conv2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv2d_wgrad_kernel<<<grid, CONV_THREADS, smem, stream>>>(x_nhwc, dy, static_cast<float*>(ws), g, Cout, b);
+    CTCB_LAUNCH_CHECK();
+    conv2d_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(static_cast<const float*>(ws), dw, grid, total);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
 
-extern "C" CTCB200_API int ctcb200_conv_pack_weight(const float* w, void* w_p, void* w_pT, int Cout, int Cin, int kh,
-                                                    int kw, int Kp, int Coutp, ctcb200_stream_t stream_) {
+extern "C" CTCB200_API int ctcb200_conv2d_dgrad(const float* dy, const float* w, float* dx_nhwc, int N, int Hi, int Wi, int Cin,
+                                                int Cout, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                                                ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    CTCB_REQUIRE(Kp >= kh * kw * Cin && Coutp >= Cout, "conv_pack_weight: padded sizes too small");
-    pack_conv_weight_kernel<<<grid_for(static_cast<long long>(Cout) * Kp), 256, 0, stream>>>(
-        w, static_cast<__nv_bfloat16*>(w_p), static_cast<__nv_bfloat16*>(w_pT), Cout, Cin, kh, kw, Kp, Coutp);
+    ConvGeom g{N, Hi, Wi, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw};
+    const int max_rows = (CONV_TH_IN - 1 + kh - 1) / sh + 2;
+    const size_t smem = (static_cast<size_t>(kh) * kw * Cout * Cin + static_cast<size_t>(max_rows) * Wo * Cout) * sizeof(float);
+    CTCB_REQUIRE(smem <= 200 * 1024, "conv2d_dgrad: tile needs %zu bytes of shared memory", smem);
+    const int bands = (Hi + CONV_TH_IN - 1) / CONV_TH_IN;
+    const int grid = conv_grid(static_cast<long long>(N) * bands, 4);
+    if (Cin % 8 == 0) {
+        CTCB_CUDA(cudaFuncSetAttribute(conv2d_dgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        conv2d_dgrad_kernel<8><<<grid, CONV_THREADS, smem, stream>>>(dy, w, dx_nhwc, g, Cout, CONV_TH_IN);
+    } else {
+        CTCB_CUDA(cudaFuncSetAttribute(conv2d_dgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        conv2d_dgrad_kernel<1><<<grid, CONV_THREADS, smem, stream>>>(dy, w, dx_nhwc, g, Cout, CONV_TH_IN);
+    }
     CTCB_LAUNCH_CHECK();
     return OK;
 }

@@ -295,6 +295,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ ws, const float* _
                                    float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift, int R,
                                    int C) {
+    // R = number of rows the statistics are over (the valid-frame count in packed mode: zero padding rows add nothing to the sums)
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double m = ws[c] / R;
@@ -359,9 +360,9 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ ws,
-                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
+                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C, int Rv) {
     const long long total = static_cast<long long>(R) * C;
-    const float invR = 1.0f / R;
+    const float invR = 1.0f / Rv;   // Rv = rows the statistics were taken over (packed mode: valid frames only)
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
          e += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(e % C);
@@ -491,6 +492,37 @@ __global__ void scale_mask_kernel(float* __restrict__ a, const uint8_t* __restri
         a[e] = mask[e] ? a[e] * inv_keep : 0.0f;
 }
 
+// Packed-sequence support (my_863_corpus/steps/model.py:37-56,93-141): the recurrent kernels always scan all T rows of a padded
+// [T, N, W] tensor, so packed semantics come from ALIGNMENT — the forward direction sees the left-aligned batch, the reverse
+// direction a right-aligned copy (frame k of utterance n at row T - len_n + k) whose scan T-1 -> 0 meets the last valid frame
+// first. This kernel moves data between the two alignments and zeroes the padding rows:
+//   columns [0, split)  : dst[t, n] = t < len_n ? src[t, n] : 0                                  (mask only)
+//   columns [split, W)  : dir = +1 (right -> left): dst[t, n] = t < len_n ? src[t + T - len_n, n] : 0
+//                         dir = -1 (left -> right): dst[t, n] = t >= T - len_n ? src[t - (T - len_n), n] : 0
+// accumulate = 1 adds into dst instead of overwriting it (dX of the reverse direction joining that of the forward direction).
+__global__ void __launch_bounds__(256)
+realign_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const long long* __restrict__ lengths, int T, int N,
+                    int W, int split, int dir, int accumulate) {
+    const long long total = static_cast<long long>(T) * N * W;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % W);
+        const long long rn = e / W;
+        const int n = static_cast<int>(rn % N), t = static_cast<int>(rn / N);
+        int len = static_cast<int>(lengths[n]);
+        len = len < 0 ? 0 : (len > T ? T : len);
+        float v = 0.0f;
+        if (c < split) {
+            if (t < len) v = src[e];
+        } else if (dir > 0) {
+            if (t < len) v = src[(static_cast<long long>(t + T - len) * N + n) * W + c];
+        } else {
+            if (t >= T - len) v = src[(static_cast<long long>(t - (T - len)) * N + n) * W + c];
+        }
+        dst[e] = accumulate ? dst[e] + v : v;
+    }
+}
+
 int stream_grid(long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
     const long long cap = static_cast<long long>(device_sm_count()) * 8;
@@ -592,9 +624,11 @@ extern "C" CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64
 extern "C" CTCB200_API int ctcb200_bn_train_stats(const float* x, int R, int C, const float* gamma, const float* beta,
                                                   float* running_mean, float* running_var, float momentum, float eps,
                                                   float* mean, float* rstd, float* scale, float* shift, void* ws,
-                                                  ctcb200_stream_t stream_) {
+                                                  int n_valid, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(R > 0 && C > 0, "bn_train_stats: empty R=%d C=%d", R, C);
+    CTCB_REQUIRE(n_valid >= 0 && n_valid <= R, "bn_train_stats: n_valid %d outside [0, R=%d]", n_valid, R);
+    const int Rv = n_valid > 0 ? n_valid : R;
     CTCB_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(2) * C * sizeof(double), stream));
     const bool vec = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const int cols_per_block = vec ? 128 : 32;
@@ -607,7 +641,7 @@ extern "C" CTCB200_API int ctcb200_bn_train_stats(const float* x, int R, int C, 
     else bn_stats_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(x, static_cast<double*>(ws), R, C, rows_per_block);
     CTCB_LAUNCH_CHECK();
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(static_cast<const double*>(ws), gamma, beta, running_mean,
-                                                          running_var, momentum, eps, mean, rstd, scale, shift, R, C);
+                                                          running_var, momentum, eps, mean, rstd, scale, shift, Rv, C);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
@@ -623,7 +657,7 @@ extern "C" CTCB200_API int ctcb200_bn_eval_affine(const float* gamma, const floa
 
 extern "C" CTCB200_API int ctcb200_bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                           const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C,
-                                          void* ws, ctcb200_stream_t stream_) {
+                                          void* ws, int n_valid, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(R > 0 && C > 0, "bn_bwd: empty R=%d C=%d", R, C);
     CTCB_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(2) * C * sizeof(double), stream));
@@ -636,14 +670,14 @@ extern "C" CTCB200_API int ctcb200_bn_bwd(const float* dy, const float* x, const
                                                                          rows_per_block);
     CTCB_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<stream_grid(static_cast<long long>(R) * C, 1024), 256, 0, stream>>>(
-        dy, x, mean, rstd, gamma, static_cast<const double*>(ws), dx, dgamma, dbeta, R, C);
+        dy, x, mean, rstd, gamma, static_cast<const double*>(ws), dx, dgamma, dbeta, R, C, n_valid > 0 ? n_valid : R);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
 
 extern "C" CTCB200_API int ctcb200_bn_bwd_coef(const float* dy, const float* x, const float* mean, const float* rstd,
                                                const float* gamma, float* coef, float* dgamma, float* dbeta, int R, int C,
-                                               void* ws, ctcb200_stream_t stream_) {
+                                               void* ws, int n_valid, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(R > 0 && C > 0, "bn_bwd_coef: empty R=%d C=%d", R, C);
     CTCB_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(2) * C * sizeof(double), stream));
@@ -663,7 +697,7 @@ extern "C" CTCB200_API int ctcb200_bn_bwd_coef(const float* dy, const float* x, 
                                                                              rows_per_block);
     CTCB_LAUNCH_CHECK();
     bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, stream>>>(static_cast<const double*>(ws), mean, rstd, gamma, coef, dgamma, dbeta,
-                                                          R, C);
+                                                          n_valid > 0 ? n_valid : R, C);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
@@ -691,6 +725,17 @@ extern "C" CTCB200_API int ctcb200_dropout_apply(float* a, const void* mask_u8, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(n > 0, "dropout_apply: empty");
     scale_mask_kernel<<<stream_grid(n, 1024), 256, 0, stream>>>(a, static_cast<const uint8_t*>(mask_u8), inv_keep, n);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_realign_rows(const float* src, float* dst, const void* lengths_i64, int T, int N, int W,
+                                                int split, int dir, int accumulate, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(T > 0 && N > 0 && W > 0 && split >= 0 && split <= W, "realign_rows: bad sizes T=%d N=%d W=%d split=%d", T, N, W, split);
+    CTCB_REQUIRE(src != dst || split == W, "realign_rows: in-place use is only valid when every column is mask-only (split == W)");
+    realign_rows_kernel<<<stream_grid(static_cast<long long>(T) * N * W, 1024), 256, 0, stream>>>(
+        src, dst, static_cast<const long long*>(lengths_i64), T, N, W, split, dir, accumulate);
     CTCB_LAUNCH_CHECK();
     return OK;
 }

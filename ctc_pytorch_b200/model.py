@@ -208,12 +208,32 @@ def _inv_keep(p):
     return 0.0 if p >= 1.0 else 1.0 / (1.0 - p)
 
 
+def _unwrap(mod):
+    """my_863_corpus wraps BatchNorm / the output layer in SequenceWise (`.module`); timit/ uses the modules directly."""
+    return mod.module if (mod is not None and hasattr(mod, "module") and not isinstance(mod, (nn.BatchNorm1d, nn.Linear, nn.Sequential))) else mod
+
+
+def _layer_dropout_p(layer):
+    d = getattr(layer, "dropout", None)
+    return float(d.p) if isinstance(d, nn.Dropout) else 0.0
+
+
+def _realign(src, lengths, T, N, W, split, direction, dst=None, accumulate=False):
+    """Move [T, N, W] rows between the left- and right-aligned layouts of a packed batch / zero its padding rows."""
+    if dst is None:
+        dst = torch.empty_like(src)
+    _call("ctcb200_realign_rows", _lib.ptr(src), _lib.ptr(dst), _lib.ptr(lengths), T, N, W, split, direction,
+          1 if accumulate else 0, _lib.stream())
+    return dst
+
+
 class _BNState(object):
     __slots__ = ("mean", "rstd", "scale", "shift", "batch")
 
 
-def _bn_prepare(bn, x2d, R, C, training):
-    """Statistics (training) or running-stat affine (eval) for BatchNorm1d `bn` over rows of x2d [R, C]."""
+def _bn_prepare(bn, x2d, R, C, training, n_valid=0):
+    """Statistics (training) or running-stat affine (eval) for BatchNorm1d `bn` over rows of x2d [R, C]. n_valid > 0: packed
+    mode, the statistics are over that many valid rows (the padding rows of x2d are zero)."""
     dev = x2d.device
     st = _BNState()
     st.scale = torch.empty(C, dtype=torch.float32, device=dev)
@@ -235,7 +255,7 @@ def _bn_prepare(bn, x2d, R, C, training):
         _call("ctcb200_bn_train_stats", _lib.ptr(x2d), R, C, _lib.ptr(gamma), _lib.ptr(beta),
               _lib.ptr(bn.running_mean if upd else None), _lib.ptr(bn.running_var if upd else None), mom,
               float(bn.eps), _lib.ptr(st.mean), _lib.ptr(st.rstd), _lib.ptr(st.scale), _lib.ptr(st.shift),
-              _lib.ptr(ws), _lib.stream())
+              _lib.ptr(ws), int(n_valid), _lib.stream())
     else:
         # frozen statistics (eval mode): the same per-column affine; mean / rstd kept for a possible backward pass
         st.mean = bn.running_mean.detach().float().contiguous()
@@ -274,8 +294,14 @@ class _RnnStackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x_src, geom, *params):
-        # geom: (T, N, I0, s_outer, s_inner, need_grad) describing where row (t, n) of the layer-0 input lives in x_src
-        T, N, I0, s_outer, s_inner, need_grad = geom
+        # geom: (T, N, I0, s_outer, s_inner, need_grad[, lengths, raw_out]) describing where row (t, n) of the layer-0 input
+        # lives in x_src; lengths (i64 [N] on the device, or None) switches on packed-sequence semantics (my_863_corpus),
+        # raw_out returns the output layer's activations instead of log-probabilities (warp-ctc applies softmax itself)
+        T, N, I0, s_outer, s_inner, need_grad = geom[:6]
+        lengths = geom[6] if len(geom) > 6 else None
+        raw_out = bool(geom[7]) if len(geom) > 7 else False
+        packed = lengths is not None
+        n_valid = int(geom[8]) if packed else 0
         dev = x_src.device
         training = model.training
         x3 = model.precision == "x3"
@@ -287,16 +313,28 @@ class _RnnStackFn(torch.autograd.Function):
         layers = list(model.rnns.children())
         ws = _Workspace()
         ws.geom, ws.layers_n, ws.x3 = geom, len(layers), x3
+        ws.lengths, ws.n_valid, ws.raw_out = lengths, n_valid, raw_out
         ws.L = []
         stream = _lib.stream
 
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
         # With the overlapped weight-gradient pipeline the transposed operands (X^T, H^T) are only produced in the
         # backward pass, on the side stream, so the forward pass does not pay for them.
-        defer_t = need_grad and _overlap_enabled(model)
+        defer_t = need_grad and _overlap_enabled(model) and not packed
         want_t = need_grad and not defer_t
         ws.defer_t = defer_t
-        X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=want_t, x3=x3)
+        if packed:
+            # layer-0 input as a dense time-major [T, N, I0] tensor with zero padding, plus its right-aligned twin
+            if s_outer != N * I0 or s_inner != I0 or not x_src.is_contiguous():
+                raise RuntimeError("packed mode takes the input as a contiguous time-major [T, N, F] tensor")
+            x_l = _realign(x_src, lengths, T, N, I0, I0, 1)       # padding rows zeroed
+            x_r = _realign(x_l, lengths, T, N, I0, 0, -1)
+            X, XT = _cast_t(x_l, N * I0, I0, N, R, I0, want=True, want_t=want_t, x3=x3)
+            Xr, XrT = _cast_t(x_r, N * I0, I0, N, R, I0, want=True, want_t=want_t, x3=x3)
+            del x_r
+        else:
+            X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=want_t, x3=x3)
+            Xr = XrT = None
         ws.x_src = x_src if defer_t else None
         h_prev = None
         I = I0
@@ -304,17 +342,28 @@ class _RnnStackFn(torch.autograd.Function):
             rec = _Workspace()
             rec.I = I
             rec.bn = None
+            layer_bn = _unwrap(layer.batch_norm)
             if li > 0:
                 I = 2 * H
                 rec.I = I
-                if layer.batch_norm is not None:
-                    rec.bn = _bn_prepare(layer.batch_norm, h_prev, R, I, training)
-                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, rec.bn.scale, rec.bn.shift, True, want_t, x3)
+                h_prev_r = _realign(h_prev, lengths, T, N, I, 0, -1) if packed else None
+                if layer_bn is not None:
+                    rec.bn = _bn_prepare(layer_bn, h_prev, R, I, training, n_valid)
+                    sc_, sh_ = rec.bn.scale, rec.bn.shift
                 else:
-                    X, XT = _cast_t(h_prev, N * I, I, N, R, I, None, None, True, want_t, x3)
+                    sc_ = sh_ = None
+                X, XT = _cast_t(h_prev, N * I, I, N, R, I, sc_, sh_, True, want_t, x3)
+                if packed:   # the BatchNorm affine turns zero padding into `shift`: harmless, those rows are never consumed
+                    Xr, XrT = _cast_t(h_prev_r, N * I, I, N, R, I, sc_, sh_, True, want_t, x3)
+                    del h_prev_r
             Ipad = _round_up(I, 8)
             wih_p, wihT_p, whh_p, whhT_p = _packed_weights(model, li, layer.rnn, H, I, Ipad, x3, dev)
-            gx = _gemm(X, wih_p, k=I)  # [R, 8H] f32
+            if packed:   # each direction's input projection on its own alignment, written into its half of gx
+                gx = torch.empty((R, 8 * H), dtype=torch.float32, device=dev)
+                _gemm(X, wih_p.rows(0, 4 * H), out=gx[:, :4 * H], k=I)
+                _gemm(Xr, wih_p.rows(4 * H, 8 * H), out=gx[:, 4 * H:], k=I)
+            else:
+                gx = _gemm(X, wih_p, k=I)  # [R, 8H] f32
             hout = torch.empty((R, 2 * H), dtype=torch.float32, device=dev)
             c_save = torch.empty((R, 2 * H), dtype=torch.float32, device=dev) if need_grad else None
             gates = torch.empty((R, 2 * H, 4), dtype=torch.float32 if x3 else torch.float16, device=dev) if need_grad else None
@@ -322,30 +371,43 @@ class _RnnStackFn(torch.autograd.Function):
                   _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, stream())
             del gx
             rec.HT = None
-            p_drop = float(layer.dropout.p)
+            p_drop = _layer_dropout_p(layer)
             # H^T pairs dG_t with the *pre-dropout* h_{t-1}: it can only be deferred when hout is not modified in place
             if need_grad and not (defer_t and not (training and p_drop > 0.0)):
                 _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True, x3=x3)
             rec.h_out = hout if need_grad else None
+            if packed:
+                # kernel alignment (forward half left-, reverse half right-aligned, garbage in the padding) -> left-aligned
+                # layer output with zero padding: what pad_packed_sequence would show (my_863_corpus/steps/model.py:93-141)
+                hout = _realign(hout, lengths, T, N, 2 * H, H, 1)
             rec.mask = None
             if training and p_drop > 0.0:
                 rec.mask = _dropout_mask(model, hout.shape, p_drop, dev)
                 _call("ctcb200_dropout_apply", _lib.ptr(hout), _lib.ptr(rec.mask), _inv_keep(p_drop), hout.numel(), stream())
-            rec.XT, rec.h_in = XT, h_prev
+            rec.XT, rec.XrT, rec.h_in = XT, XrT, h_prev
             rec.c_save, rec.gates, rec.wihT_p, rec.whhT_p = c_save, gates, wihT_p, whhT_p
             ws.L.append(rec)
             h_prev = hout
 
         # output layer: (BatchNorm1d) + Linear(no bias) + LogSoftmax
         F2 = 2 * H
-        fc_bn, fc_lin = (model.fc[0], model.fc[1]) if isinstance(model.fc, nn.Sequential) else (None, model.fc)
-        ws.fc_bn = _bn_prepare(fc_bn, h_prev, R, F2, training) if fc_bn is not None else None
+        fc = _unwrap(model.fc)
+        fc_bn, fc_lin = (fc[0], fc[1]) if isinstance(fc, nn.Sequential) else (None, fc)
+        C = fc_lin.weight.shape[0]
+        ws.fc_bn = _bn_prepare(fc_bn, h_prev, R, F2, training, n_valid) if fc_bn is not None else None
         Xfc, XfcT = _cast_t(h_prev, N * F2, F2, N, R, F2, ws.fc_bn.scale if ws.fc_bn else None,
                             ws.fc_bn.shift if ws.fc_bn else None, True, need_grad, x3)
         Wfc_b, WfcT_b = _cast_t(fc_lin.weight, F2, F2, 1, C, F2, want=True, want_t=need_grad, x3=x3)
         logits = _gemm(Xfc, Wfc_b, k=F2)  # [R, C]
-        out = torch.empty((T, N, C), dtype=torch.float32, device=dev)
-        _call("ctcb200_log_softmax_fwd", _lib.ptr(logits), logits.stride(0), _lib.ptr(out), R, C, stream())
+        if packed:   # after pad_packed_sequence every padded frame is a zero vector
+            if logits.stride(0) != C:
+                logits = logits.contiguous()
+            _realign(logits, lengths, T, N, C, C, 1, dst=logits)
+        if raw_out:
+            out = logits.view(T, N, C) if logits.stride(0) == C else logits.contiguous().view(T, N, C)
+        else:
+            out = torch.empty((T, N, C), dtype=torch.float32, device=dev)
+            _call("ctcb200_log_softmax_fwd", _lib.ptr(logits), logits.stride(0), _lib.ptr(out), R, C, stream())
         ws.h_last, ws.XfcT, ws.WfcT_b, ws.out = h_prev, XfcT, WfcT_b, out
         ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np = T, N, H, C, R, Rp, Np
         ctx.ws = ws if need_grad else None
@@ -360,6 +422,8 @@ class _RnnStackFn(torch.autograd.Function):
             raise RuntimeError("backward through a forward pass that ran without gradient bookkeeping")
         T, N, H, C, R, Rp, Np = ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np
         x3 = ws.x3
+        lengths, n_valid = ws.lengths, ws.n_valid
+        packed = lengths is not None
         dev = g_out.device
         stream = _lib.stream
         F2 = 2 * H
@@ -388,10 +452,16 @@ class _RnnStackFn(torch.autograd.Function):
             return buf, views
 
         g = g_out.detach().to(torch.float32).contiguous()
-        dlogits = torch.empty((R, C), dtype=torch.float32, device=dev)
-        _call("ctcb200_log_softmax_bwd", _lib.ptr(g), _lib.ptr(ws.out), _lib.ptr(dlogits), R, C, stream())
+        if ws.raw_out:
+            dlogits = g.view(R, C)
+        else:
+            dlogits = torch.empty((R, C), dtype=torch.float32, device=dev)
+            _call("ctcb200_log_softmax_bwd", _lib.ptr(g), _lib.ptr(ws.out), _lib.ptr(dlogits), R, C, stream())
+        if packed:   # nothing flows into padded frames
+            dlogits = _realign(dlogits, lengths, T, N, C, C, 1)
         dLb, dLT = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=True, x3=x3)
-        fc_bn, fc_lin = (model.fc[0], model.fc[1]) if isinstance(model.fc, nn.Sequential) else (None, model.fc)
+        fc = _unwrap(model.fc)
+        fc_bn, fc_lin = (fc[0], fc[1]) if isinstance(fc, nn.Sequential) else (None, fc)
         fc_buf, fc_views = _flat([C * F2] + ([F2, F2] if fc_bn is not None else []))
         grads[fc_lin.weight] = _gemm(dLT, ws.XfcT, out=fc_views[0].view(C, F2), k=Rp)   # [C, 2H]
         dh = _gemm(dLb, ws.WfcT_b, k=C)                                                # [R, 2H]
@@ -403,17 +473,19 @@ class _RnnStackFn(torch.autograd.Function):
             layer below). Returns (bn_x, bn_coef) when the input gradient is left to the BPTT kernel of that layer (no dropout
             mask in between), else applies it in place and returns None."""
             grads[bn_mod.weight], grads[bn_mod.bias] = dgam, dbet
-            if (fuse_env and ws.L[below].mask is None) or not st.batch:
+            if ((fuse_env and ws.L[below].mask is None) or not st.batch) and not (packed and st.batch):
                 coef = torch.empty(3 * C_, dtype=torch.float32, device=dev)
                 _call("ctcb200_bn_bwd_coef", _lib.ptr(dy), _lib.ptr(x_in), _lib.ptr(st.mean), _lib.ptr(st.rstd),
-                      _lib.ptr(bn_mod.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), stream())
+                      _lib.ptr(bn_mod.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), n_valid,
+                      stream())
                 if not st.batch:
                     coef[C_:].zero_()   # frozen statistics: dx = gamma * rstd * dy, no batch-coupling terms
                     if ws.L[below].mask is not None:   # (cannot happen: masks only exist in training mode)
                         raise RuntimeError("dropout mask together with frozen BatchNorm statistics")
                 return (x_in, coef)
+            # packed mode: the padding rows of dx come out non-zero here; the realign in front of the BPTT kernel zeroes them
             _call("ctcb200_bn_bwd", _lib.ptr(dy), _lib.ptr(x_in), _lib.ptr(st.mean), _lib.ptr(st.rstd),
-                  _lib.ptr(bn_mod.weight), _lib.ptr(dy), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), stream())
+                  _lib.ptr(bn_mod.weight), _lib.ptr(dy), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), n_valid, stream())
             return None
 
         bn_fuse = None
@@ -446,7 +518,12 @@ class _RnnStackFn(torch.autograd.Function):
                 _call("ctcb200_transpose_dg", _lib.ptr(d_), _lib.ptr(t_), Rp, N, Np, R, H, stream())
                 dgTs.append(t_)
             dgT = _Opnd(dgTs[0], dgTs[1])
-            dwih = _gemm(dgT, XT, out=views_[0].view(8 * H, I_), k=Rp, max_ctas=mc)     # [8H, I], torch row order
+            if packed:   # each direction against the input in its own alignment
+                dwih = views_[0].view(8 * H, I_)
+                _gemm(dgT.rows(0, 4 * H), XT, out=dwih[:4 * H], k=Rp, max_ctas=mc)
+                _gemm(dgT.rows(4 * H, 8 * H), rec_.XrT, out=dwih[4 * H:], k=Rp, max_ctas=mc)
+            else:
+                dwih = _gemm(dgT, XT, out=views_[0].view(8 * H, I_), k=Rp, max_ctas=mc)     # [8H, I], torch row order
             grads[rnn.weight_ih_l0], grads[rnn.weight_ih_l0_reverse] = dwih[:4 * H], dwih[4 * H:]
             whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
             if T > 1:
@@ -468,11 +545,14 @@ class _RnnStackFn(torch.autograd.Function):
         for li in range(len(layers) - 1, -1, -1):
             layer, rec = layers[li], ws.L[li]
             I = rec.I
-            has_bn = li > 0 and layer.batch_norm is not None
+            layer_bn = _unwrap(layer.batch_norm)
+            has_bn = li > 0 and layer_bn is not None
             buf, views = _flat([8 * H * I, 4 * H * H, 4 * H * H] + ([I, I] if has_bn else []))
             if rec.mask is not None:
-                _call("ctcb200_dropout_apply", _lib.ptr(dh), _lib.ptr(rec.mask), _inv_keep(float(layer.dropout.p)),
+                _call("ctcb200_dropout_apply", _lib.ptr(dh), _lib.ptr(rec.mask), _inv_keep(_layer_dropout_p(layer)),
                       dh.numel(), stream())
+            if packed:   # left-aligned gradient -> the kernels' alignment (reverse half right-aligned), padding rows zeroed
+                dh = _realign(dh, lengths, T, N, 2 * H, H, -1)
             dg = _Opnd(torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev),
                        torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev) if x3 else None)
             _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p.hi), _lib.ptr(rec.whhT_p.lo), _lib.ptr(rec.c_save),
@@ -500,14 +580,21 @@ class _RnnStackFn(torch.autograd.Function):
                             _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
                         _wgrad(pending[:6], side_ctas)
                 pending = [layer, rec, dg, li, buf, views, None]
+            def _input_grad():
+                if not packed:
+                    return _gemm(dg, rec.wihT_p, k=8 * H)                  # [R, I] rows (t, n)
+                dxf = _gemm(dg, rec.wihT_p, k=4 * H)                       # forward direction: already left-aligned
+                dxr = _gemm(dg, rec.wihT_p, k=4 * H, a_koff=4 * H, b_koff=4 * H)
+                return _realign(dxr, lengths, T, N, I, 0, 1, dst=dxf, accumulate=True)
             if li == 0 and ctx.needs_input_grad[1]:
-                dx0 = _gemm(dg, rec.wihT_p, k=8 * H)                       # [R, I0] rows (t, n)
+                dx0 = _input_grad()
                 T0, N0, I0 = ws.geom[0], ws.geom[1], ws.geom[2]
-                grad_x = dx0.view(T0, N0, I0).transpose(0, 1)              # back to the [N, T, I0] layout of x_src
+                # back to the layout of x_src: [N, T, I0] for the padded model, time-major for the packed one
+                grad_x = dx0.view(T0, N0, I0) if packed else dx0.view(T0, N0, I0).transpose(0, 1)
             if li > 0:
-                dh = _gemm(dg, rec.wihT_p, k=8 * H)                        # [R, I]
+                dh = _input_grad()
                 if has_bn:
-                    bn_fuse = _bn_backward(layer.batch_norm, rec.bn, dh, rec.h_in, I, li - 1, views[3], views[4])
+                    bn_fuse = _bn_backward(layer_bn, rec.bn, dh, rec.h_in, I, li - 1, views[3], views[4])
                     if overlap and sync is not None:
                         pending[6] = torch.cuda.Event()
                         pending[6].record(main)

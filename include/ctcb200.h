@@ -159,7 +159,7 @@ CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64_t dgT_pitc
  * (unbiased variance), pass NULL to skip. */
 CTCB200_API int ctcb200_bn_train_stats(const float* x, int R, int C, const float* gamma, const float* beta,
                                        float* running_mean, float* running_var, float momentum, float eps,
-                                       float* mean, float* rstd, float* scale, float* shift, void* ws,
+                                       float* mean, float* rstd, float* scale, float* shift, void* ws, int n_valid,
                                        ctcb200_stream_t stream);
 CTCB200_API int ctcb200_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
                                        const float* running_var, float eps, float* scale, float* shift, int C,
@@ -167,35 +167,46 @@ CTCB200_API int ctcb200_bn_eval_affine(const float* gamma, const float* beta, co
 /* dx may alias dy. dgamma / dbeta may be NULL. */
 CTCB200_API int ctcb200_bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C, void* ws,
-                               ctcb200_stream_t stream);
+                               int n_valid, ctcb200_stream_t stream);
 /* Same reduction, but instead of writing dx it emits coef f32 [3][C] with dx = coef[0][c]*dy + coef[1][c]*x + coef[2][c];
  * ctcb200_lstm_bwd applies it while it reads its incoming gradient (bn_x / bn_coef), which saves one pass over [R, C]. */
 CTCB200_API int ctcb200_bn_bwd_coef(const float* dy, const float* x, const float* mean, const float* rstd,
                                     const float* gamma, float* coef, float* dgamma, float* dbeta, int R, int C, void* ws,
-                                    ctcb200_stream_t stream);
+                                    int n_valid, ctcb200_stream_t stream);
 CTCB200_API int ctcb200_log_softmax_fwd(const float* x, int64_t x_pitch, float* y, int R, int C,
                                         ctcb200_stream_t stream);
 CTCB200_API int ctcb200_log_softmax_bwd(const float* g, const float* y, float* dx, int R, int C,
                                         ctcb200_stream_t stream);
+/* Packed (variable-length) sequences, my_863_corpus/steps/model.py:37-56,93-141 fed by pack_padded_sequence
+ * (lstm_ctc.py:41): the recurrent kernels always scan all T rows, so packed semantics come from alignment — the forward
+ * direction runs on the left-aligned batch, the reverse direction on a right-aligned copy — plus BatchNorm sums divided by the
+ * valid-frame count (n_valid above; 0 = all R rows; padding rows must be zero). realign_rows moves [T,N,W] f32 rows between the
+ * two alignments and zeroes the padding: columns [0,split) are masked only (dst = t < len ? src : 0), columns [split,W) are
+ * shifted by T-len_n (dir=+1: right->left aligned, dir=-1: left->right aligned); accumulate=1 adds into dst. lengths: i64 [N]. */
+CTCB200_API int ctcb200_realign_rows(const float* src, float* dst, const void* lengths_i64, int T, int N, int W, int split,
+                                     int dir, int accumulate, ctcb200_stream_t stream);
 /* a[e] = mask[e] ? a[e] * inv_keep : 0 (nn.Dropout, model_ctc.py:26,34); mask bytes come from the caller's RNG */
 CTCB200_API int ctcb200_dropout_apply(float* a, const void* mask_u8, float inv_keep, int64_t n,
                                       ctcb200_stream_t stream);
 
-/* ---- CNN front: LayerCNN = Conv2d(bias) -> BatchNorm2d -> ReLU (timit/models/model_ctc.py:38-68,148), lowered to
- * im2col + the tcgen05 GEMM. Activations are channel-last [N,H,W,C] f32 between blocks.
- * conv_im2col: cols bf16 [M=N*Ho*Wo, pitch] with k = (r,s,c) (transposed=0) or its transpose [K, pitch] (1).
- * conv_col2im: scatter-add of dcols f32 [M, pitch] onto dx [N,Hi,Wi,Cin] (zeroed first).
- * conv_pack_weight: torch [Cout,Cin,kh,kw] f32 -> w_p bf16 [Cout,Kp] (k = (r,s,c)) and w_pT bf16 [K,Coutp] (may be NULL).
+/* ---- CNN front: LayerCNN = Conv2d(bias) -> BatchNorm2d -> ReLU (timit/models/model_ctc.py:38-68,148), direct fp32
+ * convolution kernels (the front is 0.5 % of the model's FLOPs and too thin for tensor-core tiles). Activations are
+ * channel-last [N,H,W,C] f32 between blocks; w / dw are torch's [Cout,Cin,kh,kw] f32; y / dy are rows [M=N*Ho*Wo, Cout].
+ * conv2d_fwd: y = conv(x, w) + bias (bias may be NULL). conv2d_wgrad: dw = sum_m dy[m,:] (x) patch(m); ws holds
+ * ctcb200_conv2d_wgrad_ws_bytes() bytes of per-CTA partial sums (reduced in a fixed order: deterministic).
+ * conv2d_dgrad: dx = conv^T(dy, w), every element written once.
  * affine_relu: a(n,h,w,c) = relu(y[m,c]*scale[c]+shift[c]) written with strides (sn,sh,sw,sc); scale may be NULL.
  * relu_bwd_gather: dz[m,c] = a(n,h,w,c) > 0 ? da(n,h,w,c) : 0. col_sum: out[c] = sum_m y[m,c] (bias gradient). */
-CTCB200_API int ctcb200_conv_im2col(const float* x_nhwc, void* cols, int64_t pitch, int transposed, int N, int Hi,
-                                    int Wi, int Cin, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
-                                    ctcb200_stream_t stream);
-CTCB200_API int ctcb200_conv_col2im(const float* dcols, int64_t pitch, float* dx_nhwc, int N, int Hi, int Wi, int Cin,
-                                    int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
-                                    ctcb200_stream_t stream);
-CTCB200_API int ctcb200_conv_pack_weight(const float* w, void* w_p, void* w_pT, int Cout, int Cin, int kh, int kw,
-                                         int Kp, int Coutp, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_conv2d_fwd(const float* x_nhwc, const float* w, const float* bias, float* y, int N, int Hi, int Wi,
+                                   int Cin, int Cout, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                                   ctcb200_stream_t stream);
+CTCB200_API int64_t ctcb200_conv2d_wgrad_ws_bytes(int Cin, int Cout, int kh, int kw);
+CTCB200_API int ctcb200_conv2d_wgrad(const float* x_nhwc, const float* dy, float* dw, void* ws, int N, int Hi, int Wi, int Cin,
+                                     int Cout, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                                     ctcb200_stream_t stream);
+CTCB200_API int ctcb200_conv2d_dgrad(const float* dy, const float* w, float* dx_nhwc, int N, int Hi, int Wi, int Cin, int Cout,
+                                     int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                                     ctcb200_stream_t stream);
 CTCB200_API int ctcb200_add_bias_rows(float* y, const float* bias, int64_t R, int C, ctcb200_stream_t stream);
 CTCB200_API int ctcb200_affine_relu(const float* y, const float* scale, const float* shift, float* a, int64_t sn,
                                     int64_t sh, int64_t sw, int64_t sc, int N, int Ho, int Wo, int C,

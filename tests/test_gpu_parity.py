@@ -595,6 +595,80 @@ def test_eval_mode_backward_uses_frozen_statistics():
         assert relnorm(p.grad, rp[k].grad) < 1e-3, k
 
 
+@pytest.mark.parametrize("precision", ["bf16", "x3"])
+def test_packed_model_golden(golden_dir, precision):
+    """§8(f) N1: the packed / variable-length model of the 863 path (my_863_corpus/steps/model.py CTC_RNN on a
+    pack_padded_sequence input, warp-ctc style loss) against golden vectors from the UNMODIFIED reference model."""
+    from ctc_pytorch_b200.packed import CTC_RNN, WarpCTCLoss
+    meta = json.load(open(os.path.join(golden_dir, "packed_rnn.json")))
+    g = np.load(os.path.join(golden_dir, "packed_rnn.npz"))
+    cfg = meta["cfg"]
+    torch.manual_seed(cfg["seed"])
+    m = CTC_RNN(rnn_input_size=cfg["F"], rnn_hidden_size=cfg["H"], rnn_layers=cfg["L"], rnn_type=nn.LSTM, bidirectional=True,
+                batch_norm=True, num_class=cfg["C"], drop_out=0.0)
+    assert list(m.state_dict().keys()) == list(meta["checksum"].keys())
+    for k, v in m.state_dict().items():
+        assert abs(float(v.double().abs().sum()) - meta["checksum"][k]) <= 1e-9 * max(1.0, meta["checksum"][k]), k
+    m = m.to(DEV)
+    m.precision = precision
+    x = torch.from_numpy(g["x"]).to(DEV)
+    lens = g["lengths"].tolist()
+    tol_o, tol_l, tol_g = (5e-2, 2e-3, 3e-2) if precision == "bf16" else (2e-4, 1e-4, 1e-3)
+    m.train()
+    act = m(nn.utils.rnn.pack_padded_sequence(x, lens))
+    assert act.shape == tuple(g["act_train"].shape)
+    e_act = (act.detach().cpu() - torch.from_numpy(g["act_train"])).abs().max().item()
+    for n, L in enumerate(lens):                   # padded frames are zero vectors, like pad_packed_sequence's output
+        assert act[L:, n].abs().sum().item() == 0.0
+    loss = WarpCTCLoss()(act, torch.from_numpy(g["targets"]).to(DEV), lens, g["target_sizes"].tolist())
+    e_loss = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    loss.backward()
+    worst = 0.0
+    for k, p in m.named_parameters():
+        step = meta["grad_step"][k]
+        vals = p.grad.detach().cpu().reshape(-1)[::step][:256]
+        worst = max(worst, relnorm(vals, g["gradvals/" + k]),
+                    abs(p.grad.norm().item() - meta["grad_norm"][k]) / meta["grad_norm"][k])
+    bworst = max(relnorm(b, g["buffer/" + k]) for k, b in m.named_buffers() if "running" in k)
+    m.eval()
+    with torch.no_grad():
+        logp = m(nn.utils.rnn.pack_padded_sequence(x, lens))
+    e_eval = (logp.cpu() - torch.from_numpy(g["logp_eval"])).abs().max().item()
+    _report("packed_model_golden", dict(precision=precision, act_abs_max=e_act, loss_rel=e_loss, grad_rel_worst=worst,
+                                        bn_running_rel_worst=bworst, eval_logp_abs_max=e_eval))
+    assert e_act < tol_o and e_loss < tol_l and worst < tol_g and bworst < 2e-2 and e_eval < tol_o
+
+
+@pytest.mark.parametrize("T,N,H,L", [(50, 19, 256, 2), (33, 40, 640, 2)])
+def test_packed_model_vs_oracle_x3(T, N, H, L):
+    """Packed semantics against the per-utterance oracle restatement (oracle/packed_ref.py, itself pinned to the live 863
+    model) on ragged batches wider than one batch group, incl. H = 640; x3 precision, 1e-3 on every gradient."""
+    from ctc_pytorch_b200.packed import CTC_RNN, WarpCTCLoss
+    from oracle import packed_ref
+    F_, C = 40, 20
+    torch.manual_seed(T + N)
+    m = CTC_RNN(rnn_input_size=F_, rnn_hidden_size=H, rnn_layers=L, rnn_type=nn.LSTM, bidirectional=True, batch_norm=True,
+                num_class=C, drop_out=0.0)
+    ref = packed_ref.RefPackedModel(F_, H, L, True, C)
+    ref.load_state_dict(m.state_dict())
+    m = m.to(DEV)
+    m.precision = "x3"
+    x, lens, targets, tsz = packed_ref.synthetic_packed_batch(T, N, F_, C, 5, T)
+    m.train(); ref.train()
+    act = m(x.to(DEV), lens)
+    loss = WarpCTCLoss()(act, targets.to(DEV), lens, tsz)
+    loss.backward()
+    ract = ref(x, lens)
+    rloss = packed_ref.warp_ctc_loss(ract, targets, lens, tsz)
+    rloss.backward()
+    assert (act.detach().cpu() - ract.detach()).abs().max().item() < 5e-4
+    assert abs(loss.item() - rloss.item()) < 1e-4 * abs(rloss.item())
+    rp = dict(ref.named_parameters())
+    worst = max(relnorm(p.grad, rp[k].grad) for k, p in m.named_parameters())
+    _report("packed_model_vs_oracle_x3", dict(T=T, N=N, H=H, grad_rel_l2_worst=worst))
+    assert worst < 1e-3, worst
+
+
 def test_dropout_training_mode_runs():
     from ctc_pytorch_b200.model import CTC_Model
     torch.manual_seed(0)
