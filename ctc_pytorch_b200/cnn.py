@@ -3,9 +3,9 @@ a stack of LayerCNN blocks = Conv2d(bias) -> BatchNorm2d -> activation -> [MaxPo
 
 Each convolution is a direct fp32 kernel (csrc/conv.cu: forward, weight gradient, data gradient from shared-memory
 tiles — exact fp32 like the reference's nn.Conv2d in both precision modes); BatchNorm2d statistics are the
-row-statistics kernels over the M = N*Ho*Wo rows; ReLU is fused with the BatchNorm apply. Supported on the
-CUDA path: 2-D convolutions, ReLU activation, no pooling (the shipped config, conf/ctc_config.yaml:32-40);
-anything else raises instead of silently falling back.
+row-statistics kernels over the M = N*Ho*Wo rows; ReLU is fused with the BatchNorm apply. The shipped config (conf/ctc_config.yaml:32-40) uses 2-D convolutions, ReLU and no pooling;
+the reference's other LayerCNN options run too — tanh / sigmoid activations (train_ctc.py:21) and nn.MaxPool2d(pool)
+(model_ctc.py:53-54); Conv1d blocks raise instead of silently falling back.
 """
 import torch
 import torch.nn as nn
@@ -24,15 +24,30 @@ def _geometry(conv, Hi, Wi):
     return kh, kw, sh, sw, ph, pw, Ho, Wo
 
 
+_ACT_CODES = {nn.ReLU: 0, nn.Tanh: 1, nn.Sigmoid: 2}   # train_ctc.py:21 supported_activate
+_ACT_IDENTITY = 3
+
+
 def _check_block(block):
+    """Returns (activation code, pooling window or None)."""
     if not isinstance(block.conv, nn.Conv2d):
         raise RuntimeError("the B200 path implements Conv2d blocks only")
-    if not isinstance(block.activation, nn.ReLU):
-        raise RuntimeError("the B200 path implements the ReLU activation only (got %r)" % (block.activation,))
-    if block.pooling is not None:
-        raise RuntimeError("the B200 path does not implement the optional MaxPool2d of LayerCNN")
+    if type(block.activation) not in _ACT_CODES:
+        raise RuntimeError("the B200 path implements the reference's activations relu / tanh / sigmoid (got %r)" % (block.activation,))
     if block.conv.dilation != (1, 1) or block.conv.groups != 1:
         raise RuntimeError("the B200 path implements dense, undilated convolutions only")
+    pool = None
+    if block.pooling is not None:
+        if not isinstance(block.pooling, nn.MaxPool2d):
+            raise RuntimeError("the B200 path implements MaxPool2d pooling only")
+        mp = block.pooling
+        k = mp.kernel_size if isinstance(mp.kernel_size, (tuple, list)) else (mp.kernel_size, mp.kernel_size)
+        st = mp.stride if isinstance(mp.stride, (tuple, list)) else (mp.stride, mp.stride)
+        pd = mp.padding if isinstance(mp.padding, (tuple, list)) else (mp.padding, mp.padding)
+        if tuple(st) != tuple(k) or tuple(pd) != (0, 0) or mp.dilation not in (1, (1, 1)) or mp.ceil_mode:
+            raise RuntimeError("the B200 path implements nn.MaxPool2d(pool) as the reference builds it (stride = kernel, no padding)")
+        pool = (int(k[0]), int(k[1]))
+    return _ACT_CODES[type(block.activation)], pool
 
 
 class _ConvFrontFn(torch.autograd.Function):
@@ -49,7 +64,7 @@ class _ConvFrontFn(torch.autograd.Function):
         Cin = 1
         saved = []
         for bi, block in enumerate(blocks):
-            _check_block(block)
+            act_code, pool = _check_block(block)
             conv = block.conv
             if conv.in_channels != Cin:
                 raise RuntimeError("conv block %d expects %d input channels, got %d" % (bi, conv.in_channels, Cin))
@@ -62,24 +77,48 @@ class _ConvFrontFn(torch.autograd.Function):
             bn = block.batch_norm
             st = _bn_prepare(bn, y, M, Cout, training) if bn is not None else None
             last = bi == len(blocks) - 1
-            if last:   # [N, Ho, Cout, Wo]: feature index c*Wo + w, the order the reference feeds its RNN stack
-                out = torch.empty((N, Ho, Cout, Wo), dtype=torch.float32, device=dev)
-                strides = (Ho * Cout * Wo, Cout * Wo, 1, Wo)
-            else:      # channel-last for the next im2col
-                out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=dev)
-                strides = (Ho * Wo * Cout, Wo * Cout, Cout, 1)
-            _call("ctcb200_affine_relu", _lib.ptr(y), _lib.ptr(st.scale if st else None),
-                  _lib.ptr(st.shift if st else None), _lib.ptr(out), strides[0], strides[1], strides[2], strides[3],
-                  N, Ho, Wo, Cout, stream())
+
+            def _final_layout(Hx, Wx):
+                if last:   # [N, H, Cout, W]: feature index c*W + w, the order the reference feeds its RNN stack
+                    return torch.empty((N, Hx, Cout, Wx), dtype=torch.float32, device=dev), (Hx * Cout * Wx, Cout * Wx, 1, Wx)
+                return torch.empty((N, Hx, Wx, Cout), dtype=torch.float32, device=dev), (Hx * Wx * Cout, Wx * Cout, Cout, 1)
+
+            pool_idx = None
+            if pool is None:
+                a_act, a_strides = _final_layout(Ho, Wo)   # activation output directly in the block's output layout
+                _call("ctcb200_affine_act", _lib.ptr(y), _lib.ptr(st.scale if st else None), _lib.ptr(st.shift if st else None),
+                      _lib.ptr(a_act), a_strides[0], a_strides[1], a_strides[2], a_strides[3], N, Ho, Wo, Cout, act_code, stream())
+                out, strides, Hq, Wq = a_act, a_strides, Ho, Wo
+            else:
+                a_act = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=dev)   # channel-last for the pooling
+                a_strides = (Ho * Wo * Cout, Wo * Cout, Cout, 1)
+                _call("ctcb200_affine_act", _lib.ptr(y), _lib.ptr(st.scale if st else None), _lib.ptr(st.shift if st else None),
+                      _lib.ptr(a_act), a_strides[0], a_strides[1], a_strides[2], a_strides[3], N, Ho, Wo, Cout, act_code, stream())
+                Hq, Wq = Ho // pool[0], Wo // pool[1]
+                if Hq < 1 or Wq < 1:
+                    raise RuntimeError("MaxPool2d%r does not fit the %dx%d activation of conv block %d" % (pool, Ho, Wo, bi))
+                pooled = torch.empty((N, Hq, Wq, Cout), dtype=torch.float32, device=dev)
+                pool_idx = torch.empty((N, Hq, Wq, Cout), dtype=torch.uint8, device=dev)
+                _call("ctcb200_maxpool2d_fwd", _lib.ptr(a_act), _lib.ptr(pooled), _lib.ptr(pool_idx), N, Ho, Wo, Cout, pool[0],
+                      pool[1], stream())
+                if last:   # re-lay out for the RNN stack
+                    out, strides = _final_layout(Hq, Wq)
+                    _call("ctcb200_affine_act", _lib.ptr(pooled), None, None, _lib.ptr(out), strides[0], strides[1], strides[2],
+                          strides[3], N, Hq, Wq, Cout, _ACT_IDENTITY, stream())
+                else:
+                    out, strides = pooled, (Hq * Wq * Cout, Wq * Cout, Cout, 1)
             mask = None
             p_drop = float(block.dropout.p)
             if training and p_drop > 0.0:
                 mask = _dropout_mask(model, out.shape, p_drop, dev)
+                if out is a_act and act_code != 0 and need_grad:
+                    out = out.clone()   # tanh / sigmoid derivatives need the activation's own output, not its dropped copy
                 _call("ctcb200_dropout_apply", _lib.ptr(out), _lib.ptr(mask), _inv_keep(p_drop), out.numel(), stream())
             if need_grad:
-                saved.append(dict(geom=geom, Cout=Cout, M=M, x=act, y=y, st=st, out=out, strides=strides, mask=mask,
+                saved.append(dict(geom=geom, Cout=Cout, M=M, x=act, y=y, st=st, a_act=a_act, a_strides=a_strides, act=act_code,
+                                  pool=pool, pool_idx=pool_idx, out_strides=strides, Hq=Hq, Wq=Wq, last=last, mask=mask,
                                   p_drop=p_drop))
-            act, Hi, Wi, Cin = out, Ho, Wo, Cout
+            act, Hi, Wi, Cin = out, Hq, Wq, Cout
         ctx.saved = saved if need_grad else None
         ctx.model = model
         ctx.param_list = params
@@ -104,10 +143,22 @@ class _ConvFrontFn(torch.autograd.Function):
             if rec["mask"] is not None:
                 _call("ctcb200_dropout_apply", _lib.ptr(da), _lib.ptr(rec["mask"]), _inv_keep(rec["p_drop"]), da.numel(),
                       stream())
+            if rec["pool"] is not None:
+                Hq, Wq = rec["Hq"], rec["Wq"]
+                if rec["last"]:   # [N, Hq, Cout, Wq] gradient back to channel-last rows
+                    os_ = rec["out_strides"]
+                    dp = torch.empty((N, Hq, Wq, Cout), dtype=torch.float32, device=dev)
+                    _call("ctcb200_act_bwd_gather", _lib.ptr(da), None, _lib.ptr(dp), os_[0], os_[1], os_[2], os_[3], N, Hq, Wq,
+                          Cout, _ACT_IDENTITY, stream())
+                else:
+                    dp = da
+                da = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=dev)
+                _call("ctcb200_maxpool2d_bwd", _lib.ptr(dp), _lib.ptr(rec["pool_idx"]), _lib.ptr(da), N, Ho, Wo, Cout,
+                      rec["pool"][0], rec["pool"][1], stream())
             dz = torch.empty((M, Cout), dtype=torch.float32, device=dev)
-            s = rec["strides"]
-            _call("ctcb200_relu_bwd_gather", _lib.ptr(da), _lib.ptr(rec["out"]), _lib.ptr(dz), s[0], s[1], s[2], s[3], N, Ho,
-                  Wo, Cout, stream())
+            s = rec["a_strides"]
+            _call("ctcb200_act_bwd_gather", _lib.ptr(da), _lib.ptr(rec["a_act"]), _lib.ptr(dz), s[0], s[1], s[2], s[3], N, Ho,
+                  Wo, Cout, rec["act"], stream())
             bn = block.batch_norm
             if bn is not None:
                 dgam = torch.empty(Cout, dtype=torch.float32, device=dev)

@@ -233,11 +233,28 @@ __global__ void add_bias_rows_kernel(float* __restrict__ y, const float* __restr
         y[e] += bias[e % C];
 }
 
-// a(n, h, w, c) = relu(y[m, c] * scale[c] + shift[c]), written with explicit output strides
+// activation selector shared by the forward / backward kernels: the reference builds LayerCNN with
+// supported_activate = {relu, tanh, sigmoid} (train_ctc.py:21, model_ctc.py:50); 3 = identity (layout change only)
+enum { ACT_RELU = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_IDENTITY = 3 };
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == ACT_TANH) return tanhf(v);
+    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    return v;
+}
+// derivative expressed through the activation's OUTPUT a (what the forward pass keeps)
+__device__ __forceinline__ float act_grad(float a, int act) {
+    if (act == ACT_RELU) return a > 0.0f ? 1.0f : 0.0f;
+    if (act == ACT_TANH) return 1.0f - a * a;
+    if (act == ACT_SIGMOID) return a * (1.0f - a);
+    return 1.0f;
+}
+
+// a(n, h, w, c) = act(y[m, c] * scale[c] + shift[c]), written with explicit output strides
 __global__ void __launch_bounds__(256)
-affine_relu_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                   float* __restrict__ a, long long sn, long long sh, long long sw, long long sc, int N, int Ho, int Wo,
-                   int C) {
+affine_act_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                  float* __restrict__ a, long long sn, long long sh, long long sw, long long sc, int N, int Ho, int Wo,
+                  int C, int act) {
     const long long total = static_cast<long long>(N) * Ho * Wo * C;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
          e += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -247,14 +264,14 @@ affine_relu_kernel(const float* __restrict__ y, const float* __restrict__ scale,
         const long long n = m / (static_cast<long long>(Wo) * Ho);
         float v = y[e];
         if (scale) v = v * scale[c] + shift[c];
-        a[n * sn + h * sh + w * sw + c * sc] = fmaxf(v, 0.0f);
+        a[n * sn + h * sh + w * sw + c * sc] = act_fwd(v, act);
     }
 }
 
-// dz[m, c] = a(n,h,w,c) > 0 ? da(n,h,w,c) : 0   (da and a share the strided layout)
+// dz[m, c] = act'(a(n,h,w,c)) * da(n,h,w,c)   (da and a share the strided layout)
 __global__ void __launch_bounds__(256)
-relu_bwd_gather_kernel(const float* __restrict__ da, const float* __restrict__ a, float* __restrict__ dz, long long sn,
-                       long long sh, long long sw, long long sc, int N, int Ho, int Wo, int C) {
+act_bwd_gather_kernel(const float* __restrict__ da, const float* __restrict__ a, float* __restrict__ dz, long long sn,
+                      long long sh, long long sw, long long sc, int N, int Ho, int Wo, int C, int act) {
     const long long total = static_cast<long long>(N) * Ho * Wo * C;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
          e += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -263,7 +280,50 @@ relu_bwd_gather_kernel(const float* __restrict__ da, const float* __restrict__ a
         const int w = static_cast<int>(m % Wo), h = static_cast<int>((m / Wo) % Ho);
         const long long n = m / (static_cast<long long>(Wo) * Ho);
         const long long o = n * sn + h * sh + w * sw + c * sc;
-        dz[e] = a[o] > 0.0f ? da[o] : 0.0f;
+        dz[e] = act_grad(a ? a[o] : 1.0f, act) * da[o];
+    }
+}
+
+// nn.MaxPool2d(pool) on channel-last activations (kernel = stride = pool, no padding, floor mode: model_ctc.py:53-54);
+// idx keeps the position of the maximum inside its window (first maximum wins, like torch) for the backward pass
+__global__ void __launch_bounds__(256)
+maxpool2d_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx, int N, int H, int W, int C,
+                     int kh, int kw, int Ho, int Wo) {
+    const long long total = static_cast<long long>(N) * Ho * Wo * C;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % C);
+        const long long m = e / C;
+        const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
+        const long long n = m / (static_cast<long long>(Wo) * Ho);
+        float best = -INFINITY;
+        int arg = 0;
+        for (int r = 0; r < kh; ++r)
+            for (int q = 0; q < kw; ++q) {
+                const float v = x[((n * H + ho * kh + r) * W + wo * kw + q) * C + c];
+                if (v > best || (v != v && best == best)) { best = v; arg = r * kw + q; }
+            }
+        y[e] = best;
+        idx[e] = static_cast<uint8_t>(arg);
+    }
+}
+__global__ void __launch_bounds__(256)
+maxpool2d_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx, int N, int H, int W,
+                     int C, int kh, int kw, int Ho, int Wo) {
+    const long long total = static_cast<long long>(N) * H * W * C;   // every input element written once (no atomics)
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % C);
+        const long long p = e / C;
+        const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
+        const long long n = p / (static_cast<long long>(W) * H);
+        const int ho = h / kh, wo = w / kw;
+        float v = 0.0f;
+        if (ho < Ho && wo < Wo) {
+            const long long o = ((n * Ho + ho) * Wo + wo) * C + c;
+            if (idx[o] == (h - ho * kh) * kw + (w - wo * kw)) v = dy[o];
+        }
+        dx[e] = v;
     }
 }
 
@@ -371,22 +431,47 @@ extern "C" CTCB200_API int ctcb200_add_bias_rows(float* y, const float* bias, in
     return OK;
 }
 
-extern "C" CTCB200_API int ctcb200_affine_relu(const float* y, const float* scale, const float* shift, float* a,
-                                               int64_t sn, int64_t sh, int64_t sw, int64_t sc, int N, int Ho, int Wo,
-                                               int C, ctcb200_stream_t stream_) {
+extern "C" CTCB200_API int ctcb200_affine_act(const float* y, const float* scale, const float* shift, float* a,
+                                              int64_t sn, int64_t sh, int64_t sw, int64_t sc, int N, int Ho, int Wo,
+                                              int C, int act, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    affine_relu_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * C), 256, 0, stream>>>(y, scale, shift, a, sn, sh, sw,
-                                                                                            sc, N, Ho, Wo, C);
+    CTCB_REQUIRE(act >= 0 && act <= 3, "affine_act: activation code %d not in {0 relu, 1 tanh, 2 sigmoid, 3 identity}", act);
+    affine_act_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * C), 256, 0, stream>>>(y, scale, shift, a, sn, sh, sw, sc,
+                                                                                           N, Ho, Wo, C, act);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
 
-extern "C" CTCB200_API int ctcb200_relu_bwd_gather(const float* da, const float* a, float* dz, int64_t sn, int64_t sh,
-                                                   int64_t sw, int64_t sc, int N, int Ho, int Wo, int C,
-                                                   ctcb200_stream_t stream_) {
+extern "C" CTCB200_API int ctcb200_act_bwd_gather(const float* da, const float* a, float* dz, int64_t sn, int64_t sh,
+                                                  int64_t sw, int64_t sc, int N, int Ho, int Wo, int C, int act,
+                                                  ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    relu_bwd_gather_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * C), 256, 0, stream>>>(da, a, dz, sn, sh, sw, sc, N,
-                                                                                                Ho, Wo, C);
+    CTCB_REQUIRE(act >= 0 && act <= 3, "act_bwd_gather: activation code %d not in {0,1,2,3}", act);
+    CTCB_REQUIRE(a != nullptr || act == 3, "act_bwd_gather: the activation output is needed for act=%d", act);
+    act_bwd_gather_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * C), 256, 0, stream>>>(da, a, dz, sn, sh, sw, sc, N,
+                                                                                               Ho, Wo, C, act);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_maxpool2d_fwd(const float* x_nhwc, float* y_nhwc, void* idx_u8, int N, int H, int W, int C,
+                                                 int kh, int kw, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(kh > 0 && kw > 0 && kh * kw <= 256 && H >= kh && W >= kw, "maxpool2d_fwd: bad window %dx%d for %dx%d", kh, kw, H, W);
+    const int Ho = H / kh, Wo = W / kw;
+    maxpool2d_fwd_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * C), 256, 0, stream>>>(
+        x_nhwc, y_nhwc, static_cast<uint8_t*>(idx_u8), N, H, W, C, kh, kw, Ho, Wo);
+    CTCB_LAUNCH_CHECK();
+    return OK;
+}
+
+extern "C" CTCB200_API int ctcb200_maxpool2d_bwd(const float* dy_nhwc, const void* idx_u8, float* dx_nhwc, int N, int H, int W,
+                                                 int C, int kh, int kw, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTCB_REQUIRE(kh > 0 && kw > 0 && H >= kh && W >= kw, "maxpool2d_bwd: bad window");
+    const int Ho = H / kh, Wo = W / kw;
+    maxpool2d_bwd_kernel<<<grid_for(static_cast<long long>(N) * H * W * C), 256, 0, stream>>>(
+        dy_nhwc, static_cast<const uint8_t*>(idx_u8), dx_nhwc, N, H, W, C, kh, kw, Ho, Wo);
     CTCB_LAUNCH_CHECK();
     return OK;
 }

@@ -1,14 +1,62 @@
 """Drop-in for timit/utils/NgramLM.py: ARPA bigram language model used by the beam decoder.
 
-Same class name, constructor and `get_uni_prob` / `get_bi_prob` / `score_bg` behaviour: the file is the
-*tab-separated* ARPA the reference's IRSTLM recipe writes, log10 scores are converted to natural log,
-`UNK` aliases `<unk>`, an empty unit means sentence start (as w1) or sentence end (as w2), and a missing
-bigram backs off to backoff(w1) + unigram(w2). `dense_table` flattens `get_bi_prob` over the model's units
+Same class name, constructor and `get_uni_prob` / `get_bi_prob` / `score_bg` behaviour on the *tab-separated* ARPA
+the reference's IRSTLM recipe writes: log10 scores converted to natural log, `UNK` aliases `<unk>`, an empty unit
+means sentence start (as w1) or sentence end (as w2), a missing bigram backs off to backoff(w1) + unigram(w2).
+The loader itself (`parse_arpa`) is more tolerant than the reference's: space-separated entries and higher-order
+sections are parsed too. `dense_table` flattens `get_bi_prob` over the model's units
 into the [(C+1) x (C+1)] float64 table the beam-search kernel reads from HBM/L2.
 """
 import math
+import re
 
 import numpy as np
+
+
+_SECTION = re.compile(r"^\\(\d+)-grams:\s*$")
+
+
+def parse_arpa(path):
+    """{order: {"w1 ... wn": (log10 prob, log10 back-off)}} from an ARPA file.
+
+    Accepts what the reference's loader accepts — the TAB-separated layout IRSTLM / KenLM write (`prob<TAB>w1 w2<TAB>backoff`,
+    timit/utils/NgramLM.py:42-55) — and, beyond it, entries whose fields are separated by plain spaces
+    (SRILM style), sections of any order (`\\3-grams:` is parsed into its own table instead of leaking into the bigram
+    table as in NgramLM.py:39-55), the `\\data\\` / `\\end\\` markers, blank lines and Windows line ends. An entry of order n
+    has n words; a trailing extra field is the back-off weight."""
+    tables = {}
+    order = 0
+    with open(path, "r") as fh:
+        for raw in fh:
+            line = raw.rstrip("\r\n")
+            m = _SECTION.match(line.strip())
+            if m:
+                order = int(m.group(1))
+                tables.setdefault(order, {})
+                continue
+            stripped = line.strip()
+            if not stripped or stripped.startswith("\\") or order == 0:
+                if stripped == "\\end\\":
+                    order = 0
+                continue
+            if "\t" in line:
+                fields = [f for f in line.split("\t")]
+                if len(fields) < 2:
+                    continue
+                words, rest = fields[1], fields[2:]
+            else:
+                toks = stripped.split()
+                if len(toks) < 1 + order:
+                    continue
+                words, rest = " ".join(toks[1:1 + order]), toks[1 + order:]
+                fields = toks
+            try:
+                logp = float(fields[0])
+                backoff = float(rest[0]) if rest and rest[0].strip() else 0.0
+            except ValueError:
+                continue
+            tables[order][words] = (logp, backoff)
+    return tables
 
 
 class LanguageModel(object):
@@ -17,32 +65,16 @@ class LanguageModel(object):
         self.start = start
         self.end = end
         self.unk = unk
-        self.scale = math.log(10)
+        self.scale = math.log(10)     # ARPA stores log10; the search adds natural logs (NgramLM.py:22)
         self.initngrams(arpa_file)
 
     def initngrams(self, fn):
-        self.unigram = {}
-        self.bigram = {}
-        if self.n_gram == 3:
-            self.trigrame = {}
-        section = 0
-        with open(fn, "r") as fh:
-            for raw in fh.readlines():
-                line = raw.strip("\n")
-                if line == "\\1-grams:":
-                    section = 1
-                    continue
-                if line == "\\2-grams:":
-                    section = 2
-                    continue
-                if section == 0:
-                    continue
-                fields = line.split("\t")
-                table = self.unigram if section == 1 else self.bigram
-                if len(fields) == 3:
-                    table[fields[1]] = [self.scale * float(fields[0]), self.scale * float(fields[2])]
-                elif len(fields) == 2:
-                    table[fields[1]] = [self.scale * float(fields[0]), 0.0]
+        tables = parse_arpa(fn)
+        ln10 = self.scale
+        self.unigram = {w: [ln10 * p, ln10 * b] for w, (p, b) in tables.get(1, {}).items()}
+        self.bigram = {w: [ln10 * p, ln10 * b] for w, (p, b) in tables.get(2, {}).items()}
+        self.higher = {n: t for n, t in tables.items() if n > 2}   # kept for inspection; the decoder scores bigrams only
+        # class 1 of the acoustic model is spelled `UNK` (data_loader.py:16) and scores as the LM's unknown word (NgramLM.py:58)
         self.unigram["UNK"] = self.unigram[self.unk]
 
     def get_uni_prob(self, wid):

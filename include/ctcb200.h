@@ -195,8 +195,10 @@ CTCB200_API int ctcb200_dropout_apply(float* a, const void* mask_u8, float inv_k
  * conv2d_fwd: y = conv(x, w) + bias (bias may be NULL). conv2d_wgrad: dw = sum_m dy[m,:] (x) patch(m); ws holds
  * ctcb200_conv2d_wgrad_ws_bytes() bytes of per-CTA partial sums (reduced in a fixed order: deterministic).
  * conv2d_dgrad: dx = conv^T(dy, w), every element written once.
- * affine_relu: a(n,h,w,c) = relu(y[m,c]*scale[c]+shift[c]) written with strides (sn,sh,sw,sc); scale may be NULL.
- * relu_bwd_gather: dz[m,c] = a(n,h,w,c) > 0 ? da(n,h,w,c) : 0. col_sum: out[c] = sum_m y[m,c] (bias gradient). */
+ * affine_act: a(n,h,w,c) = act(y[m,c]*scale[c]+shift[c]) written with strides (sn,sh,sw,sc); scale may be NULL; act = 0 relu,
+ * 1 tanh, 2 sigmoid (train_ctc.py:21 supported_activate), 3 identity (layout change only).
+ * act_bwd_gather: dz[m,c] = act'(a(n,h,w,c)) * da(n,h,w,c), the derivative taken from the activation's output a.
+ * col_sum: out[c] = sum_m y[m,c] (bias gradient). */
 CTCB200_API int ctcb200_conv2d_fwd(const float* x_nhwc, const float* w, const float* bias, float* y, int N, int Hi, int Wi,
                                    int Cin, int Cout, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
                                    ctcb200_stream_t stream);
@@ -208,11 +210,17 @@ CTCB200_API int ctcb200_conv2d_dgrad(const float* dy, const float* w, float* dx_
                                      int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
                                      ctcb200_stream_t stream);
 CTCB200_API int ctcb200_add_bias_rows(float* y, const float* bias, int64_t R, int C, ctcb200_stream_t stream);
-CTCB200_API int ctcb200_affine_relu(const float* y, const float* scale, const float* shift, float* a, int64_t sn,
-                                    int64_t sh, int64_t sw, int64_t sc, int N, int Ho, int Wo, int C,
-                                    ctcb200_stream_t stream);
-CTCB200_API int ctcb200_relu_bwd_gather(const float* da, const float* a, float* dz, int64_t sn, int64_t sh, int64_t sw,
-                                        int64_t sc, int N, int Ho, int Wo, int C, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_affine_act(const float* y, const float* scale, const float* shift, float* a, int64_t sn,
+                                   int64_t sh, int64_t sw, int64_t sc, int N, int Ho, int Wo, int C, int act,
+                                   ctcb200_stream_t stream);
+CTCB200_API int ctcb200_act_bwd_gather(const float* da, const float* a, float* dz, int64_t sn, int64_t sh, int64_t sw,
+                                       int64_t sc, int N, int Ho, int Wo, int C, int act, ctcb200_stream_t stream);
+/* nn.MaxPool2d(pool) of LayerCNN (model_ctc.py:53-54,65-66): kernel = stride = pool, floor mode, channel-last tensors;
+ * idx_u8 [N,H/kh,W/kw,C] keeps the arg-max position inside each window for the backward pass. */
+CTCB200_API int ctcb200_maxpool2d_fwd(const float* x_nhwc, float* y_nhwc, void* idx_u8, int N, int H, int W, int C, int kh,
+                                      int kw, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_maxpool2d_bwd(const float* dy_nhwc, const void* idx_u8, float* dx_nhwc, int N, int H, int W, int C,
+                                      int kh, int kw, ctcb200_stream_t stream);
 CTCB200_API int ctcb200_col_sum(const float* y, float* out, int64_t R, int C, ctcb200_stream_t stream);
 
 /* ---- beam decode: replaces ctcBeamSearch.decode, timit/utils/BeamSearch.py:73-153 (called by

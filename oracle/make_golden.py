@@ -28,14 +28,25 @@ MODEL_CASES = {
     "rnn_bn": dict(T=10, N=3, F=40, H=128, L=2, C=12, bn=True, cnn=False, S=4, seed=3),
     "rnn_nobn": dict(T=9, N=2, F=40, H=128, L=1, C=9, bn=False, cnn=False, S=3, seed=5),
     "cnn_rnn": dict(T=16, N=2, F=40, H=128, L=1, C=12, bn=True, cnn=True, S=3, seed=7),
+    # LayerCNN's optional MaxPool2d (model_ctc.py:53-54), here over time after block 0. (The other entries of train_ctc.py:21's
+    # supported_activate, tanh / sigmoid, cannot be constructed in the reference: `activation_function(inplace=True)`,
+    # model_ctc.py:50, is a TypeError for them — the drop-in raises the same error from the same expression.)
+    "cnn_pool": dict(T=24, N=2, F=40, H=128, L=1, C=12, bn=True, cnn=True, S=3, seed=9, act="relu",
+                     cnn_layers=[[[1, 8], [3, 3], [1, 2], [1, 1], [2, 1]], [[8, 8], [3, 3], [1, 1], [1, 1], None]]),
 }
 CNN_LAYERS = [[(1, 32), (3, 3), (1, 2), (1, 1), None], [(32, 32), (3, 3), (2, 2), (1, 1), None]]
+
+
+ACTS = {"relu": nn.ReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}
 
 
 def model_args(cfg):
     rnn_param = {"rnn_input_size": cfg["F"], "rnn_hidden_size": cfg["H"], "rnn_layers": cfg["L"],
                  "rnn_type": nn.LSTM, "bidirectional": True, "batch_norm": cfg["bn"]}
-    cnn_param = {"batch_norm": cfg["bn"], "activate_function": nn.ReLU, "layer": CNN_LAYERS} if cfg["cnn"] else None
+    layers = CNN_LAYERS
+    if cfg.get("cnn_layers"):
+        layers = [[tuple(l[0]), tuple(l[1]), tuple(l[2]), tuple(l[3]), tuple(l[4]) if l[4] else None] for l in cfg["cnn_layers"]]
+    cnn_param = {"batch_norm": cfg["bn"], "activate_function": ACTS[cfg.get("act", "relu")], "layer": layers} if cfg["cnn"] else None
     return dict(add_cnn=cfg["cnn"], cnn_param=cnn_param, rnn_param=rnn_param, num_class=cfg["C"], drop_out=0.0)
 
 
@@ -67,8 +78,10 @@ def gen_ctc():
     print("ctc_small: nll", nll.detach().numpy())
 
 
-def gen_models(ref):
+def gen_models(ref, only=None):
     for name, cfg in MODEL_CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(cfg["seed"])
         model = ref.CTC_Model(**model_args(cfg))
         checksum = {k: float(v.double().abs().sum()) for k, v in model.state_dict().items()}

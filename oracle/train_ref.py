@@ -2,8 +2,9 @@
 timit/steps/train_ctc.py:162-231 as a pure function of the per-epoch (dev_loss, acc) sequence.
 
 The reference's loop cannot be imported (it lives inside `main`, behind Visdom and the Kaldi data layer), so this is a
-line-by-line restatement — parity unpinned against a live run; it is deterministic integer/float bookkeeping and is used to
-check ctc_pytorch_b200.train.DevLossSchedule on random sequences.
+restatement; it is pinned by tests/test_train_host.py::test_schedule_pinned_to_the_reference_loop_source, which execs the
+reference's own loop text with stubs (oracle/train_live.py) and compares epoch by epoch. Used to check
+ctc_pytorch_b200.train.DevLossSchedule on random sequences.
 """
 
 

@@ -175,3 +175,21 @@ def test_reference_arm_json_contract():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_arpa_loader_tolerates_spaces_and_higher_orders(golden_dir, tmp_path):
+    """N4: same tables as the reference's loader on its own tab-separated format, and the same tables again from a
+    space-separated, CRLF-terminated copy with a trigram section (which the reference's loader cannot read)."""
+    tab = os.path.join(golden_dir, "lm_c8.arpa")
+    lm = LanguageModel(arpa_file=tab)
+    if HAVE_REF:
+        rlm = ref_shim.load().LanguageModel(arpa_file=tab)
+        assert lm.unigram == rlm.unigram and lm.bigram == rlm.bigram
+    text = open(tab).read().replace("\t", " ").replace("\\end\\", "\\3-grams:\n-0.5 a b c\n\n\\end\\")
+    path = str(tmp_path / "spaces.arpa")
+    with open(path, "w", newline="") as fh:
+        fh.write(text.replace("\n", "\r\n"))
+    lm2 = LanguageModel(arpa_file=path)
+    assert lm2.unigram == lm.unigram and lm2.bigram == lm.bigram
+    assert lm2.higher[3] == {"a b c": (-0.5, 0.0)}
+    assert lm2.get_bi_prob("", "a") == lm.get_bi_prob("", "a") and lm2.get_bi_prob("f", "") == lm.get_bi_prob("f", "")

@@ -297,7 +297,7 @@ def _golden_model(golden_dir, name):
     return m.to(DEV), meta, g
 
 
-@pytest.mark.parametrize("name", ["rnn_bn", "rnn_nobn", "cnn_rnn"])
+@pytest.mark.parametrize("name", ["rnn_bn", "rnn_nobn", "cnn_rnn", "cnn_pool"])
 def test_model_golden(golden_dir, name):
     """The run_epoch loop body of the reference (train_ctc.py:44-65) on the golden batch."""
     from ctc_pytorch_b200.loss import CTCLoss

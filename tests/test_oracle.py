@@ -140,12 +140,13 @@ def test_decode_oracle_matches_reference_live(golden_dir):
 
 # ---------------------------------------------------------------------------------------------- model
 def _build_oracle(cfg):
-    from oracle.make_golden import CNN_LAYERS
+    from oracle.make_golden import model_args
+    args = model_args(cfg)
     return model_ref.RefAcousticModel(cfg["F"], cfg["H"], cfg["L"], cfg["C"], batch_norm=cfg["bn"],
-                                      cnn_layers=CNN_LAYERS if cfg["cnn"] else None, cnn_batch_norm=cfg["bn"])
+                                      cnn_layers=args["cnn_param"]["layer"] if cfg["cnn"] else None, cnn_batch_norm=cfg["bn"])
 
 
-@pytest.mark.parametrize("name", ["rnn_bn", "rnn_nobn", "cnn_rnn"])
+@pytest.mark.parametrize("name", ["rnn_bn", "rnn_nobn", "cnn_rnn", "cnn_pool"])
 def test_model_oracle_matches_golden(golden_dir, name):
     meta = json.load(open(os.path.join(golden_dir, "model_%s.json" % name)))
     g = np.load(os.path.join(golden_dir, "model_%s.npz" % name))

@@ -1,5 +1,6 @@
 """CPU tests of the training-loop services (ctc_pytorch_b200/train.py): the lr / rollback schedule against the oracle's
-restatement of train_ctc.py:162-231, and checkpoint interchange with the unmodified reference when it is mounted."""
+restatement of train_ctc.py:162-231 AND against the reference's own loop source exec'ed with stubs (oracle/train_live.py),
+and checkpoint interchange with the unmodified reference when it is mounted."""
 import random
 
 import pytest
@@ -46,6 +47,34 @@ def test_schedule_matches_reference_policy(seed):
         assert g == w
     assert sched.loss_best == final["loss_best"] and sched.acc_best == final["acc_best"]
     assert any(w["rollback"] for w in want)   # the sequences do exercise the halving path
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference modules neither mounted nor staged")
+@pytest.mark.parametrize("seed", range(12))
+def test_schedule_pinned_to_the_reference_loop_source(seed):
+    """The policy's oracle is the reference's OWN statements: oracle/train_live.py cuts the `while not stop_train:` loop out of the
+    unmodified steps/train_ctc.py (lines 159-231), execs it with stubs, and both the restatement (oracle/train_ref.py) and
+    DevLossSchedule must reproduce its learning rates, roll-backs and final bookkeeping epoch by epoch."""
+    from oracle import train_live
+    losses, accs = _sequence(seed, 120)
+    losses[0] = 30.0           # below the initial loss_best = 1000 so that the counter is bound, as in any real run
+    init_lr, decay, eps, epochs = 1e-3, 0.5, 0.05, 100
+    live, final = train_live.reference_schedule_trace(losses, accs, init_lr, decay, eps, epochs)
+    restated, rfinal = train_ref.schedule_trace(losses, accs, init_lr, decay, eps, epochs)
+    sched = DevLossSchedule(init_lr, decay, eps)
+    ours, count = [], 0
+    while not sched.stop and count < epochs and count < len(losses):
+        count += 1
+        sched.begin_epoch()
+        act = sched.update(losses[count - 1], accs[count - 1])
+        ours.append(dict(act, lr=sched.learning_rate))
+    assert len(live) == len(restated) == len(ours) == final["epochs"] == rfinal["epochs"]
+    for a, b, c in zip(live, restated, ours):
+        assert a["lr"] == pytest.approx(b["lr"], rel=0, abs=1e-18) and a["lr"] == pytest.approx(c["lr"], rel=0, abs=1e-18)
+        assert a["rollback"] == b["rollback"] == c["rollback"]
+    assert final["loss_best"] == rfinal["loss_best"] == sched.loss_best
+    assert final["acc_best"] == rfinal["acc_best"] == sched.acc_best
+    assert any(a["rollback"] for a in live)
 
 
 def test_schedule_reproduces_the_unbound_counter_quirk():
