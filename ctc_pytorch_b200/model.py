@@ -268,8 +268,20 @@ def _bn_prepare(bn, x2d, R, C, training, n_valid=0):
 def _packed_weights(model, li, rnn, H, I, Ipad, x3, dev):
     """bf16 operand layouts of one layer's four weight matrices (hi, and lo in x3 mode). Re-packed only when a parameter
     changed since the last call (inference / evaluation loops reuse them; an optimizer step bumps the version counters)."""
-    key = (x3, rnn.weight_ih_l0._version, rnn.weight_hh_l0._version, rnn.weight_ih_l0_reverse._version,
-           rnn.weight_hh_l0_reverse._version, rnn.weight_ih_l0.data_ptr(), str(dev))
+    uni = not hasattr(rnn, "weight_ih_l0_reverse")
+    if uni:
+        # unidirectional layer (rnn_param["bidirectional"] = False): the kernels always run both directions of a layer
+        # side by side on disjoint SMs, so the forward-only layer is the same launch with ZERO reverse weights — the reverse
+        # half computes h = 0 and is dropped; no extra time on the recurrence's critical path
+        zi = model.__dict__.setdefault("_zero_rev", {}).get((li, str(dev)))
+        if zi is None:
+            zi = (torch.zeros_like(rnn.weight_ih_l0), torch.zeros_like(rnn.weight_hh_l0))
+            model.__dict__["_zero_rev"][(li, str(dev))] = zi
+        wih_r, whh_r = zi
+    else:
+        wih_r, whh_r = rnn.weight_ih_l0_reverse, rnn.weight_hh_l0_reverse
+    key = (x3, rnn.weight_ih_l0._version, rnn.weight_hh_l0._version, wih_r._version, whh_r._version,
+           rnn.weight_ih_l0.data_ptr(), str(dev))
     cache = model.__dict__.setdefault("_pack_cache", {})
     ent = cache.get(li)
     if ent is not None and ent[0] == key:
@@ -281,7 +293,7 @@ def _packed_weights(model, li, rnn, H, I, Ipad, x3, dev):
         whh_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
         whhT_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
         _call("ctcb200_pack_lstm_weights", _lib.ptr(rnn.weight_ih_l0), _lib.ptr(rnn.weight_hh_l0),
-              _lib.ptr(rnn.weight_ih_l0_reverse), _lib.ptr(rnn.weight_hh_l0_reverse), _lib.ptr(wih_p),
+              _lib.ptr(wih_r), _lib.ptr(whh_r), _lib.ptr(wih_p),
               _lib.ptr(wihT_p), _lib.ptr(whh_p), _lib.ptr(whhT_p), H, I, Ipad, part, _lib.stream())
         parts.append((wih_p, wihT_p, whh_p, whhT_p))
     packed = tuple(_Opnd(parts[0][i], parts[1][i] if x3 else None) for i in range(4))
@@ -310,9 +322,12 @@ class _RnnStackFn(torch.autograd.Function):
         Rp = T * Np  # width of the time-major transposed operands (batch axis padded to 8)
         H = model.rnn_param["rnn_hidden_size"]
         C = model.num_class
+        D = 2 if model.rnn_param["bidirectional"] else 1   # D = 1: forward half only (see _packed_weights)
+        if packed and D == 1:
+            raise RuntimeError("the packed-sequence path implements bidirectional layers only")
         layers = list(model.rnns.children())
         ws = _Workspace()
-        ws.geom, ws.layers_n, ws.x3 = geom, len(layers), x3
+        ws.geom, ws.layers_n, ws.x3, ws.D = geom, len(layers), x3, D
         ws.lengths, ws.n_valid, ws.raw_out = lengths, n_valid, raw_out
         ws.L = []
         stream = _lib.stream
@@ -344,7 +359,7 @@ class _RnnStackFn(torch.autograd.Function):
             rec.bn = None
             layer_bn = _unwrap(layer.batch_norm)
             if li > 0:
-                I = 2 * H
+                I = D * H
                 rec.I = I
                 h_prev_r = _realign(h_prev, lengths, T, N, I, 0, -1) if packed else None
                 if layer_bn is not None:
@@ -380,6 +395,8 @@ class _RnnStackFn(torch.autograd.Function):
                 # kernel alignment (forward half left-, reverse half right-aligned, garbage in the padding) -> left-aligned
                 # layer output with zero padding: what pad_packed_sequence would show (my_863_corpus/steps/model.py:93-141)
                 hout = _realign(hout, lengths, T, N, 2 * H, H, 1)
+            if D == 1:
+                hout = hout[:, :H].contiguous()    # the layer's output is the forward half
             rec.mask = None
             if training and p_drop > 0.0:
                 rec.mask = _dropout_mask(model, hout.shape, p_drop, dev)
@@ -390,7 +407,7 @@ class _RnnStackFn(torch.autograd.Function):
             h_prev = hout
 
         # output layer: (BatchNorm1d) + Linear(no bias) + LogSoftmax
-        F2 = 2 * H
+        F2 = D * H
         fc = _unwrap(model.fc)
         fc_bn, fc_lin = (fc[0], fc[1]) if isinstance(fc, nn.Sequential) else (None, fc)
         C = fc_lin.weight.shape[0]
@@ -421,12 +438,12 @@ class _RnnStackFn(torch.autograd.Function):
         if ws is None:
             raise RuntimeError("backward through a forward pass that ran without gradient bookkeeping")
         T, N, H, C, R, Rp, Np = ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np
-        x3 = ws.x3
+        x3, D = ws.x3, ws.D
         lengths, n_valid = ws.lengths, ws.n_valid
         packed = lengths is not None
         dev = g_out.device
         stream = _lib.stream
-        F2 = 2 * H
+        F2 = D * H
         layers = list(model.rnns.children())
         grads = {}
         grad_x = None
@@ -473,13 +490,16 @@ class _RnnStackFn(torch.autograd.Function):
             layer below). Returns (bn_x, bn_coef) when the input gradient is left to the BPTT kernel of that layer (no dropout
             mask in between), else applies it in place and returns None."""
             grads[bn_mod.weight], grads[bn_mod.bias] = dgam, dbet
-            if ((fuse_env and ws.L[below].mask is None) or not st.batch) and not (packed and st.batch):
+            if ((fuse_env and ws.L[below].mask is None and D == 2) or not st.batch) and not (packed and st.batch):
                 coef = torch.empty(3 * C_, dtype=torch.float32, device=dev)
                 _call("ctcb200_bn_bwd_coef", _lib.ptr(dy), _lib.ptr(x_in), _lib.ptr(st.mean), _lib.ptr(st.rstd),
                       _lib.ptr(bn_mod.weight), _lib.ptr(coef), _lib.ptr(dgam), _lib.ptr(dbet), R, C_, _lib.ptr(dws), n_valid,
                       stream())
                 if not st.batch:
                     coef[C_:].zero_()   # frozen statistics: dx = gamma * rstd * dy, no batch-coupling terms
+                    if D == 1:          # no fused consumer for a half-width gradient: apply the scale here
+                        dy.mul_(coef[:C_])
+                        return None
                     if ws.L[below].mask is not None:   # (cannot happen: masks only exist in training mode)
                         raise RuntimeError("dropout mask together with frozen BatchNorm statistics")
                 return (x_in, coef)
@@ -524,16 +544,19 @@ class _RnnStackFn(torch.autograd.Function):
                 _gemm(dgT.rows(4 * H, 8 * H), rec_.XrT, out=dwih[4 * H:], k=Rp, max_ctas=mc)
             else:
                 dwih = _gemm(dgT, XT, out=views_[0].view(8 * H, I_), k=Rp, max_ctas=mc)     # [8H, I], torch row order
-            grads[rnn.weight_ih_l0], grads[rnn.weight_ih_l0_reverse] = dwih[:4 * H], dwih[4 * H:]
+            grads[rnn.weight_ih_l0] = dwih[:4 * H]
             whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
             if T > 1:
                 K = Rp - Np  # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan
                 _gemm(dgT.rows(0, 4 * H), HT.rows(0, H), out=whf, a_koff=Np, b_koff=0, k=K, max_ctas=mc)
-                _gemm(dgT.rows(4 * H, 8 * H), HT.rows(H, 2 * H), out=whr, a_koff=0, b_koff=Np, k=K, max_ctas=mc)
+                if D == 2:
+                    _gemm(dgT.rows(4 * H, 8 * H), HT.rows(H, 2 * H), out=whr, a_koff=0, b_koff=Np, k=K, max_ctas=mc)
             else:
                 whf.zero_()
                 whr.zero_()
-            grads[rnn.weight_hh_l0], grads[rnn.weight_hh_l0_reverse] = whf, whr
+            grads[rnn.weight_hh_l0] = whf
+            if D == 2:
+                grads[rnn.weight_ih_l0_reverse], grads[rnn.weight_hh_l0_reverse] = dwih[4 * H:], whr
             if sync is not None:
                 sync.reduce(buf_)    # one collective per layer, behind the BPTT kernels of the layers below
             if torch.cuda.current_stream(dev) != main:  # allocated on the main stream, written here on the side stream
@@ -553,6 +576,10 @@ class _RnnStackFn(torch.autograd.Function):
                       dh.numel(), stream())
             if packed:   # left-aligned gradient -> the kernels' alignment (reverse half right-aligned), padding rows zeroed
                 dh = _realign(dh, lengths, T, N, 2 * H, H, -1)
+            if D == 1:   # forward half only: the kernel still takes a [R, 2H] gradient, the reverse half gets none
+                dh2 = torch.zeros((R, 2 * H), dtype=torch.float32, device=dev)
+                dh2[:, :H].copy_(dh)
+                dh = dh2
             dg = _Opnd(torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev),
                        torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev) if x3 else None)
             _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p.hi), _lib.ptr(rec.whhT_p.lo), _lib.ptr(rec.c_save),
@@ -677,8 +704,6 @@ class CTC_Model(nn.Module):
         _lib.require_cuda(x)
         if self.rnn_param["rnn_type"] is not nn.LSTM:
             raise RuntimeError("the B200 path implements nn.LSTM layers only (got %r)" % (self.rnn_param["rnn_type"],))
-        if not self.rnn_param["bidirectional"]:
-            raise RuntimeError("the B200 path implements bidirectional LSTM layers only")
         if next(self.parameters()).device != x.device:
             raise RuntimeError("model parameters and input must live on the same CUDA device")
         if self.precision not in ("bf16", "x3"):
@@ -689,8 +714,9 @@ class CTC_Model(nn.Module):
         for layer in self.rnns.children():
             if layer.batch_norm is not None:
                 plist += [layer.batch_norm.weight, layer.batch_norm.bias]
-            plist += [layer.rnn.weight_ih_l0, layer.rnn.weight_hh_l0, layer.rnn.weight_ih_l0_reverse,
-                      layer.rnn.weight_hh_l0_reverse]
+            plist += [layer.rnn.weight_ih_l0, layer.rnn.weight_hh_l0]
+            if self.num_directions == 2:
+                plist += [layer.rnn.weight_ih_l0_reverse, layer.rnn.weight_hh_l0_reverse]
         if isinstance(self.fc, nn.Sequential):
             plist += [self.fc[0].weight, self.fc[0].bias, self.fc[1].weight]
         else:

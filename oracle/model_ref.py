@@ -26,10 +26,10 @@ import torch.nn.functional as F
 
 
 class _RnnBlock(nn.Module):
-    def __init__(self, input_size, hidden, batch_norm, dropout):
+    def __init__(self, input_size, hidden, batch_norm, dropout, bidirectional=True):
         super().__init__()
         self.batch_norm = nn.BatchNorm1d(input_size) if batch_norm else None
-        self.rnn = nn.LSTM(input_size=input_size, hidden_size=hidden, bidirectional=True, bias=False)
+        self.rnn = nn.LSTM(input_size=input_size, hidden_size=hidden, bidirectional=bidirectional, bias=False)
         self.p = dropout
         self.fixed_mask = None   # tests: keep-mask [T*N, 2H] shared with the CUDA path instead of this process's RNG
 
@@ -64,8 +64,9 @@ class _ConvBlock(nn.Module):
 
 class RefAcousticModel(nn.Module):
     def __init__(self, input_size, hidden, layers, num_class, batch_norm=True, cnn_layers=None, cnn_batch_norm=True,
-                 cnn_act=nn.ReLU, dropout=0.0):
+                 cnn_act=nn.ReLU, dropout=0.0, bidirectional=True):
         super().__init__()
+        D = 2 if bidirectional else 1
         rnn_in = input_size
         self.has_cnn = bool(cnn_layers)
         if self.has_cnn:
@@ -76,14 +77,14 @@ class RefAcousticModel(nn.Module):
                 rnn_in = (rnn_in + 2 * padding[1] - kernel[1]) // stride[1] + 1
             self.conv = nn.Sequential(OrderedDict(blocks))
             rnn_in *= cout
-        blocks = [("0", _RnnBlock(rnn_in, hidden, False, dropout))]
+        blocks = [("0", _RnnBlock(rnn_in, hidden, False, dropout, bidirectional))]
         for l in range(1, layers):
-            blocks.append((str(l), _RnnBlock(2 * hidden, hidden, batch_norm, dropout)))
+            blocks.append((str(l), _RnnBlock(D * hidden, hidden, batch_norm, dropout, bidirectional)))
         self.rnns = nn.Sequential(OrderedDict(blocks))
         if batch_norm:
-            self.fc = nn.Sequential(nn.BatchNorm1d(2 * hidden), nn.Linear(2 * hidden, num_class, bias=False))
+            self.fc = nn.Sequential(nn.BatchNorm1d(D * hidden), nn.Linear(D * hidden, num_class, bias=False))
         else:
-            self.fc = nn.Linear(2 * hidden, num_class, bias=False)
+            self.fc = nn.Linear(D * hidden, num_class, bias=False)
 
     def forward(self, x):  # x [N, T, F]
         if self.has_cnn:

@@ -669,6 +669,48 @@ def test_packed_model_vs_oracle_x3(T, N, H, L):
     assert worst < 1e-3, worst
 
 
+@pytest.mark.parametrize("precision,drop", [("x3", 0.0), ("bf16", 0.0), ("x3", 0.2)])
+def test_unidirectional_model_vs_oracle(precision, drop):
+    """rnn_param["bidirectional"] = False (model_ctc.py:88, train_ctc.py:96): forward-only LSTM layers, H-wide layer outputs."""
+    from ctc_pytorch_b200.model import CTC_Model
+    from ctc_pytorch_b200.loss import CTCLoss
+    T, N, F, H, L, C = 20, 9, 40, 256, 3, 14
+    torch.manual_seed(21)
+    rnn_param = {"rnn_input_size": F, "rnn_hidden_size": H, "rnn_layers": L, "rnn_type": nn.LSTM, "bidirectional": False,
+                 "batch_norm": True}
+    m = CTC_Model(rnn_param=rnn_param, num_class=C, drop_out=drop)
+    ref = model_ref.RefAcousticModel(F, H, L, C, batch_norm=True, dropout=drop, bidirectional=False)
+    assert list(m.state_dict().keys()) == list(ref.state_dict().keys())
+    ref.load_state_dict(m.state_dict())
+    m = m.to(DEV)
+    m.precision = precision
+    masks = []
+    gen = torch.Generator().manual_seed(5)
+
+    def source(shape, p_, dev):
+        k = (torch.rand(shape, generator=gen) >= p_).to(torch.uint8)
+        masks.append(k)
+        return k
+    m.mask_source = source
+    x, frac, tg, tl = model_ref.synthetic_batch(T, N, F, C, 5, 8)
+    il = (frac * T).long()
+    m.train(); ref.train()
+    out = m(x.to(DEV))
+    assert out.shape == (T, N, C)
+    loss = CTCLoss(reduction="sum")(out, tg.to(DEV), il.to(DEV), tl.to(DEV)) / N
+    loss.backward()
+    for blk, k in zip(ref.rnns.children(), masks):
+        blk.fixed_mask = k
+    rloss = nn.CTCLoss(reduction="sum")(ref(x), tg, il, tl) / N
+    rloss.backward()
+    tol_l, tol_g = (2e-3, 3e-2) if precision == "bf16" else (1e-4, 1e-3)
+    assert abs(loss.item() - rloss.item()) < tol_l * abs(rloss.item())
+    rp = dict(ref.named_parameters())
+    worst = max(relnorm(p.grad, rp[k].grad) for k, p in m.named_parameters())
+    _report("unidirectional_vs_oracle", dict(precision=precision, drop=drop, grad_rel_l2_worst=worst))
+    assert worst < tol_g, worst
+
+
 def test_dropout_training_mode_runs():
     from ctc_pytorch_b200.model import CTC_Model
     torch.manual_seed(0)
