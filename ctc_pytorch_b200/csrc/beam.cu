@@ -24,6 +24,7 @@
 // length, 64-bit prefix hash) are double-buffered in shared memory, prefix equality for the merge is
 // found through a shared-memory hash table and then verified exactly on the stored label sequences.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ctcb200.h"
@@ -72,6 +73,7 @@ struct BeamParams {
     int* out_labels;          // [N, T]
     int* out_len;             // [N]
     int* status;              // [N]
+    long long* trace;         // debug (CTCB200_BEAM_TRACE=1): per-phase cycle totals of block 0, or null
 };
 
 __device__ void bitonic_sort(double* key, int* pos, int n2) {
@@ -140,12 +142,20 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
     __syncthreads();
     bool have_pool = false;  // candidates of an earlier frame are waiting to be ranked
     int pool_n = 0;
+    // phase timing (block 0, thread 0): [0] sort, [1] beam records + sequence copies, [2] frame setup + hash table,
+    // [3] extensions, [4] stays / merge, [5] frames processed
+    long long tr[6] = {0, 0, 0, 0, 0, 0};
+    const bool tracing = p.trace != nullptr && n == 0 && tid == 0;
+#define BTICK(var) long long var = tracing ? clock64() : 0
 
     // Rank the waiting candidates and turn the best W into the current beam records (+ their label sequences).
     auto select_beams = [&]() {
         for (int i = pool_n + tid; i < P2; i += blockDim.x) { skey[i] = -INFINITY; spos[i] = 0x7fffffff; }
         __syncthreads();
+        BTICK(t_s0);
         bitonic_sort(skey, spos, P2);
+        BTICK(t_s1);
+        tr[0] += t_s1 - t_s0;
         int live = 0;
         // number of live entries among the first W (dead ones carry -inf and sort last)
         if (tid == 0) {
@@ -184,6 +194,8 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
         cur ^= 1;
         if (tid == 0) s_flags[2] = frames_done + 1;
         __syncthreads();
+        BTICK(t_s2);
+        tr[1] += t_s2 - t_s1;
     };
 
     for (int t = 0; t < len_n; ++t) {
@@ -191,6 +203,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
         __syncthreads();
         if ((1.0f - prow[blank]) < 0.1f) { __syncthreads(); continue; }  // near-certain blank: frame skipped
         if (have_pool) select_beams();
+        BTICK(t_f0);
         const int nbeams = s_flags[0];
         const BeamRec b = rec(cur);
         const int* seq_cur = seq_base + static_cast<size_t>(s_flags[2] & 1) * W * T;
@@ -215,6 +228,8 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
         const int tprev = (t - 1 + T) % T;
         const bool prev_blank_lt = probs_n[static_cast<size_t>(tprev) * C + blank] < 0.9f;
         pool_n = nbeams * C;
+        BTICK(t_f1);
+        tr[2] += t_f1 - t_f0;
         // pass 1: extensions
         for (int pos = tid; pos < pool_n; pos += blockDim.x) {
             const int i = pos / C, slot = pos - i * C;
@@ -249,6 +264,8 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
             }
         }
         __syncthreads();
+        BTICK(t_f2);
+        tr[3] += t_f2 - t_f1;
         // pass 2: stays (and the merge with a coinciding extension)
         for (int r = tid; r < nbeams; r += blockDim.x) {
             double nb = LOG_ZERO;
@@ -275,8 +292,13 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
         }
         have_pool = true;
         __syncthreads();
+        BTICK(t_f3);
+        tr[4] += t_f3 - t_f2;
+        tr[5] += 1;
         if (s_flags[1]) break;
     }
+    if (tracing)
+        for (int i = 0; i < 6; ++i) p.trace[i] = tr[i];
 
     int status = s_flags[1];
     if (status == 0) {
@@ -386,7 +408,23 @@ extern "C" CTCB200_API int ctcb200_beam_search(const float* probs_ntc, const int
     p.pool_label = reinterpret_cast<int*>(w); w += sizeof(int) * N * PC;
     p.seq = reinterpret_cast<int*>(w);
     p.out_labels = out_labels; p.out_len = out_lengths; p.status = status;
+    p.trace = nullptr;
+    static long long* dtrace = nullptr;
+    if (getenv("CTCB200_BEAM_TRACE")) {   // development aid: phase breakdown of utterance 0 on stderr
+        if (!dtrace) CTCB_CUDA(cudaMalloc(&dtrace, 6 * sizeof(long long)));
+        CTCB_CUDA(cudaMemsetAsync(dtrace, 0, 6 * sizeof(long long), stream));
+        p.trace = dtrace;
+    }
     beam_search_kernel<<<N, BEAM_THREADS, smem, stream>>>(p);
     CTCB_LAUNCH_CHECK();
+    if (p.trace) {
+        long long h[6];
+        CTCB_CUDA(cudaStreamSynchronize(stream));
+        CTCB_CUDA(cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost));
+        const double f = h[5] > 0 ? static_cast<double>(h[5]) : 1.0;
+        fprintf(stderr, "beam_search trace (utterance 0, %lld unskipped frames, cycles per frame): sort %.0f, beam records + sequence "
+                "copies %.0f, frame setup + hash table %.0f, extensions %.0f, stays/merge %.0f\n", h[5], h[0] / f, h[1] / f, h[2] / f,
+                h[3] / f, h[4] / f);
+    }
     return OK;
 }

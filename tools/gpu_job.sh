@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box visit = everything worth measuring (queueing for a box costs far more than running): the -m gpu suite, the
+# microbenchmarks and one bench line. Outputs under gpurun_out/ (merged back by gpurun).
+#   gpurun --timeout 1800 -- 'bash tools/gpu_job.sh [tests|bench|all]'
+what=${1:-all}
+mkdir -p gpurun_out
+if [ "$what" = "tests" ] || [ "$what" = "all" ]; then
+  rm -f gpurun_out/parity_report.jsonl
+  python -m pytest tests -m gpu -q -x -k "not test_full_shape_golden" > gpurun_out/tests_main.log 2>&1; echo "tests_main rc=$?"
+  tail -15 gpurun_out/tests_main.log
+  python -m pytest tests -m gpu -q -k "test_full_shape_golden" > gpurun_out/tests_full.log 2>&1; echo "tests_full rc=$?"
+  tail -25 gpurun_out/tests_full.log
+fi
+if [ "$what" = "bench" ] || [ "$what" = "all" ]; then
+  tools/dsmem_bench.bin > gpurun_out/dsmem_bench.jsonl 2> gpurun_out/dsmem_bench.err; echo "dsmem rc=$?"; tail -3 gpurun_out/dsmem_bench.jsonl
+  python tools/ctc_sweep_bench.py gpurun_out/ctc_sweep.json > gpurun_out/ctc_sweep.log 2>&1; echo "ctc_sweep rc=$?"; tail -2 gpurun_out/ctc_sweep.log
+  CTCB200_BEAM_TRACE=1 python tools/decode_bench.py 100 1 gpurun_out/decode.json > gpurun_out/decode.log 2>&1; echo "decode rc=$?"; tail -4 gpurun_out/decode.log
+  python bench.py --steps 10 --warmup 3 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; echo "bench rc=$?"; head -c 1500 gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err
+fi
