@@ -115,6 +115,11 @@ def make_batch(cfg, seed, lo=0, hi=None):
     return tuple(t[lo:hi].contiguous() for t in (x, frac, tg, tl))
 
 
+def rnn_param(cfg):
+    """rnn_param dict of a CONFIGS entry (helper for the scripts under tools/)."""
+    return synth.model_kwargs(cfg)["rnn_param"]
+
+
 def workload_name(name, cfg, per_gpu):
     return "%s: T=%d N=%d/GPU feat=%d C=%d %s%dxBiLSTM-%d+BN" % (
         name, cfg["T"], per_gpu, cfg["F"], cfg["C"], "2xConv2d+" if cfg.get("cnn") else "", cfg["L"], cfg["H"])

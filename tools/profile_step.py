@@ -1,18 +1,20 @@
-"""One cfg2 training step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off)."""
+"""One training step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off).
+usage: python tools/profile_step.py [cfg2|cfg3|cfg4] [T] [bf16|x3]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn as nn
 import bench
 from ctc_pytorch_b200.model import CTC_Model
 from ctc_pytorch_b200.loss import CTCLoss
-from ctc_pytorch_b200 import ops
+from ctc_pytorch_b200 import ops, synth
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 cfg = dict(bench.CFG[name])
 if len(sys.argv) > 2: cfg["T"] = int(sys.argv[2])
 dev = "cuda"
 torch.manual_seed(0)
-m = CTC_Model(rnn_param=bench.rnn_param(cfg), num_class=cfg["C"], drop_out=0.0).to(dev)
+m = CTC_Model(**synth.model_kwargs(cfg)).to(dev)
+m.precision = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0.005, fused=True)
 x, frac, tg, tl = (t.to(dev) for t in bench.make_batch(cfg, 1))
 lossf = CTCLoss(reduction="sum"); m.train()
