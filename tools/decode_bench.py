@@ -1,5 +1,6 @@
-"""cfg5: greedy and LM beam decode throughput at the TIMIT shape (T=800, N=32, C=62), next to the oracle's CPU restatement
-of the reference's decoders (timit/utils/ctcDecoder.py:152-192, BeamSearch.py:73-153) on a bounded sample.
+"""cfg5: greedy and LM beam decode throughput at the TIMIT shape (T=800, N=32, C=62), next to the UNMODIFIED reference's
+decoders (timit/utils/ctcDecoder.py:152-192, BeamSearch.py:73-153) timed on a bounded sample of the same batch; beam strings are
+checked against the full-size golden fixture (all 32 utterances).
 
 usage: python tools/decode_bench.py [beam_width=100] [cpu_utts=1] [out.json]
 """
@@ -15,24 +16,25 @@ import torch
 
 from ctc_pytorch_b200 import ops
 from ctc_pytorch_b200.decoder import BeamDecoder, GreedyDecoder
-from oracle import decode_ref
 
 beam_width = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 cpu_utts = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 out_path = sys.argv[3] if len(sys.argv) > 3 else None
 T, N, C = 800, 32, 62
-alpha = 0.01
 dev = "cuda"
 units = ["blank", "UNK"] + ["p%02d" % i for i in range(60)]
 int2char = dict(enumerate(units))
 arpa = os.path.join(ROOT, "tests", "golden", "lm_c62.arpa")
 
-g = torch.Generator().manual_seed(0)
-logits = 3.0 * torch.randn(T, N, C, generator=g)
-logits[:, :, 0] += 2.0                                  # log_softmax(3 N(0,1) + 2 e_blank)
-log_probs = torch.log_softmax(logits, -1)               # [T, N, C] on the host, as test_ctc.py:85 hands it over
-lens = [int(round(T * u)) for u in np.linspace(1.0, 0.6, N)]
-unskipped = int(sum(((1.0 - log_probs[:l, n, 0].exp()) >= 0.1).sum() for n, l in enumerate(lens)))
+# the posteriors of the full-size golden fixture (tests/golden/beam_full.json: strings of the UNMODIFIED reference's search for all
+# 32 utterances at width 100, lm_alpha 0.1), built from integer arithmetic so the float32 bits are the same on every machine
+from ctc_pytorch_b200 import synth
+fixture = json.load(open(os.path.join(ROOT, "tests", "golden", "beam_full.json")))
+alpha = fixture["cfg"]["lm_alpha"]
+probs_np = synth.exact_probs(N, T, C, fixture["cfg"]["seed"])
+lens = fixture["lens"]
+log_probs = torch.from_numpy(probs_np).log().transpose(0, 1).contiguous()   # [T, N, C] on the host, as test_ctc.py:85 hands it over
+unskipped = int(sum(((1.0 - probs_np[n, :l, 0]) >= np.float32(0.1)).sum() for n, l in enumerate(lens)))
 
 res = {"shape": {"T": T, "N": N, "C": C, "beam_width": beam_width, "lm_alpha": alpha, "frames": int(sum(lens)),
                  "unskipped_frames": unskipped}}
@@ -72,21 +74,31 @@ res["gpu"] = {"greedy_utt_s": N / t_g, "greedy_e2e_utt_s": N / t_g_e2e, "beam_ut
               "beam_search_call_ms": t_b_dev * 1e3, "beam_candidates_per_s": cands / t_b_dev,
               "greedy_ms": t_g * 1e3, "beam_ms": t_b * 1e3}
 
-# CPU: the oracle's restatement of the reference decoders (pure Python, one thread like the reference) on `cpu_utts`
-lm = decode_ref.BigramLM(arpa)
-probs = log_probs.exp().transpose(0, 1).contiguous().numpy()
-t0 = time.perf_counter()
-want_g = decode_ref.greedy_strings(log_probs.numpy(), lens, int2char)
-t_cg = time.perf_counter() - t0
-t0 = time.perf_counter()
-want_b, want_bs = decode_ref.beam_search(probs[:cpu_utts], lens[:cpu_utts], units, beam_width, lm, alpha)
-t_cb = time.perf_counter() - t0
-res["cpu"] = {"kind": "port", "cores": 1, "greedy_utt_s": N / t_cg, "beam_utt_s": cpu_utts / t_cb,
-              "sample": "greedy: all %d utterances; beam: first %d utterance(s) (%d frames)" % (N, cpu_utts, sum(lens[:cpu_utts]))}
-res["parity"] = {"greedy_strings_identical": gs == want_g, "beam_strings_identical_on_sample": bs[:cpu_utts] == want_bs}
-res["speedup"] = {"greedy": res["gpu"]["greedy_utt_s"] / res["cpu"]["greedy_utt_s"],
-                  "beam": res["gpu"]["beam_utt_s"] / res["cpu"]["beam_utt_s"]}
+# kernel-level parity on ALL utterances: the same float32 probabilities the golden run of the unmodified reference consumed
+labels = ops.beam_search(torch.from_numpy(probs_np).to(dev), lens, tab, beam_width, alpha, 0, input_is_log=False)
+kernel_strings = [" ".join(units[l] for l in seq) for seq in labels]
+res["parity"] = {"beam_strings_identical_to_reference_all_%d" % N: (kernel_strings == fixture["strings"]) if beam_width == fixture["cfg"]["beam_width"] else None}
+
+# CPU: the UNMODIFIED reference decoders (pure Python, one thread) on `cpu_utts` utterances, via oracle/ref_shim.py
+from oracle import ref_shim
+if cpu_utts > 0 and ref_shim.available():
+    ref = ref_shim.load()
+    rg = ref.GreedyDecoder(int2char, space_idx=-1, blank_index=0)
+    t0 = time.perf_counter()
+    want_g = rg.decode(log_probs, lens)
+    t_cg = time.perf_counter() - t0
+    rb = ref.BeamDecoder(int2char, beam_width=beam_width, blank_index=0, space_idx=-1, lm_path=arpa, lm_alpha=alpha)
+    t0 = time.perf_counter()
+    want_bs = rb._decoder.decode(torch.from_numpy(probs_np[:cpu_utts]), lens[:cpu_utts])
+    t_cb = time.perf_counter() - t0
+    res["cpu"] = {"kind": "reference", "cores": 1, "greedy_utt_s": N / t_cg, "beam_utt_s": cpu_utts / t_cb,
+                  "sample": "greedy: all %d utterances; beam: first %d utterance(s) (%d frames); unmodified ctcDecoder.py / BeamSearch.py"
+                            % (N, cpu_utts, sum(lens[:cpu_utts]))}
+    res["parity"]["greedy_strings_identical"] = gs == want_g
+    res["parity"]["beam_strings_identical_on_cpu_sample"] = kernel_strings[:cpu_utts] == want_bs
+    res["speedup"] = {"greedy": res["gpu"]["greedy_utt_s"] / res["cpu"]["greedy_utt_s"],
+                      "beam": res["gpu"]["beam_utt_s"] / res["cpu"]["beam_utt_s"]}
 print(json.dumps(res))
 if out_path:
     json.dump(res, open(out_path, "w"), indent=1)
-assert res["parity"]["greedy_strings_identical"] and res["parity"]["beam_strings_identical_on_sample"]
+assert all(v is not False for v in res["parity"].values()), res["parity"]

@@ -17,3 +17,19 @@ if [ "$what" = "bench" ] || [ "$what" = "all" ]; then
   CTCB200_BEAM_TRACE=1 python tools/decode_bench.py 100 1 gpurun_out/decode.json > gpurun_out/decode.log 2>&1; echo "decode rc=$?"; tail -4 gpurun_out/decode.log
   python bench.py --steps 10 --warmup 3 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; echo "bench rc=$?"; head -c 1500 gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err
 fi
+if [ "$what" = "sanitize" ]; then
+  for tool in memcheck synccheck; do
+    timeout 900 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_${tool}.log python tools/sanitize_target.py all > gpurun_out/sanitizer_${tool}.out 2>&1
+    echo "$tool rc=$?"; tail -3 gpurun_out/sanitizer_${tool}.log
+  done
+  timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/sanitizer_racecheck.log python tools/sanitize_target.py decode > gpurun_out/sanitizer_racecheck.out 2>&1
+  echo "racecheck(decode) rc=$?"; tail -3 gpurun_out/sanitizer_racecheck.log
+  timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/sanitizer_racecheck_model.log python tools/sanitize_target.py model > gpurun_out/sanitizer_racecheck_model.out 2>&1
+  echo "racecheck(model) rc=$?"; tail -3 gpurun_out/sanitizer_racecheck_model.log
+fi
+if [ "$what" = "ncu" ]; then
+  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_r2.csv python tools/profile_step.py cfg2 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:lstm_ -c 6 -o gpurun_out/prof_lstm_r2 -f python tools/profile_step.py cfg2 > gpurun_out/ncu_lstm.log 2>&1; echo "ncu lstm rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:beam_search -c 1 -o gpurun_out/prof_beam_r2 -f python tools/decode_bench.py 100 0 > gpurun_out/ncu_beam.log 2>&1; echo "ncu beam rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:"argmax_rows|collapse|conv2d" -c 8 --profile-from-start off -o gpurun_out/prof_misc_r2 -f python tools/profile_step.py cfg3 > gpurun_out/ncu_misc.log 2>&1; echo "ncu misc rc=$?"
+fi
