@@ -128,3 +128,62 @@ def test_grad_bucket_detects_severed_views():
     model(torch.randn(4, 3)).sum().backward()
     with pytest.raises(RuntimeError, match="attach"):
         bucket.allreduce_mean()
+
+
+def _model_sync_worker(rank, world, port, out):
+    """CTC_Model.backward with grad_sync set (per-layer buckets reduced from inside the backward pass), on the CPU emulation of
+    the C ABI over gloo: the host logic of SURVEY.md §8(e) end to end."""
+    from ctc_pytorch_b200.dist import GradSync
+    from ctc_pytorch_b200.model import CTC_Model
+    from ctc_pytorch_b200 import synth
+    from tests.emu_lib import emulated
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    T, N, F, H, L, C = 10, 6, 40, 128, 2, 8
+    torch.manual_seed(11)
+    rnn_param = {"rnn_input_size": F, "rnn_hidden_size": H, "rnn_layers": L, "rnn_type": nn.LSTM, "bidirectional": True,
+                 "batch_norm": True}
+    m = CTC_Model(rnn_param=rnn_param, num_class=C, drop_out=0.0)
+    m.precision, m.overlap_wgrad = "x3", False
+    x, frac, tg, tl = synth.synthetic_batch(T, N, F, C, 3, 2)
+    lo, hi = shard_range(N, rank, world)
+    m.grad_sync = GradSync(weight=(hi - lo) * world / float(N))
+    m.train()
+    with emulated():
+        o = m(x[lo:hi])
+        il = (frac[lo:hi] * T).long()
+        (nn.CTCLoss(reduction="sum")(o, tg[lo:hi], il, tl[lo:hi]) / (hi - lo)).backward()
+    assert m.grad_sync.bytes == 4 * sum(p.numel() for p in m.parameters())   # L + 1 buckets covered every parameter
+    if rank == 0:
+        torch.save({k: p.grad.clone() for k, p in m.named_parameters()}, out)
+    dist.destroy_process_group()
+
+
+def test_model_backward_with_grad_sync_equals_mean_of_shard_oracle_gradients(tmp_path):
+    from ctc_pytorch_b200 import synth
+    from oracle import model_ref
+    world = 2
+    out = str(tmp_path / "model_sync.pt")
+    mp.spawn(_model_sync_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = torch.load(out)
+    T, N, F, H, L, C = 10, 6, 40, 128, 2, 8
+    torch.manual_seed(11)
+    ref = model_ref.RefAcousticModel(F, H, L, C, batch_norm=True)
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    x, frac, tg, tl = synth.synthetic_batch(T, N, F, C, 3, 2)
+    want = {k: torch.zeros_like(p) for k, p in ref.named_parameters()}
+    ref.train()
+    for r in range(world):
+        lo, hi = shard_range(N, r, world)
+        ref.load_state_dict(sd0)
+        ref.zero_grad()
+        o = ref(x[lo:hi])
+        il = (frac[lo:hi] * T).long()
+        (nn.CTCLoss(reduction="sum")(o, tg[lo:hi], il, tl[lo:hi]) / (hi - lo)).backward()
+        for k, p in ref.named_parameters():
+            want[k] += p.grad * ((hi - lo) / float(N))
+    for k in want:
+        e = float((got[k].double() - want[k].double()).norm() / (want[k].double().norm() + 1e-30))
+        assert e < 2e-4, (k, e)
