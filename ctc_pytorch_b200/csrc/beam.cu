@@ -20,7 +20,7 @@
 // 3 = KeyError (unit pair missing from the LM).
 //
 // Device mapping: candidates (beam x class) are spread over the 1024 threads of the block, the candidate
-// keys live in shared memory and are ranked by an in-place bitonic sort, beam records (scores, last label,
+// keys live in shared memory; the best W are picked by a radix select + a small bitonic sort (select_top), beam records (scores, last label,
 // length, 64-bit prefix hash) are double-buffered in shared memory, prefix equality for the merge is
 // found through a shared-memory hash table and then verified exactly on the stored label sequences.
 #include <cfloat>
@@ -64,7 +64,7 @@ struct BeamParams {
     const int64_t* lengths;   // [N]
     const double* lm;         // [(C+1), (C+1)]
     double lm_alpha;
-    int T, N, C, W, blank, P2;  // P2 = power of two >= W*C (sort capacity)
+    int T, N, C, W, blank, P2;  // P2 = candidate capacity >= W*C
     double* pool_nb;          // [N, W*C]
     double* pool_bl;          // [N, W*C]
     int* pool_parent;         // [N, W*C]
@@ -94,6 +94,121 @@ __device__ void bitonic_sort(double* key, int* pos, int n2) {
     }
 }
 
+// Order-preserving map double -> uint64 (larger value = larger integer); -0.0 counts as +0.0 like the == of the reference's sort
+__device__ __forceinline__ unsigned long long key_bits(double k) {
+    if (k == 0.0) k = 0.0;
+    const long long b = __double_as_longlong(k);
+    const unsigned long long u = static_cast<unsigned long long>(b);
+    return (b < 0) ? ~u : (u | 0x8000000000000000ULL);
+}
+
+constexpr int TOP_MAX = 256;   // beam widths up to 256 (BeamDecoder's default is 200)
+
+// The next beam is the first W entries of a stable descending sort of ALL candidates (BeamSearch.py:29-33,96): only those W
+// are needed, so instead of sorting the whole pool (8192 keys: 91 compare-exchange stages, 88 % of the kernel's time in
+// round 1's profile) the W-th largest key is found by an 8-pass radix select over the 64-bit key images, the entries above
+// it plus the first (lowest-position) ties at it are compacted into a 256-entry buffer, and only that buffer is sorted by
+// (key descending, position ascending). Candidates sit at their own position in skey before the selection (spos[i] == i), so
+// "position" is the array index. Result: skey[0 .. want), spos[0 .. want) exactly as the full sort would have left them.
+__device__ void select_top(double* skey, int* spos, int n, int want, double* okey, int* opos, int* hist, int* sscan) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+    if (want > n) want = n;
+    if (want <= 0) return;
+    const int ept = (n + nthreads - 1) / nthreads;
+    const int lo = tid * ept, hi = min(n, lo + ept);
+    unsigned long long prefix = 0ULL;
+    int remaining = want;
+#pragma unroll 1
+    for (int pass = 7; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        const unsigned long long mask_above = (pass == 7) ? 0ULL : (~0ULL << (shift + 8));
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int j = 0; j < ept; ++j) {     // uniform trip count: the warp-wide match below needs every lane present
+            const int i = lo + j;
+            int d = -1;
+            if (i < hi) {
+                const unsigned long long u = key_bits(skey[i]);
+                if ((u & mask_above) == prefix) d = static_cast<int>((u >> shift) & 255ULL);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (d >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[d], __popc(peers));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int loc[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { loc[b] = hist[lane * 8 + b]; sum += loc[b]; }
+            // count in the lanes above this one (higher digits)
+            int above = 0, x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_down_sync(0xffffffffu, x, o);
+                if (lane + o < 32) x += y;
+            }
+            above = x - sum;   // x = inclusive suffix sum
+            if (above < remaining && remaining <= above + sum) {
+                int run = above;
+#pragma unroll
+                for (int b = 7; b >= 0; --b) {
+                    if (run < remaining && remaining <= run + loc[b]) { sscan[0] = lane * 8 + b; sscan[1] = run; }
+                    run += loc[b];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= static_cast<unsigned long long>(sscan[0]) << shift;
+        remaining -= sscan[1];
+        __syncthreads();
+    }
+    const unsigned long long kth = prefix;   // the want-th largest key; `remaining` entries equal to it are taken, lowest positions first
+    int cg = 0, ce = 0;
+    for (int i = lo; i < hi; ++i) {
+        const unsigned long long u = key_bits(skey[i]);
+        cg += u > kth;
+        ce += u == kth;
+    }
+    // block-wide exclusive scan of (cg, ce) packed into one int (both < 2^15)
+    int packed = cg | (ce << 16), inc = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) sscan[2 + warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = nthreads >> 5;
+        int v = lane < nw ? sscan[2 + lane] : 0, w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        sscan[2 + lane] = w - v;   // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const int excl = inc - packed + sscan[2 + warp];
+    int bg = excl & 0xffff, be = excl >> 16;
+    const int n_gt = want - remaining;
+    for (int i = lo; i < hi; ++i) {
+        const double k = skey[i];
+        const unsigned long long u = key_bits(k);
+        if (u > kth) { okey[bg] = k; opos[bg] = i; ++bg; }
+        else if (u == kth) {
+            if (be < remaining) { okey[n_gt + be] = k; opos[n_gt + be] = i; }
+            ++be;
+        }
+    }
+    int wp = 1;
+    while (wp < want) wp <<= 1;
+    for (int i = want + tid; i < wp; i += nthreads) { okey[i] = -INFINITY; opos[i] = 0x7fffffff; }
+    __syncthreads();
+    bitonic_sort(okey, opos, wp);
+    for (int i = tid; i < wp; i += nthreads) { skey[i] = okey[i]; spos[i] = opos[i]; }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams p) {
     extern __shared__ uint8_t smem_raw[];
     const int n = blockIdx.x, tid = threadIdx.x;
@@ -113,6 +228,8 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
     int* merged_with = ht_val + HT;                  // W
     float* prow = reinterpret_cast<float*>(merged_with + W);  // C
     __shared__ int s_flags[4];                       // [0] nbeams, [1] status, [2] processed frames, [3] skip
+    __shared__ double s_okey[TOP_MAX];               // selection buffer of select_top
+    __shared__ int s_opos[TOP_MAX], s_hist[256], s_scan[40];
 
     auto rec = [&](int b) {
         BeamRec r;
@@ -150,10 +267,9 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
 
     // Rank the waiting candidates and turn the best W into the current beam records (+ their label sequences).
     auto select_beams = [&]() {
-        for (int i = pool_n + tid; i < P2; i += blockDim.x) { skey[i] = -INFINITY; spos[i] = 0x7fffffff; }
         __syncthreads();
         BTICK(t_s0);
-        bitonic_sort(skey, spos, P2);
+        select_top(skey, spos, pool_n, W, s_okey, s_opos, s_hist, s_scan);
         BTICK(t_s1);
         tr[0] += t_s1 - t_s0;
         int live = 0;
@@ -357,7 +473,7 @@ size_t beam_smem_bytes(int W, int C, int P2) {
     b += sizeof(unsigned long long) * (4 * static_cast<size_t>(W) + HT);
     b += sizeof(int) * (static_cast<size_t>(P2) + 4 * W + HT + W);
     b += sizeof(float) * C;
-    return b + 16;
+    return b + 16;   // + static shared memory of the kernel (selection buffers, ~4.2 KB)
 }
 
 }  // namespace
@@ -390,9 +506,9 @@ extern "C" CTCB200_API int ctcb200_beam_search(const float* probs_ntc, const int
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0 && C > 1 && beam_width > 0, "beam_search: bad shape T=%d N=%d C=%d W=%d", T, N, C, beam_width);
     CTCB_REQUIRE(blank >= 0 && blank < C, "beam_search: blank %d out of range", blank);
+    CTCB_REQUIRE(beam_width <= TOP_MAX, "beam_search: beam width %d exceeds the supported maximum %d", beam_width, TOP_MAX);
     CTCB_REQUIRE(lm_table != nullptr, "beam_search: a bigram LM table is required (the reference cannot run without one)");
-    int P2 = 1;
-    while (P2 < beam_width * C) P2 <<= 1;
+    const int P2 = ((beam_width * C + 31) / 32) * 32;   // candidate capacity (no power-of-two padding: only the top W are sorted)
     const size_t smem = beam_smem_bytes(beam_width, C, P2);
     CTCB_REQUIRE(smem <= 227 * 1024, "beam_search: beam_width*classes = %d needs %zu B of shared memory (max 227 KB)",
                  beam_width * C, smem);

@@ -830,8 +830,11 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
         const int tprev = dir ? tt + 1 : tt - 1;       // time index that held c_{prev} in the forward scan
         const bool has_prev = dir ? (tt + 1 < T) : (tt >= 1);
         // (1) saved activations and the incoming gradient for this thread's elements
+        // NOTHING loaded here may be touched before phase (6): these loads are issued ahead of the MMA chain so that their
+        // latency hides behind it (a conversion at the load site would stall the issuing warps on the load every step)
         float dh_in[EPT], bx_in[EPT], c_t[EPT], c_p[EPT];
-        float4 gts[EPT];
+        float4 gts32[X3 ? EPT : 1];
+        uint2 gts16[X3 ? 1 : EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int gn = p.n0 + grp * NB + warp + 8 * e;
@@ -840,13 +843,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
             dh_in[e] = ok ? __ldg(p.dhout + o) : 0.0f;
             bx_in[e] = (p.bn_x != nullptr && ok) ? __ldg(p.bn_x + o) : 0.0f;   // combined with dh_in where it is consumed
             c_t[e] = ok ? __ldg(p.c_save + o) : 0.0f;
-            if constexpr (X3) {
-                gts[e] = ok ? __ldg(p.gates_save32 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                const uint2 g2 = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
-                const __half2 lo = *reinterpret_cast<const __half2*>(&g2.x), hi = *reinterpret_cast<const __half2*>(&g2.y);
-                gts[e] = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
-            }
+            if constexpr (X3) gts32[e] = ok ? __ldg(p.gates_save32 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else gts16[e] = ok ? __ldg(p.gates_save + o) : make_uint2(0u, 0u);
             const size_t op = (static_cast<size_t>(has_prev ? tprev : tt) * N + (ok ? gn : 0)) * H2 +
                               static_cast<size_t>(dir) * H + unit;
             c_p[e] = (ok && has_prev) ? __ldg(p.c_save + op) : 0.0f;
@@ -955,7 +953,13 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 if constexpr (BULK && !X3) dh += __half2float(reinterpret_cast<const __half*>(sR)[(s * NB + n) * 32 + lane]);
                 else dh += sR[(s * NB + n) * 32 + lane];
             }
-            const float gi = gts[e].x, gf = gts[e].y, gg = gts[e].z, go = gts[e].w;
+            float gi, gf, gg, go;
+            if constexpr (X3) {
+                gi = gts32[e].x; gf = gts32[e].y; gg = gts32[e].z; go = gts32[e].w;
+            } else {
+                const __half2 glo = *reinterpret_cast<const __half2*>(&gts16[e].x), ghi = *reinterpret_cast<const __half2*>(&gts16[e].y);
+                gi = __low2float(glo); gf = __high2float(glo); gg = __low2float(ghi); go = __high2float(ghi);
+            }
             const float tc = fast_tanh(c_t[e]);
             const float d_o = dh * tc * go * (1.0f - go);
             const float dc = dc_carry[e] + dh * go * (1.0f - tc * tc);

@@ -2,6 +2,7 @@
 oracle/ref_shim.py), at the shapes BASELINE.json names. Slow (minutes of CPU), so separate from make_golden.py:
 
     python -m oracle.make_golden_full model cfg2|cfg3|cfg4      # one training step of the reference's CTC_Model + nn.CTCLoss
+    python -m oracle.make_golden_full model64 cfg2|cfg3|cfg4    # the same step with the reference model in float64
     python -m oracle.make_golden_full beam <part> <nparts>      # reference ctcBeamSearch, beam 100 + bigram LM, T=800, N=32
     python -m oracle.make_golden_full beam_merge <nparts>
     python -m oracle.make_golden_full beam_edges                # width 200 and the 0.9 / 0.1 threshold rows
@@ -78,6 +79,43 @@ def gen_model(name):
     with open(os.path.join(OUT, "full_%s.json" % name), "w") as fh:
         json.dump(meta, fh, indent=1)
     print("%s: wer (%d, %d); written" % (name, errs, toks))
+
+
+def gen_model_f64(name):
+    """The same step with the reference model switched to float64 (`model.double()`, nothing else changed): the yardstick for
+    the float32 numbers above. At T=800 x 4 layers the reference's OWN float32 run deviates from this by ~1e-3 in the
+    recurrent-weight gradients (stored here as `f32_vs_f64/<param>`), i.e. north_star's 1e-3 is the noise floor of the
+    reference's arithmetic itself; the x3 mode of the CUDA path is asserted against these float64 values."""
+    ref = ref_shim.load()
+    cfg = synth.CONFIGS[name]
+    seed = FULL_SEED[name]
+    meta = json.load(open(os.path.join(OUT, "full_%s.json" % name)))
+    g32 = np.load(os.path.join(OUT, "full_%s.npz" % name))
+    torch.manual_seed(seed)
+    model = ref.CTC_Model(**synth.model_kwargs(cfg))
+    x, frac, targets, tl = synth.synthetic_batch(cfg["T"], cfg["N"], cfg["F"], cfg["C"], cfg["S"], seed)
+    model = model.double()
+    model.train()
+    t0 = time.time()
+    out = model(x.double())
+    il = (frac * out.shape[0]).long()
+    nll = nn.functional.ctc_loss(out, targets, il, tl, blank=0, reduction="none")
+    loss = nn.CTCLoss(reduction="sum")(out, targets, il, tl) / cfg["N"]
+    loss.backward()
+    print("%s: float64 reference step %.1f s, loss %.9f" % (name, time.time() - t0, float(loss.detach())), flush=True)
+    payload = dict(loss=float(loss.detach()), nll=nll.detach().numpy(), out_sample=out.detach()[torch.from_numpy(g32["out_rows"])].numpy())
+    noise = {}
+    for k, p in model.named_parameters():
+        step = meta["grad_step"][k]
+        v64 = p.grad.reshape(-1)[::step][:256]
+        payload["gradvals/" + k] = v64.numpy()
+        payload["gradnorm/" + k] = np.float64(p.grad.norm())
+        v32 = torch.from_numpy(g32["gradvals/" + k]).double()
+        noise[k] = float((v32 - v64).norm() / (v64.norm() + 1e-300))
+        payload["f32_vs_f64/" + k] = np.float64(noise[k])
+    np.savez_compressed(os.path.join(OUT, "full_%s_f64.npz" % name), **payload)
+    worst = max((v, k) for k, v in noise.items() if not k.endswith("conv.bias"))
+    print("%s: the reference's own float32 run vs float64: worst gradient rel-L2 %.2e (%s)" % (name, worst[0], worst[1]))
 
 
 def _beam_decoder(ref, width, alpha, arpa):
@@ -192,6 +230,8 @@ def main():
     torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", "4")))
     if what == "model":
         gen_model(sys.argv[2])
+    elif what == "model64":
+        gen_model_f64(sys.argv[2])
     elif what == "beam":
         gen_beam_part(int(sys.argv[2]), int(sys.argv[3]))
     elif what == "beam_merge":

@@ -33,3 +33,7 @@ if [ "$what" = "ncu" ]; then
   ncu --set full --clock-control none --import-source on -k regex:beam_search -c 1 -o gpurun_out/prof_beam_r2 -f python tools/decode_bench.py 100 0 > gpurun_out/ncu_beam.log 2>&1; echo "ncu beam rc=$?"
   ncu --set full --clock-control none --import-source on -k regex:"argmax_rows|collapse|conv2d" -c 8 --profile-from-start off -o gpurun_out/prof_misc_r2 -f python tools/profile_step.py cfg3 > gpurun_out/ncu_misc.log 2>&1; echo "ncu misc rc=$?"
 fi
+if [ "$what" = "ab" ] || [ "$what" = "all" ]; then
+  python tools/lstm_ab.py 800 32 512 > gpurun_out/lstm_ab_cfg2.json 2> gpurun_out/lstm_ab.err; echo "lstm_ab rc=$?"; cat gpurun_out/lstm_ab_cfg2.json; tail -3 gpurun_out/lstm_ab.err
+  python tools/lstm_ab.py 1200 64 640 > gpurun_out/lstm_ab_cfg4.json 2>> gpurun_out/lstm_ab.err; echo "lstm_ab cfg4 rc=$?"; cat gpurun_out/lstm_ab_cfg4.json
+fi
