@@ -37,3 +37,10 @@ if [ "$what" = "ab" ] || [ "$what" = "all" ]; then
   python tools/lstm_ab.py 800 32 512 > gpurun_out/lstm_ab_cfg2.json 2> gpurun_out/lstm_ab.err; echo "lstm_ab rc=$?"; cat gpurun_out/lstm_ab_cfg2.json; tail -3 gpurun_out/lstm_ab.err
   python tools/lstm_ab.py 1200 64 640 > gpurun_out/lstm_ab_cfg4.json 2>> gpurun_out/lstm_ab.err; echo "lstm_ab cfg4 rc=$?"; cat gpurun_out/lstm_ab_cfg4.json
 fi
+if [ "$what" = "dist" ]; then
+  # run with: gpurun --gpus G -- 'bash tools/gpu_job.sh dist'
+  G=$(python -c "import torch; print(torch.cuda.device_count())")
+  python -m pytest tests/test_gpu_dist.py -m gpu -q > gpurun_out/tests_dist.log 2>&1; echo "tests_dist rc=$?"; tail -5 gpurun_out/tests_dist.log
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $G --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_weak_g$G.json 2> gpurun_out/bench_weak_g$G.err; echo "bench weak G=$G rc=$?"; head -c 600 gpurun_out/bench_weak_g$G.json; tail -3 gpurun_out/bench_weak_g$G.err
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $G --steps 6 --warmup 3 --scaling strong --no-cpu-baseline --both-precisions 0 > gpurun_out/bench_strong_g$G.json 2> gpurun_out/bench_strong_g$G.err; echo "bench strong G=$G rc=$?"; head -c 600 gpurun_out/bench_strong_g$G.json; tail -3 gpurun_out/bench_strong_g$G.err
+fi

@@ -42,8 +42,37 @@ def report(rep, out):
                     if h == w or (h.startswith(w) and h[len(w):len(w) + 1] in ("", ".")):
                         f.write("   %-70s %s %s\n" % (h, r[ix[h]], units[ix[h]]))
 
+def traffic(rep, config, out_json):
+    """dram bytes (read + write) per launch of the recurrent kernels -> profiles/ncu_traffic.json (bench.py's roofline.traffic)"""
+    import json
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = collections.defaultdict(list)
+    for r in rows[2:]:
+        name = r[ix["Kernel Name"]]
+        key = "lstm_bwd_kernel" if "lstm_bwd" in name else ("lstm_fwd_kernel" if "lstm_fwd" in name else None)
+        if key is None:
+            continue
+        rd = float(r[ix["dram__bytes_read.sum"]].replace(",", "")) * scale.get(units[ix["dram__bytes_read.sum"]], 1.0)
+        wr = float(r[ix["dram__bytes_write.sum"]].replace(",", "")) * scale.get(units[ix["dram__bytes_write.sum"]], 1.0)
+        acc[key].append(rd + wr)
+    d = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    d.setdefault(config, {})
+    for key, v in acc.items():
+        d[config][key] = {"dram_bytes": sum(v) / len(v), "launches": len(v),
+                          "source": "profiles/%s.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
+                                    % os.path.basename(rep).replace(".ncu-rep", "")}
+    json.dump(d, open(out_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
     g = "gpurun_out"
-    if os.path.exists(g + "/launches_r1.csv"): launches(g + "/launches_r1.csv", "profiles/launches_r1.txt")
-    for nm in ("prof_lstm_r1", "prof_gemm_ctc_r1"):
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    if os.path.exists("%s/launches_%s.csv" % (g, tag)): launches("%s/launches_%s.csv" % (g, tag), "profiles/launches_%s.txt" % tag)
+    for nm in ("prof_lstm_%s" % tag, "prof_gemm_ctc_%s" % tag, "prof_beam_%s" % tag, "prof_misc_%s" % tag):
         if os.path.exists("%s/%s.ncu-rep" % (g, nm)): report("%s/%s.ncu-rep" % (g, nm), "profiles/%s.txt" % nm)
+    if os.path.exists("%s/prof_lstm_%s.ncu-rep" % (g, tag)):
+        traffic("%s/prof_lstm_%s.ncu-rep" % (g, tag), "cfg2", "profiles/ncu_traffic.json")
