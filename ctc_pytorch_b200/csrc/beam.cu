@@ -124,15 +124,21 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
         const unsigned long long mask_above = (pass == 7) ? 0ULL : (~0ULL << (shift + 8));
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
-        for (int j = 0; j < ept; ++j) {     // uniform trip count: the warp-wide match below needs every lane present
+        for (int j = 0; j < ept; ++j) {     // uniform trip count: the warp-wide vote below needs every lane present
             const int i = lo + j;
             int d = -1;
             if (i < hi) {
                 const unsigned long long u = key_bits(skey[i]);
                 if ((u & mask_above) == prefix) d = static_cast<int>((u >> shift) & 255ULL);
             }
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            if (d >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[d], __popc(peers));
+            // the high bytes of scores of similar magnitude coincide across the whole warp: one atomic for 32 lanes then;
+            // otherwise plain shared-memory atomics (few lanes still match the prefix in the later passes)
+            const int d0 = __shfl_sync(0xffffffffu, d, 0);
+            if (__all_sync(0xffffffffu, d == d0)) {
+                if (lane == 0 && d0 >= 0) atomicAdd(&hist[d0], 32);
+            } else if (d >= 0) {
+                atomicAdd(&hist[d], 1);
+            }
         }
         __syncthreads();
         if (warp == 0) {
