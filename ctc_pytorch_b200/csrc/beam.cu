@@ -111,19 +111,21 @@ constexpr int TOP_MAX = 256;   // beam widths up to 256 (BeamDecoder's default i
 // (key descending, position ascending). Candidates sit at their own position in skey before the selection (spos[i] == i), so
 // "position" is the array index. Result: skey[0 .. want), spos[0 .. want) exactly as the full sort would have left them.
 __device__ void select_top(double* skey, int* spos, int n, int want, double* okey, int* opos, int* hist, int* sscan) {
+    // hist: [8 passes][256 bins], zeroed here once; sscan: 2 + 32 + 2 ints
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     if (want > n) want = n;
     if (want <= 0) return;
     const int ept = (n + nthreads - 1) / nthreads;
     const int lo = tid * ept, hi = min(n, lo + ept);
+    for (int i = tid; i < 8 * 256; i += nthreads) hist[i] = 0;
     unsigned long long prefix = 0ULL;
     int remaining = want;
+    __syncthreads();
 #pragma unroll 1
     for (int pass = 7; pass >= 0; --pass) {
         const int shift = pass * 8;
         const unsigned long long mask_above = (pass == 7) ? 0ULL : (~0ULL << (shift + 8));
-        if (tid < 256) hist[tid] = 0;
-        __syncthreads();
+        int* h = hist + pass * 256;
         for (int j = 0; j < ept; ++j) {     // uniform trip count: the warp-wide vote below needs every lane present
             const int i = lo + j;
             int d = -1;
@@ -135,37 +137,38 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
             // otherwise plain shared-memory atomics (few lanes still match the prefix in the later passes)
             const int d0 = __shfl_sync(0xffffffffu, d, 0);
             if (__all_sync(0xffffffffu, d == d0)) {
-                if (lane == 0 && d0 >= 0) atomicAdd(&hist[d0], 32);
+                if (lane == 0 && d0 >= 0) atomicAdd(&h[d0], 32);
             } else if (d >= 0) {
-                atomicAdd(&hist[d], 1);
+                atomicAdd(&h[d], 1);
             }
         }
         __syncthreads();
-        if (warp == 0) {
-            int loc[8], sum = 0;
+        // EVERY warp finds the digit itself (256 bins, 8 per lane, one shuffle scan): no second barrier for a broadcast
+        int loc[8], sum = 0;
 #pragma unroll
-            for (int b = 0; b < 8; ++b) { loc[b] = hist[lane * 8 + b]; sum += loc[b]; }
-            // count in the lanes above this one (higher digits)
-            int above = 0, x = sum;
+        for (int b = 0; b < 8; ++b) { loc[b] = h[lane * 8 + b]; sum += loc[b]; }
+        int x = sum;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_down_sync(0xffffffffu, x, o);
-                if (lane + o < 32) x += y;
-            }
-            above = x - sum;   // x = inclusive suffix sum
-            if (above < remaining && remaining <= above + sum) {
-                int run = above;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_down_sync(0xffffffffu, x, o);
+            if (lane + o < 32) x += y;
+        }
+        const int above = x - sum;   // entries whose digit lies in a higher lane's bins
+        int digit = -1, gt = 0;
+        if (above < remaining && remaining <= above + sum) {
+            int run = above;
 #pragma unroll
-                for (int b = 7; b >= 0; --b) {
-                    if (run < remaining && remaining <= run + loc[b]) { sscan[0] = lane * 8 + b; sscan[1] = run; }
-                    run += loc[b];
-                }
+            for (int b = 7; b >= 0; --b) {
+                if (run < remaining && remaining <= run + loc[b]) { digit = lane * 8 + b; gt = run; }
+                run += loc[b];
             }
         }
-        __syncthreads();
-        prefix |= static_cast<unsigned long long>(sscan[0]) << shift;
-        remaining -= sscan[1];
-        __syncthreads();
+        const unsigned owner = __ballot_sync(0xffffffffu, digit >= 0);   // exactly one lane holds the bin
+        const int src = __ffs(owner) - 1;
+        digit = __shfl_sync(0xffffffffu, digit, src);
+        gt = __shfl_sync(0xffffffffu, gt, src);
+        prefix |= static_cast<unsigned long long>(digit) << shift;
+        remaining -= gt;
     }
     const unsigned long long kth = prefix;   // the want-th largest key; `remaining` entries equal to it are taken, lowest positions first
     int cg = 0, ce = 0;
@@ -183,18 +186,14 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
     }
     if (lane == 31) sscan[2 + warp] = inc;
     __syncthreads();
-    if (warp == 0) {
-        const int nw = nthreads >> 5;
-        int v = lane < nw ? sscan[2 + lane] : 0, w = v;
+    int wtot = lane < (nthreads >> 5) ? sscan[2 + lane] : 0, wsum = wtot;    // every warp scans the 32 warp totals itself
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += y;
-        }
-        sscan[2 + lane] = w - v;   // exclusive prefix of the warp totals
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, wsum, o);
+        if (lane >= o) wsum += y;
     }
-    __syncthreads();
-    const int excl = inc - packed + sscan[2 + warp];
+    const int warp_excl = __shfl_sync(0xffffffffu, wsum - wtot, warp);
+    const int excl = inc - packed + warp_excl;
     int bg = excl & 0xffff, be = excl >> 16;
     const int n_gt = want - remaining;
     for (int i = lo; i < hi; ++i) {
@@ -210,7 +209,28 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
     while (wp < want) wp <<= 1;
     for (int i = want + tid; i < wp; i += nthreads) { okey[i] = -INFINITY; opos[i] = 0x7fffffff; }
     __syncthreads();
-    bitonic_sort(okey, opos, wp);
+    // sort the <= 256 selected entries by (key descending, position ascending): one thread per pair, the first wp/2 threads
+    // only (<= 4 warps), synchronised with a named barrier instead of the whole block
+    const int half = wp >> 1;
+    const int team = half > 32 ? half : 32;     // whole warps take part in the barriers; threads >= half carry no pair
+    if (tid < team) {
+        for (int k = 2; k <= wp; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (tid < half) {
+                    const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));   // index with bit j clear
+                    const int ixj = i | j;
+                    const double ka = okey[i], kb = okey[ixj];
+                    const int pa = opos[i], pb = opos[ixj];
+                    const bool up = (i & k) == 0;
+                    const bool swap = up ? before(kb, pb, ka, pa) : before(ka, pa, kb, pb);
+                    if (swap) { okey[i] = kb; okey[ixj] = ka; opos[i] = pb; opos[ixj] = pa; }
+                }
+                if (team > 32) named_bar_sync(1, team);
+                else __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
     for (int i = tid; i < wp; i += nthreads) { skey[i] = okey[i]; spos[i] = opos[i]; }
     __syncthreads();
 }
@@ -235,7 +255,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
     float* prow = reinterpret_cast<float*>(merged_with + W);  // C
     __shared__ int s_flags[4];                       // [0] nbeams, [1] status, [2] processed frames, [3] skip
     __shared__ double s_okey[TOP_MAX];               // selection buffer of select_top
-    __shared__ int s_opos[TOP_MAX], s_hist[256], s_scan[40];
+    __shared__ int s_opos[TOP_MAX], s_hist[8 * 256], s_scan[40];
 
     auto rec = [&](int b) {
         BeamRec r;

@@ -39,7 +39,9 @@ __global__ void pack_lstm_weights_kernel(const float* __restrict__ wih_f, const 
                                          const float* __restrict__ wih_r, const float* __restrict__ whh_r,
                                          __nv_bfloat16* __restrict__ wih_p, __nv_bfloat16* __restrict__ wihT_p,
                                          __nv_bfloat16* __restrict__ whh_p, __nv_bfloat16* __restrict__ whhT_p, int H,
-                                         int I, int Ipad, int part) {
+                                         int I, int Ipad, int part, int gates) {
+    // gates = rows / H of the torch weights: 4 (LSTM: i,f,g,o), 3 (GRU: r,z,n), 1 (vanilla RNN); the operand layouts always
+    // have four gate slots per unit, slots >= gates are zero
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const int G4 = 4 * H, G8 = 8 * H;
@@ -48,28 +50,28 @@ __global__ void pack_lstm_weights_kernel(const float* __restrict__ wih_f, const 
         const int R = static_cast<int>(e / Ipad), i = static_cast<int>(e % Ipad);
         const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
         const float* w = dir ? wih_r : wih_f;
-        wih_p[e] = bf16_part(i < I ? w[static_cast<size_t>(orow) * I + i] : 0.0f, part);
+        wih_p[e] = bf16_part((i < I && orow < gates * H) ? w[static_cast<size_t>(orow) * I + i] : 0.0f, part);
     }
     // wihT_p [I, 8H]
     for (long long e = tid; e < static_cast<long long>(I) * G8; e += stride) {
         const int i = static_cast<int>(e / G8), R = static_cast<int>(e % G8);
         const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
         const float* w = dir ? wih_r : wih_f;
-        wihT_p[e] = bf16_part(w[static_cast<size_t>(orow) * I + i], part);
+        wihT_p[e] = bf16_part(orow < gates * H ? w[static_cast<size_t>(orow) * I + i] : 0.0f, part);
     }
     // whh_p [8H, H]
     for (long long e = tid; e < static_cast<long long>(G8) * H; e += stride) {
         const int R = static_cast<int>(e / H), k = static_cast<int>(e % H);
         const int dir = R / G4, orow = packed_to_orig_row(R % G4, H);
         const float* w = dir ? whh_r : whh_f;
-        whh_p[e] = bf16_part(w[static_cast<size_t>(orow) * H + k], part);
+        whh_p[e] = bf16_part(orow < gates * H ? w[static_cast<size_t>(orow) * H + k] : 0.0f, part);
     }
     // whhT_p [(dir,q,m), k] = whh_dir[q*H + k][m]
     for (long long e = tid; e < static_cast<long long>(G8) * H; e += stride) {
         const int R = static_cast<int>(e / H), k = static_cast<int>(e % H);
         const int dir = R / G4, q = (R % G4) / H, m = R % H;
         const float* w = dir ? whh_r : whh_f;
-        whhT_p[e] = bf16_part(w[(static_cast<size_t>(q) * H + k) * H + m], part);
+        whhT_p[e] = bf16_part(q < gates ? w[(static_cast<size_t>(q) * H + k) * H + m] : 0.0f, part);
     }
 }
 
@@ -538,14 +540,15 @@ using namespace ctcb200;
 
 extern "C" CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const float* whh_f, const float* wih_r,
                                                      const float* whh_r, void* wih_p, void* wihT_p, void* whh_p,
-                                                     void* whhT_p, int H, int I, int Ipad, int part,
+                                                     void* whhT_p, int H, int I, int Ipad, int part, int gates,
                                                      ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(H % 32 == 0 && I > 0 && Ipad >= I && Ipad % 8 == 0, "pack_lstm_weights: bad sizes H=%d I=%d Ipad=%d", H, I, Ipad);
+    CTCB_REQUIRE(gates == 4 || gates == 3 || gates == 1, "pack_lstm_weights: gates %d not in {4 LSTM, 3 GRU, 1 RNN}", gates);
     const long long work = static_cast<long long>(8) * H * (Ipad > H ? Ipad : H);
     pack_lstm_weights_kernel<<<stream_grid(work, 1024), 256, 0, stream>>>(
         wih_f, whh_f, wih_r, whh_r, static_cast<__nv_bfloat16*>(wih_p), static_cast<__nv_bfloat16*>(wihT_p),
-        static_cast<__nv_bfloat16*>(whh_p), static_cast<__nv_bfloat16*>(whhT_p), H, I, Ipad, part);
+        static_cast<__nv_bfloat16*>(whh_p), static_cast<__nv_bfloat16*>(whhT_p), H, I, Ipad, part, gates);
     CTCB_LAUNCH_CHECK();
     return OK;
 }

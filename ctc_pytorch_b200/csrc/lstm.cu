@@ -175,6 +175,12 @@ __device__ __forceinline__ void load_partial_sums(uint32_t taddr, int acc_stride
         }
     }
 }
+// Cell type of a recurrent layer (train_ctc.py:20 supported_rnn = nn.LSTM / nn.GRU / nn.RNN). All cells use the SAME operand
+// layout — four gate slots per hidden unit, 128 gate rows per CTA — so that packing, the input-projection GEMM, the exchange
+// and the weight-gradient GEMMs are shared: LSTM fills the slots with (i, f, g, o), GRU with (r, z, n, -), the vanilla RNN with
+// (g, -, -, -); unused slots carry zero weights (some idle tensor-core work for a configuration option, no extra code paths).
+enum { CELL_LSTM = 0, CELL_GRU = 1, CELL_RNN = 2 };
+
 struct FwdParams {
     const float* gx;          // [T*N, 8H] gate pre-activations from the input projection (packed column order)
     float* hout;              // [T*N, 2H] layer output (fwd | reverse)
@@ -188,6 +194,7 @@ struct FwdParams {
     const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (hi part): source of the TMEM-resident A operand
     int mma_split;            // number of warps (1, 2 or 4) that issue slices of the K chain into their own accumulator
     int act_approx;           // 1: gate non-linearities through tanh.approx (one MUFU op each)
+    int rnn_relu;             // CELL_RNN: 1 = nonlinearity='relu', 0 = 'tanh'
 };
 
 // Split a float into bf16 hi + bf16 lo (hi + lo carries 16 mantissa bits of the value).
@@ -204,7 +211,7 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 //           is accumulated as W_hi h_hi + W_hi h_lo + W_lo h_hi in the fp32 TMEM accumulator (the dropped W_lo h_lo term is
 //           2^-18 relative). W_hi stays resident in TMEM, W_lo in shared memory (TMA-loaded once, SWIZZLE_128B); every
 //           32-unit block of the operand image carries [hi | lo], so the exchange is still one copy per peer.
-template <int NB, int EX, bool X3>
+template <int NB, int EX, bool X3, int CELL = CELL_LSTM>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
     constexpr bool CL = EX != 0, BULK = EX == 3;
@@ -372,13 +379,29 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
         tc_fence_before();
         TRACE(4); TRACE(9);
         // (6) gate non-linearity, then regroup the four gates of a unit through shared memory
+        if constexpr (CELL == CELL_LSTM) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const float pre = __uint_as_float(acc[c]) + gx[c];
-            float a;
-            if (p.act_approx) a = act_h * tanh_approx(act_h * pre) + (1.0f - act_h);   // sigmoid(x) = (tanh(x/2) + 1) / 2
-            else a = act_s * fast_sigmoid(act_s * pre) - (act_s - 1.0f);              // sigmoid, or tanh for gate g
-            sS[u_loc * S_STRIDE + (ch * CPT + c) * 4 + q] = a;
+            for (int c = 0; c < CPT; ++c) {
+                const float pre = __uint_as_float(acc[c]) + gx[c];
+                float a;
+                if (p.act_approx) a = act_h * tanh_approx(act_h * pre) + (1.0f - act_h);   // sigmoid(x) = (tanh(x/2) + 1) / 2
+                else a = act_s * fast_sigmoid(act_s * pre) - (act_s - 1.0f);              // sigmoid, or tanh for gate g
+                sS[u_loc * S_STRIDE + (ch * CPT + c) * 4 + q] = a;
+            }
+        } else if constexpr (CELL == CELL_GRU) {
+            // slots (r, z, n, -): r, z = sigmoid(W_h. h + gx); the n gate needs r first, so its recurrent part W_hn h and its
+            // input part gx_n travel separately (slot 2 and the unused slot 3) to the thread that finishes the unit
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const float rec = __uint_as_float(acc[c]);
+                float* dst = sS + u_loc * S_STRIDE + (ch * CPT + c) * 4;
+                if (q < 2) dst[q] = fast_sigmoid(rec + gx[c]);
+                else if (q == 2) { dst[2] = rec; dst[3] = gx[c]; }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+                if (q == 0) sS[u_loc * S_STRIDE + (ch * CPT + c) * 4] = __uint_as_float(acc[c]) + gx[c];
         }
         TRACE(10);
         if constexpr (BULK) { if (warp_leader) bulk_wait_read_all(); }  // last step's copies have finished reading sOut
@@ -390,10 +413,23 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int n = warp + 8 * e;
-            const float4 g4 = *reinterpret_cast<const float4*>(&sS[lane * S_STRIDE + n * 4]);
-            const float cn = g4.y * c_state[e] + g4.x * g4.z;
-            c_state[e] = cn;
-            const float h = g4.w * (p.act_approx ? tanh_approx(cn) : fast_tanh(cn));
+            float4 g4 = *reinterpret_cast<const float4*>(&sS[lane * S_STRIDE + n * 4]);
+            float h;
+            if constexpr (CELL == CELL_LSTM) {
+                const float cn = g4.y * c_state[e] + g4.x * g4.z;
+                c_state[e] = cn;
+                h = g4.w * (p.act_approx ? tanh_approx(cn) : fast_tanh(cn));
+            } else if constexpr (CELL == CELL_GRU) {
+                // n = tanh(gx_n + r (W_hn h)), h' = (1 - z) n + z h  (torch's GRU, bias-free); saved slots: (r, z, n, W_hn h)
+                const float nn_ = fast_tanh(g4.w + g4.x * g4.z);
+                h = (1.0f - g4.y) * nn_ + g4.y * c_state[e];
+                c_state[e] = h;                       // the recurrent state is h itself; c_save then holds h_t for BPTT
+                g4 = make_float4(g4.x, g4.y, nn_, g4.z);
+            } else {
+                h = p.rnn_relu ? fmaxf(g4.x, 0.0f) : fast_tanh(g4.x);
+                c_state[e] = h;
+                g4 = make_float4(h, 0.0f, 0.0f, 0.0f);
+            }
             hv[e] = h;
             gv[e] = g4;
             __nv_bfloat16 h_hi, h_lo;
@@ -686,6 +722,9 @@ struct BwdParams {
     const float4* gates_save32;  // split-operand mode: 4 x fp32 instead
     __nv_bfloat16* dg;         // [T*N, 8H] gate gradients, packed column order (A operand of the dX GEMM); hi part in X3 mode
     __nv_bfloat16* dg_lo;      // X3: the lo part of the same
+    __nv_bfloat16* dg_rec;     // GRU: gate gradients as the RECURRENT weights see them (n slot = dn_pre * r), for dW_hh; hi part
+    __nv_bfloat16* dg_rec_lo;  // GRU + X3: lo part
+    int rnn_relu;              // CELL_RNN: 1 = relu, 0 = tanh
     __nv_bfloat16* dgimg;      // EX = 0: [2 dirs][groups][4 gates][2][H*NB*PARTS] operand images
     unsigned int* flags;       // EX = 0: [2 dirs][groups]
     int T, N, H, groups, n0;
@@ -729,7 +768,7 @@ __device__ __forceinline__ void announce_resident(unsigned int* resident) {
 //         copies with complete_tx on the receiver's mbarrier (partials as fp16, or fp32 in X3 mode).
 // EX = 0: cluster of the 4 gate CTAs only; dG images + release/acquire counter in global memory (any H).
 // X3    : split-operand mode as in the forward kernel: W^T = hi (TMEM) + lo (shared memory), dG = hi + lo blocks.
-template <int NB, int EX, bool X3>
+template <int NB, int EX, bool X3, int CELL = CELL_LSTM>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
     constexpr bool CL = EX != 0, BULK = EX == 3;
@@ -944,6 +983,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
         }
         // (6) finish 32 units: recurrent dh, LSTM cell backward, publish the four gate gradients
         uint2 dgp[EPT], dgl[EPT];
+        uint2 dgr[CELL == CELL_GRU ? EPT : 1], dgrl[CELL == CELL_GRU ? EPT : 1];   // GRU: input-side gate gradients (see below)
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int n = warp + 8 * e;
@@ -960,13 +1000,42 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 const __half2 glo = *reinterpret_cast<const __half2*>(&gts16[e].x), ghi = *reinterpret_cast<const __half2*>(&gts16[e].y);
                 gi = __low2float(glo); gf = __high2float(glo); gg = __low2float(ghi); go = __high2float(ghi);
             }
-            const float tc = fast_tanh(c_t[e]);
-            const float d_o = dh * tc * go * (1.0f - go);
-            const float dc = dc_carry[e] + dh * go * (1.0f - tc * tc);
-            const float d_i = dc * gg * gi * (1.0f - gi);
-            const float d_f = dc * c_p[e] * gf * (1.0f - gf);
-            const float d_g = dc * gi * (1.0f - gg * gg);
-            dc_carry[e] = dc * gf;
+            float d_i, d_f, d_g, d_o;     // the four slots handed to the next BPTT step (what W_hh^T multiplies)
+            if constexpr (CELL == CELL_LSTM) {
+                const float tc = fast_tanh(c_t[e]);
+                d_o = dh * tc * go * (1.0f - go);
+                const float dc = dc_carry[e] + dh * go * (1.0f - tc * tc);
+                d_i = dc * gg * gi * (1.0f - gi);
+                d_f = dc * c_p[e] * gf * (1.0f - gf);
+                d_g = dc * gi * (1.0f - gg * gg);
+                dc_carry[e] = dc * gf;
+            } else if constexpr (CELL == CELL_GRU) {
+                // saved slots (r, z, n, hn = W_hn h_prev); c_p = h_prev. h' = (1 - z) n + z h_prev, n = tanh(gx_n + r hn)
+                dh += dc_carry[e];                             // the direct path h' -> h_prev of the step before
+                const float dn_pre = dh * (1.0f - gf) * (1.0f - gg * gg);
+                d_i = dn_pre * go * gi * (1.0f - gi);          // r gate
+                d_f = dh * (c_p[e] - gg) * gf * (1.0f - gf);   // z gate
+                d_g = dn_pre * gi;                             // what reaches W_hn: dn_pre * r
+                d_o = 0.0f;
+                dc_carry[e] = dh * gf;
+                // the INPUT weights see dn_pre itself in the n slot: second set of rows for dX / dW_ih
+                __nv_bfloat16 ih[4], il[4];
+                split_bf16(d_i, ih[0], il[0]);
+                split_bf16(d_f, ih[1], il[1]);
+                split_bf16(dn_pre, ih[2], il[2]);
+                ih[3] = il[3] = __float2bfloat16(0.0f);
+                __nv_bfloat162 a01, a23;
+                a01.x = ih[0]; a01.y = ih[1]; a23.x = ih[2]; a23.y = ih[3];
+                dgr[e] = make_uint2(*reinterpret_cast<uint32_t*>(&a01), *reinterpret_cast<uint32_t*>(&a23));
+                if constexpr (X3) {
+                    a01.x = il[0]; a01.y = il[1]; a23.x = il[2]; a23.y = il[3];
+                    dgrl[e] = make_uint2(*reinterpret_cast<uint32_t*>(&a01), *reinterpret_cast<uint32_t*>(&a23));
+                }
+            } else {
+                // saved slot 0 = h_t; h' = tanh(pre) or relu(pre)
+                d_i = p.rnn_relu ? (gi > 0.0f ? dh : 0.0f) : dh * (1.0f - gi * gi);
+                d_f = d_g = d_o = 0.0f;
+            }
             __nv_bfloat16 hi4[4], lo4[4];
             split_bf16(d_i, hi4[0], lo4[0]);
             split_bf16(d_f, hi4[1], lo4[1]);
@@ -1033,8 +1102,19 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
         for (int e = 0; e < EPT; ++e) {
             const int gn = p.n0 + grp * NB + warp + 8 * e;
             if (gn < N) {
-                *reinterpret_cast<uint2*>(p.dg + (static_cast<size_t>(tt) * N + gn) * G8 + dg_col) = dgp[e];
-                if constexpr (X3) *reinterpret_cast<uint2*>(p.dg_lo + (static_cast<size_t>(tt) * N + gn) * G8 + dg_col) = dgl[e];
+                const size_t go_ = (static_cast<size_t>(tt) * N + gn) * G8 + dg_col;
+                if constexpr (CELL == CELL_GRU) {
+                    // dg = what the input weights see (dX, dW_ih), dg_rec = what the recurrent weights see (dW_hh)
+                    *reinterpret_cast<uint2*>(p.dg + go_) = dgr[e];
+                    *reinterpret_cast<uint2*>(p.dg_rec + go_) = dgp[e];
+                    if constexpr (X3) {
+                        *reinterpret_cast<uint2*>(p.dg_lo + go_) = dgrl[e];
+                        *reinterpret_cast<uint2*>(p.dg_rec_lo + go_) = dgl[e];
+                    }
+                } else {
+                    *reinterpret_cast<uint2*>(p.dg + go_) = dgp[e];
+                    if constexpr (X3) *reinterpret_cast<uint2*>(p.dg_lo + go_) = dgl[e];
+                }
             }
         }
     }
@@ -1563,12 +1643,28 @@ bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads = L
 
 using FwdKern = void (*)(CUtensorMap, FwdParams);
 using BwdKern = void (*)(CUtensorMap, BwdParams);
-FwdKern fwd_kernel(int NB, int ex, bool x3) {
+FwdKern fwd_kernel(int NB, int ex, bool x3, int cell = CELL_LSTM) {
+    if (cell == CELL_GRU) {
+        if (x3) return ex == 3 ? lstm_fwd_kernel<16, 3, true, CELL_GRU> : lstm_fwd_kernel<16, 0, true, CELL_GRU>;
+        return ex == 3 ? lstm_fwd_kernel<16, 3, false, CELL_GRU> : lstm_fwd_kernel<16, 0, false, CELL_GRU>;
+    }
+    if (cell == CELL_RNN) {
+        if (x3) return ex == 3 ? lstm_fwd_kernel<16, 3, true, CELL_RNN> : lstm_fwd_kernel<16, 0, true, CELL_RNN>;
+        return ex == 3 ? lstm_fwd_kernel<16, 3, false, CELL_RNN> : lstm_fwd_kernel<16, 0, false, CELL_RNN>;
+    }
     if (x3) return ex == 3 ? lstm_fwd_kernel<16, 3, true> : lstm_fwd_kernel<16, 0, true>;
     if (NB == 16) return ex == 3 ? lstm_fwd_kernel<16, 3, false> : lstm_fwd_kernel<16, 0, false>;
     return ex == 3 ? lstm_fwd_kernel<32, 3, false> : lstm_fwd_kernel<32, 0, false>;
 }
-BwdKern bwd_kernel(int NB, int ex, bool x3) {
+BwdKern bwd_kernel(int NB, int ex, bool x3, int cell = CELL_LSTM) {
+    if (cell == CELL_GRU) {
+        if (x3) return ex == 3 ? lstm_bwd_kernel<16, 3, true, CELL_GRU> : lstm_bwd_kernel<16, 0, true, CELL_GRU>;
+        return ex == 3 ? lstm_bwd_kernel<16, 3, false, CELL_GRU> : lstm_bwd_kernel<16, 0, false, CELL_GRU>;
+    }
+    if (cell == CELL_RNN) {
+        if (x3) return ex == 3 ? lstm_bwd_kernel<16, 3, true, CELL_RNN> : lstm_bwd_kernel<16, 0, true, CELL_RNN>;
+        return ex == 3 ? lstm_bwd_kernel<16, 3, false, CELL_RNN> : lstm_bwd_kernel<16, 0, false, CELL_RNN>;
+    }
     if (x3) return ex == 3 ? lstm_bwd_kernel<16, 3, true> : lstm_bwd_kernel<16, 0, true>;
     if (NB == 16) return ex == 3 ? lstm_bwd_kernel<16, 3, false> : lstm_bwd_kernel<16, 0, false>;
     return ex == 3 ? lstm_bwd_kernel<32, 3, false> : lstm_bwd_kernel<32, 0, false>;
@@ -1688,19 +1784,22 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd_ctas(int N, int H, int batch_tile) {
 
 extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
                                             float* c_save, void* gates_save, void* scratch, int T, int N, int H,
-                                            int batch_tile, ctcb200_stream_t stream_) {
+                                            int batch_tile, int cell, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool x3 = whh_lo_packed != nullptr;
+    CTCB_REQUIRE(cell >= 0 && cell <= 3, "lstm_fwd: cell %d not in {0 LSTM, 1 GRU, 2 RNN tanh, 3 RNN relu}", cell);
+    const int cell_k = cell == 0 ? CELL_LSTM : (cell == 1 ? CELL_GRU : CELL_RNN);
+    const bool plain = cell_k == CELL_LSTM;   // the pipelined / two-tile fast paths exist for the LSTM cell only
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_fwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_fwd: hidden size %d must be a multiple of 128 in [128,640]", H);
     FwdParams p;
     p.gx = gx; p.hout = hout; p.c_save = c_save;
     p.gates_save = x3 ? nullptr : static_cast<uint2*>(gates_save);
     p.gates_save32 = x3 ? static_cast<float4*>(gates_save) : nullptr;
-    p.himg = nullptr; p.flags = nullptr; p.trace = nullptr; p.act_approx = 0;
+    p.himg = nullptr; p.flags = nullptr; p.trace = nullptr; p.act_approx = 0; p.rnn_relu = cell == 3 ? 1 : 0;
     p.w = static_cast<const __nv_bfloat16*>(whh_packed);
     p.T = T; p.N = N; p.H = H; p.n0 = 0;
-    if (!x3 && two_tile_path(H)) {
+    if (!x3 && plain && two_tile_path(H)) {
         // H > 512: 64 units per CTA (tile 0 in TMEM, tile 1 in shared memory), H/64 CTAs per cluster, NB = 16
         constexpr int NB2 = 16;
         const int groups2 = (N + NB2 - 1) / NB2;
@@ -1717,13 +1816,13 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     }
     int ex = exchange_mode(H);
     {   // fall back to the global-memory exchange when a cluster of this size cannot be scheduled on this device
-        const int nb_try = x3 ? 16 : pick_nb(N, H, batch_tile, false, ex != 0);
-        if (ex != 0 && !cluster_ok(fwd_kernel(nb_try, ex, x3), dim3(H / 32, 2, (N + nb_try - 1) / nb_try), dim3(H / 32, 1, 1),
+        const int nb_try = (x3 || !plain) ? 16 : pick_nb(N, H, batch_tile, false, ex != 0);
+        if (ex != 0 && !cluster_ok(fwd_kernel(nb_try, ex, x3, cell_k), dim3(H / 32, 2, (N + nb_try - 1) / nb_try), dim3(H / 32, 1, 1),
                                    lstm_smem_bytes(nb_try, H, false, ex, x3)))
             ex = 0;
     }
     const bool cl = ex != 0;
-    const int NB = x3 ? 16 : pick_nb(N, H, batch_tile, false, cl);
+    const int NB = (x3 || !plain) ? 16 : pick_nb(N, H, batch_tile, false, cl);
     const int groups_total = (N + NB - 1) / NB;
     CUtensorMap tmW;   // only read by the split-operand kernels (W_lo slice -> shared memory)
     int rc = make_tmap_bf16_2d(&tmW, x3 ? whh_lo_packed : whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
@@ -1732,7 +1831,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
     {
         const char* act = getenv("CTCB200_LSTM_ACT");
-        p.act_approx = (!x3 && act != nullptr && act[0] == 'a') ? 1 : 0;
+        p.act_approx = (!x3 && plain && act != nullptr && act[0] == 'a') ? 1 : 0;
     }
     p.mma_split = mma_issuers(NB, H);
     p.groups = groups_total;
@@ -1745,7 +1844,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         }
     }
     FwdTraceDump trace_dump{p, stream, false};
-    if (cl && !x3 && NB == 16 && pipelined_fwd()) {
+    if (cl && !x3 && plain && NB == 16 && pipelined_fwd()) {
         trace_dump.pipe = true;
         // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core warps
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
@@ -1758,7 +1857,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     if (cl) {
         // independent clusters: no co-residency requirement between them, one launch covers every batch group
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
-        return launch_clustered(fwd_kernel(NB, ex, x3), grid, cluster, smem, false, tmW, p, stream);
+        return launch_clustered(fwd_kernel(NB, ex, x3, cell_k), grid, cluster, smem, false, tmW, p, stream);
     }
     const int per_group = 2 * (H / 32);
     const int sms = device_sm_count();
@@ -1774,19 +1873,25 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         p.himg = reinterpret_cast<__nv_bfloat16*>(scr);
         p.flags = reinterpret_cast<unsigned int*>(scr + img_bytes);
         p.groups = groups; p.n0 = g0 * NB;
-        rc = launch_clustered(fwd_kernel(NB, 0, x3), dim3(H / 32, 2, groups), dim3(1, 1, 1), smem, true, tmW, p, stream);
+        rc = launch_clustered(fwd_kernel(NB, 0, x3, cell_k), dim3(H / 32, 2, groups), dim3(1, 1, 1), smem, true, tmW, p, stream);
         if (rc != OK) return rc;
     }
     return OK;
 }
 
 extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
-                                            const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* scratch,
-                                            int T, int N, int H, int batch_tile, const float* bn_x, const float* bn_coef,
-                                            void* resident_counter, void* resident_event, ctcb200_stream_t stream_) {
+                                            const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* dg_rec,
+                                            void* dg_rec_lo, void* scratch, int T, int N, int H, int batch_tile, int cell,
+                                            const float* bn_x, const float* bn_coef, void* resident_counter,
+                                            void* resident_event, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     cudaEvent_t start_ev = static_cast<cudaEvent_t>(resident_event);
     const bool x3 = whhT_lo_packed != nullptr;
+    CTCB_REQUIRE(cell >= 0 && cell <= 3, "lstm_bwd: cell %d not in {0 LSTM, 1 GRU, 2 RNN tanh, 3 RNN relu}", cell);
+    const int cell_k = cell == 0 ? CELL_LSTM : (cell == 1 ? CELL_GRU : CELL_RNN);
+    const bool plain = cell_k == CELL_LSTM;
+    CTCB_REQUIRE(cell_k != CELL_GRU || (dg_rec != nullptr && (!x3 || dg_rec_lo != nullptr)),
+                 "lstm_bwd: the GRU cell needs dg_rec (and dg_rec_lo in the split-operand mode)");
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE((reinterpret_cast<uintptr_t>(resident_counter) & 3) == 0, "lstm_bwd: resident_counter must be 4-byte aligned");
     CTCB_REQUIRE((bn_x == nullptr) == (bn_coef == nullptr), "lstm_bwd: bn_x and bn_coef must be given together");
@@ -1797,11 +1902,13 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     p.gates_save = x3 ? nullptr : static_cast<const uint2*>(gates_save);
     p.gates_save32 = x3 ? static_cast<const float4*>(gates_save) : nullptr;
     p.dg = static_cast<__nv_bfloat16*>(dg); p.dg_lo = static_cast<__nv_bfloat16*>(dg_lo);
+    p.dg_rec = static_cast<__nv_bfloat16*>(dg_rec); p.dg_rec_lo = static_cast<__nv_bfloat16*>(dg_rec_lo);
+    p.rnn_relu = cell == 3 ? 1 : 0;
     p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter);
     p.bn_x = bn_x; p.bn_coef = bn_coef;
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed);
     p.T = T; p.N = N; p.H = H; p.n0 = 0;
-    if (!x3 && two_tile_path(H)) {
+    if (!x3 && plain && two_tile_path(H)) {
         constexpr int NB2 = 16;
         const int groups2 = (N + NB2 - 1) / NB2;
         CUtensorMap tmWT2;
@@ -1817,13 +1924,13 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     }
     int ex = exchange_mode(H);
     {
-        const int nb_try = x3 ? 16 : pick_nb(N, H, batch_tile, true, ex != 0);
-        if (ex != 0 && !cluster_ok(bwd_kernel(nb_try, ex, x3), dim3(4, H / 128, 2 * ((N + nb_try - 1) / nb_try)),
+        const int nb_try = (x3 || !plain) ? 16 : pick_nb(N, H, batch_tile, true, ex != 0);
+        if (ex != 0 && !cluster_ok(bwd_kernel(nb_try, ex, x3, cell_k), dim3(4, H / 128, 2 * ((N + nb_try - 1) / nb_try)),
                                    dim3(4, H / 128, 1), lstm_smem_bytes(nb_try, H, true, ex, x3)))
             ex = 0;
     }
     const bool cl = ex != 0;
-    const int NB = x3 ? 16 : pick_nb(N, H, batch_tile, true, cl);
+    const int NB = (x3 || !plain) ? 16 : pick_nb(N, H, batch_tile, true, cl);
     const int groups_total = (N + NB - 1) / NB;
     const int MB = H / 128;
     CUtensorMap tmWT;   // only read by the split-operand kernels (W^T_lo slice -> shared memory)
@@ -1835,7 +1942,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     p.groups = groups_total;
     if (cl) {
         dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
-        return launch_clustered(bwd_kernel(NB, ex, x3), grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
+        return launch_clustered(bwd_kernel(NB, ex, x3, cell_k), grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
     }
     const int per_group = 2 * 4 * MB;
     const int sms = device_sm_count();
@@ -1855,7 +1962,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         if (g0 > 0) p.resident = nullptr;
         dim3 grid(4, MB, 2 * groups), cluster(4, 1, 1);
         const bool coop = getenv("CTCB200_BWD_NO_COOP") == nullptr;  // profilers may reject cooperative + cluster
-        rc = launch_clustered(bwd_kernel(NB, 0, x3), grid, cluster, smem, coop, tmWT, p, stream, LSTM_THREADS, g0 == 0 ? start_ev : nullptr);
+        rc = launch_clustered(bwd_kernel(NB, 0, x3, cell_k), grid, cluster, smem, coop, tmWT, p, stream, LSTM_THREADS, g0 == 0 ? start_ev : nullptr);
         if (rc != OK) return rc;
     }
     return OK;

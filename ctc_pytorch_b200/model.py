@@ -213,6 +213,18 @@ def _unwrap(mod):
     return mod.module if (mod is not None and hasattr(mod, "module") and not isinstance(mod, (nn.BatchNorm1d, nn.Linear, nn.Sequential))) else mod
 
 
+def _cell_of(rnn):
+    """(cell code of the C ABI, gate rows per unit in torch's weights) for a recurrent module the reference may build
+    (train_ctc.py:20 supported_rnn): nn.LSTM -> (0, 4), nn.GRU -> (1, 3), nn.RNN tanh / relu -> (2 / 3, 1)."""
+    if isinstance(rnn, nn.LSTM):
+        return 0, 4
+    if isinstance(rnn, nn.GRU):
+        return 1, 3
+    if isinstance(rnn, nn.RNN):
+        return (3 if rnn.nonlinearity == "relu" else 2), 1
+    raise RuntimeError("the B200 path implements nn.LSTM / nn.GRU / nn.RNN layers (got %r)" % (type(rnn),))
+
+
 def _layer_dropout_p(layer):
     d = getattr(layer, "dropout", None)
     return float(d.p) if isinstance(d, nn.Dropout) else 0.0
@@ -294,7 +306,7 @@ def _packed_weights(model, li, rnn, H, I, Ipad, x3, dev):
         whhT_p = torch.empty((8 * H, H), dtype=torch.bfloat16, device=dev)
         _call("ctcb200_pack_lstm_weights", _lib.ptr(rnn.weight_ih_l0), _lib.ptr(rnn.weight_hh_l0),
               _lib.ptr(wih_r), _lib.ptr(whh_r), _lib.ptr(wih_p),
-              _lib.ptr(wihT_p), _lib.ptr(whh_p), _lib.ptr(whhT_p), H, I, Ipad, part, _lib.stream())
+              _lib.ptr(wihT_p), _lib.ptr(whh_p), _lib.ptr(whhT_p), H, I, Ipad, part, _cell_of(rnn)[1], _lib.stream())
         parts.append((wih_p, wihT_p, whh_p, whhT_p))
     packed = tuple(_Opnd(parts[0][i], parts[1][i] if x3 else None) for i in range(4))
     cache[li] = (key, packed)
@@ -382,8 +394,10 @@ class _RnnStackFn(torch.autograd.Function):
             hout = torch.empty((R, 2 * H), dtype=torch.float32, device=dev)
             c_save = torch.empty((R, 2 * H), dtype=torch.float32, device=dev) if need_grad else None
             gates = torch.empty((R, 2 * H, 4), dtype=torch.float32 if x3 else torch.float16, device=dev) if need_grad else None
+            cell, G = _cell_of(layer.rnn)
+            rec.cell, rec.G = cell, G
             _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout), _lib.ptr(c_save),
-                  _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, stream())
+                  _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, cell, stream())
             del gx
             rec.HT = None
             p_drop = _layer_dropout_p(layer)
@@ -516,8 +530,9 @@ class _RnnStackFn(torch.autograd.Function):
 
         def _wgrad(item, mc):
             """dW_ih, dW_hh (both directions) of one layer from its gate gradients; runs on the current stream."""
-            layer_, rec_, dg_, li_, buf_, views_ = item
+            layer_, rec_, (dg_, dgrec_), li_, buf_, views_ = item
             rnn = layer_.rnn
+            GH = rec_.G * H     # rows of torch's weight matrices per direction (4H LSTM, 3H GRU, H RNN)
             I_ = rec_.I
             XT, HT = rec_.XT, rec_.HT
             if XT is None:   # deferred transposed operands (see forward)
@@ -529,39 +544,42 @@ class _RnnStackFn(torch.autograd.Function):
                     _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, None, None, False, True, x3)
             if HT is None:
                 _, HT = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True, x3=x3)
-            dgTs = []
-            for d_ in (dg_.hi, dg_.lo):
-                if d_ is None:
-                    dgTs.append(None)
-                    continue
-                t_ = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
-                _call("ctcb200_transpose_dg", _lib.ptr(d_), _lib.ptr(t_), Rp, N, Np, R, H, stream())
-                dgTs.append(t_)
-            dgT = _Opnd(dgTs[0], dgTs[1])
+            def _transposed(o_):
+                ts = []
+                for d_ in (o_.hi, o_.lo):
+                    if d_ is None:
+                        ts.append(None)
+                        continue
+                    t_ = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
+                    _call("ctcb200_transpose_dg", _lib.ptr(d_), _lib.ptr(t_), Rp, N, Np, R, H, stream())
+                    ts.append(t_)
+                return _Opnd(ts[0], ts[1])
+            dgT = _transposed(dg_)
+            dgT_rec = _transposed(dgrec_) if dgrec_ is not None else dgT     # what the recurrent weights see (GRU differs)
             if packed:   # each direction against the input in its own alignment
                 dwih = views_[0].view(8 * H, I_)
                 _gemm(dgT.rows(0, 4 * H), XT, out=dwih[:4 * H], k=Rp, max_ctas=mc)
                 _gemm(dgT.rows(4 * H, 8 * H), rec_.XrT, out=dwih[4 * H:], k=Rp, max_ctas=mc)
             else:
                 dwih = _gemm(dgT, XT, out=views_[0].view(8 * H, I_), k=Rp, max_ctas=mc)     # [8H, I], torch row order
-            grads[rnn.weight_ih_l0] = dwih[:4 * H]
+            grads[rnn.weight_ih_l0] = dwih[:GH]
             whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
             if T > 1:
                 K = Rp - Np  # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan
-                _gemm(dgT.rows(0, 4 * H), HT.rows(0, H), out=whf, a_koff=Np, b_koff=0, k=K, max_ctas=mc)
+                _gemm(dgT_rec.rows(0, 4 * H), HT.rows(0, H), out=whf, a_koff=Np, b_koff=0, k=K, max_ctas=mc)
                 if D == 2:
-                    _gemm(dgT.rows(4 * H, 8 * H), HT.rows(H, 2 * H), out=whr, a_koff=0, b_koff=Np, k=K, max_ctas=mc)
+                    _gemm(dgT_rec.rows(4 * H, 8 * H), HT.rows(H, 2 * H), out=whr, a_koff=0, b_koff=Np, k=K, max_ctas=mc)
             else:
                 whf.zero_()
                 whr.zero_()
-            grads[rnn.weight_hh_l0] = whf
+            grads[rnn.weight_hh_l0] = whf[:GH]
             if D == 2:
-                grads[rnn.weight_ih_l0_reverse], grads[rnn.weight_hh_l0_reverse] = dwih[4 * H:], whr
+                grads[rnn.weight_ih_l0_reverse], grads[rnn.weight_hh_l0_reverse] = dwih[4 * H:4 * H + GH], whr[:GH]
             if sync is not None:
                 sync.reduce(buf_)    # one collective per layer, behind the BPTT kernels of the layers below
             if torch.cuda.current_stream(dev) != main:  # allocated on the main stream, written here on the side stream
                 buf_.record_stream(torch.cuda.current_stream(dev))
-            keep.append((dg_, dgT, XT, HT))  # alive until the streams are joined
+            keep.append((dg_, dgrec_, dgT, dgT_rec, XT, HT))  # alive until the streams are joined
 
         pending = None
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
@@ -580,10 +598,16 @@ class _RnnStackFn(torch.autograd.Function):
                 dh2 = torch.zeros((R, 2 * H), dtype=torch.float32, device=dev)
                 dh2[:, :H].copy_(dh)
                 dh = dh2
-            dg = _Opnd(torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev),
-                       torch.empty((R, 8 * H), dtype=torch.bfloat16, device=dev) if x3 else None)
+            def _dg_buf():
+                # unused gate slots of GRU / RNN layers are never written by the kernel: they must read as zero
+                alloc = torch.empty if rec.G == 4 else torch.zeros
+                return _Opnd(alloc((R, 8 * H), dtype=torch.bfloat16, device=dev),
+                             alloc((R, 8 * H), dtype=torch.bfloat16, device=dev) if x3 else None)
+            dg = _dg_buf()
+            dg_rec = _dg_buf() if rec.cell == 1 else None   # GRU: the recurrent weights see a different n-gate gradient
             _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p.hi), _lib.ptr(rec.whhT_p.lo), _lib.ptr(rec.c_save),
-                  _lib.ptr(rec.gates), _lib.ptr(dg.hi), _lib.ptr(dg.lo), _lib.ptr(scratch), T, N, H, model.batch_tile,
+                  _lib.ptr(rec.gates), _lib.ptr(dg.hi), _lib.ptr(dg.lo), _lib.ptr(dg_rec.hi) if dg_rec else None,
+                  _lib.ptr(dg_rec.lo) if dg_rec else None, _lib.ptr(scratch), T, N, H, model.batch_tile, rec.cell,
                   _lib.ptr(bn_fuse[0]) if bn_fuse else None, _lib.ptr(bn_fuse[1]) if bn_fuse else None,
                   _lib.ptr(res[0]) if (overlap and gate == "memop") else None,
                   gate_ev_ptr if (overlap and gate == "event") else None, stream())
@@ -606,7 +630,7 @@ class _RnnStackFn(torch.autograd.Function):
                         else:
                             _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
                         _wgrad(pending[:6], side_ctas)
-                pending = [layer, rec, dg, li, buf, views, None]
+                pending = [layer, rec, (dg, dg_rec), li, buf, views, None]
             def _input_grad():
                 if not packed:
                     return _gemm(dg, rec.wihT_p, k=8 * H)                  # [R, I] rows (t, n)
@@ -626,7 +650,7 @@ class _RnnStackFn(torch.autograd.Function):
                         pending[6] = torch.cuda.Event()
                         pending[6].record(main)
             if not overlap:
-                _wgrad((layer, rec, dg, li, buf, views), 0)
+                _wgrad((layer, rec, (dg, dg_rec), li, buf, views), 0)
         if overlap:
             if pending is not None:
                 _wgrad(pending[:6], 0)  # the first layer's weight gradients: nothing left to hide them under
@@ -702,8 +726,8 @@ class CTC_Model(nn.Module):
     # -- checks that keep the CUDA path honest -------------------------------------------------------
     def _check_supported(self, x):
         _lib.require_cuda(x)
-        if self.rnn_param["rnn_type"] is not nn.LSTM:
-            raise RuntimeError("the B200 path implements nn.LSTM layers only (got %r)" % (self.rnn_param["rnn_type"],))
+        if self.rnn_param["rnn_type"] not in (nn.LSTM, nn.GRU, nn.RNN):
+            raise RuntimeError("the B200 path implements nn.LSTM / nn.GRU / nn.RNN layers (got %r)" % (self.rnn_param["rnn_type"],))
         if next(self.parameters()).device != x.device:
             raise RuntimeError("model parameters and input must live on the same CUDA device")
         if self.precision not in ("bf16", "x3"):

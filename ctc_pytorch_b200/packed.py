@@ -112,8 +112,8 @@ class CTC_RNN(nn.Module):
         elif lengths is None:
             raise ValueError("CTC_RNN.forward takes a PackedSequence, or a padded [T, N, F] tensor together with lengths")
         _lib.require_cuda(x)
-        if self.rnn_type is not nn.LSTM or self.num_directions != 2:
-            raise RuntimeError("the B200 path implements bidirectional nn.LSTM layers only")
+        if self.rnn_type not in (nn.LSTM, nn.GRU, nn.RNN) or self.num_directions != 2:
+            raise RuntimeError("the packed B200 path implements bidirectional nn.LSTM / nn.GRU / nn.RNN layers")
         if next(self.parameters()).device != x.device:
             raise RuntimeError("model parameters and input must live on the same CUDA device")
         with torch.cuda.device(x.device):

@@ -118,16 +118,22 @@ CTCB200_API int64_t ctcb200_lstm_scratch_bytes(int N, int H);
  * A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (three ctcb200_gemm_tn_bf16 launches with accumulate=1, or three tcgen05.mma chains
  * inside the recurrent kernels). Passing the *_lo operands to lstm_fwd / lstm_bwd selects the mode there: gates_save is then
  * 4 x fp32 = 16 bytes per element and lstm_bwd also writes dg_lo. */
+/* Other cell types the reference can be configured with (train_ctc.py:20 supported_rnn, model_ctc.py:23): `cell` = 0 nn.LSTM,
+ * 1 nn.GRU, 2 nn.RNN(tanh), 3 nn.RNN(relu); `gates` = 4 / 3 / 1 rows of H in the torch weights. All cells share the LSTM's
+ * operand layout with four gate slots per unit — GRU uses (r, z, n, -), RNN (g, -, -, -), unused slots carry zero weights —
+ * so packing, Gx / dX / dW GEMMs and the exchange are common. GRU: lstm_bwd writes dg (what the input weights see: the n slot
+ * holds dn_pre) and dg_rec (what the recurrent weights see: dn_pre * r), the latter feeding dW_hh; c_save holds h_t. */
 CTCB200_API int ctcb200_pack_lstm_weights(const float* wih_f, const float* whh_f, const float* wih_r,
                                           const float* whh_r, void* wih_p, void* wihT_p, void* whh_p, void* whhT_p,
-                                          int H, int I, int Ipad, int part, ctcb200_stream_t stream);
+                                          int H, int I, int Ipad, int part, int gates, ctcb200_stream_t stream);
 CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
                                  float* c_save, void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
-                                 ctcb200_stream_t stream);
+                                 int cell, ctcb200_stream_t stream);
 CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
-                                 const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* scratch, int T,
-                                 int N, int H, int batch_tile, const float* bn_x, const float* bn_coef,
-                                 void* resident_counter, void* resident_event, ctcb200_stream_t stream);
+                                 const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* dg_rec,
+                                 void* dg_rec_lo, void* scratch, int T, int N, int H, int batch_tile, int cell,
+                                 const float* bn_x, const float* bn_coef, void* resident_counter, void* resident_event,
+                                 ctcb200_stream_t stream);
 /* Scheduling aid for overlapping off-critical-path work (weight-gradient GEMMs) with the latency-bound BPTT kernel:
  * resident_event (NULL = off) is a cudaEvent_t (created with timing disabled) attached to the launch as a programmatic event
  * that fires once every block of the BPTT grid has started: cudaStreamWaitEvent on it from another stream is a dependency

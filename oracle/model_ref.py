@@ -26,10 +26,10 @@ import torch.nn.functional as F
 
 
 class _RnnBlock(nn.Module):
-    def __init__(self, input_size, hidden, batch_norm, dropout, bidirectional=True):
+    def __init__(self, input_size, hidden, batch_norm, dropout, bidirectional=True, rnn_type=nn.LSTM):
         super().__init__()
         self.batch_norm = nn.BatchNorm1d(input_size) if batch_norm else None
-        self.rnn = nn.LSTM(input_size=input_size, hidden_size=hidden, bidirectional=bidirectional, bias=False)
+        self.rnn = rnn_type(input_size=input_size, hidden_size=hidden, bidirectional=bidirectional, bias=False)
         self.p = dropout
         self.fixed_mask = None   # tests: keep-mask [T*N, 2H] shared with the CUDA path instead of this process's RNG
 
@@ -64,7 +64,7 @@ class _ConvBlock(nn.Module):
 
 class RefAcousticModel(nn.Module):
     def __init__(self, input_size, hidden, layers, num_class, batch_norm=True, cnn_layers=None, cnn_batch_norm=True,
-                 cnn_act=nn.ReLU, dropout=0.0, bidirectional=True):
+                 cnn_act=nn.ReLU, dropout=0.0, bidirectional=True, rnn_type=nn.LSTM):
         super().__init__()
         D = 2 if bidirectional else 1
         rnn_in = input_size
@@ -77,9 +77,9 @@ class RefAcousticModel(nn.Module):
                 rnn_in = (rnn_in + 2 * padding[1] - kernel[1]) // stride[1] + 1
             self.conv = nn.Sequential(OrderedDict(blocks))
             rnn_in *= cout
-        blocks = [("0", _RnnBlock(rnn_in, hidden, False, dropout, bidirectional))]
+        blocks = [("0", _RnnBlock(rnn_in, hidden, False, dropout, bidirectional, rnn_type))]
         for l in range(1, layers):
-            blocks.append((str(l), _RnnBlock(D * hidden, hidden, batch_norm, dropout, bidirectional)))
+            blocks.append((str(l), _RnnBlock(D * hidden, hidden, batch_norm, dropout, bidirectional, rnn_type)))
         self.rnns = nn.Sequential(OrderedDict(blocks))
         if batch_norm:
             self.fc = nn.Sequential(nn.BatchNorm1d(D * hidden), nn.Linear(D * hidden, num_class, bias=False))

@@ -37,9 +37,13 @@ class Emu(object):
         return 0
 
     # ---- layout kernels -------------------------------------------------------------------------------------------
-    def pack_lstm_weights(self, wih_f, whh_f, wih_r, whh_r, wih_p, wihT_p, whh_p, whhT_p, H, I, Ipad, part, stream):
+    def pack_lstm_weights(self, wih_f, whh_f, wih_r, whh_r, wih_p, wihT_p, whh_p, whhT_p, H, I, Ipad, part, gates, stream):
         perm = torch.tensor([_orig_row(p, H) for p in range(4 * H)])
-        for d, (wi, wh) in enumerate(((wih_f, whh_f), (wih_r, whh_r))):
+
+        def four(w):     # torch rows [gates*H, .] -> four gate slots, the unused ones zero
+            w = w.detach()
+            return torch.cat([w, torch.zeros((4 - gates) * H, w.shape[1])], 0) if gates < 4 else w
+        for d, (wi, wh) in enumerate(((four(wih_f), four(whh_f)), (four(wih_r), four(whh_r)))):
             rows = slice(d * 4 * H, (d + 1) * 4 * H)
             wih_p[rows].zero_()
             wih_p[rows, :I] = _part(wi.detach()[perm], part)
@@ -100,7 +104,7 @@ class Emu(object):
         p = torch.arange(4 * H)
         return p & 3, (p >> 7) * 32 + ((p & 127) >> 2)
 
-    def lstm_fwd(self, gx, whh, whh_lo, hout, c_save, gates, scratch, T, N, H, tile, stream):
+    def lstm_fwd(self, gx, whh, whh_lo, hout, c_save, gates, scratch, T, N, H, tile, cell, stream):
         x3 = whh_lo is not None
         q_of, u_of = self._unpack_cols(H)
         for d in range(2):
@@ -118,18 +122,33 @@ class Emu(object):
                 pre = g[t] + rec                                  # packed columns
                 gate = torch.empty(N, 4, H)
                 gate[:, q_of, u_of] = pre
-                i, f, gg, o = torch.sigmoid(gate[:, 0]), torch.sigmoid(gate[:, 1]), torch.tanh(gate[:, 2]), torch.sigmoid(gate[:, 3])
-                c = f * c + i * gg
-                h = o * torch.tanh(c)
+                if cell == 0:
+                    i, f, gg, o = torch.sigmoid(gate[:, 0]), torch.sigmoid(gate[:, 1]), torch.tanh(gate[:, 2]), torch.sigmoid(gate[:, 3])
+                    c = f * c + i * gg
+                    h = o * torch.tanh(c)
+                    saved = torch.stack([i, f, gg, o], -1)
+                elif cell == 1:      # GRU: slots (r, z, n, -); the n gate takes r * (W_hn h) from the recurrent product alone
+                    recg = torch.empty(N, 4, H)
+                    recg[:, q_of, u_of] = rec
+                    r_, z_ = torch.sigmoid(gate[:, 0]), torch.sigmoid(gate[:, 1])
+                    hn = recg[:, 2]
+                    nn_ = torch.tanh(gate[:, 2] - hn + r_ * hn)
+                    h = (1 - z_) * nn_ + z_ * h
+                    c = h
+                    saved = torch.stack([r_, z_, nn_, hn], -1)
+                else:                # vanilla RNN, slot 0
+                    h = torch.relu(gate[:, 0]) if cell == 3 else torch.tanh(gate[:, 0])
+                    c = h
+                    saved = torch.stack([h, torch.zeros_like(h), torch.zeros_like(h), torch.zeros_like(h)], -1)
                 rows = slice(t * N, (t + 1) * N)
                 hout[rows, d * H:(d + 1) * H] = h
                 if c_save is not None:
                     c_save[rows, d * H:(d + 1) * H] = c
                 if gates is not None:
-                    gates[rows, d * H:(d + 1) * H] = torch.stack([i, f, gg, o], -1).to(gates.dtype)
+                    gates[rows, d * H:(d + 1) * H] = saved.to(gates.dtype)
 
-    def lstm_bwd(self, dhout, whhT, whhT_lo, c_save, gates, dg, dg_lo, scratch, T, N, H, tile, bn_x, bn_coef, res_counter,
-                 res_event, stream):
+    def lstm_bwd(self, dhout, whhT, whhT_lo, c_save, gates, dg, dg_lo, dg_rec, dg_rec_lo, scratch, T, N, H, tile, cell, bn_x,
+                 bn_coef, res_counter, res_event, stream):
         x3 = whhT_lo is not None
         dh_all = dhout.detach().view(T, N, 2 * H).float()
         if bn_x is not None:
@@ -159,19 +178,39 @@ class Emu(object):
                 gi, gf, gg, go = gt[..., 0], gt[..., 1], gt[..., 2], gt[..., 3]
                 c_t = c_save[rows, d * H:(d + 1) * H]
                 c_p = c_save[tprev * N:(tprev + 1) * N, d * H:(d + 1) * H] if has_prev else torch.zeros(N, H)
-                tc = torch.tanh(c_t)
-                d_o = dh * tc * go * (1 - go)
-                dc = dc_carry + dh * go * (1 - tc * tc)
-                d_i = dc * gg * gi * (1 - gi)
-                d_f = dc * c_p * gf * (1 - gf)
-                d_g = dc * gi * (1 - gg * gg)
-                dc_carry = dc * gf
-                dG_prev = torch.stack([d_i, d_f, d_g, d_o], 1)                  # [N, 4, H]
-                packed = dG_prev[:, q_of, u_of]                                 # [N, 4H] packed columns of this direction
-                hi = packed.to(torch.bfloat16)
-                dg[rows, d * 4 * H:(d + 1) * 4 * H] = hi
-                if x3:
-                    dg_lo[rows, d * 4 * H:(d + 1) * 4 * H] = (packed - hi.float()).to(torch.bfloat16)
+                zero = torch.zeros_like(dh)
+                if cell == 0:
+                    tc = torch.tanh(c_t)
+                    d_o = dh * tc * go * (1 - go)
+                    dc = dc_carry + dh * go * (1 - tc * tc)
+                    d_i = dc * gg * gi * (1 - gi)
+                    d_f = dc * c_p * gf * (1 - gf)
+                    d_g = dc * gi * (1 - gg * gg)
+                    dc_carry = dc * gf
+                    dG_prev = torch.stack([d_i, d_f, d_g, d_o], 1)              # [N, 4, H]: what W_hh^T multiplies next step
+                    dG_in = dG_prev
+                elif cell == 1:      # saved (r, z, n, hn), c_p = h_prev
+                    dh = dh + dc_carry
+                    dn_pre = dh * (1 - gf) * (1 - gg * gg)
+                    d_r = dn_pre * go * gi * (1 - gi)
+                    d_z = dh * (c_p - gg) * gf * (1 - gf)
+                    dc_carry = dh * gf
+                    dG_prev = torch.stack([d_r, d_z, dn_pre * gi, zero], 1)
+                    dG_in = torch.stack([d_r, d_z, dn_pre, zero], 1)
+                else:
+                    dpre = dh * (gi > 0).float() if cell == 3 else dh * (1 - gi * gi)
+                    dG_prev = torch.stack([dpre, zero, zero, zero], 1)
+                    dG_in = dG_prev
+
+                def store(dst, dst_lo, val):
+                    packed = val[:, q_of, u_of]                                 # [N, 4H] packed columns of this direction
+                    hi = packed.to(torch.bfloat16)
+                    dst[rows, d * 4 * H:(d + 1) * 4 * H] = hi
+                    if x3:
+                        dst_lo[rows, d * 4 * H:(d + 1) * 4 * H] = (packed - hi.float()).to(torch.bfloat16)
+                store(dg, dg_lo, dG_in)
+                if cell == 1:
+                    store(dg_rec, dg_rec_lo, dG_prev)
 
     # ---- BatchNorm / softmax --------------------------------------------------------------------------------------------
     def bn_train_stats(self, x, R, C, gamma, beta, rmean, rvar, momentum, eps, mean, rstd, scale, shift, ws, n_valid, stream):

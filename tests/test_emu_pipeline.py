@@ -195,3 +195,30 @@ def test_packed_model_orchestration(precision):
     with emulated(), torch.no_grad():
         logp = m(x, lens)
     assert (logp - ref(x, lens)).abs().max().item() < tol[2]
+
+
+@pytest.mark.parametrize("rnn_type,nonlin", [(nn.GRU, None), (nn.RNN, "tanh"), (nn.RNN, "relu")])
+def test_gru_and_rnn_cells_orchestration(rnn_type, nonlin):
+    """The reference's other recurrent cells (train_ctc.py:20 supported_rnn): same four-slot operand layout, cell-specific
+    element phases; GRU's second set of gate gradients (input-side vs recurrent-side n slot) reaches the right GEMMs."""
+    T, N, F, H, L, C = 11, 4, 40, 128, 2, 8
+    torch.manual_seed(9)
+    rnn_param = {"rnn_input_size": F, "rnn_hidden_size": H, "rnn_layers": L, "rnn_type": rnn_type, "bidirectional": True,
+                 "batch_norm": True}
+    m = CTC_Model(rnn_param=rnn_param, num_class=C, drop_out=0.0)
+    ref = model_ref.RefAcousticModel(F, H, L, C, batch_norm=True, rnn_type=rnn_type)
+    if nonlin == "relu":   # not reachable through the reference's config (nn.RNN defaults to tanh); swap the modules in
+        for model_ in (m, ref):
+            for blk in model_.rnns.children():
+                old = blk.rnn
+                blk.rnn = nn.RNN(input_size=old.input_size, hidden_size=old.hidden_size, bidirectional=True, bias=False,
+                                 nonlinearity="relu")
+    assert list(m.state_dict().keys()) == list(ref.state_dict().keys())
+    ref.load_state_dict(m.state_dict())
+    m.precision, m.overlap_wgrad = "x3", False
+    x, frac, tg, tl = synth.synthetic_batch(T, N, F, C, 3, 4)
+    il = (frac * T).long()
+    m.train(); ref.train()
+    with emulated():
+        e_loss, e_grad, e_x, e_out = _run_pair(m, ref, x, tg, il, tl, N, input_grad=True)
+    assert e_loss < 1e-5 and e_grad < 3e-4 and e_x < 3e-4 and e_out < 1e-4, (e_loss, e_grad, e_x, e_out)

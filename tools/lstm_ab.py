@@ -26,6 +26,8 @@ gates32 = torch.empty(R, 2 * H, 4, device=dev)
 dh = torch.randn(R, 2 * H, device=dev)
 dg = torch.empty(R, 8 * H, dtype=torch.bfloat16, device=dev)
 dg_lo = torch.empty(R, 8 * H, dtype=torch.bfloat16, device=dev)
+dg2 = torch.empty(R, 8 * H, dtype=torch.bfloat16, device=dev)
+dg2_lo = torch.empty(R, 8 * H, dtype=torch.bfloat16, device=dev)
 scratch = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -53,19 +55,22 @@ def chk(rc, lib):
 
 
 for name, lo, gates in (("bf16", None, gates16), ("x3", whh_lo, gates32)):
-    f = timed(lambda: chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), P(lo), P(hout), P(c_save), P(gates), P(scratch), T, N, H, 0, S()), cur))
-    b = timed(lambda: chk(cur.ctcb200_lstm_bwd(P(dh), P(whh), P(lo), P(c_save), P(gates), P(dg), P(dg_lo) if lo is not None else None,
-                                               P(scratch), T, N, H, 0, None, None, None, None, S()), cur))
-    res["r2_" + name] = {"fwd_ms": f, "bwd_ms": b, "fwd_us_per_step": f * 1e3 / T, "bwd_us_per_step": b * 1e3 / T}
+    for cell, cname in ((0, ""), (1, "_gru"), (2, "_rnn")):
+        f = timed(lambda: chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), P(lo), P(hout), P(c_save), P(gates), P(scratch), T, N, H, 0, cell,
+                                                   S()), cur))
+        b = timed(lambda: chk(cur.ctcb200_lstm_bwd(P(dh), P(whh), P(lo), P(c_save), P(gates), P(dg), P(dg_lo) if lo is not None else None,
+                                                   P(dg2), P(dg2_lo) if lo is not None else None, P(scratch), T, N, H, 0, cell,
+                                                   None, None, None, None, S()), cur))
+        res["r2_" + name + cname] = {"fwd_ms": f, "bwd_ms": b, "fwd_us_per_step": f * 1e3 / T, "bwd_us_per_step": b * 1e3 / T}
 os.environ["CTCB200_LSTM_PIPE"] = "0"
-f = timed(lambda: chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), None, P(hout), P(c_save), P(gates16), P(scratch), T, N, H, 0, S()), cur))
+f = timed(lambda: chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), None, P(hout), P(c_save), P(gates16), P(scratch), T, N, H, 0, 0, S()), cur))
 res["r2_bf16_unpipelined_fwd_ms"] = f
 os.environ.pop("CTCB200_LSTM_PIPE")
 old_path = os.path.join(ROOT, "tools", "_ab", "libctcb200_r1.so")
 if os.path.exists(old_path):
     old = ctypes.CDLL(old_path)
     old.ctcb200_last_error.restype = ctypes.c_char_p
-    chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), None, P(hout), P(c_save), P(gates16), P(scratch), T, N, H, 0, S()), cur)
+    chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), None, P(hout), P(c_save), P(gates16), P(scratch), T, N, H, 0, 0, S()), cur)
     f = timed(lambda: chk(old.ctcb200_lstm_fwd(P(gx), P(whh), P(hout), P(c_save), P(gates16), P(scratch), T, N, H, 0, S()), old))
     b = timed(lambda: chk(old.ctcb200_lstm_bwd(P(dh), P(whh), P(c_save), P(gates16), P(dg), P(scratch), T, N, H, 0, None, None, None, None,
                                                S()), old))
