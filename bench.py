@@ -60,7 +60,8 @@ class ClockSampler(object):
     """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []          # (host time of arrival, csv line)
+        self.windows = []       # [t0, t1] host-time intervals of the timed regions
         self.proc = None
         self.index = index
 
@@ -70,7 +71,7 @@ class ClockSampler(object):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -79,7 +80,13 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
+
+    def open_window(self):
+        self.windows.append([time.monotonic(), None])
+
+    def close_window(self):
+        self.windows[-1][1] = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -91,7 +98,11 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            # the process is started before the warm-up (nvidia-smi needs a few hundred ms to come up); only samples taken
+            # inside a timed region count
+            if self.windows and not any(w0 <= ts <= (w1 if w1 is not None else ts) for w0, w1 in self.windows):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -105,7 +116,8 @@ class ClockSampler(object):
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "samples every 25 ms inside the timed regions (device-resident loop + e2e loop)"}
 
 
 def make_batch(cfg, seed, lo=0, hi=None):
@@ -296,19 +308,23 @@ def run_ours(args, name, cfg, rank, world):
     N = job.n_local
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # larger than the 126 MB L2
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for w in range(warm):
         job.step(job.devb[w % len(job.devb)])
 
     # ---- timed region 1: inputs resident in HBM ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.open_window()
     launches0 = L.launches
     ms_dev = timed_loop(job, args.steps, flush, world, e2e=False)
     launches = L.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.close_window()
     # ---- timed region 2: end to end from host buffers ----
+    sampler.open_window()
     ms_e2e = timed_loop(job, args.steps, flush, world, e2e=True)
+    sampler.close_window()
+    clocks = sampler.stop() if rank == 0 else None
     d2h_bytes = 4 + 16
 
     # ---- secondary measurements (all ranks take part in the collectives) ----

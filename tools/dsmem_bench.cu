@@ -89,6 +89,67 @@ __global__ void __launch_bounds__(256, 1) allgather_kernel(int bytes, int iters,
     cluster_sync();
 }
 
+
+// all-gather with per-lane remote stores instead of the bulk-copy engine: MODE 1 = st.async (16 B per lane, complete_tx on the
+// receiver's mbarrier), MODE 2 = st.shared::cluster.v4 followed by one release-arrive per (sender warp, peer) on the receiver's
+// mbarrier. `send_warps` warps share the peers round-robin. The receiver fences the async proxy after the wait (what a
+// tcgen05.mma consumer of the image would need).
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, uint4 v, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t dst_cluster, uint4 v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void remote_arrive_release(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) allgather_st_kernel(int bytes, int iters, int send_warps, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t cs = gridDim.x;
+    uint8_t* recv = smem;                          // [2 parities][cs][bytes]
+    uint8_t* send = smem + 2 * cs * bytes;         // [bytes]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(send + bytes);   // [2]
+    const uint32_t me = cluster_rank();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&bar[0], MODE == 1 ? 1 : cs);
+        mbar_init(&bar[1], MODE == 1 ? 1 : cs);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (MODE == 1) { mbar_expect(&bar[0], cs * bytes); mbar_expect(&bar[1], cs * bytes); }
+    }
+    for (int i = tid; i < bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(send)[i] = me * 1000 + i;
+    __syncthreads();
+    cluster_sync();
+    long long t0 = 0;
+    uint32_t check = 0;
+    for (int it = 0; it < iters; ++it) {
+        if (it == 8 && tid == 0) t0 = clock64();
+        const int par = it & 1;
+        if (warp < send_warps) {
+            for (uint32_t d = warp; d < cs; d += send_warps) {
+                const uint32_t dst = mapa(smem_u32(recv + (par * cs + me) * bytes), d);
+                const uint32_t rb = mapa(smem_u32(&bar[par]), d);
+                for (int o = lane * 16; o < bytes; o += 512) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(send + o);
+                    if (MODE == 1) st_async_v4(dst + o, v, rb); else st_cluster_v4(dst + o, v);
+                }
+                if (MODE == 2) { __syncwarp(); if (lane == 0) remote_arrive_release(rb); }
+            }
+        }
+        mbar_wait(&bar[par], (it >> 1) & 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        check += reinterpret_cast<const uint32_t*>(recv + (par * cs + (tid % cs)) * bytes)[0];
+        __syncthreads();
+        if (MODE == 1 && tid == 0) mbar_expect(&bar[par], cs * bytes);
+    }
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) cycles[0] = clock64() - t0;
+    if (check == 0xffffffffu) cycles[1] = check;
+    __syncthreads();
+    cluster_sync();
+}
+
 // ping-pong between CTA 0 and CTA 1 of a cluster: the latency of one bulk-copy hand-off
 __global__ void __launch_bounds__(32, 1) pingpong_kernel(int bytes, int iters, long long* cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -125,8 +186,8 @@ __global__ void __launch_bounds__(32, 1) pingpong_kernel(int bytes, int iters, l
     cluster_sync();
 }
 
-template <typename K>
-static bool launch(K kern, int cs, int clusters, int threads, size_t smem, int bytes, int iters, long long* d_cycles) {
+template <typename K, typename... Extra>
+static bool launch(K kern, int cs, int clusters, int threads, size_t smem, long long* d_cycles, int bytes, int iters, Extra... extra) {
     CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     if (cs > 8) CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -143,7 +204,7 @@ static bool launch(K kern, int cs, int clusters, int threads, size_t smem, int b
         (void)cudaGetLastError();
         return false;
     }
-    CHECK(cudaLaunchKernelEx(&cfg, kern, bytes, iters, d_cycles));
+    CHECK(cudaLaunchKernelEx(&cfg, kern, bytes, iters, extra..., d_cycles));
     CHECK(cudaDeviceSynchronize());
     return true;
 }
@@ -154,7 +215,7 @@ int main() {
     int clk_khz = 0;
     CHECK(cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0));
     long long* d_cycles;
-    CHECK(cudaMalloc(&d_cycles, sizeof(long long)));
+    CHECK(cudaMalloc(&d_cycles, 2 * sizeof(long long)));
     const int iters = 4008;
     printf("{\"device\": \"%s\", \"sms\": %d, \"sm_clock_khz\": %d}\n", prop.name, prop.multiProcessorCount, clk_khz);
     const int css[] = {16, 8, 4};
@@ -165,7 +226,7 @@ int main() {
             for (int bytes : sizes) {
                 const size_t smem = static_cast<size_t>(2) * cs * bytes + bytes + 64 + 1024;
                 if (smem > 200 * 1024) continue;
-                if (!launch(allgather_kernel, cs, clusters, 256, smem, bytes, iters, d_cycles)) continue;
+                if (!launch(allgather_kernel, cs, clusters, 256, smem, d_cycles, bytes, iters)) continue;
                 long long cyc = 0;
                 CHECK(cudaMemcpy(&cyc, d_cycles, sizeof(cyc), cudaMemcpyDeviceToHost));
                 const double per = static_cast<double>(cyc) / (iters - 8);
@@ -176,9 +237,32 @@ int main() {
             }
         }
     }
+
+    // the same all-gather with per-lane remote stores (no bulk-copy engine)
+    for (int mode : {1, 2}) {
+        for (int cs : {16, 8}) {
+            for (int clusters : {4, 8}) {
+                if (cs * clusters > prop.multiProcessorCount) continue;
+                for (int bytes : {256, 512, 1024}) {
+                    for (int sw : {1, 2, 4, 8}) {
+                        const size_t smem = static_cast<size_t>(2) * cs * bytes + bytes + 64 + 1024;
+                        const bool ok = mode == 1 ? launch(allgather_st_kernel<1>, cs, clusters, 256, smem, d_cycles, bytes, iters, sw)
+                                                  : launch(allgather_st_kernel<2>, cs, clusters, 256, smem, d_cycles, bytes, iters, sw);
+                        if (!ok) continue;
+                        long long cyc = 0;
+                        CHECK(cudaMemcpy(&cyc, d_cycles, sizeof(cyc), cudaMemcpyDeviceToHost));
+                        const double per = static_cast<double>(cyc) / (iters - 8);
+                        printf("{\"mode\": \"%s\", \"cluster\": %d, \"clusters_resident\": %d, \"bytes_per_peer\": %d, \"send_warps\": %d, "
+                               "\"cycles_per_exchange\": %.1f}\n", mode == 1 ? "allgather_st_async" : "allgather_st_arrive", cs, clusters,
+                               bytes, sw, per);
+                    }
+                }
+            }
+        }
+    }
     for (int bytes : {16, 512, 1024}) {
         const size_t smem = static_cast<size_t>(2) * bytes + 64 + 1024;
-        if (!launch(pingpong_kernel, 2, 1, 32, smem, bytes, 2000, d_cycles)) continue;
+        if (!launch(pingpong_kernel, 2, 1, 32, smem, d_cycles, bytes, 2000)) continue;
         long long cyc = 0;
         CHECK(cudaMemcpy(&cyc, d_cycles, sizeof(cyc), cudaMemcpyDeviceToHost));
         printf("{\"mode\": \"pingpong\", \"bytes\": %d, \"cycles_one_way\": %.1f}\n", bytes, static_cast<double>(cyc) / 2000 / 2);
