@@ -181,6 +181,32 @@ __device__ __forceinline__ void load_partial_sums(uint32_t taddr, int acc_stride
 // (g, -, -, -); unused slots carry zero weights (some idle tensor-core work for a configuration option, no extra code paths).
 enum { CELL_LSTM = 0, CELL_GRU = 1, CELL_RNN = 2 };
 
+// ------------------------------------------------------------------------------------------------
+// Order of the per-step all-gather inside a cluster. A bulk DSMEM copy costs ~33 cycles of the SM's copy engine on top of a
+// ~315-cycle hand-off (tools/dsmem_bench.cu), so the 16 copies of a CTA leave over ~500 cycles. If every CTA served its peers in
+// the same order, all blocks addressed to one receiver would land together — early for some receivers, last for others — and
+// the MMA chain of the slowest receiver would start only after the whole exchange. Instead the CTAs are paired (pair a = CTAs
+// 2a, 2a+1 = the two 32-unit blocks of K block a) and sender (a, b) serves receiver pair (a + i) mod P in slot i: every receiver
+// gets exactly one K block (two copies) per slot, the MMA warps wait per K block (one mbarrier each) and multiply each K block
+// as it lands; the chain ends one K block after the last arrival instead of a whole chain after it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pin_reg(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void pin_reg(uint32_t& x) { asm volatile("" : "+r"(x)); }
+constexpr int MAX_KB = 8;   // K blocks of 64 units in a one-cluster kernel (H <= 512)
+__device__ __forceinline__ uint32_t exchange_peer(int me, int pos, int ctas, int rot) {   // pos-th destination of CTA `me`
+    if (!rot) return static_cast<uint32_t>(pos);   // every CTA serves the peers in the same order (A/B: CTCB200_LSTM_ORDER=fixed)
+    const int pairs = ctas >> 1;
+    int c = (me >> 1) + (pos >> 1);
+    if (c >= pairs) c -= pairs;
+    return static_cast<uint32_t>(2 * c + ((me ^ pos) & 1));
+}
+__device__ __forceinline__ int arrival_kblock(int me, int it, int kblocks, int rot) {     // K block that lands it-th at CTA `me`
+    if (!rot) return it;
+    int kb = (me >> 1) - it;
+    if (kb < 0) kb += kblocks;
+    return kb;
+}
+
 struct FwdParams {
     const float* gx;          // [T*N, 8H] gate pre-activations from the input projection (packed column order)
     float* hout;              // [T*N, 2H] layer output (fwd | reverse)
@@ -194,6 +220,8 @@ struct FwdParams {
     const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (hi part): source of the TMEM-resident A operand
     int mma_split;            // number of warps (1, 2 or 4) that issue slices of the K chain into their own accumulator
     int act_approx;           // 1: gate non-linearities through tanh.approx (one MUFU op each)
+    int rot;                  // 1: rotated all-gather order (exchange_peer)
+    int kbbar;                // 1: one mbarrier per K block of the operand image, 0: one for the whole image
     int rnn_relu;             // CELL_RNN: 1 = nonlinearity='relu', 0 = 'tanh'
 };
 
@@ -232,9 +260,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
     uint4* sOut = reinterpret_cast<uint4*>(sS + 32 * S_STRIDE);      // BULK only: staging of this CTA's block [hi | lo]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (BULK ? PARTS * OUT_CHUNKS : 0));
     uint64_t* w_full = bars;
-    uint64_t* h_full = bars + 1;   // [2]: BULK -> the peers' blocks of a parity have landed; EX=0 -> [0] counts the local image copy
-    uint64_t* acc_full = bars + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* acc_full = bars + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    // BULK: h_full[parity][kb] -> the two 32-unit blocks of K block kb (64 units) have landed: the MMA chain starts on the first
+    // K block that arrives instead of waiting for all of them (see exchange_peer). EX=0: [0] counts the local image copy
+    uint64_t* h_full = bars + 4;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
@@ -244,13 +274,12 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
     if (tid == 0) {
         if constexpr (X3) tma_prefetch_desc(&tmWlo);
         mbar_init(w_full, 1);
-        mbar_init(&h_full[0], BULK ? 1 : LSTM_THREADS);
-        mbar_init(&h_full[1], BULK ? 1 : LSTM_THREADS);
+        for (int i = 0; i < 2 * MAX_KB; ++i) mbar_init(&h_full[i], BULK ? 1 : LSTM_THREADS);
         mbar_init(acc_full, p.mma_split);
         fence_mbar_init();
-        if constexpr (BULK) {  // arm both parities: each expects one block from every CTA of the cluster
-            mbar_expect_tx(&h_full[0], ctas * BLK_STRIDE);
-            mbar_expect_tx(&h_full[1], ctas * BLK_STRIDE);
+        if constexpr (BULK) {  // arm both parities: every K block expects the blocks of its two source CTAs
+            for (int i = 0; i < 2 * MAX_KB; ++i)
+                if (p.kbbar || (i % MAX_KB) == 0) mbar_expect_tx(&h_full[i], (p.kbbar ? 2 : ctas) * BLK_STRIDE);
         }
     }
     // TMEM: up to four accumulators in columns [0, 64), the W_hi slice (A operand) in columns [64, 64 + H/2)
@@ -323,14 +352,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
         // arithmetic so the descriptors live in uniform registers, one elected lane issues each tcgen05.mma
         if (warp < p.mma_split) {
             if constexpr (X3) { if (t == 0) mbar_wait(w_full, 0); }
-            if constexpr (BULK) {
-                if (t > 0) {
-                    mbar_wait(&h_full[t & 1], ((t - 1) >> 1) & 1);                // every peer's block has landed
-                    if (lane == 0 && warp == 0) mbar_expect_tx(&h_full[t & 1], ctas * BLK_STRIDE);  // re-arm for step t+2
-                }
-            } else {
-                mbar_wait(&h_full[0], t & 1);
-            }
+            if constexpr (!BULK) mbar_wait(&h_full[0], t & 1);
+            // ONE fence per step: it orders this step's first (overwriting) MMA after the tcgen05.ld of the previous step's
+            // accumulators (this warp took part in that step's CTA barriers). A fence per K block would make the warp wait for
+            // its own MMAs in flight
             tc_fence_after();
             TRACE(1);
             const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sH) + (BULK ? (t & 1) * himg_bytes : 0);
@@ -340,12 +365,27 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
             constexpr uint32_t B2 = BLK_STRIDE / 16;   // descriptor step to the second 32-unit block of a 64-wide K block
             constexpr uint32_t LO = BLK_BYTES / 16;    // descriptor step from a block's hi part to its lo part
 #pragma unroll 1
-            for (int kb = kfirst; kb < kblocks; kb += kstep) {
+            for (int it = kfirst; it < kblocks; it += kstep) {
+                // BULK: K blocks in their arrival order at this CTA (the peers send in rotated order, exchange_peer)
+                const int kb = BULK ? arrival_kblock(j, it, kblocks, p.rot) : it;
+                if constexpr (BULK) {
+                    if (t > 0) {
+                        if (p.kbbar) {
+                            uint64_t* hf = &h_full[(t & 1) * MAX_KB + kb];
+                            mbar_wait(hf, ((t - 1) >> 1) & 1);                    // both source blocks of this K block have landed
+                            if (lane == 0) mbar_expect_tx(hf, 2 * BLK_STRIDE);    // re-arm for step t + 2 (this warp owns kb)
+                        } else if (it == kfirst) {
+                            uint64_t* hf = &h_full[(t & 1) * MAX_KB];
+                            mbar_wait(hf, ((t - 1) >> 1) & 1);                    // every peer's block has landed
+                            if (lane == 0 && warp == 0) mbar_expect_tx(hf, ctas * BLK_STRIDE);
+                        }
+                    }
+                }
                 // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
                 const uint64_t bd = umma_desc_sw64(b0 + kb * (2 * BLK_STRIDE));
                 const uint32_t ta = tmem_base + 64 + kb * 32;
                 if (leader) {
-                    umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
+                    umma_bf16_ts(dacc, ta, bd, idesc, it != kfirst ? 1u : 0u);
                     umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
                     umma_bf16_ts(dacc, ta + 16, bd + B2, idesc, 1u);
                     umma_bf16_ts(dacc, ta + 24, bd + B2 + 2, idesc, 1u);
@@ -459,12 +499,13 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
                 // one bulk copy per peer (our contiguous block -> slot j of the peer's next operand buffer); warp w
                 // serves peers w and w + 8 so the copies are issued in parallel with warp-uniform operands
                 const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_STRIDE;
-                const uint32_t bar = smem_u32(&h_full[(t + 1) & 1]);
+                const uint32_t bar = smem_u32(&h_full[((t + 1) & 1) * MAX_KB + (p.kbbar ? (j >> 1) : 0)]);
 #pragma unroll
-                for (int d = warp; d < 16; d += 8) {
-                    if (d < ctas && warp_leader)
-                        bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), smem_u32(sOut), BLK_STRIDE,
-                                          mapa_shared(bar, static_cast<uint32_t>(d)));
+                for (int pos = warp; pos < 16; pos += 8) {
+                    if (pos < ctas && warp_leader) {
+                        const uint32_t d = exchange_peer(j, pos, ctas, p.rot);
+                        bulk_copy_to_peer(mapa_shared(dst, d), smem_u32(sOut), BLK_STRIDE, mapa_shared(bar, d));
+                    }
                 }
                 if (warp_leader) bulk_commit();
             }
@@ -524,11 +565,11 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
     uint8_t* sOut = sH + 2 * himg_bytes;                                    // [2 halves][2 parities][HALF_BYTES] staging
     float* sGx = reinterpret_cast<float*>(sOut + 4 * HALF_BYTES);           // [4 stages][8 batch rows][128 gate rows] (TMA boxes)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sGx + 4 * HB * 128);
-    uint64_t* h_full = bars;          // [half][parity]: every peer's half block of h_{t-1} has landed
-    uint64_t* acc_full = bars + 4;    // [half]: the four partial accumulators of a half-step are complete
-    uint64_t* so_ready = bars + 6;    // [half]: all element warps have staged their part of h_t
-    uint64_t* gx_full = bars + 8;     // [4 stages]: the input-projection box of a half-step has landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* acc_full = bars;        // [half]: the four partial accumulators of a half-step are complete
+    uint64_t* so_ready = bars + 2;    // [half]: all element warps have staged their part of h_t
+    uint64_t* gx_full = bars + 4;     // [4 stages]: the input-projection box of a half-step has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* h_full = bars + 10;     // [half][parity][kb]: the two half blocks of K block kb of h_{t-1} have landed (exchange_peer)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
@@ -536,7 +577,7 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
     const int kblocks = H / 64;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&h_full[i], 1);
+        for (int i = 0; i < 4 * MAX_KB; ++i) mbar_init(&h_full[i], 1);
         mbar_init(&acc_full[0], 4);
         mbar_init(&acc_full[1], 4);
         mbar_init(&so_ready[0], 8);
@@ -544,7 +585,8 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
         for (int i = 0; i < 4; ++i) mbar_init(&gx_full[i], 1);
         tma_prefetch_desc(&tmGx);
         fence_mbar_init();
-        for (int i = 0; i < 4; ++i) mbar_expect_tx(&h_full[i], ctas * HALF_BYTES);
+        for (int i = 0; i < 4 * MAX_KB; ++i)
+            if (p.kbbar || (i % MAX_KB) == 0) mbar_expect_tx(&h_full[i], (p.kbbar ? 2 : ctas) * HALF_BYTES);
     }
     uint32_t tmem_cols = 256;
     while (tmem_cols < ACC_COLS + H / 2) tmem_cols <<= 1;
@@ -586,13 +628,13 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
                 mbar_wait(&so_ready[half], t & 1);
                 if (warp == 12 && half == 0) PTRACE(10);
                 if (warp == 12 && lane == 0 && 2 * t + half + 4 < 2 * T) fetch_gx(2 * t + half + 4);  // its stage was read in this half-step
-                const int d = (warp - 12) * 4 + lane;
-                if (lane < 4 && d < ctas) {
+                const int pos = (warp - 12) + 4 * lane;   // the four warps take consecutive slots of the rotated order
+                if (lane < 4 && pos < ctas) {
+                    const uint32_t d = exchange_peer(j, pos, ctas, p.rot);
                     const uint32_t src = smem_u32(sOut + (half * 2 + (t & 1)) * HALF_BYTES);
                     const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_BYTES + half * HALF_BYTES;
-                    const uint32_t bar = smem_u32(&h_full[half * 2 + ((t + 1) & 1)]);
-                    bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), src, HALF_BYTES,
-                                      mapa_shared(bar, static_cast<uint32_t>(d)));
+                    const uint32_t bar = smem_u32(&h_full[(half * 2 + ((t + 1) & 1)) * MAX_KB + (p.kbbar ? (j >> 1) : 0)]);
+                    bulk_copy_to_peer(mapa_shared(dst, d), src, HALF_BYTES, mapa_shared(bar, d));
                 }
                 __syncwarp();
                 if (warp == 12 && half == 0) PTRACE(11);
@@ -605,26 +647,37 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
         for (int t = 0; t < T; ++t) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                uint64_t* hf = &h_full[half * 2 + (t & 1)];
-                if (t > 0) {
-                    mbar_wait(hf, ((t - 1) >> 1) & 1);                       // every peer's half block has landed
-                    if (m == 0 && lane == 0) mbar_expect_tx(hf, ctas * HALF_BYTES);   // re-arm for step t + 2
-                }
-                tc_fence_after();
+                uint64_t* hf = &h_full[(half * 2 + (t & 1)) * MAX_KB];
                 if (m == 0) PTRACE(12 + 2 * half);
                 const uint32_t b0 = smem_u32(sH) + (t & 1) * himg_bytes;
                 const uint32_t dacc = tmem_base + half * 64 + m * NB;
+                // This CTA's own half block travels through the exchange like the others (K block j/2, the first to arrive in
+                // the rotated order): its landing implies that the element warps have finished reading the accumulators of the
+                // previous step, which this step's first MMA overwrites -> every issuing warp waits for it, then ONE fence
+                // (a fence per K block would make the warp wait for its own MMAs in flight)
+                if (t > 0) {
+                    mbar_wait(&hf[p.kbbar ? (j >> 1) : 0], ((t - 1) >> 1) & 1);
+                    if (!p.kbbar && m == 0 && lane == 0) mbar_expect_tx(&hf[0], ctas * HALF_BYTES);   // re-arm for step t + 2
+                }
+                tc_fence_after();
 #pragma unroll 1
-                for (int kb = m; kb < kblocks; kb += 4) {
+                for (int it = m; it < kblocks; it += 4) {
+                    const int kb = arrival_kblock(j, it, kblocks, p.rot);               // K blocks in their arrival order
+                    if (t > 0 && p.kbbar) {
+                        mbar_wait(&hf[kb], ((t - 1) >> 1) & 1);                  // both half blocks of this K block have landed
+                        if (lane == 0) mbar_expect_tx(&hf[kb], 2 * HALF_BYTES);  // re-arm for step t + 2 (this warp owns kb)
+                    }
                     const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
                     const uint32_t ta = tmem_base + ACC_COLS + kb * 32;
                     if (leader) {
-                        umma_bf16_ts(dacc, ta, bd, idesc, kb != m ? 1u : 0u);
+                        umma_bf16_ts(dacc, ta, bd, idesc, it != m ? 1u : 0u);
                         umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
                         umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
                         umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
+                if (m >= kblocks && t > 0 && p.kbbar)   // H = 128: no K block for this warp; it still paces itself on the exchange (no re-arm:
+                    mbar_wait(&hf[arrival_kblock(j, kblocks - 1, kblocks, p.rot)], ((t - 1) >> 1) & 1);   // the owner does that)
                 if (leader) umma_commit(&acc_full[half]);
                 __syncwarp();
                 if (m == 0) PTRACE(13 + 2 * half);
@@ -730,6 +783,10 @@ struct BwdParams {
     int T, N, H, groups, n0;
     const __nv_bfloat16* w;    // packed transposed recurrent weights [8H, H] (hi part)
     int mma_split;
+    int rot;                   // 1: rotated all-gather order (exchange_peer)
+    int kbbar;                 // 1: one mbarrier per K block of the operand image, 0: one for the whole image
+    int rs_merge;              // 1: one reduce-scatter copy per destination CTA instead of one per warp
+    long long* trace;          // optional [T][16] clock64 stamps of CTA 0 / thread 0 (CTCB200_LSTM_TRACE)
     unsigned int* resident;    // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
     const float* bn_x;         // optional: layer output [T*N, 2H]; the BatchNorm backward of the layer above is applied to
     const float* bn_coef;      // dhout on the fly: dh = coef[0][c]*dhout + coef[1][c]*bn_x + coef[2][c], coef f32 [3][2H]
@@ -790,10 +847,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
     float* sP = reinterpret_cast<float*>(sOut + (BULK ? 4 * PARTS * OUT_CHUNKS : 0));  // BULK only: [4 dst][NB][32] partial staging
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (BULK ? 4 * NB * 32 : 0));
     uint64_t* w_full = bars;
-    uint64_t* b_full = bars + 1;   // [2]
-    uint64_t* acc_full = bars + 3;
-    uint64_t* r_full = bars + 4;   // BULK: the 4 partial blocks of a step have landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* acc_full = bars + 1;
+    uint64_t* r_full = bars + 2;   // BULK: the 4 partial blocks of a step have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* b_full = bars + 4;   // BULK: [parity][kb], one barrier per K block of the dG image (see exchange_peer); else [0]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     announce_resident(p.resident);
@@ -809,14 +866,13 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
     if (tid == 0) {
         if constexpr (X3) tma_prefetch_desc(&tmWTlo);
         mbar_init(w_full, 1);
-        mbar_init(&b_full[0], BULK ? 1 : LSTM_THREADS);
-        mbar_init(&b_full[1], BULK ? 1 : LSTM_THREADS);
+        for (int i = 0; i < 2 * MAX_KB; ++i) mbar_init(&b_full[i], BULK ? 1 : LSTM_THREADS);
         mbar_init(acc_full, p.mma_split);
         mbar_init(r_full, 1);
         fence_mbar_init();
         if constexpr (BULK) {
-            mbar_expect_tx(&b_full[0], ctas * BLK_STRIDE);
-            mbar_expect_tx(&b_full[1], ctas * BLK_STRIDE);
+            for (int i = 0; i < 2 * MAX_KB; ++i)
+                if (p.kbbar || (i % MAX_KB) == 0) mbar_expect_tx(&b_full[i], (p.kbbar ? 2 : ctas) * BLK_STRIDE);
             mbar_expect_tx(r_full, 4 * NB * 32 * PART_BYTES);  // four gate partials of [NB][32] values per step
         }
     }
@@ -864,8 +920,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
 #pragma unroll
     for (int e = 0; e < EPT; ++e) dc_carry[e] = 0.0f;
 
+#define BTRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) p.trace[t * 16 + (k)] = clock64(); } while (0)
     for (int t = 0; t < T; ++t) {
         const int tt = dir ? t : (T - 1 - t);          // reverse of the forward scan order
+        BTRACE(0);
         const int tprev = dir ? tt + 1 : tt - 1;       // time index that held c_{prev} in the forward scan
         const bool has_prev = dir ? (tt + 1 < T) : (tt >= 1);
         // (1) saved activations and the incoming gradient for this thread's elements
@@ -902,27 +960,36 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
         // (4) partial dh[128 units, NB] = W_q^T slice * dG_q (issued like the forward kernel's chain)
         if (warp < p.mma_split) {
             if constexpr (X3) { if (t == 0) mbar_wait(w_full, 0); }
-            if constexpr (BULK) {
-                if (t > 0) {
-                    mbar_wait(&b_full[t & 1], ((t - 1) >> 1) & 1);
-                    if (lane == 0 && warp == 0) mbar_expect_tx(&b_full[t & 1], ctas * BLK_STRIDE);
-                }
-            } else {
-                mbar_wait(&b_full[0], t & 1);
-            }
-            tc_fence_after();
+            if constexpr (!BULK) mbar_wait(&b_full[0], t & 1);
+            tc_fence_after();   // one fence per step (see the forward kernel)
             const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sB) + (BULK ? (t & 1) * img_bytes : 0);
             const bool leader = elect_one();
             const int kstep = p.mma_split, kfirst = warp;
             const uint32_t dacc = tmem_base + warp * NB;
             constexpr uint32_t B2 = BLK_STRIDE / 16, LO = BLK_BYTES / 16;
+            const int my_rank = q + 4 * mb;
 #pragma unroll 1
-            for (int kb = kfirst; kb < kblocks; kb += kstep) {
+            for (int it = kfirst; it < kblocks; it += kstep) {
+                const int kb = BULK ? arrival_kblock(my_rank, it, kblocks, p.rot) : it;   // K blocks in their arrival order
+                if constexpr (BULK) {
+                    if (t > 0) {
+                        if (p.kbbar) {
+                            uint64_t* bf = &b_full[(t & 1) * MAX_KB + kb];
+                            mbar_wait(bf, ((t - 1) >> 1) & 1);                    // both source blocks of this K block have landed
+                            if (lane == 0) mbar_expect_tx(bf, 2 * BLK_STRIDE);    // re-arm for step t + 2 (this warp owns kb)
+                        } else if (it == kfirst) {
+                            uint64_t* bf = &b_full[(t & 1) * MAX_KB];
+                            mbar_wait(bf, ((t - 1) >> 1) & 1);                    // every source block has landed
+                            if (lane == 0 && warp == 0) mbar_expect_tx(bf, ctas * BLK_STRIDE);
+                        }
+                    }
+                    if (it == kfirst) BTRACE(1);
+                }
                 // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
                 const uint64_t bd = umma_desc_sw64(b0 + kb * (2 * BLK_STRIDE));
                 const uint32_t ta = tmem_base + 64 + kb * 32;
                 if (leader) {
-                    umma_bf16_ts(dacc, ta, bd, idesc, kb != kfirst ? 1u : 0u);
+                    umma_bf16_ts(dacc, ta, bd, idesc, it != kfirst ? 1u : 0u);
                     umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
                     umma_bf16_ts(dacc, ta + 16, bd + B2, idesc, 1u);
                     umma_bf16_ts(dacc, ta + 24, bd + B2 + 2, idesc, 1u);
@@ -942,14 +1009,17 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 }
             }
             if (leader) umma_commit(acc_full);
+            BTRACE(2);
         }
         __syncwarp();
         // (5) scatter the partial rows to their owner CTA through distributed shared memory
         mbar_wait(acc_full, t & 1);
         tc_fence_after();
+        BTRACE(3);
         uint32_t acc[CPT];
         load_partial_sums<CPT>(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + ch * CPT, NB, p.mma_split, acc);
         tc_fence_before();
+        BTRACE(4);
         if constexpr (BULK) {
             // every warp holds the [NB/2][32] sub-block of partial rows that belongs to CTA (lq, mb): stage it, then
             // one bulk copy per warp into that CTA's receive slot for source gate q (complete_tx on its r_full)
@@ -967,14 +1037,28 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 for (int c = 0; c < CPT; ++c) stage[c * 32] = __float2half_rn(__uint_as_float(acc[c]));
             }
             fence_proxy_async_smem();
-            __syncwarp();
-            if (warp_leader) {
-                const uint32_t peer = rank_of(lq, mb);
-                bulk_copy_to_peer(mapa_shared(smem_u32(sR) + re * PART_BYTES, peer), smem_u32(sP) + pe * PART_BYTES,
-                                  CPT * 32 * PART_BYTES, mapa_shared(smem_u32(r_full), peer));
-                bulk_commit();
+            // the two warps that hold the halves (ch = 0, 1) of the block for CTA (lq, mb) meet on a named barrier and send it as
+            // ONE copy: a copy costs the engine ~33 cycles whatever its size, and these are on the step's critical path
+            if (p.rs_merge) {
+                named_bar_sync(1 + lq, 64);
+                if (ch == 0 && warp_leader) {
+                    const uint32_t peer = rank_of(lq, mb);
+                    bulk_copy_to_peer(mapa_shared(smem_u32(sR) + re * PART_BYTES, peer), smem_u32(sP) + pe * PART_BYTES,
+                                      NB * 32 * PART_BYTES, mapa_shared(smem_u32(r_full), peer));
+                    bulk_commit();
+                }
+            } else {
+                __syncwarp();
+                if (warp_leader) {
+                    const uint32_t peer = rank_of(lq, mb);
+                    bulk_copy_to_peer(mapa_shared(smem_u32(sR) + re * PART_BYTES, peer), smem_u32(sP) + pe * PART_BYTES,
+                                      CPT * 32 * PART_BYTES, mapa_shared(smem_u32(r_full), peer));
+                    bulk_commit();
+                }
             }
+            BTRACE(5);
             mbar_wait(r_full, t & 1);
+            BTRACE(6);
             if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * PART_BYTES);  // re-arm for the next step
         } else {
 #pragma unroll
@@ -982,6 +1066,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
             cluster_sync_all();
         }
         // (6) finish 32 units: recurrent dh, LSTM cell backward, publish the four gate gradients
+        // The values prefetched in (1) are passed through an empty volatile asm here: volatile asms keep their order, so no
+        // arithmetic on them can be scheduled above the waits of (4)/(5) (ptxas otherwise hoists e.g. the tanh of c_t in front
+        // of the MMA issue, and the issuing warps then stall on the global load every step: +15 % step time when it happens)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            pin_reg(dh_in[e]); pin_reg(bx_in[e]); pin_reg(c_t[e]); pin_reg(c_p[e]);
+            if constexpr (X3) { pin_reg(gts32[e].x); pin_reg(gts32[e].y); pin_reg(gts32[e].z); pin_reg(gts32[e].w); }
+            else { pin_reg(gts16[e].x); pin_reg(gts16[e].y); }
+        }
         uint2 dgp[EPT], dgl[EPT];
         uint2 dgr[CELL == CELL_GRU ? EPT : 1], dgrl[CELL == CELL_GRU ? EPT : 1];   // GRU: input-side gate gradients (see below)
 #pragma unroll
@@ -1073,25 +1166,29 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 dgl[e] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
             }
         }
+        BTRACE(7);
         if constexpr (BULK) {
             fence_proxy_async_smem();
             __syncthreads();
+            BTRACE(8);
             if (t + 1 < T) {
                 // copy i = (g, mdst): gate g's block [hi | lo] of this CTA's 32 units -> slot (4 mb + q) of CTA (g, mdst)'s
                 // buffer; warp w issues copies w and w + 8
-                const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + (4 * mb + q) * BLK_STRIDE;
-                const uint32_t bar = smem_u32(&b_full[(t + 1) & 1]);
+                const int me = 4 * mb + q;   // = this CTA's rank in the cluster = its slot in every receiver's image
+                const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + me * BLK_STRIDE;
+                const uint32_t bar = smem_u32(&b_full[((t + 1) & 1) * MAX_KB + (p.kbbar ? (me >> 1) : 0)]);
 #pragma unroll
-                for (int i = warp; i < 16; i += 8) {
-                    const int g = i & 3, mdst = i >> 2;
-                    if (mdst < MB && warp_leader) {
-                        const uint32_t peer = rank_of(g, mdst);
+                for (int pos = warp; pos < 16; pos += 8) {
+                    if (pos < ctas && warp_leader) {
+                        const uint32_t peer = exchange_peer(me, pos, ctas, p.rot);   // rank = gate + 4 * unit block: it gets its gate's block
+                        const int g = peer & 3;
                         bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * PARTS * OUT_CHUNKS), BLK_STRIDE,
                                           mapa_shared(bar, peer));
                     }
                 }
                 if (warp_leader) bulk_commit();
             }
+            BTRACE(9);
         } else {
             __threadfence();
             __syncthreads();
@@ -1483,6 +1580,13 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         }
         uint2 dgp[2][EPT];
 #pragma unroll
+        for (int hf = 0; hf < 2; ++hf)   // keep all arithmetic on the prefetched values below the waits (see lstm_bwd_kernel)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                pin_reg(dh_in[hf][e]); pin_reg(bx_in[hf][e]); pin_reg(c_t[hf][e]); pin_reg(c_p[hf][e]);
+                pin_reg(gts[hf][e].x); pin_reg(gts[hf][e].y);
+            }
+#pragma unroll
         for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
@@ -1563,13 +1667,28 @@ int mma_issuers(int NB, int H) {
     return n < 1 ? 1 : n;
 }
 
+// A/B switches for the exchange schedule (defaults = measured best)
+int exchange_rotated() {
+    const char* e = getenv("CTCB200_LSTM_ORDER");
+    return (e != nullptr && e[0] == 'f') ? 0 : 1;    // "fixed": every CTA serves its peers in the same order
+}
+int kblock_barriers(bool x3) {   // per-K-block mbarriers: the MMA chain starts on the first K block that lands
+    const char* e = getenv("CTCB200_LSTM_KBBAR");
+    if (e != nullptr) return e[0] == '0' ? 0 : 1;
+    return x3 ? 1 : 0;
+}
+int rs_merged() {
+    const char* e = getenv("CTCB200_LSTM_RS_MERGE");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
+
 size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool x3) {
     const bool bulk = ex == 3;
     const size_t parts = x3 ? 2 : 1;
     size_t b = (x3 ? static_cast<size_t>(128) * H * 2 : 0) + static_cast<size_t>(bulk ? 2 : 1) * H * NB * 2 * parts;
     if (bwd) b += static_cast<size_t>(4) * NB * 32 * 4 + (bulk ? static_cast<size_t>(4) * parts * NB * 4 * 16 + static_cast<size_t>(4) * NB * 32 * 4 : 0);
     else b += static_cast<size_t>(32) * (NB * 4 + 4) * 4 + (bulk ? parts * NB * 4 * 16 : 0);
-    return b + 64 + 1024;
+    return b + 256 + 1024;
 }
 
 // How the CTAs of one (direction, batch group) hand h_t / dG_t to each other every step:
@@ -1760,6 +1879,28 @@ struct FwdTraceDump {
     }
 };
 
+struct BwdTraceDump {
+    const BwdParams& p; cudaStream_t s;
+    ~BwdTraceDump() {
+        if (!p.trace) return;
+        cudaStreamSynchronize(s);
+        const int T = p.T;
+        long long* h = static_cast<long long*>(malloc(sizeof(long long) * 16 * T));
+        cudaMemcpy(h, p.trace, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost);
+        double rel[10] = {0}, tot = 0;
+        int cnt = 0;
+        for (int t = 8; t + 1 < T; ++t, ++cnt) {
+            for (int k = 0; k < 10; ++k) rel[k] += double(h[t * 16 + k] - h[t * 16]);
+            tot += double(h[(t + 1) * 16] - h[t * 16]);
+        }
+        fprintf(stderr, "lstm_bwd trace (CTA 0 thread 0, cycles after the step start, avg over %d steps): step %.0f | first K block landed "
+                "%.0f, MMAs issued %.0f, acc ready %.0f, tcgen05.ld done %.0f, partials staged + reduce-scatter issued %.0f, partials "
+                "landed %.0f, element phase done %.0f, CTA barrier %.0f, all-gather issued %.0f\n", cnt, tot / cnt, rel[1] / cnt,
+                rel[2] / cnt, rel[3] / cnt, rel[4] / cnt, rel[5] / cnt, rel[6] / cnt, rel[7] / cnt, rel[8] / cnt, rel[9] / cnt);
+        free(h);
+    }
+};
+
 }  // namespace
 }  // namespace ctcb200
 
@@ -1809,7 +1950,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         const size_t smem2 = static_cast<size_t>(128) * H * 2 + static_cast<size_t>(2) * H * NB2 * 2 +
                              static_cast<size_t>(2) * 32 * (NB2 * 4 + 4) * 4 + static_cast<size_t>(2) * NB2 * 4 * 16 + 64 + 1024;
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
-        p.mma_split = 4; p.groups = groups2;
+        p.mma_split = 4; p.rot = 0; p.kbbar = 0; p.groups = groups2;
         if (cluster_ok(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2))
             return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p,
                                     stream);
@@ -1834,6 +1975,8 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         p.act_approx = (!x3 && plain && act != nullptr && act[0] == 'a') ? 1 : 0;
     }
     p.mma_split = mma_issuers(NB, H);
+    p.rot = exchange_rotated();
+    p.kbbar = kblock_barriers(x3);
     p.groups = groups_total;
     if (getenv("CTCB200_LSTM_TRACE")) {
         static long long* dbuf = nullptr;
@@ -1848,7 +1991,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         trace_dump.pipe = true;
         // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core warps
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
-        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 4 * 512 + 4 * 8 * 128 * 4 + 128 + 1024;
+        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 4 * 512 + 4 * 8 * 128 * 4 + 512 + 1024;
         CUtensorMap tmGx;   // gate pre-activations as a 2-D f32 tensor [T*N rows, 8H columns], boxes of 8 rows x 128 columns
         rc = make_tmap_f32_2d(&tmGx, gx, static_cast<uint64_t>(T) * N, static_cast<uint64_t>(8) * H, static_cast<uint64_t>(8) * H, 8, 128);
         if (rc == OK && cluster_ok(lstm_fwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS))
@@ -1904,7 +2047,8 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     p.dg = static_cast<__nv_bfloat16*>(dg); p.dg_lo = static_cast<__nv_bfloat16*>(dg_lo);
     p.dg_rec = static_cast<__nv_bfloat16*>(dg_rec); p.dg_rec_lo = static_cast<__nv_bfloat16*>(dg_rec_lo);
     p.rnn_relu = cell == 3 ? 1 : 0;
-    p.dgimg = nullptr; p.flags = nullptr; p.resident = static_cast<unsigned int*>(resident_counter);
+    p.dgimg = nullptr; p.flags = nullptr; p.trace = nullptr; p.rot = 0; p.kbbar = 0; p.rs_merge = 0;
+    p.resident = static_cast<unsigned int*>(resident_counter);
     p.bn_x = bn_x; p.bn_coef = bn_coef;
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed);
     p.T = T; p.N = N; p.H = H; p.n0 = 0;
@@ -1917,7 +2061,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         const size_t smem2 = static_cast<size_t>(128) * (H - 256) * 2 + static_cast<size_t>(4) * H * NB2 * 2 +
                              static_cast<size_t>(4) * NB2 * 32 * 4 * 2 + static_cast<size_t>(8) * NB2 * 4 * 16 + 64 + 1024;
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
-        p.mma_split = 4; p.groups = groups2;
+        p.mma_split = 4; p.rot = 0; p.kbbar = 0; p.groups = groups2;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
             return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false,
                                     tmWT2, p, stream, LSTM_THREADS, start_ev);
@@ -1939,7 +2083,19 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     const size_t smem = lstm_smem_bytes(NB, H, true, ex, x3);
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
     p.mma_split = mma_issuers(NB, H);
+    p.rot = exchange_rotated();
+    p.kbbar = kblock_barriers(x3);
+    p.rs_merge = rs_merged();
     p.groups = groups_total;
+    if (getenv("CTCB200_LSTM_TRACE")) {
+        static long long* dbuf = nullptr;
+        if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
+        if (T <= 4096) {
+            CTCB_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 16 * T, stream));
+            p.trace = dbuf;
+        }
+    }
+    BwdTraceDump trace_dump{p, stream};
     if (cl) {
         dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
         return launch_clustered(bwd_kernel(NB, ex, x3, cell_k), grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
