@@ -182,30 +182,31 @@ __device__ __forceinline__ void load_partial_sums(uint32_t taddr, int acc_stride
 enum { CELL_LSTM = 0, CELL_GRU = 1, CELL_RNN = 2 };
 
 // ------------------------------------------------------------------------------------------------
-// Order of the per-step all-gather inside a cluster. A bulk DSMEM copy costs ~33 cycles of the SM's copy engine on top of a
-// ~315-cycle hand-off (tools/dsmem_bench.cu), so the 16 copies of a CTA leave over ~500 cycles. If every CTA served its peers in
-// the same order, all blocks addressed to one receiver would land together — early for some receivers, last for others — and
-// the MMA chain of the slowest receiver would start only after the whole exchange. Instead the CTAs are paired (pair a = CTAs
-// 2a, 2a+1 = the two 32-unit blocks of K block a) and sender (a, b) serves receiver pair (a + i) mod P in slot i: every receiver
-// gets exactly one K block (two copies) per slot, the MMA warps wait per K block (one mbarrier each) and multiply each K block
-// as it lands; the chain ends one K block after the last arrival instead of a whole chain after it.
+// Split-operand (X3) kernels only: order of the per-step all-gather inside a cluster, and one mbarrier per K block.
+// A bulk DSMEM copy costs ~33 cycles of the SM's copy engine on top of a ~315-cycle hand-off (tools/dsmem_bench.cu). The x3
+// MMA chain is three times as long as the bf16 one (96 tcgen05.mma per step), so it pays to start it on the first K block that
+// lands: the CTAs are paired (pair a = CTAs 2a, 2a+1 = the two 32-unit blocks of K block a), sender (a, b) serves receiver pair
+// (a + i) mod P in slot i, every receiver gets one K block (two copies) per slot, and the issuing warps wait per K block.
+// Measured (cfg2 layer shape, ms per launch): x3 forward 2.39 -> 2.14, x3 BPTT 2.61 -> 2.45. The bf16 kernels keep ONE barrier
+// per operand image: with their short chain the extra waits cost more than the overlap returns (measured: BPTT 1.48 -> 1.7).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pin_reg(float& x) { asm volatile("" : "+f"(x)); }
-__device__ __forceinline__ void pin_reg(uint32_t& x) { asm volatile("" : "+r"(x)); }
 constexpr int MAX_KB = 8;   // K blocks of 64 units in a one-cluster kernel (H <= 512)
-__device__ __forceinline__ uint32_t exchange_peer(int me, int pos, int ctas, int rot) {   // pos-th destination of CTA `me`
-    if (!rot) return static_cast<uint32_t>(pos);   // every CTA serves the peers in the same order (A/B: CTCB200_LSTM_ORDER=fixed)
+__device__ __forceinline__ uint32_t exchange_peer(int me, int pos, int ctas) {   // pos-th destination of CTA `me`
     const int pairs = ctas >> 1;
     int c = (me >> 1) + (pos >> 1);
     if (c >= pairs) c -= pairs;
     return static_cast<uint32_t>(2 * c + ((me ^ pos) & 1));
 }
-__device__ __forceinline__ int arrival_kblock(int me, int it, int kblocks, int rot) {     // K block that lands it-th at CTA `me`
-    if (!rot) return it;
+__device__ __forceinline__ int arrival_kblock(int me, int it, int kblocks) {     // K block that lands it-th at CTA `me`
     int kb = (me >> 1) - it;
     if (kb < 0) kb += kblocks;
     return kb;
 }
+// Values prefetched from global memory at the top of a step go through an empty volatile asm where they are first used:
+// volatile asms keep their order, so no arithmetic on them can be scheduled above the mbarrier waits in between (ptxas otherwise
+// hoists e.g. the tanh of c_t in front of the MMA issue, and the issuing warps then stall on the global load every step).
+__device__ __forceinline__ void pin_reg(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void pin_reg(uint32_t& x) { asm volatile("" : "+r"(x)); }
 
 struct FwdParams {
     const float* gx;          // [T*N, 8H] gate pre-activations from the input projection (packed column order)
@@ -220,8 +221,6 @@ struct FwdParams {
     const __nv_bfloat16* w;   // packed recurrent weights [8H, H] (hi part): source of the TMEM-resident A operand
     int mma_split;            // number of warps (1, 2 or 4) that issue slices of the K chain into their own accumulator
     int act_approx;           // 1: gate non-linearities through tanh.approx (one MUFU op each)
-    int rot;                  // 1: rotated all-gather order (exchange_peer)
-    int kbbar;                // 1: one mbarrier per K block of the operand image, 0: one for the whole image
     int rnn_relu;             // CELL_RNN: 1 = nonlinearity='relu', 0 = 'tanh'
 };
 
@@ -262,8 +261,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
     uint64_t* w_full = bars;
     uint64_t* acc_full = bars + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-    // BULK: h_full[parity][kb] -> the two 32-unit blocks of K block kb (64 units) have landed: the MMA chain starts on the first
-    // K block that arrives instead of waiting for all of them (see exchange_peer). EX=0: [0] counts the local image copy
+    // h_full[parity * HB_STRIDE + kb]: BULK -> the peers' blocks of a parity have landed (X3: one barrier per K block kb, see
+    // exchange_peer; bf16: kb = 0 only); EX=0 -> [0] counts the local image copy
+    constexpr bool KBB = BULK && X3;
+    constexpr int HB_STRIDE = KBB ? MAX_KB : 1;
     uint64_t* h_full = bars + 4;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -274,12 +275,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
     if (tid == 0) {
         if constexpr (X3) tma_prefetch_desc(&tmWlo);
         mbar_init(w_full, 1);
-        for (int i = 0; i < 2 * MAX_KB; ++i) mbar_init(&h_full[i], BULK ? 1 : LSTM_THREADS);
+        for (int i = 0; i < 2 * HB_STRIDE; ++i) mbar_init(&h_full[i], BULK ? 1 : LSTM_THREADS);
         mbar_init(acc_full, p.mma_split);
         fence_mbar_init();
-        if constexpr (BULK) {  // arm both parities: every K block expects the blocks of its two source CTAs
-            for (int i = 0; i < 2 * MAX_KB; ++i)
-                if (p.kbbar || (i % MAX_KB) == 0) mbar_expect_tx(&h_full[i], (p.kbbar ? 2 : ctas) * BLK_STRIDE);
+        if constexpr (BULK) {  // arm both parities: each expects one block from every CTA of the cluster (two per K block)
+            for (int i = 0; i < 2 * HB_STRIDE; ++i) mbar_expect_tx(&h_full[i], (KBB ? 2 : ctas) * BLK_STRIDE);
         }
     }
     // TMEM: up to four accumulators in columns [0, 64), the W_hi slice (A operand) in columns [64, 64 + H/2)
@@ -352,10 +352,16 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
         // arithmetic so the descriptors live in uniform registers, one elected lane issues each tcgen05.mma
         if (warp < p.mma_split) {
             if constexpr (X3) { if (t == 0) mbar_wait(w_full, 0); }
-            if constexpr (!BULK) mbar_wait(&h_full[0], t & 1);
-            // ONE fence per step: it orders this step's first (overwriting) MMA after the tcgen05.ld of the previous step's
-            // accumulators (this warp took part in that step's CTA barriers). A fence per K block would make the warp wait for
-            // its own MMAs in flight
+            if constexpr (KBB) {
+                // per-K-block waits inside the loop; the issuing warps took part in last step's CTA barriers themselves
+            } else if constexpr (BULK) {
+                if (t > 0) {
+                    mbar_wait(&h_full[t & 1], ((t - 1) >> 1) & 1);                // every peer's block has landed
+                    if (lane == 0 && warp == 0) mbar_expect_tx(&h_full[t & 1], ctas * BLK_STRIDE);  // re-arm for step t+2
+                }
+            } else {
+                mbar_wait(&h_full[0], t & 1);
+            }
             tc_fence_after();
             TRACE(1);
             const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sH) + (BULK ? (t & 1) * himg_bytes : 0);
@@ -366,19 +372,12 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
             constexpr uint32_t LO = BLK_BYTES / 16;    // descriptor step from a block's hi part to its lo part
 #pragma unroll 1
             for (int it = kfirst; it < kblocks; it += kstep) {
-                // BULK: K blocks in their arrival order at this CTA (the peers send in rotated order, exchange_peer)
-                const int kb = BULK ? arrival_kblock(j, it, kblocks, p.rot) : it;
-                if constexpr (BULK) {
+                const int kb = KBB ? arrival_kblock(j, it, kblocks) : it;   // X3: K blocks in their arrival order
+                if constexpr (KBB) {
                     if (t > 0) {
-                        if (p.kbbar) {
-                            uint64_t* hf = &h_full[(t & 1) * MAX_KB + kb];
-                            mbar_wait(hf, ((t - 1) >> 1) & 1);                    // both source blocks of this K block have landed
-                            if (lane == 0) mbar_expect_tx(hf, 2 * BLK_STRIDE);    // re-arm for step t + 2 (this warp owns kb)
-                        } else if (it == kfirst) {
-                            uint64_t* hf = &h_full[(t & 1) * MAX_KB];
-                            mbar_wait(hf, ((t - 1) >> 1) & 1);                    // every peer's block has landed
-                            if (lane == 0 && warp == 0) mbar_expect_tx(hf, ctas * BLK_STRIDE);
-                        }
+                        uint64_t* kf = &h_full[(t & 1) * HB_STRIDE + kb];
+                        mbar_wait(kf, ((t - 1) >> 1) & 1);                    // both source blocks of this K block have landed
+                        if (lane == 0) mbar_expect_tx(kf, 2 * BLK_STRIDE);    // re-arm for step t + 2 (this warp owns kb)
                     }
                 }
                 // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
@@ -499,11 +498,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
                 // one bulk copy per peer (our contiguous block -> slot j of the peer's next operand buffer); warp w
                 // serves peers w and w + 8 so the copies are issued in parallel with warp-uniform operands
                 const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_STRIDE;
-                const uint32_t bar = smem_u32(&h_full[((t + 1) & 1) * MAX_KB + (p.kbbar ? (j >> 1) : 0)]);
+                const uint32_t bar = smem_u32(&h_full[((t + 1) & 1) * HB_STRIDE + (KBB ? (j >> 1) : 0)]);
 #pragma unroll
                 for (int pos = warp; pos < 16; pos += 8) {
                     if (pos < ctas && warp_leader) {
-                        const uint32_t d = exchange_peer(j, pos, ctas, p.rot);
+                        const uint32_t d = KBB ? exchange_peer(j, pos, ctas) : static_cast<uint32_t>(pos);
                         bulk_copy_to_peer(mapa_shared(dst, d), smem_u32(sOut), BLK_STRIDE, mapa_shared(bar, d));
                     }
                 }
@@ -565,11 +564,11 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
     uint8_t* sOut = sH + 2 * himg_bytes;                                    // [2 halves][2 parities][HALF_BYTES] staging
     float* sGx = reinterpret_cast<float*>(sOut + 4 * HALF_BYTES);           // [4 stages][8 batch rows][128 gate rows] (TMA boxes)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sGx + 4 * HB * 128);
-    uint64_t* acc_full = bars;        // [half]: the four partial accumulators of a half-step are complete
-    uint64_t* so_ready = bars + 2;    // [half]: all element warps have staged their part of h_t
-    uint64_t* gx_full = bars + 4;     // [4 stages]: the input-projection box of a half-step has landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    uint64_t* h_full = bars + 10;     // [half][parity][kb]: the two half blocks of K block kb of h_{t-1} have landed (exchange_peer)
+    uint64_t* h_full = bars;          // [half][parity]: every peer's half block of h_{t-1} has landed
+    uint64_t* acc_full = bars + 4;    // [half]: the four partial accumulators of a half-step are complete
+    uint64_t* so_ready = bars + 6;    // [half]: all element warps have staged their part of h_t
+    uint64_t* gx_full = bars + 8;     // [4 stages]: the input-projection box of a half-step has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
@@ -577,7 +576,7 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
     const int kblocks = H / 64;
 
     if (tid == 0) {
-        for (int i = 0; i < 4 * MAX_KB; ++i) mbar_init(&h_full[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&h_full[i], 1);
         mbar_init(&acc_full[0], 4);
         mbar_init(&acc_full[1], 4);
         mbar_init(&so_ready[0], 8);
@@ -585,8 +584,7 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
         for (int i = 0; i < 4; ++i) mbar_init(&gx_full[i], 1);
         tma_prefetch_desc(&tmGx);
         fence_mbar_init();
-        for (int i = 0; i < 4 * MAX_KB; ++i)
-            if (p.kbbar || (i % MAX_KB) == 0) mbar_expect_tx(&h_full[i], (p.kbbar ? 2 : ctas) * HALF_BYTES);
+        for (int i = 0; i < 4; ++i) mbar_expect_tx(&h_full[i], ctas * HALF_BYTES);
     }
     uint32_t tmem_cols = 256;
     while (tmem_cols < ACC_COLS + H / 2) tmem_cols <<= 1;
@@ -628,13 +626,13 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
                 mbar_wait(&so_ready[half], t & 1);
                 if (warp == 12 && half == 0) PTRACE(10);
                 if (warp == 12 && lane == 0 && 2 * t + half + 4 < 2 * T) fetch_gx(2 * t + half + 4);  // its stage was read in this half-step
-                const int pos = (warp - 12) + 4 * lane;   // the four warps take consecutive slots of the rotated order
-                if (lane < 4 && pos < ctas) {
-                    const uint32_t d = exchange_peer(j, pos, ctas, p.rot);
+                const int d = (warp - 12) * 4 + lane;
+                if (lane < 4 && d < ctas) {
                     const uint32_t src = smem_u32(sOut + (half * 2 + (t & 1)) * HALF_BYTES);
                     const uint32_t dst = smem_u32(sH) + ((t + 1) & 1) * himg_bytes + j * BLK_BYTES + half * HALF_BYTES;
-                    const uint32_t bar = smem_u32(&h_full[(half * 2 + ((t + 1) & 1)) * MAX_KB + (p.kbbar ? (j >> 1) : 0)]);
-                    bulk_copy_to_peer(mapa_shared(dst, d), src, HALF_BYTES, mapa_shared(bar, d));
+                    const uint32_t bar = smem_u32(&h_full[half * 2 + ((t + 1) & 1)]);
+                    bulk_copy_to_peer(mapa_shared(dst, static_cast<uint32_t>(d)), src, HALF_BYTES,
+                                      mapa_shared(bar, static_cast<uint32_t>(d)));
                 }
                 __syncwarp();
                 if (warp == 12 && half == 0) PTRACE(11);
@@ -647,37 +645,26 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
         for (int t = 0; t < T; ++t) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                uint64_t* hf = &h_full[(half * 2 + (t & 1)) * MAX_KB];
+                uint64_t* hf = &h_full[half * 2 + (t & 1)];
+                if (t > 0) {
+                    mbar_wait(hf, ((t - 1) >> 1) & 1);                       // every peer's half block has landed
+                    if (m == 0 && lane == 0) mbar_expect_tx(hf, ctas * HALF_BYTES);   // re-arm for step t + 2
+                }
+                tc_fence_after();
                 if (m == 0) PTRACE(12 + 2 * half);
                 const uint32_t b0 = smem_u32(sH) + (t & 1) * himg_bytes;
                 const uint32_t dacc = tmem_base + half * 64 + m * NB;
-                // This CTA's own half block travels through the exchange like the others (K block j/2, the first to arrive in
-                // the rotated order): its landing implies that the element warps have finished reading the accumulators of the
-                // previous step, which this step's first MMA overwrites -> every issuing warp waits for it, then ONE fence
-                // (a fence per K block would make the warp wait for its own MMAs in flight)
-                if (t > 0) {
-                    mbar_wait(&hf[p.kbbar ? (j >> 1) : 0], ((t - 1) >> 1) & 1);
-                    if (!p.kbbar && m == 0 && lane == 0) mbar_expect_tx(&hf[0], ctas * HALF_BYTES);   // re-arm for step t + 2
-                }
-                tc_fence_after();
 #pragma unroll 1
-                for (int it = m; it < kblocks; it += 4) {
-                    const int kb = arrival_kblock(j, it, kblocks, p.rot);               // K blocks in their arrival order
-                    if (t > 0 && p.kbbar) {
-                        mbar_wait(&hf[kb], ((t - 1) >> 1) & 1);                  // both half blocks of this K block have landed
-                        if (lane == 0) mbar_expect_tx(&hf[kb], 2 * HALF_BYTES);  // re-arm for step t + 2 (this warp owns kb)
-                    }
+                for (int kb = m; kb < kblocks; kb += 4) {
                     const uint64_t bd = umma_desc_sw64(b0 + kb * (NB * 128));
                     const uint32_t ta = tmem_base + ACC_COLS + kb * 32;
                     if (leader) {
-                        umma_bf16_ts(dacc, ta, bd, idesc, it != m ? 1u : 0u);
+                        umma_bf16_ts(dacc, ta, bd, idesc, kb != m ? 1u : 0u);
                         umma_bf16_ts(dacc, ta + 8, bd + 2, idesc, 1u);
                         umma_bf16_ts(dacc, ta + 16, bd + (NB * 64 / 16), idesc, 1u);
                         umma_bf16_ts(dacc, ta + 24, bd + (NB * 64 / 16) + 2, idesc, 1u);
                     }
                 }
-                if (m >= kblocks && t > 0 && p.kbbar)   // H = 128: no K block for this warp; it still paces itself on the exchange (no re-arm:
-                    mbar_wait(&hf[arrival_kblock(j, kblocks - 1, kblocks, p.rot)], ((t - 1) >> 1) & 1);   // the owner does that)
                 if (leader) umma_commit(&acc_full[half]);
                 __syncwarp();
                 if (m == 0) PTRACE(13 + 2 * half);
@@ -783,9 +770,6 @@ struct BwdParams {
     int T, N, H, groups, n0;
     const __nv_bfloat16* w;    // packed transposed recurrent weights [8H, H] (hi part)
     int mma_split;
-    int rot;                   // 1: rotated all-gather order (exchange_peer)
-    int kbbar;                 // 1: one mbarrier per K block of the operand image, 0: one for the whole image
-    int rs_merge;              // 1: one reduce-scatter copy per destination CTA instead of one per warp
     long long* trace;          // optional [T][16] clock64 stamps of CTA 0 / thread 0 (CTCB200_LSTM_TRACE)
     unsigned int* resident;    // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
     const float* bn_x;         // optional: layer output [T*N, 2H]; the BatchNorm backward of the layer above is applied to
@@ -850,7 +834,9 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
     uint64_t* acc_full = bars + 1;
     uint64_t* r_full = bars + 2;   // BULK: the 4 partial blocks of a step have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-    uint64_t* b_full = bars + 4;   // BULK: [parity][kb], one barrier per K block of the dG image (see exchange_peer); else [0]
+    constexpr bool KBB = BULK && X3;               // X3: one barrier per K block of the dG image (see exchange_peer)
+    constexpr int HB_STRIDE = KBB ? MAX_KB : 1;
+    uint64_t* b_full = bars + 4;   // [parity * HB_STRIDE + kb]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     announce_resident(p.resident);
@@ -866,13 +852,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
     if (tid == 0) {
         if constexpr (X3) tma_prefetch_desc(&tmWTlo);
         mbar_init(w_full, 1);
-        for (int i = 0; i < 2 * MAX_KB; ++i) mbar_init(&b_full[i], BULK ? 1 : LSTM_THREADS);
+        for (int i = 0; i < 2 * HB_STRIDE; ++i) mbar_init(&b_full[i], BULK ? 1 : LSTM_THREADS);
         mbar_init(acc_full, p.mma_split);
         mbar_init(r_full, 1);
         fence_mbar_init();
         if constexpr (BULK) {
-            for (int i = 0; i < 2 * MAX_KB; ++i)
-                if (p.kbbar || (i % MAX_KB) == 0) mbar_expect_tx(&b_full[i], (p.kbbar ? 2 : ctas) * BLK_STRIDE);
+            for (int i = 0; i < 2 * HB_STRIDE; ++i) mbar_expect_tx(&b_full[i], (KBB ? 2 : ctas) * BLK_STRIDE);
             mbar_expect_tx(r_full, 4 * NB * 32 * PART_BYTES);  // four gate partials of [NB][32] values per step
         }
     }
@@ -960,30 +945,32 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
         // (4) partial dh[128 units, NB] = W_q^T slice * dG_q (issued like the forward kernel's chain)
         if (warp < p.mma_split) {
             if constexpr (X3) { if (t == 0) mbar_wait(w_full, 0); }
-            if constexpr (!BULK) mbar_wait(&b_full[0], t & 1);
-            tc_fence_after();   // one fence per step (see the forward kernel)
+            if constexpr (KBB) {
+                // per-K-block waits inside the loop; the issuing warps took part in last step's CTA barriers themselves
+            } else if constexpr (BULK) {
+                if (t > 0) {
+                    mbar_wait(&b_full[t & 1], ((t - 1) >> 1) & 1);
+                    if (lane == 0 && warp == 0) mbar_expect_tx(&b_full[t & 1], ctas * BLK_STRIDE);
+                }
+            } else {
+                mbar_wait(&b_full[0], t & 1);
+            }
+            tc_fence_after();
+            BTRACE(1);
             const uint32_t a0 = smem_u32(sW), b0 = smem_u32(sB) + (BULK ? (t & 1) * img_bytes : 0);
             const bool leader = elect_one();
             const int kstep = p.mma_split, kfirst = warp;
             const uint32_t dacc = tmem_base + warp * NB;
             constexpr uint32_t B2 = BLK_STRIDE / 16, LO = BLK_BYTES / 16;
-            const int my_rank = q + 4 * mb;
 #pragma unroll 1
             for (int it = kfirst; it < kblocks; it += kstep) {
-                const int kb = BULK ? arrival_kblock(my_rank, it, kblocks, p.rot) : it;   // K blocks in their arrival order
-                if constexpr (BULK) {
+                const int kb = KBB ? arrival_kblock(q + 4 * mb, it, kblocks) : it;   // X3: K blocks in their arrival order
+                if constexpr (KBB) {
                     if (t > 0) {
-                        if (p.kbbar) {
-                            uint64_t* bf = &b_full[(t & 1) * MAX_KB + kb];
-                            mbar_wait(bf, ((t - 1) >> 1) & 1);                    // both source blocks of this K block have landed
-                            if (lane == 0) mbar_expect_tx(bf, 2 * BLK_STRIDE);    // re-arm for step t + 2 (this warp owns kb)
-                        } else if (it == kfirst) {
-                            uint64_t* bf = &b_full[(t & 1) * MAX_KB];
-                            mbar_wait(bf, ((t - 1) >> 1) & 1);                    // every source block has landed
-                            if (lane == 0 && warp == 0) mbar_expect_tx(bf, ctas * BLK_STRIDE);
-                        }
+                        uint64_t* kf = &b_full[(t & 1) * HB_STRIDE + kb];
+                        mbar_wait(kf, ((t - 1) >> 1) & 1);                    // both source blocks of this K block have landed
+                        if (lane == 0) mbar_expect_tx(kf, 2 * BLK_STRIDE);    // re-arm for step t + 2 (this warp owns kb)
                     }
-                    if (it == kfirst) BTRACE(1);
                 }
                 // 64 K elements = two SWIZZLE_64B blocks of the B image, two K=16 slices (32 bytes apart) in each
                 const uint64_t bd = umma_desc_sw64(b0 + kb * (2 * BLK_STRIDE));
@@ -1037,24 +1024,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 for (int c = 0; c < CPT; ++c) stage[c * 32] = __float2half_rn(__uint_as_float(acc[c]));
             }
             fence_proxy_async_smem();
-            // the two warps that hold the halves (ch = 0, 1) of the block for CTA (lq, mb) meet on a named barrier and send it as
-            // ONE copy: a copy costs the engine ~33 cycles whatever its size, and these are on the step's critical path
-            if (p.rs_merge) {
-                named_bar_sync(1 + lq, 64);
-                if (ch == 0 && warp_leader) {
-                    const uint32_t peer = rank_of(lq, mb);
-                    bulk_copy_to_peer(mapa_shared(smem_u32(sR) + re * PART_BYTES, peer), smem_u32(sP) + pe * PART_BYTES,
-                                      NB * 32 * PART_BYTES, mapa_shared(smem_u32(r_full), peer));
-                    bulk_commit();
-                }
-            } else {
-                __syncwarp();
-                if (warp_leader) {
-                    const uint32_t peer = rank_of(lq, mb);
-                    bulk_copy_to_peer(mapa_shared(smem_u32(sR) + re * PART_BYTES, peer), smem_u32(sP) + pe * PART_BYTES,
-                                      CPT * 32 * PART_BYTES, mapa_shared(smem_u32(r_full), peer));
-                    bulk_commit();
-                }
+            __syncwarp();
+            if (warp_leader) {
+                const uint32_t peer = rank_of(lq, mb);
+                bulk_copy_to_peer(mapa_shared(smem_u32(sR) + re * PART_BYTES, peer), smem_u32(sP) + pe * PART_BYTES,
+                                  CPT * 32 * PART_BYTES, mapa_shared(smem_u32(r_full), peer));
+                bulk_commit();
             }
             BTRACE(5);
             mbar_wait(r_full, t & 1);
@@ -1066,11 +1041,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
             cluster_sync_all();
         }
         // (6) finish 32 units: recurrent dh, LSTM cell backward, publish the four gate gradients
-        // The values prefetched in (1) are passed through an empty volatile asm here: volatile asms keep their order, so no
-        // arithmetic on them can be scheduled above the waits of (4)/(5) (ptxas otherwise hoists e.g. the tanh of c_t in front
-        // of the MMA issue, and the issuing warps then stall on the global load every step: +15 % step time when it happens)
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
+        for (int e = 0; e < EPT; ++e) {   // keep all arithmetic on the values prefetched in (1) below the waits (see pin_reg)
             pin_reg(dh_in[e]); pin_reg(bx_in[e]); pin_reg(c_t[e]); pin_reg(c_p[e]);
             if constexpr (X3) { pin_reg(gts32[e].x); pin_reg(gts32[e].y); pin_reg(gts32[e].z); pin_reg(gts32[e].w); }
             else { pin_reg(gts16[e].x); pin_reg(gts16[e].y); }
@@ -1174,14 +1146,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
             if (t + 1 < T) {
                 // copy i = (g, mdst): gate g's block [hi | lo] of this CTA's 32 units -> slot (4 mb + q) of CTA (g, mdst)'s
                 // buffer; warp w issues copies w and w + 8
-                const int me = 4 * mb + q;   // = this CTA's rank in the cluster = its slot in every receiver's image
+                const int me = 4 * mb + q;   // this CTA's slot in every receiver's image (= its cluster rank)
                 const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + me * BLK_STRIDE;
-                const uint32_t bar = smem_u32(&b_full[((t + 1) & 1) * MAX_KB + (p.kbbar ? (me >> 1) : 0)]);
+                const uint32_t bar = smem_u32(&b_full[((t + 1) & 1) * HB_STRIDE + (KBB ? (me >> 1) : 0)]);
 #pragma unroll
-                for (int pos = warp; pos < 16; pos += 8) {
-                    if (pos < ctas && warp_leader) {
-                        const uint32_t peer = exchange_peer(me, pos, ctas, p.rot);   // rank = gate + 4 * unit block: it gets its gate's block
-                        const int g = peer & 3;
+                for (int i = warp; i < 16; i += 8) {
+                    // receiver rank = gate + 4 * unit block; X3: rotated order (exchange_peer)
+                    const uint32_t peer = KBB ? exchange_peer(me, i, ctas) : rank_of(i & 3, i >> 2);
+                    const int g = peer & 3;
+                    if (i < ctas && warp_leader) {
                         bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * PARTS * OUT_CHUNKS), BLK_STRIDE,
                                           mapa_shared(bar, peer));
                     }
@@ -1580,7 +1553,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
         }
         uint2 dgp[2][EPT];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf)   // keep all arithmetic on the prefetched values below the waits (see lstm_bwd_kernel)
+        for (int hf = 0; hf < 2; ++hf)   // keep all arithmetic on the prefetched values below the waits (see pin_reg)
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
                 pin_reg(dh_in[hf][e]); pin_reg(bx_in[hf][e]); pin_reg(c_t[hf][e]); pin_reg(c_p[hf][e]);
@@ -1665,21 +1638,6 @@ int mma_issuers(int NB, int H) {
     if (n > 4) n = 4;
     while (n > 1 && (n > H / 64 || n * NB > 64)) n >>= 1;
     return n < 1 ? 1 : n;
-}
-
-// A/B switches for the exchange schedule (defaults = measured best)
-int exchange_rotated() {
-    const char* e = getenv("CTCB200_LSTM_ORDER");
-    return (e != nullptr && e[0] == 'f') ? 0 : 1;    // "fixed": every CTA serves its peers in the same order
-}
-int kblock_barriers(bool x3) {   // per-K-block mbarriers: the MMA chain starts on the first K block that lands
-    const char* e = getenv("CTCB200_LSTM_KBBAR");
-    if (e != nullptr) return e[0] == '0' ? 0 : 1;
-    return x3 ? 1 : 0;
-}
-int rs_merged() {
-    const char* e = getenv("CTCB200_LSTM_RS_MERGE");
-    return (e != nullptr && e[0] == '0') ? 0 : 1;
 }
 
 size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool x3) {
@@ -1950,7 +1908,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         const size_t smem2 = static_cast<size_t>(128) * H * 2 + static_cast<size_t>(2) * H * NB2 * 2 +
                              static_cast<size_t>(2) * 32 * (NB2 * 4 + 4) * 4 + static_cast<size_t>(2) * NB2 * 4 * 16 + 64 + 1024;
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
-        p.mma_split = 4; p.rot = 0; p.kbbar = 0; p.groups = groups2;
+        p.mma_split = 4; p.groups = groups2;
         if (cluster_ok(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2))
             return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p,
                                     stream);
@@ -1975,8 +1933,6 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         p.act_approx = (!x3 && plain && act != nullptr && act[0] == 'a') ? 1 : 0;
     }
     p.mma_split = mma_issuers(NB, H);
-    p.rot = exchange_rotated();
-    p.kbbar = kblock_barriers(x3);
     p.groups = groups_total;
     if (getenv("CTCB200_LSTM_TRACE")) {
         static long long* dbuf = nullptr;
@@ -1991,7 +1947,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         trace_dump.pipe = true;
         // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core warps
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
-        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 4 * 512 + 4 * 8 * 128 * 4 + 512 + 1024;
+        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 4 * 512 + 4 * 8 * 128 * 4 + 128 + 1024;
         CUtensorMap tmGx;   // gate pre-activations as a 2-D f32 tensor [T*N rows, 8H columns], boxes of 8 rows x 128 columns
         rc = make_tmap_f32_2d(&tmGx, gx, static_cast<uint64_t>(T) * N, static_cast<uint64_t>(8) * H, static_cast<uint64_t>(8) * H, 8, 128);
         if (rc == OK && cluster_ok(lstm_fwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS))
@@ -2047,7 +2003,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     p.dg = static_cast<__nv_bfloat16*>(dg); p.dg_lo = static_cast<__nv_bfloat16*>(dg_lo);
     p.dg_rec = static_cast<__nv_bfloat16*>(dg_rec); p.dg_rec_lo = static_cast<__nv_bfloat16*>(dg_rec_lo);
     p.rnn_relu = cell == 3 ? 1 : 0;
-    p.dgimg = nullptr; p.flags = nullptr; p.trace = nullptr; p.rot = 0; p.kbbar = 0; p.rs_merge = 0;
+    p.dgimg = nullptr; p.flags = nullptr; p.trace = nullptr;
     p.resident = static_cast<unsigned int*>(resident_counter);
     p.bn_x = bn_x; p.bn_coef = bn_coef;
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed);
@@ -2061,7 +2017,7 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         const size_t smem2 = static_cast<size_t>(128) * (H - 256) * 2 + static_cast<size_t>(4) * H * NB2 * 2 +
                              static_cast<size_t>(4) * NB2 * 32 * 4 * 2 + static_cast<size_t>(8) * NB2 * 4 * 16 + 64 + 1024;
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
-        p.mma_split = 4; p.rot = 0; p.kbbar = 0; p.groups = groups2;
+        p.mma_split = 4; p.groups = groups2;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
             return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false,
                                     tmWT2, p, stream, LSTM_THREADS, start_ev);
@@ -2083,9 +2039,6 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     const size_t smem = lstm_smem_bytes(NB, H, true, ex, x3);
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
     p.mma_split = mma_issuers(NB, H);
-    p.rot = exchange_rotated();
-    p.kbbar = kblock_barriers(x3);
-    p.rs_merge = rs_merged();
     p.groups = groups_total;
     if (getenv("CTCB200_LSTM_TRACE")) {
         static long long* dbuf = nullptr;

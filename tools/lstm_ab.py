@@ -66,28 +66,6 @@ os.environ["CTCB200_LSTM_PIPE"] = "0"
 f = timed(lambda: chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), None, P(hout), P(c_save), P(gates16), P(scratch), T, N, H, 0, 0, S()), cur))
 res["r2_bf16_unpipelined_fwd_ms"] = f
 os.environ.pop("CTCB200_LSTM_PIPE")
-# exchange-schedule switches (CTCB200_LSTM_KBBAR=0|1: one mbarrier per image / per K block; CTCB200_LSTM_RS_MERGE=0|1): LSTM,
-# both operand modes. (CTCB200_LSTM_ORDER=fixed|rot made no difference in either mode.)
-sw = {}
-for order in ("kbbar0", "kbbar1"):
-    os.environ["CTCB200_LSTM_KBBAR"] = order[-1]
-    for name, lo, gates in (("bf16", None, gates16), ("x3", whh_lo, gates32)):
-        f = timed(lambda: chk(cur.ctcb200_lstm_fwd(P(gx), P(whh), P(lo), P(hout), P(c_save), P(gates), P(scratch), T, N, H, 0, 0, S()), cur))
-        sw["fwd_%s_%s" % (name, order)] = f
-        if name == "bf16":
-            os.environ["CTCB200_LSTM_PIPE"] = "0"
-            sw["fwd_bf16_unpipelined_%s" % order] = timed(lambda: chk(cur.ctcb200_lstm_fwd(
-                P(gx), P(whh), None, P(hout), P(c_save), P(gates16), P(scratch), T, N, H, 0, 0, S()), cur))
-            os.environ.pop("CTCB200_LSTM_PIPE")
-        for merge in ("1", "0"):
-            os.environ["CTCB200_LSTM_RS_MERGE"] = merge
-            b = timed(lambda: chk(cur.ctcb200_lstm_bwd(P(dh), P(whh), P(lo), P(c_save), P(gates), P(dg), P(dg_lo) if lo is not None else None,
-                                                       P(dg2), P(dg2_lo) if lo is not None else None, P(scratch), T, N, H, 0, 0,
-                                                       None, None, None, None, S()), cur))
-            sw["bwd_%s_%s_merge%s" % (name, order, merge)] = b
-os.environ.pop("CTCB200_LSTM_KBBAR")
-os.environ.pop("CTCB200_LSTM_RS_MERGE")
-res["exchange_switches_ms"] = sw
 old_path = os.path.join(ROOT, "tools", "_ab", "libctcb200_r1.so")
 if os.path.exists(old_path):
     old = ctypes.CDLL(old_path)
