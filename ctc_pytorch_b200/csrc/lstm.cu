@@ -835,6 +835,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
     uint64_t* r_full = bars + 2;   // BULK: the 4 partial blocks of a step have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
     constexpr bool KBB = BULK && X3;               // X3: one barrier per K block of the dG image (see exchange_peer)
+    constexpr bool PRE = BULK && CELL == CELL_LSTM; // cell-backward factors that do not need the recurrent dh are computed early
     constexpr int HB_STRIDE = KBB ? MAX_KB : 1;
     uint64_t* b_full = bars + 4;   // [parity * HB_STRIDE + kb]
 
@@ -915,6 +916,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
         // NOTHING loaded here may be touched before phase (6): these loads are issued ahead of the MMA chain so that their
         // latency hides behind it (a conversion at the load site would stall the issuing warps on the load every step)
         float dh_in[EPT], bx_in[EPT], c_t[EPT], c_p[EPT];
+        float pre_dh[PRE ? EPT : 1], k_o[PRE ? EPT : 1], k_c[PRE ? EPT : 1], k_i[PRE ? EPT : 1], k_f[PRE ? EPT : 1], k_g[PRE ? EPT : 1],
+            k_carry[PRE ? EPT : 1];   // LSTM cluster kernels: cell-backward factors computed while the partials are in flight
         float4 gts32[X3 ? EPT : 1];
         uint2 gts16[X3 ? 1 : EPT];
 #pragma unroll
@@ -1032,6 +1035,30 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 bulk_commit();
             }
             BTRACE(5);
+            if constexpr (PRE) {
+                // while the partials are in flight: everything of the cell backward that does not depend on the recurrent dh
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    pin_reg(dh_in[e]); pin_reg(bx_in[e]); pin_reg(c_t[e]); pin_reg(c_p[e]);
+                    float gi, gf, gg, go;
+                    if constexpr (X3) {
+                        pin_reg(gts32[e].x); pin_reg(gts32[e].y); pin_reg(gts32[e].z); pin_reg(gts32[e].w);
+                        gi = gts32[e].x; gf = gts32[e].y; gg = gts32[e].z; go = gts32[e].w;
+                    } else {
+                        pin_reg(gts16[e].x); pin_reg(gts16[e].y);
+                        const __half2 glo = *reinterpret_cast<const __half2*>(&gts16[e].x), ghi = *reinterpret_cast<const __half2*>(&gts16[e].y);
+                        gi = __low2float(glo); gf = __high2float(glo); gg = __low2float(ghi); go = __high2float(ghi);
+                    }
+                    const float tc = fast_tanh(c_t[e]);
+                    pre_dh[e] = bnk.a * dh_in[e] + bnk.b * bx_in[e] + ((p.n0 + grp * NB + warp + 8 * e < N) ? bnk.d : 0.0f);
+                    k_o[e] = tc * go * (1.0f - go);
+                    k_c[e] = go * (1.0f - tc * tc);
+                    k_i[e] = gg * gi * (1.0f - gi);
+                    k_f[e] = c_p[e] * gf * (1.0f - gf);
+                    k_g[e] = gi * (1.0f - gg * gg);
+                    k_carry[e] = gf;
+                }
+            }
             mbar_wait(r_full, t & 1);
             BTRACE(6);
             if (tid == 0) mbar_expect_tx(r_full, 4 * NB * 32 * PART_BYTES);  // re-arm for the next step
@@ -1041,32 +1068,44 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
             cluster_sync_all();
         }
         // (6) finish 32 units: recurrent dh, LSTM cell backward, publish the four gate gradients
+        if constexpr (!PRE) {
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {   // keep all arithmetic on the values prefetched in (1) below the waits (see pin_reg)
-            pin_reg(dh_in[e]); pin_reg(bx_in[e]); pin_reg(c_t[e]); pin_reg(c_p[e]);
-            if constexpr (X3) { pin_reg(gts32[e].x); pin_reg(gts32[e].y); pin_reg(gts32[e].z); pin_reg(gts32[e].w); }
-            else { pin_reg(gts16[e].x); pin_reg(gts16[e].y); }
+            for (int e = 0; e < EPT; ++e) {   // keep all arithmetic on the values prefetched in (1) below the waits (see pin_reg)
+                pin_reg(dh_in[e]); pin_reg(bx_in[e]); pin_reg(c_t[e]); pin_reg(c_p[e]);
+                if constexpr (X3) { pin_reg(gts32[e].x); pin_reg(gts32[e].y); pin_reg(gts32[e].z); pin_reg(gts32[e].w); }
+                else { pin_reg(gts16[e].x); pin_reg(gts16[e].y); }
+            }
         }
         uint2 dgp[EPT], dgl[EPT];
         uint2 dgr[CELL == CELL_GRU ? EPT : 1], dgrl[CELL == CELL_GRU ? EPT : 1];   // GRU: input-side gate gradients (see below)
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int n = warp + 8 * e;
-            float dh = bnk.a * dh_in[e] + bnk.b * bx_in[e] + ((p.n0 + grp * NB + n < N) ? bnk.d : 0.0f);   // BatchNorm backward on the fly
+            float dh;
+            if constexpr (PRE) dh = pre_dh[e];
+            else dh = bnk.a * dh_in[e] + bnk.b * bx_in[e] + ((p.n0 + grp * NB + n < N) ? bnk.d : 0.0f);   // BatchNorm backward on the fly
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 if constexpr (BULK && !X3) dh += __half2float(reinterpret_cast<const __half*>(sR)[(s * NB + n) * 32 + lane]);
                 else dh += sR[(s * NB + n) * 32 + lane];
             }
-            float gi, gf, gg, go;
-            if constexpr (X3) {
+            float gi = 0.0f, gf = 0.0f, gg = 0.0f, go = 0.0f;
+            if constexpr (PRE) {
+            } else if constexpr (X3) {
                 gi = gts32[e].x; gf = gts32[e].y; gg = gts32[e].z; go = gts32[e].w;
             } else {
                 const __half2 glo = *reinterpret_cast<const __half2*>(&gts16[e].x), ghi = *reinterpret_cast<const __half2*>(&gts16[e].y);
                 gi = __low2float(glo); gf = __high2float(glo); gg = __low2float(ghi); go = __high2float(ghi);
             }
             float d_i, d_f, d_g, d_o;     // the four slots handed to the next BPTT step (what W_hh^T multiplies)
-            if constexpr (CELL == CELL_LSTM) {
+            if constexpr (PRE) {
+                d_o = dh * k_o[e];
+                const float dc = dc_carry[e] + dh * k_c[e];
+                d_i = dc * k_i[e];
+                d_f = dc * k_f[e];
+                d_g = dc * k_g[e];
+                dc_carry[e] = dc * k_carry[e];
+            } else if constexpr (CELL == CELL_LSTM) {
                 const float tc = fast_tanh(c_t[e]);
                 d_o = dh * tc * go * (1.0f - go);
                 const float dc = dc_carry[e] + dh * go * (1.0f - tc * tc);
@@ -1149,14 +1188,16 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 const int me = 4 * mb + q;   // this CTA's slot in every receiver's image (= its cluster rank)
                 const uint32_t dst = smem_u32(sB) + ((t + 1) & 1) * img_bytes + me * BLK_STRIDE;
                 const uint32_t bar = smem_u32(&b_full[((t + 1) & 1) * HB_STRIDE + (KBB ? (me >> 1) : 0)]);
+                {
 #pragma unroll
-                for (int i = warp; i < 16; i += 8) {
-                    // receiver rank = gate + 4 * unit block; X3: rotated order (exchange_peer)
-                    const uint32_t peer = KBB ? exchange_peer(me, i, ctas) : rank_of(i & 3, i >> 2);
-                    const int g = peer & 3;
-                    if (i < ctas && warp_leader) {
-                        bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * PARTS * OUT_CHUNKS), BLK_STRIDE,
-                                          mapa_shared(bar, peer));
+                    for (int i = warp; i < 16; i += 8) {
+                        // receiver rank = gate + 4 * unit block; X3: rotated order (exchange_peer)
+                        const uint32_t peer = KBB ? exchange_peer(me, i, ctas) : rank_of(i & 3, i >> 2);
+                        const int g = peer & 3;
+                        if (i < ctas && warp_leader) {
+                            bulk_copy_to_peer(mapa_shared(dst, peer), smem_u32(sOut + g * PARTS * OUT_CHUNKS), BLK_STRIDE,
+                                              mapa_shared(bar, peer));
+                        }
                     }
                 }
                 if (warp_leader) bulk_commit();
