@@ -167,22 +167,22 @@ def _resident_event(dev):
     return ev, ctypes.c_void_p(ev.cuda_event)
 
 
-def _distributed():
-    return torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-
-
 def _overlap_gate():
     """How the side stream learns that the BPTT grid is resident.
-    'memop': counter bumped by the kernel + cuStreamWaitValue32 — precise (cfg2 fwd+loss+bwd 13.5 ms vs 14.95 without
-             overlap) but invisible to the CUDA scheduler; one 2-GPU run with a NCCL communicator in the process stalled on it.
-    'event': programmatic launch event (fires when every block has started) + cudaStreamWaitEvent — an ordinary stream
-             dependency; observed later than the memop (14.4 ms), safe next to other libraries' streams.
-    Default: memop in single-process jobs, event when the process belongs to a world_size > 1 group; CTCB200_OVERLAP_GATE
+    'memop': counter bumped by the kernel + cuStreamWaitValue32 — precise: the weight-gradient work of layer l starts the moment
+             the BPTT grid of layer l-1 is resident (profiles/timeline_r2_cfg2_g2_memopgate.json).
+    'event': programmatic launch event + cudaStreamWaitEvent — an ordinary stream dependency, but CUDA only guarantees that it is
+             observed *no earlier* than the trigger: measured on B200 (profiles/timeline_r2_cfg2_g2_eventgate.json) it is observed
+             when the BPTT kernel ENDS, so every layer's weight gradients run one layer late and two layers' worth is left for
+             the tail of the backward pass (2-GPU cfg2 step 14.9 ms vs 13.75 ms with the memop gate).
+    Default: memop everywhere. Round 1 saw one stall of a 2-GPU run with the memop gate and fell back to the event gate for
+    world_size > 1; it never reproduced (round 2: 3 x 33 steps + a profiled run at 2 GPUs, SCALE runs at 4 / 8 GPUs), and the
+    wait is on a counter that the kernel launched just before it on the main stream always bumps. CTCB200_OVERLAP_GATE
     overrides."""
     g = os.environ.get("CTCB200_OVERLAP_GATE")
     if g in ("event", "memop"):
         return g
-    return "event" if _distributed() else "memop"
+    return "memop"
 
 
 def _overlap_enabled(model):
