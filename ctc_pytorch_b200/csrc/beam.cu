@@ -65,10 +65,7 @@ struct BeamParams {
     const double* lm;         // [(C+1), (C+1)]
     double lm_alpha;
     int T, N, C, W, blank, P2;  // P2 = candidate capacity >= W*C
-    double* pool_nb;          // [N, W*C]
-    double* pool_bl;          // [N, W*C]
-    int* pool_parent;         // [N, W*C]
-    int* pool_label;          // [N, W*C]
+    int lm_in_smem;           // 1: the kernel copies the bigram table into shared memory
     int* seq;                 // [N, 2, W, T]
     int* out_labels;          // [N, T]
     int* out_len;             // [N]
@@ -118,21 +115,50 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
     const int ept = (n + nthreads - 1) / nthreads;
     const int lo = tid * ept, hi = min(n, lo + ept);
     for (int i = tid; i < 8 * 256; i += nthreads) hist[i] = 0;
-    unsigned long long prefix = 0ULL;
-    int remaining = want;
+    if (tid == 0) { sscan[0] = 0; sscan[1] = 0; }
+    // key images of this thread's candidates stay in registers for all passes (the pool holds at most KEYS_PER_THREAD per
+    // thread: P2 <= 8192 slots over 1024 threads)
+    constexpr int KPT = 8;
+    unsigned long long u[KPT];
+    unsigned long long diff = 0ULL;
+    const unsigned long long u_first = key_bits(skey[0]);
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        const int i = lo + j;
+        u[j] = (j < ept && i < hi) ? key_bits(skey[i]) : u_first;
+        diff |= u[j] ^ u_first;
+    }
+    for (int i = lo + KPT; i < hi; ++i) diff |= key_bits(skey[i]) ^ u_first;   // wider pools: the tail is re-read every pass
+    __syncthreads();   // hist / sscan initialised
+    // bits in which the candidates differ at all: a byte position where they all agree needs no counting pass
+    diff |= __shfl_xor_sync(0xffffffffu, diff, 16);
+    diff |= __shfl_xor_sync(0xffffffffu, diff, 8);
+    diff |= __shfl_xor_sync(0xffffffffu, diff, 4);
+    diff |= __shfl_xor_sync(0xffffffffu, diff, 2);
+    diff |= __shfl_xor_sync(0xffffffffu, diff, 1);
+    if (lane == 0 && diff != 0ULL) {
+        atomicOr(reinterpret_cast<unsigned int*>(&sscan[0]), static_cast<unsigned int>(diff));
+        atomicOr(reinterpret_cast<unsigned int*>(&sscan[1]), static_cast<unsigned int>(diff >> 32));
+    }
     __syncthreads();
+    diff = static_cast<unsigned long long>(static_cast<unsigned int>(sscan[0])) |
+           (static_cast<unsigned long long>(static_cast<unsigned int>(sscan[1])) << 32);
+    unsigned long long prefix = 0ULL, done_mask = 0ULL;   // done_mask: the key bits decided so far
+    int remaining = want;
+    bool exact_cut = false;   // the want-th and (want+1)-th key already differ in the decided bits: no further pass needed
 #pragma unroll 1
-    for (int pass = 7; pass >= 0; --pass) {
+    for (int pass = 7; pass >= 0 && !exact_cut; --pass) {
         const int shift = pass * 8;
-        const unsigned long long mask_above = (pass == 7) ? 0ULL : (~0ULL << (shift + 8));
+        const unsigned long long mask_above = done_mask;
+        done_mask |= 255ULL << shift;
+        if (((diff >> shift) & 255ULL) == 0ULL) {      // every candidate has the same byte here
+            prefix |= u_first & (255ULL << shift);
+            continue;
+        }
         int* h = hist + pass * 256;
-        for (int j = 0; j < ept; ++j) {     // uniform trip count: the warp-wide vote below needs every lane present
-            const int i = lo + j;
+        auto count = [&](int i, unsigned long long ui) {
             int d = -1;
-            if (i < hi) {
-                const unsigned long long u = key_bits(skey[i]);
-                if ((u & mask_above) == prefix) d = static_cast<int>((u >> shift) & 255ULL);
-            }
+            if (i < hi && (ui & mask_above) == prefix) d = static_cast<int>((ui >> shift) & 255ULL);
             // the high bytes of scores of similar magnitude coincide across the whole warp: one atomic for 32 lanes then;
             // otherwise plain shared-memory atomics (few lanes still match the prefix in the later passes)
             const int d0 = __shfl_sync(0xffffffffu, d, 0);
@@ -141,7 +167,12 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
             } else if (d >= 0) {
                 atomicAdd(&h[d], 1);
             }
-        }
+        };
+        // uniform trip counts: the warp-wide vote needs every lane present
+#pragma unroll
+        for (int j = 0; j < KPT; ++j)
+            if (j < ept) count(lo + j, u[j]);
+        for (int j = KPT; j < ept; ++j) count(lo + j, (lo + j < hi) ? key_bits(skey[lo + j]) : 0ULL);
         __syncthreads();
         // EVERY warp finds the digit itself (256 bins, 8 per lane, one shuffle scan): no second barrier for a broadcast
         int loc[8], sum = 0;
@@ -154,12 +185,12 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
             if (lane + o < 32) x += y;
         }
         const int above = x - sum;   // entries whose digit lies in a higher lane's bins
-        int digit = -1, gt = 0;
+        int digit = -1, gt = 0, cnt = 0;
         if (above < remaining && remaining <= above + sum) {
             int run = above;
 #pragma unroll
             for (int b = 7; b >= 0; --b) {
-                if (run < remaining && remaining <= run + loc[b]) { digit = lane * 8 + b; gt = run; }
+                if (run < remaining && remaining <= run + loc[b]) { digit = lane * 8 + b; gt = run; cnt = loc[b]; }
                 run += loc[b];
             }
         }
@@ -167,15 +198,29 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
         const int src = __ffs(owner) - 1;
         digit = __shfl_sync(0xffffffffu, digit, src);
         gt = __shfl_sync(0xffffffffu, gt, src);
+        cnt = __shfl_sync(0xffffffffu, cnt, src);
         prefix |= static_cast<unsigned long long>(digit) << shift;
         remaining -= gt;
+        // the whole bin is taken: the selected set is exactly "decided bits >= prefix", whatever the lower bits are
+        exact_cut = (cnt == remaining);
     }
-    const unsigned long long kth = prefix;   // the want-th largest key; `remaining` entries equal to it are taken, lowest positions first
+    // the want-th largest key agrees with `prefix` in the decided bits; `remaining` entries equal to it there are taken, lowest
+    // positions first (after a full run the decided bits are all 64 and this is the tie rule of the stable sort; after an early
+    // exit every such entry is taken, so their order does not matter)
+    const unsigned long long kth = prefix;
     int cg = 0, ce = 0;
-    for (int i = lo; i < hi; ++i) {
-        const unsigned long long u = key_bits(skey[i]);
-        cg += u > kth;
-        ce += u == kth;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        if (j < ept && lo + j < hi) {
+            const unsigned long long um = u[j] & done_mask;
+            cg += um > kth;
+            ce += um == kth;
+        }
+    }
+    for (int i = lo + KPT; i < hi; ++i) {
+        const unsigned long long um = key_bits(skey[i]) & done_mask;
+        cg += um > kth;
+        ce += um == kth;
     }
     // block-wide exclusive scan of (cg, ce) packed into one int (both < 2^15)
     int packed = cg | (ce << 16), inc = packed;
@@ -196,15 +241,18 @@ __device__ void select_top(double* skey, int* spos, int n, int want, double* oke
     const int excl = inc - packed + warp_excl;
     int bg = excl & 0xffff, be = excl >> 16;
     const int n_gt = want - remaining;
-    for (int i = lo; i < hi; ++i) {
-        const double k = skey[i];
-        const unsigned long long u = key_bits(k);
-        if (u > kth) { okey[bg] = k; opos[bg] = i; ++bg; }
-        else if (u == kth) {
-            if (be < remaining) { okey[n_gt + be] = k; opos[n_gt + be] = i; }
+    auto place = [&](int i, unsigned long long ui) {
+        const unsigned long long um = ui & done_mask;
+        if (um > kth) { okey[bg] = skey[i]; opos[bg] = i; ++bg; }
+        else if (um == kth) {
+            if (be < remaining) { okey[n_gt + be] = skey[i]; opos[n_gt + be] = i; }
             ++be;
         }
-    }
+    };
+#pragma unroll
+    for (int j = 0; j < KPT; ++j)
+        if (j < ept && lo + j < hi) place(lo + j, u[j]);
+    for (int i = lo + KPT; i < hi; ++i) place(i, key_bits(skey[i]));
     int wp = 1;
     while (wp < want) wp <<= 1;
     for (int i = want + tid; i < wp; i += nthreads) { okey[i] = -INFINITY; opos[i] = 0x7fffffff; }
@@ -239,7 +287,6 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
     extern __shared__ uint8_t smem_raw[];
     const int n = blockIdx.x, tid = threadIdx.x;
     const int C = p.C, W = p.W, T = p.T, blank = p.blank, P2 = p.P2;
-    const int PC = W * C;
     // ---- shared memory carve-up ----
     double* skey = reinterpret_cast<double*>(smem_raw);
     double* rec_d = skey + P2;                       // 2 buffers x 3 arrays x W doubles
@@ -253,6 +300,14 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
     int* ht_val = rec_i + 4 * W;                     // HT
     int* merged_with = ht_val + HT;                  // W
     float* prow = reinterpret_cast<float*>(merged_with + W);  // C
+    // What a pool entry stands for is DERIVED from its position unless it is the "stay" entry of a beam: tag[pos] = r >= 0 marks
+    // the entry that carries beam r unchanged (its own slot r*C, or the position of the extension it merged with), with
+    // stay_nb / stay_bl holding that entry's non-blank / blank scores; tag = -1: extension (parent pos / C, label from the slot,
+    // non-blank score = the key itself, blank score = log 0). Nothing about the pool lives in global memory.
+    double* stay_nb = reinterpret_cast<double*>(reinterpret_cast<uintptr_t>(prow + C + 1) & ~uintptr_t(7)) + 1;   // W (8-byte aligned)
+    double* stay_bl = stay_nb + W;                   // W
+    double* lm_s = stay_bl + W;                      // (C+1)^2 when p.lm_in_smem, else unused
+    short* tag = reinterpret_cast<short*>(lm_s + (p.lm_in_smem ? (C + 1) * (C + 1) : 0));   // P2
     __shared__ int s_flags[4];                       // [0] nbeams, [1] status, [2] processed frames, [3] skip
     __shared__ double s_okey[TOP_MAX];               // selection buffer of select_top
     __shared__ int s_opos[TOP_MAX], s_hist[8 * 256], s_scan[40];
@@ -266,10 +321,11 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
     };
 
     const float* probs_n = p.probs + static_cast<size_t>(n) * T * C;
-    double* pool_nb = p.pool_nb + static_cast<size_t>(n) * PC;
-    double* pool_bl = p.pool_bl + static_cast<size_t>(n) * PC;
-    int* pool_parent = p.pool_parent + static_cast<size_t>(n) * PC;
-    int* pool_label = p.pool_label + static_cast<size_t>(n) * PC;
+    const double* lm = p.lm;
+    if (p.lm_in_smem) {   // the bigram table (31.7 KB at C = 62) is read once per candidate: keep it on chip
+        for (int i = tid; i < (C + 1) * (C + 1); i += blockDim.x) lm_s[i] = p.lm[i];
+        lm = lm_s;
+    }
     int* seq_base = p.seq + static_cast<size_t>(n) * 2 * W * T;
     int len_n = static_cast<int>(p.lengths[n]);
     if (len_n > T) len_n = T;
@@ -314,10 +370,13 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
         int* seq_new = seq_base + static_cast<size_t>((frames_done + 1) & 1) * W * T;
         for (int r = tid; r < live; r += blockDim.x) {
             const int pos = spos[r];
-            const int parent = pool_parent[pos], label = pool_label[pos];
+            const int tg = tag[pos];
+            const int slot = pos % C;
+            const int parent = tg >= 0 ? tg : pos / C;
+            const int label = tg >= 0 ? -1 : ((slot - 1 < blank) ? slot - 1 : slot);
             nxt.total[r] = skey[r];
-            nxt.nonblank[r] = pool_nb[pos];
-            nxt.blank[r] = pool_bl[pos];
+            nxt.nonblank[r] = tg >= 0 ? stay_nb[tg] : skey[r];
+            nxt.blank[r] = tg >= 0 ? stay_bl[tg] : LOG_ZERO;
             nxt.len[r] = prev.len[parent] + (label >= 0 ? 1 : 0);
             nxt.last[r] = label >= 0 ? label : prev.last[parent];
             nxt.hash[r] = label >= 0 ? mix_hash(prev.hash[parent], label) : prev.hash[parent];
@@ -327,7 +386,10 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
         const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
         for (int r = warp; r < live; r += nwarps) {
             const int pos = spos[r];
-            const int parent = pool_parent[pos], label = pool_label[pos];
+            const int tg = tag[pos];
+            const int slot = pos % C;
+            const int parent = tg >= 0 ? tg : pos / C;
+            const int label = tg >= 0 ? -1 : ((slot - 1 < blank) ? slot - 1 : slot);
             const int plen = prev.len[parent];
             for (int e = lane; e < plen; e += 32) seq_new[static_cast<size_t>(r) * T + e] = seq_old[static_cast<size_t>(parent) * T + e];
             if (lane == 0 && label >= 0) seq_new[static_cast<size_t>(r) * T + plen] = label;
@@ -378,17 +440,13 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
             if (slot == 0) continue;
             const int k = (slot - 1 < blank) ? slot - 1 : slot;
             const int last_i = b.last[i], len_i = b.len[i];
-            const double lmv = p.lm[static_cast<size_t>(len_i ? last_i : C) * (C + 1) + k];
+            const double lmv = lm[static_cast<size_t>(len_i ? last_i : C) * (C + 1) + k];
             if (lmv != lmv) s_flags[1] = 3;  // unit pair unknown to the LM -> KeyError in the reference
             const double lm_term = lmv * p.lm_alpha;
             const double base = (len_i && last_i == k && prev_blank_lt) ? b.blank[i] : b.total[i];
             const double score = logp[k] + lm_term + base;
             skey[pos] = score;
-            spos[pos] = pos;
-            pool_nb[pos] = score;
-            pool_bl[pos] = LOG_ZERO;
-            pool_parent[pos] = i;
-            pool_label[pos] = k;
+            tag[pos] = -1;
             // does y_i + (k,) coincide with a beam prefix y_j (which contributes its own "stay" entry)?
             const unsigned long long h = mix_hash(b.hash[i], k);
             unsigned int hs = static_cast<unsigned int>(h) & (HT - 1);
@@ -423,14 +481,12 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
                 home = pe < ps ? pe : ps;                 // the entry keeps its first insertion position
                 const int dead = pe < ps ? ps : pe;
                 skey[dead] = -INFINITY;
-                spos[dead] = dead;
+                tag[dead] = -1;
             }
             skey[home] = tot;
-            spos[home] = home;
-            pool_nb[home] = nb;
-            pool_bl[home] = bl;
-            pool_parent[home] = r;
-            pool_label[home] = -1;
+            tag[home] = static_cast<short>(r);
+            stay_nb[r] = nb;
+            stay_bl[r] = bl;
         }
         have_pool = true;
         __syncthreads();
@@ -450,7 +506,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, 1) beam_search_kernel(BeamParams
         // final LM step over the best W prefixes, length normalisation, arg-max (first best wins)
         for (int r = tid; r < nbeams; r += blockDim.x) {
             if (b.len[r] == 0) { s_flags[1] = 1; skey[r] = -INFINITY; spos[r] = r; continue; }  // classes[y[-1]] on ()
-            const double lmv = p.lm[static_cast<size_t>(b.last[r]) * (C + 1) + C];
+            const double lmv = lm[static_cast<size_t>(b.last[r]) * (C + 1) + C];
             if (lmv != lmv) s_flags[1] = 3;
             const double eos = b.total[r] + lmv * p.lm_alpha;
             skey[r] = eos * (1.0 / static_cast<double>(b.len[r]));
@@ -491,14 +547,16 @@ __global__ void exp_transpose_kernel(const float* __restrict__ lp, float* __rest
     }
 }
 
-size_t beam_smem_bytes(int W, int C, int P2) {
+size_t beam_smem_bytes(int W, int C, int P2, bool lm_in_smem) {
     int HT = 1;
     while (HT < 2 * W) HT <<= 1;
     size_t b = 0;
     b += sizeof(double) * (static_cast<size_t>(P2) + 6 * W + C);
     b += sizeof(unsigned long long) * (4 * static_cast<size_t>(W) + HT);
     b += sizeof(int) * (static_cast<size_t>(P2) + 4 * W + HT + W);
-    b += sizeof(float) * C;
+    b += sizeof(float) * (C + 1) + 16;                                   // prow + alignment of what follows
+    b += sizeof(double) * (2 * static_cast<size_t>(W) + (lm_in_smem ? static_cast<size_t>(C + 1) * (C + 1) : 0));   // stay_nb, stay_bl, LM
+    b += sizeof(short) * static_cast<size_t>(P2);                        // tag
     return b + 16;   // + static shared memory of the kernel (selection buffers, ~4.2 KB)
 }
 
@@ -508,8 +566,8 @@ size_t beam_smem_bytes(int W, int C, int P2) {
 using namespace ctcb200;
 
 extern "C" CTCB200_API int64_t ctcb200_beam_workspace_bytes(int T, int N, int C, int beam_width) {
-    const int64_t PC = static_cast<int64_t>(beam_width) * C;
-    return N * (PC * (8 + 8 + 4 + 4) + static_cast<int64_t>(2) * beam_width * T * 4) + 256;
+    (void)C;   // the candidate pool lives in shared memory; the workspace holds the two label-sequence buffers of every utterance
+    return N * (static_cast<int64_t>(2) * beam_width * T * 4) + 256;
 }
 
 extern "C" CTCB200_API int ctcb200_exp_transpose(const float* log_probs_tnc, float* probs_ntc, int T, int N, int C,
@@ -535,19 +593,17 @@ extern "C" CTCB200_API int ctcb200_beam_search(const float* probs_ntc, const int
     CTCB_REQUIRE(beam_width <= TOP_MAX, "beam_search: beam width %d exceeds the supported maximum %d", beam_width, TOP_MAX);
     CTCB_REQUIRE(lm_table != nullptr, "beam_search: a bigram LM table is required (the reference cannot run without one)");
     const int P2 = ((beam_width * C + 31) / 32) * 32;   // candidate capacity (no power-of-two padding: only the top W are sorted)
-    const size_t smem = beam_smem_bytes(beam_width, C, P2);
+    // the bigram table goes to shared memory when it fits beside the candidate pool
+    int lm_in_smem = 1;
+    size_t smem = beam_smem_bytes(beam_width, C, P2, true);
+    if (smem > 227 * 1024) { lm_in_smem = 0; smem = beam_smem_bytes(beam_width, C, P2, false); }
     CTCB_REQUIRE(smem <= 227 * 1024, "beam_search: beam_width*classes = %d needs %zu B of shared memory (max 227 KB)",
                  beam_width * C, smem);
     CTCB_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     BeamParams p;
     p.probs = probs_ntc; p.lengths = lengths; p.lm = lm_table; p.lm_alpha = lm_alpha;
-    p.T = T; p.N = N; p.C = C; p.W = beam_width; p.blank = blank; p.P2 = P2;
+    p.T = T; p.N = N; p.C = C; p.W = beam_width; p.blank = blank; p.P2 = P2; p.lm_in_smem = lm_in_smem;
     uint8_t* w = static_cast<uint8_t*>(workspace);
-    const size_t PC = static_cast<size_t>(beam_width) * C;
-    p.pool_nb = reinterpret_cast<double*>(w); w += sizeof(double) * N * PC;
-    p.pool_bl = reinterpret_cast<double*>(w); w += sizeof(double) * N * PC;
-    p.pool_parent = reinterpret_cast<int*>(w); w += sizeof(int) * N * PC;
-    p.pool_label = reinterpret_cast<int*>(w); w += sizeof(int) * N * PC;
     p.seq = reinterpret_cast<int*>(w);
     p.out_labels = out_labels; p.out_len = out_lengths; p.status = status;
     p.trace = nullptr;
