@@ -472,6 +472,8 @@ class _RnnStackFn(torch.autograd.Function):
             gate_ev, gate_ev_ptr = _resident_event(dev)
             side_ctas = max(8, torch.cuda.get_device_properties(dev).multi_processor_count
                             - int(_lib.lib().dll.ctcb200_lstm_bwd_ctas(N, H, model.batch_tile)))
+            if os.environ.get("CTCB200_SIDE_CTAS"):   # measurements: fewer CTAs for the side-stream GEMMs
+                side_ctas = max(8, min(side_ctas, int(os.environ["CTCB200_SIDE_CTAS"])))
 
         def _flat(sizes):
             """One flat fp32 buffer per layer (views per parameter): its all-reduce is a single collective."""
