@@ -222,6 +222,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major operand (element (mn, k) stored with mn contiguous), SWIZZLE_128B: the tile is a row of 8 KB boxes, each 64 K rows x
+// 64 mn elements (128-byte rows, exactly what a TMA box load writes); the canonical layout is ((8,n),(8,k)):((1,LBO),(8,SBO))
+// in 16-byte units — 8 chunks of a 128-byte row, then the next 64-wide mn group LBO = 8 KB further; 8 K rows 128 bytes apart,
+// then the next group of 8 K rows SBO = 1 KB further. One tcgen05.mma (K = 16) reads two such groups.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(8192 >> 4) << 16;    // LBO: next 64-element group along M / N
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO: next group of 8 K rows
+    d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+    return d;
+}
+
 // Same for SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row atoms 512 bytes apart, tile base 512-byte aligned.
 // Used for the recurrent kernels' B operand so that the 32 hidden units one CTA produces form one contiguous block.
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {

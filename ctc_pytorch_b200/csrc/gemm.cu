@@ -45,7 +45,7 @@ template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, void* __restrict__ Cout, long long ldc, int M, int N, int K,
-               int a_koff, int b_koff, int out_bf16, int accumulate, int tma_store, int split_k) {
+               int a_koff, int b_koff, int out_bf16, int accumulate, int tma_store, int split_k, int mn_major) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -98,8 +98,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, &full[stage], a_koff + kb * BK, m_blk * BM);
-                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], b_koff + kb * BK, n_blk * BN);
+                    if (mn_major) {
+                        // operands stored [K rows, M (N) columns]: boxes of 64 K rows x 64 columns (8 KB, SWIZZLE_128B), one per
+                        // 64-wide column group of the tile; the K offsets are ROW coordinates here (no alignment constraint)
+#pragma unroll
+                        for (int g = 0; g < BM / 64; ++g)
+                            tma_load_2d(sa + g * 8192, &tmA, &full[stage], m_blk * BM + g * 64, a_koff + kb * BK);
+#pragma unroll
+                        for (int g = 0; g < BN / 64; ++g)
+                            tma_load_2d(sa + Cfg::A_BYTES + g * 8192, &tmB, &full[stage], n_blk * BN + g * 64, b_koff + kb * BK);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full[stage], a_koff + kb * BK, m_blk * BM);
+                        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], b_koff + kb * BK, n_blk * BN);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -107,7 +118,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // the whole warp runs the (warp-uniform) pipeline bookkeeping so descriptors stay in uniform registers;
         // one elected lane issues the tcgen05 instructions
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc_k = umma_idesc_bf16(BM, BN);
+        // MN-major operands (both): bits 15 / 16 of the instruction descriptor select the transposed shared-memory layout
+        const uint32_t idesc = mn_major ? (idesc_k | (1u << 15) | (1u << 16)) : idesc_k;
         const bool leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
@@ -124,12 +137,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+                // K-major: a K=16 slice is 32 bytes along a 128-byte row; MN-major: 16 K rows = two 8-row groups of 1 KB
+                const uint64_t ad = mn_major ? umma_desc_mn_sw128(a_addr) : umma_desc_sw128(a_addr);
+                const uint64_t bd = mn_major ? umma_desc_mn_sw128(a_addr + Cfg::A_BYTES) : umma_desc_sw128(a_addr + Cfg::A_BYTES);
+                const uint64_t ks = mn_major ? (2048 >> 4) : 2;
                 if (leader) {
                     umma_bf16(d_tmem, ad, bd, idesc, kb != kb0 ? 1u : 0u);
-                    umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                    umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                    umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                    umma_bf16(d_tmem, ad + ks, bd + ks, idesc, 1u);
+                    umma_bf16(d_tmem, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+                    umma_bf16(d_tmem, ad + 3 * ks, bd + 3 * ks, idesc, 1u);
                     umma_commit(&empty[stage]);
                 }
                 __syncwarp();
@@ -255,7 +271,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int tma_store, int split_k,
                 void* C, long long ldc, int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
-                int max_ctas, cudaStream_t stream) {
+                int max_ctas, cudaStream_t stream, int mn_major = 0) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set[MAX_DEVICES] = {false};   // function attributes are per device (context)
     const int dev = current_device();
@@ -270,7 +286,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     int limit = max_ctas > 0 ? max_ctas : device_sm_count();
     int grid = (max_ctas < 0 || tiles < limit) ? tiles : limit;
     gemm_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, C, ldc, M, N, K, a_koff, b_koff, out_bf16,
-                                                              accumulate, tma_store, split_k);
+                                                              accumulate, tma_store, split_k, mn_major);
     CTCB_LAUNCH_CHECK();
     return OK;
 }
@@ -278,13 +294,13 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 }  // namespace
 
 // Internal entry used by the other translation units as well as the C ABI below.
-int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
-                 int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, int max_ctas,
-                 cudaStream_t stream) {
+static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
+                     int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, int max_ctas,
+                     cudaStream_t stream, int mn_major) {
     CTCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-    CTCB_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0 && a_koff >= 0 && b_koff >= 0,
-                 "gemm: K offsets (%d, %d) must be non-negative multiples of 8 (TMA box start is 16-byte aligned)", a_koff,
-                 b_koff);
+    CTCB_REQUIRE(a_koff >= 0 && b_koff >= 0 && (mn_major || (a_koff % 8 == 0 && b_koff % 8 == 0)),
+                 "gemm: K offsets (%d, %d) must be non-negative (multiples of 8 for K-major operands: TMA box start is 16-byte "
+                 "aligned)", a_koff, b_koff);
     int bn = force_bn;
     // SMs this launch may use: a positive max_ctas leaves the rest of the device to a concurrent kernel
     const int sms = (max_ctas > 0 && max_ctas < device_sm_count()) ? max_ctas : device_sm_count();
@@ -303,9 +319,16 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
     }
     CTCB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: tile width %d not in {64,128,256}", bn);
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_bf16_2d(&tmA, A, M, static_cast<uint64_t>(a_koff) + K, lda, BM, BK);
-    if (rc != OK) return rc;
-    rc = make_tmap_bf16_2d(&tmB, B, N, static_cast<uint64_t>(b_koff) + K, ldb, bn, BK);
+    int rc;
+    if (mn_major) {   // operands stored [K rows, M (N) columns]; out-of-range rows / columns of a box read as zero
+        rc = make_tmap_bf16_2d(&tmA, A, static_cast<uint64_t>(a_koff) + K, M, lda, BK, 64);
+        if (rc != OK) return rc;
+        rc = make_tmap_bf16_2d(&tmB, B, static_cast<uint64_t>(b_koff) + K, N, ldb, BK, 64);
+    } else {
+        rc = make_tmap_bf16_2d(&tmA, A, M, static_cast<uint64_t>(a_koff) + K, lda, BM, BK);
+        if (rc != OK) return rc;
+        rc = make_tmap_bf16_2d(&tmB, B, N, static_cast<uint64_t>(b_koff) + K, ldb, bn, BK);
+    }
     if (rc != OK) return rc;
     // fp32 results leave through TMA stores when the row pitch allows a tensor map (16-byte multiples)
     CUtensorMap tmC = tmA;
@@ -327,13 +350,30 @@ int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, voi
         if (split_k > 1 && !accumulate) CTCB_CUDA(cudaMemsetAsync(C, 0, static_cast<size_t>(M) * ldc * sizeof(float), stream));
     }
     switch (bn) {
-        case 64: return launch_gemm<64>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream);
-        case 128: return launch_gemm<128>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream);
-        default: return launch_gemm<256>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream);
+        case 64: return launch_gemm<64>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream, mn_major);
+        case 128: return launch_gemm<128>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream, mn_major);
+        default: return launch_gemm<256>(tmA, tmB, tmC, tma_store, split_k, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, max_ctas, stream, mn_major);
     }
 }
 
+int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
+                 int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, int max_ctas,
+                 cudaStream_t stream) {
+    return gemm_impl(A, lda, B, ldb, C, ldc, M, N, K, a_koff, b_koff, out_bf16, accumulate, force_bn, max_ctas, stream, 0);
+}
+
 }  // namespace ctcb200
+
+// C[M,N] (+)= A[a_roff : a_roff+K, 0:M]^T * B[b_roff : b_roff+K, 0:N]: both operands stored with the CONTRACTED index as the row
+// index (MN-major for the tensor core). This is the shape of every weight gradient (dW = dG^T X over the T*N rows of a batch):
+// the gate gradients and the activations are consumed as the recurrent kernels / the forward pass left them, no transposed
+// copies (round 1 spent 1.1 ms per cfg2 step on transpose_dg / cast_transpose kernels for the K-major form).
+extern "C" CTCB200_API int ctcb200_gemm_atb_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                                                 int M, int N, int K, int a_roff, int b_roff, int accumulate, int tile_n,
+                                                 int max_ctas, ctcb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    return ctcb200::gemm_impl(A, lda, B, ldb, C, ldc, M, N, K, a_roff, b_roff, 0, accumulate, tile_n, max_ctas, stream, 1);
+}
 
 extern "C" CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                     int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,

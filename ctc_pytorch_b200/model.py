@@ -94,6 +94,9 @@ class _Opnd(object):
     def rows(self, a, b):
         return _Opnd(self.hi[a:b], None if self.lo is None else self.lo[a:b])
 
+    def cols(self, a, b):
+        return _Opnd(self.hi[:, a:b], None if self.lo is None else self.lo[:, a:b])
+
 
 def _gemm(a, b, out=None, **kw):
     """C = A * B^T on the tcgen05 GEMM; in x3 mode the three products A_lo B_hi + A_hi B_lo + A_hi B_hi accumulate in fp32
@@ -104,6 +107,31 @@ def _gemm(a, b, out=None, **kw):
     ops.gemm_tn(a.hi, b.lo, out=out, accumulate=True, **kw)
     ops.gemm_tn(a.hi, b.hi, out=out, accumulate=True, **kw)
     return out
+
+
+def _gemm_atb(a, b, out=None, **kw):
+    """C = A^T * B, both operands with the contracted index as rows (the weight-gradient form, ops.gemm_atb); x3 mode: the same
+    three accumulated products as _gemm."""
+    if a.lo is None:
+        return ops.gemm_atb(a.hi, b.hi, out=out, **kw)
+    out = ops.gemm_atb(a.lo, b.hi, out=out, **kw)
+    ops.gemm_atb(a.hi, b.lo, out=out, accumulate=True, **kw)
+    ops.gemm_atb(a.hi, b.hi, out=out, accumulate=True, **kw)
+    return out
+
+
+_GATE_PERM = {}
+
+
+def _gate_row_perm(H, dev):
+    """Row gather that turns a [4H, ...] matrix whose rows follow the recurrent kernels' packed gate order (unit block j, unit u,
+    gate g -> row j*128 + u*4 + g: the column order of dG) into torch's order (row g*H + unit)."""
+    key = (H, str(dev))
+    if key not in _GATE_PERM:
+        unit = torch.arange(H, device=dev)
+        g = torch.arange(4, device=dev).view(4, 1)
+        _GATE_PERM[key] = ((unit // 32) * 128 + (unit % 32) * 4 + g).reshape(-1)     # [4H]: index of torch row g*H + unit
+    return _GATE_PERM[key]
 
 
 def _cast_t(src, s_outer, s_inner, n_inner, R, C, scale=None, shift=None, want=True, want_t=False, x3=False):
@@ -345,10 +373,11 @@ class _RnnStackFn(torch.autograd.Function):
         stream = _lib.stream
 
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
-        # With the overlapped weight-gradient pipeline the transposed operands (X^T, H^T) are only produced in the
-        # backward pass, on the side stream, so the forward pass does not pay for them.
+        # Weight gradients contract over the T*N rows: the tensor-core GEMM takes both operands in that (MN-major) form
+        # (ops.gemm_atb), so the padded model keeps the bf16 operands the forward pass makes anyway and never builds transposed
+        # copies. The packed model still uses transposed operands (K-major form) for its two alignments.
         defer_t = need_grad and _overlap_enabled(model) and not packed
-        want_t = need_grad and not defer_t
+        want_t = need_grad and packed
         ws.defer_t = defer_t
         if packed:
             # layer-0 input as a dense time-major [T, N, I0] tensor with zero padding, plus its right-aligned twin
@@ -399,11 +428,14 @@ class _RnnStackFn(torch.autograd.Function):
             _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout), _lib.ptr(c_save),
                   _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, cell, stream())
             del gx
-            rec.HT = None
+            rec.HT = rec.Hb = None
             p_drop = _layer_dropout_p(layer)
-            # H^T pairs dG_t with the *pre-dropout* h_{t-1}: it can only be deferred when hout is not modified in place
-            if need_grad and not (defer_t and not (training and p_drop > 0.0)):
+            # dW_hh pairs dG_t with the *pre-dropout* h_{t-1}: its bf16 copy can only be left to the backward pass when hout
+            # is not modified in place
+            if need_grad and packed:
                 _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True, x3=x3)
+            elif need_grad and training and p_drop > 0.0:
+                rec.Hb, _ = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
             rec.h_out = hout if need_grad else None
             if packed:
                 # kernel alignment (forward half left-, reverse half right-aligned, garbage in the padding) -> left-aligned
@@ -416,6 +448,7 @@ class _RnnStackFn(torch.autograd.Function):
                 rec.mask = _dropout_mask(model, hout.shape, p_drop, dev)
                 _call("ctcb200_dropout_apply", _lib.ptr(hout), _lib.ptr(rec.mask), _inv_keep(p_drop), hout.numel(), stream())
             rec.XT, rec.XrT, rec.h_in = XT, XrT, h_prev
+            rec.Xb = X if (need_grad and not packed) else None
             rec.c_save, rec.gates, rec.wihT_p, rec.whhT_p = c_save, gates, wihT_p, whhT_p
             ws.L.append(rec)
             h_prev = hout
@@ -427,7 +460,8 @@ class _RnnStackFn(torch.autograd.Function):
         C = fc_lin.weight.shape[0]
         ws.fc_bn = _bn_prepare(fc_bn, h_prev, R, F2, training, n_valid) if fc_bn is not None else None
         Xfc, XfcT = _cast_t(h_prev, N * F2, F2, N, R, F2, ws.fc_bn.scale if ws.fc_bn else None,
-                            ws.fc_bn.shift if ws.fc_bn else None, True, need_grad, x3)
+                            ws.fc_bn.shift if ws.fc_bn else None, True, need_grad and packed, x3)
+        ws.Xfc = Xfc if (need_grad and not packed) else None
         Wfc_b, WfcT_b = _cast_t(fc_lin.weight, F2, F2, 1, C, F2, want=True, want_t=need_grad, x3=x3)
         logits = _gemm(Xfc, Wfc_b, k=F2)  # [R, C]
         if packed:   # after pad_packed_sequence every padded frame is a zero vector
@@ -492,11 +526,14 @@ class _RnnStackFn(torch.autograd.Function):
             _call("ctcb200_log_softmax_bwd", _lib.ptr(g), _lib.ptr(ws.out), _lib.ptr(dlogits), R, C, stream())
         if packed:   # nothing flows into padded frames
             dlogits = _realign(dlogits, lengths, T, N, C, C, 1)
-        dLb, dLT = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=True, x3=x3)
+        dLb, dLT = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=packed, x3=x3)
         fc = _unwrap(model.fc)
         fc_bn, fc_lin = (fc[0], fc[1]) if isinstance(fc, nn.Sequential) else (None, fc)
         fc_buf, fc_views = _flat([C * F2] + ([F2, F2] if fc_bn is not None else []))
-        grads[fc_lin.weight] = _gemm(dLT, ws.XfcT, out=fc_views[0].view(C, F2), k=Rp)   # [C, 2H]
+        if packed:
+            grads[fc_lin.weight] = _gemm(dLT, ws.XfcT, out=fc_views[0].view(C, F2), k=Rp)   # [C, 2H]
+        else:
+            grads[fc_lin.weight] = _gemm_atb(dLb.cols(0, C), ws.Xfc.cols(0, F2), out=fc_views[0].view(C, F2), k=R)
         dh = _gemm(dLb, ws.WfcT_b, k=C)                                                # [R, 2H]
         dws = torch.empty(2 * F2, dtype=torch.float64, device=dev)
         fuse_env = os.environ.get("CTCB200_BN_FUSE", "1") != "0"
@@ -536,6 +573,42 @@ class _RnnStackFn(torch.autograd.Function):
             rnn = layer_.rnn
             GH = rec_.G * H     # rows of torch's weight matrices per direction (4H LSTM, 3H GRU, H RNN)
             I_ = rec_.I
+            if not packed:
+                # contraction over the T*N rows with both operands as they are (ops.gemm_atb): gate gradients [R, 8H] from the
+                # BPTT kernel, layer input [R, I] bf16 from the forward pass, layer output [R, 2H] cast here
+                Xb, Hb = rec_.Xb, rec_.Hb
+                if Hb is None:
+                    Hb, _ = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
+                # the products come out with their rows in dG's packed gate order; one row gather each puts them into torch's
+                perm = _gate_row_perm(H, dev)
+                dwih = views_[0].view(8 * H, I_)
+                tmp = _gemm_atb(dg_, Xb.cols(0, I_), k=R, max_ctas=mc)                       # [8H, I]
+                torch.index_select(tmp[:4 * H], 0, perm, out=dwih[:4 * H])
+                torch.index_select(tmp[4 * H:], 0, perm, out=dwih[4 * H:])
+                grads[rnn.weight_ih_l0] = dwih[:GH]
+                whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
+                dgr_ = dgrec_ if dgrec_ is not None else dg_     # what the recurrent weights see (GRU differs)
+                if T > 1:
+                    # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan: one time step = N rows
+                    t1 = _gemm_atb(dgr_.cols(0, 4 * H), Hb.cols(0, H), a_roff=N, b_roff=0, k=R - N, max_ctas=mc)
+                    torch.index_select(t1, 0, perm, out=whf)
+                    tmp = (tmp, t1)
+                    if D == 2:
+                        t2 = _gemm_atb(dgr_.cols(4 * H, 8 * H), Hb.cols(H, 2 * H), a_roff=0, b_roff=N, k=R - N, max_ctas=mc)
+                        torch.index_select(t2, 0, perm, out=whr)
+                        tmp = tmp + (t2,)
+                else:
+                    whf.zero_()
+                    whr.zero_()
+                grads[rnn.weight_hh_l0] = whf[:GH]
+                if D == 2:
+                    grads[rnn.weight_ih_l0_reverse], grads[rnn.weight_hh_l0_reverse] = dwih[4 * H:4 * H + GH], whr[:GH]
+                if sync is not None:
+                    sync.reduce(buf_)    # one collective per layer, behind the BPTT kernels of the layers below
+                if torch.cuda.current_stream(dev) != main:  # allocated on the main stream, written here on the side stream
+                    buf_.record_stream(torch.cuda.current_stream(dev))
+                keep.append((dg_, dgrec_, Xb, Hb, tmp))  # alive until the streams are joined
+                return
             XT, HT = rec_.XT, rec_.HT
             if XT is None:   # deferred transposed operands (see forward)
                 if li_ == 0:

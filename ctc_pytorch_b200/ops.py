@@ -28,6 +28,24 @@ def gemm_tn(a, b, out=None, out_dtype=torch.float32, accumulate=False, a_koff=0,
     return out
 
 
+def gemm_atb(a, b, out=None, accumulate=False, a_roff=0, b_roff=0, k=None, tile_n=0, max_ctas=0):
+    """C[M,N] (+)= A[a_roff:a_roff+K, :]^T @ B[b_roff:b_roff+K, :] on the tcgen05 tensor cores (MN-major operands): the
+    weight-gradient form, operands as the forward / BPTT kernels left them (rows = the T*N frames)."""
+    _lib.require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "gemm_atb takes bf16 operands"
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, N = a.shape[1], b.shape[1]
+    if k is None:
+        k = a.shape[0] - a_roff
+    assert a_roff + k <= a.shape[0] and b_roff + k <= b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert out.shape[0] == M and out.shape[1] == N and out.stride(1) == 1 and out.dtype == torch.float32
+    _lib.lib().call("ctcb200_gemm_atb_bf16", _lib.ptr(a), a.stride(0), _lib.ptr(b), b.stride(0), _lib.ptr(out), out.stride(0),
+                    M, N, k, a_roff, b_roff, 1 if accumulate else 0, tile_n, max_ctas, _lib.stream())
+    return out
+
+
 @_lib.on_tensor_device
 def argmax_nt(log_probs, want_max=False):
     """Frame arg-max of [T,N,C] log-probs -> int32 [N,T] (first index on ties), optionally the max values."""

@@ -94,6 +94,15 @@ CTCB200_API int ctcb200_pad_labels(const int64_t* labels, const int64_t* offsets
 CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                      int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
                                      int tile_n, int max_ctas, ctcb200_stream_t stream);
+/* Weight-gradient form: C[M,N] (+)= A[a_roff : a_roff+K, 0:M]^T * B[b_roff : b_roff+K, 0:N] — both operands bf16 with the
+ * CONTRACTED index as the row index (pitches lda / ldb in elements, multiples of 8), C f32. a_roff / b_roff shift the row
+ * window of each operand (any value: the h_{t-1} shift of dW_hh is N rows); rows and columns outside a tensor read as zero.
+ * The operands are consumed as the forward pass / ctcb200_lstm_bwd left them (activations [T*N, I], gate gradients [T*N, 8H]):
+ * no transposed copies. Carries dW_ih, dW_hh, dW_fc of autograd's nn.LSTM / nn.Linear backward (train_ctc.py:63). */
+CTCB200_API int ctcb200_gemm_atb_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int M, int N,
+                                      int K, int a_roff, int b_roff, int accumulate, int tile_n, int max_ctas,
+                                      ctcb200_stream_t stream);
+
 
 /* ---- bidirectional LSTM layer: replaces nn.LSTM(bias=False, bidirectional=True) fwd/bwd time loops,
  * timit/models/model_ctc.py:23-26,33 and the BPTT behind timit/steps/train_ctc.py:63.

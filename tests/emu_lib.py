@@ -97,6 +97,15 @@ class Emu(object):
         else:
             C[:M, :N] = prod.to(C.dtype)
 
+    def gemm_atb_bf16(self, A, lda, B, ldb, C, ldc, M, N, K, a_roff, b_roff, accumulate, tile_n, max_ctas, stream):
+        assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+        assert A.stride(0) == lda and B.stride(0) == ldb and C.stride(0) == ldc
+        prod = A[a_roff:a_roff + K, :M].float().t() @ B[b_roff:b_roff + K, :N].float()
+        if accumulate:
+            C[:M, :N] += prod
+        else:
+            C[:M, :N] = prod
+
     # ---- recurrent kernels ------------------------------------------------------------------------------------------
     @staticmethod
     def _unpack_cols(H):
