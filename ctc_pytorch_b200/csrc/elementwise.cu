@@ -7,7 +7,6 @@
 //   bn_stats/finalize   training-mode BatchNorm1d statistics over T*N rows (model_ctc.py:29-32,136)
 //   bn_bwd_reduce/apply BatchNorm backward
 //   log_softmax fwd/bwd nn.LogSoftmax(dim=-1) (model_ctc.py:140,168)
-//   transpose_dg        dG bf16 [R,8H] (packed gate order) -> dG^T bf16 [8H,R] in torch's gate order
 //
 // All are grid-stride / tiled streaming kernels: coalesced 128-byte rows, 32x33 shared-memory tiles
 // for the transposes, grids sized in multiples of the SM count.
@@ -175,52 +174,6 @@ cast_transpose_v2_kernel(const float* __restrict__ src, long long s_outer, long 
     }
 }
 
-// dG [R, 8H] bf16 with packed gate columns -> dG^T [8H, Rp] bf16 with rows in torch order (dir, q, unit).
-// 64 x 64 tiles, 4-byte (bf16x2) global accesses on both sides: 128-byte rows in, 128-byte rows out.
-__global__ void __launch_bounds__(256)
-transpose_dg_kernel(const __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ dgT, long long dgT_pitch,
-                    int n_inner, int n_pad, int R, int H) {
-    __shared__ __nv_bfloat16 tile[64][66];
-    const int G8 = 8 * H, G4 = 4 * H;
-    const int tiles_c = G8 / 64, tiles_r = (R + 63) / 64;
-    const long long tiles = static_cast<long long>(tiles_c) * tiles_r;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    const bool fast_rows = (n_inner == n_pad) && (R % 2 == 0);  // output columns are the input rows, pairs stay adjacent
-    for (long long tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
-        const int r0 = static_cast<int>(tile_id / tiles_c) * 64, c0 = static_cast<int>(tile_id % tiles_c) * 64;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int r = r0 + ty + 8 * k;
-            __nv_bfloat162 v = __floats2bfloat162_rn(0.0f, 0.0f);
-            if (r < R) v = *reinterpret_cast<const __nv_bfloat162*>(dg + static_cast<long long>(r) * G8 + c0 + 2 * tx);
-            tile[ty + 8 * k][2 * tx] = v.x;
-            tile[ty + 8 * k][2 * tx + 1] = v.y;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int cc = c0 + ty + 8 * k;
-            const int dir = cc / G4, orow = dir * G4 + packed_to_orig_row(cc % G4, H);
-            const int rr = r0 + 2 * tx;
-            __nv_bfloat16* orow_p = dgT + static_cast<long long>(orow) * dgT_pitch;
-            if (fast_rows) {
-                if (rr < R) {
-                    __nv_bfloat162 v;
-                    v.x = tile[2 * tx][ty + 8 * k];
-                    v.y = tile[2 * tx + 1][ty + 8 * k];
-                    *reinterpret_cast<__nv_bfloat162*>(orow_p + rr) = v;
-                }
-            } else {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = rr + h;
-                    if (r < R) orow_p[static_cast<long long>(r / n_inner) * n_pad + r % n_inner] = tile[2 * tx + h][ty + 8 * k];
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
 
 // ---- BatchNorm ------------------------------------------------------------------------------------
 // partial column sums over a slab of rows; double atomics into ws[0..C) (sum) and ws[C..2C) (sum of squares)
@@ -610,17 +563,6 @@ extern "C" CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_ou
     return OK;
 }
 
-extern "C" CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64_t dgT_pitch, int n_inner, int n_pad,
-                                                int R, int H, ctcb200_stream_t stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    CTCB_REQUIRE(R > 0 && H % 32 == 0 && (dgT_pitch % 2) == 0, "transpose_dg: bad sizes R=%d H=%d", R, H);
-    const long long tiles = static_cast<long long>((R + 63) / 64) * (8 * H / 64);
-    transpose_dg_kernel<<<stream_grid(tiles, 1), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dg),
-                                                                 static_cast<__nv_bfloat16*>(dgT), dgT_pitch, n_inner,
-                                                                 n_pad, R, H);
-    CTCB_LAUNCH_CHECK();
-    return OK;
-}
 
 // ws: 2*C doubles of scratch. Training statistics over R rows; writes mean/rstd (saved for backward),
 // scale/shift (the affine cast_transpose applies) and updates the running statistics like nn.BatchNorm1d.

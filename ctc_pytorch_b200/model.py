@@ -358,8 +358,6 @@ class _RnnStackFn(torch.autograd.Function):
         training = model.training
         x3 = model.precision == "x3"
         R = T * N
-        Np = _round_up(N, 8)
-        Rp = T * Np  # width of the time-major transposed operands (batch axis padded to 8)
         H = model.rnn_param["rnn_hidden_size"]
         C = model.num_class
         D = 2 if model.rnn_param["bidirectional"] else 1   # D = 1: forward half only (see _packed_weights)
@@ -374,10 +372,8 @@ class _RnnStackFn(torch.autograd.Function):
 
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
         # Weight gradients contract over the T*N rows: the tensor-core GEMM takes both operands in that (MN-major) form
-        # (ops.gemm_atb), so the padded model keeps the bf16 operands the forward pass makes anyway and never builds transposed
-        # copies. The packed model still uses transposed operands (K-major form) for its two alignments.
-        defer_t = need_grad and _overlap_enabled(model) and not packed
-        want_t = need_grad and packed
+        # (ops.gemm_atb), so the bf16 operands the forward pass makes anyway are kept and no transposed copies are built.
+        defer_t = need_grad and _overlap_enabled(model) and not packed   # overlapped weight-gradient pipeline in backward()
         ws.defer_t = defer_t
         if packed:
             # layer-0 input as a dense time-major [T, N, I0] tensor with zero padding, plus its right-aligned twin
@@ -385,13 +381,12 @@ class _RnnStackFn(torch.autograd.Function):
                 raise RuntimeError("packed mode takes the input as a contiguous time-major [T, N, F] tensor")
             x_l = _realign(x_src, lengths, T, N, I0, I0, 1)       # padding rows zeroed
             x_r = _realign(x_l, lengths, T, N, I0, 0, -1)
-            X, XT = _cast_t(x_l, N * I0, I0, N, R, I0, want=True, want_t=want_t, x3=x3)
-            Xr, XrT = _cast_t(x_r, N * I0, I0, N, R, I0, want=True, want_t=want_t, x3=x3)
+            X, _ = _cast_t(x_l, N * I0, I0, N, R, I0, want=True, want_t=False, x3=x3)
+            Xr, _ = _cast_t(x_r, N * I0, I0, N, R, I0, want=True, want_t=False, x3=x3)
             del x_r
         else:
-            X, XT = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=want_t, x3=x3)
-            Xr = XrT = None
-        ws.x_src = x_src if defer_t else None
+            X, _ = _cast_t(x_src, s_outer, s_inner, N, R, I0, want=True, want_t=False, x3=x3)
+            Xr = None
         h_prev = None
         I = I0
         for li, layer in enumerate(layers):
@@ -408,9 +403,9 @@ class _RnnStackFn(torch.autograd.Function):
                     sc_, sh_ = rec.bn.scale, rec.bn.shift
                 else:
                     sc_ = sh_ = None
-                X, XT = _cast_t(h_prev, N * I, I, N, R, I, sc_, sh_, True, want_t, x3)
+                X, _ = _cast_t(h_prev, N * I, I, N, R, I, sc_, sh_, True, False, x3)
                 if packed:   # the BatchNorm affine turns zero padding into `shift`: harmless, those rows are never consumed
-                    Xr, XrT = _cast_t(h_prev_r, N * I, I, N, R, I, sc_, sh_, True, want_t, x3)
+                    Xr, _ = _cast_t(h_prev_r, N * I, I, N, R, I, sc_, sh_, True, False, x3)
                     del h_prev_r
             Ipad = _round_up(I, 8)
             wih_p, wihT_p, whh_p, whhT_p = _packed_weights(model, li, layer.rnn, H, I, Ipad, x3, dev)
@@ -428,13 +423,11 @@ class _RnnStackFn(torch.autograd.Function):
             _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout), _lib.ptr(c_save),
                   _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, cell, stream())
             del gx
-            rec.HT = rec.Hb = None
+            rec.Hb = None
             p_drop = _layer_dropout_p(layer)
             # dW_hh pairs dG_t with the *pre-dropout* h_{t-1}: its bf16 copy can only be left to the backward pass when hout
             # is not modified in place
-            if need_grad and packed:
-                _, rec.HT = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True, x3=x3)
-            elif need_grad and training and p_drop > 0.0:
+            if need_grad and training and p_drop > 0.0 and not packed:
                 rec.Hb, _ = _cast_t(hout, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
             rec.h_out = hout if need_grad else None
             if packed:
@@ -447,8 +440,9 @@ class _RnnStackFn(torch.autograd.Function):
             if training and p_drop > 0.0:
                 rec.mask = _dropout_mask(model, hout.shape, p_drop, dev)
                 _call("ctcb200_dropout_apply", _lib.ptr(hout), _lib.ptr(rec.mask), _inv_keep(p_drop), hout.numel(), stream())
-            rec.XT, rec.XrT, rec.h_in = XT, XrT, h_prev
-            rec.Xb = X if (need_grad and not packed) else None
+            rec.h_in = h_prev
+            rec.Xb = X if need_grad else None
+            rec.Xrb = Xr if (need_grad and packed) else None
             rec.c_save, rec.gates, rec.wihT_p, rec.whhT_p = c_save, gates, wihT_p, whhT_p
             ws.L.append(rec)
             h_prev = hout
@@ -459,9 +453,9 @@ class _RnnStackFn(torch.autograd.Function):
         fc_bn, fc_lin = (fc[0], fc[1]) if isinstance(fc, nn.Sequential) else (None, fc)
         C = fc_lin.weight.shape[0]
         ws.fc_bn = _bn_prepare(fc_bn, h_prev, R, F2, training, n_valid) if fc_bn is not None else None
-        Xfc, XfcT = _cast_t(h_prev, N * F2, F2, N, R, F2, ws.fc_bn.scale if ws.fc_bn else None,
-                            ws.fc_bn.shift if ws.fc_bn else None, True, need_grad and packed, x3)
-        ws.Xfc = Xfc if (need_grad and not packed) else None
+        Xfc, _ = _cast_t(h_prev, N * F2, F2, N, R, F2, ws.fc_bn.scale if ws.fc_bn else None,
+                            ws.fc_bn.shift if ws.fc_bn else None, True, False, x3)
+        ws.Xfc = Xfc if need_grad else None
         Wfc_b, WfcT_b = _cast_t(fc_lin.weight, F2, F2, 1, C, F2, want=True, want_t=need_grad, x3=x3)
         logits = _gemm(Xfc, Wfc_b, k=F2)  # [R, C]
         if packed:   # after pad_packed_sequence every padded frame is a zero vector
@@ -473,8 +467,8 @@ class _RnnStackFn(torch.autograd.Function):
         else:
             out = torch.empty((T, N, C), dtype=torch.float32, device=dev)
             _call("ctcb200_log_softmax_fwd", _lib.ptr(logits), logits.stride(0), _lib.ptr(out), R, C, stream())
-        ws.h_last, ws.XfcT, ws.WfcT_b, ws.out = h_prev, XfcT, WfcT_b, out
-        ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np = T, N, H, C, R, Rp, Np
+        ws.h_last, ws.WfcT_b, ws.out = h_prev, WfcT_b, out
+        ws.T, ws.N, ws.H, ws.C, ws.R = T, N, H, C, R
         ctx.ws = ws if need_grad else None
         ctx.model = model
         ctx.param_list = params
@@ -485,7 +479,7 @@ class _RnnStackFn(torch.autograd.Function):
         ws, model = ctx.ws, ctx.model
         if ws is None:
             raise RuntimeError("backward through a forward pass that ran without gradient bookkeeping")
-        T, N, H, C, R, Rp, Np = ws.T, ws.N, ws.H, ws.C, ws.R, ws.Rp, ws.Np
+        T, N, H, C, R = ws.T, ws.N, ws.H, ws.C, ws.R
         x3, D = ws.x3, ws.D
         lengths, n_valid = ws.lengths, ws.n_valid
         packed = lengths is not None
@@ -526,14 +520,11 @@ class _RnnStackFn(torch.autograd.Function):
             _call("ctcb200_log_softmax_bwd", _lib.ptr(g), _lib.ptr(ws.out), _lib.ptr(dlogits), R, C, stream())
         if packed:   # nothing flows into padded frames
             dlogits = _realign(dlogits, lengths, T, N, C, C, 1)
-        dLb, dLT = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=packed, x3=x3)
+        dLb, _ = _cast_t(dlogits, N * C, C, N, R, C, want=True, want_t=False, x3=x3)
         fc = _unwrap(model.fc)
         fc_bn, fc_lin = (fc[0], fc[1]) if isinstance(fc, nn.Sequential) else (None, fc)
         fc_buf, fc_views = _flat([C * F2] + ([F2, F2] if fc_bn is not None else []))
-        if packed:
-            grads[fc_lin.weight] = _gemm(dLT, ws.XfcT, out=fc_views[0].view(C, F2), k=Rp)   # [C, 2H]
-        else:
-            grads[fc_lin.weight] = _gemm_atb(dLb.cols(0, C), ws.Xfc.cols(0, F2), out=fc_views[0].view(C, F2), k=R)
+        grads[fc_lin.weight] = _gemm_atb(dLb.cols(0, C), ws.Xfc.cols(0, F2), out=fc_views[0].view(C, F2), k=R)   # [C, 2H]
         dh = _gemm(dLb, ws.WfcT_b, k=C)                                                # [R, 2H]
         dws = torch.empty(2 * F2, dtype=torch.float64, device=dev)
         fuse_env = os.environ.get("CTCB200_BN_FUSE", "1") != "0"
@@ -573,77 +564,36 @@ class _RnnStackFn(torch.autograd.Function):
             rnn = layer_.rnn
             GH = rec_.G * H     # rows of torch's weight matrices per direction (4H LSTM, 3H GRU, H RNN)
             I_ = rec_.I
-            if not packed:
-                # contraction over the T*N rows with both operands as they are (ops.gemm_atb): gate gradients [R, 8H] from the
-                # BPTT kernel, layer input [R, I] bf16 from the forward pass, layer output [R, 2H] cast here
-                Xb, Hb = rec_.Xb, rec_.Hb
-                if Hb is None:
-                    Hb, _ = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
-                # the products come out with their rows in dG's packed gate order; one row gather each puts them into torch's
-                perm = _gate_row_perm(H, dev)
-                dwih = views_[0].view(8 * H, I_)
-                tmp = _gemm_atb(dg_, Xb.cols(0, I_), k=R, max_ctas=mc)                       # [8H, I]
+            # contraction over the T*N rows with both operands as they are (ops.gemm_atb): gate gradients [R, 8H] from the
+            # BPTT kernel, layer input [R, I] bf16 from the forward pass, layer output [R, 2H] cast here
+            Xb, Hb = rec_.Xb, rec_.Hb
+            if Hb is None:
+                Hb, _ = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
+            # the products come out with their rows in dG's packed gate order; one row gather each puts them into torch's
+            perm = _gate_row_perm(H, dev)
+            dwih = views_[0].view(8 * H, I_)
+            if packed:   # each direction against the input in its own alignment
+                tmp = (_gemm_atb(dg_.cols(0, 4 * H), Xb.cols(0, I_), k=R, max_ctas=mc),
+                       _gemm_atb(dg_.cols(4 * H, 8 * H), rec_.Xrb.cols(0, I_), k=R, max_ctas=mc))
+                torch.index_select(tmp[0], 0, perm, out=dwih[:4 * H])
+                torch.index_select(tmp[1], 0, perm, out=dwih[4 * H:])
+            else:
+                tmp = _gemm_atb(dg_, Xb.cols(0, I_), k=R, max_ctas=mc)                   # [8H, I]
                 torch.index_select(tmp[:4 * H], 0, perm, out=dwih[:4 * H])
                 torch.index_select(tmp[4 * H:], 0, perm, out=dwih[4 * H:])
-                grads[rnn.weight_ih_l0] = dwih[:GH]
-                whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
-                dgr_ = dgrec_ if dgrec_ is not None else dg_     # what the recurrent weights see (GRU differs)
-                if T > 1:
-                    # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan: one time step = N rows
-                    t1 = _gemm_atb(dgr_.cols(0, 4 * H), Hb.cols(0, H), a_roff=N, b_roff=0, k=R - N, max_ctas=mc)
-                    torch.index_select(t1, 0, perm, out=whf)
-                    tmp = (tmp, t1)
-                    if D == 2:
-                        t2 = _gemm_atb(dgr_.cols(4 * H, 8 * H), Hb.cols(H, 2 * H), a_roff=0, b_roff=N, k=R - N, max_ctas=mc)
-                        torch.index_select(t2, 0, perm, out=whr)
-                        tmp = tmp + (t2,)
-                else:
-                    whf.zero_()
-                    whr.zero_()
-                grads[rnn.weight_hh_l0] = whf[:GH]
-                if D == 2:
-                    grads[rnn.weight_ih_l0_reverse], grads[rnn.weight_hh_l0_reverse] = dwih[4 * H:4 * H + GH], whr[:GH]
-                if sync is not None:
-                    sync.reduce(buf_)    # one collective per layer, behind the BPTT kernels of the layers below
-                if torch.cuda.current_stream(dev) != main:  # allocated on the main stream, written here on the side stream
-                    buf_.record_stream(torch.cuda.current_stream(dev))
-                keep.append((dg_, dgrec_, Xb, Hb, tmp))  # alive until the streams are joined
-                return
-            XT, HT = rec_.XT, rec_.HT
-            if XT is None:   # deferred transposed operands (see forward)
-                if li_ == 0:
-                    _, XT = _cast_t(ws.x_src, ws.geom[3], ws.geom[4], N, R, I_, want=False, want_t=True, x3=x3)
-                elif rec_.bn is not None:
-                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, rec_.bn.scale, rec_.bn.shift, False, True, x3)
-                else:
-                    _, XT = _cast_t(rec_.h_in, N * I_, I_, N, R, I_, None, None, False, True, x3)
-            if HT is None:
-                _, HT = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=False, want_t=True, x3=x3)
-            def _transposed(o_):
-                ts = []
-                for d_ in (o_.hi, o_.lo):
-                    if d_ is None:
-                        ts.append(None)
-                        continue
-                    t_ = (torch.empty if Np == N else torch.zeros)((8 * H, Rp), dtype=torch.bfloat16, device=dev)
-                    _call("ctcb200_transpose_dg", _lib.ptr(d_), _lib.ptr(t_), Rp, N, Np, R, H, stream())
-                    ts.append(t_)
-                return _Opnd(ts[0], ts[1])
-            dgT = _transposed(dg_)
-            dgT_rec = _transposed(dgrec_) if dgrec_ is not None else dgT     # what the recurrent weights see (GRU differs)
-            if packed:   # each direction against the input in its own alignment
-                dwih = views_[0].view(8 * H, I_)
-                _gemm(dgT.rows(0, 4 * H), XT, out=dwih[:4 * H], k=Rp, max_ctas=mc)
-                _gemm(dgT.rows(4 * H, 8 * H), rec_.XrT, out=dwih[4 * H:], k=Rp, max_ctas=mc)
-            else:
-                dwih = _gemm(dgT, XT, out=views_[0].view(8 * H, I_), k=Rp, max_ctas=mc)     # [8H, I], torch row order
+                tmp = (tmp,)
             grads[rnn.weight_ih_l0] = dwih[:GH]
             whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
+            dgr_ = dgrec_ if dgrec_ is not None else dg_     # what the recurrent weights see (GRU differs)
             if T > 1:
-                K = Rp - Np  # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan
-                _gemm(dgT_rec.rows(0, 4 * H), HT.rows(0, H), out=whf, a_koff=Np, b_koff=0, k=K, max_ctas=mc)
+                # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan: one time step = N rows
+                t1 = _gemm_atb(dgr_.cols(0, 4 * H), Hb.cols(0, H), a_roff=N, b_roff=0, k=R - N, max_ctas=mc)
+                torch.index_select(t1, 0, perm, out=whf)
+                tmp = tmp + (t1,)
                 if D == 2:
-                    _gemm(dgT_rec.rows(4 * H, 8 * H), HT.rows(H, 2 * H), out=whr, a_koff=0, b_koff=Np, k=K, max_ctas=mc)
+                    t2 = _gemm_atb(dgr_.cols(4 * H, 8 * H), Hb.cols(H, 2 * H), a_roff=0, b_roff=N, k=R - N, max_ctas=mc)
+                    torch.index_select(t2, 0, perm, out=whr)
+                    tmp = tmp + (t2,)
             else:
                 whf.zero_()
                 whr.zero_()
@@ -654,7 +604,7 @@ class _RnnStackFn(torch.autograd.Function):
                 sync.reduce(buf_)    # one collective per layer, behind the BPTT kernels of the layers below
             if torch.cuda.current_stream(dev) != main:  # allocated on the main stream, written here on the side stream
                 buf_.record_stream(torch.cuda.current_stream(dev))
-            keep.append((dg_, dgrec_, dgT, dgT_rec, XT, HT))  # alive until the streams are joined
+            keep.append((dg_, dgrec_, Xb, Hb, tmp))  # alive until the streams are joined
 
         pending = None
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)

@@ -166,9 +166,7 @@ CTCB200_API int ctcb200_cast_transpose(const float* src, int64_t s_outer, int64_
                                        const float* scale, const float* shift, void* dst, int64_t dst_pitch,
                                        void* dstT, int64_t dstT_pitch, int n_pad, int R, int C, int part,
                                        ctcb200_stream_t stream);
-/* dg bf16 [R, 8H] (wih_p column order) -> dgT bf16 [8H, dgT_pitch] with rows in torch gate order (dir, gate, unit) */
-CTCB200_API int ctcb200_transpose_dg(const void* dg, void* dgT, int64_t dgT_pitch, int n_inner, int n_pad, int R,
-                                     int H, ctcb200_stream_t stream);
+
 /* ws: 2*C doubles. Batch statistics over R rows of x f32 [R, C]; mean/rstd saved for backward, scale/shift =
  * the affine to apply (gamma*rstd, beta - mean*gamma*rstd); running stats updated with `momentum`
  * (unbiased variance), pass NULL to skip. */

@@ -63,11 +63,6 @@ class Emu(object):
             cols = (torch.arange(R) // n_inner) * n_pad + torch.arange(R) % n_inner
             dstT[:, cols] = _part(v, part).t()
 
-    def transpose_dg(self, dg, dgT, pitch, n_inner, n_pad, R, H, stream):
-        rows = torch.tensor([d * 4 * H + _orig_row(p, H) for d in range(2) for p in range(4 * H)])
-        cols = (torch.arange(R) // n_inner) * n_pad + torch.arange(R) % n_inner
-        dgT[rows[:, None], cols[None, :]] = dg.t()
-
     def realign_rows(self, src, dst, lengths, T, N, W, split, direction, accumulate, stream):
         s = src.detach().reshape(T, N, W).clone()
         out = torch.zeros(T, N, W)
