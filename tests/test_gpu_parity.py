@@ -284,6 +284,30 @@ def test_gemm_vs_fp32(M, N, K):
     assert relnorm(acc, 2 * ref) < (1e-5 if K <= 4096 else 1e-4), relnorm(acc, 2 * ref)
 
 
+@pytest.mark.parametrize("K,M,N,a_roff,b_roff", [(1000, 200, 72, 0, 0), (70, 64, 40, 3, 0), (25568, 2048, 512, 32, 0),
+                                                (25568, 2048, 512, 0, 32), (4097, 4096, 1024, 0, 0), (9, 136, 8, 1, 2)])
+def test_gemm_atb_vs_fp32(K, M, N, a_roff, b_roff):
+    """The weight-gradient form C = A^T B (MN-major tcgen05 operands): ragged K (tail rows beyond the window read as zero),
+    row offsets that are not multiples of anything, M / N that are not multiples of the 64-column boxes, column-slice views,
+    accumulation, every tile width."""
+    from ctc_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(K + M + N)
+    rows_a, rows_b = a_roff + K + 5, b_roff + K + 2              # extra rows after the window must not be read
+    A = torch.randn(rows_a, M + 8, generator=g).bfloat16().to(DEV)
+    B = torch.randn(rows_b, N + 16, generator=g).bfloat16().to(DEV)
+    a, b = A[:, 8:], B[:, :N]                                     # views: 16-byte aligned base, pitch > width
+    ref = a[a_roff:a_roff + K].float().t() @ b[b_roff:b_roff + K].float()
+    tol = 1e-5 if K <= 4097 else 1e-4
+    for tile in (0, 64, 128, 256):
+        c = ops.gemm_atb(a, b, a_roff=a_roff, b_roff=b_roff, k=K, tile_n=tile)
+        assert relnorm(c, ref) < tol, (tile, relnorm(c, ref))
+    acc = ops.gemm_atb(a, b, out=ref.clone(), accumulate=True, a_roff=a_roff, b_roff=b_roff, k=K)
+    assert relnorm(acc, 2 * ref) < tol, relnorm(acc, 2 * ref)
+    side = ops.gemm_atb(a, b, a_roff=a_roff, b_roff=b_roff, k=K, max_ctas=40)    # capped CTA count (side-stream use)
+    assert relnorm(side, ref) < tol
+    _report("gemm_atb", dict(K=K, M=M, N=N, a_roff=a_roff, b_roff=b_roff, rel_err=relnorm(c, ref)))
+
+
 # ---------------------------------------------------------------------------------------------- model
 def _golden_model(golden_dir, name):
     from ctc_pytorch_b200.model import CTC_Model
