@@ -18,12 +18,15 @@
 // Kernels in this file (DESIGN.md §3.2 has the measurements):
 //   lstm_fwd_pipe_kernel   default forward for H <= 512: two 8-column halves software-pipelined over element,
 //                          tensor-core and copy warps; gx arrives as TMA boxes
-//   lstm_fwd_kernel<NB,EX,X3> un-pipelined forward; EX selects the exchange (3 = bulk DSMEM copies inside one cluster,
+//   lstm_fwd_kernel<NB,EX,X3,CELL> un-pipelined forward; EX selects the exchange (3 = bulk DSMEM copies inside one cluster,
 //                          0 = global image + counter, cooperative launch: the fallback when no cluster fits)
-//   lstm_bwd_kernel<NB,EX,X3> BPTT: CTA (q, mb) of a (4, H/128) cluster holds gate q's transposed slice for 128 units; the
+//   lstm_bwd_kernel<NB,EX,X3,CELL> BPTT: CTA (q, mb) of a (4, H/128) cluster holds gate q's transposed slice for 128 units; the
 //                          four gate partials are reduce-scattered (fp16 on the wire), the dG blocks all-gathered
 //   X3 = split-operand mode (precision "x3"): every product is W_hi h_hi + W_hi h_lo + W_lo h_hi on bf16 hi/lo halves,
-//                          fp32 hand-offs and fp32 saved gates: the path whose gradients meet the reference's fp32 numbers to 1e-3
+//                          fp32 hand-offs and fp32 saved gates: the path whose gradients meet the reference's fp32 numbers to 1e-3;
+//                          its three-times-longer MMA chain starts on the first K block that lands (one mbarrier per K block,
+//                          rotated exchange order: exchange_peer / arrival_kblock)
+//   CELL = LSTM / GRU / vanilla RNN on one four-gate-slot layout (train_ctc.py:20's rnn_type choices)
 //   lstm_fwd2/bwd2_kernel  two gate tiles per CTA for H in (512, 640]
 #include <cuda_fp16.h>
 
