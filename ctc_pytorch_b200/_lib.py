@@ -53,7 +53,7 @@ def parse_header(path=HEADER_PATH):
 
 
 # kernels of ours enqueued by one call of each entry point (memsets not counted)
-KERNELS_PER_CALL = {"ctcb200_stream_wait_geq": 0, "ctcb200_greedy_decode": 2, "ctcb200_bn_train_stats": 2, "ctcb200_bn_bwd": 2,
+KERNELS_PER_CALL = {"ctcb200_stream_wait_geq": 0, "ctcb200_stream_write_value": 0, "ctcb200_greedy_decode": 2, "ctcb200_bn_train_stats": 2, "ctcb200_bn_bwd": 2,
                     "ctcb200_bn_bwd_coef": 2}
 
 

@@ -147,3 +147,32 @@ extern "C" CTCB200_API int ctcb200_stream_wait_geq(ctcb200_stream_t stream_, con
     }
     return ctcb200::OK;
 }
+
+// Stream-ordered store to a device word (driver stream memory operation): *counter = value once everything enqueued on `stream`
+// before this call has completed (and its writes are visible). The counterpart of ctcb200_stream_wait_geq for publishing the
+// progress of a chunked producer to a kernel that is already running (ctcb200_lstm_fwd_streamed polls such a word).
+extern "C" CTCB200_API int ctcb200_stream_write_value(ctcb200_stream_t stream_, void* counter, uint32_t value) {
+    typedef CUresult (*WriteFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WriteFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            (void)cudaGetLastError();
+            ctcb200::set_error("cuStreamWriteValue32 driver entry point unavailable");
+            return ctcb200::ERR_DRIVER;
+        }
+        fn = reinterpret_cast<WriteFn>(p);
+    }
+    if (!counter || (reinterpret_cast<uintptr_t>(counter) & 3) != 0) {
+        ctcb200::set_error("stream_write_value: counter %p must be a 4-byte aligned device address", counter);
+        return ctcb200::ERR_INVALID;
+    }
+    CUresult r = fn(static_cast<CUstream>(stream_), reinterpret_cast<CUdeviceptr>(counter), value, 0u /* default: with memory barrier */);
+    if (r != CUDA_SUCCESS) {
+        ctcb200::set_error("cuStreamWriteValue32 failed (%d)", static_cast<int>(r));
+        return ctcb200::ERR_DRIVER;
+    }
+    return ctcb200::OK;
+}

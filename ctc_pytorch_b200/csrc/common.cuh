@@ -111,6 +111,23 @@ static __device__ __noinline__ void spin_timeout_trap(int what) {
     printf("ctcb200: device wait timed out (kind %d) block %d thread %d\n", what, blockIdx.x, threadIdx.x);
     __trap();
 }
+// Tagged variant for kernels with several roles: on a timeout every waiting warp reports WHICH hand-off it was waiting for and
+// at which step before the launch is trapped (all warps get ~0.5 s to report), so a protocol stall can be read off the log.
+static __device__ __noinline__ void spin_timeout_report(int tag, int step) {
+    if ((threadIdx.x & 31) == 0)
+        printf("ctcb200: wait timed out: tag %d step %d block (%d,%d,%d) warp %d\n", tag, step, blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x >> 5);
+}
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag, int step) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    bool reported = false;
+    while (!mbar_try_wait(bar, parity)) {
+        const long long dt = clock64() - t0;
+        if (dt > SPIN_LIMIT_CYCLES && !reported) { spin_timeout_report(tag, step); reported = true; }
+        if (dt > SPIN_LIMIT_CYCLES + SPIN_LIMIT_CYCLES / 4) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -301,6 +318,16 @@ __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v)
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {   // words published by stream memory operations
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint4 ld_cg_v4(const void* p) {

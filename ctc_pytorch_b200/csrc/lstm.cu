@@ -225,7 +225,52 @@ struct FwdParams {
     int mma_split;            // number of warps (1, 2 or 4) that issue slices of the K chain into their own accumulator
     int act_approx;           // 1: gate non-linearities through tanh.approx (one MUFU op each)
     int rnn_relu;             // CELL_RNN: 1 = nonlinearity='relu', 0 = 'tanh'
+    unsigned int* resident;   // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
+    // Streamed input projection (all optional, gx_ready = null: gx is complete at launch). The rows of gx are produced chunk by
+    // chunk by GEMM launches on ANOTHER stream while this kernel runs: chunk c holds the time steps each direction visits in
+    // its scan steps [c * chunk_T, (c + 1) * chunk_T) (forward scan: rows t, reverse scan: rows T - 1 - t). Chunk 0 is complete
+    // at launch (stream order); a stream memory operation publishes *gx_ready = gx_base + c once chunks 1..c are complete.
+    const unsigned int* gx_ready;
+    unsigned int gx_base;
+    int chunk_T;
 };
+
+// Tell the host-side scheduler that the whole grid of this launch is resident: from then on the SMs this kernel does
+// not use can be handed to independent work on another stream (the weight-gradient GEMMs of the layer above under a BPTT
+// kernel, the later time chunks of the input projection under a forward kernel) without delaying the cluster launch. The last
+// CTA to arrive publishes; the arrival word is reset for the next launch.
+__device__ __forceinline__ void announce_resident(unsigned int* resident) {
+    if (resident != nullptr && threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(resident + 1, 1u) == total - 1) {
+            atomicExch(resident + 1, 0u);
+            __threadfence();
+            atomicAdd(resident, 1u);
+        }
+    }
+}
+
+// Streamed input projection: block until the chunk that scan step t opens has been published (called by one lane; the data
+// were written by TMA stores of a kernel that completed before the stream memory operation that published the counter).
+__device__ __forceinline__ void wait_gx_chunk(const unsigned int* ready, unsigned int need) {
+    if (static_cast<int>(ld_acquire_sys(ready) - need) >= 0) return;
+    const long long t0 = clock64();
+    bool reported = false;
+    while (static_cast<int>(ld_acquire_sys(ready) - need) < 0) {
+        __nanosleep(100);
+        const long long dt = clock64() - t0;
+        if (dt > SPIN_LIMIT_CYCLES / 2 && !reported) {   // (earlier than the mbarrier waits that pile up behind this one)
+            printf("ctcb200: streamed input projection late: chunk counter %u, needed %u (block %d,%d,%d)\n",
+                   ld_acquire_sys(ready), need, blockIdx.x, blockIdx.y, blockIdx.z);
+            reported = true;
+        }
+        if (dt > SPIN_LIMIT_CYCLES + SPIN_LIMIT_CYCLES / 2) spin_timeout_trap(3);
+    }
+}
+// gx element: coherent (L2) load while the projection is being streamed in by another kernel, read-only path otherwise
+__device__ __forceinline__ float load_gx(const FwdParams& p, const float* a) {
+    return p.gx_ready != nullptr ? ld_cg_f32(a) : __ldg(a);
+}
 
 // Split a float into bf16 hi + bf16 lo (hi + lo carries 16 mantissa bits of the value).
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -274,6 +319,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
     const int ctas = gridDim.x;
     const int kblocks = H / 64;
+    announce_resident(p.resident);
 
     if (tid == 0) {
         if constexpr (X3) tma_prefetch_desc(&tmWlo);
@@ -329,15 +375,21 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmWlo, FwdParams p) {
     for (int e = 0; e < EPT; ++e) c_state[e] = 0.0f;
 
 #define TRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == (k >= 8 ? 255 : 0)) p.trace[t * 16 + (k)] = clock64(); } while (0)
+    int gx_gate = p.chunk_T;   // first scan step of the next chunk of a streamed input projection
     for (int t = 0; t < T; ++t) {
         const int tt = dir ? (T - 1 - t) : t;
         TRACE(0);
         // (1) this step's input-projection terms: independent of the recurrence, issued first
+        if (p.gx_ready != nullptr && t == gx_gate) {   // streamed projection: the chunk this step opens must have landed
+            if (lane == 0) wait_gx_chunk(p.gx_ready, p.gx_base + static_cast<unsigned int>(t / p.chunk_T));
+            __syncwarp();
+            gx_gate += p.chunk_T;
+        }
         float gx[CPT];
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int gn = p.n0 + grp * NB + ch * CPT + c;
-            gx[c] = (gn < N) ? __ldg(p.gx + (static_cast<size_t>(tt) * N + gn) * G8 + gx_col) : 0.0f;
+            gx[c] = (gn < N) ? load_gx(p, p.gx + (static_cast<size_t>(tt) * N + gn) * G8 + gx_col) : 0.0f;
         }
         if constexpr (!BULK) {
             // (2) all CTAs of this (direction, group) have published h_{t-1}
@@ -569,21 +621,25 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sGx + 4 * HB * 128);
     uint64_t* h_full = bars;          // [half][parity]: every peer's half block of h_{t-1} has landed
     uint64_t* acc_full = bars + 4;    // [half]: the four partial accumulators of a half-step are complete
-    uint64_t* so_ready = bars + 6;    // [half]: all element warps have staged their part of h_t
-    uint64_t* gx_full = bars + 8;     // [4 stages]: the input-projection box of a half-step has landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    // [half][parity of t]: all element warps have staged their part of h_t. One barrier per step parity: a copy warp that is
+    // late by more than a step (it polls the chunk counter of a streamed input projection) must not find its barrier a full
+    // parity cycle ahead — the cluster stalls before the element warps can arrive for step t + 2, so with two barriers per half
+    // a late waiter always still sees "its" phase
+    uint64_t* so_ready = bars + 6;
+    uint64_t* gx_full = bars + 10;    // [4 stages]: the input-projection box of a half-step has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
     const int ctas = gridDim.x;
     const int kblocks = H / 64;
+    announce_resident(p.resident);
 
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&h_full[i], 1);
         mbar_init(&acc_full[0], 4);
         mbar_init(&acc_full[1], 4);
-        mbar_init(&so_ready[0], 8);
-        mbar_init(&so_ready[1], 8);
+        for (int i = 0; i < 4; ++i) mbar_init(&so_ready[i], 8);
         for (int i = 0; i < 4; ++i) mbar_init(&gx_full[i], 1);
         tma_prefetch_desc(&tmGx);
         fence_mbar_init();
@@ -615,20 +671,57 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
         // block had landed everywhere — no wait_group needed.
         // Warp 12 also keeps a 4-deep ring of input-projection boxes (gx rows of the 8 batch columns of a half-step x this
         // CTA's 128 gate rows, one TMA tensor load each) four half-steps ahead of the element phase.
-        auto fetch_gx = [&](int k) {   // k = 2 t + half
+        // Streamed input projection (FwdParams::gx_ready): a box of a chunk that has not been published yet is NOT waited for
+        // here — the copy duties of this warp must never fall behind (the hand-off barriers are parity-tracked: a copy warp that
+        // blocks for a while finds its so_ready barrier two phases ahead and waits forever; observed). The fetch is deferred
+        // instead and retried while this lane waits for the next so_ready, which is exactly where the element warps end up
+        // waiting when they run out of boxes.
+        int gx_gate = p.chunk_T;               // first scan step of the next unpublished chunk ...
+        unsigned int gate_need = p.gx_base + 1u;   // ... and the counter value that publishes it
+        int next_k = 0;                        // next half-step (k = 2 t + half) whose box has not been requested yet
+        auto try_fetch = [&]() -> bool {
+            const int k = next_k;
             const int t_ = k >> 1, half_ = k & 1;
             const int tt_ = dir ? (T - 1 - t_) : t_;
+            if (p.gx_ready != nullptr && t_ >= gx_gate) {
+                if (static_cast<int>(ld_acquire_sys(p.gx_ready) - gate_need) < 0) return false;
+                fence_proxy_async_all();   // the flag was read through the generic proxy, the box is fetched by the TMA unit
+                gx_gate += p.chunk_T;
+                ++gate_need;
+            }
             mbar_expect_tx(&gx_full[k & 3], HB * 128 * 4);
             tma_load_2d(sGx + (k & 3) * HB * 128, &tmGx, &gx_full[k & 3], dir * 4 * H + j * 128, tt_ * N + grp * NB + half_ * HB);
+            ++next_k;
+            return true;
         };
         if (warp == 12 && lane == 0)
-            for (int k = 0; k < 4 && k < 2 * T; ++k) fetch_gx(k);
+            while (next_k < 4 && next_k < 2 * T && try_fetch()) {}   // (chunk_T >= 2: steps 0 and 1 are in chunk 0)
         for (int t = 0; t + 1 < T; ++t) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                mbar_wait(&so_ready[half], t & 1);
+                const int k_cur = 2 * t + half;
+                if (warp == 12) {
+                    // only lane 0 polls (the other lanes wait for it at the __syncwarp): while it waits for this half-step's
+                    // so_ready it retries deferred boxes whose ring stage is already free (box k uses stage k & 3, free once
+                    // half-step k - 4 has been observed: k <= k_cur + 3)
+                    if (lane == 0) {
+                        uint64_t* sr = &so_ready[half * 2 + (t & 1)];
+                        if (!mbar_try_wait(sr, (t >> 1) & 1)) {
+                            const long long t0 = clock64();
+                            bool reported = false;
+                            while (!mbar_try_wait(sr, (t >> 1) & 1)) {
+                                if (next_k <= k_cur + 3 && next_k < 2 * T) try_fetch();
+                                const long long dt = clock64() - t0;
+                                if (dt > SPIN_LIMIT_CYCLES && !reported) { spin_timeout_report(10 + half, t); reported = true; }
+                                if (dt > SPIN_LIMIT_CYCLES + SPIN_LIMIT_CYCLES / 4) __trap();
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    mbar_wait_tag(&so_ready[half * 2 + (t & 1)], (t >> 1) & 1, 10 + half, t);
+                }
                 if (warp == 12 && half == 0) PTRACE(10);
-                if (warp == 12 && lane == 0 && 2 * t + half + 4 < 2 * T) fetch_gx(2 * t + half + 4);  // its stage was read in this half-step
                 const int d = (warp - 12) * 4 + lane;
                 if (lane < 4 && d < ctas) {
                     const uint32_t src = smem_u32(sOut + (half * 2 + (t & 1)) * HALF_BYTES);
@@ -638,7 +731,17 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
                                       mapa_shared(bar, static_cast<uint32_t>(d)));
                 }
                 __syncwarp();
+                // the hand-off first, then the prefetch: this half-step's stage is free now as well (k <= k_cur + 4)
+                if (warp == 12 && lane == 0)
+                    while (next_k <= k_cur + 4 && next_k < 2 * T && try_fetch()) {}
                 if (warp == 12 && half == 0) PTRACE(11);
+            }
+        }
+        if (warp == 12 && lane == 0) {
+            // deferred boxes of the last steps: their stages are free (half-steps <= 2T - 5 were observed above) and this warp
+            // has no other duty left, so it may block on the chunk counter now
+            while (next_k < 2 * T) {
+                if (!try_fetch()) wait_gx_chunk(p.gx_ready, gate_need);
             }
         }
     } else if (warp >= 8) {
@@ -650,7 +753,7 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
             for (int half = 0; half < 2; ++half) {
                 uint64_t* hf = &h_full[half * 2 + (t & 1)];
                 if (t > 0) {
-                    mbar_wait(hf, ((t - 1) >> 1) & 1);                       // every peer's half block has landed
+                    mbar_wait_tag(hf, ((t - 1) >> 1) & 1, 20 + half, t);   // every peer's half block has landed
                     if (m == 0 && lane == 0) mbar_expect_tx(hf, ctas * HALF_BYTES);   // re-arm for step t + 2
                 }
                 tc_fence_after();
@@ -695,7 +798,7 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (warp == 0) PTRACE(6 * half + 0);
-                mbar_wait(&acc_full[half], t & 1);
+                mbar_wait_tag(&acc_full[half], t & 1, 30 + half, t);
                 tc_fence_after();
                 if (warp == 0) PTRACE(6 * half + 1);
                 uint32_t acc[4];
@@ -704,7 +807,7 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
                                      acc);
                 tc_fence_before();
                 if (warp == 0) PTRACE(6 * half + 2);
-                mbar_wait(&gx_full[((t & 1) << 1) | half], (t >> 1) & 1);   // box of half-step k = 2t + half: stage k & 3, phase k >> 2
+                mbar_wait_tag(&gx_full[((t & 1) << 1) | half], (t >> 1) & 1, 40 + half, t);   // box of half-step k = 2t + half: stage k & 3, phase k >> 2
                 const float* gxs = sGx + ((((t & 1) << 1) | half) * HB + ch * 4) * 128 + row;
                 float a[4];
 #pragma unroll
@@ -732,7 +835,7 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
                 reinterpret_cast<__nv_bfloat16*>(so)[so_off] = __float2bfloat16(h);
                 fence_proxy_async_smem();   // staging writes (generic proxy) -> bulk-copy engine (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&so_ready[half]);
+                if (lane == 0) mbar_arrive(&so_ready[half * 2 + (t & 1)]);
                 if (warp == 0) PTRACE(6 * half + 4);
                 // off the critical path: layer output and what BPTT needs
                 const int gn = grp * NB + half * HB + n;
@@ -789,20 +892,6 @@ __device__ __forceinline__ BnCoef load_bn_coef(const BwdParams& p, int c) {
         k.d = __ldg(p.bn_coef + 4 * p.H + c);
     }
     return k;
-}
-
-// Tell the host-side scheduler that the whole grid of this launch is resident: from then on the SMs this kernel does
-// not use can be handed to off-critical-path work (the weight-gradient GEMMs of the layer above) without delaying the
-// cluster launch. The last CTA to arrive publishes; the arrival word is reset for the next launch.
-__device__ __forceinline__ void announce_resident(unsigned int* resident) {
-    if (resident != nullptr && threadIdx.x == 0) {
-        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-        if (atomicAdd(resident + 1, 1u) == total - 1) {
-            atomicExch(resident + 1, 0u);
-            __threadfence();
-            atomicAdd(resident, 1u);
-        }
-    }
 }
 
 // CTA (mb, q) keeps the [128 units x H] slice of gate q's transposed recurrent block. Per BPTT step:
@@ -1268,6 +1357,7 @@ lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
     const int j = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
     const int ctas = gridDim.x;
     const int kblocks = H / 64;
+    announce_resident(p.resident);
 
     if (tid == 0) {
         tma_prefetch_desc(&tmW);
@@ -1315,15 +1405,21 @@ lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, FwdParams p) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) c_state[u][e] = 0.0f;
 
+    int gx_gate = p.chunk_T;   // streamed input projection: first scan step of the next chunk
     for (int t = 0; t < T; ++t) {
         const int tt = dir ? (T - 1 - t) : t;
+        if (p.gx_ready != nullptr && t == gx_gate) {
+            if (lane == 0) wait_gx_chunk(p.gx_ready, p.gx_base + static_cast<unsigned int>(t / p.chunk_T));
+            __syncwarp();
+            gx_gate += p.chunk_T;
+        }
         float gx[2][CPT];
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int gn = p.n0 + grp * NB + ch * CPT + c;
             const float* g = p.gx + (static_cast<size_t>(tt) * N + (gn < N ? gn : 0)) * G8 + gx_col;
-            gx[0][c] = (gn < N) ? __ldg(g) : 0.0f;
-            gx[1][c] = (gn < N) ? __ldg(g + 128) : 0.0f;
+            gx[0][c] = (gn < N) ? load_gx(p, g) : 0.0f;
+            gx[1][c] = (gn < N) ? load_gx(p, g + 128) : 0.0f;
         }
         if (warp < 4) {
             const int u = warp >> 1, slot = warp & 1;
@@ -1684,13 +1780,22 @@ int mma_issuers(int NB, int H) {
     return n < 1 ? 1 : n;
 }
 
+// A recurrent CTA owns its SM: it holds (nearly) all 512 TMEM columns for the whole launch, so a tensor-core CTA of ANOTHER kernel
+// (the GEMMs the host runs beside the recurrence on the idle SMs: weight gradients under BPTT, later chunks of a streamed
+// input projection under the forward pass) must never become co-resident with it — its tcgen05.alloc would block until the
+// recurrent kernel ends, and a forward kernel that is itself waiting for that GEMM's output would never end (observed: the
+// bf16 kernels keep their weights in TMEM and need only ~50 KB of shared memory, which leaves room for a second CTA). Asking
+// for at least 200 KB of dynamic shared memory makes the SM exclusive for every kernel that uses more than 27 KB.
+constexpr size_t EXCLUSIVE_SMEM = 200 * 1024;
+size_t exclusive_smem(size_t b) { return b < EXCLUSIVE_SMEM ? EXCLUSIVE_SMEM : b; }
+
 size_t lstm_smem_bytes(int NB, int H, bool bwd, int ex, bool x3) {
     const bool bulk = ex == 3;
     const size_t parts = x3 ? 2 : 1;
     size_t b = (x3 ? static_cast<size_t>(128) * H * 2 : 0) + static_cast<size_t>(bulk ? 2 : 1) * H * NB * 2 * parts;
     if (bwd) b += static_cast<size_t>(4) * NB * 32 * 4 + (bulk ? static_cast<size_t>(4) * parts * NB * 4 * 16 + static_cast<size_t>(4) * NB * 32 * 4 : 0);
     else b += static_cast<size_t>(32) * (NB * 4 + 4) * 4 + (bulk ? parts * NB * 4 * 16 : 0);
-    return b + 256 + 1024;
+    return exclusive_smem(b + 256 + 1024);
 }
 
 // How the CTAs of one (direction, batch group) hand h_t / dG_t to each other every step:
@@ -1719,15 +1824,15 @@ int pick_nb(int N, int H, int force_nb, bool bwd, bool cl) {
 
 // Can at least one cluster of this shape be resident? (fails on parts / partitions whose GPCs are too small)
 template <typename Kern>
-bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads) {
+int cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads) {   // co-resident clusters (0: none)
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
         (void)cudaGetLastError();
-        return false;
+        return 0;
     }
     if (cluster.x * cluster.y * cluster.z > 8 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
         (void)cudaGetLastError();
-        return false;
+        return 0;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -1741,25 +1846,29 @@ bool cluster_probe(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads)
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
         (void)cudaGetLastError();
-        return false;
+        return 0;
     }
-    return n >= 1;
+    return n;
 }
 
 template <typename Kern>
-bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads = LSTM_THREADS) {
+int cluster_capacity(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads = LSTM_THREADS) {
     // the answer depends only on (device, kernel, cluster shape, shared memory): remember the last few probes
-    struct Entry { int dev; const void* k; unsigned cx, cy; size_t smem; bool ok; };
+    struct Entry { int dev; const void* k; unsigned cx, cy; size_t smem; int n; };
     static Entry cache[32];
     static int n_cache = 0;
     const int dev = current_device();
     for (int i = 0; i < n_cache; ++i)
         if (cache[i].dev == dev && cache[i].k == reinterpret_cast<const void*>(kern) && cache[i].cx == cluster.x &&
             cache[i].cy == cluster.y && cache[i].smem == smem)
-            return cache[i].ok;
-    const bool ok = cluster_probe(kern, grid, cluster, smem, threads);
-    if (n_cache < 32) cache[n_cache++] = Entry{dev, reinterpret_cast<const void*>(kern), cluster.x, cluster.y, smem, ok};
-    return ok;
+            return cache[i].n;
+    const int n = cluster_probe(kern, grid, cluster, smem, threads);
+    if (n_cache < 32) cache[n_cache++] = Entry{dev, reinterpret_cast<const void*>(kern), cluster.x, cluster.y, smem, n};
+    return n;
+}
+template <typename Kern>
+bool cluster_ok(Kern kern, dim3 grid, dim3 cluster, size_t smem, int threads = LSTM_THREADS) {
+    return cluster_capacity(kern, grid, cluster, smem, threads) >= 1;
 }
 
 using FwdKern = void (*)(CUtensorMap, FwdParams);
@@ -1925,11 +2034,18 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd_ctas(int N, int H, int batch_tile) {
     return total < sms ? total : sms;
 }
 
-extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
-                                            float* c_save, void* gates_save, void* scratch, int T, int N, int H,
-                                            int batch_tile, int cell, ctcb200_stream_t stream_) {
+namespace ctcb200 {
+namespace {
+// One body for ctcb200_lstm_fwd / ctcb200_lstm_fwd_streamed / ctcb200_lstm_fwd_ctas. plan_only: nothing is launched; *plan_ctas
+// receives the number of CTAs (= SMs) the launch would occupy when it is ONE clustered launch (the only form a streamed input
+// projection can run under: every batch group resident at once, nothing cooperative), else 0.
+int lstm_fwd_impl(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout, float* c_save,
+                  void* gates_save, void* scratch, int T, int N, int H, int batch_tile, int cell, void* resident_counter,
+                  const void* gx_ready, uint32_t gx_base, int chunk_T, bool x3_plan, bool plan_only, int* plan_ctas,
+                  ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const bool x3 = whh_lo_packed != nullptr;
+    const bool x3 = plan_only ? x3_plan : whh_lo_packed != nullptr;
+    if (plan_ctas) *plan_ctas = 0;
     CTCB_REQUIRE(cell >= 0 && cell <= 3, "lstm_fwd: cell %d not in {0 LSTM, 1 GRU, 2 RNN tanh, 3 RNN relu}", cell);
     const int cell_k = cell == 0 ? CELL_LSTM : (cell == 1 ? CELL_GRU : CELL_RNN);
     const bool plain = cell_k == CELL_LSTM;   // the pipelined / two-tile fast paths exist for the LSTM cell only
@@ -1942,20 +2058,33 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     p.himg = nullptr; p.flags = nullptr; p.trace = nullptr; p.act_approx = 0; p.rnn_relu = cell == 3 ? 1 : 0;
     p.w = static_cast<const __nv_bfloat16*>(whh_packed);
     p.T = T; p.N = N; p.H = H; p.n0 = 0;
+    CTCB_REQUIRE((reinterpret_cast<uintptr_t>(resident_counter) & 3) == 0 && (reinterpret_cast<uintptr_t>(gx_ready) & 3) == 0,
+                 "lstm_fwd: resident_counter / gx_ready must be 4-byte aligned");
+    CTCB_REQUIRE(gx_ready == nullptr || chunk_T >= 2, "lstm_fwd: a streamed input projection needs chunk_T >= 2 (got %d)", chunk_T);
+    p.resident = static_cast<unsigned int*>(resident_counter);
+    p.gx_ready = static_cast<const unsigned int*>(gx_ready);
+    p.gx_base = gx_base;
+    p.chunk_T = (gx_ready != nullptr) ? chunk_T : 0x3fffffff;
     if (!x3 && plain && two_tile_path(H)) {
         // H > 512: 64 units per CTA (tile 0 in TMEM, tile 1 in shared memory), H/64 CTAs per cluster, NB = 16
         constexpr int NB2 = 16;
         const int groups2 = (N + NB2 - 1) / NB2;
         CUtensorMap tmW2;
-        int rc2 = make_tmap_bf16_2d(&tmW2, whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+        int rc2 = plan_only ? OK : make_tmap_bf16_2d(&tmW2, whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
         if (rc2 != OK) return rc2;
-        const size_t smem2 = static_cast<size_t>(128) * H * 2 + static_cast<size_t>(2) * H * NB2 * 2 +
-                             static_cast<size_t>(2) * 32 * (NB2 * 4 + 4) * 4 + static_cast<size_t>(2) * NB2 * 4 * 16 + 64 + 1024;
+        const size_t smem2 = exclusive_smem(static_cast<size_t>(128) * H * 2 + static_cast<size_t>(2) * H * NB2 * 2 +
+                                            static_cast<size_t>(2) * 32 * (NB2 * 4 + 4) * 4 + static_cast<size_t>(2) * NB2 * 4 * 16 + 64 + 1024);
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
         p.mma_split = 4; p.groups = groups2;
-        if (cluster_ok(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2))
+        if (cluster_ok(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2)) {
+            if (plan_only) {   // streaming needs every cluster of the launch resident at once
+                if (2 * groups2 <= cluster_capacity(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2))
+                    *plan_ctas = (H / 64) * 2 * groups2;
+                return OK;
+            }
             return launch_clustered(lstm_fwd2_kernel<NB2>, dim3(H / 64, 2, groups2), dim3(H / 64, 1, 1), smem2, false, tmW2, p,
                                     stream);
+        }
     }
     int ex = exchange_mode(H);
     {   // fall back to the global-memory exchange when a cluster of this size cannot be scheduled on this device
@@ -1968,7 +2097,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     const int NB = (x3 || !plain) ? 16 : pick_nb(N, H, batch_tile, false, cl);
     const int groups_total = (N + NB - 1) / NB;
     CUtensorMap tmW;   // only read by the split-operand kernels (W_lo slice -> shared memory)
-    int rc = make_tmap_bf16_2d(&tmW, x3 ? whh_lo_packed : whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+    int rc = plan_only ? OK : make_tmap_bf16_2d(&tmW, x3 ? whh_lo_packed : whh_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
     if (rc != OK) return rc;
     const size_t smem = lstm_smem_bytes(NB, H, false, ex, x3);
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_fwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
@@ -1978,7 +2107,7 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
     }
     p.mma_split = mma_issuers(NB, H);
     p.groups = groups_total;
-    if (getenv("CTCB200_LSTM_TRACE")) {
+    if (!plan_only && getenv("CTCB200_LSTM_TRACE")) {
         static long long* dbuf = nullptr;
         if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
         if (T <= 4096) {
@@ -1991,17 +2120,31 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         trace_dump.pipe = true;
         // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core warps
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
-        const size_t smem_p = static_cast<size_t>(2) * H * 16 * 2 + 4 * 512 + 4 * 8 * 128 * 4 + 128 + 1024;
+        const size_t smem_p = exclusive_smem(static_cast<size_t>(2) * H * 16 * 2 + 4 * 512 + 4 * 8 * 128 * 4 + 128 + 1024);
         CUtensorMap tmGx;   // gate pre-activations as a 2-D f32 tensor [T*N rows, 8H columns], boxes of 8 rows x 128 columns
-        rc = make_tmap_f32_2d(&tmGx, gx, static_cast<uint64_t>(T) * N, static_cast<uint64_t>(8) * H, static_cast<uint64_t>(8) * H, 8, 128);
-        if (rc == OK && cluster_ok(lstm_fwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS))
+        rc = plan_only ? OK : make_tmap_f32_2d(&tmGx, gx, static_cast<uint64_t>(T) * N, static_cast<uint64_t>(8) * H, static_cast<uint64_t>(8) * H, 8, 128);
+        if (rc == OK && cluster_ok(lstm_fwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS)) {
+            if (plan_only) {
+                if (2 * groups_total <= cluster_capacity(lstm_fwd_pipe_kernel, grid, cluster, smem_p, PIPE_THREADS))
+                    *plan_ctas = (H / 32) * 2 * groups_total;
+                return OK;
+            }
             return launch_clustered(lstm_fwd_pipe_kernel, grid, cluster, smem_p, false, tmGx, p, stream, PIPE_THREADS);
+        }
     }
     if (cl) {
         // independent clusters: no co-residency requirement between them, one launch covers every batch group
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
+        if (plan_only) {
+            if (2 * groups_total <= cluster_capacity(fwd_kernel(NB, ex, x3, cell_k), grid, cluster, smem))
+                *plan_ctas = (H / 32) * 2 * groups_total;
+            return OK;
+        }
         return launch_clustered(fwd_kernel(NB, ex, x3, cell_k), grid, cluster, smem, false, tmW, p, stream);
     }
+    if (plan_only) return OK;   // global-memory exchange: several cooperative launches, no streaming
+    CTCB_REQUIRE(gx_ready == nullptr && resident_counter == nullptr,
+                 "lstm_fwd: a streamed input projection needs the clustered kernels (ask ctcb200_lstm_fwd_ctas first)");
     const int per_group = 2 * (H / 32);
     const int sms = device_sm_count();
     CTCB_REQUIRE(per_group <= sms, "lstm_fwd: one batch group needs %d CTAs but the device has %d SMs", per_group, sms);
@@ -2020,6 +2163,32 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_pac
         if (rc != OK) return rc;
     }
     return OK;
+}
+}  // namespace
+}  // namespace ctcb200
+
+extern "C" CTCB200_API int ctcb200_lstm_fwd(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
+                                            float* c_save, void* gates_save, void* scratch, int T, int N, int H,
+                                            int batch_tile, int cell, ctcb200_stream_t stream) {
+    return lstm_fwd_impl(gx, whh_packed, whh_lo_packed, hout, c_save, gates_save, scratch, T, N, H, batch_tile, cell, nullptr,
+                         nullptr, 0u, 0, false, false, nullptr, stream);
+}
+
+extern "C" CTCB200_API int ctcb200_lstm_fwd_streamed(const float* gx, const void* whh_packed, const void* whh_lo_packed,
+                                                     float* hout, float* c_save, void* gates_save, void* scratch, int T, int N,
+                                                     int H, int batch_tile, int cell, void* resident_counter,
+                                                     const void* gx_ready, uint32_t gx_base, int chunk_T,
+                                                     ctcb200_stream_t stream) {
+    return lstm_fwd_impl(gx, whh_packed, whh_lo_packed, hout, c_save, gates_save, scratch, T, N, H, batch_tile, cell,
+                         resident_counter, gx_ready, gx_base, chunk_T, false, false, nullptr, stream);
+}
+
+extern "C" CTCB200_API int ctcb200_lstm_fwd_ctas(int N, int H, int batch_tile, int x3, int cell) {
+    int ctas = 0;
+    if (lstm_fwd_impl(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1, N, H, batch_tile, cell, nullptr, nullptr,
+                      0u, 0, x3 != 0, true, &ctas, nullptr) != OK)
+        return 0;
+    return ctas;
 }
 
 extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
@@ -2058,8 +2227,8 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         CUtensorMap tmWT2;
         int rc2 = make_tmap_bf16_2d(&tmWT2, whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
         if (rc2 != OK) return rc2;
-        const size_t smem2 = static_cast<size_t>(128) * (H - 256) * 2 + static_cast<size_t>(4) * H * NB2 * 2 +
-                             static_cast<size_t>(4) * NB2 * 32 * 4 * 2 + static_cast<size_t>(8) * NB2 * 4 * 16 + 64 + 1024;
+        const size_t smem2 = exclusive_smem(static_cast<size_t>(128) * (H - 256) * 2 + static_cast<size_t>(4) * H * NB2 * 2 +
+                                            static_cast<size_t>(4) * NB2 * 32 * 4 * 2 + static_cast<size_t>(8) * NB2 * 4 * 16 + 64 + 1024);
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
         p.mma_split = 4; p.groups = groups2;
         if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))

@@ -223,6 +223,44 @@ def _overlap_enabled(model):
     return bool(getattr(model, "overlap_wgrad", True))
 
 
+_GX_READY = {}
+
+
+def _gx_ready_state(dev):
+    """[uint32[1] device word, host-side base value] the side stream publishes the input projection's chunk count through."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _GX_READY:
+        _GX_READY[key] = [torch.zeros(1, dtype=torch.int32, device=dev), 0]
+    return _GX_READY[key]
+
+
+def _gx_stream_plan(model, T, N, H, x3, cell, packed, dev):
+    """Streamed input projection (include/ctcb200.h, ctcb200_lstm_fwd_streamed): only the first time chunk of Gx = X W_ih^T is
+    computed before the recurrent kernel starts; the other chunks are GEMM launches on the side stream, on the SMs the
+    latency-bound recurrence leaves idle, published chunk by chunk through a stream memory operation the kernel polls.
+    Returns None (whole projection first) or (chunks, chunk_T, side_ctas, mode) with mode 'stream' or 'serial' (same chunk
+    launches, all before the recurrent kernel: the CPU emulation and CTCB200_OVERLAP_GX=serial).
+    model.overlap_gx / CTCB200_OVERLAP_GX=0|1|serial, model.gx_chunks / CTCB200_GX_CHUNKS (default 8)."""
+    env = os.environ.get("CTCB200_OVERLAP_GX")
+    on = bool(getattr(model, "overlap_gx", True)) if env is None else env != "0"
+    if not on or packed or T < 4:
+        return None
+    chunks = int(os.environ.get("CTCB200_GX_CHUNKS", getattr(model, "gx_chunks", 8)))
+    chunk_T = max(2, -(-T // max(1, chunks)))   # (the kernels prefetch two steps ahead: chunk 0 must hold steps 0 and 1)
+    chunks = -(-T // chunk_T)
+    if chunks < 2:
+        return None
+    if dev.type != "cuda" or env == "serial":
+        return chunks, chunk_T, 0, "serial"
+    if _lib._DEBUG_SYNC or _overlap_gate() != "memop":
+        return None   # a host synchronize between the launch and its chunks would never return
+    ctas = int(_lib.lib().dll.ctcb200_lstm_fwd_ctas(N, H, int(model.batch_tile), 1 if x3 else 0, int(cell)))
+    free = torch.cuda.get_device_properties(dev).multi_processor_count - ctas
+    if ctas <= 0 or free < 16:
+        return None   # not one all-resident clustered launch, or no SMs left for the GEMMs
+    return chunks, chunk_T, free, "stream"
+
+
 def _dropout_mask(model, shape, p, dev):
     """uint8 keep-mask for nn.Dropout(p). `model.mask_source(shape, p, device)` (tests: masks shared with the oracle)
     replaces the framework RNG when set."""
@@ -409,19 +447,57 @@ class _RnnStackFn(torch.autograd.Function):
                     del h_prev_r
             Ipad = _round_up(I, 8)
             wih_p, wihT_p, whh_p, whhT_p = _packed_weights(model, li, layer.rnn, H, I, Ipad, x3, dev)
-            if packed:   # each direction's input projection on its own alignment, written into its half of gx
-                gx = torch.empty((R, 8 * H), dtype=torch.float32, device=dev)
-                _gemm(X, wih_p.rows(0, 4 * H), out=gx[:, :4 * H], k=I)
-                _gemm(Xr, wih_p.rows(4 * H, 8 * H), out=gx[:, 4 * H:], k=I)
-            else:
-                gx = _gemm(X, wih_p, k=I)  # [R, 8H] f32
+            cell, G = _cell_of(layer.rnn)
+            rec.cell, rec.G = cell, G
             hout = torch.empty((R, 2 * H), dtype=torch.float32, device=dev)
             c_save = torch.empty((R, 2 * H), dtype=torch.float32, device=dev) if need_grad else None
             gates = torch.empty((R, 2 * H, 4), dtype=torch.float32 if x3 else torch.float16, device=dev) if need_grad else None
-            cell, G = _cell_of(layer.rnn)
-            rec.cell, rec.G = cell, G
-            _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout), _lib.ptr(c_save),
-                  _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, cell, stream())
+            plan = _gx_stream_plan(model, T, N, H, x3, cell, packed, dev)
+            if plan is None:
+                if packed:   # each direction's input projection on its own alignment, written into its half of gx
+                    gx = torch.empty((R, 8 * H), dtype=torch.float32, device=dev)
+                    _gemm(X, wih_p.rows(0, 4 * H), out=gx[:, :4 * H], k=I)
+                    _gemm(Xr, wih_p.rows(4 * H, 8 * H), out=gx[:, 4 * H:], k=I)
+                else:
+                    gx = _gemm(X, wih_p, k=I)  # [R, 8H] f32
+                _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout), _lib.ptr(c_save),
+                      _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, cell, stream())
+            else:
+                # streamed input projection: chunk c = the rows each direction visits in its scan steps [c*chunk_T, ...)
+                chunks, chunk_T, side_ctas, mode = plan
+                gx = torch.empty((R, 8 * H), dtype=torch.float32, device=dev)
+
+                def _gx_chunk(c, mc):
+                    a, b = c * chunk_T, min(T, (c + 1) * chunk_T)
+                    for d, (r0, r1) in enumerate(((a * N, b * N), ((T - b) * N, (T - a) * N))):
+                        _gemm(X.rows(r0, r1), wih_p.rows(d * 4 * H, (d + 1) * 4 * H), out=gx[r0:r1, d * 4 * H:(d + 1) * 4 * H],
+                              k=I, max_ctas=mc)
+
+                _gx_chunk(0, 0)
+                if mode == "serial":
+                    for c in range(1, chunks):
+                        _gx_chunk(c, 0)
+                    _call("ctcb200_lstm_fwd", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout),
+                          _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, cell, stream())
+                else:
+                    main_s, side_s = torch.cuda.current_stream(dev), _side_stream(dev)
+                    res, rdy = _resident_state(dev), _gx_ready_state(dev)
+                    base = rdy[1]
+                    rdy[1] = (base + chunks) & 0xFFFFFFFF
+                    x_ready = torch.cuda.Event()
+                    x_ready.record(main_s)
+                    _call("ctcb200_lstm_fwd_streamed", _lib.ptr(gx), _lib.ptr(whh_p.hi), _lib.ptr(whh_p.lo), _lib.ptr(hout),
+                          _lib.ptr(c_save), _lib.ptr(gates), _lib.ptr(scratch), T, N, H, model.batch_tile, cell,
+                          _lib.ptr(res[0]), _lib.ptr(rdy[0]), base, chunk_T, stream())
+                    res[1] = (res[1] + 1) & 0xFFFFFFFF
+                    with torch.cuda.stream(side_s):
+                        side_s.wait_event(x_ready)
+                        # the recurrent grid is resident: its clusters can no longer be blocked by GEMM CTAs
+                        _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
+                        for c in range(1, chunks):
+                            _gx_chunk(c, side_ctas)
+                            _call("ctcb200_stream_write_value", _lib.stream(), _lib.ptr(rdy[0]), (base + c) & 0xFFFFFFFF)
+                    main_s.wait_stream(side_s)   # (already implied by the kernel's own waits; keeps the allocator's view simple)
             del gx
             rec.Hb = None
             p_drop = _layer_dropout_p(layer)
@@ -709,6 +785,8 @@ class CTC_Model(nn.Module):
         self.drop_out = drop_out
         self.batch_tile = 0  # 0 = let the library pick the recurrent kernels' batch tile (16 or 32)
         self.overlap_wgrad = True  # weight-gradient GEMMs on a side stream, on the SMs the BPTT kernels leave idle
+        self.overlap_gx = True     # input projection streamed chunk by chunk under the forward recurrence (_gx_stream_plan)
+        self.gx_chunks = 8
         # operand mode of every contraction: "bf16" (fast; gradients within ~1 % of fp32) or "x3" (split bf16 hi+lo, three
         # tensor-core products per contraction: gradients within 1e-3 of the reference's fp32 arithmetic)
         self.precision = os.environ.get("CTCB200_PRECISION", "bf16")

@@ -153,6 +153,23 @@ CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, co
  * how many SMs the BPTT launch occupies, i.e. how many a concurrent kernel may take (gemm max_ctas). */
 CTCB200_API int ctcb200_lstm_bwd_ctas(int N, int H, int batch_tile);
 CTCB200_API int ctcb200_stream_wait_geq(ctcb200_stream_t stream, const void* counter, uint32_t value);
+/* Streamed input projection: the forward recurrence of a layer (model_ctc.py:33, nn.LSTM's time loop) starts while most of its
+ * input projection Gx = X * W_ih^T (the first half of the same nn.LSTM call) is still being computed on the SMs the
+ * latency-bound recurrent kernel leaves idle. Time is cut into chunks of chunk_T >= 2 scan steps; chunk c of a direction holds the
+ * rows that direction visits in its scan steps [c*chunk_T, (c+1)*chunk_T) (forward scan: frames t, reverse scan: frames
+ * T-1-t). The caller computes chunk 0 of both directions before the launch (stream order), then — on ANOTHER stream, after
+ * ctcb200_stream_wait_geq on resident_counter word 0 (incremented once the whole grid is running) and with gemm max_ctas =
+ * SM count - ctcb200_lstm_fwd_ctas() — chunk 1, 2, ... each followed by ctcb200_stream_write_value(gx_ready, gx_base + c)
+ * (a driver stream memory operation: *gx_ready = value once the preceding work of that stream has completed). The kernel
+ * waits for gx_ready - gx_base >= c (wrap-around compare) before it first touches chunk c.
+ * ctcb200_lstm_fwd_ctas: SMs the forward launch occupies when it is a single launch with every cluster resident at once
+ * (the only form that can be streamed), else 0 — ask before using ctcb200_lstm_fwd_streamed. */
+CTCB200_API int ctcb200_lstm_fwd_streamed(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
+                                          float* c_save, void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
+                                          int cell, void* resident_counter, const void* gx_ready, uint32_t gx_base,
+                                          int chunk_T, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_lstm_fwd_ctas(int N, int H, int batch_tile, int x3, int cell);
+CTCB200_API int ctcb200_stream_write_value(ctcb200_stream_t stream, void* counter, uint32_t value);
 
 /* ---- layout / normalisation kernels around the GEMMs (model_ctc.py:29-32 BatchNorm1d over T*N rows,
  * model_ctc.py:136-140,165-168 fc BatchNorm + LogSoftmax, model_ctc.py:175 the (N,T,F)->(T,N,F) transpose).

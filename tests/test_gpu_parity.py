@@ -823,6 +823,43 @@ def test_overlapped_wgrad_matches_serial(H, L, N, drop):
         assert relnorm(grads[True][k], grads[False][k]) < 1e-4, (k, relnorm(grads[True][k], grads[False][k]))
 
 
+@pytest.mark.parametrize("rnn_type,precision,T,N,H,L,chunks", [(nn.LSTM, "bf16", 800, 32, 512, 2, 8), (nn.LSTM, "x3", 203, 32, 512, 2, 5),
+                                                          (nn.LSTM, "bf16", 120, 40, 640, 2, 8), (nn.GRU, "bf16", 64, 20, 256, 2, 4),
+                                                          (nn.LSTM, "bf16", 37, 5, 128, 3, 37)])
+def test_streamed_input_projection_matches_whole(rnn_type, precision, T, N, H, L, chunks):
+    """ctcb200_lstm_fwd_streamed: the recurrence starts after the first time chunk of Gx, the rest arrives from the side stream
+    while the kernel runs (pipelined / split-operand / two-tile / GRU kernels; ragged last chunk; one step per chunk). Only the
+    schedule changes: outputs and gradients must equal the whole-projection-first path."""
+    from ctc_pytorch_b200.model import CTC_Model, _gx_stream_plan
+    from ctc_pytorch_b200.loss import CTCLoss
+    F, C = 40, 20
+    rnn_param = {"rnn_input_size": F, "rnn_hidden_size": H, "rnn_layers": L, "rnn_type": rnn_type, "bidirectional": True,
+                 "batch_norm": True}
+    torch.manual_seed(H + L + T)
+    m = CTC_Model(rnn_param=rnn_param, num_class=C, drop_out=0.0).to(DEV)
+    m.precision = precision
+    m.gx_chunks = chunks
+    x, frac, tg, tl = model_ref.synthetic_batch(T, N, F, C, 6, 11)
+    il = (frac * T).long()
+    m.train()
+    plan = _gx_stream_plan(m, T, N, H, precision == "x3", {nn.LSTM: 0, nn.GRU: 1}[rnn_type], False, torch.device(DEV))
+    assert plan is not None and plan[3] == "stream", plan     # the streamed path is really what runs below
+    res = {}
+    for mode in (False, True, True):
+        m.overlap_gx = mode
+        m.zero_grad(set_to_none=True)
+        out = m(x.to(DEV))
+        loss = CTCLoss(reduction="sum")(out, tg.to(DEV), il.to(DEV), tl.to(DEV)) / N
+        loss.backward()
+        torch.cuda.synchronize()
+        res[mode] = (out.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()})
+    e_out = float((res[True][0] - res[False][0]).abs().max())
+    e_grad = max(relnorm(res[True][1][k], res[False][1][k]) for k in res[False][1])
+    _report("streamed_gx_vs_whole", dict(cell=rnn_type.__name__, precision=precision, T=T, N=N, H=H, chunks=plan[0], chunk_T=plan[1],
+                                         side_ctas=plan[2], max_abs_out_diff=e_out, worst_grad_rel_diff=e_grad))
+    assert e_out < 1e-6 and e_grad < 1e-6, (e_out, e_grad)
+
+
 def _recurrence_fp64(gx, whh, T, N, H):
     """The time loop of nn.LSTM(bias=False, bidirectional) in float64 from the packed operands the kernels consume:
     gx [T*N, 8H] (columns (dir, cta j, unit, gate)), whh [8H, H] (same row order)."""
