@@ -370,16 +370,16 @@ def run_ours(args, name, cfg, rank, world):
         return r
     L.call = timed_call
     prof_steps = 3
-    overlap_was, gx_was = job.model.overlap_wgrad, job.model.overlap_gx
+    overlap_was, gx_was, dg_was = job.model.overlap_wgrad, job.model.overlap_gx, job.model.overlap_dg
     # kernels timed one at a time on one stream (the timed steps above overlap the wgrad GEMMs with BPTT and stream the input
     # projection under the forward recurrence)
-    job.model.overlap_wgrad = job.model.overlap_gx = False
+    job.model.overlap_wgrad = job.model.overlap_gx = job.model.overlap_dg = False
     for k in range(prof_steps):
         flush.zero_()
         job.step(job.devb[k % len(job.devb)], comm=False)  # rank 0 only: no collective in this diagnostic pass
     torch.cuda.synchronize()
     L.call = orig_call
-    job.model.overlap_wgrad, job.model.overlap_gx = overlap_was, gx_was
+    job.model.overlap_wgrad, job.model.overlap_gx, job.model.overlap_dg = overlap_was, gx_was, dg_was
     kern_ms = {nm: sum(s.elapsed_time(e) for s, e in v) / prof_steps for nm, v in per_call.items()}
     kern_cnt = {nm: len(v) // prof_steps for nm, v in per_call.items()}
     step_ms_prof = sum(kern_ms.values())

@@ -86,4 +86,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--tags" in sys.argv:   # debugging build: stalled mbarrier waits of the pipelined kernel report their role and step
+        NVCC_FLAGS.append("-DCTCB200_WAIT_TAGS")
+    print(build(force="--force" in sys.argv or "--tags" in sys.argv, verbose="-v" in sys.argv))

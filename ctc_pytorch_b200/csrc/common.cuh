@@ -118,6 +118,7 @@ static __device__ __noinline__ void spin_timeout_report(int tag, int step) {
         printf("ctcb200: wait timed out: tag %d step %d block (%d,%d,%d) warp %d\n", tag, step, blockIdx.x, blockIdx.y, blockIdx.z,
                threadIdx.x >> 5);
 }
+#ifdef CTCB200_WAIT_TAGS   // debugging build: -DCTCB200_WAIT_TAGS (python -m ctc_pytorch_b200._build --tags)
 __device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag, int step) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -128,6 +129,7 @@ __device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, in
         if (dt > SPIN_LIMIT_CYCLES + SPIN_LIMIT_CYCLES / 4) __trap();
     }
 }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -135,6 +137,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > SPIN_LIMIT_CYCLES) spin_timeout_trap(1);
     }
 }
+#ifndef CTCB200_WAIT_TAGS
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int, int) { mbar_wait(bar, parity); }
+#endif
 
 // ---- proxies / fences ------------------------------------------------------------------------
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma reads)

@@ -700,21 +700,17 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int k_cur = 2 * t + half;
-                if (warp == 12) {
-                    // only lane 0 polls (the other lanes wait for it at the __syncwarp): while it waits for this half-step's
-                    // so_ready it retries deferred boxes whose ring stage is already free (box k uses stage k & 3, free once
-                    // half-step k - 4 has been observed: k <= k_cur + 3)
+                // Normally every box up to k_cur + 3 has been requested and all lanes simply wait for the element warps. Only
+                // when a box was deferred (its chunk of a streamed projection had not been published) lane 0 polls alone and
+                // retries the request while it waits: box k uses ring stage k & 3, free once half-step k - 4 has been observed.
+                const bool deferred = warp == 12 && __shfl_sync(0xffffffffu, next_k <= k_cur + 3 && next_k < 2 * T ? 1 : 0, 0) != 0;
+                if (deferred) {
                     if (lane == 0) {
                         uint64_t* sr = &so_ready[half * 2 + (t & 1)];
-                        if (!mbar_try_wait(sr, (t >> 1) & 1)) {
-                            const long long t0 = clock64();
-                            bool reported = false;
-                            while (!mbar_try_wait(sr, (t >> 1) & 1)) {
-                                if (next_k <= k_cur + 3 && next_k < 2 * T) try_fetch();
-                                const long long dt = clock64() - t0;
-                                if (dt > SPIN_LIMIT_CYCLES && !reported) { spin_timeout_report(10 + half, t); reported = true; }
-                                if (dt > SPIN_LIMIT_CYCLES + SPIN_LIMIT_CYCLES / 4) __trap();
-                            }
+                        const long long t0 = clock64();
+                        while (!mbar_try_wait(sr, (t >> 1) & 1)) {
+                            if (next_k <= k_cur + 3 && next_k < 2 * T) try_fetch();
+                            if (clock64() - t0 > SPIN_LIMIT_CYCLES) { spin_timeout_report(10 + half, t); spin_timeout_trap(4); }
                         }
                     }
                     __syncwarp();
@@ -878,9 +874,26 @@ struct BwdParams {
     int mma_split;
     long long* trace;          // optional [T][16] clock64 stamps of CTA 0 / thread 0 (CTCB200_LSTM_TRACE)
     unsigned int* resident;    // optional uint32[2]: [0] += 1 once every CTA of this launch is running ([1] = arrivals)
+    // Streamed gate gradients (optional): every CTA adds 1 to *progress once its dG rows of the scan steps [c*chunk_T,
+    // (c+1)*chunk_T) are written and visible (c = 0, 1, ...; also after the last, possibly shorter, chunk), so another stream can
+    // run the input-gradient / weight-gradient GEMMs of a chunk (stream memory-operation wait on the counter) while the
+    // recurrence is still going: forward scan of BPTT = rows T-1-s, reverse scan = rows s.
+    unsigned int* progress;
+    int chunk_T;
     const float* bn_x;         // optional: layer output [T*N, 2H]; the BatchNorm backward of the layer above is applied to
     const float* bn_coef;      // dhout on the fly: dh = coef[0][c]*dhout + coef[1][c]*bn_x + coef[2][c], coef f32 [3][2H]
 };
+
+
+// Streamed gate gradients: called by every thread at the end of scan step t, after its dG stores of that step.
+__device__ __forceinline__ void publish_dg_chunk(const BwdParams& p, int t, int T, int& next_pub) {
+    if (p.progress != nullptr && (t + 1 == next_pub || t + 1 == T)) {
+        __threadfence();          // this thread's dG rows are visible device-wide ...
+        __syncthreads();          // ... for every thread of the CTA ...
+        if (threadIdx.x == 0) red_release_add(p.progress, 1u);   // ... before the chunk is counted
+        next_pub += p.chunk_T;
+    }
+}
 
 // BatchNorm-backward coefficients of column c (identity when the fusion is off)
 struct BnCoef { float a, b, d; };
@@ -999,6 +1012,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
     for (int e = 0; e < EPT; ++e) dc_carry[e] = 0.0f;
 
 #define BTRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) p.trace[t * 16 + (k)] = clock64(); } while (0)
+    int next_pub = p.chunk_T;   // streamed gate gradients: scan step count that completes the next chunk
     for (int t = 0; t < T; ++t) {
         const int tt = dir ? t : (T - 1 - t);          // reverse of the forward scan order
         BTRACE(0);
@@ -1320,6 +1334,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWTlo, BwdParams p) {
                 }
             }
         }
+        publish_dg_chunk(p, t, T, next_pub);
     }
     tc_fence_before();
     __syncthreads();
@@ -1609,6 +1624,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) dc_carry[hf][e] = 0.0f;
 
+    int next_pub = p.chunk_T;   // streamed gate gradients: scan step count that completes the next chunk
     for (int t = 0; t < T; ++t) {
         const int tt = dir ? t : (T - 1 - t);
         const int tprev = dir ? tt + 1 : tt - 1;
@@ -1750,6 +1766,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmWT, BwdParams p) {
                     *reinterpret_cast<uint2*>(p.dg + (static_cast<size_t>(tt) * N + gn) * G8 + static_cast<size_t>(dir) * 4 * H +
                                               static_cast<size_t>(unit >> 5) * 128 + (unit & 31) * 4) = dgp[hf][e];
             }
+        publish_dg_chunk(p, t, T, next_pub);
     }
     tc_fence_before();
     __syncthreads();
@@ -2191,24 +2208,31 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd_ctas(int N, int H, int batch_tile, i
     return ctas;
 }
 
-extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
-                                            const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* dg_rec,
-                                            void* dg_rec_lo, void* scratch, int T, int N, int H, int batch_tile, int cell,
-                                            const float* bn_x, const float* bn_coef, void* resident_counter,
-                                            void* resident_event, ctcb200_stream_t stream_) {
+namespace ctcb200 {
+namespace {
+// One body for ctcb200_lstm_bwd / ctcb200_lstm_bwd_streamed / ctcb200_lstm_bwd_plan (plan_only: nothing is launched, *plan_ctas
+// = CTAs of the launch when it is ONE clustered launch — the form whose per-chunk progress counts are simply CTAs x chunks —
+// else 0).
+int lstm_bwd_impl(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed, const float* c_save,
+                  const void* gates_save, void* dg, void* dg_lo, void* dg_rec, void* dg_rec_lo, void* scratch, int T, int N, int H,
+                  int batch_tile, int cell, const float* bn_x, const float* bn_coef, void* resident_counter, void* resident_event,
+                  void* progress_counter, int chunk_T, bool x3_plan, bool plan_only, int* plan_ctas, ctcb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     cudaEvent_t start_ev = static_cast<cudaEvent_t>(resident_event);
-    const bool x3 = whhT_lo_packed != nullptr;
+    const bool x3 = plan_only ? x3_plan : whhT_lo_packed != nullptr;
+    if (plan_ctas) *plan_ctas = 0;
     CTCB_REQUIRE(cell >= 0 && cell <= 3, "lstm_bwd: cell %d not in {0 LSTM, 1 GRU, 2 RNN tanh, 3 RNN relu}", cell);
     const int cell_k = cell == 0 ? CELL_LSTM : (cell == 1 ? CELL_GRU : CELL_RNN);
     const bool plain = cell_k == CELL_LSTM;
-    CTCB_REQUIRE(cell_k != CELL_GRU || (dg_rec != nullptr && (!x3 || dg_rec_lo != nullptr)),
+    CTCB_REQUIRE(plan_only || cell_k != CELL_GRU || (dg_rec != nullptr && (!x3 || dg_rec_lo != nullptr)),
                  "lstm_bwd: the GRU cell needs dg_rec (and dg_rec_lo in the split-operand mode)");
     CTCB_REQUIRE(T > 0 && N > 0, "lstm_bwd: empty T=%d N=%d", T, N);
     CTCB_REQUIRE((reinterpret_cast<uintptr_t>(resident_counter) & 3) == 0, "lstm_bwd: resident_counter must be 4-byte aligned");
     CTCB_REQUIRE((bn_x == nullptr) == (bn_coef == nullptr), "lstm_bwd: bn_x and bn_coef must be given together");
     CTCB_REQUIRE(H % 128 == 0 && H >= 128 && H <= 640, "lstm_bwd: hidden size %d must be a multiple of 128 in [128,640]", H);
-    CTCB_REQUIRE(!x3 || dg_lo != nullptr, "lstm_bwd: the split-operand mode needs dg_lo");
+    CTCB_REQUIRE(plan_only || !x3 || dg_lo != nullptr, "lstm_bwd: the split-operand mode needs dg_lo");
+    CTCB_REQUIRE((reinterpret_cast<uintptr_t>(progress_counter) & 3) == 0, "lstm_bwd: progress_counter must be 4-byte aligned");
+    CTCB_REQUIRE(progress_counter == nullptr || chunk_T >= 1, "lstm_bwd: streamed gate gradients need chunk_T >= 1 (got %d)", chunk_T);
     BwdParams p;
     p.dhout = dhout; p.c_save = c_save;
     p.gates_save = x3 ? nullptr : static_cast<const uint2*>(gates_save);
@@ -2219,21 +2243,25 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     p.dgimg = nullptr; p.flags = nullptr; p.trace = nullptr;
     p.resident = static_cast<unsigned int*>(resident_counter);
     p.bn_x = bn_x; p.bn_coef = bn_coef;
+    p.progress = static_cast<unsigned int*>(progress_counter);
+    p.chunk_T = progress_counter != nullptr ? chunk_T : 0x3fffffff;
     p.w = static_cast<const __nv_bfloat16*>(whhT_packed);
     p.T = T; p.N = N; p.H = H; p.n0 = 0;
     if (!x3 && plain && two_tile_path(H)) {
         constexpr int NB2 = 16;
         const int groups2 = (N + NB2 - 1) / NB2;
         CUtensorMap tmWT2;
-        int rc2 = make_tmap_bf16_2d(&tmWT2, whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+        int rc2 = plan_only ? OK : make_tmap_bf16_2d(&tmWT2, whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
         if (rc2 != OK) return rc2;
         const size_t smem2 = exclusive_smem(static_cast<size_t>(128) * (H - 256) * 2 + static_cast<size_t>(4) * H * NB2 * 2 +
                                             static_cast<size_t>(4) * NB2 * 32 * 4 * 2 + static_cast<size_t>(8) * NB2 * 4 * 16 + 64 + 1024);
         CTCB_REQUIRE(smem2 <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem2, H);
         p.mma_split = 4; p.groups = groups2;
-        if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2))
+        if (cluster_ok(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2)) {
+            if (plan_only) { *plan_ctas = 2 * (H / 128) * 2 * groups2; return OK; }
             return launch_clustered(lstm_bwd2_kernel<NB2>, dim3(2, H / 128, 2 * groups2), dim3(2, H / 128, 1), smem2, false,
                                     tmWT2, p, stream, LSTM_THREADS, start_ev);
+        }
     }
     int ex = exchange_mode(H);
     {
@@ -2247,13 +2275,13 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
     const int groups_total = (N + NB - 1) / NB;
     const int MB = H / 128;
     CUtensorMap tmWT;   // only read by the split-operand kernels (W^T_lo slice -> shared memory)
-    int rc = make_tmap_bf16_2d(&tmWT, x3 ? whhT_lo_packed : whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
+    int rc = plan_only ? OK : make_tmap_bf16_2d(&tmWT, x3 ? whhT_lo_packed : whhT_packed, static_cast<uint64_t>(8) * H, H, H, 128, 64);
     if (rc != OK) return rc;
     const size_t smem = lstm_smem_bytes(NB, H, true, ex, x3);
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
     p.mma_split = mma_issuers(NB, H);
     p.groups = groups_total;
-    if (getenv("CTCB200_LSTM_TRACE")) {
+    if (!plan_only && getenv("CTCB200_LSTM_TRACE")) {
         static long long* dbuf = nullptr;
         if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
         if (T <= 4096) {
@@ -2262,6 +2290,12 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         }
     }
     BwdTraceDump trace_dump{p, stream};
+    if (plan_only) {
+        if (cl) *plan_ctas = 4 * MB * 2 * groups_total;
+        return OK;
+    }
+    CTCB_REQUIRE(cl || progress_counter == nullptr,
+                 "lstm_bwd: streamed gate gradients need the clustered kernels (ask ctcb200_lstm_bwd_plan first)");
     if (cl) {
         dim3 grid(4, MB, 2 * groups_total), cluster(4, MB, 1);
         return launch_clustered(bwd_kernel(NB, ex, x3, cell_k), grid, cluster, smem, false, tmWT, p, stream, LSTM_THREADS, start_ev);
@@ -2288,4 +2322,35 @@ extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT
         if (rc != OK) return rc;
     }
     return OK;
+}
+}  // namespace
+}  // namespace ctcb200
+
+extern "C" CTCB200_API int ctcb200_lstm_bwd(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
+                                            const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* dg_rec,
+                                            void* dg_rec_lo, void* scratch, int T, int N, int H, int batch_tile, int cell,
+                                            const float* bn_x, const float* bn_coef, void* resident_counter,
+                                            void* resident_event, ctcb200_stream_t stream) {
+    return lstm_bwd_impl(dhout, whhT_packed, whhT_lo_packed, c_save, gates_save, dg, dg_lo, dg_rec, dg_rec_lo, scratch, T, N, H,
+                         batch_tile, cell, bn_x, bn_coef, resident_counter, resident_event, nullptr, 0, false, false, nullptr,
+                         stream);
+}
+
+extern "C" CTCB200_API int ctcb200_lstm_bwd_streamed(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
+                                                     const float* c_save, const void* gates_save, void* dg, void* dg_lo,
+                                                     void* dg_rec, void* dg_rec_lo, void* scratch, int T, int N, int H,
+                                                     int batch_tile, int cell, const float* bn_x, const float* bn_coef,
+                                                     void* resident_counter, void* progress_counter, int chunk_T,
+                                                     ctcb200_stream_t stream) {
+    return lstm_bwd_impl(dhout, whhT_packed, whhT_lo_packed, c_save, gates_save, dg, dg_lo, dg_rec, dg_rec_lo, scratch, T, N, H,
+                         batch_tile, cell, bn_x, bn_coef, resident_counter, nullptr, progress_counter, chunk_T, false, false,
+                         nullptr, stream);
+}
+
+extern "C" CTCB200_API int ctcb200_lstm_bwd_plan(int N, int H, int batch_tile, int x3, int cell) {
+    int ctas = 0;
+    if (lstm_bwd_impl(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1, N, H, batch_tile,
+                      cell, nullptr, nullptr, nullptr, nullptr, nullptr, 0, x3 != 0, true, &ctas, nullptr) != OK)
+        return 0;
+    return ctas;
 }

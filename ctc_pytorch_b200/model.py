@@ -13,6 +13,7 @@ Behaviour kept on purpose: the LSTM and BatchNorm run ove
 layer 0 never has BatchNorm, BatchNorm statistics are over T*N rows, the fc BatchNorm follows
 rnn_param['batch_norm'].
 """
+import contextlib
 import ctypes
 import math
 import os
@@ -103,7 +104,8 @@ def _gemm(a, b, out=None, **kw):
     (the accumulating launches add their tiles into C through the TMA unit)."""
     if a.lo is None:
         return ops.gemm_tn(a.hi, b.hi, out=out, **kw)
-    out = ops.gemm_tn(a.lo, b.hi, out=out, **kw)
+    acc = bool(kw.pop("accumulate", False))
+    out = ops.gemm_tn(a.lo, b.hi, out=out, accumulate=acc, **kw)
     ops.gemm_tn(a.hi, b.lo, out=out, accumulate=True, **kw)
     ops.gemm_tn(a.hi, b.hi, out=out, accumulate=True, **kw)
     return out
@@ -114,7 +116,8 @@ def _gemm_atb(a, b, out=None, **kw):
     three accumulated products as _gemm."""
     if a.lo is None:
         return ops.gemm_atb(a.hi, b.hi, out=out, **kw)
-    out = ops.gemm_atb(a.lo, b.hi, out=out, **kw)
+    acc = bool(kw.pop("accumulate", False))
+    out = ops.gemm_atb(a.lo, b.hi, out=out, accumulate=acc, **kw)
     ops.gemm_atb(a.hi, b.lo, out=out, accumulate=True, **kw)
     ops.gemm_atb(a.hi, b.hi, out=out, accumulate=True, **kw)
     return out
@@ -259,6 +262,44 @@ def _gx_stream_plan(model, T, N, H, x3, cell, packed, dev):
     if ctas <= 0 or free < 16:
         return None   # not one all-resident clustered launch, or no SMs left for the GEMMs
     return chunks, chunk_T, free, "stream"
+
+
+_DG_PROGRESS = {}
+
+
+def _dg_progress_state(dev):
+    """[uint32[1] device counter, host-side base] the BPTT kernels count their finished gate-gradient chunks in."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _DG_PROGRESS:
+        _DG_PROGRESS[key] = [torch.zeros(1, dtype=torch.int32, device=dev), 0]
+    return _DG_PROGRESS[key]
+
+
+def _dg_stream_plan(model, T, N, H, D, x3, cell, packed, overlap, dev):
+    """Streamed gate gradients (include/ctcb200.h, ctcb200_lstm_bwd_streamed): the input-gradient GEMM dX = dG W_ih of a layer —
+    and the weight-gradient contractions of the FIRST layer, which have no later BPTT kernel to hide under — follow the BPTT
+    kernel chunk by chunk on the side stream instead of starting when it ends; only the last chunk is left for the main
+    stream. Returns None or (chunks, chunk_T, ctas, mode), mode 'stream' or 'serial' (same chunk launches after the kernel: the
+    CPU emulation and CTCB200_OVERLAP_DG=serial). model.overlap_dg / CTCB200_OVERLAP_DG=0|1|serial|force, model.dg_chunks /
+    CTCB200_DG_CHUNKS (default 8). On the GPU the split-operand mode keeps the whole-GEMM path unless forced: its three products
+    per contraction already fill the idle SMs for longer than a BPTT kernel runs."""
+    env = os.environ.get("CTCB200_OVERLAP_DG")
+    on = bool(getattr(model, "overlap_dg", True)) if env is None else env != "0"
+    if not on or packed or D != 2 or T < 4:
+        return None
+    chunks = int(os.environ.get("CTCB200_DG_CHUNKS", getattr(model, "dg_chunks", 8)))
+    chunk_T = max(1, -(-T // max(1, chunks)))
+    chunks = -(-T // chunk_T)
+    if chunks < 2:
+        return None
+    if dev.type != "cuda" or env == "serial":
+        return chunks, chunk_T, 0, "serial"
+    if (x3 and env != "force") or not overlap or _lib._DEBUG_SYNC or _overlap_gate() != "memop":
+        return None
+    ctas = int(_lib.lib().dll.ctcb200_lstm_bwd_plan(N, H, int(model.batch_tile), 1 if x3 else 0, int(cell)))
+    if ctas <= 0:
+        return None
+    return chunks, chunk_T, ctas, "stream"
 
 
 def _dropout_mask(model, shape, p, dev):
@@ -634,44 +675,26 @@ class _RnnStackFn(torch.autograd.Function):
         if sync is not None:
             sync.reduce(fc_buf)   # the output layer's gradients travel while the whole RNN stack is still back-propagating
 
-        def _wgrad(item, mc):
-            """dW_ih, dW_hh (both directions) of one layer from its gate gradients; runs on the current stream."""
+        def _wgrad_finish(item, tmp_ih, t1, t2, extra=()):
+            """Weight-gradient products (rows in dG's packed gate order) -> torch's layout inside the layer's flat bucket; hands
+            the bucket to the gradient all-reduce."""
             layer_, rec_, (dg_, dgrec_), li_, buf_, views_ = item
             rnn = layer_.rnn
             GH = rec_.G * H     # rows of torch's weight matrices per direction (4H LSTM, 3H GRU, H RNN)
             I_ = rec_.I
-            # contraction over the T*N rows with both operands as they are (ops.gemm_atb): gate gradients [R, 8H] from the
-            # BPTT kernel, layer input [R, I] bf16 from the forward pass, layer output [R, 2H] cast here
-            Xb, Hb = rec_.Xb, rec_.Hb
-            if Hb is None:
-                Hb, _ = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
-            # the products come out with their rows in dG's packed gate order; one row gather each puts them into torch's
             perm = _gate_row_perm(H, dev)
             dwih = views_[0].view(8 * H, I_)
-            if packed:   # each direction against the input in its own alignment
-                tmp = (_gemm_atb(dg_.cols(0, 4 * H), Xb.cols(0, I_), k=R, max_ctas=mc),
-                       _gemm_atb(dg_.cols(4 * H, 8 * H), rec_.Xrb.cols(0, I_), k=R, max_ctas=mc))
-                torch.index_select(tmp[0], 0, perm, out=dwih[:4 * H])
-                torch.index_select(tmp[1], 0, perm, out=dwih[4 * H:])
-            else:
-                tmp = _gemm_atb(dg_, Xb.cols(0, I_), k=R, max_ctas=mc)                   # [8H, I]
-                torch.index_select(tmp[:4 * H], 0, perm, out=dwih[:4 * H])
-                torch.index_select(tmp[4 * H:], 0, perm, out=dwih[4 * H:])
-                tmp = (tmp,)
+            torch.index_select(tmp_ih[0], 0, perm, out=dwih[:4 * H])
+            torch.index_select(tmp_ih[1], 0, perm, out=dwih[4 * H:])
             grads[rnn.weight_ih_l0] = dwih[:GH]
             whf, whr = views_[1].view(4 * H, H), views_[2].view(4 * H, H)
-            dgr_ = dgrec_ if dgrec_ is not None else dg_     # what the recurrent weights see (GRU differs)
-            if T > 1:
-                # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan: one time step = N rows
-                t1 = _gemm_atb(dgr_.cols(0, 4 * H), Hb.cols(0, H), a_roff=N, b_roff=0, k=R - N, max_ctas=mc)
+            if t1 is not None:
                 torch.index_select(t1, 0, perm, out=whf)
-                tmp = tmp + (t1,)
-                if D == 2:
-                    t2 = _gemm_atb(dgr_.cols(4 * H, 8 * H), Hb.cols(H, 2 * H), a_roff=0, b_roff=N, k=R - N, max_ctas=mc)
-                    torch.index_select(t2, 0, perm, out=whr)
-                    tmp = tmp + (t2,)
             else:
                 whf.zero_()
+            if t2 is not None:
+                torch.index_select(t2, 0, perm, out=whr)
+            else:
                 whr.zero_()
             grads[rnn.weight_hh_l0] = whf[:GH]
             if D == 2:
@@ -680,7 +703,59 @@ class _RnnStackFn(torch.autograd.Function):
                 sync.reduce(buf_)    # one collective per layer, behind the BPTT kernels of the layers below
             if torch.cuda.current_stream(dev) != main:  # allocated on the main stream, written here on the side stream
                 buf_.record_stream(torch.cuda.current_stream(dev))
-            keep.append((dg_, dgrec_, Xb, Hb, tmp))  # alive until the streams are joined
+            keep.append((dg_, dgrec_, tmp_ih, t1, t2) + tuple(extra))  # alive until the streams are joined
+
+        def _wgrad(item, mc):
+            """dW_ih, dW_hh (both directions) of one layer from its gate gradients; runs on the current stream."""
+            layer_, rec_, (dg_, dgrec_), li_, buf_, views_ = item
+            I_ = rec_.I
+            # contraction over the T*N rows with both operands as they are (ops.gemm_atb): gate gradients [R, 8H] from the
+            # BPTT kernel, layer input [R, I] bf16 from the forward pass, layer output [R, 2H] cast here
+            Xb, Hb = rec_.Xb, rec_.Hb
+            if Hb is None:
+                Hb, _ = _cast_t(rec_.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
+            if packed:   # each direction against the input in its own alignment
+                tmp_ih = (_gemm_atb(dg_.cols(0, 4 * H), Xb.cols(0, I_), k=R, max_ctas=mc),
+                          _gemm_atb(dg_.cols(4 * H, 8 * H), rec_.Xrb.cols(0, I_), k=R, max_ctas=mc))
+            else:
+                tmp = _gemm_atb(dg_, Xb.cols(0, I_), k=R, max_ctas=mc)                   # [8H, I]
+                tmp_ih = (tmp[:4 * H], tmp[4 * H:])
+            dgr_ = dgrec_ if dgrec_ is not None else dg_     # what the recurrent weights see (GRU differs)
+            t1 = t2 = None
+            if T > 1:
+                # pairs (dG_t, h_{t-1}) for the forward scan, (dG_t, h_{t+1}) for the reverse scan: one time step = N rows
+                t1 = _gemm_atb(dgr_.cols(0, 4 * H), Hb.cols(0, H), a_roff=N, b_roff=0, k=R - N, max_ctas=mc)
+                if D == 2:
+                    t2 = _gemm_atb(dgr_.cols(4 * H, 8 * H), Hb.cols(H, 2 * H), a_roff=0, b_roff=N, k=R - N, max_ctas=mc)
+            _wgrad_finish(item, tmp_ih, t1, t2, (Xb, Hb))
+
+        # ---- streamed gate gradients (_dg_stream_plan): chunk c = scan steps [c*chunk_T, (c+1)*chunk_T) of both BPTT scans ----
+        def _chunk_frames(c, chunk_T):
+            a, b = c * chunk_T, min(T, (c + 1) * chunk_T)
+            return (T - b, T - a), (a, b)     # frames the forward direction's / the reverse direction's BPTT covers in chunk c
+
+        def _dx_chunk(dg_, rec_, dx_, c, chunk_T, mc):
+            """this chunk's share of dX = dG W_ih: each direction's K half against the rows it has finished (accumulated)."""
+            for d, (ta, tb) in enumerate(_chunk_frames(c, chunk_T)):
+                _gemm(dg_.rows(ta * N, tb * N), rec_.wihT_p, out=dx_[ta * N:tb * N], k=4 * H, a_koff=d * 4 * H, b_koff=d * 4 * H,
+                      accumulate=True, max_ctas=mc)
+
+        def _wg_chunk(st, c, chunk_T, mc):
+            """this chunk's share of the first layer's dW_ih / dW_hh contractions over time (accumulated)."""
+            dg_, dgr_, Xb, Hb, I_, tmp_ih, t1, t2 = st
+            (fa, fb), (ra, rb) = _chunk_frames(c, chunk_T)
+            _gemm_atb(dg_.cols(0, 4 * H), Xb.cols(0, I_), out=tmp_ih[0], accumulate=True, a_roff=fa * N, b_roff=fa * N,
+                      k=(fb - fa) * N, max_ctas=mc)
+            _gemm_atb(dg_.cols(4 * H, 8 * H), Xb.cols(0, I_), out=tmp_ih[1], accumulate=True, a_roff=ra * N, b_roff=ra * N,
+                      k=(rb - ra) * N, max_ctas=mc)
+            f0 = max(fa, 1)           # (dG_t, h_{t-1}), t >= 1
+            if fb > f0:
+                _gemm_atb(dgr_.cols(0, 4 * H), Hb.cols(0, H), out=t1, accumulate=True, a_roff=f0 * N, b_roff=(f0 - 1) * N,
+                          k=(fb - f0) * N, max_ctas=mc)
+            r1 = min(rb, T - 1)       # (dG_t, h_{t+1}), t <= T - 2
+            if r1 > ra:
+                _gemm_atb(dgr_.cols(4 * H, 8 * H), Hb.cols(H, 2 * H), out=t2, accumulate=True, a_roff=ra * N, b_roff=(ra + 1) * N,
+                          k=(r1 - ra) * N, max_ctas=mc)
 
         pending = None
         scratch = torch.empty(_lib.lib().dll.ctcb200_lstm_scratch_bytes(N, H), dtype=torch.uint8, device=dev)
@@ -706,12 +781,33 @@ class _RnnStackFn(torch.autograd.Function):
                              alloc((R, 8 * H), dtype=torch.bfloat16, device=dev) if x3 else None)
             dg = _dg_buf()
             dg_rec = _dg_buf() if rec.cell == 1 else None   # GRU: the recurrent weights see a different n-gate gradient
-            _call("ctcb200_lstm_bwd", _lib.ptr(dh), _lib.ptr(rec.whhT_p.hi), _lib.ptr(rec.whhT_p.lo), _lib.ptr(rec.c_save),
-                  _lib.ptr(rec.gates), _lib.ptr(dg.hi), _lib.ptr(dg.lo), _lib.ptr(dg_rec.hi) if dg_rec else None,
-                  _lib.ptr(dg_rec.lo) if dg_rec else None, _lib.ptr(scratch), T, N, H, model.batch_tile, rec.cell,
-                  _lib.ptr(bn_fuse[0]) if bn_fuse else None, _lib.ptr(bn_fuse[1]) if bn_fuse else None,
-                  _lib.ptr(res[0]) if (overlap and gate == "memop") else None,
-                  gate_ev_ptr if (overlap and gate == "event") else None, stream())
+            need_dx = li > 0 or bool(ctx.needs_input_grad[1])
+            plan = _dg_stream_plan(model, T, N, H, D, x3, rec.cell, packed, overlap and gate == "memop", dev)
+            streamed = plan is not None and plan[3] == "stream"
+            dx_s = wg0 = None
+            if plan is not None:
+                # streamed gate gradients: the chunk GEMMs accumulate into zero-initialised outputs (written on the main stream
+                # before the BPTT launch, so they are ordered before every chunk on either stream)
+                chunks, chunk_T, prog_ctas, _mode = plan
+                if need_dx:
+                    dx_s = torch.zeros((R, I), dtype=torch.float32, device=dev)
+                if li == 0:   # the first layer's weight gradients have no later BPTT kernel to hide under
+                    tmp0 = torch.zeros((8 * H, I), dtype=torch.float32, device=dev)
+                    wg0 = [dg, dg_rec if dg_rec is not None else dg, rec.Xb, rec.Hb, I, (tmp0[:4 * H], tmp0[4 * H:]),
+                           torch.zeros((4 * H, H), dtype=torch.float32, device=dev),
+                           torch.zeros((4 * H, H), dtype=torch.float32, device=dev)]
+            bwd_args = (_lib.ptr(dh), _lib.ptr(rec.whhT_p.hi), _lib.ptr(rec.whhT_p.lo), _lib.ptr(rec.c_save),
+                        _lib.ptr(rec.gates), _lib.ptr(dg.hi), _lib.ptr(dg.lo), _lib.ptr(dg_rec.hi) if dg_rec else None,
+                        _lib.ptr(dg_rec.lo) if dg_rec else None, _lib.ptr(scratch), T, N, H, model.batch_tile, rec.cell,
+                        _lib.ptr(bn_fuse[0]) if bn_fuse else None, _lib.ptr(bn_fuse[1]) if bn_fuse else None,
+                        _lib.ptr(res[0]) if (overlap and gate == "memop") else None)
+            if streamed:
+                prog = _dg_progress_state(dev)
+                prog_base = prog[1]
+                prog[1] = (prog_base + prog_ctas * chunks) & 0xFFFFFFFF
+                _call("ctcb200_lstm_bwd_streamed", *(bwd_args + (_lib.ptr(prog[0]), chunk_T, stream())))
+            else:
+                _call("ctcb200_lstm_bwd", *(bwd_args + (gate_ev_ptr if (overlap and gate == "event") else None, stream())))
             if bn_fuse:
                 keep.append(bn_fuse)
                 bn_fuse = None
@@ -719,6 +815,7 @@ class _RnnStackFn(torch.autograd.Function):
             # above (its dG is complete) go to the side stream, gated on *this* layer's BPTT grid being resident, and
             # are confined to the SMs that latency-bound kernel leaves idle. The gate is only ever enqueued after the
             # launch it waits for.
+            item = (layer, rec, (dg, dg_rec), li, buf, views)
             if overlap:
                 if gate == "memop":
                     res[1] = (res[1] + 1) & 0xFFFFFFFF
@@ -731,8 +828,35 @@ class _RnnStackFn(torch.autograd.Function):
                         else:
                             _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(res[0]), res[1])
                         _wgrad(pending[:6], side_ctas)
-                pending = [layer, rec, (dg, dg_rec), li, buf, views, None]
+                pending = None if wg0 is not None else [layer, rec, (dg, dg_rec), li, buf, views, None]
+
+            def _chunks_of(c_list, mc):
+                for c in c_list:
+                    if streamed and mc:   # this chunk's rows of every CTA of the BPTT launch are written
+                        _call("ctcb200_stream_wait_geq", _lib.stream(), _lib.ptr(prog[0]),
+                              (prog_base + prog_ctas * (c + 1)) & 0xFFFFFFFF)
+                    if dx_s is not None:
+                        _dx_chunk(dg, rec, dx_s, c, chunk_T, mc)
+                    if wg0 is not None:
+                        _wg_chunk(wg0, c, chunk_T, mc)
+
+            if plan is not None:
+                if wg0 is not None and wg0[3] is None:
+                    with torch.cuda.stream(side) if streamed else contextlib.nullcontext():
+                        wg0[3], _ = _cast_t(rec.h_out, N * 2 * H, 2 * H, N, R, 2 * H, want=True, want_t=False, x3=x3)
+                if streamed:
+                    with torch.cuda.stream(side):
+                        _chunks_of(range(chunks - 1), side_ctas)
+                    main.wait_stream(side)
+                    _chunks_of([chunks - 1], 0)   # the last chunk: behind the BPTT kernel on the main stream, on all SMs
+                else:
+                    _chunks_of(range(chunks), 0)
+                if wg0 is not None:
+                    _wgrad_finish(item, wg0[5], wg0[6], wg0[7], (wg0[2], wg0[3]))
+
             def _input_grad():
+                if dx_s is not None:
+                    return dx_s
                 if not packed:
                     return _gemm(dg, rec.wihT_p, k=8 * H)                  # [R, I] rows (t, n)
                 dxf = _gemm(dg, rec.wihT_p, k=4 * H)                       # forward direction: already left-aligned
@@ -747,11 +871,11 @@ class _RnnStackFn(torch.autograd.Function):
                 dh = _input_grad()
                 if has_bn:
                     bn_fuse = _bn_backward(layer_bn, rec.bn, dh, rec.h_in, I, li - 1, views[3], views[4])
-                    if overlap and sync is not None:
+                    if overlap and sync is not None and pending is not None:
                         pending[6] = torch.cuda.Event()
                         pending[6].record(main)
-            if not overlap:
-                _wgrad((layer, rec, (dg, dg_rec), li, buf, views), 0)
+            if not overlap and wg0 is None:
+                _wgrad(item, 0)
         if overlap:
             if pending is not None:
                 _wgrad(pending[:6], 0)  # the first layer's weight gradients: nothing left to hide them under
@@ -787,6 +911,8 @@ class CTC_Model(nn.Module):
         self.overlap_wgrad = True  # weight-gradient GEMMs on a side stream, on the SMs the BPTT kernels leave idle
         self.overlap_gx = True     # input projection streamed chunk by chunk under the forward recurrence (_gx_stream_plan)
         self.gx_chunks = 8
+        self.overlap_dg = True     # input-gradient / first-layer weight-gradient GEMMs follow the BPTT kernel chunk by chunk
+        self.dg_chunks = 8
         # operand mode of every contraction: "bf16" (fast; gradients within ~1 % of fp32) or "x3" (split bf16 hi+lo, three
         # tensor-core products per contraction: gradients within 1e-3 of the reference's fp32 arithmetic)
         self.precision = os.environ.get("CTCB200_PRECISION", "bf16")

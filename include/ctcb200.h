@@ -170,6 +170,20 @@ CTCB200_API int ctcb200_lstm_fwd_streamed(const float* gx, const void* whh_packe
                                           int chunk_T, ctcb200_stream_t stream);
 CTCB200_API int ctcb200_lstm_fwd_ctas(int N, int H, int batch_tile, int x3, int cell);
 CTCB200_API int ctcb200_stream_write_value(ctcb200_stream_t stream, void* counter, uint32_t value);
+/* Streamed gate gradients: the mirror image for the backward pass (train_ctc.py:63). lstm_bwd_streamed is lstm_bwd plus a
+ * progress counter: every CTA of the launch adds 1 to *progress_counter each time its dG rows of another chunk_T scan steps
+ * are written (chunk c = scan steps [c*chunk_T, (c+1)*chunk_T): rows of frames T-1-s for the forward direction's BPTT, frames
+ * s for the reverse direction's; the last chunk may be shorter and is counted too). A second stream waits
+ * (ctcb200_stream_wait_geq) for base + (c+1) * ctcb200_lstm_bwd_plan() and runs the chunk's share of the input-gradient GEMM
+ * dX = dG * W_ih (and, for the first layer, of the weight-gradient contractions) on the SMs the BPTT kernel leaves idle, so
+ * that only the last chunk is left when the recurrence ends. ctcb200_lstm_bwd_plan: CTAs of the BPTT launch when it is one
+ * clustered launch (the only form that can be streamed), else 0. */
+CTCB200_API int ctcb200_lstm_bwd_streamed(const float* dhout, const void* whhT_packed, const void* whhT_lo_packed,
+                                          const float* c_save, const void* gates_save, void* dg, void* dg_lo, void* dg_rec,
+                                          void* dg_rec_lo, void* scratch, int T, int N, int H, int batch_tile, int cell,
+                                          const float* bn_x, const float* bn_coef, void* resident_counter,
+                                          void* progress_counter, int chunk_T, ctcb200_stream_t stream);
+CTCB200_API int ctcb200_lstm_bwd_plan(int N, int H, int batch_tile, int x3, int cell);
 
 /* ---- layout / normalisation kernels around the GEMMs (model_ctc.py:29-32 BatchNorm1d over T*N rows,
  * model_ctc.py:136-140,165-168 fc BatchNorm + LogSoftmax, model_ctc.py:175 the (N,T,F)->(T,N,F) transpose).

@@ -1,5 +1,5 @@
-"""Streamed input projection A/B on one GPU: bench.py's training step (cfg2 / cfg3 / cfg4, bf16 / x3) with the whole
-projection first (overlap_gx off) and with 4 / 8 / 16 time chunks streamed under the forward recurrence. Same Job, same
+"""Streamed input projection / streamed gate gradients A/B on one GPU: bench.py's training step (cfg2 / cfg3 / cfg4, bf16 / x3)
+with whole GEMMs around the recurrent kernels (overlap_gx / overlap_dg off) and with the time-chunked launches under them. Same Job, same
 batches, L2 flushed between steps; prints one JSON line per setting.
     python tools/gx_stream_ab.py [cfg2] [bf16] [steps]"""
 import json
@@ -23,9 +23,11 @@ def main():
     job = bench.Job(name, cfg, 0, 1, dev, prec, strong=False)
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
     rows = []
-    for label, on, chunks in (("whole", False, 8), ("stream4", True, 4), ("stream8", True, 8), ("stream16", True, 16),
-                              ("whole_again", False, 8), ("stream8_again", True, 8)):
+    for label, on, chunks, dg in (("whole", False, 8, False), ("gx8", True, 8, False), ("gx8_dg4", True, 8, 4), ("gx8_dg8", True, 8, 8),
+                                  ("gx8_dg16", True, 8, 16), ("gx16_dg16", True, 16, 16), ("whole_again", False, 8, False),
+                                  ("gx8_dg8_again", True, 8, 8)):
         job.model.overlap_gx, job.model.gx_chunks = on, chunks
+        job.model.overlap_dg, job.model.dg_chunks = bool(dg), (dg or 8)
         for w in range(3):
             job.step(job.devb[w % len(job.devb)])
         ms = bench.timed_loop(job, steps, flush, 1, e2e=False) / steps
@@ -43,7 +45,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
         job.model.train()
-        row = {"config": name, "precision": prec, "setting": label, "chunks": chunks if on else 1, "train_step_ms": round(ms, 4),
+        row = {"config": name, "precision": prec, "setting": label, "gx_chunks": chunks if on else 1, "dg_chunks": dg or 1, "train_step_ms": round(ms, 4),
                "forward_only_ms": round(e0.elapsed_time(e1) / steps, 4)}
         rows.append(row)
         print(json.dumps(row), flush=True)
