@@ -26,6 +26,9 @@ dg = torch.empty(R, 8 * H, dtype=torch.bfloat16, device=dev)
 scratch = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
 libs = {"head": ctypes.CDLL(os.path.join(ROOT, "tools", "_ab", "libctcb200_head.so")),
         "tree": ctypes.CDLL(os.path.join(ROOT, "ctc_pytorch_b200", "libctcb200.so"))}
+for f in sorted(os.listdir(os.path.join(ROOT, "tools", "_ab"))):    # optional experiment builds (-DAB_...)
+    if f.startswith("libctcb200_AB_"):
+        libs[f[len("libctcb200_"):-3]] = ctypes.CDLL(os.path.join(ROOT, "tools", "_ab", f))
 for L in libs.values():
     L.ctcb200_last_error.restype = ctypes.c_char_p
 
