@@ -417,7 +417,7 @@ def run_ours(args, name, cfg, rank, world):
         gemm_flops += 2.0 * rows * 8 * H * I * (3 if (l > 0 or cfg.get("cnn")) else 2)   # Gx, dWih (+ dX)
         gemm_flops += 2.0 * rows * 8 * H * H                          # dWhh (both directions)
     gemm_flops += 3 * 2.0 * rows * 2 * H * C
-    gemm_ms = kern_ms.get("ctcb200_gemm_tn_bf16", 0.0)
+    gemm_ms = kern_ms.get("ctcb200_gemm_tn_bf16", 0.0) + kern_ms.get("ctcb200_gemm_atb_bf16", 0.0)   # K-major + MN-major launches
     ctc_bytes = 2.0 * Tr * N * C * 4
     ctc_ms = kern_ms.get("ctcb200_ctc_loss_fwd", 0.0) + kern_ms.get("ctcb200_ctc_loss_bwd", 0.0)
     extra = {

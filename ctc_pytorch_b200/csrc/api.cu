@@ -176,3 +176,60 @@ extern "C" CTCB200_API int ctcb200_stream_write_value(ctcb200_stream_t stream_, 
     }
     return ctcb200::OK;
 }
+
+// ---- can a kernel on one stream make progress while a kernel on another stream is resident? ----------------------------------
+// The streamed input projection (ctcb200_lstm_fwd_streamed) launches a kernel that WAITS for the output of kernels launched after
+// it on a second stream. That is only legal when the device really runs them concurrently: profilers (Nsight Compute serialises
+// every kernel), CUDA_LAUNCH_BLOCKING, some debuggers and MPS configurations do not — the recurrent kernel would wait until its
+// timeout trap. The probe runs the same pattern in miniature: a one-thread kernel on stream_a polls a flag for at most
+// `limit_ms`; a trivial kernel followed by a stream memory operation on stream_b raises the flag.
+namespace ctcb200 {
+namespace {
+__global__ void probe_wait_kernel(const unsigned int* flag, unsigned int* result, long long limit_cycles) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) == 0u) {
+        if (clock64() - t0 > limit_cycles) { *result = 0u; return; }
+        __nanosleep(500);
+    }
+    *result = 1u;
+}
+__global__ void probe_touch_kernel(unsigned int* word) { *word = 1u; }
+}  // namespace
+}  // namespace ctcb200
+
+// returns 1 (concurrent), 0 (the second stream's work only ran after the waiting kernel gave up) or a negative error code.
+// Synchronises both streams; meant to be called once per device and process, not per step.
+extern "C" CTCB200_API int ctcb200_concurrency_probe(ctcb200_stream_t stream_a_, ctcb200_stream_t stream_b_, int limit_ms) {
+    using namespace ctcb200;
+    cudaStream_t sa = static_cast<cudaStream_t>(stream_a_), sb = static_cast<cudaStream_t>(stream_b_);
+    CTCB_REQUIRE(sa != sb, "concurrency_probe: the two streams must differ");
+    CTCB_REQUIRE(limit_ms > 0 && limit_ms <= 1000, "concurrency_probe: limit_ms %d not in (0, 1000]", limit_ms);
+    // both kernels loaded before the first one spins (a lazy first-launch load of the second would itself wait for the first)
+    cudaFuncAttributes fa;
+    CTCB_CUDA(cudaFuncGetAttributes(&fa, probe_wait_kernel));
+    CTCB_CUDA(cudaFuncGetAttributes(&fa, probe_touch_kernel));
+    int khz = 0;
+    CTCB_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, current_device()));
+    if (khz <= 0) khz = 2000000;
+    unsigned int* words = nullptr;   // [0] flag, [1] result, [2] scratch of the touch kernel
+    CTCB_CUDA(cudaMalloc(&words, 3 * sizeof(unsigned int)));
+    int rc = OK;
+    unsigned int result = 0;
+    cudaError_t e = cudaMemsetAsync(words, 0, 3 * sizeof(unsigned int), sa);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sa);
+    if (e == cudaSuccess) {
+        probe_wait_kernel<<<1, 1, 0, sa>>>(words, words + 1, static_cast<long long>(khz) * limit_ms);
+        probe_touch_kernel<<<1, 1, 0, sb>>>(words + 2);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        rc = ctcb200_stream_write_value(sb, words, 1u);
+        cudaError_t e1 = cudaStreamSynchronize(sa), e2 = cudaStreamSynchronize(sb);
+        e = e1 != cudaSuccess ? e1 : e2;
+    }
+    if (e == cudaSuccess && rc == OK) e = cudaMemcpy(&result, words + 1, sizeof(result), cudaMemcpyDeviceToHost);
+    (void)cudaFree(words);
+    if (e != cudaSuccess) return cuda_fail(e, "concurrency probe", __FILE__, __LINE__);
+    if (rc != OK) return rc;
+    return result ? 1 : 0;
+}

@@ -53,6 +53,7 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t
 // Per-device host-side state (function attributes, probe caches, SM counts) is indexed by the CUDA device ordinal.
 constexpr int MAX_DEVICES = 64;
 int current_device();
+int gemm_preload();   // gemm.cu: load every GEMM tile width on the current device (see gemm_prepare)
 int device_sm_count();
 
 }  // namespace ctcb200

@@ -18,6 +18,7 @@
 // the per-row scales are stored so the posterior exponent is formed as (a~ + b~ - lp) + float(A_t + B_t + nll).
 #include "common.cuh"
 #include "ctcb200.h"
+#include <stdlib.h>
 
 namespace ctcb200 {
 
@@ -113,7 +114,7 @@ __device__ __forceinline__ void load_states(LaneStates<KS>& st, const int64_t* t
 // workspace per utterance: hist_a / hist_b [T][KS*32] floats (slot j*32+lane), off_a / off_b [T] doubles (log-scale
 // removed from the stored row), nll_d (double)
 // ---------------------------------------------------------------------------------------------
-template <int KS>
+template <int KS, bool ALPHA_ONLY>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
                  const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len, float* __restrict__ hist_a,
@@ -121,8 +122,9 @@ ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
                  double* __restrict__ nll_d, float* __restrict__ nll, int T, int N, int C, int blank) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (WARPS_PER_BLOCK / 2) + (warp >> 1);
-    const bool is_beta = warp & 1;
+    // ALPHA_ONLY (throughput form, see ctc_beta_grad_kernel): every warp is the alpha sweep of its own utterance
+    const int n = ALPHA_ONLY ? blockIdx.x * WARPS_PER_BLOCK + warp : blockIdx.x * (WARPS_PER_BLOCK / 2) + (warp >> 1);
+    const bool is_beta = ALPHA_ONLY ? false : (warp & 1);
     if (n >= N) return;
     float* rowbuf = smem + warp * PF * C;  // ring of PF rows
 
@@ -325,6 +327,151 @@ ctc_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ target
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Throughput form for large batches (N >= ctc_fused_min_batch): the alpha sweep alone (ctc_sweep_kernel<KS, true>, one warp
+// per utterance, history kept), then ONE kernel that runs the beta sweep and emits the gradient row of frame t the moment
+// beta_t is known — no beta history, no separate gradient pass. HBM traffic per (t, n) row: log-probs twice (2 x 4C bytes),
+// the alpha row once each way (2 x 128 KS bytes), the gradient once (4C bytes); the latency form above moves two histories
+// each way and reads the log-probs three times. The chain of an utterance is twice as long (alpha, then beta), which is why
+// small batches — where the T dependent steps are the cost — keep the concurrent sweeps.
+// The arithmetic is the gradient kernel's, term for term: g_s = exp((alpha~ + beta~ - lp) + float(A_t + B_t + nll)).
+// Ring slot r of a warp: [C_pad floats log-probs of row r | KS*32 floats alpha row r], both brought in with cp.async
+// PF - 1 frames ahead of the sweep.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int KS>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
+                     const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
+                     const float* __restrict__ hist_a, const double* __restrict__ off_a, const double* __restrict__ nll_d,
+                     const float* __restrict__ grad_nll, float grad_scale, float* __restrict__ grad, int T, int N, int C,
+                     int blank) {
+    extern __shared__ __align__(16) float smem_bg[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (n >= N) return;
+    const int C_pad = (C + 3) & ~3;
+    const int ROW = C_pad + KS * 32;
+    float* ring = smem_bg + warp * (PF * ROW + C_pad);
+    float* occ = ring + PF * ROW;
+
+    const int S = static_cast<int>(tgt_len[n]);
+    const int L = 2 * S + 1;
+    int Tn = static_cast<int>(in_len[n]);
+    if (Tn > T) Tn = T;
+    const long long row_stride = static_cast<long long>(N) * C;
+    const float* lp_n = lp + static_cast<size_t>(n) * C;
+    float* g_n = grad + static_cast<size_t>(n) * C;
+    // frames past the utterance end: zero gradient (torch semantics)
+    for (int t = Tn > 0 ? Tn : 0; t < T; ++t)
+        for (int c = lane; c < C; c += 32) g_n[t * row_stride + c] = 0.0f;
+    if (Tn <= 0) return;
+    LaneStates<KS> st;
+    load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
+    const float* hist = hist_a + static_cast<size_t>(n) * T * (KS * 32);
+    const double* offs = off_a + static_cast<size_t>(n) * T;
+    const double nllv = nll_d[n];
+    const float gscale = grad_scale * (grad_nll ? grad_nll[n] : 1.0f);
+    for (int c = lane; c < C; c += 32) occ[c] = 0.0f;
+
+    auto prefetch = [&](int r) {   // one commit group per call (empty for r < 0): the group count follows the frame count
+        if (r >= 0) {
+            float* dst = ring + (r % PF) * ROW;
+            const float* src = lp_n + static_cast<long long>(r) * row_stride;
+            for (int c = lane; c < C; c += 32) cp_async_4(dst + c, src + c);
+            const float* hsrc = hist + static_cast<size_t>(r) * (KS * 32);
+            for (int i = lane; i < KS * 8; i += 32) cp_async_16(dst + C_pad + i * 4, hsrc + i * 4);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < PF - 1; ++i) prefetch(Tn - 1 - i);
+
+    double scale_acc = 0.0;
+    double offa_next = offs[Tn - 1];
+    float a[KS];
+    for (int t = Tn - 1; t >= 0; --t) {
+        const float* cur = ring + (t % PF) * ROW;
+        const float* al = cur + C_pad;
+        cp_async_wait_pending<PF - 2>();
+        __syncwarp();   // row t has landed for every lane; every lane is done with row t + 1 and with its occupancy sums
+        prefetch(t - (PF - 1));
+        const double offa = offa_next;
+        if (t > 0) offa_next = offs[t - 1];
+        if (t == Tn - 1) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                int s = lane * KS + j;
+                a[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
+            }
+        } else {
+            float dn1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+            float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
+                                  : __shfl_down_sync(0xffffffffu, a[0], 2);
+            if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
+            if (KS == 1 && lane == 30) dn2 = NEG_INF;
+            float nw[KS];
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                float n1 = (j + 1 < KS) ? a[j + 1 < KS ? j + 1 : 0] : dn1;
+                float n2 = (j + 2 < KS) ? a[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
+                if (KS >= 2 && j == KS - 1) n2 = dn2;
+                if (!st.skip_out[j]) n2 = NEG_INF;
+                float v = (KS % 2 == 0 && (j & 1) == 0) ? lse2_fast(a[j], n1) : lse3(a[j], n1, n2);
+                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+            }
+#pragma unroll
+            for (int j = 0; j < KS; ++j) a[j] = nw[j];
+        }
+        if ((t % RENORM) == 0) {
+            float m = NEG_INF;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (m > NEG_INF) {
+#pragma unroll
+                for (int j = 0; j < KS; ++j) a[j] -= m;
+                scale_acc += static_cast<double>(m);
+            }
+        }
+        // state posteriors of frame t, summed per class
+        const float shift = static_cast<float>(offa + scale_acc + nllv);
+        float blank_sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            if (st.valid[j]) {
+                const float g = expf((al[j * 32 + lane] + a[j] - cur[st.label[j]]) + shift);
+                if ((lane * KS + j) & 1) atomicAdd(&occ[st.label[j]], g);
+                else blank_sum += g;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) blank_sum += __shfl_xor_sync(0xffffffffu, blank_sum, o);
+        if (lane == 0) atomicAdd(&occ[blank], blank_sum);
+        __syncwarp();
+        float* g_row = g_n + t * row_stride;
+        for (int c = lane; c < C; c += 32) {
+            g_row[c] = (expf(cur[c]) - occ[c]) * gscale;
+            occ[c] = 0.0f;
+        }
+    }
+}
+
+// Batch size from which the throughput form is used (ctcb200_ctc_set_fused_min_batch; CTCB200_CTC_FUSED_MIN_N at load time).
+int& ctc_fused_min_batch() {
+    static int v = [] {
+        const char* e = getenv("CTCB200_CTC_FUSED_MIN_N");
+        return e ? atoi(e) : 2048;
+    }();
+    return v;
+}
+bool ctc_fused(int N) { return N >= ctc_fused_min_batch(); }
+
 int ks_for(int max_target_len) {
     int L = 2 * max_target_len + 1;
     int k = (L + 31) / 32;
@@ -359,6 +506,12 @@ extern "C" CTCB200_API int64_t ctcb200_ctc_workspace_floats(int T, int N, int ma
     return 2 * hist_floats(T, N, ks) + 2 * (2 * static_cast<int64_t>(N) * T + N) + 2;
 }
 
+extern "C" CTCB200_API int ctcb200_ctc_set_fused_min_batch(int min_batch) {
+    const int prev = ctc_fused_min_batch();
+    if (min_batch >= 0) ctc_fused_min_batch() = min_batch;
+    return prev;
+}
+
 extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const int64_t* targets, int64_t target_stride,
                                     const int64_t* input_lengths, const int64_t* target_lengths, int T, int N,
                                     int C, int max_target_len, int blank, float* alpha_ws, float* nll,
@@ -366,19 +519,26 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTCB_REQUIRE(T > 0 && N > 0 && C > 0, "ctc_loss_fwd: empty shape T=%d N=%d C=%d", T, N, C);
     CTCB_REQUIRE(blank >= 0 && blank < C, "ctc_loss_fwd: blank %d out of range [0,%d)", blank, C);
-    CTCB_REQUIRE((reinterpret_cast<uintptr_t>(alpha_ws) & 7) == 0, "ctc_loss_fwd: workspace must be 8-byte aligned");
+    CTCB_REQUIRE((reinterpret_cast<uintptr_t>(alpha_ws) & 15) == 0, "ctc_loss_fwd: workspace must be 16-byte aligned");
     int ks = ks_for(max_target_len);
     CTCB_REQUIRE(ks <= 16, "ctc_loss_fwd: target length %d exceeds the supported maximum 255", max_target_len);
-    const int utt_per_block = WARPS_PER_BLOCK / 2;
+    const bool fused = ctc_fused(N);   // throughput form: alpha sweeps only here, beta + gradient in ctcb200_ctc_loss_bwd
+    const int utt_per_block = fused ? WARPS_PER_BLOCK : WARPS_PER_BLOCK / 2;
     dim3 grid((N + utt_per_block - 1) / utt_per_block), block(WARPS_PER_BLOCK * 32);
     size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * PF * C * sizeof(float);
     CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_fwd: class count %d too large for the row buffer", C);
     CtcWs w = carve(alpha_ws, T, N, ks);
-#define LAUNCH_A(KS)                                                                                          \
-    CTCB_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ctc_sweep_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,     \
-                                                        target_lengths, w.hist_a, w.hist_b, w.off_a, w.off_b, \
-                                                        w.nll_d, nll, T, N, C, blank)
+#define LAUNCH_A2(KS, AO)                                                                                           \
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<KS, AO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_sweep_kernel<KS, AO><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,       \
+                                                            target_lengths, w.hist_a, w.hist_b, w.off_a, w.off_b,   \
+                                                            w.nll_d, nll, T, N, C, blank)
+#define LAUNCH_A(KS)          \
+    if (fused) {              \
+        LAUNCH_A2(KS, true);  \
+    } else {                  \
+        LAUNCH_A2(KS, false); \
+    }
     switch (ks) {
         case 1: LAUNCH_A(1); break;
         case 2: LAUNCH_A(2); break;
@@ -386,6 +546,7 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const in
         case 8: LAUNCH_A(8); break;
         default: LAUNCH_A(16); break;
     }
+#undef LAUNCH_A2
 #undef LAUNCH_A
     CTCB_LAUNCH_CHECK();
     return OK;
@@ -401,6 +562,29 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_bwd(const float* log_probs, const in
     int ks = ks_for(max_target_len);
     CTCB_REQUIRE(ks <= 16, "ctc_loss_bwd: target length %d exceeds the supported maximum 255", max_target_len);
     (void)nll;
+    CTCB_REQUIRE((reinterpret_cast<uintptr_t>(alpha_ws) & 15) == 0, "ctc_loss_bwd: workspace must be 16-byte aligned");
+    if (ctc_fused(N)) {
+        CtcWs w = carve(const_cast<float*>(alpha_ws), T, N, ks);
+        const int C_pad = (C + 3) & ~3;
+        const size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * (static_cast<size_t>(PF) * (C_pad + ks * 32) + C_pad) * sizeof(float);
+        CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_bwd: class count %d too large for the row ring", C);
+        dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+#define LAUNCH_F(KS)                                                                                                      \
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    ctc_beta_grad_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,             \
+                                                            target_lengths, w.hist_a, w.off_a, w.nll_d, grad_nll,         \
+                                                            grad_scale, grad, T, N, C, blank)
+        switch (ks) {
+            case 1: LAUNCH_F(1); break;
+            case 2: LAUNCH_F(2); break;
+            case 4: LAUNCH_F(4); break;
+            case 8: LAUNCH_F(8); break;
+            default: LAUNCH_F(16); break;
+        }
+#undef LAUNCH_F
+        CTCB_LAUNCH_CHECK();
+        return OK;
+    }
     const long long rows = static_cast<long long>(T) * N;
     long long blocks = (rows + 7) / 8;
     const long long cap = static_cast<long long>(device_sm_count()) * 8;

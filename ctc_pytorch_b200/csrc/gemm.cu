@@ -268,18 +268,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// First use of a tile width on a device: opt in to its shared memory AND make sure the kernel is loaded. CUDA loads kernels
+// lazily, at their first launch, and that load may have to wait for everything running on the device: a GEMM whose first
+// launch is a chunk of a streamed input projection (side stream, see ctcb200_lstm_fwd_streamed) would then wait for the
+// recurrent kernel, which itself spins on that chunk — observed as a device-wait timeout in the very first step of a fresh
+// process, whenever the capped launch picked a tile width the uncapped first chunk had not used. gemm_preload() therefore
+// touches every tile width before a kernel that waits on GEMM output is launched (cudaFuncGetAttributes forces the load).
+template <int BN>
+int gemm_prepare() {
+    static bool ready[MAX_DEVICES] = {false};   // function attributes and loaded modules are per device (context)
+    const int dev = current_device();
+    if (!ready[dev]) {
+        CTCB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GemmCfg<BN>::SMEM_BYTES));
+        cudaFuncAttributes fa;
+        CTCB_CUDA(cudaFuncGetAttributes(&fa, gemm_tn_kernel<BN>));
+        ready[dev] = true;
+    }
+    return OK;
+}
+
 template <int BN>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int tma_store, int split_k,
                 void* C, long long ldc, int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
                 int max_ctas, cudaStream_t stream, int mn_major = 0) {
     using Cfg = GemmCfg<BN>;
-    static bool attr_set[MAX_DEVICES] = {false};   // function attributes are per device (context)
-    const int dev = current_device();
-    if (!attr_set[dev]) {
-        CTCB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
-        attr_set[dev] = true;
-    }
+    const int rc_attr = gemm_prepare<BN>();
+    if (rc_attr != OK) return rc_attr;
     int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * split_k;
     // max_ctas: 0 = persistent over all SMs; > 0 = cap (leave SMs to a concurrent kernel); < 0 = one tile per CTA
     // (short-lived CTAs, so a kernel launched later on another stream gets SMs quickly)
@@ -356,6 +371,13 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
     }
 }
 
+int gemm_preload() {
+    int rc = gemm_prepare<64>();
+    if (rc == OK) rc = gemm_prepare<128>();
+    if (rc == OK) rc = gemm_prepare<256>();
+    return rc;
+}
+
 int gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
                  int K, int a_koff, int b_koff, int out_bf16, int accumulate, int force_bn, int max_ctas,
                  cudaStream_t stream) {
@@ -374,6 +396,8 @@ extern "C" CTCB200_API int ctcb200_gemm_atb_bf16(const void* A, int64_t lda, con
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     return ctcb200::gemm_impl(A, lda, B, ldb, C, ldc, M, N, K, a_roff, b_roff, 0, accumulate, tile_n, max_ctas, stream, 1);
 }
+
+extern "C" CTCB200_API int ctcb200_gemm_preload(void) { return ctcb200::gemm_preload(); }
 
 extern "C" CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                     int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,

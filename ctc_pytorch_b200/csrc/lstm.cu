@@ -2196,6 +2196,11 @@ extern "C" CTCB200_API int ctcb200_lstm_fwd_streamed(const float* gx, const void
                                                      int H, int batch_tile, int cell, void* resident_counter,
                                                      const void* gx_ready, uint32_t gx_base, int chunk_T,
                                                      ctcb200_stream_t stream) {
+    // the kernel launched here waits for GEMM chunks: none of them may be a kernel's first (lazily loading) launch
+    if (gx_ready != nullptr) {
+        const int rc = gemm_preload();
+        if (rc != OK) return rc;
+    }
     return lstm_fwd_impl(gx, whh_packed, whh_lo_packed, hout, c_save, gates_save, scratch, T, N, H, batch_tile, cell,
                          resident_counter, gx_ready, gx_base, chunk_T, false, false, nullptr, stream);
 }

@@ -237,6 +237,30 @@ def _gx_ready_state(dev):
     return _GX_READY[key]
 
 
+_CONCURRENT = {}
+
+
+def _streams_overlap(dev):
+    """True when a kernel on the side stream runs while a kernel on the main stream is resident on `dev` (once per device and
+    process). The streamed input projection launches a kernel that waits for later launches of another stream: under a tool that
+    serialises kernels (Nsight Compute, CUDA_LAUNCH_BLOCKING, anything injected through CUDA_INJECTION64_PATH) it would wait for
+    its timeout trap, so those cases keep the whole-projection form. ctcb200_concurrency_probe (include/ctcb200.h) measures what
+    the environment variables cannot tell."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _CONCURRENT:
+        ok = True
+        for var in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_PORT_BASE"):
+            if os.environ.get(var):
+                ok = False
+        if os.environ.get("CUDA_LAUNCH_BLOCKING", "0") not in ("", "0"):
+            ok = False
+        if ok:
+            main_s, side_s = torch.cuda.current_stream(dev), _side_stream(dev)
+            ok = _lib.lib().dll.ctcb200_concurrency_probe(ctypes.c_void_p(main_s.cuda_stream), ctypes.c_void_p(side_s.cuda_stream), 20) == 1
+        _CONCURRENT[key] = ok
+    return _CONCURRENT[key]
+
+
 def _gx_stream_plan(model, T, N, H, x3, cell, packed, dev):
     """Streamed input projection (include/ctcb200.h, ctcb200_lstm_fwd_streamed): only the first time chunk of Gx = X W_ih^T is
     computed before the recurrent kernel starts; the other chunks are GEMM launches on the side stream, on the SMs the
@@ -261,6 +285,12 @@ def _gx_stream_plan(model, T, N, H, x3, cell, packed, dev):
     free = torch.cuda.get_device_properties(dev).multi_processor_count - ctas
     if ctas <= 0 or free < 16:
         return None   # not one all-resident clustered launch, or no SMs left for the GEMMs
+    if not _streams_overlap(dev):
+        return None   # kernels of two streams do not overlap here (profiler, blocking launches): the kernel would wait forever
+    # The recurrent kernel will WAIT for the chunk GEMMs: none of them may be a kernel's first launch on this device (CUDA's
+    # lazy loading of a kernel can wait for the running recurrent kernel — a deadlock in the first step of a fresh process).
+    # ctcb200_lstm_fwd_streamed does this as well; doing it here keeps the load out of the launch sequence.
+    _call("ctcb200_gemm_preload")
     return chunks, chunk_T, free, "stream"
 
 

@@ -42,11 +42,17 @@ CTCB200_API int ctcb200_version(void);
 /* ---- CTC loss: replaces nn.CTCLoss(reduction='sum') fwd/bwd, timit/steps/train_ctc.py:144,47,63 ------
  * log_probs [T,N,C] f32; targets [N,*] int64 zero-padded rows of pitch target_stride
  * (timit/utils/data_loader.py:125,140); input_lengths / target_lengths [N] int64.
- * alpha_ws: caller-provided, 8-byte aligned workspace of ctcb200_ctc_workspace_floats(T,N,max_target_len) floats (alpha and
+ * alpha_ws: caller-provided, 16-byte aligned workspace of ctcb200_ctc_workspace_floats(T,N,max_target_len) floats (alpha and
  * beta histories + their log-scale offsets; fwd runs both sweeps concurrently, bwd is the parallel gradient kernel), kept
  * between fwd and bwd. nll [N] f32 = per-utterance negative log likelihood (+inf if infeasible).
  * bwd writes grad [T,N,C] f32 = grad_scale * grad_nll[n] * (exp(lp) - exp(lcab + nll - lp)), zero for
- * t >= input_length (torch's native convention); grad_nll may be NULL (= all ones). */
+ * t >= input_length (torch's native convention); grad_nll may be NULL (= all ones).
+ * Two forms, chosen by the batch size alone (so fwd and bwd of one call pair always agree): below the threshold the latency form
+ * above; from N >= threshold the throughput form — fwd runs only the alpha sweeps, bwd runs the beta sweep and emits each frame's
+ * gradient row as it goes (no beta history, no separate gradient pass). ctcb200_ctc_set_fused_min_batch sets the threshold
+ * (default 2048 — where the two forms cross on a B200 at T = 800 —, or CTCB200_CTC_FUSED_MIN_N at load time; 0 = always, negative = query only) and returns the previous value; it
+ * must not change between a fwd and its bwd. */
+CTCB200_API int ctcb200_ctc_set_fused_min_batch(int min_batch);
 CTCB200_API int64_t ctcb200_ctc_workspace_floats(int T, int N, int max_target_len);
 CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const int64_t* targets, int64_t target_stride,
                                      const int64_t* input_lengths, const int64_t* target_lengths, int T, int N,
@@ -90,7 +96,12 @@ CTCB200_API int ctcb200_pad_labels(const int64_t* labels, const int64_t* offsets
  * a_koff/b_koff (multiples of 8) shift the K window of each operand (the h_{t-1} shift of dW_hh).
  * tile_n: 0 = auto, else 64/128/256. max_ctas: 0 = persistent over all SMs, > 0 = cap on the CTA count, < 0 = one
  * tile per CTA (for weight-gradient GEMMs that run on a side stream beside the recurrent kernels). Carries the
- * contractions behind nn.LSTM / nn.Linear at timit/models/model_ctc.py:23-26,33,136-139. */
+ * contractions behind nn.LSTM / nn.Linear at timit/models/model_ctc.py:23-26,33,136-139.
+ * ctcb200_gemm_preload: loads every tile width of the GEMM kernel on the current device. CUDA loads kernels lazily at their
+ * first launch and that load can wait for whatever is running; a GEMM launched for the first time while a kernel that WAITS FOR
+ * ITS OUTPUT is resident (the streamed input projection of ctcb200_lstm_fwd_streamed) would never start. The streamed entry
+ * point calls it itself; callers that build their own producer/consumer overlap on top of the GEMM should too. */
+CTCB200_API int ctcb200_gemm_preload(void);
 CTCB200_API int ctcb200_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                      int M, int N, int K, int a_koff, int b_koff, int out_bf16, int accumulate,
                                      int tile_n, int max_ctas, ctcb200_stream_t stream);
@@ -163,7 +174,14 @@ CTCB200_API int ctcb200_stream_wait_geq(ctcb200_stream_t stream, const void* cou
  * (a driver stream memory operation: *gx_ready = value once the preceding work of that stream has completed). The kernel
  * waits for gx_ready - gx_base >= c (wrap-around compare) before it first touches chunk c.
  * ctcb200_lstm_fwd_ctas: SMs the forward launch occupies when it is a single launch with every cluster resident at once
- * (the only form that can be streamed), else 0 — ask before using ctcb200_lstm_fwd_streamed. */
+ * (the only form that can be streamed), else 0 — ask before using ctcb200_lstm_fwd_streamed.
+ * ctcb200_concurrency_probe: the streamed form is only legal where a kernel on one stream makes progress while a kernel on
+ * another stream is resident. Profilers (Nsight Compute serialises all kernels), CUDA_LAUNCH_BLOCKING and some debug / MPS
+ * set-ups do not provide that — the recurrent kernel would wait for chunks that cannot be produced until its timeout trap. The
+ * probe runs the pattern in miniature (a one-thread kernel on stream_a polls a flag for at most limit_ms; a trivial kernel and a
+ * stream memory operation on stream_b raise it) and returns 1 / 0 (negative: error); it synchronises both streams — call it
+ * once per device before choosing the streamed form, and keep the whole-projection form (ctcb200_lstm_fwd) otherwise. */
+CTCB200_API int ctcb200_concurrency_probe(ctcb200_stream_t stream_a, ctcb200_stream_t stream_b, int limit_ms);
 CTCB200_API int ctcb200_lstm_fwd_streamed(const float* gx, const void* whh_packed, const void* whh_lo_packed, float* hout,
                                           float* c_save, void* gates_save, void* scratch, int T, int N, int H, int batch_tile,
                                           int cell, void* resident_counter, const void* gx_ready, uint32_t gx_base,

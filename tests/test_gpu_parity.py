@@ -48,7 +48,18 @@ def relnorm(a, b):
 
 
 # ------------------------------------------------------------------------------------------------ CTC
-def test_ctc_golden(golden_dir):
+@pytest.fixture(params=["latency", "throughput"])
+def ctc_form(request):
+    """Both forms of the CTC kernels (include/ctcb200.h, ctcb200_ctc_set_fused_min_batch): concurrent alpha / beta sweeps +
+    gradient kernel (small batches), and alpha sweep + fused beta-and-gradient kernel (N >= threshold)."""
+    from ctc_pytorch_b200 import _lib
+    dll = _lib.lib().dll
+    prev = dll.ctcb200_ctc_set_fused_min_batch(1 << 30 if request.param == "latency" else 0)
+    yield request.param
+    dll.ctcb200_ctc_set_fused_min_batch(prev)
+
+
+def test_ctc_golden(golden_dir, ctc_form):
     from ctc_pytorch_b200.loss import ctc_loss
     g = np.load(os.path.join(golden_dir, "ctc_small.npz"))
     lp = torch.from_numpy(g["log_probs"]).to(DEV).requires_grad_(True)
@@ -68,7 +79,7 @@ def test_ctc_golden(golden_dir):
 
 
 @pytest.mark.parametrize("T,N,C,S,seed", [(60, 5, 12, 9, 0), (33, 3, 40, 16, 1), (20, 4, 6, 70, 2), (800, 32, 62, 60, 3)])
-def test_ctc_vs_oracle(T, N, C, S, seed):
+def test_ctc_vs_oracle(T, N, C, S, seed, ctc_form):
     from ctc_pytorch_b200.loss import ctc_loss
     g = torch.Generator().manual_seed(seed)
     lp = torch.log_softmax(torch.randn(T, N, C, generator=g) * 2, -1)
@@ -106,6 +117,45 @@ def test_ctc_reductions_and_1d_targets():
         got = CTCLoss(reduction=red)(lp.to(DEV), tg.to(DEV), il.to(DEV), tl.to(DEV)).cpu()
         got1d = CTCLoss(reduction=red)(lp.to(DEV), flat.to(DEV), il, tl).cpu()
         assert torch.allclose(got, want, rtol=1e-4) and torch.allclose(got1d, want, rtol=1e-4)
+
+
+def test_ctc_forms_agree_at_large_batch():
+    """A batch at the threshold takes the throughput form (alpha sweep, then fused beta + gradient); the same batch through
+    the latency form must give the same nll bits (same alpha sweep) and the same gradient up to the summation order of the
+    per-class occupancies — including an empty utterance, an empty target, an infeasible target and weighted grad_nll."""
+    from ctc_pytorch_b200 import _lib
+    from ctc_pytorch_b200.loss import ctc_loss
+    dll = _lib.lib().dll
+    T, N, C, S = 96, 1100, 30, 20
+    g = torch.Generator().manual_seed(11)
+    lp = torch.log_softmax(torch.randn(T, N, C, generator=g) * 2, -1).to(DEV)
+    tl = torch.randint(0, S + 1, (N,), generator=g)
+    tg = torch.randint(1, C, (N, S), generator=g)
+    il = torch.randint(T // 2, T + 1, (N,), generator=g)
+    il[0], tl[0] = 0, 0          # nothing to align
+    il[1], tl[1] = 0, 3          # no frames for three labels: +inf
+    il[2], tl[2] = 5, 20         # infeasible
+    tl[3] = 0                    # all-blank target
+    wts = torch.rand(N, generator=g).to(DEV)
+    res = {}
+    for form, thr in (("throughput", N), ("latency", N + 1)):   # the threshold itself: N >= thr takes the throughput form
+        prev = dll.ctcb200_ctc_set_fused_min_batch(thr)
+        try:
+            x = lp.clone().requires_grad_(True)
+            nll = ctc_loss(x, tg.to(DEV), il.to(DEV), tl.to(DEV), reduction="none")
+            fin = torch.isfinite(nll)
+            (nll[fin] * wts[fin]).sum().backward()
+            res[form] = (nll.detach().cpu(), x.grad.cpu(), fin.cpu())
+        finally:
+            dll.ctcb200_ctc_set_fused_min_batch(prev)
+    (na, ga, fa), (nb, gb, fb) = res["throughput"], res["latency"]
+    assert torch.equal(fa, fb) and torch.equal(na[fa], nb[fb]) and torch.isinf(na[1]) and torch.isinf(na[2]) and na[0] == 0
+    m = fa.view(1, N, 1).expand_as(ga)
+    err = (ga[m] - gb[m]).abs().max().item()
+    _report("ctc_forms_agree", dict(N=N, T=T, max_abs_grad_diff=err))
+    assert err < 2e-6
+    for n in range(N):
+        assert ga[int(il[n]):, n].abs().sum().item() == 0.0
 
 
 # --------------------------------------------------------------------------------------------- greedy
