@@ -268,6 +268,9 @@ class Job(object):
         return loss
 
 
+PER_STEP = None   # list of per-step event times of every timed loop when --per-step is given
+
+
 def timed_loop(job, steps, flush, world, e2e):
     import torch.distributed as dist
 
@@ -276,6 +279,7 @@ def timed_loop(job, steps, flush, world, e2e):
             dist.barrier()
         torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)] if PER_STEP is not None else None
     barrier()
     e0.record()
     for k in range(steps):
@@ -286,8 +290,12 @@ def timed_loop(job, steps, flush, world, e2e):
         else:
             flush.zero_()  # L2 flush between steps (counted inside the timed region: ~0.03 ms)
             job.step(job.devb[k % len(job.devb)])
+        if marks is not None:
+            marks[k].record()
     e1.record()
     barrier()
+    if marks is not None:   # diagnostic (--per-step): where inside the timed region the time went
+        PER_STEP.append({"e2e": bool(e2e), "ms": [round((e0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]), 3) for k in range(steps)]})
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=job.dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -474,6 +482,8 @@ def run_ours(args, name, cfg, rank, world):
         line["other_precision"] = other_precision
     if strong_line is not None:
         line["strong_cfg4"] = strong_line
+    if PER_STEP is not None:
+        line["per_step_ms"] = PER_STEP
     emit(line)
 
 
@@ -514,7 +524,12 @@ def main():
     ap.add_argument("--strong-cfg4", dest="strong_cfg4", type=int, default=1,
                     help="also measure cfg4 sharded N/G per rank (strong_cfg4 object)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-step", dest="per_step", action="store_true",
+                    help="diagnostic: also record the device time of every step of the timed loops (key per_step_ms)")
     args = ap.parse_args()
+    if args.per_step:
+        global PER_STEP
+        PER_STEP = []
     name = args.config or ("cfg4" if args.scaling == "strong" else "cfg2")
     cfg = CFG[name]
     wd = int(os.environ.get("BENCH_WATCHDOG", "0"))
