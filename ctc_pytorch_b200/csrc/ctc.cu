@@ -11,7 +11,7 @@
 // (t = T-1..0) of an utterance run CONCURRENTLY in two warps of one launch; each stores its (renormalised) history.
 // Inside a warp the 2S+1 lattice states are blocked over the 32 lanes (KS consecutive states per lane) so the
 // s-1 / s-2 neighbours are lane-local except at block edges, where one or two warp shuffles fetch them; each
-// (t, n) row of log-probs is brought in with coalesced cp.async into a per-warp double buffer one step ahead.
+// (t, n) row of log-probs is brought in with coalesced cp.async into a per-warp ring of 8 rows, 7 frames ahead.
 // The gradient is then a fully parallel kernel (one warp per (t, n) row): posteriors exp(alpha+beta+nll-lp) are
 // accumulated per class in shared memory, grad = exp(lp) - occupancy.
 // Numerics: every RENORM frames a sweep subtracts its row maximum and accumulates the removed log-scale in double;
@@ -75,13 +75,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int PENDING>
 __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
-// one commit group per call, empty when `pred` is false, so the group count stays in step with the frame count
-__device__ __forceinline__ void prefetch_row(float* dst, const float* src, int C, int lane, bool pred) {
-    if (pred)
-        for (int c = lane; c < C; c += 32) cp_async_4(dst + c, src + c);
-    cp_async_commit();
-}
-
 // Per-lane static description of the states this lane owns.
 template <int KS>
 struct LaneStates {
@@ -114,19 +107,26 @@ __device__ __forceinline__ void load_states(LaneStates<KS>& st, const int64_t* t
 // workspace per utterance: hist_a / hist_b [T][KS*32] floats (slot j*32+lane), off_a / off_b [T] doubles (log-scale
 // removed from the stored row), nll_d (double)
 // ---------------------------------------------------------------------------------------------
-template <int KS, bool ALPHA_ONLY>
+// The step loop is the whole cost at small N (one warp per scheduler: every instruction's latency is exposed, ncu: 177
+// instructions and ~710 cycles per frame in the first version), so it is written for instruction count: frames are processed in
+// aligned blocks of PF = RENORM = 8 with the body unrolled — ring slots, history offsets and the renormalisation point are then
+// compile-time, pointers run instead of being recomputed, and the row stride of the ring is a template constant (RS floats; 0 =
+// run-time C for C > 64); the frames before / after the aligned blocks take a generic loop with the same step code.
+template <int KS, bool ALPHA_ONLY, int RS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
                  const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len, float* __restrict__ hist_a,
                  float* __restrict__ hist_b, double* __restrict__ off_a, double* __restrict__ off_b,
                  double* __restrict__ nll_d, float* __restrict__ nll, int T, int N, int C, int blank) {
+    static_assert(PF == 8 && RENORM == 8, "the unrolled blocks assume ring depth = renormalisation period = 8");
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // ALPHA_ONLY (throughput form, see ctc_beta_grad_kernel): every warp is the alpha sweep of its own utterance
     const int n = ALPHA_ONLY ? blockIdx.x * WARPS_PER_BLOCK + warp : blockIdx.x * (WARPS_PER_BLOCK / 2) + (warp >> 1);
     const bool is_beta = ALPHA_ONLY ? false : (warp & 1);
     if (n >= N) return;
-    float* rowbuf = smem + warp * PF * C;  // ring of PF rows
+    const int RSTR = RS ? RS : C;            // ring row stride in floats
+    float* rowbuf = smem + warp * PF * RSTR;  // ring of PF rows, row t in slot t & 7
 
     const int S = static_cast<int>(tgt_len[n]);
     const int L = 2 * S + 1;
@@ -143,62 +143,99 @@ ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
     load_states<KS>(st, targets + n * tgt_stride, S, blank, lane);
     const long long row_stride = static_cast<long long>(N) * C;
     const float* lp_n = lp + static_cast<size_t>(n) * C;
-    float* hist = (is_beta ? hist_b : hist_a) + static_cast<size_t>(n) * T * (KS * 32);
+    float* hist = (is_beta ? hist_b : hist_a) + static_cast<size_t>(n) * T * (KS * 32) + lane;   // + t*KS*32 + j*32
     double* offs = (is_beta ? off_b : off_a) + static_cast<size_t>(n) * T;
     double scale_acc = 0.0;  // log-scale removed so far (double: the stored rows stay O(100) however long the utterance)
     float a[KS];
 
+    // one row of log-probs into a ring slot; exactly one commit group per call (empty when !pred) so that the group count
+    // stays in step with the frame count
+    const bool c0 = lane < C, c1 = lane + 32 < C;
+    auto fetch_row = [&](float* dst, const float* src, bool pred) {
+        if (pred) {
+            if (c0) cp_async_4(dst + lane, src + lane);
+            if (c1) cp_async_4(dst + lane + 32, src + lane + 32);
+            if (RS == 0)
+                for (int c = lane + 64; c < C; c += 32) cp_async_4(dst + c, src + c);
+        }
+        cp_async_commit();
+    };
+    auto renorm = [&]() {
+        float m = NEG_INF;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m > NEG_INF) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) a[j] -= m;
+            scale_acc += static_cast<double>(m);
+        }
+    };
+    auto store_row = [&](float* h, double* o) {
+        if (lane == 0) *o = scale_acc;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) h[j * 32] = a[j];
+    };
+
     if (!is_beta) {
+        auto alpha_init = [&](const float* cur) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) a[j] = (st.valid[j] && lane * KS + j < 2) ? cur[st.label[j]] : NEG_INF;
+        };
+        auto alpha_step = [&](const float* cur) {
+            float up1 = __shfl_up_sync(0xffffffffu, a[KS - 1], 1);
+            float up2 = (KS >= 2) ? __shfl_up_sync(0xffffffffu, a[KS >= 2 ? KS - 2 : 0], 1)
+                                  : __shfl_up_sync(0xffffffffu, a[0], 2);
+            if (lane == 0) { up1 = NEG_INF; up2 = NEG_INF; }
+            if (KS == 1 && lane == 1) up2 = NEG_INF;
+            float nw[KS];
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                float p1 = (j >= 1) ? a[j >= 1 ? j - 1 : 0] : up1;
+                float p2 = (j >= 2) ? a[j >= 2 ? j - 2 : 0] : ((j == 1) ? up1 : up2);
+                if (KS >= 2 && j == 0) p2 = up2;
+                if (!st.skip_in[j]) p2 = NEG_INF;
+                // even states are blanks (no skip transition): known at compile time when KS is even
+                float v = (KS % 2 == 0 && (j & 1) == 0) ? lse2_fast(a[j], p1) : lse3(a[j], p1, p2);
+                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+            }
+#pragma unroll
+            for (int j = 0; j < KS; ++j) a[j] = nw[j];
+        };
         // rows 0 .. PF-2 in flight before the first frame; frame t tops the ring up with row t + PF - 1, whose slot held
         // row t - 1 (all lanes are done with it after the __syncwarp)
 #pragma unroll
-        for (int i = 0; i < PF - 1; ++i) prefetch_row(rowbuf + i * C, lp_n + i * row_stride, C, lane, i < Tn);
-        for (int t = 0; t < Tn; ++t) {
-            float* cur = rowbuf + (t % PF) * C;
+        for (int i = 0; i < PF - 1; ++i) fetch_row(rowbuf + i * RSTR, lp_n + i * row_stride, i < Tn);
+        const float* next = lp_n + (PF - 1) * row_stride;   // row t + PF - 1 of the frame about to run
+        const int full = Tn & ~(PF - 1);                    // frames in aligned blocks of 8
+        for (int tb = 0; tb < full; tb += PF) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                cp_async_wait_pending<PF - 2>();
+                __syncwarp();
+                fetch_row(rowbuf + ((i + PF - 1) % PF) * RSTR, next, tb + i + PF - 1 < Tn);
+                next += row_stride;
+                const float* cur = rowbuf + i * RSTR;
+                if (i == 0 && tb == 0) alpha_init(cur);
+                else alpha_step(cur);
+                if (i == PF - 1) renorm();
+                store_row(hist + i * (KS * 32), offs + i);
+            }
+            hist += PF * (KS * 32);
+            offs += PF;
+        }
+        for (int t = full; t < Tn; ++t) {   // the last Tn % 8 frames
             cp_async_wait_pending<PF - 2>();
             __syncwarp();
-            prefetch_row(rowbuf + ((t + PF - 1) % PF) * C, lp_n + (t + PF - 1) * row_stride, C, lane, t + PF - 1 < Tn);
-            if (t == 0) {
-#pragma unroll
-                for (int j = 0; j < KS; ++j) {
-                    int s = lane * KS + j;
-                    a[j] = (st.valid[j] && s < 2) ? cur[st.label[j]] : NEG_INF;
-                }
-            } else {
-                float up1 = __shfl_up_sync(0xffffffffu, a[KS - 1], 1);
-                float up2 = (KS >= 2) ? __shfl_up_sync(0xffffffffu, a[KS >= 2 ? KS - 2 : 0], 1)
-                                      : __shfl_up_sync(0xffffffffu, a[0], 2);
-                if (lane == 0) { up1 = NEG_INF; up2 = NEG_INF; }
-                if (KS == 1 && lane == 1) up2 = NEG_INF;
-                float nw[KS];
-#pragma unroll
-                for (int j = 0; j < KS; ++j) {
-                    float p1 = (j >= 1) ? a[j >= 1 ? j - 1 : 0] : up1;
-                    float p2 = (j >= 2) ? a[j >= 2 ? j - 2 : 0] : ((j == 1) ? up1 : up2);
-                    if (KS >= 2 && j == 0) p2 = up2;
-                    if (!st.skip_in[j]) p2 = NEG_INF;
-                    // even states are blanks (no skip transition): known at compile time when KS is even
-                    float v = (KS % 2 == 0 && (j & 1) == 0) ? lse2_fast(a[j], p1) : lse3(a[j], p1, p2);
-                    nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
-                }
-#pragma unroll
-                for (int j = 0; j < KS; ++j) a[j] = nw[j];
-            }
-            if ((t % RENORM) == RENORM - 1 || t == Tn - 1) {
-                float m = NEG_INF;
-#pragma unroll
-                for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                if (m > NEG_INF) {
-#pragma unroll
-                    for (int j = 0; j < KS; ++j) a[j] -= m;
-                    scale_acc += static_cast<double>(m);
-                }
-            }
-            if (lane == 0) offs[t] = scale_acc;
-#pragma unroll
-            for (int j = 0; j < KS; ++j) hist[static_cast<size_t>(t) * (KS * 32) + j * 32 + lane] = a[j];
+            fetch_row(rowbuf + ((t + PF - 1) % PF) * RSTR, next, false);   // (nothing left to fetch: t + 7 >= Tn here)
+            const float* cur = rowbuf + (t % PF) * RSTR;
+            if (t == 0) alpha_init(cur);
+            else alpha_step(cur);
+            if (t == Tn - 1) renorm();
+            store_row(hist, offs);
+            hist += KS * 32;
+            offs += 1;
         }
         // nll = -lse(alpha_{Tn-1}(L-1), alpha_{Tn-1}(L-2))
         float loc = NEG_INF;
@@ -215,59 +252,73 @@ ctc_sweep_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targe
             nll_d[n] = v;
         }
     } else {
+        auto beta_init = [&](const float* cur) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                const int s = lane * KS + j;
+                a[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
+            }
+        };
+        auto beta_step = [&](const float* cur) {
+            float dn1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+            float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
+                                  : __shfl_down_sync(0xffffffffu, a[0], 2);
+            if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
+            if (KS == 1 && lane == 30) dn2 = NEG_INF;
+            float nw[KS];
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                float n1 = (j + 1 < KS) ? a[j + 1 < KS ? j + 1 : 0] : dn1;
+                float n2 = (j + 2 < KS) ? a[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
+                if (KS >= 2 && j == KS - 1) n2 = dn2;
+                if (!st.skip_out[j]) n2 = NEG_INF;
+                float v = (KS % 2 == 0 && (j & 1) == 0) ? lse2_fast(a[j], n1) : lse3(a[j], n1, n2);
+                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+            }
+#pragma unroll
+            for (int j = 0; j < KS; ++j) a[j] = nw[j];
+        };
+        // rows Tn-1 .. Tn-PF+1 in flight before the first frame; frame t tops the ring up with row t - (PF - 1)
 #pragma unroll
         for (int i = 0; i < PF - 1; ++i) {
             const int r = Tn - 1 - i;
-            prefetch_row(rowbuf + ((r % PF + PF) % PF) * C, lp_n + static_cast<long long>(r) * row_stride, C, lane, r >= 0);
+            fetch_row(rowbuf + (r & (PF - 1)) * RSTR, lp_n + static_cast<long long>(r) * row_stride, r >= 0);
         }
-        for (int t = Tn - 1; t >= 0; --t) {
-            float* cur = rowbuf + (t % PF) * C;
+        const float* next = lp_n + static_cast<long long>(Tn - PF) * row_stride;   // row t - (PF - 1) of the frame about to run
+        const int full = Tn & ~(PF - 1);
+        hist += static_cast<size_t>(Tn - 1) * (KS * 32);
+        offs += Tn - 1;
+        for (int t = Tn - 1; t >= full; --t) {   // the top Tn % 8 frames
             cp_async_wait_pending<PF - 2>();
             __syncwarp();
-            {
-                const int r = t - (PF - 1);
-                prefetch_row(rowbuf + ((r % PF + PF) % PF) * C, lp_n + static_cast<long long>(r) * row_stride, C, lane, r >= 0);
+            fetch_row(rowbuf + ((t + 1) & (PF - 1)) * RSTR, next, t - (PF - 1) >= 0);
+            next -= row_stride;
+            const float* cur = rowbuf + (t & (PF - 1)) * RSTR;
+            if (t == Tn - 1) beta_init(cur);
+            else beta_step(cur);
+            if ((t & (PF - 1)) == 0) renorm();   // (t == full: the lowest frame of the partial top block)
+            store_row(hist, offs);
+            hist -= KS * 32;
+            offs -= 1;
+        }
+        // hist / offs now point at frame full - 1 = the top frame of the aligned blocks
+        for (int tb = full - PF; tb >= 0; tb -= PF) {
+            hist -= (PF - 1) * (KS * 32);   // -> frame tb
+            offs -= PF - 1;
+#pragma unroll
+            for (int i = PF - 1; i >= 0; --i) {
+                cp_async_wait_pending<PF - 2>();
+                __syncwarp();
+                fetch_row(rowbuf + ((i + 1) % PF) * RSTR, next, tb + i - (PF - 1) >= 0);
+                next -= row_stride;
+                const float* cur = rowbuf + i * RSTR;
+                if (i == PF - 1 && tb + PF == Tn) beta_init(cur);
+                else beta_step(cur);
+                if (i == 0) renorm();
+                store_row(hist + i * (KS * 32), offs + i);
             }
-            if (t == Tn - 1) {
-#pragma unroll
-                for (int j = 0; j < KS; ++j) {
-                    int s = lane * KS + j;
-                    a[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
-                }
-            } else {
-                float dn1 = __shfl_down_sync(0xffffffffu, a[0], 1);
-                float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
-                                      : __shfl_down_sync(0xffffffffu, a[0], 2);
-                if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
-                if (KS == 1 && lane == 30) dn2 = NEG_INF;
-                float nw[KS];
-#pragma unroll
-                for (int j = 0; j < KS; ++j) {
-                    float n1 = (j + 1 < KS) ? a[j + 1 < KS ? j + 1 : 0] : dn1;
-                    float n2 = (j + 2 < KS) ? a[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
-                    if (KS >= 2 && j == KS - 1) n2 = dn2;
-                    if (!st.skip_out[j]) n2 = NEG_INF;
-                    float v = (KS % 2 == 0 && (j & 1) == 0) ? lse2_fast(a[j], n1) : lse3(a[j], n1, n2);
-                    nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
-                }
-#pragma unroll
-                for (int j = 0; j < KS; ++j) a[j] = nw[j];
-            }
-            if ((t % RENORM) == 0) {
-                float m = NEG_INF;
-#pragma unroll
-                for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                if (m > NEG_INF) {
-#pragma unroll
-                    for (int j = 0; j < KS; ++j) a[j] -= m;
-                    scale_acc += static_cast<double>(m);
-                }
-            }
-            if (lane == 0) offs[t] = scale_acc;
-#pragma unroll
-            for (int j = 0; j < KS; ++j) hist[static_cast<size_t>(t) * (KS * 32) + j * 32 + lane] = a[j];
+            hist -= KS * 32;                // -> frame tb - 1
+            offs -= 1;
         }
     }
 }
@@ -329,7 +380,7 @@ ctc_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ target
 
 
 // ---------------------------------------------------------------------------------------------
-// Throughput form for large batches (N >= ctc_fused_min_batch): the alpha sweep alone (ctc_sweep_kernel<KS, true>, one warp
+// Throughput form for large batches (N >= ctc_fused_min_batch): the alpha sweep alone (ctc_sweep_kernel<KS, true, RS>, one warp
 // per utterance, history kept), then ONE kernel that runs the beta sweep and emits the gradient row of frame t the moment
 // beta_t is known — no beta history, no separate gradient pass. HBM traffic per (t, n) row: log-probs twice (2 x 4C bytes),
 // the alpha row once each way (2 x 128 KS bytes), the gradient once (4C bytes); the latency form above moves two histories
@@ -343,7 +394,7 @@ __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
-template <int KS>
+template <int KS, int RS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets, int64_t tgt_stride,
                      const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
@@ -354,7 +405,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (n >= N) return;
-    const int C_pad = (C + 3) & ~3;
+    const int C_pad = RS ? RS : ((C + 3) & ~3);   // log-prob part of a ring slot (compile-time 64 floats for C <= 64)
     const int ROW = C_pad + KS * 32;
     float* ring = smem_bg + warp * (PF * ROW + C_pad);
     float* occ = ring + PF * ROW;
@@ -377,69 +428,65 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
     const double nllv = nll_d[n];
     const float gscale = grad_scale * (grad_nll ? grad_nll[n] : 1.0f);
     for (int c = lane; c < C; c += 32) occ[c] = 0.0f;
+    const bool c0 = lane < C, c1 = lane + 32 < C;
 
-    auto prefetch = [&](int r) {   // one commit group per call (empty for r < 0): the group count follows the frame count
-        if (r >= 0) {
-            float* dst = ring + (r % PF) * ROW;
-            const float* src = lp_n + static_cast<long long>(r) * row_stride;
-            for (int c = lane; c < C; c += 32) cp_async_4(dst + c, src + c);
-            const float* hsrc = hist + static_cast<size_t>(r) * (KS * 32);
-            for (int i = lane; i < KS * 8; i += 32) cp_async_16(dst + C_pad + i * 4, hsrc + i * 4);
+    // log-prob row and alpha row of one frame into a ring slot; one commit group per call (empty when !pred)
+    auto fetch_row = [&](float* dst, const float* src, const float* hsrc, bool pred) {
+        if (pred) {
+            if (c0) cp_async_4(dst + lane, src + lane);
+            if (c1) cp_async_4(dst + lane + 32, src + lane + 32);
+            if (RS == 0)
+                for (int c = lane + 64; c < C; c += 32) cp_async_4(dst + c, src + c);
+#pragma unroll
+            for (int i = 0; i < (KS * 8 + 31) / 32; ++i)
+                if (KS * 8 >= 32 || lane < KS * 8) cp_async_16(dst + C_pad + (i * 32 + lane) * 4, hsrc + (i * 32 + lane) * 4);
         }
         cp_async_commit();
     };
-#pragma unroll
-    for (int i = 0; i < PF - 1; ++i) prefetch(Tn - 1 - i);
 
     double scale_acc = 0.0;
-    double offa_next = offs[Tn - 1];
     float a[KS];
-    for (int t = Tn - 1; t >= 0; --t) {
-        const float* cur = ring + (t % PF) * ROW;
+    auto beta_init = [&](const float* cur) {
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            const int s = lane * KS + j;
+            a[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
+        }
+    };
+    auto beta_step = [&](const float* cur) {
+        float dn1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+        float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
+                              : __shfl_down_sync(0xffffffffu, a[0], 2);
+        if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
+        if (KS == 1 && lane == 30) dn2 = NEG_INF;
+        float nw[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            float n1 = (j + 1 < KS) ? a[j + 1 < KS ? j + 1 : 0] : dn1;
+            float n2 = (j + 2 < KS) ? a[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
+            if (KS >= 2 && j == KS - 1) n2 = dn2;
+            if (!st.skip_out[j]) n2 = NEG_INF;
+            float v = (KS % 2 == 0 && (j & 1) == 0) ? lse2_fast(a[j], n1) : lse3(a[j], n1, n2);
+            nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
+        }
+#pragma unroll
+        for (int j = 0; j < KS; ++j) a[j] = nw[j];
+    };
+    auto renorm = [&]() {
+        float m = NEG_INF;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m > NEG_INF) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) a[j] -= m;
+            scale_acc += static_cast<double>(m);
+        }
+    };
+    // state posteriors of a frame summed per class, then its gradient row
+    auto emit = [&](const float* cur, double offa, float* g_row) {
         const float* al = cur + C_pad;
-        cp_async_wait_pending<PF - 2>();
-        __syncwarp();   // row t has landed for every lane; every lane is done with row t + 1 and with its occupancy sums
-        prefetch(t - (PF - 1));
-        const double offa = offa_next;
-        if (t > 0) offa_next = offs[t - 1];
-        if (t == Tn - 1) {
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                int s = lane * KS + j;
-                a[j] = (st.valid[j] && (s == L - 1 || s == L - 2)) ? cur[st.label[j]] : NEG_INF;
-            }
-        } else {
-            float dn1 = __shfl_down_sync(0xffffffffu, a[0], 1);
-            float dn2 = (KS >= 2) ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
-                                  : __shfl_down_sync(0xffffffffu, a[0], 2);
-            if (lane == 31) { dn1 = NEG_INF; dn2 = NEG_INF; }
-            if (KS == 1 && lane == 30) dn2 = NEG_INF;
-            float nw[KS];
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                float n1 = (j + 1 < KS) ? a[j + 1 < KS ? j + 1 : 0] : dn1;
-                float n2 = (j + 2 < KS) ? a[j + 2 < KS ? j + 2 : 0] : ((j + 1 < KS) ? dn1 : dn2);
-                if (KS >= 2 && j == KS - 1) n2 = dn2;
-                if (!st.skip_out[j]) n2 = NEG_INF;
-                float v = (KS % 2 == 0 && (j & 1) == 0) ? lse2_fast(a[j], n1) : lse3(a[j], n1, n2);
-                nw[j] = st.valid[j] ? (v + cur[st.label[j]]) : NEG_INF;
-            }
-#pragma unroll
-            for (int j = 0; j < KS; ++j) a[j] = nw[j];
-        }
-        if ((t % RENORM) == 0) {
-            float m = NEG_INF;
-#pragma unroll
-            for (int j = 0; j < KS; ++j) m = fmaxf(m, a[j]);
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (m > NEG_INF) {
-#pragma unroll
-                for (int j = 0; j < KS; ++j) a[j] -= m;
-                scale_acc += static_cast<double>(m);
-            }
-        }
-        // state posteriors of frame t, summed per class
         const float shift = static_cast<float>(offa + scale_acc + nllv);
         float blank_sum = 0.0f;
 #pragma unroll
@@ -454,10 +501,60 @@ ctc_beta_grad_kernel(const float* __restrict__ lp, const int64_t* __restrict__ t
         for (int o = 16; o >= 1; o >>= 1) blank_sum += __shfl_xor_sync(0xffffffffu, blank_sum, o);
         if (lane == 0) atomicAdd(&occ[blank], blank_sum);
         __syncwarp();
-        float* g_row = g_n + t * row_stride;
-        for (int c = lane; c < C; c += 32) {
-            g_row[c] = (expf(cur[c]) - occ[c]) * gscale;
-            occ[c] = 0.0f;
+        if (c0) { g_row[lane] = (expf(cur[lane]) - occ[lane]) * gscale; occ[lane] = 0.0f; }
+        if (c1) { g_row[lane + 32] = (expf(cur[lane + 32]) - occ[lane + 32]) * gscale; occ[lane + 32] = 0.0f; }
+        if (RS == 0)
+            for (int c = lane + 64; c < C; c += 32) {
+                g_row[c] = (expf(cur[c]) - occ[c]) * gscale;
+                occ[c] = 0.0f;
+            }
+    };
+
+    // rows Tn-1 .. Tn-PF+1 in flight before the first frame; frame t tops the ring up with row t - (PF - 1) (slot (t + 1) & 7,
+    // whose row t + 1 every lane is done with after the __syncwarp)
+#pragma unroll
+    for (int i = 0; i < PF - 1; ++i) {
+        const int r = Tn - 1 - i;
+        fetch_row(ring + (r & (PF - 1)) * ROW, lp_n + static_cast<long long>(r) * row_stride,
+                  hist + static_cast<long long>(r) * (KS * 32), r >= 0);
+    }
+    const float* next = lp_n + static_cast<long long>(Tn - PF) * row_stride;      // row t - (PF - 1) of the frame about to run
+    const float* hnext = hist + static_cast<long long>(Tn - PF) * (KS * 32);
+    float* g_row = g_n + static_cast<long long>(Tn - 1) * row_stride;
+    const double* op = offs + (Tn - 1);
+    double offa_next = *op;
+    const int full = Tn & ~(PF - 1);
+    for (int t = Tn - 1; t >= full; --t) {   // the top Tn % 8 frames
+        cp_async_wait_pending<PF - 2>();
+        __syncwarp();   // row t has landed for every lane; every lane is done with row t + 1 and with its occupancy sums
+        fetch_row(ring + ((t + 1) & (PF - 1)) * ROW, next, hnext, t - (PF - 1) >= 0);
+        next -= row_stride;
+        hnext -= KS * 32;
+        const double offa = offa_next;
+        if (t > 0) offa_next = *--op;
+        const float* cur = ring + (t & (PF - 1)) * ROW;
+        if (t == Tn - 1) beta_init(cur);
+        else beta_step(cur);
+        if ((t & (PF - 1)) == 0) renorm();
+        emit(cur, offa, g_row);
+        g_row -= row_stride;
+    }
+    for (int tb = full - PF; tb >= 0; tb -= PF) {
+#pragma unroll
+        for (int i = PF - 1; i >= 0; --i) {
+            cp_async_wait_pending<PF - 2>();
+            __syncwarp();
+            fetch_row(ring + ((i + 1) % PF) * ROW, next, hnext, tb + i - (PF - 1) >= 0);
+            next -= row_stride;
+            hnext -= KS * 32;
+            const double offa = offa_next;
+            if (i > 0 || tb > 0) offa_next = *--op;
+            const float* cur = ring + i * ROW;
+            if (i == PF - 1 && tb + PF == Tn) beta_init(cur);
+            else beta_step(cur);
+            if (i == 0) renorm();
+            emit(cur, offa, g_row);
+            g_row -= row_stride;
         }
     }
 }
@@ -525,14 +622,21 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const in
     const bool fused = ctc_fused(N);   // throughput form: alpha sweeps only here, beta + gradient in ctcb200_ctc_loss_bwd
     const int utt_per_block = fused ? WARPS_PER_BLOCK : WARPS_PER_BLOCK / 2;
     dim3 grid((N + utt_per_block - 1) / utt_per_block), block(WARPS_PER_BLOCK * 32);
-    size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * PF * C * sizeof(float);
+    const bool rs64 = C <= 64;   // ring row stride: compile-time 64 floats, or the run-time class count
+    size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * PF * (rs64 ? 64 : C) * sizeof(float);
     CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_fwd: class count %d too large for the row buffer", C);
     CtcWs w = carve(alpha_ws, T, N, ks);
-#define LAUNCH_A2(KS, AO)                                                                                           \
-    CTCB_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<KS, AO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ctc_sweep_kernel<KS, AO><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,       \
-                                                            target_lengths, w.hist_a, w.hist_b, w.off_a, w.off_b,   \
-                                                            w.nll_d, nll, T, N, C, blank)
+#define LAUNCH_A3(KS, AO, RS)                                                                                           \
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<KS, AO, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_sweep_kernel<KS, AO, RS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,       \
+                                                                target_lengths, w.hist_a, w.hist_b, w.off_a, w.off_b,   \
+                                                                w.nll_d, nll, T, N, C, blank)
+#define LAUNCH_A2(KS, AO)      \
+    if (rs64) {                \
+        LAUNCH_A3(KS, AO, 64); \
+    } else {                   \
+        LAUNCH_A3(KS, AO, 0);  \
+    }
 #define LAUNCH_A(KS)          \
     if (fused) {              \
         LAUNCH_A2(KS, true);  \
@@ -546,6 +650,7 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_fwd(const float* log_probs, const in
         case 8: LAUNCH_A(8); break;
         default: LAUNCH_A(16); break;
     }
+#undef LAUNCH_A3
 #undef LAUNCH_A2
 #undef LAUNCH_A
     CTCB_LAUNCH_CHECK();
@@ -565,15 +670,22 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_bwd(const float* log_probs, const in
     CTCB_REQUIRE((reinterpret_cast<uintptr_t>(alpha_ws) & 15) == 0, "ctc_loss_bwd: workspace must be 16-byte aligned");
     if (ctc_fused(N)) {
         CtcWs w = carve(const_cast<float*>(alpha_ws), T, N, ks);
-        const int C_pad = (C + 3) & ~3;
+        const bool rs64 = C <= 64;
+        const int C_pad = rs64 ? 64 : ((C + 3) & ~3);
         const size_t smem = static_cast<size_t>(WARPS_PER_BLOCK) * (static_cast<size_t>(PF) * (C_pad + ks * 32) + C_pad) * sizeof(float);
         CTCB_REQUIRE(smem <= 200 * 1024, "ctc_loss_bwd: class count %d too large for the row ring", C);
         dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
-#define LAUNCH_F(KS)                                                                                                      \
-    CTCB_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    ctc_beta_grad_kernel<KS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,             \
-                                                            target_lengths, w.hist_a, w.off_a, w.nll_d, grad_nll,         \
-                                                            grad_scale, grad, T, N, C, blank)
+#define LAUNCH_F2(KS, RS)                                                                                                     \
+    CTCB_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<KS, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    ctc_beta_grad_kernel<KS, RS><<<grid, block, smem, stream>>>(log_probs, targets, target_stride, input_lengths,             \
+                                                                target_lengths, w.hist_a, w.off_a, w.nll_d, grad_nll,         \
+                                                                grad_scale, grad, T, N, C, blank)
+#define LAUNCH_F(KS)          \
+    if (rs64) {               \
+        LAUNCH_F2(KS, 64);    \
+    } else {                  \
+        LAUNCH_F2(KS, 0);     \
+    }
         switch (ks) {
             case 1: LAUNCH_F(1); break;
             case 2: LAUNCH_F(2); break;
@@ -581,6 +693,7 @@ extern "C" CTCB200_API int ctcb200_ctc_loss_bwd(const float* log_probs, const in
             case 8: LAUNCH_F(8); break;
             default: LAUNCH_F(16); break;
         }
+#undef LAUNCH_F2
 #undef LAUNCH_F
         CTCB_LAUNCH_CHECK();
         return OK;

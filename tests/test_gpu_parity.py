@@ -78,7 +78,8 @@ def test_ctc_golden(golden_dir, ctc_form):
                                                            reduction="sum"))
 
 
-@pytest.mark.parametrize("T,N,C,S,seed", [(60, 5, 12, 9, 0), (33, 3, 40, 16, 1), (20, 4, 6, 70, 2), (800, 32, 62, 60, 3)])
+@pytest.mark.parametrize("T,N,C,S,seed", [(60, 5, 12, 9, 0), (33, 3, 40, 16, 1), (20, 4, 6, 70, 2), (800, 32, 62, 60, 3),
+                                          (45, 3, 150, 12, 4), (7, 6, 70, 3, 5), (8, 4, 10, 2, 6), (17, 2, 64, 5, 7)])
 def test_ctc_vs_oracle(T, N, C, S, seed, ctc_form):
     from ctc_pytorch_b200.loss import ctc_loss
     g = torch.Generator().manual_seed(seed)
