@@ -88,4 +88,6 @@ def build(force=False, verbose=False):
 if __name__ == "__main__":
     if "--tags" in sys.argv:   # debugging build: stalled mbarrier waits of the pipelined kernel report their role and step
         NVCC_FLAGS.append("-DCTCB200_WAIT_TAGS")
-    print(build(force="--force" in sys.argv or "--tags" in sys.argv, verbose="-v" in sys.argv))
+    if "--trace" in sys.argv:  # profiling build: in-kernel phase stamps of the recurrent kernels (CTCB200_LSTM_TRACE=1 at run time)
+        NVCC_FLAGS.append("-DCTCB200_TRACE")
+    print(build(force="--force" in sys.argv or "--tags" in sys.argv or "--trace" in sys.argv, verbose="-v" in sys.argv))

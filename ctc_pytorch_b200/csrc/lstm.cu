@@ -661,7 +661,11 @@ lstm_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmGx, FwdParams p) {
     __syncthreads();
     tc_fence_after();
     constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
+#ifdef CTCB200_TRACE   // phase stamps: compiled in only for the trace build (python -m ctc_pytorch_b200._build --trace)
 #define PTRACE(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[t * 16 + (k)] = clock64(); } while (0)
+#else
+#define PTRACE(k) do { } while (0)
+#endif
 
     if (warp >= 12) {
         // ---------------- copy warps: warp 12 + w ships this CTA's staged half block to peers 4w .. 4w+3 (issuing a bulk
@@ -1963,6 +1967,25 @@ int launch_clustered(Kern kern, dim3 grid, dim3 cluster, size_t smem, bool coope
     return OK;
 }
 
+// CTCB200_LSTM_TRACE=1 asks for the per-phase cycle breakdown. In the pipelined forward kernel the clock stamps cost ~14 % of its
+// run time even when switched off at run time (every warp role tests the pointer at several points of every half-step:
+// 1.16 -> 1.00 ms per cfg2 layer without them, tools/rec_ab_head.py), so that kernel carries them only with -DCTCB200_TRACE
+// (python -m ctc_pytorch_b200._build --trace). The BPTT kernel keeps its run-time switch: compiled without the stamps it came
+// out 3 % SLOWER (1.494 -> 1.535 ms; the stamps happen to keep ptxas from a worse schedule), measured in the same run.
+static bool trace_requested() { return getenv("CTCB200_LSTM_TRACE") != nullptr; }
+static void pipe_trace_needs_build(FwdParams& p) {
+#ifndef CTCB200_TRACE
+    if (p.trace) {
+        static bool told = false;
+        if (!told) fprintf(stderr, "ctcb200: tracing the pipelined forward kernel needs the trace build: python -m ctc_pytorch_b200._build --trace\n");
+        told = true;
+        p.trace = nullptr;
+    }
+#else
+    (void)p;
+#endif
+}
+
 // development aid (CTCB200_LSTM_TRACE=1): per-phase cycle breakdown of the forward recurrence on stderr
 struct FwdTraceDump {
     const FwdParams& p; cudaStream_t s; bool pipe;
@@ -2124,7 +2147,7 @@ int lstm_fwd_impl(const float* gx, const void* whh_packed, const void* whh_lo_pa
     }
     p.mma_split = mma_issuers(NB, H);
     p.groups = groups_total;
-    if (!plan_only && getenv("CTCB200_LSTM_TRACE")) {
+    if (!plan_only && trace_requested()) {
         static long long* dbuf = nullptr;
         if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
         if (T <= 4096) {
@@ -2134,6 +2157,7 @@ int lstm_fwd_impl(const float* gx, const void* whh_packed, const void* whh_lo_pa
     }
     FwdTraceDump trace_dump{p, stream, false};
     if (cl && !x3 && plain && NB == 16 && pipelined_fwd()) {
+        pipe_trace_needs_build(p);
         trace_dump.pipe = true;
         // software-pipelined kernel: two 8-column halves per group, dedicated tensor-core warps
         dim3 grid(H / 32, 2, groups_total), cluster(H / 32, 1, 1);
@@ -2286,7 +2310,7 @@ int lstm_bwd_impl(const float* dhout, const void* whhT_packed, const void* whhT_
     CTCB_REQUIRE(smem <= 227 * 1024, "lstm_bwd: shared memory %zu exceeds 227 KB (H=%d)", smem, H);
     p.mma_split = mma_issuers(NB, H);
     p.groups = groups_total;
-    if (!plan_only && getenv("CTCB200_LSTM_TRACE")) {
+    if (!plan_only && trace_requested()) {
         static long long* dbuf = nullptr;
         if (!dbuf) CTCB_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 4096));
         if (T <= 4096) {
