@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box visit = everything worth measuring (queueing for a box costs far more than running): the -m gpu suite, the
 # microbenchmarks and one bench line. Outputs under gpurun_out/ (merged back by gpurun).
-#   gpurun --timeout 1800 -- 'bash tools/gpu_job.sh [tests|bench|all]'
+#   gpurun --timeout 1800 -- 'bash tools/gpu_job.sh [tests|bench|all|final|fresh|ab_head|sanitize|ncu|ab|dist]'
 what=${1:-all}
 mkdir -p gpurun_out
 if [ "$what" = "tests" ] || [ "$what" = "all" ]; then
@@ -16,6 +16,28 @@ if [ "$what" = "bench" ] || [ "$what" = "all" ]; then
   python tools/ctc_sweep_bench.py gpurun_out/ctc_sweep.json > gpurun_out/ctc_sweep.log 2>&1; echo "ctc_sweep rc=$?"; tail -2 gpurun_out/ctc_sweep.log
   CTCB200_BEAM_TRACE=1 python tools/decode_bench.py 100 1 gpurun_out/decode.json > gpurun_out/decode.log 2>&1; echo "decode rc=$?"; tail -4 gpurun_out/decode.log
   python bench.py --steps 10 --warmup 3 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; echo "bench rc=$?"; head -c 1500 gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err
+fi
+if [ "$what" = "final" ]; then
+  # the round-end sequence the driver runs, each step in a FRESH process (lazy kernel loading and the stream-overlap probe only
+  # show up there): smoke, the whole -m gpu suite, one full bench line with per-step times, the ncu launch list
+  timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; grep -v "timed out" gpurun_out/smoke.log | tail -1 | cut -c1-300
+  rm -f gpurun_out/parity_report.jsonl
+  timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/tests_all.log 2>&1; echo "tests rc=$?"; grep -v "timed out" gpurun_out/tests_all.log | tail -3 | cut -c1-300
+  timeout 400 python bench.py --steps 10 --warmup 3 --per-step > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; echo "bench rc=$?"; head -c 600 gpurun_out/bench_cfg2.json; echo
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_r2.csv python tools/profile_step.py cfg2 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+fi
+if [ "$what" = "fresh" ]; then
+  # environments in which kernels of two streams do NOT overlap (the streamed input projection must fall back by itself):
+  # smoke() under Nsight Compute (what the driver's kernel census does) and with blocking launches
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/smoke_ncu.csv python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_ncu.log 2>&1; echo "smoke under ncu rc=$?"; grep -v "timed out" gpurun_out/smoke_ncu.log | tail -1 | cut -c1-300
+  CUDA_LAUNCH_BLOCKING=1 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_blocking.log 2>&1; echo "smoke CUDA_LAUNCH_BLOCKING rc=$?"
+  timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "streamed" > gpurun_out/tests_stream.log 2>&1; echo "streamed tests, fresh process rc=$?"; tail -2 gpurun_out/tests_stream.log | cut -c1-300
+fi
+if [ "$what" = "ab_head" ]; then
+  # recurrent kernels of the working tree against a saved build (cp ctc_pytorch_b200/libctcb200.so tools/_ab/libctcb200_head.so
+  # BEFORE rebuilding), alternating in one process
+  timeout -s KILL 100 python tools/rec_ab_head.py 800 32 512 > gpurun_out/rec_ab_head.json 2> gpurun_out/rec_ab_head.err; echo "rec rc=$?"; cat gpurun_out/rec_ab_head.json
+  timeout -s KILL 100 python tools/rec_ab_head.py 1200 64 640 > gpurun_out/rec_ab_head4.json 2> gpurun_out/rec_ab_head4.err; echo "rec4 rc=$?"; cat gpurun_out/rec_ab_head4.json
 fi
 if [ "$what" = "sanitize" ]; then
   # memcheck: the DSMEM bulk copies (cp.async.bulk.shared::cluster with a mapa address) are reported as "not located in remote
