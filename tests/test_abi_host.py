@@ -193,3 +193,25 @@ def test_arpa_loader_tolerates_spaces_and_higher_orders(golden_dir, tmp_path):
     assert lm2.unigram == lm.unigram and lm2.bigram == lm.bigram
     assert lm2.higher[3] == {"a b c": (-0.5, 0.0)}
     assert lm2.get_bi_prob("", "a") == lm.get_bi_prob("", "a") and lm2.get_bi_prob("f", "") == lm.get_bi_prob("f", "")
+
+
+def test_readme_switches_exist_in_the_source():
+    """Every CTCB200_* environment switch the README documents is read somewhere in the product or bench source, and the job
+    script the README points at parses."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    readme = open(os.path.join(root, "README.md")).read()
+    names = set(re.findall(r"`(CTCB200_[A-Z0-9_]+)", readme))
+    assert len(names) >= 10
+    src = ""
+    for d, _, files in os.walk(os.path.join(root, "ctc_pytorch_b200")):
+        if os.path.basename(d) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src += open(os.path.join(d, f), errors="ignore").read()
+    src += open(os.path.join(root, "bench.py")).read()
+    missing = sorted(n for n in names if n not in src)
+    assert not missing, "documented but never read: %s" % missing
+    assert subprocess.run(["bash", "-n", os.path.join(root, "tools", "gpu_job.sh")]).returncode == 0
